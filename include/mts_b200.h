@@ -1,0 +1,206 @@
+/*
+ * mts_b200.h — C ABI of libmtsb200.so, the sm_100a kernel stack behind MedTsLLM's hot path.
+ *
+ * This is the drop-in boundary.  The reference (flixpar/med-ts-llm) is pure Python
+ * and reaches its "kernels" through PyTorch/HuggingFace library calls; every entry point below
+ * replaces one of those call sites and cites it as   ref: <file>:<line>   (paths relative to the
+ * reference tree; `HF:` = site-packages/transformers 5.5.0, the reference's third-party backbone).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its
+ *     name starts with `h_`.  The library owns no tensor memory: callers allocate everything.
+ *   - All launches are asynchronous on the cudaStream_t passed as `mts_stream_t`; no entry point
+ *     synchronises or allocates device memory.  (Host-side caches: TMA descriptors only.)
+ *   - Return value: MTS_OK (0) or an mts_status error code; `mts_last_error()` returns a
+ *     thread-local human-readable message for the last failure on the calling thread.
+ *   - Row-major everywhere.  "ld*" strides and batch strides are in ELEMENTS, not bytes.
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t).  Residual stream and statistics are fp32.
+ *   - There is NO CPU fallback.  On a machine without an sm_100 GPU every compute entry point
+ *     returns MTS_ERR_CUDA.
+ */
+#ifndef MTS_B200_H_
+#define MTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTS_ABI_VERSION 1
+
+typedef void* mts_stream_t; /* cudaStream_t */
+
+typedef enum mts_status {
+  MTS_OK = 0,
+  MTS_ERR_INVALID_ARG = 1,
+  MTS_ERR_CUDA = 2,
+  MTS_ERR_UNSUPPORTED = 3
+} mts_status;
+
+typedef enum mts_dtype { MTS_BF16 = 0, MTS_F32 = 1 } mts_dtype;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Library                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+
+/* ABI version (MTS_ABI_VERSION of the build). */
+int mts_version(void);
+/* Thread-local message for the last non-OK status returned on this thread ("" if none). */
+const char* mts_last_error(void);
+/* Number of kernels this library has launched since load (process-wide; bench `gpu_launches`). */
+int64_t mts_launch_count(void);
+/* Drop the host-side TMA descriptor cache. */
+int mts_clear_caches(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1+K2  RevIN + patching + TokenEmbedding (fused front end)                                  */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * ref: models/layers/RevIN.py:37-56 (statistics + normalise), models/layers/embed.py:155-163
+ *      (ReplicationPad1d), :186-197 (PatchEmbedding.forward: unfold(P,S)), :29-46 (TokenEmbedding:
+ *      Conv1d(P->d_model, k=3, circular over the patch axis, no bias)), and the `concat` reshape at
+ *      models/medtsllm.py:276-279.
+ *
+ *   x       [B,T,C] fp32
+ *   w_conv  [d_model, P, 3] fp32     (patch_embedding.value_embedding.tokenConv.weight)
+ *   mean, stdev  [B,C] fp32 out      (RevIN statistics; stdev = sqrt(var_biased + eps))
+ *   out     bf16 and/or fp32, either pointer may be NULL:
+ *             concat_layout = 1 :  [B, N, C*d_model]   (feature-major inside a token)
+ *             concat_layout = 0 :  [B*C, N, d_model]
+ *   N = (T + S - P)/S + 1 patches; patch n covers padded samples n*S .. n*S+P-1, where the padded
+ *   series repeats sample T-1 S times at the end.
+ */
+int mts_revin_patch_embed(const float* x, const float* w_conv, float* mean, float* stdev,
+                          uint16_t* out_bf16, float* out_f32, int B, int T, int C, int P, int S,
+                          int d_model, int concat_layout, float eps, mts_stream_t stream);
+
+/*
+ * Pure index work of the same path: gathers the (un-normalised) patches so that the patch index
+ * map can be checked bit-exactly against `unfold` (ref: models/layers/embed.py:188-190).
+ *   patches [B*C, N, P] fp32 out;  patches[(b*C+c), n, p] = x[b, min(n*S+p, T-1), c]
+ */
+int mts_patch_gather(const float* x, float* patches, int B, int T, int C, int P, int S,
+                     mts_stream_t stream);
+
+/*
+ * Backward of the front end w.r.t. the conv weight (the only trainable tensor in it; the RevIN
+ * statistics are detached in the reference, RevIN.py:42-43).
+ *   dout  [same layout as out] fp32,  dw_conv [d_model,P,3] fp32 (overwritten)
+ */
+int mts_revin_patch_embed_bwd(const float* x, const float* mean, const float* stdev,
+                              const float* dout, float* dw_conv, int B, int T, int C, int P, int S,
+                              int d_model, int concat_layout, mts_stream_t stream);
+
+/* RevIN "denorm": y[b,t,c] = y[b,t,c]*stdev[b,c] + mean[b,c]   (ref: RevIN.py:58-69) */
+int mts_revin_denorm(float* y, const float* mean, const float* stdev, int B, int T, int C,
+                     mts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K3/K4/K7/K9/K10/K11/K12/K13  tcgen05 GEMM with fused epilogues                              */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * D[b] = epilogue( alpha * A[b] (m x k) * B[b]^T (k x n) + bias )       ("NT": both K-major)
+ *
+ * Replaces every nn.Linear / Conv1D / einsum contraction on the path:
+ *   ref: models/medtsllm.py:281 (mapping_layer), :566-591 (ReprogrammingLayer projections and the
+ *        two einsums), :358 (embedding_downsample_layer), :541-552 (FlattenHead.linear);
+ *        HF:models/llama/modeling_llama.py:182-184,262-264,288; HF:models/gpt2/modeling_gpt2.py:185,
+ *        223,238-243 + HF:pytorch_utils.py:119-123 (Conv1D = addmm).
+ *
+ * A, B: bf16.  TMA-staged 128B-swizzled shared-memory tiles (BLOCK_M=128, BLOCK_K=64, BLOCK_N in
+ * {64,128,256}), tcgen05.mma kind::f16 into fp32 TMEM accumulators (double-buffered), persistent
+ * over min(tiles, SMs) CTAs.  Requirements: lda, ldb multiples of 8; a, b 16-byte aligned;
+ * k >= 1; batch strides multiples of 8 (or 0 = the operand is shared by all batches).
+ */
+typedef enum mts_epilogue {
+  MTS_EPI_STORE = 0,     /* D = v                      (D bf16 or fp32)                          */
+  MTS_EPI_RESID_ADD = 1, /* D += v                     (D fp32, read-modify-write: residual)     */
+  MTS_EPI_GELU_NEW = 2,  /* D = gelu_new(v)            (D bf16; HF:activations.py:59-66)         */
+  MTS_EPI_SWIGLU = 3     /* D[:, j] = silu(v_gate[j]) * v_up[j]   (D bf16, n/2 columns).  B rows  */
+                         /* must be packed by mts_pack_gate_up: blocks of 128 gate rows followed  */
+                         /* by the matching 128 up rows (HF:models/llama/modeling_llama.py:182-184) */
+} mts_epilogue;
+
+typedef enum mts_bias_axis { MTS_BIAS_NONE = 0, MTS_BIAS_N = 1, MTS_BIAS_M = 2 } mts_bias_axis;
+
+typedef struct mts_gemm_args {
+  const void* a;     /* bf16 [batch][m][k]                                                        */
+  const void* b;     /* bf16 [batch][n][k]                                                        */
+  void* d;           /* [batch][m][n'] (n' = n, or n/2 for SWIGLU); or [batch][n][m] if d_transposed */
+  const float* bias; /* fp32 [n] (MTS_BIAS_N) or [m] (MTS_BIAS_M) or NULL                         */
+  int64_t lda, ldb, ldd;
+  int64_t a_batch_stride, b_batch_stride, d_batch_stride;
+  int32_t m, n, k, batch;
+  int32_t d_dtype;      /* mts_dtype */
+  int32_t epilogue;     /* mts_epilogue */
+  int32_t bias_axis;    /* mts_bias_axis */
+  int32_t d_transposed; /* STORE only: element (row i, col j) goes to d[j*ldd + i]               */
+  int32_t block_n;      /* 0 = choose; else 64 / 128 / 256                                        */
+  float alpha;
+} mts_gemm_args;
+
+int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);
+
+/* Pack [gate; up] weights for MTS_EPI_SWIGLU: out[(j/128)*256 + (j%128)] = gate[j],
+ * out[(j/128)*256 + 128 + (j%128)] = up[j]; rows beyond I in the last block are zero.
+ *   gate, up: bf16 [I, K];  out: bf16 [2*ceil(I/128)*128, K] */
+int mts_pack_gate_up(const uint16_t* gate, const uint16_t* up, uint16_t* out, int I, int K,
+                     mts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Element-wise / row kernels of the backbone                                                  */
+/* ------------------------------------------------------------------------------------------ */
+
+/* fp32 -> bf16 cast (weights when the trainer updates them; activations entering a GEMM). */
+int mts_cast_f32_bf16(const float* in, uint16_t* out, int64_t n, mts_stream_t stream);
+int mts_cast_bf16_f32(const uint16_t* in, float* out, int64_t n, mts_stream_t stream);
+/* out[c, r] = in[r, c] with cast; in fp32 [rows, cols] -> out bf16 [cols, rows] */
+int mts_transpose_f32_bf16(const float* in, uint16_t* out, int rows, int cols, mts_stream_t stream);
+int mts_transpose_bf16(const uint16_t* in, uint16_t* out, int rows, int cols, mts_stream_t stream);
+
+/* K6  RMSNorm (ref: HF:models/llama/modeling_llama.py:53-67): y = w * x * rsqrt(mean(x^2)+eps)
+ *   x fp32 [rows, ldx>=D] (the residual stream), w fp32 [D], y bf16 [rows, D] and/or y_f32. */
+int mts_rmsnorm(const float* x, int64_t ldx, const float* w, uint16_t* y_bf16, float* y_f32,
+                int rows, int D, float eps, mts_stream_t stream);
+/* K6  LayerNorm (ref: HF:models/gpt2/modeling_gpt2.py:252-254,628; torch.nn.LayerNorm) */
+int mts_layernorm(const float* x, int64_t ldx, const float* w, const float* b, uint16_t* y_bf16,
+                  float* y_f32, int rows, int D, float eps, mts_stream_t stream);
+
+/* K8  causal self-attention, eager semantics (ref: HF:models/llama/modeling_llama.py:199-221 with
+ *     RoPE :124-168; HF:models/gpt2/modeling_gpt2.py:54-72): softmax(q k^T * scale + causal) v,
+ *     no padding mask (the reference never passes one, models/medtsllm.py:350).
+ *   qkv  bf16 [Bp*L, 3*H*hd]   columns = [q heads | k heads | v heads]
+ *   rope_cos, rope_sin fp32 [L, hd/2] or NULL (GPT-2); rotate-half convention
+ *   out  bf16 [Bp*L, H*hd]
+ *   lse  fp32 [Bp, H, L] or NULL: log-sum-exp of the scaled scores (saved for backward)
+ *   hd in {64, 128}. */
+int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                    uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
+                    mts_stream_t stream);
+
+/* row softmax with scale: p = softmax(scale * s) over the last axis.
+ *   s fp32 [rows, n], p bf16 [rows, n]   (ref: models/medtsllm.py:587, reprogramming scores) */
+int mts_softmax_rows(const float* s, uint16_t* p, int64_t rows, int n, float scale,
+                     mts_stream_t stream);
+
+/* K5  prompt gather + left padding + (GPT-2) position embedding, building the backbone input
+ *     (ref: models/medtsllm.py:299-311 encode_text/pad_sequence, :331-337, :349 cat;
+ *      HF:models/gpt2/modeling_gpt2.py:584-585 wpe add).
+ *   ids  int32 [B, Lp]  (already left-padded with the pad id by the host)
+ *   emb  fp32 [V, D] input-embedding table
+ *   wpe  fp32 [>=L, D] or NULL
+ *   x    fp32 [B*rep, L, D] out: rows [0,Lp) = emb[ids] (+wpe), rows [Lp,L) = 0 (+wpe);
+ *        sample b is written to rows b*rep .. b*rep+rep-1 (repeat_interleave, :343-344). */
+int mts_prompt_gather(const int32_t* ids, const float* emb, const float* wpe, float* x, int B,
+                      int rep, int Lp, int L, int D, mts_stream_t stream);
+
+/* y = silu(g) * u on bf16, g/u being the two halves of a [rows, 2*I] (ld = ldgu) buffer laid out
+ * [g | u];  (training path keeps g,u for the backward; ref HF llama :182-184) */
+int mts_swiglu(const uint16_t* gu, int64_t ldgu, uint16_t* y, int64_t rows, int I,
+               mts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTS_B200_H_ */

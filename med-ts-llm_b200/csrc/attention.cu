@@ -1,0 +1,270 @@
+// attention.cu — K8: causal self-attention of the frozen backbone with eager semantics
+// (ref: HF:models/llama/modeling_llama.py:199-221 eager_attention_forward, RoPE :124-168;
+//  HF:models/gpt2/modeling_gpt2.py:54-72).  No padding mask: the reference never passes one
+// (models/medtsllm.py:350), so left-pad tokens are attended to like any other.
+//
+// Sequence lengths on this path are short (prompt + patches, L <= ~260), so attention is < 1 % of
+// the FLOPs.  Per the design brief it is a shared-memory-tiled kernel with warp-level reductions:
+// 64-query x 64-key tiles, Q/K/V staged in padded smem (RoPE applied while staging, in fp32),
+// S = QK^T and O = PV on the warp-level tensor path (mma.sync m16n8k16 bf16 -> fp32), online
+// softmax in fp32 registers with quad shuffles.  The big GEMMs are the tcgen05 kernels.
+//
+// Algorithmic work: 4*Bp*H*L*L*hd FLOP (dense; the causal half is skipped in practice).
+#include "mts_internal.h"
+#include "ptx.cuh"
+
+namespace mts {
+
+constexpr int kAttnBlockQ = 64;
+constexpr int kAttnBlockKV = 64;
+constexpr int kAttnThreads = 128;
+
+// Stage `rows` x HD bf16 from global (row stride ld elements) into padded smem [64][HD+8],
+// optionally applying rotate-half RoPE with position = global row index.  Rows >= L are zeroed.
+template <int HD, bool kRope>
+__device__ __forceinline__ void stage_tile(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src,
+                                           int64_t ld, int row0, int L,
+                                           const float* __restrict__ cosb,
+                                           const float* __restrict__ sinb) {
+  constexpr int kPitch = HD + 8;
+  constexpr int kHalf = HD / 2;
+  if (kRope) {
+    constexpr int kVecPerRow = kHalf / 8;  // each item handles columns [j, j+8) and [j+HD/2, ...)
+    for (int i = threadIdx.x; i < 64 * kVecPerRow; i += kAttnThreads) {
+      const int r = i / kVecPerRow, j = (i - r * kVecPerRow) * 8;
+      const int row = row0 + r;
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+      if (row < L) {
+        const uint4 a = *reinterpret_cast<const uint4*>(src + (int64_t)row * ld + j);
+        const uint4 b = *reinterpret_cast<const uint4*>(src + (int64_t)row * ld + kHalf + j);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        const float* cr = cosb + (int64_t)row * kHalf + j;
+        const float* sr = sinb + (int64_t)row * kHalf + j;
+        uint32_t lo_w[4], hi_w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float x1a = bf16_lo(aw[q]), x1b = bf16_hi(aw[q]);
+          const float x2a = bf16_lo(bw[q]), x2b = bf16_hi(bw[q]);
+          const float ca = cr[2 * q], cb = cr[2 * q + 1], sa = sr[2 * q], sb = sr[2 * q + 1];
+          lo_w[q] = pack_bf16(x1a * ca - x2a * sa, x1b * cb - x2b * sb);
+          hi_w[q] = pack_bf16(x2a * ca + x1a * sa, x2b * cb + x1b * sb);
+        }
+        lo = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+        hi = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+      }
+      *reinterpret_cast<uint4*>(dst + r * kPitch + j) = lo;
+      *reinterpret_cast<uint4*>(dst + r * kPitch + kHalf + j) = hi;
+    }
+  } else {
+    constexpr int kVecPerRow = HD / 8;
+    for (int i = threadIdx.x; i < 64 * kVecPerRow; i += kAttnThreads) {
+      const int r = i / kVecPerRow, j = (i - r * kVecPerRow) * 8;
+      const int row = row0 + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < L) v = *reinterpret_cast<const uint4*>(src + (int64_t)row * ld + j);
+      *reinterpret_cast<uint4*>(dst + r * kPitch + j) = v;
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_causal_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                       const float* __restrict__ rope_sin, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ lse, int L, int H, float scale_log2e) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Ks = Qs + 64 * kPitch;
+  __nv_bfloat16* Vs = Ks + 64 * kPitch;
+
+  const int n_qblk = (L + kAttnBlockQ - 1) / kAttnBlockQ;
+  const int bh = blockIdx.x / n_qblk;
+  const int q0 = (blockIdx.x - bh * n_qblk) * kAttnBlockQ;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const bool rope = rope_cos != nullptr;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+
+  if (rope) stage_tile<HD, true>(Qs, qbase, ld, q0, L, rope_cos, rope_sin);
+  else      stage_tile<HD, false>(Qs, qbase, ld, q0, L, nullptr, nullptr);
+  __syncthreads();
+
+  // Q fragments stay in registers for the whole kernel
+  uint32_t qf[HD / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    const uint32_t addr = smem_u32(Qs + (warp * 16 + (lane & 15)) * kPitch + ks * 16 + (lane >> 4) * 8);
+    ldmatrix_x4(addr, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  }
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+  float m_run[2] = {-INFINITY, -INFINITY};  // running max (log2 units), rows g and g+8
+  float l_run[2] = {0.0f, 0.0f};            // per-thread partial row sums
+
+  const int row_a = q0 + warp * 16 + g;  // this thread's two query rows
+  const int row_b = row_a + 8;
+  const int kv_end = min(L, q0 + kAttnBlockQ);  // causal: keys <= last query of the tile
+
+  for (int j0 = 0; j0 < kv_end; j0 += kAttnBlockKV) {
+    __syncthreads();  // previous K/V tile fully consumed
+    if (rope) stage_tile<HD, true>(Ks, kbase, ld, j0, L, rope_cos, rope_sin);
+    else      stage_tile<HD, false>(Ks, kbase, ld, j0, L, nullptr, nullptr);
+    stage_tile<HD, false>(Vs, vbase, ld, j0, L, nullptr, nullptr);
+    __syncthreads();
+
+    // S = Q K^T  (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        const int id = lane >> 3;
+        const uint32_t addr = smem_u32(Ks + (np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch +
+                                       ks * 16 + (id & 1) * 8);
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4(addr, r0, r1, r2, r3);
+        mma_bf16_16816(s[2 * np], qf[ks], r0, r1);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], r2, r3);
+      }
+    }
+
+    // scale, causal mask, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+        const int row = (e < 2) ? row_a : row_b;
+        float v = s[nt][e] * scale_log2e;
+        if (col > row || col >= L) v = -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float alpha[2], m_new[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      m_new[r] = fmaxf(m_run[r], mx[r]);
+      const float m_safe = (m_new[r] == -INFINITY) ? 0.0f : m_new[r];
+      alpha[r] = exp2f(m_run[r] - m_safe);  // m_run = -inf on the first tile -> 0
+      m_run[r] = m_new[r];
+      m_new[r] = m_safe;
+      l_run[r] *= alpha[r];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[nt][e] - m_new[e >> 1]);
+        s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+    }
+
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < HD / 16; ++np) {
+        const int id = lane >> 3;
+        const uint32_t addr = smem_u32(Vs + (kk * 16 + (id & 1) * 8 + (lane & 7)) * kPitch +
+                                       np * 16 + (id >> 1) * 8);
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4_trans(addr, r0, r1, r2, r3);
+        mma_bf16_16816(o[2 * np], pa, r0, r1);
+        mma_bf16_16816(o[2 * np + 1], pa, r2, r3);
+      }
+    }
+  }
+
+  // finalise: reduce the row sums over the quad, normalise, store
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv_a = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f;
+  const float inv_b = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
+  __nv_bfloat16* obase = out + (int64_t)b * L * D + (int64_t)h * HD;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt) {
+    const int col = nt * 8 + tq * 2;
+    if (row_a < L)
+      *reinterpret_cast<uint32_t*>(obase + (int64_t)row_a * D + col) =
+          pack_bf16(o[nt][0] * inv_a, o[nt][1] * inv_a);
+    if (row_b < L)
+      *reinterpret_cast<uint32_t*>(obase + (int64_t)row_b * D + col) =
+          pack_bf16(o[nt][2] * inv_b, o[nt][3] * inv_b);
+  }
+  if (lse && tq == 0) {
+    // natural-log LSE of the scaled scores: ln(sum exp(s*scale)) = (m + log2(l)) * ln 2
+    if (row_a < L) lse[(int64_t)bh * L + row_a] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
+    if (row_b < L) lse[(int64_t)bh * L + row_b] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
+  }
+}
+
+template <int HD>
+static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, uint16_t* out,
+                       float* lse, int Bp, int L, int H, float scale, cudaStream_t stream) {
+  constexpr int kSmem = 3 * 64 * (HD + 8) * 2;
+  auto kern = attn_causal_fwd_kernel<HD>;
+  static bool attr_done = false;
+  if (!attr_done && kSmem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn)", e);
+    attr_done = true;
+  }
+  const int64_t grid_l = (int64_t)((L + kAttnBlockQ - 1) / kAttnBlockQ) * Bp * H;
+  if (grid_l > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal: grid too large");
+  const int grid = (int)grid_l;
+  kern<<<grid, kAttnThreads, kSmem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs,
+                                               reinterpret_cast<__nv_bfloat16*>(out), lse, L, H,
+                                               scale * 1.4426950408889634f);
+  count_launch();
+  return check_launch("attn_causal_fwd_kernel");
+}
+
+}  // namespace mts
+
+using namespace mts;
+
+extern "C" int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                               uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
+                               mts_stream_t s) {
+  if (!qkv || !out || Bp <= 0 || L <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal: bad args");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal: rope_cos and rope_sin go together");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (rope_cos && ((reinterpret_cast<uintptr_t>(rope_cos) & 3) || (reinterpret_cast<uintptr_t>(rope_sin) & 3))))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal: misaligned pointer");
+  switch (hd) {
+    case 64: return launch_attn<64>(qkv, rope_cos, rope_sin, out, lse, Bp, L, H, scale, (cudaStream_t)s);
+    case 128: return launch_attn<128>(qkv, rope_cos, rope_sin, out, lse, Bp, L, H, scale, (cudaStream_t)s);
+    default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal: head dim %d (supported: 64, 128)", hd);
+  }
+}

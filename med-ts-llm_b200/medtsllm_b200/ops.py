@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, libmtsb200 does the work.
+
+Every function here launches hand-written sm_100a kernels through ctypes on the current CUDA stream.
+Nothing falls back to torch arithmetic: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (BIAS_M, BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_STORE, EPI_SWIGLU,
+                   MTS_BF16, MTS_F32, GemmArgs, MtsError)
+
+__all__ = [
+    "gemm", "linear_bf16", "revin_patch_embed", "patch_gather", "revin_patch_embed_bwd",
+    "revin_denorm", "rmsnorm", "layernorm", "attn_causal", "softmax_rows", "prompt_gather",
+    "cast_bf16", "cast_f32", "transpose_to_bf16", "pack_gate_up", "swiglu",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MtsError(f"{name} must be a CUDA tensor (libmtsb200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise MtsError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
+         bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
+         block_n=0, a_off=0, b_off=0, d_off=0):
+    """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
+    _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
+    if d.dtype not in (torch.bfloat16, torch.float32):
+        raise MtsError("d must be bf16 or fp32")
+    args = GemmArgs()
+    args.a = a.data_ptr() + 2 * a_off
+    args.b = b.data_ptr() + 2 * b_off
+    args.d = d.data_ptr() + d.element_size() * d_off
+    args.bias = _ptr(bias)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    args.lda = k if lda is None else lda
+    args.ldb = k if ldb is None else ldb
+    n_store = n // 2 if epilogue == EPI_SWIGLU else n
+    args.ldd = (m if d_transposed else n_store) if ldd is None else ldd
+    args.a_batch_stride, args.b_batch_stride, args.d_batch_stride = a_bs, b_bs, d_bs
+    args.m, args.n, args.k, args.batch = m, n, k, batch
+    args.d_dtype = MTS_F32 if d.dtype == torch.float32 else MTS_BF16
+    args.epilogue = epilogue
+    args.bias_axis = bias_axis
+    args.d_transposed = 1 if d_transposed else 0
+    args.block_n = block_n
+    args.alpha = alpha
+    _lib.call("mts_gemm", C.byref(args), _stream())
+    return d
+
+
+def linear_bf16(x, w, bias=None, *, out=None, out_dtype=torch.bfloat16, epilogue=EPI_STORE,
+                block_n=0):
+    """y = x @ w^T (+ bias): x bf16 [..., K] contiguous, w bf16 [N, K] contiguous."""
+    _chk(x, torch.bfloat16, "x"); _chk(w, torch.bfloat16, "w")
+    if not x.is_contiguous() or not w.is_contiguous():
+        raise MtsError("linear_bf16 needs contiguous operands")
+    K = x.shape[-1]
+    N = w.shape[0]
+    M = x.numel() // K
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n_out, device=x.device, dtype=out_dtype)
+    gemm(x, w, out, m=M, n=N, k=K, bias=bias, bias_axis=BIAS_N if bias is not None else BIAS_NONE,
+         epilogue=epilogue, block_n=block_n)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# front end
+# ------------------------------------------------------------------------------------------------
+def n_patches(T, P, S):
+    return (T + S - P) // S + 1
+
+
+def revin_patch_embed(x, w_conv, P, S, *, concat, eps=1e-5, want_bf16=True, want_f32=False):
+    """Fused RevIN-norm + pad + unfold + TokenEmbedding conv.  Returns (out_bf16, out_f32, mean, std)."""
+    _chk(x, torch.float32, "x"); _chk(w_conv, torch.float32, "w_conv")
+    x = x.contiguous(); w_conv = w_conv.contiguous()
+    B, T, Cc = x.shape
+    dm = w_conv.shape[0]
+    N = n_patches(T, P, S)
+    shape = (B, N, Cc * dm) if concat else (B * Cc, N, dm)
+    mean = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    std = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    ob = torch.empty(shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    of = torch.empty(shape, device=x.device, dtype=torch.float32) if want_f32 else None
+    _lib.call("mts_revin_patch_embed", x.data_ptr(), w_conv.data_ptr(), mean.data_ptr(),
+              std.data_ptr(), _ptr(ob), _ptr(of), B, T, Cc, P, S, dm, 1 if concat else 0, eps,
+              _stream())
+    return ob, of, mean, std
+
+
+def patch_gather(x, P, S):
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    B, T, Cc = x.shape
+    N = n_patches(T, P, S)
+    out = torch.empty(B * Cc, N, P, device=x.device, dtype=torch.float32)
+    _lib.call("mts_patch_gather", x.data_ptr(), out.data_ptr(), B, T, Cc, P, S, _stream())
+    return out
+
+
+def revin_patch_embed_bwd(x, mean, std, dout, P, S, dm, *, concat):
+    _chk(x, torch.float32, "x"); _chk(dout, torch.float32, "dout")
+    x = x.contiguous(); dout = dout.contiguous()
+    B, T, Cc = x.shape
+    dw = torch.empty(dm, P, 3, device=x.device, dtype=torch.float32)
+    _lib.call("mts_revin_patch_embed_bwd", x.data_ptr(), mean.data_ptr(), std.data_ptr(),
+              dout.data_ptr(), dw.data_ptr(), B, T, Cc, P, S, dm, 1 if concat else 0, _stream())
+    return dw
+
+
+def revin_denorm(y, mean, std):
+    """In-place y[b,t,c] = y*std[b,c] + mean[b,c]."""
+    _chk(y, torch.float32, "y")
+    if not y.is_contiguous():
+        raise MtsError("revin_denorm needs a contiguous tensor")
+    B, T, Cc = y.shape
+    _lib.call("mts_revin_denorm", y.data_ptr(), mean.data_ptr(), std.data_ptr(), B, T, Cc, _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------
+def rmsnorm(x, w, eps, *, out_dtype=torch.bfloat16, out=None):
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    if not x.is_contiguous():
+        raise MtsError("rmsnorm needs contiguous input")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    yb, yf = (out.data_ptr(), 0) if out.dtype == torch.bfloat16 else (0, out.data_ptr())
+    _lib.call("mts_rmsnorm", x.data_ptr(), D, w.data_ptr(), yb, yf, rows, D, eps, _stream())
+    return out
+
+
+def layernorm(x, w, b, eps, *, out_dtype=torch.bfloat16, out=None):
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    if not x.is_contiguous():
+        raise MtsError("layernorm needs contiguous input")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    yb, yf = (out.data_ptr(), 0) if out.dtype == torch.bfloat16 else (0, out.data_ptr())
+    _lib.call("mts_layernorm", x.data_ptr(), D, w.data_ptr(), b.data_ptr(), yb, yf, rows, D, eps,
+              _stream())
+    return out
+
+
+def attn_causal(qkv, Bp, L, H, hd, *, rope=None, scale=None, want_lse=False, out=None):
+    """qkv bf16 [Bp*L, 3*H*hd] -> out bf16 [Bp*L, H*hd]; rope = (cos, sin) fp32 [L, hd/2] or None."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    if not qkv.is_contiguous():
+        raise MtsError("attn_causal needs contiguous qkv")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty(Bp * L, H * hd, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(Bp, H, L, device=qkv.device, dtype=torch.float32) if want_lse else None
+    cos = sin = None
+    if rope is not None:
+        cos, sin = rope
+        _chk(cos, torch.float32, "rope cos"); _chk(sin, torch.float32, "rope sin")
+        if cos.shape[0] < L or cos.shape[1] != hd // 2 or not cos.is_contiguous() or not sin.is_contiguous():
+            raise MtsError("rope tables must be contiguous [>=L, hd/2]")
+    _lib.call("mts_attn_causal", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), _ptr(lse),
+              Bp, L, H, hd, scale, _stream())
+    return (out, lse) if want_lse else out
+
+
+def softmax_rows(s, scale, out=None):
+    _chk(s, torch.float32, "s")
+    if not s.is_contiguous():
+        raise MtsError("softmax_rows needs contiguous input")
+    n = s.shape[-1]
+    rows = s.numel() // n
+    if out is None:
+        out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    _lib.call("mts_softmax_rows", s.data_ptr(), out.data_ptr(), rows, n, scale, _stream())
+    return out
+
+
+def prompt_gather(ids, emb, wpe, x, *, rep, Lp, L):
+    """Fills x fp32 [B*rep, L, D]: rows <Lp from emb[ids] (+wpe), rows >=Lp zero (+wpe)."""
+    _chk(emb, torch.float32, "emb"); _chk(x, torch.float32, "x")
+    D = emb.shape[1]
+    B = x.shape[0] // rep
+    if Lp > 0:
+        _chk(ids, torch.int32, "ids")
+        if not ids.is_contiguous() or ids.shape != (B, Lp):
+            raise MtsError("ids must be contiguous int32 [B, Lp]")
+    if not x.is_contiguous() or not emb.is_contiguous():
+        raise MtsError("prompt_gather needs contiguous tensors")
+    _lib.call("mts_prompt_gather", _ptr(ids) if Lp > 0 else 0, emb.data_ptr(), _ptr(wpe),
+              x.data_ptr(), B, rep, Lp, L, D, _stream())
+    return x
+
+
+def cast_bf16(x, out=None):
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("mts_cast_f32_bf16", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def cast_f32(x, out=None):
+    _chk(x, torch.bfloat16, "x")
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _lib.call("mts_cast_bf16_f32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def transpose_to_bf16(x):
+    """[rows, cols] fp32 or bf16 -> [cols, rows] bf16."""
+    _chk(x, None, "x")
+    x = x.contiguous()
+    rows, cols = x.shape
+    out = torch.empty(cols, rows, device=x.device, dtype=torch.bfloat16)
+    fn = "mts_transpose_f32_bf16" if x.dtype == torch.float32 else "mts_transpose_bf16"
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise MtsError("transpose_to_bf16: fp32 or bf16 input")
+    _lib.call(fn, x.data_ptr(), out.data_ptr(), rows, cols, _stream())
+    return out
+
+
+def pack_gate_up(gate, up):
+    _chk(gate, torch.bfloat16, "gate"); _chk(up, torch.bfloat16, "up")
+    gate = gate.contiguous(); up = up.contiguous()
+    I, K = gate.shape
+    out = torch.empty(((I + 127) // 128) * 256, K, device=gate.device, dtype=torch.bfloat16)
+    _lib.call("mts_pack_gate_up", gate.data_ptr(), up.data_ptr(), out.data_ptr(), I, K, _stream())
+    return out
+
+
+def swiglu(gu, I):
+    _chk(gu, torch.bfloat16, "gu")
+    rows = gu.numel() // gu.shape[-1]
+    out = torch.empty(*gu.shape[:-1], I, device=gu.device, dtype=torch.bfloat16)
+    _lib.call("mts_swiglu", gu.data_ptr(), gu.shape[-1], out.data_ptr(), rows, I, _stream())
+    return out
