@@ -1,0 +1,269 @@
+"""TEST INFRASTRUCTURE — CPU restatement (plain PyTorch fp32) of the reference's MedTsLLM hot path.
+
+NOT part of the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this module, and only as the checker / the timed CPU baseline.
+The product path (medtsllm_b200) never routes through it.
+
+Every function restates one piece of flixpar/med-ts-llm (paths relative to the reference tree) or of
+its third-party backbone (HF: = transformers 5.5.0, the version installed in this image; the
+reference's requirements.txt:13 says `transformers >= 4.39.0`, unpinned).
+
+Parity status: PINNED.  tests/test_oracle.py checks this restatement against (a) golden stage
+tensors produced by running the unmodified reference in the build container
+(oracle/make_golden.py -> tests/golden/*), and (b) HuggingFace's own LlamaModel / GPT2Model executed
+at test time (transformers is in the image on both machines).  The reference itself has no tests or
+golden vectors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------- RevIN (K1)
+def revin_stats(x: torch.Tensor, eps: float = 1e-5):
+    """models/layers/RevIN.py:37-43 — mean and sqrt(biased var + eps) over time, x [B,T,C]."""
+    mean = x.mean(dim=1, keepdim=True)
+    stdev = torch.sqrt(x.var(dim=1, keepdim=True, unbiased=False) + eps)
+    return mean, stdev
+
+
+def revin_norm(x, mean, stdev):
+    """models/layers/RevIN.py:45-56 (affine=False)."""
+    return (x - mean) / stdev
+
+
+def revin_denorm(y, mean, stdev):
+    """models/layers/RevIN.py:58-69 (affine=False)."""
+    return y * stdev + mean
+
+
+# ----------------------------------------------------------------------------- patching (K2)
+def n_patches(T: int, P: int, S: int) -> int:
+    """models/medtsllm.py:52  int((T - P) / S + 2) == unfold count on the S-padded series."""
+    return (T + S - P) // S + 1
+
+
+def patch_index(T: int, P: int, S: int) -> torch.Tensor:
+    """Integer index map [N,P] into the ORIGINAL series: ReplicationPad1d((0,S)) then unfold(P,S)
+    (models/layers/embed.py:155-163, :188-189) — padded index t reads sample min(t, T-1)."""
+    N = n_patches(T, P, S)
+    idx = torch.arange(N)[:, None] * S + torch.arange(P)[None, :]
+    return idx.clamp_max(T - 1)
+
+
+def patchify(x_bct: torch.Tensor, P: int, S: int) -> torch.Tensor:
+    """x [B,C,T] -> [B*C, N, P]  (models/layers/embed.py:186-190)."""
+    B, C, T = x_bct.shape
+    idx = patch_index(T, P, S)
+    return x_bct[:, :, idx].reshape(B * C, idx.shape[0], P)
+
+
+def token_conv(patches: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """TokenEmbedding: Conv1d(P->d, k=3, circular over the patch axis, bias=False)
+    (models/layers/embed.py:29-46): out[n] = W[:,:,0] p[n-1] + W[:,:,1] p[n] + W[:,:,2] p[n+1]."""
+    prev = torch.roll(patches, 1, dims=1)
+    nxt = torch.roll(patches, -1, dims=1)
+    return prev @ w[:, :, 0].T + patches @ w[:, :, 1].T + nxt @ w[:, :, 2].T
+
+
+# ----------------------------------------------------------------------------- reprogramming (K3/K4)
+def mapping(word_emb, w, b):
+    """models/medtsllm.py:281: mapping_layer(E^T)^T -> source [num_tokens, D]."""
+    return w @ word_emb + b[:, None]
+
+
+def reprogramming(x, source, sd, n_heads: int, prefix="reprogramming_layer."):
+    """models/medtsllm.py:566-591 (dropout = identity at p=0 / eval)."""
+    B, L, _ = x.shape
+    S = source.shape[0]
+    q = F.linear(x, sd[prefix + "query_projection.weight"], sd[prefix + "query_projection.bias"]).view(B, L, n_heads, -1)
+    k = F.linear(source, sd[prefix + "key_projection.weight"], sd[prefix + "key_projection.bias"]).view(S, n_heads, -1)
+    v = F.linear(source, sd[prefix + "value_projection.weight"], sd[prefix + "value_projection.bias"]).view(S, n_heads, -1)
+    scale = 1.0 / math.sqrt(q.shape[-1])
+    scores = torch.einsum("blhe,she->bhls", q, k)
+    A = torch.softmax(scale * scores, dim=-1)
+    out = torch.einsum("bhls,she->blhe", A, v).reshape(B, L, -1)
+    return F.linear(out, sd[prefix + "out_projection.weight"], sd[prefix + "out_projection.bias"])
+
+
+# ----------------------------------------------------------------------------- prompt (K5)
+def assemble_prompt(ids_per_sample, word_emb, pad_id: int):
+    """models/medtsllm.py:299-311, 331-337: embed, LEFT-pad with the pad-token embedding, stack."""
+    B = len(ids_per_sample)
+    D = word_emb.shape[1]
+    Lp = max((len(i) for i in ids_per_sample), default=0)
+    out = word_emb.new_zeros(B, Lp, D)
+    for b, ids in enumerate(ids_per_sample):
+        pad = Lp - len(ids)
+        if pad:
+            out[b, :pad] = word_emb[pad_id]
+        if len(ids):
+            out[b, pad:] = word_emb[torch.as_tensor(ids, dtype=torch.long)]
+    return out
+
+
+# ----------------------------------------------------------------------------- Llama backbone (K6-K10)
+def rmsnorm(x, w, eps):
+    """HF:models/llama/modeling_llama.py:61-67."""
+    var = x.float().pow(2).mean(-1, keepdim=True)
+    return w * (x.float() * torch.rsqrt(var + eps)).to(x.dtype)
+
+
+def rope_tables(L: int, head_dim: int, theta: float = 10000.0):
+    """HF:models/llama/modeling_llama.py:107-136 (default rope): cos/sin [L, head_dim/2] fp32."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    freqs = torch.arange(L, dtype=torch.float32)[:, None] * inv_freq[None, :]
+    return freqs.cos(), freqs.sin()
+
+
+def apply_rope(t, cos, sin):
+    """HF:models/llama/modeling_llama.py:139-168 — rotate-half; t [B,H,L,hd]."""
+    hd = t.shape[-1]
+    cos = torch.cat([cos, cos], -1)[None, None]
+    sin = torch.cat([sin, sin], -1)[None, None]
+    rot = torch.cat([-t[..., hd // 2:], t[..., : hd // 2]], dim=-1)
+    return t * cos + rot * sin
+
+
+def causal_attention(q, k, v, scale):
+    """HF:models/llama/modeling_llama.py:199-221 / HF:models/gpt2/modeling_gpt2.py:54-72 — eager,
+    causal, no padding mask (models/medtsllm.py:350 passes none)."""
+    L = q.shape[-2]
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = torch.ones(L, L, dtype=torch.bool, device=q.device).tril()
+    s = s.masked_fill(~mask, torch.finfo(s.dtype).min)
+    return torch.softmax(s.float(), dim=-1).to(q.dtype) @ v
+
+
+def llama_forward(x, sd, *, n_layers: int, n_heads: int, eps: float, theta: float = 10000.0,
+                  return_hidden: bool = False):
+    """HF LlamaModel.forward on inputs_embeds (HF:models/llama/modeling_llama.py:375-425, decoder
+    layer :303-332, attention :251-300, MLP :171-184).  `sd` uses HF parameter names."""
+    B, L, D = x.shape
+    hd = D // n_heads
+    cos, sin = rope_tables(L, hd, theta)
+    hidden = [x]
+    for i in range(n_layers):
+        p = f"layers.{i}."
+        h = rmsnorm(x, sd[p + "input_layernorm.weight"], eps)
+        q = F.linear(h, sd[p + "self_attn.q_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
+        k = F.linear(h, sd[p + "self_attn.k_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
+        v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
+        q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+        a = causal_attention(q, k, v, hd ** -0.5).transpose(1, 2).reshape(B, L, D)
+        x = x + F.linear(a, sd[p + "self_attn.o_proj.weight"])
+        h = rmsnorm(x, sd[p + "post_attention_layernorm.weight"], eps)
+        g = F.linear(h, sd[p + "mlp.gate_proj.weight"])
+        u = F.linear(h, sd[p + "mlp.up_proj.weight"])
+        x = x + F.linear(F.silu(g) * u, sd[p + "mlp.down_proj.weight"])
+        hidden.append(x)
+    out = rmsnorm(x, sd["norm.weight"], eps)
+    return (out, hidden) if return_hidden else out
+
+
+# ----------------------------------------------------------------------------- GPT-2 backbone
+def gelu_new(x):
+    """HF:activations.py:59-66."""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
+
+
+def conv1d_hf(x, w, b):
+    """HF:pytorch_utils.py:97-123 — Conv1D: addmm(bias, x, W) with W [in, out]."""
+    return x @ w + b
+
+
+def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, return_hidden: bool = False):
+    """HF GPT2Model.forward on inputs_embeds, eval mode (HF:models/gpt2/modeling_gpt2.py:522-636:
+    + wpe[0..L) :584-585; block :262-309; attention :144-236; MLP :238-243; ln_f :628)."""
+    B, L, D = x.shape
+    hd = D // n_heads
+    x = x + sd["wpe.weight"][:L][None]
+    hidden = [x]
+    for i in range(n_layers):
+        p = f"h.{i}."
+        h = F.layer_norm(x, (D,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
+        qkv = conv1d_hf(h, sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"])
+        q, k, v = (t.view(B, L, n_heads, hd).transpose(1, 2) for t in qkv.split(D, dim=-1))
+        a = causal_attention(q, k, v, 1.0 / math.sqrt(hd)).transpose(1, 2).reshape(B, L, D)
+        x = x + conv1d_hf(a, sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
+        h = F.layer_norm(x, (D,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
+        h = gelu_new(conv1d_hf(h, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
+        x = x + conv1d_hf(h, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        hidden.append(x)
+    out = F.layer_norm(x, (D,), sd["ln_f.weight"], sd["ln_f.bias"], eps)
+    return (out, hidden) if return_hidden else out
+
+
+# ----------------------------------------------------------------------------- whole path
+def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training: bool = False,
+                     return_stages: bool = False):
+    """MedTsLLM.forward/predict (models/medtsllm.py:248-261, 321-384) for covariate modes
+    `concat` / `univariate` and all three down-sample modes, dropout = 0.
+
+    spec keys: task, pred_len, patch_len, stride, d_model (per-feature), d_ff, n_heads, covariate_mode,
+    downsample, n_outputs_per_step, backbone ("llama"|"gpt2"), n_layers, llm_heads, eps, rope_theta,
+    pad_id, seg_mode, n_classes."""
+    if x_enc.ndim == 2:
+        x_enc = x_enc.unsqueeze(-1)
+    B, T, C = x_enc.shape
+    P, S, dm = spec["patch_len"], spec["stride"], spec["d_model"]
+    emb_key = "embed_tokens.weight" if spec["backbone"] == "llama" else "wte.weight"
+    word_emb = backbone_sd[emb_key]
+    stages = {}
+
+    # encode_ts (models/medtsllm.py:263-297)
+    mean, stdev = revin_stats(x_enc)
+    xn = revin_norm(x_enc, mean, stdev).permute(0, 2, 1).contiguous()
+    enc = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
+    N = enc.shape[1]
+    stages["patch_embedding"] = enc
+    if spec["covariate_mode"] == "concat":
+        enc = enc.reshape(B, C, N, dm).permute(0, 2, 1, 3).reshape(B, N, C * dm)
+    elif spec["covariate_mode"] != "univariate":
+        raise NotImplementedError(spec["covariate_mode"])
+    source = mapping(word_emb, adapters["mapping_layer.weight"], adapters["mapping_layer.bias"])
+    stages["source_embeddings"] = source
+    enc = reprogramming(enc, source, adapters, spec["n_heads"])
+    stages["reprogramming_layer"] = enc
+
+    # prompt + backbone (models/medtsllm.py:330-351)
+    prompt = assemble_prompt(prompt_ids, word_emb, spec["pad_id"])
+    llm_in = torch.cat([prompt, enc], dim=1)
+    stages["llm_input"] = llm_in
+    if spec["backbone"] == "llama":
+        dec, hidden = llama_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
+                                    eps=spec["eps"], theta=spec.get("rope_theta", 10000.0), return_hidden=True)
+    else:
+        dec, hidden = gpt2_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
+                                   eps=spec["eps"], return_hidden=True)
+    stages["llm"] = dec
+    stages["llm.hidden_states"] = hidden
+
+    # head (models/medtsllm.py:353-382)
+    dec = dec[:, -N:, :]
+    if spec["downsample"] == "truncate":
+        dec = dec[:, :, : spec["d_ff"]]
+    elif spec["downsample"] == "linear":
+        dec = F.linear(dec, adapters["embedding_downsample_layer.weight"], adapters["embedding_downsample_layer.bias"])
+    elif spec["downsample"] == "average":
+        dec = dec.reshape(B, N, spec["d_ff"], -1).mean(dim=-1)
+    stages["downsample"] = dec
+    dec = dec.permute(0, 2, 1).contiguous().flatten(start_dim=-2)          # k = f*N + n
+    dec = F.linear(dec, adapters["output_projection.linear.weight"], adapters["output_projection.linear.bias"])
+    stages["output_projection"] = dec
+    dec = dec.view(B, spec["pred_len"], spec["n_outputs_per_step"])
+    if spec["task"] in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
+        dec = revin_denorm(dec, mean, stdev)
+    else:
+        dec = dec.squeeze(-1)
+    if not training:  # models/medtsllm.py:251-259
+        if spec["task"] == "semantic_segmentation":
+            dec = F.softmax(dec, dim=-1) if spec.get("n_classes", 0) > 2 else torch.sigmoid(dec)
+        elif spec["task"] == "segmentation" and spec.get("seg_mode") == "boundary-prediction":
+            dec = torch.sigmoid(dec)
+    stages["revin_mean"], stages["revin_stdev"] = mean, stdev
+    stages["output"] = dec
+    return (dec, stages) if return_stages else dec

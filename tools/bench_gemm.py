@@ -1,0 +1,54 @@
+"""Micro-benchmark of mts_gemm at the backbone shapes (CUDA events, L2-sized rotation of operands)."""
+import json, sys, time
+from pathlib import Path
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "med-ts-llm_b200"))
+import torch
+from medtsllm_b200 import ops
+
+dev = torch.device("cuda:0")
+shapes = [  # (name, m, n, k, epilogue, block_n)
+    ("llama_qkv", 6144, 12288, 4096, 0, 0),
+    ("llama_o_resid", 6144, 4096, 4096, 1, 0),
+    ("llama_gateup_swiglu", 6144, 22016, 4096, 3, 256),
+    ("llama_down_resid", 6144, 4096, 11008, 1, 0),
+    ("llama_qkv_bn128", 6144, 12288, 4096, 0, 128),
+    ("gpt2m_qkv", 8960, 3072, 1024, 0, 0),
+    ("gpt2m_fc_gelu", 8960, 4096, 1024, 2, 0),
+    ("gpt2m_proj_resid", 8960, 1024, 4096, 1, 0),
+    ("mapping", 1024, 4096, 32000, 0, 0),
+]
+res = []
+for name, m, n, k, epi, bn in shapes:
+    nrot = 3
+    A = [torch.randn(m, k, device=dev).to(torch.bfloat16) for _ in range(nrot)]
+    B = [(torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16) for _ in range(nrot)]
+    n_out = n // 2 if epi == 3 else n
+    D = torch.zeros(m, n_out, device=dev, dtype=torch.float32 if epi == 1 else torch.bfloat16)
+    bias = torch.zeros(n, device=dev) if epi == 2 else None
+    def run(i):
+        ops.gemm(A[i % nrot], B[i % nrot], D, m=m, n=n, k=k, epilogue=epi, block_n=bn,
+                 bias=bias, bias_axis=1 if bias is not None else 0)
+    for i in range(3): run(i)
+    torch.cuda.synchronize()
+    iters = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters): run(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # cuBLAS yardstick (library GEMM, plain store)
+    C = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    for i in range(3): torch.matmul(A[i % nrot], B[i % nrot].t(), out=C)
+    torch.cuda.synchronize(); e0.record()
+    for i in range(iters): torch.matmul(A[i % nrot], B[i % nrot].t(), out=C)
+    e1.record(); torch.cuda.synchronize()
+    ms_cublas = e0.elapsed_time(e1) / iters
+    fl = 2.0 * m * n * k
+    r = dict(name=name, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+             cublas_ms=round(ms_cublas, 4), cublas_tflops=round(fl / ms_cublas / 1e9, 1))
+    print(json.dumps(r), flush=True)
+    res.append(r)
+    del A, B, D, C
+Path(REPO / "gpurun_out").mkdir(exist_ok=True)
+(REPO / "gpurun_out" / "bench_gemm.json").write_text(json.dumps(res, indent=1))
