@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — samples/sec of the MedTsLLM hot path on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+* ours (default): medtsllm_b200.MedTsLLM — hand-written sm_100a kernels through the C ABI.  A "step"
+  is one forward pass of the hot path (MedTsLLM.forward, eval) over one batch of synthetic windows of
+  the named (seq_len, n_vars) shape through the full-depth frozen backbone (random-init weights of
+  the named architecture, generated on the device; no checkpoints exist offline).
+    value  = whole-job samples/s with the windows already resident in HBM,
+    e2e    = the same metric through the public call `model({"x_enc": host_tensor})`: pinned-host ->
+             device copy of the windows and device -> host read of the predictions inside the timed
+             region, every step.
+  N > 1: one process per GPU (torchrun), the batch dimension shards across ranks (weak scaling: the
+  BASELINE batch is per GPU), no data-path collective in the forward; times are max over ranks.
+* reference: the reference algorithm's CPU implementation (the oracle port: plain PyTorch fp32 on all
+  host cores — the reference is Python/PyTorch, there is nothing to compile) on a bounded sample of
+  the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+for p in (REPO, REPO / "med-ts-llm_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import torch  # noqa: E402
+
+METRIC = "samples/sec (patched windows)"
+
+
+# ------------------------------------------------------------------------------------------------
+def _peaks():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from medtsllm_b200 import _lib, ops
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.model import MedTsLLM
+    from medtsllm_b200.synthetic import (WORKLOADS, AttrDict, FixedLengthTokenizer, SyntheticDataset,
+                                         experiment_config, forward_flops, make_inputs)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    w = WORKLOADS[args.workload]
+    t_build = time.time()
+    backbone = KernelBackbone.random_init(w.backbone, dev, seed=0)
+    tok = FixedLengthTokenizer(w.backbone.vocab, w.prompt_len)
+    torch.manual_seed(0)
+    model = MedTsLLM(AttrDict(experiment_config(w)), SyntheticDataset(w), backbone=backbone, tokenizer=tok)
+    model = model.to(dev, torch.float32).eval()
+    torch.cuda.synchronize()
+    t_build = time.time() - t_build
+
+    host = make_inputs(w, seed=1234 + rank, pin=True)             # pinned host windows
+    resident = {"x_enc": host["x_enc"].to(dev)}                   # HBM-resident copy for `value`
+    with torch.no_grad():
+        out_host = torch.empty(model(resident).shape, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def step_resident():
+        with torch.no_grad():
+            model(resident)
+
+    def step_e2e():
+        with torch.no_grad():
+            x = host["x_enc"].to(dev, non_blocking=True)          # H2D from pinned memory
+            y = model({"x_enc": x})
+            out_host.copy_(y, non_blocking=True)                  # D2H of the predictions
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every mts_gemm launch,
+    # recorded on the launching stream over instrumented steps of the same workload
+    gemm_ms, gemm_flops = None, None
+    if rank == 0:
+        ev, fl = [], []
+        real_gemm = ops.gemm
+
+        def traced_gemm(a, b, d, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = real_gemm(a, b, d, **kw)
+            e.record()
+            ev.append((s, e)); fl.append(2.0 * kw["m"] * kw["n"] * kw["k"] * kw.get("batch", 1))
+            return r
+
+        ops.gemm = traced_gemm
+        try:
+            for _ in range(3):
+                step_resident()
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm = real_gemm
+        gemm_ms = sum(s.elapsed_time(e) for s, e in ev) / 3
+        gemm_flops = sum(fl) / 3
+    barrier()
+
+    if rank == 0:
+        peaks = _peaks()
+        fl = forward_flops(w)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        traffic = None
+        tf = REPO / "profiles" / "gemm_traffic.json"          # per-launch DRAM bytes from the ncu capture
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
+        cpu = cpu_baseline(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+        Lp = w.prompt_len
+        line = {
+            "metric": METRIC, "value": round(world * w.B / (ms_step * 1e-3), 2), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{w.name}: MedTsLLM.forward (eval), {w.backbone.kind} D={w.backbone.hidden} "
+                                   f"x{w.backbone.layers} layers random-init, B={w.B}/GPU T={w.T} C={w.C} "
+                                   f"patches={w.n_patches} prompt={Lp} tokens (L={w.seq})",
+                       "per_gpu_batch": w.B, "seq_len": w.T, "n_vars": w.C, "tokens_per_step": w.B * w.seq,
+                       "l2_policy": f"inputs larger than L2: {backbone.weight_bytes() / 1e9:.1f} GB of weights streamed per step",
+                       "parallelism": f"dp{world} (batch sharded, frozen backbone replicated, no forward collective)",
+                       "build_s": round(t_build, 1)},
+            "clocks": clocks,
+            "e2e": {"value": round(world * w.B / (ms_e2e * 1e-3), 2), "unit": "samples/s",
+                    "h2d_bytes_per_step": host["x_enc"].numel() * 4 + w.B * Lp * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e, 3)},
+            "gpu_launches": int(launches) * world,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_nt_kernel (tcgen05)", "achieved": round(achieved, 1),
+                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": traffic,
+                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                         "gemm_ms_per_step": round(gemm_ms, 3), "gemm_share_of_step": round(gemm_ms / ms_step, 3),
+                         "gemm_flops_per_step": gemm_flops, "algorithmic_fwd_flops": fl["total"]},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def _oracle_step_factory(workload: str, sample_batch: int):
+    """Builds the CPU port (oracle) of the workload at full depth on a reduced batch.  All layers
+    share ONE layer's random weights: identical arithmetic and memory traffic per layer (each layer's
+    weights are far larger than any CPU cache) without materialising 26 GB of fp32 weights."""
+    from medtsllm_b200.synthetic import WORKLOADS
+    from oracle import medtsllm_oracle as O
+    w = WORKLOADS[workload]
+    s = w.backbone
+    g = torch.Generator().manual_seed(0)
+    D, I, V = s.hidden, s.inter, s.vocab
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=g) * 0.02
+
+    sd = {}
+    if s.kind == "llama":
+        one = {"self_attn.q_proj.weight": rnd(D, D), "self_attn.k_proj.weight": rnd(D, D),
+               "self_attn.v_proj.weight": rnd(D, D), "self_attn.o_proj.weight": rnd(D, D),
+               "mlp.gate_proj.weight": rnd(I, D), "mlp.up_proj.weight": rnd(I, D), "mlp.down_proj.weight": rnd(D, I),
+               "input_layernorm.weight": torch.ones(D), "post_attention_layernorm.weight": torch.ones(D)}
+        for i in range(s.layers):
+            for k, v in one.items():
+                sd[f"layers.{i}.{k}"] = v
+        sd["norm.weight"] = torch.ones(D)
+        sd["embed_tokens.weight"] = rnd(V, D)
+    else:
+        one = {"attn.c_attn.weight": rnd(D, 3 * D), "attn.c_attn.bias": torch.zeros(3 * D),
+               "attn.c_proj.weight": rnd(D, D), "attn.c_proj.bias": torch.zeros(D),
+               "mlp.c_fc.weight": rnd(D, I), "mlp.c_fc.bias": torch.zeros(I),
+               "mlp.c_proj.weight": rnd(I, D), "mlp.c_proj.bias": torch.zeros(D),
+               "ln_1.weight": torch.ones(D), "ln_1.bias": torch.zeros(D), "ln_2.weight": torch.ones(D), "ln_2.bias": torch.zeros(D)}
+        for i in range(s.layers):
+            for k, v in one.items():
+                sd[f"h.{i}.{k}"] = v
+        sd["ln_f.weight"], sd["ln_f.bias"] = torch.ones(D), torch.zeros(D)
+        sd["wpe.weight"] = rnd(s.max_pos, D)
+        sd["wte.weight"] = rnd(V, D)
+    dm = 32 * (w.C if w.covariate_mode == "concat" else 1)
+    HE = 8 * w.d_ff
+    nops = w.C if w.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining") else (
+        (w.n_classes if w.n_classes > 2 else 1) if w.task == "semantic_segmentation" else 1)
+    ad = {"mapping_layer.weight": rnd(1024, V), "mapping_layer.bias": torch.zeros(1024),
+          "patch_embedding.value_embedding.tokenConv.weight": rnd(32, 16, 3) * 10,
+          "reprogramming_layer.query_projection.weight": rnd(HE, dm), "reprogramming_layer.query_projection.bias": torch.zeros(HE),
+          "reprogramming_layer.key_projection.weight": rnd(HE, D), "reprogramming_layer.key_projection.bias": torch.zeros(HE),
+          "reprogramming_layer.value_projection.weight": rnd(HE, D), "reprogramming_layer.value_projection.bias": torch.zeros(HE),
+          "reprogramming_layer.out_projection.weight": rnd(D, HE), "reprogramming_layer.out_projection.bias": torch.zeros(D),
+          "embedding_downsample_layer.weight": rnd(w.d_ff, D), "embedding_downsample_layer.bias": torch.zeros(w.d_ff),
+          "output_projection.linear.weight": rnd(nops * w.pred, w.d_ff * w.n_patches),
+          "output_projection.linear.bias": torch.zeros(nops * w.pred)}
+    spec = dict(task=w.task, pred_len=w.pred, patch_len=16, stride=8, d_model=32, d_ff=w.d_ff, n_heads=8,
+                covariate_mode=w.covariate_mode, downsample="linear", n_outputs_per_step=nops, backbone=s.kind,
+                n_layers=s.layers, llm_heads=s.heads, eps=s.eps, rope_theta=s.rope_theta, pad_id=2,
+                seg_mode="boundary-prediction", n_classes=w.n_classes)
+    x = torch.randn(sample_batch, w.T, w.C, generator=g) * 3 + 1
+    ids = [torch.randint(3, V, (w.prompt_len,), generator=g).tolist() for _ in range(sample_batch)]
+
+    def step():
+        with torch.no_grad():
+            return O.medtsllm_forward(x, ids, ad, sd, spec)
+    return step, w
+
+
+def cpu_baseline(workload: str, sample_batch: int | None = None, steps: int = 1, warmup: int = 1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from medtsllm_b200.synthetic import WORKLOADS
+    w = WORKLOADS[workload]
+    if sample_batch is None:
+        sample_batch = 2 if w.backbone.hidden >= 4096 else min(w.B, 16)
+    step, w = _oracle_step_factory(workload, sample_batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_batch / dt, 4), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (plain PyTorch fp32, {cores} threads), full depth ({w.backbone.layers} layers, one "
+                      f"layer's weights shared by all), batch {sample_batch} of {w.B}, {steps} timed forward(s) after "
+                      f"{warmup} warm-up; {dt:.2f} s per forward", "s_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from medtsllm_b200.synthetic import WORKLOADS
+    w = WORKLOADS[args.workload]
+    # bounded: the whole --steps/--warmup run must end within a few minutes
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    cpu = cpu_baseline(args.workload, steps=steps, warmup=warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "samples/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup,
+        "ms_per_step": round(cpu["s_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w.name}: reference algorithm on host cores (CPU), bounded sample — {cpu['sample']}"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="bidmc_llama2_7b")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

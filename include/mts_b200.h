@@ -200,6 +200,11 @@ int mts_prompt_gather(const int32_t* ids, const float* emb, const float* wpe, fl
 int mts_swiglu(const uint16_t* gu, int64_t ldgu, uint16_t* y, int64_t rows, int I,
                mts_stream_t stream);
 
+/* eval-only output activations, in place on fp32 (ref: models/medtsllm.py:251-259):
+ *   sigmoid (binary semantic segmentation / boundary prediction), softmax over n classes. */
+int mts_sigmoid(float* y, int64_t n, mts_stream_t stream);
+int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

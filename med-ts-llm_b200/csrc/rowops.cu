@@ -206,6 +206,27 @@ prompt_gather_kernel(const int32_t* __restrict__ ids, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// eval-only output activations (models/medtsllm.py:251-259): tiny, in place
+// ------------------------------------------------------------------------------------------
+__global__ void sigmoid_kernel(float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = 1.0f / (1.0f + expf(-y[i]));
+}
+__global__ void softmax_lastdim_kernel(float* __restrict__ y, int64_t rows, int n) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    float* p = y + r * n;
+    float mx = -INFINITY;
+    for (int i = 0; i < n; ++i) mx = fmaxf(mx, p[i]);
+    float sum = 0.0f;
+    for (int i = 0; i < n; ++i) sum += expf(p[i] - mx);
+    const float inv = 1.0f / sum;
+    for (int i = 0; i < n; ++i) p[i] = expf(p[i] - mx) * inv;
+  }
+}
+
 static int grid_for(int64_t n, int per_block) {
   int64_t g = (n + per_block - 1) / per_block;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -335,4 +356,20 @@ extern "C" int mts_prompt_gather(const int32_t* ids, const float* emb, const flo
   prompt_gather_kernel<<<B * L, 256, 0, (cudaStream_t)s>>>(ids, emb, wpe, x, rep, Lp, L, D);
   count_launch();
   return check_launch("prompt_gather_kernel");
+}
+
+extern "C" int mts_sigmoid(float* y, int64_t n, mts_stream_t s) {
+  if (!y || n < 0) return set_error(MTS_ERR_INVALID_ARG, "mts_sigmoid: bad args");
+  if (n == 0) return MTS_OK;
+  sigmoid_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(y, n);
+  count_launch();
+  return check_launch("sigmoid_kernel");
+}
+
+extern "C" int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t s) {
+  if (!y || rows < 0 || n <= 0) return set_error(MTS_ERR_INVALID_ARG, "mts_softmax_lastdim: bad args");
+  if (rows == 0) return MTS_OK;
+  softmax_lastdim_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)s>>>(y, rows, n);
+  count_launch();
+  return check_launch("softmax_lastdim_kernel");
 }

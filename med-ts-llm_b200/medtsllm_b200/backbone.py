@@ -1,0 +1,285 @@
+"""Frozen LLM backbones (Llama / GPT-2 decoder stacks) laid out for the sm_100a kernels.
+
+Replaces the HuggingFace backbone call `self.llm(inputs_embeds=...)` (models/medtsllm.py:346-351):
+the arithmetic of HF:models/llama/modeling_llama.py:303-332,375-425 and
+HF:models/gpt2/modeling_gpt2.py:262-309,522-636 is re-implemented on libmtsb200 kernels.
+
+HBM layout (per layer, all K-major so every GEMM is the one NT tcgen05 kernel):
+  Llama: wqkv [3D,D] bf16 (q|k|v rows), wo [D,D], wgu packed [2*Ipad,D] (128 gate rows then the
+         matching 128 up rows, for the fused SwiGLU epilogue), wdown [D,Ipad]; RMSNorm weights fp32.
+  GPT-2: Conv1D weights are [in,out]; stored transposed: wqkv [3D,D], wo [D,D], wfc [4D,D],
+         wproj [D,4D]; biases and LayerNorm parameters fp32; wpe fp32.
+  For the training path each frozen weight additionally keeps its transpose (dgrad is then the same
+  NT kernel): ~2x weight memory (26 GB for Llama-2-7B), sized for the 180 GB of a B200.
+The residual stream is fp32 [B', L, D] (as in the reference under bf16 autocast, where the residual
+adds promote to fp32); GEMM operands are bf16, accumulation fp32 in TMEM.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+from ._lib import BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_STORE, EPI_SWIGLU, MtsError
+
+
+@dataclass
+class BackboneSpec:
+    kind: str            # "llama" | "gpt2"
+    hidden: int
+    layers: int
+    heads: int
+    inter: int
+    vocab: int
+    eps: float
+    rope_theta: float = 10000.0
+    max_pos: int = 4096
+
+    @property
+    def head_dim(self):
+        return self.hidden // self.heads
+
+
+def spec_from_hf_config(cfg) -> BackboneSpec:
+    mt = cfg.model_type
+    if mt == "llama":
+        if getattr(cfg, "num_key_value_heads", cfg.num_attention_heads) != cfg.num_attention_heads:
+            raise MtsError("grouped-query attention is not supported (Llama-2-7B has 32 KV heads)")
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
+        if rp.get("rope_type", "default") != "default":
+            raise MtsError(f"rope_type {rp.get('rope_type')} is not supported")
+        return BackboneSpec("llama", cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                            cfg.intermediate_size, cfg.vocab_size, cfg.rms_norm_eps, theta,
+                            cfg.max_position_embeddings)
+    if mt == "gpt2":
+        inner = cfg.n_inner if cfg.n_inner is not None else 4 * cfg.n_embd
+        if cfg.activation_function != "gelu_new":
+            raise MtsError(f"GPT-2 activation {cfg.activation_function} is not supported")
+        return BackboneSpec("gpt2", cfg.n_embd, cfg.n_layer, cfg.n_head, inner, cfg.vocab_size,
+                            cfg.layer_norm_epsilon, max_pos=cfg.n_positions)
+    raise MtsError(f"backbone model_type {mt!r} is not supported (llama, gpt2)")
+
+
+def _rope_tables(L, hd, theta, device):
+    # HF:models/llama/modeling_llama.py:107-136 (default rope), fp32
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    f = torch.arange(L, dtype=torch.float32)[:, None] * inv[None, :]
+    return f.cos().contiguous().to(device), f.sin().contiguous().to(device)
+
+
+class KernelBackbone:
+    """Device-resident frozen decoder stack.  Not an nn.Module on purpose: `.to(dtype)` from the
+    Trainer (tasks/base.py:41) must not re-cast the bf16 kernel weights."""
+
+    def __init__(self, spec: BackboneSpec, device, keep_transposed: bool = False):
+        self.spec = spec
+        self.device = torch.device(device)
+        self.keep_transposed = keep_transposed
+        self.layers: list[dict] = []
+        self.final_norm_w = None
+        self.final_norm_b = None
+        self.embed = None       # fp32 [V, D] input embedding table (prompt gather)
+        self.embed_t = None     # bf16 [D, V] (K-major operand of the mapping GEMM)
+        self.wpe = None         # GPT-2 only, fp32 [max_pos, D]
+        self._rope = None
+        self.i_pad = ((spec.inter + 127) // 128) * 128 if spec.kind == "llama" else spec.inter
+
+    # ---------------------------------------------------------------------------------- building
+    def _bf16(self, w: torch.Tensor) -> torch.Tensor:
+        """fp32 (any device) -> bf16 on the target device, cast by our kernel."""
+        return ops.cast_bf16(w.detach().to(self.device, torch.float32))
+
+    def _t_bf16(self, w: torch.Tensor) -> torch.Tensor:
+        return ops.transpose_to_bf16(w.detach().to(self.device, torch.float32))
+
+    def _f32(self, w):
+        return w.detach().to(self.device, torch.float32).contiguous()
+
+    def _finish_embeddings(self, emb: torch.Tensor):
+        self.embed = self._f32(emb)
+        self.embed_t = ops.transpose_to_bf16(self.embed)
+
+    def _add_llama_layer(self, wq, wk, wv, wo, wg, wu, wd, ln1, ln2):
+        s = self.spec
+        lay = {}
+        lay["wqkv"] = self._bf16(torch.cat([wq, wk, wv], dim=0))
+        lay["wo"] = self._bf16(wo)
+        lay["wgu"] = ops.pack_gate_up(self._bf16(wg), self._bf16(wu))
+        wd_b = self._bf16(wd)                                    # [D, I]
+        if self.i_pad != s.inter:
+            pad = torch.zeros(s.hidden, self.i_pad, device=self.device, dtype=torch.bfloat16)
+            pad[:, : s.inter] = wd_b
+            wd_b = pad
+        lay["wdown"] = wd_b
+        lay["ln1"] = self._f32(ln1)
+        lay["ln2"] = self._f32(ln2)
+        if self.keep_transposed:
+            lay["wqkv_t"] = ops.transpose_to_bf16(lay["wqkv"])
+            lay["wo_t"] = ops.transpose_to_bf16(lay["wo"])
+            lay["wg_t"] = self._t_bf16(wg)        # [D, I]
+            lay["wu_t"] = self._t_bf16(wu)
+            lay["wdown_t"] = self._t_bf16(wd)     # [I, D]
+        self.layers.append(lay)
+
+    def _add_gpt2_layer(self, c_attn_w, c_attn_b, c_proj_w, c_proj_b, fc_w, fc_b, proj_w, proj_b,
+                        ln1w, ln1b, ln2w, ln2b):
+        lay = {}
+        lay["wqkv"] = self._t_bf16(c_attn_w)       # Conv1D [D,3D] -> [3D,D]
+        lay["bqkv"] = self._f32(c_attn_b)
+        lay["wo"] = self._t_bf16(c_proj_w)
+        lay["bo"] = self._f32(c_proj_b)
+        lay["wfc"] = self._t_bf16(fc_w)            # [D,4D] -> [4D,D]
+        lay["bfc"] = self._f32(fc_b)
+        lay["wproj"] = self._t_bf16(proj_w)        # [4D,D] -> [D,4D]
+        lay["bproj"] = self._f32(proj_b)
+        lay["ln1"], lay["ln1b"] = self._f32(ln1w), self._f32(ln1b)
+        lay["ln2"], lay["ln2b"] = self._f32(ln2w), self._f32(ln2b)
+        if self.keep_transposed:
+            lay["wqkv_t"] = self._bf16(c_attn_w)   # [D,3D] is already the transpose
+            lay["wo_t"] = self._bf16(c_proj_w)
+            lay["wfc_t"] = self._bf16(fc_w)
+            lay["wproj_t"] = self._bf16(proj_w)
+        self.layers.append(lay)
+
+    @classmethod
+    def from_hf(cls, hf_model, device, keep_transposed=False) -> "KernelBackbone":
+        """Converts a HuggingFace LlamaModel / GPT2Model (as loaded by the reference's setup_llm,
+        models/medtsllm.py:175-185) layer by layer."""
+        spec = spec_from_hf_config(hf_model.config)
+        self = cls(spec, device, keep_transposed)
+        sd = hf_model.state_dict()
+        if spec.kind == "llama":
+            for i in range(spec.layers):
+                p = f"layers.{i}."
+                self._add_llama_layer(
+                    sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
+                    sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.o_proj.weight"],
+                    sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"],
+                    sd[p + "mlp.down_proj.weight"], sd[p + "input_layernorm.weight"],
+                    sd[p + "post_attention_layernorm.weight"])
+            self.final_norm_w = self._f32(sd["norm.weight"])
+            self._finish_embeddings(sd["embed_tokens.weight"])
+        else:
+            for i in range(spec.layers):
+                p = f"h.{i}."
+                self._add_gpt2_layer(
+                    sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"],
+                    sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"],
+                    sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"],
+                    sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"],
+                    sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], sd[p + "ln_2.weight"], sd[p + "ln_2.bias"])
+            self.final_norm_w, self.final_norm_b = self._f32(sd["ln_f.weight"]), self._f32(sd["ln_f.bias"])
+            self.wpe = self._f32(sd["wpe.weight"])
+            self._finish_embeddings(sd["wte.weight"])
+        return self
+
+    @classmethod
+    def random_init(cls, spec: BackboneSpec, device, seed=0, keep_transposed=False, std=0.02):
+        """Seeded random-init stack generated directly on the device (no checkpoints exist offline;
+        HF `initializer_range` = 0.02, norms = 1, biases = 0)."""
+        self = cls(spec, device, keep_transposed)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        D, I = spec.hidden, spec.inter
+
+        def rnd(*shape):
+            return torch.randn(*shape, device=self.device, dtype=torch.float32, generator=g) * std
+
+        ones, zeros = (lambda n: torch.ones(n, device=self.device)), (lambda n: torch.zeros(n, device=self.device))
+        for _ in range(spec.layers):
+            if spec.kind == "llama":
+                self._add_llama_layer(rnd(D, D), rnd(D, D), rnd(D, D), rnd(D, D), rnd(I, D), rnd(I, D),
+                                      rnd(D, I), ones(D), ones(D))
+            else:
+                self._add_gpt2_layer(rnd(D, 3 * D), zeros(3 * D), rnd(D, D), zeros(D), rnd(D, I), zeros(I),
+                                     rnd(I, D), zeros(D), ones(D), zeros(D), ones(D), zeros(D))
+        self.final_norm_w = ones(D)
+        if spec.kind == "gpt2":
+            self.final_norm_b = zeros(D)
+            self.wpe = rnd(spec.max_pos, D)
+        self._finish_embeddings(rnd(spec.vocab, D))
+        return self
+
+    # ---------------------------------------------------------------------------------- forward
+    def rope(self, L):
+        if self.spec.kind != "llama":
+            return None
+        if self._rope is None or self._rope[0].shape[0] < L:
+            self._rope = _rope_tables(max(L, 512), self.spec.head_dim, self.spec.rope_theta, self.device)
+        return self._rope
+
+    def weight_bytes(self) -> int:
+        n = 0
+        for lay in self.layers:
+            n += sum(t.numel() * t.element_size() for t in lay.values())
+        return n
+
+    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None) -> torch.Tensor:
+        """x: fp32 residual stream [Bp*L, D], updated IN PLACE layer by layer; returns the final-norm
+        output bf16 [Bp*L, D].  If `stash` is a list, per-layer activations needed by backward() are
+        appended to it (training)."""
+        s = self.spec
+        D, H, hd = s.hidden, s.heads, s.head_dim
+        M = Bp * L
+        if x.shape != (M, D) or x.dtype != torch.float32 or not x.is_contiguous():
+            raise MtsError("backbone.forward expects a contiguous fp32 [Bp*L, D] residual stream")
+        if s.kind == "gpt2" and L > s.max_pos:
+            raise IndexError(f"sequence length {L} exceeds GPT-2 position table {s.max_pos}")
+        rope = self.rope(L)
+        dev = x.device
+        h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+        att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        for lay in self.layers:
+            if stash is not None:
+                st = {"x_in": x.clone()}
+                h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+                qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+                att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+            if s.kind == "llama":
+                ops.rmsnorm(x, lay["ln1"], s.eps, out=h)
+                ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D)
+                if stash is not None:
+                    _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att, want_lse=True)
+                    st.update(qkv=qkv, att=att, lse=lse)
+                else:
+                    ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att)
+                ops.gemm(att, lay["wo"], x, m=M, n=D, k=D, epilogue=EPI_RESID_ADD)
+                if stash is not None:
+                    st["x_mid"] = x.clone()
+                    h2 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+                else:
+                    h2 = h
+                ops.rmsnorm(x, lay["ln2"], s.eps, out=h2)
+                if stash is not None:
+                    # keep gate/up pre-activations for the backward: plain store + separate SwiGLU
+                    raise MtsError("training stash for llama is implemented in backbone_train.py")
+                act = torch.empty(M, self.i_pad, device=dev, dtype=torch.bfloat16)
+                ops.gemm(h2, lay["wgu"], act, m=M, n=2 * self.i_pad, k=D, epilogue=EPI_SWIGLU, block_n=256)
+                ops.gemm(act, lay["wdown"], x, m=M, n=D, k=self.i_pad, epilogue=EPI_RESID_ADD)
+            else:
+                ops.layernorm(x, lay["ln1"], lay["ln1b"], s.eps, out=h)
+                ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"], bias_axis=BIAS_N)
+                ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att)
+                ops.gemm(att, lay["wo"], x, m=M, n=D, k=D, bias=lay["bo"], bias_axis=BIAS_N,
+                         epilogue=EPI_RESID_ADD)
+                ops.layernorm(x, lay["ln2"], lay["ln2b"], s.eps, out=h)
+                act = torch.empty(M, s.inter, device=dev, dtype=torch.bfloat16)
+                ops.gemm(h, lay["wfc"], act, m=M, n=s.inter, k=D, bias=lay["bfc"], bias_axis=BIAS_N,
+                         epilogue=EPI_GELU_NEW)
+                ops.gemm(act, lay["wproj"], x, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
+                         epilogue=EPI_RESID_ADD)
+        out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        if s.kind == "llama":
+            ops.rmsnorm(x, self.final_norm_w, s.eps, out=out)
+        else:
+            ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
+        return out
+
+    def flops_per_token_fwd(self, L: int) -> float:
+        """Dense algorithmic forward FLOPs per token: 2*W_blk + 4*L*D per layer."""
+        s = self.spec
+        w_blk = 4 * s.hidden ** 2 + (3 if s.kind == "llama" else 2) * s.hidden * s.inter
+        return s.layers * (2.0 * w_blk + 4.0 * L * s.hidden)

@@ -1,0 +1,520 @@
+"""`MedTsLLM` — drop-in for the reference class of the same name (models/medtsllm.py:24-527).
+
+Same constructor `(config, dataset)`, same `forward(inputs: dict) -> Tensor`, same config keys, same
+`state_dict()` keys (adapters only; the frozen LLM and `word_embeddings` are never checkpointed,
+models/medtsllm.py:235-246), same `load_pretrained`, `supported_tasks`, `lora_enabled`.  Everything
+numeric runs on libmtsb200 kernels through `ops` (C ABI): there is no torch-arithmetic fallback and
+a CPU tensor raises `MtsError`.
+
+Host-side logic kept in Python exactly like the reference: prompt text building and tokenisation
+(HF tokenizer).  The per-sample/per-part embedding gathers + left padding + concat
+(models/medtsllm.py:299-311, 331-337, 349) become ONE batched gather kernel over a host-built
+token-id table, with static parts tokenised once and cached.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import BIAS_M, BIAS_N, EPI_RESID_ADD, MtsError
+from .backbone import BackboneSpec, KernelBackbone, spec_from_hf_config
+
+os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
+
+_DEFAULT_PROMPTING = {"dataset": True, "clip": True, "input_stats": True, "task": True, "examples": False,
+                      "input_stats_dim": 0, "input_stats_select": "all"}
+
+
+def _get(obj, key, default=None):
+    """config objects are the reference's `dict_to_object` (utils.py:19-39) or plain dicts."""
+    if obj is None:
+        return default
+    if isinstance(obj, dict):
+        return obj.get(key, default)
+    if hasattr(obj, "get"):
+        return obj.get(key, default)
+    return getattr(obj, key, default)
+
+
+def _has(obj, key):
+    if isinstance(obj, dict):
+        return key in obj
+    try:
+        return key in obj
+    except TypeError:
+        return hasattr(obj, key)
+
+
+class _TokenEmbeddingParams(nn.Module):
+    """Parameter holder with the reference's module path (models/layers/embed.py:29-42):
+    `value_embedding.tokenConv.weight` [d_model, patch_len, 3], kaiming-normal init."""
+
+    def __init__(self, c_in, d_model):
+        super().__init__()
+        self.tokenConv = nn.Conv1d(c_in, d_model, kernel_size=3, padding=1, padding_mode="circular", bias=False)
+        nn.init.kaiming_normal_(self.tokenConv.weight, mode="fan_in", nonlinearity="leaky_relu")
+
+
+class _PatchEmbeddingParams(nn.Module):
+    def __init__(self, d_model, patch_len, stride, dropout):
+        super().__init__()
+        self.patch_len, self.stride, self.p_dropout = patch_len, stride, dropout
+        self.value_embedding = _TokenEmbeddingParams(patch_len, d_model)
+
+
+class _ReprogrammingParams(nn.Module):
+    """models/medtsllm.py:555-564 — parameter holder (same names, same nn.Linear init)."""
+
+    def __init__(self, d_model, n_heads, d_keys, d_llm):
+        super().__init__()
+        self.query_projection = nn.Linear(d_model, d_keys * n_heads)
+        self.key_projection = nn.Linear(d_llm, d_keys * n_heads)
+        self.value_projection = nn.Linear(d_llm, d_keys * n_heads)
+        self.out_projection = nn.Linear(d_keys * n_heads, d_llm)
+        self.n_heads = n_heads
+
+
+class _FlattenHeadParams(nn.Module):
+    """models/medtsllm.py:541-546."""
+
+    def __init__(self, nf, target_window):
+        super().__init__()
+        self.linear = nn.Linear(nf, target_window)
+
+
+class _LLMHandle:
+    """What the reference's surroundings touch on `model.llm` (loggers/base_logger.py:42-43,
+    models/medtsllm.py:346): `.config` and, for LoRA runs, `.save_pretrained`."""
+
+    def __init__(self, config):
+        self.config = config
+
+    def save_pretrained(self, path, *a, **k):
+        raise MtsError("LoRA adapters are not implemented in medtsllm_b200 yet")
+
+
+class MedTsLLM(nn.Module):
+
+    supported_tasks = ["forecasting", "reconstruction", "anomaly_detection", "semantic_segmentation", "segmentation", "pretraining"]
+    supported_modes = ["univariate", "multivariate"]
+
+    def __init__(self, config, dataset, backbone: KernelBackbone | None = None, tokenizer=None):
+        """`backbone`/`tokenizer` are optional injection points for benchmarks and tests (a
+        device-resident random-init stack); by default both are loaded exactly as the reference
+        does (AutoConfig/AutoModel/AutoTokenizer from `llm.llm`, models/medtsllm.py:129-233)."""
+        super().__init__()
+        self.config = config
+        models_cfg = _get(config, "models")
+        self.model_config = _get(models_cfg, "medtsllm") if _has(models_cfg, "medtsllm") else _get(models_cfg, "timellm")
+        mc = self.model_config
+
+        self.device = None
+        self.pred_len = _get(config, "pred_len")
+        self.seq_len = _get(config, "history_len")
+        self.task = _get(config, "task")
+        self.task_description = self.get_task_description(dataset)
+        self.dataset_description = dataset.description
+
+        self.d_ff = _get(mc, "d_ff")
+        self.d_model = _get(mc, "d_model")
+        self.n_attention_heads = _get(mc, "n_heads")
+        self.num_tokens = _get(mc, "num_tokens")
+        self.dropout = _get(_get(config, "training"), "dropout")
+        self.n_lags = 5
+
+        patching = _get(mc, "patching")
+        self.patch_len = _get(patching, "patch_len")
+        self.stride = _get(patching, "stride")
+        self.n_patches = int((self.seq_len - self.patch_len) / self.stride + 2)
+        self.d_patch = self.d_model
+
+        self.covariate_mode = _get(mc, "covariate_mode")
+        self.n_features = dataset.n_features
+        self.n_classes = dataset.n_classes if self.task in ["classification", "semantic_segmentation"] else 0
+
+        if self.task in ["forecasting", "reconstruction", "anomaly_detection", "pretraining"]:
+            self.n_outputs_per_step = self.n_features
+        elif self.task == "semantic_segmentation":
+            self.n_outputs_per_step = self.n_classes if self.n_classes > 2 else 1
+        elif self.task == "segmentation":
+            self.n_outputs_per_step = 1
+            self.seg_mode = _get(_get(_get(config, "tasks"), "segmentation"), "mode")
+            assert self.seg_mode in ["boundary-prediction", "steps-to-boundary"]
+        else:
+            raise ValueError(f"Task {self.task} is not supported.")
+        self.n_outputs = self.n_outputs_per_step * self.pred_len
+
+        if self.covariate_mode == "univariate":
+            assert self.n_features == 1
+        elif self.covariate_mode == "concat":
+            self.d_model *= self.n_features
+        elif self.covariate_mode in ("interleave", "independent", "merge-end", "weighted-average", "add"):
+            raise NotImplementedError(
+                f"covariate_mode={self.covariate_mode!r}: medtsllm_b200 implements the modes used by the shipped "
+                "configs (concat, univariate); the others are listed as next in DESIGN.md")
+        else:
+            raise ValueError(f"Unknown covariate mode {self.covariate_mode}")
+
+        self.setup_llm(backbone, tokenizer)
+
+        # trainable adapters: same module paths / shapes / init as the reference (models/medtsllm.py:91-101)
+        self.mapping_layer = nn.Linear(self.vocab_size, self.num_tokens)
+        self.patch_embedding = _PatchEmbeddingParams(self.d_patch, self.patch_len, self.stride, self.dropout)
+        self.reprogramming_layer = _ReprogrammingParams(self.d_model, self.n_attention_heads, self.d_ff, self.d_llm)
+        self.output_projection = _FlattenHeadParams(self.d_ff * self.n_patches, self.n_outputs)
+
+        self.embedding_downsample_mode = _get(mc, "embedding_downsample_mode")
+        if self.embedding_downsample_mode == "linear":
+            self.embedding_downsample_layer = nn.Linear(self.d_llm, self.d_ff)
+        elif self.embedding_downsample_mode in ("truncate", "average"):
+            raise NotImplementedError(
+                f"embedding_downsample_mode={self.embedding_downsample_mode!r} is listed as next in DESIGN.md "
+                "(shipped configs use 'linear')")
+        else:
+            raise ValueError(f"Unknown embedding downsample mode {self.embedding_downsample_mode}")
+
+        if self.dropout and self.dropout > 0:
+            # PatchEmbedding / reprogramming dropout (models/medtsllm.py:93-94) are training-time noise;
+            # the kernels implement the deterministic path.  Recorded so train() can refuse loudly.
+            self._dropout_requested = float(self.dropout)
+        else:
+            self._dropout_requested = 0.0
+
+        self._capture = None       # tests: dict filled with per-stage tensors
+        self._prompt_cache: dict[str, list[int]] = {}
+        self._src_cache = None     # (versions, source_bf16, K_bf16, Vt_bf16)
+        self._w_cache: dict[str, tuple[int, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------------------------------ LLM
+    def setup_llm(self, backbone=None, tokenizer=None):
+        mc = self.model_config
+        llm_cfg = _get(mc, "llm")
+        self.llm_enabled = _get(llm_cfg, "enabled")
+        if not self.llm_enabled:
+            raise NotImplementedError("llm.enabled = false (llm_replacement MLP) is outside the accelerated path")
+        self.llm_id = _get(llm_cfg, "llm")
+        self.llm_layers = _get(llm_cfg, "llm_layers")
+        if _get(llm_cfg, "load_in_4bit") or _get(llm_cfg, "load_in_8bit"):
+            raise NotImplementedError("bitsandbytes 4/8-bit loading is outside the accelerated path")
+        lora = _get(mc, "lora")
+        self.lora_enabled = bool(lora is not None and _get(lora, "enabled"))
+        if self.lora_enabled:
+            raise NotImplementedError("LoRA is listed as next in DESIGN.md")
+        dtype_name = _get(_get(self.config, "setup"), "dtype")
+        if dtype_name not in ("float32", "float", "fp32", "32", 32, "mixed"):
+            raise NotImplementedError(
+                f"setup.dtype={dtype_name!r}: adapters are fp32 masters and kernels compute in bf16 with fp32 "
+                "accumulation; use 'mixed' (the shipped configs) or 'float32'")
+
+        if backbone is not None:
+            self._backbone = backbone
+            object.__setattr__(self, "_hf_model", None)
+            self.tokenizer = tokenizer
+            self.llm = _LLMHandle(None)
+            spec = backbone.spec
+        else:
+            from transformers import AutoConfig, AutoModel, AutoTokenizer
+            cache_dir = _get(_get(self.config, "paths", {}), "llm_path")
+            if cache_dir in ("", "none"):
+                cache_dir = None
+            llm_config = AutoConfig.from_pretrained(self.llm_id, cache_dir=cache_dir)
+            if self.llm_layers > 0 and self.llm_layers < llm_config.num_hidden_layers:
+                llm_config.num_hidden_layers = self.llm_layers
+            spec = spec_from_hf_config(llm_config)
+            # host copy, converted to kernel layout when the model is moved to the GPU (`_apply`)
+            # (kept out of the Module tree: the frozen LLM is never a parameter of this model)
+            object.__setattr__(self, "_hf_model", AutoModel.from_pretrained(
+                self.llm_id, config=llm_config, torch_dtype=torch.float32, cache_dir=cache_dir))
+            self._backbone = None
+            self.tokenizer = tokenizer or AutoTokenizer.from_pretrained(self.llm_id, cache_dir=cache_dir)
+            self.llm = _LLMHandle(llm_config)
+
+        if self.tokenizer is not None:
+            if self.tokenizer.eos_token:
+                self.tokenizer.pad_token = self.tokenizer.eos_token
+            else:
+                self.tokenizer.add_special_tokens({"pad_token": "[PAD]"})
+                self.tokenizer.pad_token = "[PAD]"
+        if spec.vocab > 100_000:
+            raise NotImplementedError("vocabularies > 100k (sub-sampled trainable word_embeddings, "
+                                      "models/medtsllm.py:219-222) are outside the BASELINE configs")
+        self.backbone_spec: BackboneSpec = spec
+        self.vocab_size = spec.vocab
+        self.d_llm = spec.hidden
+
+    def _apply(self, fn, *args, **kwargs):
+        """`.to(device, dtype)` from the Trainer (tasks/base.py:41): adapters follow torch; the frozen
+        stack is converted once to the bf16 kernel layout on the target GPU and the host copy freed."""
+        super()._apply(fn, *args, **kwargs)
+        dev = self.mapping_layer.weight.device
+        if dev.type == "cuda":
+            if self._backbone is None:
+                self._backbone = KernelBackbone.from_hf(self._hf_model, dev, keep_transposed=False)
+                object.__setattr__(self, "_hf_model", None)
+            elif self._backbone.device != dev:
+                raise MtsError("the kernel backbone lives on another device")
+            self.device = dev
+        return self
+
+    def state_dict(self, *args, **kwargs):
+        # adapters only, as the reference (models/medtsllm.py:235-246); the backbone is not a Module
+        return super().state_dict(*args, **kwargs)
+
+    def load_pretrained(self, saved_state):
+        """models/medtsllm.py:515-527."""
+        for k in ("word_embeddings", "output_projection.linear.bias", "output_projection.linear.weight"):
+            saved_state.pop(k, None)
+        incompat = self.load_state_dict(saved_state, strict=False)
+        assert len(incompat.unexpected_keys) == 0, f"Unexpected keys in model state: {incompat.unexpected_keys}"
+        return list(saved_state.keys())
+
+    def train(self, mode: bool = True):
+        return super().train(mode)
+
+    # ------------------------------------------------------------------------------------------ prompt
+    def get_task_description(self, dataset):
+        """models/medtsllm.py:497-513."""
+        if getattr(dataset, "task_description", None) is not None:
+            return dataset.task_description
+        if self.task in ("forecasting", "pretraining"):
+            return f"Forecast the next {self.pred_len} steps given the previous {self.seq_len} steps of data."
+        if self.task in ("anomaly_detection", "reconstruction"):
+            return f"Reconstruct the past {self.seq_len} steps of data as accurately as possible using the following information."
+        if self.task == "semantic_segmentation":
+            return f"Classify the past {self.seq_len} steps of data as accurately as possible using the following information."
+        if self.task == "segmentation":
+            return f"Identify the change points in the past {self.seq_len} steps of data to segment the sequence."
+        raise ValueError(f"Task {self.task} is not supported.")
+
+    def build_prompt(self, inputs):
+        """models/medtsllm.py:386-439 — per-sample list of prompt parts (host strings)."""
+        bs = inputs["x_enc"].size(0)
+        cfg = _get(self.model_config, "prompting") or _DEFAULT_PROMPTING
+        flags = {k: _get(cfg, k, _DEFAULT_PROMPTING[k]) for k in _DEFAULT_PROMPTING}
+        if not (flags["dataset"] or flags["clip"] or flags["input_stats"] or flags["task"] or flags["examples"]):
+            return [[] for _ in range(bs)]
+        dataset_prompt = f"Dataset: {self.dataset_description}" if flags["dataset"] else ""
+        if flags["examples"]:
+            raise NotImplementedError("prompting.examples (time-series example parts) is listed as next in DESIGN.md")
+        clip_prompts = inputs.get("descriptions", [""] * bs) if flags["clip"] else [""] * bs
+        stats_prompts = self.build_input_stats_prompt(flags, inputs) if flags["input_stats"] else [""] * bs
+        task_prompt = f"Task: {self.task_description}" if flags["task"] else ""
+        bos = self.tokenizer.bos_token if self.tokenizer.bos_token is not None else ""
+        prompts = []
+        for b in range(bs):
+            parts = [bos, dataset_prompt, clip_prompts[b], stats_prompts[b], task_prompt, "Time series:"]
+            parts = [p for p in parts if p != ""]
+            parts = [(p + " " if i != 0 else p) for i, p in enumerate(parts)]
+            prompts.append(parts)
+        return prompts
+
+    def build_input_stats_prompt(self, flags, inputs):
+        """models/medtsllm.py:441-495 — text statistics of the window.  Text generation on the host
+        side of the boundary; the numbers come from the same torch reductions as the reference."""
+        xs = inputs["x_enc"].detach()
+        if xs.ndim == 2:
+            xs = xs.unsqueeze(-1)
+        assert flags["input_stats_select"] == "all"
+
+        def fmt_list(v):
+            return "[" + ", ".join(v) + "]"
+
+        def fmt_float(v):
+            return fmt_list([fmt_float(u) for u in v]) if isinstance(v, list) else f"{v:.3f}"
+
+        def fmt_trend(v):
+            if v is True:
+                return "upward"
+            if v is False:
+                return "downward"
+            if isinstance(v, list):
+                return fmt_list([fmt_trend(u) for u in v])
+            return v
+
+        if flags["input_stats_dim"] == "all":
+            insert, s = "per feature", "s"
+        else:
+            d = flags["input_stats_dim"]
+            insert, s = f"feature {d}", ""
+            xs = xs[:, :, d]
+        with torch.no_grad():
+            mins = torch.min(xs, dim=1).values.tolist()
+            maxs = torch.max(xs, dim=1).values.tolist()
+            meds = torch.median(xs.float(), dim=1).values.tolist()
+            trends = (xs.diff(dim=1).sum(dim=1) > 0).tolist()
+            lags = _calcute_lags(xs.float(), self.n_lags).tolist()
+        return [
+            f"Input statistics ({insert}): min value{s} = {fmt_float(mins[b])}, max value{s} = {fmt_float(maxs[b])}, "
+            f"median value{s} = {fmt_float(meds[b])}, the trend of input is {fmt_trend(trends[b])}, "
+            f"the top {self.n_lags} lags are {lags[b]}."
+            for b in range(xs.size(0))
+        ]
+
+    def _tokenize_part(self, text: str) -> list[int]:
+        ids = self._prompt_cache.get(text)
+        if ids is None:
+            # same call as encode_text (models/medtsllm.py:300): default add_special_tokens
+            ids = list(self.tokenizer(text, padding=False, truncation=False).input_ids)
+            if len(self._prompt_cache) < 4096:
+                self._prompt_cache[text] = ids
+        return ids
+
+    def prompt_token_ids(self, inputs):
+        """Host token-id table [B, Lp] (int32, LEFT-padded with the pad id, models/medtsllm.py:304-311)."""
+        prompts = self.build_prompt(inputs)
+        per_sample = [[t for part in parts for t in self._tokenize_part(part)] for parts in prompts]
+        Lp = max((len(p) for p in per_sample), default=0)
+        pad = self.tokenizer.pad_token_id if self.tokenizer is not None else 0
+        table = torch.full((len(per_sample), Lp), pad if pad is not None else 0, dtype=torch.int32)
+        for b, ids in enumerate(per_sample):
+            if ids:
+                table[b, Lp - len(ids):] = torch.tensor(ids, dtype=torch.int32)
+        return table
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _bf16_weight(self, name: str, p: torch.Tensor) -> torch.Tensor:
+        """bf16 copy of a trainable fp32 master, re-cast (by our kernel) only when the optimizer has
+        changed it (`_version` bumps on every in-place update)."""
+        key = (p._version, p.data_ptr())
+        hit = self._w_cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        w = ops.cast_bf16(p.detach())
+        self._w_cache[name] = (key, w)
+        return w
+
+    def _source_kv(self):
+        """Prototype path (models/medtsllm.py:281, :574-575): source = W_map E + b; K = W_k source + b_k;
+        V^T = W_v source^T + b_v.  Batch independent -> cached until a contributing weight changes."""
+        rl = self.reprogramming_layer
+        plist = [self.mapping_layer.weight, self.mapping_layer.bias, rl.key_projection.weight,
+                 rl.key_projection.bias, rl.value_projection.weight, rl.value_projection.bias]
+        key = tuple((p._version, p.data_ptr()) for p in plist)
+        if self._src_cache is not None and self._src_cache[0] == key:
+            return self._src_cache[1:]
+        bb = self._backbone
+        S, D, HE, V = self.num_tokens, self.d_llm, self.d_ff * self.n_attention_heads, self.vocab_size
+        dev = self.device
+        w_map = self._bf16_weight("map", self.mapping_layer.weight)                       # [S, V]
+        source = torch.empty(S, D, device=dev, dtype=torch.bfloat16)
+        ops.gemm(w_map, bb.embed_t, source, m=S, n=D, k=V, bias=self.mapping_layer.bias.detach(), bias_axis=BIAS_M)
+        wk = self._bf16_weight("wk", rl.key_projection.weight)                            # [HE, D]
+        wv = self._bf16_weight("wv", rl.value_projection.weight)
+        K = torch.empty(S, HE, device=dev, dtype=torch.bfloat16)
+        ops.gemm(source, wk, K, m=S, n=HE, k=D, bias=rl.key_projection.bias.detach(), bias_axis=BIAS_N)
+        Vt = torch.empty(HE, S, device=dev, dtype=torch.bfloat16)                          # [H*E, S]
+        ops.gemm(wv, source, Vt, m=HE, n=S, k=D, bias=rl.value_projection.bias.detach(), bias_axis=BIAS_M)
+        self._src_cache = (key, source, K, Vt)
+        return source, K, Vt
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, inputs):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .train import forward_train  # autograd path (adapter gradients)
+            return forward_train(self, inputs)
+        return self.predict(inputs)
+
+    @torch.no_grad()
+    def predict(self, inputs):
+        """Inference path: models/medtsllm.py:321-384 + the eval-only activation of :248-261."""
+        x_enc = inputs["x_enc"]
+        if not x_enc.is_cuda:
+            raise MtsError("medtsllm_b200 runs on a CUDA device only (no CPU fallback)")
+        if self._backbone is None:
+            raise MtsError("model has not been moved to a CUDA device yet (call .to('cuda'))")
+        if self.device is None:
+            self.device = x_enc.device
+        if x_enc.ndim == 2:
+            x_enc = x_enc.unsqueeze(-1)
+        if x_enc.dtype != torch.float32:
+            raise MtsError(f"x_enc must be fp32 (setup.dtype 'mixed'/'float32'), got {x_enc.dtype}")
+        B, T, C = x_enc.shape
+        assert C == self.n_features and T == self.seq_len
+        bb = self._backbone
+        dev = x_enc.device
+        D, N, E, H = self.d_llm, self.n_patches, self.d_ff, self.n_attention_heads
+        HE = H * E
+        rl = self.reprogramming_layer
+
+        # K5: prompt ids (host) -> backbone input rows [0, Lp)
+        ids = self.prompt_token_ids(inputs)
+        Lp = ids.shape[1]
+        L = Lp + N
+        ids_dev = ids.to(dev, non_blocking=True) if Lp > 0 else None
+        X = torch.empty(B, L, D, device=dev, dtype=torch.float32)
+        ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=1, Lp=Lp, L=L)
+
+        # K1+K2: RevIN + patches + token conv (concat layout for multivariate)
+        concat = self.covariate_mode == "concat"
+        enc, _, mean, std = ops.revin_patch_embed(
+            x_enc, self.patch_embedding.value_embedding.tokenConv.weight.detach(), self.patch_len, self.stride,
+            concat=concat)
+        Bp = enc.shape[0]
+        assert enc.shape[1] == N and Bp == B
+
+        # K3/K4: reprogramming cross-attention on tcgen05 GEMMs
+        source, K, Vt = self._source_kv()
+        S = self.num_tokens
+        rows = Bp * N
+        wq = self._bf16_weight("wq", rl.query_projection.weight)
+        Q = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
+        ops.gemm(enc, wq, Q, m=rows, n=HE, k=self.d_model, bias=rl.query_projection.bias.detach(), bias_axis=BIAS_N)
+        scores = torch.empty(H, rows, S, device=dev, dtype=torch.float32)
+        ops.gemm(Q, K, scores, m=rows, n=S, k=E, batch=H, lda=HE, ldb=HE, a_bs=E, b_bs=E, d_bs=rows * S)
+        P = ops.softmax_rows(scores, 1.0 / math.sqrt(E))
+        O = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
+        ops.gemm(P, Vt, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
+        wo = self._bf16_weight("wo", rl.out_projection.weight)
+        ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=L * D, ldd=D, d_off=Lp * D,
+                 bias=rl.out_projection.bias.detach(), bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+
+        cap = self._capture
+        if cap is not None:
+            cap.update(revin_mean=mean.clone(), revin_stdev=std.clone(), patch_embedding=enc.clone(),
+                       source_embeddings=source.clone(), llm_input=X.clone())
+        # backbone
+        hid = bb.forward(X.view(Bp * L, D), Bp, L)                    # bf16 [Bp*L, D], final norm applied
+        if cap is not None:
+            cap["llm"] = hid.view(Bp, L, D).clone()
+
+        # K11: last N tokens -> Linear(D -> d_ff), stored transposed as [Bp, d_ff, N] (flatten index f*N+n)
+        wds = self._bf16_weight("wds", self.embedding_downsample_layer.weight)
+        flat = torch.empty(Bp, E * N, device=dev, dtype=torch.bfloat16)
+        ops.gemm(hid, wds, flat, m=N, n=E, k=D, batch=Bp, a_off=Lp * D, a_bs=L * D, b_bs=0, d_bs=E * N,
+                 d_transposed=True, ldd=N, bias=self.embedding_downsample_layer.bias.detach(), bias_axis=BIAS_N)
+        # K12: flatten head
+        wh = self._bf16_weight("wh", self.output_projection.linear.weight)
+        out = torch.empty(Bp, self.n_outputs, device=dev, dtype=torch.float32)
+        ops.gemm(flat, wh, out, m=Bp, n=self.n_outputs, k=E * N, bias=self.output_projection.linear.bias.detach(),
+                 bias_axis=BIAS_N)
+        if cap is not None:
+            cap["output_projection"] = out.clone()
+        out = out.view(B, self.pred_len, self.n_outputs_per_step)
+        if self.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
+            ops.revin_denorm(out, mean, std)
+        else:
+            out = out.squeeze(-1)
+        if not self.training:
+            if self.task == "semantic_segmentation":
+                if self.n_classes > 2:
+                    ops.softmax_lastdim_(out)
+                else:
+                    ops.sigmoid_(out)
+            elif self.task == "segmentation" and self.seg_mode == "boundary-prediction":
+                ops.sigmoid_(out)
+        return out
+
+
+def _calcute_lags(x, n_lags=5):
+    """models/medtsllm.py:530-538 (prompt text only)."""
+    x = x.permute(0, 2, 1).contiguous() if x.ndim == 3 else x.unsqueeze(1)
+    q_fft = torch.fft.rfft(x, dim=-1)
+    res = q_fft * torch.conj(q_fft)
+    corr = torch.fft.irfft(res, dim=-1)
+    mean_value = torch.mean(corr, dim=1)
+    _, lags = torch.topk(mean_value, n_lags, dim=-1)
+    return lags

@@ -17,7 +17,7 @@ from ._lib import (BIAS_M, BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_S
 __all__ = [
     "gemm", "linear_bf16", "revin_patch_embed", "patch_gather", "revin_patch_embed_bwd",
     "revin_denorm", "rmsnorm", "layernorm", "attn_causal", "softmax_rows", "prompt_gather",
-    "cast_bf16", "cast_f32", "transpose_to_bf16", "pack_gate_up", "swiglu",
+    "cast_bf16", "cast_f32", "transpose_to_bf16", "pack_gate_up", "swiglu", "sigmoid_", "softmax_lastdim_",
 ]
 
 
@@ -267,3 +267,20 @@ def swiglu(gu, I):
     out = torch.empty(*gu.shape[:-1], I, device=gu.device, dtype=torch.bfloat16)
     _lib.call("mts_swiglu", gu.data_ptr(), gu.shape[-1], out.data_ptr(), rows, I, _stream())
     return out
+
+
+def sigmoid_(y):
+    _chk(y, torch.float32, "y")
+    if not y.is_contiguous():
+        raise MtsError("sigmoid_ needs a contiguous tensor")
+    _lib.call("mts_sigmoid", y.data_ptr(), y.numel(), _stream())
+    return y
+
+
+def softmax_lastdim_(y):
+    _chk(y, torch.float32, "y")
+    if not y.is_contiguous():
+        raise MtsError("softmax_lastdim_ needs a contiguous tensor")
+    n = y.shape[-1]
+    _lib.call("mts_softmax_lastdim", y.data_ptr(), y.numel() // n, n, _stream())
+    return y

@@ -143,7 +143,10 @@ def build_llm_dir(kind: str, out_dir: Path, texts, *, seed: int = 0, **cfg):
         config = transformers.GPT2Config(
             vocab_size=cfg.get("vocab_size", 512), n_embd=cfg.get("hidden_size", 128),
             n_layer=cfg.get("layers", 2), n_head=cfg.get("heads", 2), n_positions=cfg.get("max_pos", 512),
-            bos_token_id=2, eos_token_id=2)
+            bos_token_id=2, eos_token_id=2,
+            # the real checkpoints carry 0.1 dropouts that stay LIVE in the reference's train mode
+            # (model.train() flips the frozen backbone too); fixtures need a deterministic train pass
+            attn_pdrop=cfg.get("pdrop", 0.0), embd_pdrop=cfg.get("pdrop", 0.0), resid_pdrop=cfg.get("pdrop", 0.0))
         model = transformers.GPT2Model(config)
     else:
         raise ValueError(kind)

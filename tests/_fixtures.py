@@ -1,0 +1,110 @@
+"""Helpers shared by the parity tests: load a golden fixture (tests/golden/*.pt, produced by
+oracle/make_golden.py from the unmodified reference), rebuild its HF backbone directory, and run the
+oracle restatement on it."""
+from __future__ import annotations
+
+import copy
+import sys
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+GOLDEN = REPO / "tests" / "golden"
+for p in (REPO, REPO / "med-ts-llm_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+CASES = ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate", "llama_forecast_clip_stats"]
+
+
+def load_case(name: str) -> dict:
+    return torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+
+
+class Dataset:
+    def __init__(self, d):
+        self.n_features = d["n_features"]
+        self.n_classes = d["n_classes"]
+        self.description = d["description"]
+        self.task_description = None
+
+
+def hf_model_from_fixture(fix):
+    import transformers
+    cfg_dict = dict(fix["hf_config"])
+    cfg_dict.pop("model_type", None)
+    cfg_dict.pop("transformers_version", None)
+    if fix["kind"] == "llama":
+        config = transformers.LlamaConfig(**cfg_dict)
+        model = transformers.LlamaModel(config)
+    else:
+        config = transformers.GPT2Config(**cfg_dict)
+        model = transformers.GPT2Model(config)
+    missing = model.load_state_dict({k: v.float() for k, v in fix["backbone_state"].items()}, strict=False)
+    assert not missing.unexpected_keys, missing
+    return model.eval()
+
+
+def materialize_llm_dir(fix, path: Path) -> Path:
+    """Writes config + weights + tokenizer so that AutoModel/AutoTokenizer load it like a checkpoint."""
+    from tokenizers import Tokenizer
+    from transformers import PreTrainedTokenizerFast
+    path.mkdir(parents=True, exist_ok=True)
+    hf_model_from_fixture(fix).save_pretrained(str(path))
+    tok = Tokenizer.from_str(fix["tokenizer_json"])
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="<unk>",
+                                   bos_token="<s>" if fix["tokenizer_bos"] else None, eos_token="</s>")
+    fast.save_pretrained(str(path))
+    return path
+
+
+def config_for(fix, llm_dir):
+    cfg = copy.deepcopy(fix["config"])
+    cfg["models"]["medtsllm"]["llm"]["llm"] = str(llm_dir)
+    return cfg
+
+
+class Cfg(dict):
+    """Minimal attribute-dict with the surface of the reference's dict_to_object (utils.py:19-39)."""
+
+    def __init__(self, d):
+        super().__init__({k: Cfg(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def oracle_spec(fix) -> dict:
+    cfg = fix["config"]
+    mc = cfg["models"]["medtsllm"]
+    hc = fix["hf_config"]
+    task = cfg["task"]
+    C = fix["dataset"]["n_features"]
+    ncls = fix["dataset"]["n_classes"] if task == "semantic_segmentation" else 0
+    if task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
+        nops = C
+    elif task == "semantic_segmentation":
+        nops = ncls if ncls > 2 else 1
+    else:
+        nops = 1
+    llama = fix["kind"] == "llama"
+    return dict(
+        task=task, pred_len=cfg["pred_len"], patch_len=mc["patching"]["patch_len"], stride=mc["patching"]["stride"],
+        d_model=mc["d_model"], d_ff=mc["d_ff"], n_heads=mc["n_heads"], covariate_mode=mc["covariate_mode"],
+        downsample=mc["embedding_downsample_mode"], n_outputs_per_step=nops, backbone=fix["kind"],
+        n_layers=hc["num_hidden_layers"] if llama else hc["n_layer"],
+        llm_heads=hc["num_attention_heads"] if llama else hc["n_head"],
+        eps=hc["rms_norm_eps"] if llama else hc["layer_norm_epsilon"],
+        rope_theta=(hc.get("rope_parameters") or {}).get("rope_theta", 10000.0) if llama else None,
+        pad_id=fix["pad_id"], seg_mode=cfg["tasks"]["segmentation"]["mode"], n_classes=ncls)
+
+
+def run_oracle(fix, training=False, prompt_ids=None):
+    from oracle import medtsllm_oracle as O
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    return O.medtsllm_forward(fix["inputs"]["x_enc"], prompt_ids or fix["prompt_ids"], fix["adapters"], sd,
+                              oracle_spec(fix), training=training, return_stages=True)

@@ -19,3 +19,15 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The tests exercise the in-tree libmtsb200.so; (re)build it when sources changed and nvcc exists."""
+    from medtsllm_b200 import _build
+    try:
+        _build.build(verbose=False)
+    except RuntimeError as e:
+        if "nvcc not found" in str(e) and _build.LIB_PATH.exists():
+            return
+        raise

@@ -1,0 +1,87 @@
+"""CPU-only tests of the host side of the boundary: the C ABI surface, the drop-in class surface
+(constructor, state_dict keys, prompt building/tokenisation) and loud failure without a GPU."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from _fixtures import CASES, Cfg, Dataset, config_for, load_case, materialize_llm_dir
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from medtsllm_b200 import _lib
+    header = (REPO / "include" / "mts_b200.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|const char\*|int64_t)\s+(mts_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared, "no prototypes parsed"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/mts_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.version() == 1
+    assert ctypes.sizeof(_lib.GemmArgs) == 120      # layout of mts_gemm_args (8-byte aligned)
+
+
+def test_no_cpu_fallback():
+    from medtsllm_b200 import MtsError, ops
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(MtsError):
+        ops.gemm(a, a, a, m=8, n=8, k=8)
+    with pytest.raises(MtsError):
+        ops.rmsnorm(torch.zeros(2, 8), torch.ones(8), 1e-5)
+    if not torch.cuda.is_available():
+        # with valid-looking arguments but no device the library itself must refuse
+        from medtsllm_b200 import _lib
+        with pytest.raises(MtsError):
+            _lib.call("mts_cast_f32_bf16", 16, 32, 8, None)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dropin_surface_and_prompts(name, tmp_path):
+    from medtsllm_b200 import MtsError
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    # checkpoint contract: exactly the reference's adapter keys, same shapes
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(fix["adapters"].keys())
+    for k, v in fix["adapters"].items():
+        assert sd[k].shape == v.shape, k
+    res = model.load_state_dict(fix["adapters"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert trainable == set(fix["adapters"].keys())
+    assert "forecasting" in model.supported_tasks and model.lora_enabled is False
+    # prompt text + tokenisation identical to the reference's (models/medtsllm.py:386-439, :299-302)
+    inputs = dict(fix["inputs"])
+    assert model.build_prompt(inputs) == fix["prompts"]
+    table = model.prompt_token_ids(inputs)
+    Lp = max(len(p) for p in fix["prompt_ids"])
+    assert table.shape == (len(fix["prompt_ids"]), Lp) and table.dtype == torch.int32
+    for b, ids in enumerate(fix["prompt_ids"]):
+        assert table[b, Lp - len(ids):].tolist() == ids
+        assert all(t == fix["pad_id"] for t in table[b, : Lp - len(ids)].tolist())
+    # load_pretrained drops the head (models/medtsllm.py:515-527)
+    loaded = model.load_pretrained(dict(fix["adapters"]))
+    assert "output_projection.linear.weight" not in loaded and "mapping_layer.weight" in loaded
+    # no silent CPU path
+    with pytest.raises(MtsError):
+        model.eval()(inputs)
+
+
+def test_unsupported_options_fail_loudly(tmp_path):
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case("llama_seg_concat")
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["covariate_mode"] = "interleave"
+    with pytest.raises(NotImplementedError):
+        MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16}
+    with pytest.raises(NotImplementedError):
+        MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
