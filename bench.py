@@ -165,6 +165,14 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.profile_step:
+        # for `ncu --profile-from-start off`: exactly one warm step between cudaProfilerStart/Stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -356,6 +364,7 @@ def main():
     ap.add_argument("--workload", default="bidmc_llama2_7b")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

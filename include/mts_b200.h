@@ -110,12 +110,14 @@ int mts_revin_denorm(float* y, const float* mean, const float* stdev, int B, int
  *
  * A, B: bf16.  TMA-staged 128B-swizzled shared-memory tiles (BLOCK_M=128, BLOCK_K=64, BLOCK_N in
  * {64,128,256}), tcgen05.mma kind::f16 into fp32 TMEM accumulators (double-buffered), persistent
- * over min(tiles, SMs) CTAs.  Requirements: lda, ldb multiples of 8; a, b 16-byte aligned;
- * k >= 1; batch strides multiples of 8 (or 0 = the operand is shared by all batches).
+ * over min(tiles, SMs) CTAs.  Requirements: lda, ldb multiples of 8 (k itself may be anything: the
+ * TMA zero-fills past k); a, b 16-byte aligned; k >= 1; batch strides multiples of 8 (or 0 = the
+ * operand is shared by all batches).  D rows that are 16-byte aligned get vector stores, others a
+ * scalar epilogue.
  */
 typedef enum mts_epilogue {
   MTS_EPI_STORE = 0,     /* D = v                      (D bf16 or fp32)                          */
-  MTS_EPI_RESID_ADD = 1, /* D += v                     (D fp32, read-modify-write: residual)     */
+  MTS_EPI_RESID_ADD = 1, /* D = C + v                  (D, C fp32; C = D when args.c is NULL)     */
   MTS_EPI_GELU_NEW = 2,  /* D = gelu_new(v)            (D bf16; HF:activations.py:59-66)         */
   MTS_EPI_SWIGLU = 3     /* D[:, j] = silu(v_gate[j]) * v_up[j]   (D bf16, n/2 columns).  B rows  */
                          /* must be packed by mts_pack_gate_up: blocks of 128 gate rows followed  */
@@ -129,6 +131,7 @@ typedef struct mts_gemm_args {
   const void* b;     /* bf16 [batch][n][k]                                                        */
   void* d;           /* [batch][m][n'] (n' = n, or n/2 for SWIGLU); or [batch][n][m] if d_transposed */
   const float* bias; /* fp32 [n] (MTS_BIAS_N) or [m] (MTS_BIAS_M) or NULL                         */
+  const float* c;    /* RESID_ADD only: D = C + v with C laid out like D; NULL = in place (C = D)  */
   int64_t lda, ldb, ldd;
   int64_t a_batch_stride, b_batch_stride, d_batch_stride;
   int32_t m, n, k, batch;
@@ -204,6 +207,55 @@ int mts_swiglu(const uint16_t* gu, int64_t ldgu, uint16_t* y, int64_t rows, int 
  *   sigmoid (binary semantic segmentation / boundary prediction), softmax over n classes. */
 int mts_sigmoid(float* y, int64_t n, mts_stream_t stream);
 int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Training path (adapter gradients; dgrad through the frozen backbone)                        */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference trains patch-embedding, mapping, reprogramming, down-sample and head parameters
+ * (all 13-15 adapter tensors; the backbone is frozen, models/medtsllm.py:231-233), so loss.backward()
+ * (tasks/forecasting.py:26) flows through every frozen block.  GEMM-shaped pieces of the backward
+ * are mts_gemm on transposed operands; the kernels below are the rest.                           */
+
+/* dx (+)= d(RMSNorm)/dx^T (w*dy) and the LayerNorm analogue; x fp32 [rows, ldx], dy bf16 [rows, D],
+ * dx fp32 [rows, D]; accumulate != 0 adds into dx (residual-stream gradient). */
+int mts_rmsnorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy, float* dx,
+                    int rows, int D, float eps, int accumulate, mts_stream_t stream);
+int mts_layernorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy, float* dx,
+                      int rows, int D, float eps, int accumulate, mts_stream_t stream);
+
+/* Causal attention backward (ref: autograd of HF eager attention, HF:models/llama/modeling_llama.py:
+ * 199-221).  qkv/out/lse as produced by mts_attn_causal; dout bf16 [Bp*L, H*hd]; delta fp32 [Bp,H,L]
+ * workspace; dqkv bf16 [Bp*L, 3*H*hd] receives d(q|k|v) w.r.t. the (un-rotated) projection outputs. */
+int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                        const uint16_t* out, const uint16_t* dout, const float* lse, float* delta,
+                        uint16_t* dqkv, int Bp, int L, int H, int hd, float scale, mts_stream_t stream);
+
+/* SwiGLU on saved pre-activations.  Activation column j reads gate column (j/blk)*2*blk + j%blk and
+ * the up column blk further: blk = 128 for the packed layout (mts_pack_gate_up), blk = I for [g|u].
+ *   gu, dgu bf16 [rows, ld];  y, dact bf16 [rows, I] */
+int mts_swiglu_blk(const uint16_t* gu, int64_t ld, uint16_t* y, int64_t rows, int I, int blk,
+                   mts_stream_t stream);
+int mts_swiglu_bwd(const uint16_t* gu, int64_t ld, const uint16_t* dact, uint16_t* dgu, int64_t rows,
+                   int I, int blk, mts_stream_t stream);
+/* dact == NULL: out = gelu_new(pre); else out = dact * gelu_new'(pre)   (bf16, n even) */
+int mts_gelu_new(const uint16_t* pre, const uint16_t* dact, uint16_t* out, int64_t n,
+                 mts_stream_t stream);
+/* ds = scale * p * (dp - rowsum(dp*p));  p bf16, dp fp32, ds bf16, all [rows, n] */
+int mts_softmax_bwd_rows(const uint16_t* p, const float* dp, uint16_t* ds, int64_t rows, int n,
+                         float scale, mts_stream_t stream);
+/* out[c] = sum_r x[r*ld + c]  (bias gradients); dtype: mts_dtype of x */
+int mts_colsum(const void* x, int dtype, int64_t ld, float* out, int rows, int cols,
+               mts_stream_t stream);
+/* out[c*ld_out + b*rows + r] = bf16(in[b*in_batch_stride + r*ld_in + c]); dtype: mts_dtype of in */
+int mts_transpose_strided(const void* in, int dtype, int64_t ld_in, int64_t in_batch_stride,
+                          uint16_t* out, int64_t ld_out, int batch, int rows, int cols,
+                          mts_stream_t stream);
+/* out[(b*rows + r)*ld_out + c] = bf16(in[b*in_batch_stride + r*ld_in + c]) */
+int mts_cast_rows_f32_bf16(const float* in, int64_t ld_in, int64_t in_batch_stride, uint16_t* out,
+                           int64_t ld_out, int batch, int rows, int cols, mts_stream_t stream);
+/* out = dy * stdev[b,c]  (backward of RevIN denorm; statistics are detached, RevIN.py:42-43) */
+int mts_revin_denorm_bwd(const float* dy, const float* stdev, float* out, int B, int T, int C,
+                         mts_stream_t stream);
 
 #ifdef __cplusplus
 }

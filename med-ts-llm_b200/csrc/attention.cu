@@ -248,6 +248,300 @@ static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, ui
   return check_launch("attn_causal_fwd_kernel");
 }
 
+
+// =============================================================================================
+// Backward (training path: gradients flow through the frozen backbone to the adapters in front of
+// it).  Two kernels, both recomputing S = QK^T from the saved qkv and the forward's log-sum-exp, so
+// that neither needs atomics (deterministic):
+//   attn_bwd_dq_kernel   one CTA per (b, h, 64 queries): dQ = sum_k dS K
+//   attn_bwd_dkv_kernel  one CTA per (b, h, 64 keys):    dK = sum_q dS^T Q,  dV = sum_q P^T dO
+// with P = exp(S*scale - lse), dS = P * (dP - delta) * scale, dP = dO V^T, delta = rowsum(dO * O).
+// RoPE: q/k are rotated while staging exactly as in the forward; dQ/dK are rotated back on store.
+// =============================================================================================
+
+__global__ void __launch_bounds__(256)
+attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                      float* __restrict__ delta, int L, int H, int hd, int64_t total) {
+  // one warp per (b, l, h); delta laid out [b, h, l]
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int h = (int)(wid % H);
+  const int64_t bl = wid / H;
+  const int l = (int)(bl % L);
+  const int64_t b = bl / L;
+  const __nv_bfloat16* op = o + (bl * H + h) * hd;
+  const __nv_bfloat16* dp = dout + (bl * H + h) * hd;
+  float acc = 0.f;
+  for (int i = lane * 2; i < hd; i += 64) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(op + i);
+    const uint32_t d = *reinterpret_cast<const uint32_t*>(dp + i);
+    acc += bf16_lo(a) * bf16_lo(d) + bf16_hi(a) * bf16_hi(d);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) delta[(b * H + h) * L + l] = acc;
+}
+
+// C(16 x 64) = A(16 x HD, rows [arow0, +16) of As) * B^T, B = 64 rows of Bs (both [row][HD+8] bf16)
+template <int HD>
+__device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* As, int arow0,
+                                         const __nv_bfloat16* Bs, int lane) {
+  constexpr int kPitch = HD + 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    ldmatrix_x4(smem_u32(As + (arow0 + (lane & 15)) * kPitch + ks * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const int id = lane >> 3;
+      uint32_t r0, r1, r2, r3;
+      ldmatrix_x4(smem_u32(Bs + (np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch + ks * 16 + (id & 1) * 8),
+                  r0, r1, r2, r3);
+      mma_bf16_16816(c[2 * np], a, r0, r1);
+      mma_bf16_16816(c[2 * np + 1], a, r2, r3);
+    }
+  }
+}
+
+// acc(16 x HD) += P(16 x 64, fp32 C-fragments) * B, B = 64 rows of Bs ([row][HD+8] bf16)
+template <int HD>
+__device__ __forceinline__ void mma_p_b(float (&acc)[HD / 8][4], const float (&pm)[8][4],
+                                        const __nv_bfloat16* Bs, int lane) {
+  constexpr int kPitch = HD + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16(pm[2 * kk][0], pm[2 * kk][1]);
+    pa[1] = pack_bf16(pm[2 * kk][2], pm[2 * kk][3]);
+    pa[2] = pack_bf16(pm[2 * kk + 1][0], pm[2 * kk + 1][1]);
+    pa[3] = pack_bf16(pm[2 * kk + 1][2], pm[2 * kk + 1][3]);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      const int id = lane >> 3;
+      uint32_t r0, r1, r2, r3;
+      ldmatrix_x4_trans(smem_u32(Bs + (kk * 16 + (id & 1) * 8 + (lane & 7)) * kPitch + np * 16 + (id >> 1) * 8),
+                        r0, r1, r2, r3);
+      mma_bf16_16816(acc[2 * np], pa, r0, r1);
+      mma_bf16_16816(acc[2 * np + 1], pa, r2, r3);
+    }
+  }
+}
+
+// Rotate a gradient w.r.t. rotated q/k back to the un-rotated projection output and store it (bf16).
+template <int HD>
+__device__ __forceinline__ void store_grad_rows(float (&acc)[HD / 8][4], __nv_bfloat16* dst, int64_t ld,
+                                                int row_a, int row_b, int L, int tq,
+                                                const float* __restrict__ cosb, const float* __restrict__ sinb) {
+  constexpr int kHalfTiles = HD / 16;
+  if (cosb != nullptr) {
+#pragma unroll
+    for (int nt = 0; nt < kHalfTiles; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = (e < 2) ? row_a : row_b;
+        if (row < L) {
+          const int j = nt * 8 + tq * 2 + (e & 1);
+          const float c = cosb[(int64_t)row * (HD / 2) + j], s = sinb[(int64_t)row * (HD / 2) + j];
+          const float lo = acc[nt][e], hi = acc[nt + kHalfTiles][e];
+          acc[nt][e] = lo * c + hi * s;
+          acc[nt + kHalfTiles][e] = hi * c - lo * s;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt) {
+    const int col = nt * 8 + tq * 2;
+    if (row_a < L) *reinterpret_cast<uint32_t*>(dst + (int64_t)row_a * ld + col) = pack_bf16(acc[nt][0], acc[nt][1]);
+    if (row_b < L) *reinterpret_cast<uint32_t*>(dst + (int64_t)row_b * ld + col) = pack_bf16(acc[nt][2], acc[nt][3]);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                   const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, const float* __restrict__ delta,
+                   __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* dOs = Qs + 64 * kPitch;
+  __nv_bfloat16* Ks = dOs + 64 * kPitch;
+  __nv_bfloat16* Vs = Ks + 64 * kPitch;
+
+  const int n_qblk = (L + kAttnBlockQ - 1) / kAttnBlockQ;
+  const int bh = blockIdx.x / n_qblk;
+  const int q0 = (blockIdx.x - bh * n_qblk) * kAttnBlockQ;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
+  const bool rope = rope_cos != nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+
+  if (rope) stage_tile<HD, true>(Qs, qbase, ld, q0, L, rope_cos, rope_sin);
+  else      stage_tile<HD, false>(Qs, qbase, ld, q0, L, nullptr, nullptr);
+  stage_tile<HD, false>(dOs, dobase, D, q0, L, nullptr, nullptr);
+
+  const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
+  const float lse_a = row_a < L ? lse[(int64_t)bh * L + row_a] * 1.4426950408889634f : INFINITY;
+  const float lse_b = row_b < L ? lse[(int64_t)bh * L + row_b] * 1.4426950408889634f : INFINITY;
+  const float del_a = row_a < L ? delta[(int64_t)bh * L + row_a] : 0.f;
+  const float del_b = row_b < L ? delta[(int64_t)bh * L + row_b] : 0.f;
+
+  float dq[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+
+  const int kv_end = min(L, q0 + kAttnBlockQ);
+  for (int j0 = 0; j0 < kv_end; j0 += kAttnBlockKV) {
+    __syncthreads();
+    if (rope) stage_tile<HD, true>(Ks, kbase, ld, j0, L, rope_cos, rope_sin);
+    else      stage_tile<HD, false>(Ks, kbase, ld, j0, L, nullptr, nullptr);
+    stage_tile<HD, false>(Vs, vbase, ld, j0, L, nullptr, nullptr);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    mma_a_bt<HD>(s, Qs, warp * 16, Ks, lane);
+    mma_a_bt<HD>(dp, dOs, warp * 16, Vs, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+        const int row = (e < 2) ? row_a : row_b;
+        const float pv = (col > row || col >= L) ? 0.f : exp2f(s[nt][e] * scale_log2e - ((e < 2) ? lse_a : lse_b));
+        s[nt][e] = pv * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * scale;   // dS
+      }
+    }
+    mma_p_b<HD>(dq, s, Ks, lane);
+  }
+  store_grad_rows<HD>(dq, dqkv + (int64_t)b * L * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq,
+                      rope ? rope_cos : nullptr, rope_sin);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                    const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
+                    const float* __restrict__ lse, const float* __restrict__ delta,
+                    __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Vs = Ks + 64 * kPitch;
+  __nv_bfloat16* Qs = Vs + 64 * kPitch;
+  __nv_bfloat16* dOs = Qs + 64 * kPitch;
+  float* lse_s = reinterpret_cast<float*>(dOs + 64 * kPitch);
+  float* del_s = lse_s + 64;
+
+  const int n_kblk = (L + kAttnBlockKV - 1) / kAttnBlockKV;
+  const int bh = blockIdx.x / n_kblk;
+  const int j0 = (blockIdx.x - bh * n_kblk) * kAttnBlockKV;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
+  const bool rope = rope_cos != nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+
+  if (rope) stage_tile<HD, true>(Ks, kbase, ld, j0, L, rope_cos, rope_sin);
+  else      stage_tile<HD, false>(Ks, kbase, ld, j0, L, nullptr, nullptr);
+  stage_tile<HD, false>(Vs, vbase, ld, j0, L, nullptr, nullptr);
+
+  const int key_a = j0 + warp * 16 + g, key_b = key_a + 8;   // this thread's two key rows
+  float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+
+  // causal: only query blocks at or after this key block contribute
+  for (int i0 = j0; i0 < L; i0 += kAttnBlockQ) {
+    __syncthreads();
+    if (rope) stage_tile<HD, true>(Qs, qbase, ld, i0, L, rope_cos, rope_sin);
+    else      stage_tile<HD, false>(Qs, qbase, ld, i0, L, nullptr, nullptr);
+    stage_tile<HD, false>(dOs, dobase, D, i0, L, nullptr, nullptr);
+    if (threadIdx.x < 64) {
+      const int r = i0 + threadIdx.x;
+      lse_s[threadIdx.x] = r < L ? lse[(int64_t)bh * L + r] * 1.4426950408889634f : INFINITY;
+      del_s[threadIdx.x] = r < L ? delta[(int64_t)bh * L + r] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];              // rows = keys, cols = queries
+    mma_a_bt<HD>(st, Ks, warp * 16, Qs, lane);
+    mma_a_bt<HD>(dpt, Vs, warp * 16, dOs, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = nt * 8 + tq * 2 + (e & 1);       // query index inside the tile
+        const int qrow = i0 + qi;
+        const int key = (e < 2) ? key_a : key_b;
+        const float pv = (key > qrow || key >= L || qrow >= L) ? 0.f
+                                                               : exp2f(st[nt][e] * scale_log2e - lse_s[qi]);
+        st[nt][e] = pv;                                              // P^T
+        dpt[nt][e] = pv * (dpt[nt][e] - del_s[qi]) * scale;          // dS^T
+      }
+    }
+    mma_p_b<HD>(dv, st, dOs, lane);
+    mma_p_b<HD>(dk, dpt, Qs, lane);
+  }
+  __nv_bfloat16* dbase = dqkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, L, tq, rope ? rope_cos : nullptr, rope_sin);
+  store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, L, tq, nullptr, nullptr);
+}
+
+template <int HD>
+static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
+                           const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp,
+                           int L, int H, float scale, cudaStream_t stream) {
+  constexpr int kSmemQ = 4 * 64 * (HD + 8) * 2;
+  constexpr int kSmemKV = kSmemQ + 2 * 64 * 4;
+  auto kq = attn_bwd_dq_kernel<HD>;
+  auto kkv = attn_bwd_dkv_kernel<HD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQ);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKV);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd)", e);
+    attr_done = true;
+  }
+  const int64_t nwarps = (int64_t)Bp * L * H;
+  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, L, H, HD, nwarps);
+  count_launch();
+  int rc_ = check_launch("attn_bwd_delta_kernel");
+  if (rc_) return rc_;
+  const int64_t grid_l = (int64_t)((L + 63) / 64) * Bp * H;
+  if (grid_l > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: grid too large");
+  kq<<<(int)grid_l, kAttnThreads, kSmemQ, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+  count_launch();
+  rc_ = check_launch("attn_bwd_dq_kernel");
+  if (rc_) return rc_;
+  kkv<<<(int)grid_l, kAttnThreads, kSmemKV, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+  count_launch();
+  return check_launch("attn_bwd_dkv_kernel");
+}
+
 }  // namespace mts
 
 using namespace mts;
@@ -266,5 +560,23 @@ extern "C" int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const
     case 64: return launch_attn<64>(qkv, rope_cos, rope_sin, out, lse, Bp, L, H, scale, (cudaStream_t)s);
     case 128: return launch_attn<128>(qkv, rope_cos, rope_sin, out, lse, Bp, L, H, scale, (cudaStream_t)s);
     default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal: head dim %d (supported: 64, 128)", hd);
+  }
+}
+
+extern "C" int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                                   const uint16_t* out, const uint16_t* dout, const float* lse,
+                                   float* delta, uint16_t* dqkv, int Bp, int L, int H, int hd,
+                                   float scale, mts_stream_t s) {
+  if (!qkv || !out || !dout || !lse || !delta || !dqkv || Bp <= 0 || L <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: bad args");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: rope_cos and rope_sin go together");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: misaligned pointer");
+  switch (hd) {
+    case 64: return launch_attn_bwd<64>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, (cudaStream_t)s);
+    case 128: return launch_attn_bwd<128>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, (cudaStream_t)s);
+    default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_bwd: head dim %d (supported: 64, 128)", hd);
   }
 }

@@ -23,6 +23,7 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 192;
 constexpr int kNumEpiThreads = 128;
+constexpr int kEpiPitch = 36;  // floats per staged row (144 B: 16-byte aligned, bank-conflict free)
 
 template <int BN>
 struct GemmCfg {
@@ -33,7 +34,8 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: all powers of two >= 32
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+  static constexpr int kEpiStageBytes = 4 * 32 * kEpiPitch * 4;  // per-epilogue-warp 32x32 fp32 tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kEpiStageBytes + 1024;
 };
 
 struct GemmParams {
@@ -42,16 +44,33 @@ struct GemmParams {
   int64_t ldd, d_batch_stride;
   int m, n, k, batch;
   int a_batched, b_batched;  // 0: operand shared by all batches
-  int bias_axis, d_transposed, d_is_f32;
+  int bias_axis, d_transposed, d_is_f32, bias_vec, vec_ok;
+  const float* c;  // RESID_ADD: residual source, same layout as d
   float alpha;
 };
 
 __device__ __forceinline__ float gelu_new_f(float x) {
   // HF:activations.py:65-66  0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));  // |err| ~ 2^-11: below the bf16 output rounding
+  return 0.5f * x * (1.0f + t);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// Tile order inside one batch: groups of kGroupM row-blocks, m fastest inside a group.  The ~148
+// tiles in flight then form a roughly square patch (12 x 12 blocks) of the output, so a wave streams
+// ~24 operand strips from L2/HBM instead of 48 + 3 with a plain m-fastest order.
+constexpr int kGroupM = 12;
+__device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * n_blocks;
+  const int group = t / per_group;
+  const int first_m = group * kGroupM;
+  const int gsize = min(kGroupM, m_blocks - first_m);
+  const int r = t - group * per_group;
+  n_blk = r / gsize;
+  m_blk = first_m + (r - n_blk * gsize);
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -71,6 +90,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + Cfg::kBarrierBytes;  // 16-byte aligned
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -112,8 +132,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
-        const int n_blk = t / m_blocks;  // m fastest: CTAs running together share the B tile
-        const int m_blk = t - n_blk * m_blocks;
+        int m_blk, n_blk;
+        tile_coords(t, m_blocks, n_blocks, m_blk, n_blk);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -156,91 +176,75 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..5
+    // TMEM -> registers (thread = accumulator row, 32 columns) -> per-warp padded smem tile ->
+    // coalesced 16-byte global accesses (a quarter-warp covers one contiguous 128-byte row piece).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row_in_tile = quarter * 32 + lane;
+    float* stage_buf = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) +
+                       quarter * (32 * kEpiPitch);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / tiles_per_batch;
       const int t = tile - b * tiles_per_batch;
-      const int n_blk = t / m_blocks;
-      const int m_blk = t - n_blk * m_blocks;
+      int m_blk, n_blk;
+      tile_coords(t, m_blocks, n_blocks, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
 
-      const int row = m_blk * kBlockM + row_in_tile;
-      const bool row_ok = row < p.m;
+      const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
+      const int row = row0 + lane;                       // the accumulator row this thread reads
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      const float bias_m = (p.bias_axis == 2 && row_ok) ? p.bias[row] : 0.0f;
+      const float bias_m = (p.bias_axis == 2 && row < p.m) ? p.bias[row] : 0.0f;
 
-      if constexpr (EPI == MTS_EPI_SWIGLU) {
-        // columns [0,BN/2) of the tile are gate, [BN/2,BN) the matching up projections
-        constexpr int kHalf = BN / 2;
-        __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride +
-                              (int64_t)row * p.ldd;
-        const int n_out = p.n / 2;
+      constexpr int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : BN / 32;
+      const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
 #pragma unroll 1
-        for (int c = 0; c < kHalf; c += 32) {
+      for (int ci = 0; ci < kChunks; ++ci) {
+        float v[32];
+        int col0;  // first output column of this chunk
+        __syncwarp();  // tcgen05.ld is .sync.aligned; also orders the previous chunk's smem reads
+        if constexpr (EPI == MTS_EPI_SWIGLU) {
+          // columns [0,BN/2) of the tile are gate, [BN/2,BN) the matching up projections
           uint32_t g[32], u[32];
-          __syncwarp();
-          tmem_ld_32x32(taddr + c, g);
-          tmem_ld_32x32(taddr + kHalf + c, u);
+          tmem_ld_32x32(taddr + ci * 32, g);
+          tmem_ld_32x32(taddr + BN / 2 + ci * 32, u);
           tmem_ld_wait();
-          const int col0 = n_blk * kHalf + c;
-          if (row_ok) {
+          col0 = n_blk * (BN / 2) + ci * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < n_out) {
-                uint32_t o[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float g0 = __uint_as_float(g[j + 2 * q]) * p.alpha;
-                  const float g1 = __uint_as_float(g[j + 2 * q + 1]) * p.alpha;
-                  const float u0 = __uint_as_float(u[j + 2 * q]) * p.alpha;
-                  const float u1 = __uint_as_float(u[j + 2 * q + 1]) * p.alpha;
-                  o[q] = pack_bf16(silu_f(g0) * u0, silu_f(g1) * u1);
-                }
-                *reinterpret_cast<uint4*>(dptr + col0 + j) = make_uint4(o[0], o[1], o[2], o[3]);
-              }
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+          for (int j = 0; j < 32; ++j)
+            v[j] = silu_f(__uint_as_float(g[j]) * p.alpha) * (__uint_as_float(u[j]) * p.alpha);
+        } else {
           uint32_t r[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_32x32(taddr + ci * 32, r);
           tmem_ld_wait();
-          const int col0 = n_blk * BN + c;
-          if (row_ok && col0 < p.n) {
-          float v[32];
+          col0 = n_blk * BN + ci * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_m;
-          if (p.bias_axis == 1) {
+          if (p.bias_axis == 1 && col0 < p.n) {
+            if (p.bias_vec && col0 + 32 <= p.n) {  // warp-uniform 16-byte loads (broadcast)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
+            }
           }
           if constexpr (EPI == MTS_EPI_GELU_NEW) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
           }
-          if constexpr (EPI == MTS_EPI_RESID_ADD) {
-            float* dptr = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride +
-                          (int64_t)row * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.n) {  // n % 4 == 0 enforced on the host
-                float4 o = *reinterpret_cast<const float4*>(dptr + j);
-                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                *reinterpret_cast<float4*>(dptr + j) = o;
-              }
-            }
-          } else if (p.d_transposed) {
-            // element (row, col) -> d[col*ldd + row]; small matrices only (head staging)
+        }
+        if (col0 >= n_store) continue;  // warp-uniform
+
+        if (EPI == MTS_EPI_STORE && p.d_transposed) {
+          // element (row, col) -> d[col*ldd + row]: lanes (= rows) are contiguous in memory
+          if (row < p.m) {
             if (p.d_is_f32) {
               float* dptr = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride + row;
 #pragma unroll
@@ -253,27 +257,84 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n) dptr[(int64_t)(col0 + j) * p.ldd] = __float2bfloat16_rn(v[j]);
             }
-          } else if (p.d_is_f32) {
-            float* dptr = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride +
-                          (int64_t)row * p.ldd + col0;
+          }
+          continue;
+        }
+
+        // stage the 32x32 chunk: thread `lane` owns row `lane` (pitch 36 floats: 16-byte aligned
+        // rows, conflict-free for both the 128-bit writes here and the 128-bit reads below)
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.n)
-                *reinterpret_cast<float4*>(dptr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-            __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.d) +
-                                  (int64_t)b * p.d_batch_stride + (int64_t)row * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.n) {  // n % 8 == 0 enforced on the host
-                *reinterpret_cast<uint4*>(dptr + j) =
-                    make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                               pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
+              make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+
+        if (!p.vec_ok) {
+          // rows of D are not 16-byte aligned (odd n / ldd): scalar, still row-contiguous per lane
+#pragma unroll 1
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r_g = row0 + rr;
+            const int col = col0 + lane;
+            if (r_g < p.m && col < n_store) {
+              const int64_t off = (int64_t)b * p.d_batch_stride + (int64_t)r_g * p.ldd + col;
+              float val = stage_buf[rr * kEpiPitch + lane];
+              if (p.d_is_f32) {
+                if constexpr (EPI == MTS_EPI_RESID_ADD) val += p.c[off];
+                reinterpret_cast<float*>(p.d)[off] = val;
+              } else {
+                reinterpret_cast<__nv_bfloat16*>(p.d)[off] = __float2bfloat16_rn(val);
               }
             }
           }
-          }  // row_ok && col0 < n
+        } else if (p.d_is_f32) {
+          // 8 lanes x float4 per row, 4 rows per pass
+          const int rr = lane >> 3, cc = (lane & 7) * 4;
+          const int64_t boff = (int64_t)b * p.d_batch_stride + col0 + cc;
+          float* dbase = reinterpret_cast<float*>(p.d) + boff;
+          const bool col_ok = col0 + cc < n_store;
+          if constexpr (EPI == MTS_EPI_RESID_ADD) {
+            const float* cbase = p.c + boff;  // residual source (== D for the in-place form)
+            float4 o[8];
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r_g = row0 + ps * 4 + rr;
+              if (col_ok && r_g < p.m) o[ps] = *reinterpret_cast<const float4*>(cbase + (int64_t)r_g * p.ldd);
+            }
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r_g = row0 + ps * 4 + rr;
+              if (col_ok && r_g < p.m) {
+                const float4 a = *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr) * kEpiPitch + cc);
+                o[ps].x += a.x; o[ps].y += a.y; o[ps].z += a.z; o[ps].w += a.w;
+                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) = o[ps];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r_g = row0 + ps * 4 + rr;
+              if (col_ok && r_g < p.m)
+                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) =
+                    *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr) * kEpiPitch + cc);
+            }
+          }
+        } else {
+          // bf16: 4 lanes x 8 columns (16 bytes) per row, 8 rows per pass
+          const int rr = lane >> 2, cc = (lane & 3) * 8;
+          __nv_bfloat16* dbase =
+              reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride + col0 + cc;
+          const bool col_ok = col0 + cc < n_store;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r_g = row0 + ps * 8 + rr;
+            if (col_ok && r_g < p.m) {
+              const float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
+              const float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
+              *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd) =
+                  make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
+                             pack_bf16(a1.z, a1.w));
+            }
+          }
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
@@ -323,16 +384,19 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 static int pick_block_n(int m, int n, int batch) {
-  // minimise (waves x tile width); prefer the wider tile on ties (fewer B re-reads of A)
+  // minimise waves x (measured relative time of one tile).  A 128x128 tile is shared-memory-bandwidth
+  // bound (A and B are each re-read per MMA): it costs ~0.77 of a 128x256 tile, not 0.5; a 128x64
+  // tile ~0.6 (B200 measurements, tools/bench_gemm.py).  Narrow tiles only win on small problems.
   const int mb = (m + kBlockM - 1) / kBlockM;
   int best = 64;
   long best_cost = -1;
   const int cands[3] = {256, 128, 64};
+  const int tile_cost[3] = {280, 209, 160};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const long tiles = (long)mb * ((n + bn - 1) / bn) * batch;
     const long waves = (tiles + num_sms() - 1) / num_sms();
-    const long cost = waves * (bn + 24);  // +24: per-tile pipeline fill/drain, in "columns"
+    const long cost = waves * tile_cost[i];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -384,14 +448,16 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
     default:
       return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: unknown epilogue");
   }
+  int vec_ok = 1;
   if (!a->d_transposed) {
     const int vec = f32 ? 4 : 8;
     if ((n_store % vec) || (a->ldd % vec) || (a->d_batch_stride % vec) ||
-        (reinterpret_cast<uintptr_t>(a->d) & 15))
-      return set_error(MTS_ERR_INVALID_ARG,
-                       "mts_gemm: D needs 16-byte aligned rows (n, ldd, batch stride multiples of "
-                       "8 for bf16 / 4 for fp32)");
+        (reinterpret_cast<uintptr_t>(a->d) & 15) || (a->c && (reinterpret_cast<uintptr_t>(a->c) & 15)))
+      vec_ok = 0;  // scalar epilogue stores
+    if (a->ldd < n_store) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: ldd < n");
   }
+  if (a->c && a->epilogue != MTS_EPI_RESID_ADD)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: c is only used by MTS_EPI_RESID_ADD");
   if (bn == 0) bn = pick_block_n(a->m, a->n, a->batch);
   if (bn != 64 && bn != 128 && bn != 256)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: block_n must be 0, 64, 128 or 256");
@@ -417,6 +483,9 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.bias_axis = a->bias_axis;
   p.d_transposed = a->d_transposed;
   p.d_is_f32 = f32 ? 1 : 0;
+  p.vec_ok = vec_ok;
+  p.c = a->c ? a->c : static_cast<const float*>(a->d);
+  p.bias_vec = (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
   p.alpha = a->alpha;
 
   const int mb = (a->m + kBlockM - 1) / kBlockM;

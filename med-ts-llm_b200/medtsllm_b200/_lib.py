@@ -23,7 +23,7 @@ class MtsError(RuntimeError):
 
 class GemmArgs(C.Structure):
     _fields_ = [
-        ("a", C.c_void_p), ("b", C.c_void_p), ("d", C.c_void_p), ("bias", C.c_void_p),
+        ("a", C.c_void_p), ("b", C.c_void_p), ("d", C.c_void_p), ("bias", C.c_void_p), ("c", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
         ("a_batch_stride", C.c_int64), ("b_batch_stride", C.c_int64), ("d_batch_stride", C.c_int64),
         ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("batch", C.c_int32),
@@ -54,6 +54,17 @@ SIGNATURES = {
     "mts_swiglu": [_p, _i64, _p, _i64, _i, _p],
     "mts_sigmoid": [_p, _i64, _p],
     "mts_softmax_lastdim": [_p, _i64, _i, _p],
+    "mts_rmsnorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
+    "mts_layernorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
+    "mts_attn_causal_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
+    "mts_swiglu_blk": [_p, _i64, _p, _i64, _i, _i, _p],
+    "mts_swiglu_bwd": [_p, _i64, _p, _p, _i64, _i, _i, _p],
+    "mts_gelu_new": [_p, _p, _p, _i64, _p],
+    "mts_softmax_bwd_rows": [_p, _p, _p, _i64, _i, _f, _p],
+    "mts_colsum": [_p, _i, _i64, _p, _i, _i, _p],
+    "mts_transpose_strided": [_p, _i, _i64, _i64, _p, _i64, _i, _i, _i, _p],
+    "mts_cast_rows_f32_bf16": [_p, _i64, _i64, _p, _i64, _i, _i, _i, _p],
+    "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "mts_clear_caches": [],
 }
 _SPECIAL = {

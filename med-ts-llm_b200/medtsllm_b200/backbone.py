@@ -100,7 +100,9 @@ class KernelBackbone:
 
     def _finish_embeddings(self, emb: torch.Tensor):
         self.embed = self._f32(emb)
-        self.embed_t = ops.transpose_to_bf16(self.embed)
+        V, D = self.embed.shape
+        # [D, ceil8(V)] zero padded: GPT-2's V = 50257 is odd and TMA rows must be 16-byte aligned
+        self.embed_t = ops.transpose_strided(self.embed, rows=V, cols=D)
 
     def _add_llama_layer(self, wq, wk, wv, wo, wg, wu, wd, ln1, ln2):
         s = self.spec
@@ -116,12 +118,6 @@ class KernelBackbone:
         lay["wdown"] = wd_b
         lay["ln1"] = self._f32(ln1)
         lay["ln2"] = self._f32(ln2)
-        if self.keep_transposed:
-            lay["wqkv_t"] = ops.transpose_to_bf16(lay["wqkv"])
-            lay["wo_t"] = ops.transpose_to_bf16(lay["wo"])
-            lay["wg_t"] = self._t_bf16(wg)        # [D, I]
-            lay["wu_t"] = self._t_bf16(wu)
-            lay["wdown_t"] = self._t_bf16(wd)     # [I, D]
         self.layers.append(lay)
 
     def _add_gpt2_layer(self, c_attn_w, c_attn_b, c_proj_w, c_proj_b, fc_w, fc_b, proj_w, proj_b,
@@ -137,11 +133,6 @@ class KernelBackbone:
         lay["bproj"] = self._f32(proj_b)
         lay["ln1"], lay["ln1b"] = self._f32(ln1w), self._f32(ln1b)
         lay["ln2"], lay["ln2b"] = self._f32(ln2w), self._f32(ln2b)
-        if self.keep_transposed:
-            lay["wqkv_t"] = self._bf16(c_attn_w)   # [D,3D] is already the transpose
-            lay["wo_t"] = self._bf16(c_proj_w)
-            lay["wfc_t"] = self._bf16(fc_w)
-            lay["wproj_t"] = self._bf16(proj_w)
         self.layers.append(lay)
 
     @classmethod
@@ -216,10 +207,33 @@ class KernelBackbone:
             n += sum(t.numel() * t.element_size() for t in lay.values())
         return n
 
-    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None) -> torch.Tensor:
-        """x: fp32 residual stream [Bp*L, D], updated IN PLACE layer by layer; returns the final-norm
-        output bf16 [Bp*L, D].  If `stash` is a list, per-layer activations needed by backward() are
-        appended to it (training)."""
+    def ensure_transposed(self):
+        """Training needs every frozen weight transposed too (dgrad = the same NT GEMM).  Built once,
+        lazily, by our transpose kernel; doubles the weight footprint (see module docstring)."""
+        if self.layers and "wqkv_t" in self.layers[0]:
+            return
+        for lay in self.layers:
+            lay["wqkv_t"] = ops.transpose_to_bf16(lay["wqkv"])       # [D, 3D]
+            lay["wo_t"] = ops.transpose_to_bf16(lay["wo"])           # [D, D]
+            if self.spec.kind == "llama":
+                lay["wgu_t"] = ops.transpose_to_bf16(lay["wgu"])     # [D, 2*Ipad] (packed column order)
+                lay["wdown_t"] = ops.transpose_to_bf16(lay["wdown"])  # [Ipad, D]
+            else:
+                lay["wfc_t"] = ops.transpose_to_bf16(lay["wfc"])     # [D, I]
+                lay["wproj_t"] = ops.transpose_to_bf16(lay["wproj"])  # [I, D]
+        self.keep_transposed = True
+
+    def embed_bf16(self):
+        """bf16 [V, D] copy of the embedding table (B operand of dW_map = dSource E^T)."""
+        if getattr(self, "_embed_bf16", None) is None:
+            self._embed_bf16 = ops.cast_bf16(self.embed)
+        return self._embed_bf16
+
+    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None):
+        """x: fp32 residual stream [Bp*L, D].  Inference (stash None): updated IN PLACE layer by layer.
+        Training (stash = list): every residual write goes to a fresh buffer (the GEMM epilogue reads
+        C = previous stream, writes D = new one) and the per-layer tensors backward() needs are
+        appended to `stash`.  Returns (final-norm output bf16 [Bp*L, D], final residual stream fp32)."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
         M = Bp * L
@@ -229,54 +243,103 @@ class KernelBackbone:
             raise IndexError(f"sequence length {L} exceeds GPT-2 position table {s.max_pos}")
         rope = self.rope(L)
         dev = x.device
-        h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-        qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
-        att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        train = stash is not None
+        bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
+        h, qkv, att = bf(M, D), bf(M, 3 * D), bf(M, D)
+        llama = s.kind == "llama"
         for lay in self.layers:
-            if stash is not None:
-                st = {"x_in": x.clone()}
-                h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-                qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
-                att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-            if s.kind == "llama":
-                ops.rmsnorm(x, lay["ln1"], s.eps, out=h)
+            if train:
+                qkv, att = bf(M, 3 * D), bf(M, D)
+            x_in = x
+            # --- attention half
+            if llama:
+                ops.rmsnorm(x_in, lay["ln1"], s.eps, out=h)
                 ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D)
-                if stash is not None:
-                    _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att, want_lse=True)
-                    st.update(qkv=qkv, att=att, lse=lse)
-                else:
-                    ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att)
-                ops.gemm(att, lay["wo"], x, m=M, n=D, k=D, epilogue=EPI_RESID_ADD)
-                if stash is not None:
-                    st["x_mid"] = x.clone()
-                    h2 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-                else:
-                    h2 = h
-                ops.rmsnorm(x, lay["ln2"], s.eps, out=h2)
-                if stash is not None:
-                    # keep gate/up pre-activations for the backward: plain store + separate SwiGLU
-                    raise MtsError("training stash for llama is implemented in backbone_train.py")
-                act = torch.empty(M, self.i_pad, device=dev, dtype=torch.bfloat16)
-                ops.gemm(h2, lay["wgu"], act, m=M, n=2 * self.i_pad, k=D, epilogue=EPI_SWIGLU, block_n=256)
-                ops.gemm(act, lay["wdown"], x, m=M, n=D, k=self.i_pad, epilogue=EPI_RESID_ADD)
             else:
-                ops.layernorm(x, lay["ln1"], lay["ln1b"], s.eps, out=h)
+                ops.layernorm(x_in, lay["ln1"], lay["ln1b"], s.eps, out=h)
                 ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"], bias_axis=BIAS_N)
-                ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att)
-                ops.gemm(att, lay["wo"], x, m=M, n=D, k=D, bias=lay["bo"], bias_axis=BIAS_N,
-                         epilogue=EPI_RESID_ADD)
-                ops.layernorm(x, lay["ln2"], lay["ln2b"], s.eps, out=h)
-                act = torch.empty(M, s.inter, device=dev, dtype=torch.bfloat16)
-                ops.gemm(h, lay["wfc"], act, m=M, n=s.inter, k=D, bias=lay["bfc"], bias_axis=BIAS_N,
-                         epilogue=EPI_GELU_NEW)
-                ops.gemm(act, lay["wproj"], x, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
-                         epilogue=EPI_RESID_ADD)
-        out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-        if s.kind == "llama":
+            lse = None
+            if train:
+                _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att, want_lse=True)
+            else:
+                ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att)
+            x_mid = torch.empty_like(x_in) if train else x_in
+            ops.gemm(att, lay["wo"], x_mid, m=M, n=D, k=D, epilogue=EPI_RESID_ADD, c=x_in if train else None,
+                     bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
+            # --- MLP half
+            x_out = torch.empty_like(x_in) if train else x_in
+            if llama:
+                ops.rmsnorm(x_mid, lay["ln2"], s.eps, out=h)
+                if train:   # keep the gate/up pre-activations (packed column order) for the backward
+                    pre = bf(M, 2 * self.i_pad)
+                    ops.gemm(h, lay["wgu"], pre, m=M, n=2 * self.i_pad, k=D, block_n=256)
+                    act = ops.swiglu_blk(pre, self.i_pad, 128)
+                else:
+                    pre = None
+                    act = bf(M, self.i_pad)
+                    ops.gemm(h, lay["wgu"], act, m=M, n=2 * self.i_pad, k=D, epilogue=EPI_SWIGLU, block_n=256)
+                ops.gemm(act, lay["wdown"], x_out, m=M, n=D, k=self.i_pad, epilogue=EPI_RESID_ADD,
+                         c=x_mid if train else None)
+            else:
+                ops.layernorm(x_mid, lay["ln2"], lay["ln2b"], s.eps, out=h)
+                if train:
+                    pre = bf(M, s.inter)
+                    ops.gemm(h, lay["wfc"], pre, m=M, n=s.inter, k=D, bias=lay["bfc"], bias_axis=BIAS_N)
+                    act = ops.gelu_new(pre)
+                else:
+                    pre = None
+                    act = bf(M, s.inter)
+                    ops.gemm(h, lay["wfc"], act, m=M, n=s.inter, k=D, bias=lay["bfc"], bias_axis=BIAS_N,
+                             epilogue=EPI_GELU_NEW)
+                ops.gemm(act, lay["wproj"], x_out, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
+                         epilogue=EPI_RESID_ADD, c=x_mid if train else None)
+            if train:
+                stash.append(dict(x_in=x_in, x_mid=x_mid, qkv=qkv, att=att, lse=lse, pre=pre))
+            x = x_out
+        out = bf(M, D)
+        if llama:
             ops.rmsnorm(x, self.final_norm_w, s.eps, out=out)
         else:
             ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
-        return out
+        return out, x
+
+    def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int) -> torch.Tensor:
+        """dgrad through the frozen stack: dhid = dL/d(final-norm output) bf16 [Bp*L, D] -> returns
+        dL/d(input residual stream) fp32 [Bp*L, D].  No weight gradients (frozen)."""
+        s = self.spec
+        D, H, hd = s.hidden, s.heads, s.head_dim
+        M = Bp * L
+        self.ensure_transposed()
+        rope = self.rope(L)
+        dev = dhid.device
+        llama = s.kind == "llama"
+        norm_bwd = ops.rmsnorm_bwd if llama else ops.layernorm_bwd
+        bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
+        dR = torch.empty(M, D, device=dev, dtype=torch.float32)
+        norm_bwd(x_final, self.final_norm_w, dhid, dR, s.eps, accumulate=False)
+        dRb, dH = bf(M, D), bf(M, D)
+        for lay, st in zip(reversed(self.layers), reversed(stash)):
+            # --- MLP half: x_out = x_mid + W2 act(W1 norm(x_mid))
+            ops.cast_bf16(dR, out=dRb)
+            if llama:
+                dact = bf(M, self.i_pad)
+                ops.gemm(dRb, lay["wdown_t"], dact, m=M, n=self.i_pad, k=D)
+                dpre = ops.swiglu_bwd(st["pre"], dact, self.i_pad, 128)
+                ops.gemm(dpre, lay["wgu_t"], dH, m=M, n=D, k=2 * self.i_pad)
+            else:
+                dact = bf(M, s.inter)
+                ops.gemm(dRb, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
+                dpre = ops.gelu_new(st["pre"], dact)
+                ops.gemm(dpre, lay["wfc_t"], dH, m=M, n=D, k=s.inter)
+            norm_bwd(st["x_mid"], lay["ln2"], dH, dR, s.eps, accumulate=True)
+            # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
+            ops.cast_bf16(dR, out=dRb)
+            datt = bf(M, D)
+            ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
+            dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope)
+            ops.gemm(dqkv, lay["wqkv_t"], dH, m=M, n=D, k=3 * D)
+            norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True)
+        return dR
 
     def flops_per_token_fwd(self, L: int) -> float:
         """Dense algorithmic forward FLOPs per token: 2*W_blk + 4*L*D per layer."""

@@ -376,14 +376,32 @@ class MedTsLLM(nn.Module):
         return table
 
     # ------------------------------------------------------------------------------------------ weights
+    PARAM_ORDER = (
+        "patch_embedding.value_embedding.tokenConv.weight",
+        "mapping_layer.weight", "mapping_layer.bias",
+        "reprogramming_layer.query_projection.weight", "reprogramming_layer.query_projection.bias",
+        "reprogramming_layer.key_projection.weight", "reprogramming_layer.key_projection.bias",
+        "reprogramming_layer.value_projection.weight", "reprogramming_layer.value_projection.bias",
+        "reprogramming_layer.out_projection.weight", "reprogramming_layer.out_projection.bias",
+        "embedding_downsample_layer.weight", "embedding_downsample_layer.bias",
+        "output_projection.linear.weight", "output_projection.linear.bias",
+    )
+
+    def adapter_params(self):
+        """The trainable tensors in PARAM_ORDER (the 15 adapter tensors of the shipped configs)."""
+        named = dict(self.named_parameters())
+        return [named[k] for k in self.PARAM_ORDER]
+
     def _bf16_weight(self, name: str, p: torch.Tensor) -> torch.Tensor:
-        """bf16 copy of a trainable fp32 master, re-cast (by our kernel) only when the optimizer has
-        changed it (`_version` bumps on every in-place update)."""
+        """bf16 copy [rows, ceil8(cols)] (zero padded: TMA rows must be 16-byte aligned) of a trainable
+        fp32 master, re-cast by our kernel only when the optimizer has changed it (`_version` bumps on
+        every in-place update)."""
         key = (p._version, p.data_ptr())
         hit = self._w_cache.get(name)
         if hit is not None and hit[0] == key:
             return hit[1]
-        w = ops.cast_bf16(p.detach())
+        rows, cols = p.shape
+        w = ops.cast_rows(p.detach().contiguous(), rows=rows, cols=cols)
         self._w_cache[name] = (key, w)
         return w
 
@@ -399,9 +417,10 @@ class MedTsLLM(nn.Module):
         bb = self._backbone
         S, D, HE, V = self.num_tokens, self.d_llm, self.d_ff * self.n_attention_heads, self.vocab_size
         dev = self.device
-        w_map = self._bf16_weight("map", self.mapping_layer.weight)                       # [S, V]
+        w_map = self._bf16_weight("map", self.mapping_layer.weight)                       # [S, ceil8(V)]
         source = torch.empty(S, D, device=dev, dtype=torch.bfloat16)
-        ops.gemm(w_map, bb.embed_t, source, m=S, n=D, k=V, bias=self.mapping_layer.bias.detach(), bias_axis=BIAS_M)
+        ops.gemm(w_map, bb.embed_t, source, m=S, n=D, k=V, lda=w_map.shape[1], ldb=bb.embed_t.shape[1],
+                 bias=self.mapping_layer.bias.detach(), bias_axis=BIAS_M)
         wk = self._bf16_weight("wk", rl.key_projection.weight)                            # [HE, D]
         wv = self._bf16_weight("wv", rl.value_projection.weight)
         K = torch.empty(S, HE, device=dev, dtype=torch.bfloat16)
@@ -421,6 +440,18 @@ class MedTsLLM(nn.Module):
     @torch.no_grad()
     def predict(self, inputs):
         """Inference path: models/medtsllm.py:321-384 + the eval-only activation of :248-261."""
+        out = self._forward_impl(inputs, None)
+        if not self.training:
+            if self.task == "semantic_segmentation":
+                if self.n_classes > 2:
+                    ops.softmax_lastdim_(out)
+                else:
+                    ops.sigmoid_(out)
+            elif self.task == "segmentation" and self.seg_mode == "boundary-prediction":
+                ops.sigmoid_(out)
+        return out
+
+    def _check_input(self, inputs):
         x_enc = inputs["x_enc"]
         if not x_enc.is_cuda:
             raise MtsError("medtsllm_b200 runs on a CUDA device only (no CPU fallback)")
@@ -434,6 +465,13 @@ class MedTsLLM(nn.Module):
             raise MtsError(f"x_enc must be fp32 (setup.dtype 'mixed'/'float32'), got {x_enc.dtype}")
         B, T, C = x_enc.shape
         assert C == self.n_features and T == self.seq_len
+        return x_enc.contiguous()
+
+    def _forward_impl(self, inputs, stash):
+        """The hot path (models/medtsllm.py:321-382), everything before the eval-only activation.
+        `stash` (dict) collects what train.backward needs; None for inference."""
+        x_enc = self._check_input(inputs)
+        B, T, C = x_enc.shape
         bb = self._backbone
         dev = x_enc.device
         D, N, E, H = self.d_llm, self.n_patches, self.d_ff, self.n_attention_heads
@@ -462,22 +500,25 @@ class MedTsLLM(nn.Module):
         rows = Bp * N
         wq = self._bf16_weight("wq", rl.query_projection.weight)
         Q = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
-        ops.gemm(enc, wq, Q, m=rows, n=HE, k=self.d_model, bias=rl.query_projection.bias.detach(), bias_axis=BIAS_N)
+        ops.gemm(enc, wq, Q, m=rows, n=HE, k=self.d_model, ldb=wq.shape[1],
+                 bias=rl.query_projection.bias.detach(), bias_axis=BIAS_N)
         scores = torch.empty(H, rows, S, device=dev, dtype=torch.float32)
         ops.gemm(Q, K, scores, m=rows, n=S, k=E, batch=H, lda=HE, ldb=HE, a_bs=E, b_bs=E, d_bs=rows * S)
-        P = ops.softmax_rows(scores, 1.0 / math.sqrt(E))
+        scale = 1.0 / math.sqrt(E)
+        P = ops.softmax_rows(scores, scale)
         O = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
         ops.gemm(P, Vt, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
         wo = self._bf16_weight("wo", rl.out_projection.weight)
         ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=L * D, ldd=D, d_off=Lp * D,
-                 bias=rl.out_projection.bias.detach(), bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+                 ldb=wo.shape[1], bias=rl.out_projection.bias.detach(), bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
 
         cap = self._capture
         if cap is not None:
             cap.update(revin_mean=mean.clone(), revin_stdev=std.clone(), patch_embedding=enc.clone(),
                        source_embeddings=source.clone(), llm_input=X.clone())
         # backbone
-        hid = bb.forward(X.view(Bp * L, D), Bp, L)                    # bf16 [Bp*L, D], final norm applied
+        layer_stash = [] if stash is not None else None
+        hid, x_final = bb.forward(X.view(Bp * L, D), Bp, L, stash=layer_stash)   # bf16 [Bp*L, D], final norm applied
         if cap is not None:
             cap["llm"] = hid.view(Bp, L, D).clone()
 
@@ -489,23 +530,22 @@ class MedTsLLM(nn.Module):
         # K12: flatten head
         wh = self._bf16_weight("wh", self.output_projection.linear.weight)
         out = torch.empty(Bp, self.n_outputs, device=dev, dtype=torch.float32)
-        ops.gemm(flat, wh, out, m=Bp, n=self.n_outputs, k=E * N, bias=self.output_projection.linear.bias.detach(),
-                 bias_axis=BIAS_N)
+        if (E * N) % 8:
+            raise MtsError("d_ff * n_patches must be a multiple of 8")
+        ops.gemm(flat, wh, out, m=Bp, n=self.n_outputs, k=E * N, ldb=wh.shape[1],
+                 bias=self.output_projection.linear.bias.detach(), bias_axis=BIAS_N)
         if cap is not None:
             cap["output_projection"] = out.clone()
         out = out.view(B, self.pred_len, self.n_outputs_per_step)
-        if self.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
+        denorm = self.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining")
+        if denorm:
             ops.revin_denorm(out, mean, std)
         else:
             out = out.squeeze(-1)
-        if not self.training:
-            if self.task == "semantic_segmentation":
-                if self.n_classes > 2:
-                    ops.softmax_lastdim_(out)
-                else:
-                    ops.sigmoid_(out)
-            elif self.task == "segmentation" and self.seg_mode == "boundary-prediction":
-                ops.sigmoid_(out)
+        if stash is not None:
+            stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
+                         hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Bp=Bp,
+                         scale=scale, denorm=denorm, concat=concat)
         return out
 
 

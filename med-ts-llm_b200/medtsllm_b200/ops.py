@@ -42,7 +42,7 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
-         block_n=0, a_off=0, b_off=0, d_off=0):
+         block_n=0, a_off=0, b_off=0, d_off=0, c=None):
     """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
     if d.dtype not in (torch.bfloat16, torch.float32):
@@ -52,6 +52,7 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.b = b.data_ptr() + 2 * b_off
     args.d = d.data_ptr() + d.element_size() * d_off
     args.bias = _ptr(bias)
+    args.c = 0 if c is None else _chk(c, torch.float32, "c").data_ptr() + 4 * d_off
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     args.lda = k if lda is None else lda
@@ -284,3 +285,126 @@ def softmax_lastdim_(y):
     n = y.shape[-1]
     _lib.call("mts_softmax_lastdim", y.data_ptr(), y.numel() // n, n, _stream())
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# training-path kernels
+# ------------------------------------------------------------------------------------------------
+def _dt(t):
+    return MTS_F32 if t.dtype == torch.float32 else MTS_BF16
+
+
+def rmsnorm_bwd(x, w, dy, dx, eps, accumulate=True):
+    """dx (+)= J_rmsnorm(x)^T (w*dy); x fp32 [rows,D], dy bf16, dx fp32."""
+    _chk(x, torch.float32, "x"); _chk(dy, torch.bfloat16, "dy"); _chk(dx, torch.float32, "dx")
+    D = x.shape[-1]
+    _lib.call("mts_rmsnorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+              x.numel() // D, D, eps, 1 if accumulate else 0, _stream())
+    return dx
+
+
+def layernorm_bwd(x, w, dy, dx, eps, accumulate=True):
+    _chk(x, torch.float32, "x"); _chk(dy, torch.bfloat16, "dy"); _chk(dx, torch.float32, "dx")
+    D = x.shape[-1]
+    _lib.call("mts_layernorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+              x.numel() // D, D, eps, 1 if accumulate else 0, _stream())
+    return dx
+
+
+def attn_causal_bwd(qkv, out, dout, lse, Bp, L, H, hd, *, rope=None, scale=None):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
+    _chk(lse, torch.float32, "lse")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(Bp, H, L, device=qkv.device, dtype=torch.float32)
+    cos, sin = rope if rope is not None else (None, None)
+    _lib.call("mts_attn_causal_bwd", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), dout.data_ptr(),
+              lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, L, H, hd, scale, _stream())
+    return dqkv
+
+
+def swiglu_blk(gu, I, blk):
+    _chk(gu, torch.bfloat16, "gu")
+    rows = gu.numel() // gu.shape[-1]
+    out = torch.empty(*gu.shape[:-1], I, device=gu.device, dtype=torch.bfloat16)
+    _lib.call("mts_swiglu_blk", gu.data_ptr(), gu.shape[-1], out.data_ptr(), rows, I, blk, _stream())
+    return out
+
+
+def swiglu_bwd(gu, dact, I, blk):
+    _chk(gu, torch.bfloat16, "gu"); _chk(dact, torch.bfloat16, "dact")
+    rows = gu.numel() // gu.shape[-1]
+    dgu = torch.empty_like(gu)
+    _lib.call("mts_swiglu_bwd", gu.data_ptr(), gu.shape[-1], dact.data_ptr(), dgu.data_ptr(), rows, I, blk,
+              _stream())
+    return dgu
+
+
+def gelu_new(pre, dact=None):
+    _chk(pre, torch.bfloat16, "pre")
+    out = torch.empty_like(pre)
+    _lib.call("mts_gelu_new", pre.data_ptr(), _ptr(dact), out.data_ptr(), pre.numel(), _stream())
+    return out
+
+
+def softmax_bwd_rows(p, dp, scale):
+    _chk(p, torch.bfloat16, "p"); _chk(dp, torch.float32, "dp")
+    n = p.shape[-1]
+    ds = torch.empty_like(p)
+    _lib.call("mts_softmax_bwd_rows", p.data_ptr(), dp.data_ptr(), ds.data_ptr(), p.numel() // n, n, scale,
+              _stream())
+    return ds
+
+
+def colsum(x, rows=None, cols=None, ld=None):
+    """fp32 [cols] = column sums of a (possibly strided) 2-D view of x."""
+    _chk(x, None, "x")
+    if rows is None:
+        cols = x.shape[-1]; rows = x.numel() // cols
+    ld = cols if ld is None else ld
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    _lib.call("mts_colsum", x.data_ptr(), _dt(x), ld, out.data_ptr(), rows, cols, _stream())
+    return out
+
+
+def ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+def transpose_strided(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, out=None, ld_out=None):
+    """out[c, b*rows + r] = bf16(x[b][r][c]); out is [cols, ld_out] with ld_out = ceil8(batch*rows),
+    zero padded (so it can be a K-major GEMM operand with K = batch*rows)."""
+    _chk(x, None, "x")
+    ld_in = cols if ld_in is None else ld_in
+    k = batch * rows
+    if ld_out is None:
+        ld_out = ceil8(k)
+    if out is None:
+        out = (torch.zeros if ld_out != k else torch.empty)(cols, ld_out, device=x.device, dtype=torch.bfloat16)
+    _lib.call("mts_transpose_strided", x.data_ptr() + x.element_size() * in_off, _dt(x), ld_in, in_bs,
+              out.data_ptr(), ld_out, batch, rows, cols, _stream())
+    return out
+
+
+def cast_rows(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, ld_out=None, out=None):
+    """out[(b*rows + r), :cols] = bf16(x[b][r][:cols]); out [batch*rows, ld_out] (zero padded columns)."""
+    _chk(x, torch.float32, "x")
+    ld_in = cols if ld_in is None else ld_in
+    if ld_out is None:
+        ld_out = ceil8(cols)
+    if out is None:
+        out = (torch.zeros if ld_out != cols else torch.empty)(batch * rows, ld_out, device=x.device,
+                                                               dtype=torch.bfloat16)
+    _lib.call("mts_cast_rows_f32_bf16", x.data_ptr() + 4 * in_off, ld_in, in_bs, out.data_ptr(), ld_out, batch,
+              rows, cols, _stream())
+    return out
+
+
+def revin_denorm_bwd(dy, std):
+    _chk(dy, torch.float32, "dy")
+    dy = dy.contiguous()
+    B, T, Cc = dy.shape
+    out = torch.empty_like(dy)
+    _lib.call("mts_revin_denorm_bwd", dy.data_ptr(), std.data_ptr(), out.data_ptr(), B, T, Cc, _stream())
+    return out

@@ -1,8 +1,176 @@
-"""Autograd (training) path: forward with activation stash + backward through the frozen backbone
-for the adapter gradients.  See DESIGN.md §training."""
-from ._lib import MtsError
+"""Training path: `loss.backward()` of the reference's Trainer (tasks/forecasting.py:26) through the
+kernel stack.
+
+The reference trains every adapter around the frozen LLM — patch-embedding conv, mapping layer,
+the four reprogramming projections, the down-sample Linear and the flatten head (15 tensors with the
+shipped configs) — and three of those sit IN FRONT of the backbone, so the gradient has to flow
+through all frozen blocks (dgrad only, no backbone weight gradients).  One autograd.Function wraps
+the whole hot path: forward = MedTsLLM._forward_impl with an activation stash, backward = the manual
+chain below.  Every contraction is the tcgen05 NT GEMM (mts_gemm) on transposed operands
+(dX = dY W -> B = W^T; dW = dY^T X -> A = dY^T, B = X^T, both produced by our transpose kernel);
+the rest are the kernels of csrc/backward.cu and the attention backward.
+
+Numerics: bf16 operands / fp32 accumulation like the forward (= the reference's bf16-autocast
+regime); the residual-stream gradient is fp32.  Dropout is not implemented: `training.dropout` must be
+0 (the shipped configs use 0.1 — see DESIGN.md, deviation list).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import BIAS_NONE, EPI_RESID_ADD, MtsError
 
 
 def forward_train(model, inputs):
-    raise MtsError("the training path (adapter gradients through the frozen backbone) is not built yet; "
-                   "wrap inference calls in torch.no_grad()")
+    if model._dropout_requested > 0:
+        raise MtsError(
+            f"training.dropout = {model._dropout_requested}: the kernel path implements the deterministic model "
+            "only (PatchEmbedding / reprogramming dropout not built yet); set training.dropout = 0")
+    params = model.adapter_params()
+    return _HotPathFn.apply(model, inputs, *params)
+
+
+def _t(x, **kw):
+    """[rows, cols] -> bf16 [cols, ceil8(rows)] (zero padded): a K-major operand with K = rows."""
+    rows, cols = x.shape
+    return ops.transpose_strided(x, rows=rows, cols=cols, **kw)
+
+
+class _HotPathFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, model, inputs, *params):
+        stash = {}
+        out = model._forward_impl(inputs, stash)
+        ctx.model = model
+        ctx.stash = stash
+        ctx.out_shape = out.shape
+        return out
+
+    @staticmethod
+    @torch.no_grad()
+    def backward(ctx, dout):
+        m, st = ctx.model, ctx.stash
+        bb = m._backbone
+        dev = dout.device
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        B, N, E, H, D = st["Bp"], m.n_patches, m.d_ff, m.n_attention_heads, m.d_llm
+        HE, S, Lp, L, V = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size
+        R = B * N                                   # reprogrammed rows
+        dm = m.d_model
+        rl = m.reprogramming_layer
+        f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
+        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)     # noqa: E731
+        zbf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)    # noqa: E731
+
+        # ---- de-norm / squeeze (models/medtsllm.py:379-382): statistics are detached
+        dout = dout.reshape(B, m.pred_len, m.n_outputs_per_step).contiguous()
+        dy = ops.revin_denorm_bwd(dout, st["std"]) if st["denorm"] else dout
+        n_out = m.n_outputs
+        dy2 = dy.view(B, n_out)
+
+        # ---- flatten head: out = flat W_h^T + b_h
+        g_bh = ops.colsum(dy2)
+        dy_b = ops.cast_rows(dy2, rows=B, cols=n_out)                          # bf16 [B, ceil8(n_out)]
+        wh = m._bf16_weight("wh", m.output_projection.linear.weight)           # [n_out, ceil8(EN)]
+        EN = E * N
+        g_wh = f32(n_out, EN)
+        ops.gemm(_t(dy2), _t(st["flat"]), g_wh, m=n_out, n=EN, k=B, lda=ops.ceil8(B), ldb=ops.ceil8(B))
+        wh_t = ops.transpose_strided(wh, rows=n_out, cols=EN, ld_in=wh.shape[1])   # [EN, ceil8(n_out)]
+        dflat = bf(B, EN)                                                       # [B, E, N]
+        ops.gemm(dy_b, wh_t, dflat, m=B, n=EN, k=n_out, lda=dy_b.shape[1], ldb=wh_t.shape[1])
+
+        # ---- down-sample Linear on the last N tokens: flat[b, f, n] = hid[b, Lp+n] . W_ds[f] + b_ds[f]
+        # dflat is [B][E][N]; dY_ds[(b, n), f] = dflat[b, f, n] is a per-batch transpose
+        dyds = bf(R, E)
+        for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
+            ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
+        g_bds = ops.colsum(dyds)
+        hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D,
+                                           in_off=Lp * D)                      # [D, ceil8(R)]
+        g_wds = f32(E, D)
+        ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=R, lda=ops.ceil8(R), ldb=hid_last_t.shape[1])
+        wds = m._bf16_weight("wds", m.embedding_downsample_layer.weight)       # [E, D]
+        wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
+        dhid = zbf(B * L, D)                                                    # zero for prompt rows
+        ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
+                 d_bs=L * D, ldd=D, d_off=Lp * D)
+
+        # ---- frozen backbone (dgrad only)
+        dR = bb.backward(dhid, st["x_final"], st["layers"], B, L)              # fp32 [B*L, D]
+
+        # ---- reprogramming out-projection: X[b, Lp+n] = O W_o^T + b_o
+        dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D, in_off=Lp * D)   # bf16 [R, D]
+        g_bo = ops.colsum(dxp)
+        Rp = ops.ceil8(R)
+        g_wo = f32(D, HE)
+        ops.gemm(_t(dxp), _t(st["O"]), g_wo, m=D, n=HE, k=R, lda=Rp, ldb=Rp)
+        wo = m._bf16_weight("wo", rl.out_projection.weight)                    # [D, HE]
+        wo_t = ops.transpose_strided(wo, rows=D, cols=HE, ld_in=wo.shape[1])   # [HE, D]
+        dO = bf(R, HE)
+        ops.gemm(dxp, wo_t, dO, m=R, n=HE, k=D, ldb=wo_t.shape[1])
+
+        # ---- cross-attention core, per head h: O_h = P_h V_h, P_h = softmax(scale Q_h K_h^T)
+        P, Q, K, Vt = st["P"], st["Q"], st["K"], st["Vt"]
+        Vm = ops.transpose_strided(Vt, rows=HE, cols=S)                        # [S, HE]
+        dP = f32(H, R, S)
+        ops.gemm(dO, Vm, dP, m=R, n=S, k=E, batch=H, lda=HE, a_bs=E, ldb=Vm.shape[1], b_bs=E, d_bs=R * S)
+        dS = ops.softmax_bwd_rows(P, dP, st["scale"])                          # bf16 [H, R, S]
+        # per-head transposes laid out [S, H*Rp]: head h occupies columns [h*Rp, h*Rp + R)
+        P_t, dS_t = zbf(S, H * Rp), zbf(S, H * Rp)
+        for h in range(H):
+            ops.transpose_strided(P, rows=R, cols=S, in_off=h * R * S, out=P_t[:, h * Rp:], ld_out=H * Rp)
+            ops.transpose_strided(dS, rows=R, cols=S, in_off=h * R * S, out=dS_t[:, h * Rp:], ld_out=H * Rp)
+        dO_t, Q_t = _t(dO), _t(Q)                                              # [HE, Rp]
+        dV = bf(S, HE)
+        ops.gemm(P_t, dO_t, dV, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
+        dK = bf(S, HE)
+        ops.gemm(dS_t, Q_t, dK, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
+        K_t = _t(K)                                                            # [HE, S]
+        dQ = bf(R, HE)
+        ops.gemm(dS, K_t, dQ, m=R, n=E, k=S, batch=H, a_bs=R * S, lda=S, ldb=K_t.shape[1], b_bs=E * K_t.shape[1],
+                 ldd=HE, d_bs=E)
+
+        # ---- query projection + front end
+        g_bq = ops.colsum(dQ)
+        enc2 = st["enc"].view(R, dm)
+        g_wq = f32(HE, dm)
+        ops.gemm(_t(dQ), _t(enc2), g_wq, m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
+        wq = m._bf16_weight("wq", rl.query_projection.weight)                  # [HE, ceil8(dm)]
+        wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
+        denc = f32(R, dm)
+        ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
+        g_conv = ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
+                                           m.patch_len, m.stride, m.d_patch, concat=st["concat"])
+
+        # ---- key / value projections of the prototypes, then the mapping layer
+        source = st["source"]
+        src_t = _t(source)                                                     # [D, S]
+        g_bk, g_bv = ops.colsum(dK), ops.colsum(dV)
+        g_wk, g_wv = f32(HE, D), f32(HE, D)
+        ops.gemm(_t(dK), src_t, g_wk, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
+        ops.gemm(_t(dV), src_t, g_wv, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
+        wk = m._bf16_weight("wk", rl.key_projection.weight)                    # [HE, D]
+        wv = m._bf16_weight("wv", rl.value_projection.weight)
+        dsrc = f32(S, D)
+        ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
+        ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
+        dsrc_b = ops.cast_bf16(dsrc)
+        g_bmap = ops.colsum(ops.transpose_strided(dsrc_b, rows=S, cols=D, ld_out=S, out=bf(D, S)))   # row sums of dsrc
+        g_wmap = f32(S, V)
+        ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
+
+        ctx.stash = None
+        grads = {
+            "patch_embedding.value_embedding.tokenConv.weight": g_conv,
+            "mapping_layer.weight": g_wmap, "mapping_layer.bias": g_bmap,
+            "reprogramming_layer.query_projection.weight": g_wq, "reprogramming_layer.query_projection.bias": g_bq,
+            "reprogramming_layer.key_projection.weight": g_wk, "reprogramming_layer.key_projection.bias": g_bk,
+            "reprogramming_layer.value_projection.weight": g_wv, "reprogramming_layer.value_projection.bias": g_bv,
+            "reprogramming_layer.out_projection.weight": g_wo, "reprogramming_layer.out_projection.bias": g_bo,
+            "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
+            "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
+        }
+        return (None, None) + tuple(grads[k] for k in m.PARAM_ORDER)

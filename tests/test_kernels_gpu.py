@@ -271,3 +271,130 @@ def test_attn_causal(ops, cuda, Bp, L, H, hd, rope):
     assert _rel_l2(out, ref) < 8e-3
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------- training-path kernels
+def test_gemm_resid_out_of_place_and_scalar_epilogue(ops, cuda):
+    g = torch.Generator().manual_seed(21)
+    m, n, k = 200, 130, 72                      # n % 4 != 0 -> scalar epilogue path
+    a = torch.randn(m, k, generator=g).to(cuda, torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(cuda, torch.bfloat16)
+    c = torch.randn(m, n, generator=g).to(cuda)
+    d = torch.full((m, n), float("nan"), device=cuda)
+    ops.gemm(a, b, d, m=m, n=n, k=k, epilogue=1, c=c)
+    torch.testing.assert_close(d, c + _bf16_gemm_ref(a, b), rtol=1e-4, atol=1e-3)
+    d16 = torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, b, d16, m=m, n=n, k=k)
+    torch.testing.assert_close(d16.float(), _bf16_gemm_ref(a, b), rtol=8e-3, atol=6e-2)
+    # odd K with padded leading dimensions (GPT-2 vocabulary 50257)
+    k2, ld = 77, 80
+    a2 = torch.zeros(m, ld, device=cuda, dtype=torch.bfloat16); a2[:, :k2] = torch.randn(m, k2, generator=g).to(cuda)
+    b2 = torch.zeros(64, ld, device=cuda, dtype=torch.bfloat16); b2[:, :k2] = torch.randn(64, k2, generator=g).to(cuda)
+    a2[:, k2:] = 7.0; b2[:, k2:] = 7.0          # must be ignored: TMA extent is k, not ld
+    d2 = torch.empty(m, 64, device=cuda)
+    ops.gemm(a2, b2, d2, m=m, n=64, k=k2, lda=ld, ldb=ld)
+    torch.testing.assert_close(d2, a2[:, :k2].float() @ b2[:, :k2].float().t(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows,D", [(33, 4096), (64, 256)])
+def test_norm_bwd(ops, cuda, rows, D):
+    g = torch.Generator().manual_seed(D)
+    x = (torch.randn(rows, D, generator=g) * 1.5 + 0.2).to(cuda).requires_grad_(True)
+    w = torch.randn(D, generator=g).to(cuda)
+    b = torch.randn(D, generator=g).to(cuda)
+    dy = torch.randn(rows, D, generator=g).to(cuda, torch.bfloat16)
+    base = torch.randn(rows, D, generator=g).to(cuda)
+    y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w
+    (gx,) = torch.autograd.grad(y, x, dy.float())
+    dx = base.clone()
+    ops.rmsnorm_bwd(x.detach(), w, dy, dx, 1e-5, accumulate=True)
+    torch.testing.assert_close(dx, base + gx, rtol=1e-4, atol=1e-4)
+    y = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
+    (gx,) = torch.autograd.grad(y, x, dy.float())
+    dx = torch.full_like(base, float("nan"))
+    ops.layernorm_bwd(x.detach(), w, dy, dx, 1e-5, accumulate=False)
+    torch.testing.assert_close(dx, gx, rtol=1e-4, atol=1e-4)
+
+
+def test_swiglu_gelu_softmax_bwd(ops, cuda):
+    g = torch.Generator().manual_seed(31)
+    rows, I = 40, 256
+    # packed layout, blk = 128
+    gate = torch.randn(rows, I, generator=g).to(cuda, torch.bfloat16)
+    up = torch.randn(rows, I, generator=g).to(cuda, torch.bfloat16)
+    packed = torch.stack([gate.view(rows, 2, 128), up.view(rows, 2, 128)], dim=2).reshape(rows, 2 * I).contiguous()
+    dact = torch.randn(rows, I, generator=g).to(cuda, torch.bfloat16)
+    gf, uf = gate.float().requires_grad_(True), up.float().requires_grad_(True)
+    act = torch.nn.functional.silu(gf) * uf
+    torch.testing.assert_close(ops.swiglu_blk(packed, I, 128).float(), act.detach(), rtol=8e-3, atol=2e-3)
+    dg, du = torch.autograd.grad(act, (gf, uf), dact.float())
+    dgu = ops.swiglu_bwd(packed, dact, I, 128).float().view(rows, 2, 2, 128)
+    torch.testing.assert_close(dgu[:, :, 0].reshape(rows, I), dg, rtol=1e-2, atol=4e-3)
+    torch.testing.assert_close(dgu[:, :, 1].reshape(rows, I), du, rtol=1e-2, atol=4e-3)
+    # gelu_new
+    pre = torch.randn(rows, I, generator=g).to(cuda, torch.bfloat16)
+    pf = pre.float().requires_grad_(True)
+    ref = 0.5 * pf * (1 + torch.tanh(math.sqrt(2 / math.pi) * (pf + 0.044715 * pf ** 3)))
+    torch.testing.assert_close(ops.gelu_new(pre).float(), ref.detach(), rtol=8e-3, atol=2e-3)
+    (dp,) = torch.autograd.grad(ref, pf, dact.float())
+    torch.testing.assert_close(ops.gelu_new(pre, dact).float(), dp, rtol=1e-2, atol=4e-3)
+    # softmax backward
+    s = (torch.randn(24, 512, generator=g) * 3).to(cuda).requires_grad_(True)
+    p = torch.softmax(s * 0.25, -1)
+    dpv = torch.randn(24, 512, generator=g).to(cuda)
+    (ds_ref,) = torch.autograd.grad(p, s, dpv)
+    pb = p.detach().to(torch.bfloat16)
+    ds = ops.softmax_bwd_rows(pb, dpv, 0.25)
+    pf32 = pb.float()
+    ds_exact = 0.25 * pf32 * (dpv - (dpv * pf32).sum(-1, keepdim=True))     # same bf16-rounded P
+    torch.testing.assert_close(ds.float(), ds_exact, rtol=8e-3, atol=1e-5)
+    assert _rel_l2(ds, ds_ref) < 1e-2
+
+
+def test_colsum_transpose_cast_rows_denorm_bwd(ops, cuda):
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(300, 77, generator=g).to(cuda)
+    torch.testing.assert_close(ops.colsum(x), x.sum(0), rtol=1e-5, atol=1e-4)
+    xb = x.to(torch.bfloat16)
+    torch.testing.assert_close(ops.colsum(xb), xb.float().sum(0), rtol=1e-5, atol=1e-4)
+    # batched strided transpose with zero padded K
+    src = torch.randn(3, 10, 50, generator=g).to(cuda)           # rows 4..9 of each batch are skipped
+    out = ops.transpose_strided(src, batch=3, rows=5, cols=50, ld_in=50, in_bs=500, in_off=50 * 4)
+    assert out.shape == (50, 16)
+    ref = src[:, 4:9, :].reshape(15, 50).t().to(torch.bfloat16)
+    assert torch.equal(out[:, :15], ref) and torch.all(out[:, 15:] == 0)
+    # strided cast with padded output rows
+    c = ops.cast_rows(src, batch=3, rows=5, cols=50, ld_in=50, in_bs=500, in_off=50 * 4)
+    assert c.shape == (15, 56)
+    assert torch.equal(c[:, :50], src[:, 4:9, :].reshape(15, 50).to(torch.bfloat16)) and torch.all(c[:, 50:] == 0)
+    odd = torch.randn(7, 13, generator=g).to(cuda)
+    assert torch.equal(ops.cast_rows(odd, rows=7, cols=13)[:, :13], odd.to(torch.bfloat16))
+    dy = torch.randn(4, 9, 3, generator=g).to(cuda)
+    std = torch.rand(4, 3, generator=g).to(cuda) + 0.5
+    torch.testing.assert_close(ops.revin_denorm_bwd(dy, std), dy * std[:, None], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("Bp,L,H,hd,rope", [(2, 192, 2, 128, True), (2, 140, 3, 64, False), (1, 70, 2, 64, True)])
+def test_attn_causal_bwd(ops, cuda, Bp, L, H, hd, rope):
+    g = torch.Generator().manual_seed(L * 3 + hd)
+    D = H * hd
+    qkv = (torch.randn(Bp * L, 3 * D, generator=g) * 0.7).to(cuda, torch.bfloat16)
+    dout = torch.randn(Bp * L, D, generator=g).to(cuda, torch.bfloat16)
+    tabs = _rope_tables(L, hd, cuda) if rope else None
+    out, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=tabs, want_lse=True)
+    dqkv = ops.attn_causal_bwd(qkv, out, dout, lse, Bp, L, H, hd, rope=tabs)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (t.view(Bp, L, H, hd).transpose(1, 2) for t in x.split(D, dim=-1))
+    if rope:
+        cos = torch.cat([tabs[0], tabs[0]], -1)[None, None]
+        sin = torch.cat([tabs[1], tabs[1]], -1)[None, None]
+        rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)
+        q = q * cos + rot(q) * sin
+        k = k * cos + rot(k) * sin
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    mask = torch.ones(L, L, device=cuda, dtype=torch.bool).tril()
+    ref = (torch.softmax(s.masked_fill(~mask, float("-inf")), -1) @ v).transpose(1, 2).reshape(Bp * L, D)
+    (gx,) = torch.autograd.grad(ref, x, dout.float())
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = _rel_l2(dqkv[:, sl], gx[:, sl])
+        assert err < 1.5e-2, (name, err)     # bf16 P / dS / outputs

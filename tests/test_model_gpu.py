@@ -35,9 +35,15 @@ def test_forward_parity(name, tmp_path, cuda):
     with torch.no_grad():
         out = model(inputs)
     torch.cuda.synchronize()
-    cap = model._capture
-    ref_out, st = run_oracle(fix)
-    g = fix["stages"]
+    cap, model._capture = model._capture, None
+    # the input-statistics prompt ranks FFT autocorrelation lags whose values tie exactly in theory
+    # (corr[k] == corr[T-k]), so CPU and GPU can order them differently: embed the GPU-side tokens in
+    # the oracle, and compare with the CPU-generated goldens only when the prompts agree
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    Lp_max = max(len(p) for p in fix["prompt_ids"])
+    same_prompt = all(r[Lp_max - len(p):] == p for r, p in zip(ids, fix["prompt_ids"]))
+    ref_out, st = run_oracle(fix, prompt_ids=ids)
+    g = fix["stages"] if same_prompt else {**st, "output": ref_out, "output_train": run_oracle(fix, True, ids)[0]}
 
     assert out.shape == g["output"].shape and out.dtype == torch.float32
     B, T, C = fix["inputs"]["x_enc"].shape
@@ -50,6 +56,11 @@ def test_forward_parity(name, tmp_path, cuda):
         pe = pe.reshape(B, C, N, -1).permute(0, 2, 1, 3).reshape(B, N, -1)
     assert _rel_l2(cap["patch_embedding"], pe) < 4e-3
     # stages: vs oracle (run here) and vs the reference goldens
+    if fix["kind"] == "gpt2":
+        # the kernel path folds GPT-2's position embedding into the gather (HF adds wpe inside the model,
+        # HF:models/gpt2/modeling_gpt2.py:584-585); the reference-side capture is pre-wpe
+        L = cap["llm_input"].shape[1]
+        cap["llm_input"] = cap["llm_input"] - model._backbone.wpe[:L][None]
     for key in ("source_embeddings", "llm_input", "llm", "output_projection"):
         e_o = _rel_l2(cap[key].float().view(st[key].shape), st[key])
         e_g = _rel_l2(cap[key].float().view(g[key].shape), g[key])
@@ -94,5 +105,48 @@ def test_random_init_backbone_matches_oracle_llama_hd128(cuda):
     Bp, L = 3, 70
     x = torch.randn(Bp, L, 256, generator=torch.Generator().manual_seed(0))
     ref = O.llama_forward(x, sd, n_layers=2, n_heads=2, eps=1e-5)
-    got = bb.forward(x.to(cuda).view(Bp * L, 256).contiguous(), Bp, L).float().cpu().view(Bp, L, 256)
+    got = bb.forward(x.to(cuda).view(Bp * L, 256).contiguous(), Bp, L)[0].float().cpu().view(Bp, L, 256)
     assert _rel_l2(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_training_step_gradients(name, tmp_path, cuda):
+    """loss.backward() through the kernel stack vs autograd through the oracle (fp32, CPU) on the same
+    weights/inputs/loss.  Tolerance: relative L2 < 5e-2 per adapter tensor (bf16 operands in ~10
+    chained GEMMs forward and backward; the largest tensors come out around 1e-2)."""
+    from medtsllm_b200.model import MedTsLLM
+    from oracle import medtsllm_oracle as O
+    from _fixtures import oracle_spec
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda, torch.float32).train()
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    out = model(inputs)
+    assert out.requires_grad
+    gen = torch.Generator().manual_seed(5)
+    wgt = torch.randn(out.shape, generator=gen)
+    (out * wgt.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+
+    # oracle gradients (prompt ids from the GPU-side host logic so both sides embed the same tokens)
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ad = {k: v.clone().requires_grad_(True) for k, v in fix["adapters"].items()}
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, oracle_spec(fix), training=True)
+    assert _rel_l2(out, ref) < 2e-2
+    (ref * wgt).sum().backward()
+    report = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        e = _rel_l2(p.grad, ad[k].grad)
+        report.append(f"{k.split('.')[-2][:8]}.{k.split('.')[-1][0]} {e:.1e}")
+        assert e < 5e-2, (name, k, e)
+    print(f"\n[grad parity] {name}: " + "  ".join(report))
+    # one optimizer step changes the cached bf16 weights (version tracking) and the output
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-2)
+    opt.step()
+    with torch.no_grad():
+        out2 = model(inputs)
+    assert not torch.equal(out2, out.detach())
