@@ -186,6 +186,40 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
 
+    # ---- training step (same workload): forward with activation stash + backward through the frozen
+    # backbone to all 15 adapter tensors + (N>1) gradient all-reduce + Adam step + loss read-back, through
+    # the public API exactly like the reference Trainer loop (tasks/forecasting.py:19-30)
+    train = None
+    if not args.no_train:
+        model.train()
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+        y_host = torch.zeros(out_host.shape).pin_memory()
+        loss_fn = torch.nn.MSELoss()
+
+        def step_train():
+            x = host["x_enc"].to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True)
+            pred = model({"x_enc": x})
+            loss = loss_fn(pred, y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss.item()                                    # D2H sync every step, as the Trainer does
+
+        n_tr = max(3, args.steps // 2)
+        for _ in range(2):
+            step_train()
+        n1 = _lib.launch_count()
+        ms_train = timed(step_train, n_tr) / n_tr
+        train = {"value": round(world * w.B / (ms_train * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms_train, 3),
+                 "steps": n_tr, "gpu_launches_per_step": int((_lib.launch_count() - n1) // n_tr),
+                 "what": "fwd + bwd (dgrad through all frozen blocks, 15 adapter grads) + Adam step + loss.item(), "
+                         "host windows/labels copied in every step; dropout 0"}
+        model.eval()
+        opt.zero_grad(set_to_none=True)
+        del opt
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every mts_gemm launch,
     # recorded on the launching stream over instrumented steps of the same workload
     gemm_ms, gemm_flops = None, None
@@ -237,6 +271,7 @@ def run_ours(args):
             "e2e": {"value": round(world * w.B / (ms_e2e * 1e-3), 2), "unit": "samples/s",
                     "h2d_bytes_per_step": host["x_enc"].numel() * 4 + w.B * Lp * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e, 3)},
+            "train_step": train,
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_nt_kernel (tcgen05)", "achieved": round(achieved, 1),
                          "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
@@ -364,6 +399,7 @@ def main():
     ap.add_argument("--workload", default="bidmc_llama2_7b")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
     ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
     args = ap.parse_args()
     if args.impl == "reference":

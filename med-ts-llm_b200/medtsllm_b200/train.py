@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import dp, ops
 from ._lib import BIAS_NONE, EPI_RESID_ADD, MtsError
 
 
@@ -98,6 +98,9 @@ class _HotPathFn(torch.autograd.Function):
         ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
                  d_bs=L * D, ldd=D, d_off=Lp * D)
 
+        # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
+        early = dp.GradBucket([g_wh, g_bh, g_wds, g_bds]).launch()
+
         # ---- frozen backbone (dgrad only)
         dR = bb.backward(dhid, st["x_final"], st["layers"], B, L)              # fp32 [B*L, D]
 
@@ -162,6 +165,9 @@ class _HotPathFn(torch.autograd.Function):
         g_wmap = f32(S, V)
         ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
 
+        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo]).launch()
+        early.finish()
+        late.finish()
         ctx.stash = None
         grads = {
             "patch_embedding.value_embedding.tokenConv.weight": g_conv,

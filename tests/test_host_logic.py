@@ -85,3 +85,27 @@ def test_unsupported_options_fail_loudly(tmp_path):
     cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16}
     with pytest.raises(NotImplementedError):
         MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+
+
+def test_plugin_registers_into_reference_model_lookup(tmp_path):
+    """Drop-in seam (tasks/base.py:81-85): after register(), the reference's own lookup builds OUR class from
+    the reference's own config object.  Needs the reference tree, i.e. runs in the build container only."""
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip("/root/reference not present on this machine")
+    ref = H.import_reference()              # installs the third-party shims and imports `models`
+    import models
+    original = dict(models.model_lookup)
+    try:
+        from medtsllm_b200 import plugin
+        from medtsllm_b200.model import MedTsLLM
+        lookup = plugin.register()
+        assert lookup["medtsllm"] is MedTsLLM and lookup["timellm"] is MedTsLLM
+        fix = load_case("gpt2_anomaly_concat")
+        llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+        cfg = ref.dict_to_object(config_for(fix, llm_dir))          # the reference's config type
+        model = models.model_lookup[cfg.model](cfg, Dataset(fix["dataset"]))   # == BaseTask.build_model
+        assert isinstance(model, MedTsLLM) and cfg.task in model.supported_tasks
+        assert list(model.state_dict().keys()) == list(fix["adapters"].keys())
+    finally:
+        models.model_lookup.clear(); models.model_lookup.update(original)

@@ -137,13 +137,27 @@ def test_training_step_gradients(name, tmp_path, cuda):
     ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, oracle_spec(fix), training=True)
     assert _rel_l2(out, ref) < 2e-2
     (ref * wgt).sum().backward()
-    report = []
+    report, bad = [], []
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        e = _rel_l2(p.grad, ad[k].grad)
-        report.append(f"{k.split('.')[-2][:8]}.{k.split('.')[-1][0]} {e:.1e}")
-        assert e < 5e-2, (name, k, e)
+        gref = ad[k].grad
+        tag = f"{k.split('.')[-2][:8]}.{k.split('.')[-1][0]}"
+        if k == "reprogramming_layer.key_projection.bias":
+            # d/d(b_k) is EXACTLY zero in exact arithmetic: q.(k + b_k) shifts every score of a query row by
+            # the same amount and softmax is shift invariant.  Both sides only hold rounding noise, so the
+            # check is absolute, against the scale of the sibling weight gradient.
+            scale = model.reprogramming_layer.key_projection.weight.grad.abs().max().item()
+            e = p.grad.abs().max().item() / max(scale, 1e-30)
+            report.append(f"{tag} |g|/|gW| {e:.1e}")
+            if not e < 5e-2:
+                bad.append((k, e))
+            continue
+        e = _rel_l2(p.grad, gref)
+        report.append(f"{tag} {e:.1e}")
+        if not e < 5e-2:
+            bad.append((k, e))
     print(f"\n[grad parity] {name}: " + "  ".join(report))
+    assert not bad, (name, bad)
     # one optimizer step changes the cached bf16 weights (version tracking) and the output
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-2)
     opt.step()
