@@ -181,6 +181,11 @@ int mts_layernorm(const float* x, int64_t ldx, const float* w, const float* b, u
 int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                     uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
                     mts_stream_t stream);
+/* RoPE applied in place to the q and k sections of qkv (same tables / convention as above).  After it,
+ * call mts_attn_causal with NULL tables: short sequences (K and V of one head fit in shared memory)
+ * then take the single-staging kernel. */
+int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int L, int H,
+                int hd, mts_stream_t stream);
 
 /* row softmax with scale: p = softmax(scale * s) over the last axis.
  *   s fp32 [rows, n], p bf16 [rows, n]   (ref: models/medtsllm.py:587, reprogramming scores) */
@@ -225,10 +230,13 @@ int mts_layernorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_
 
 /* Causal attention backward (ref: autograd of HF eager attention, HF:models/llama/modeling_llama.py:
  * 199-221).  qkv/out/lse as produced by mts_attn_causal; dout bf16 [Bp*L, H*hd]; delta fp32 [Bp,H,L]
- * workspace; dqkv bf16 [Bp*L, 3*H*hd] receives d(q|k|v) w.r.t. the (un-rotated) projection outputs. */
+ * workspace; dqkv bf16 [Bp*L, 3*H*hd] receives d(q|k|v) w.r.t. the (un-rotated) projection outputs.
+ * pre_roped != 0: qkv already holds rotated q/k (mts_rope_qk); tables are then only used to rotate
+ * dq/dk back. */
 int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                         const uint16_t* out, const uint16_t* dout, const float* lse, float* delta,
-                        uint16_t* dqkv, int Bp, int L, int H, int hd, float scale, mts_stream_t stream);
+                        uint16_t* dqkv, int Bp, int L, int H, int hd, float scale, int pre_roped,
+                        mts_stream_t stream);
 
 /* SwiGLU on saved pre-activations.  Activation column j reads gate column (j/blk)*2*blk + j%blk and
  * the up column blk further: blk = 128 for the packed layout (mts_pack_gate_up), blk = I for [g|u].

@@ -227,9 +227,249 @@ attn_causal_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// RoPE in place on the q and k sections of a [Bp*L, 3*H*hd] bf16 buffer (rotate-half, position =
+// row index inside the sample).  16 bytes per access; bytes: 8*M*D read + written.
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cosb,
+                               const float* __restrict__ sinb, int64_t rows, int L, int H, int hd) {
+  const int half = hd >> 1;
+  const int vec_per_head = half >> 3;                 // 8 column pairs per item
+  const int64_t per_row = (int64_t)2 * H * vec_per_head;  // q heads then k heads
+  const int64_t total = rows * per_row;
+  const int64_t D = (int64_t)H * hd;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / per_row;
+    const int rem = (int)(idx - row * per_row);
+    const int head = rem / vec_per_head;              // 0..2H-1 (>= H: key heads)
+    const int j = (rem - head * vec_per_head) * 8;
+    const int pos = (int)(row % L);
+    __nv_bfloat16* base = qkv + row * 3 * D + (int64_t)head * hd;  // k section follows q contiguously
+    const uint4 a = *reinterpret_cast<const uint4*>(base + j);
+    const uint4 b = *reinterpret_cast<const uint4*>(base + half + j);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    const float* cr = cosb + (int64_t)pos * half + j;
+    const float* sr = sinb + (int64_t)pos * half + j;
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x1a = bf16_lo(aw[q]), x1b = bf16_hi(aw[q]);
+      const float x2a = bf16_lo(bw[q]), x2b = bf16_hi(bw[q]);
+      const float ca = cr[2 * q], cb = cr[2 * q + 1], sa = sr[2 * q], sb = sr[2 * q + 1];
+      lo[q] = pack_bf16(x1a * ca - x2a * sa, x1b * cb - x2b * sb);
+      hi[q] = pack_bf16(x2a * ca + x1a * sa, x2b * cb + x1b * sb);
+    }
+    *reinterpret_cast<uint4*>(base + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(base + half + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Forward, short sequences (the whole K and V of one (sample, head) fit in shared memory, L <= ~350
+// at hd = 128): one CTA per (b, h), K/V staged ONCE with cp.async (q/k already rotated by
+// rope_qk_kernel), 8 warps pull 16-query strips from a shared counter, heaviest (latest) strips
+// first.  Key tiles beyond a strip's causal limit are skipped at 16-key granularity.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSeqThreads = 256;
+
+template <int HD>
+__global__ void __launch_bounds__(kSeqThreads)
+attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                           float* __restrict__ lse, int L, int H, float scale_log2e) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int Lp = (L + 63) & ~63;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Vs = Ks + (size_t)Lp * kPitch;
+  __nv_bfloat16* Qw = Vs + (size_t)Lp * kPitch;           // [8 warps][16][kPitch]
+  int* counter = reinterpret_cast<int*>(Qw + 8 * 16 * kPitch);
+
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+
+  constexpr int kVec = HD / 8;
+  for (int i = threadIdx.x; i < Lp * kVec; i += kSeqThreads) {
+    const int r = i / kVec, c = (i - r * kVec) * 8;
+    if (r < L) {
+      cp_async16(smem_u32(Ks + r * kPitch + c), kbase + (int64_t)r * ld + c);
+      cp_async16(smem_u32(Vs + r * kPitch + c), vbase + (int64_t)r * ld + c);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  if (threadIdx.x == 0) *counter = 0;
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int n_strips = (L + 15) >> 4;
+  __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
+  while (true) {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counter, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_strips) break;
+    const int q0 = (n_strips - 1 - ticket) * 16;   // heaviest strips first
+    // stage this warp's 16 query rows
+    for (int i = lane; i < 16 * kVec; i += 32) {
+      const int r = i / kVec, c = (i - r * kVec) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (q0 + r < L) v = *reinterpret_cast<const uint4*>(qbase + (int64_t)(q0 + r) * ld + c);
+      *reinterpret_cast<uint4*>(Qs + r * kPitch + c) = v;
+    }
+    __syncwarp();
+    uint32_t qf[HD / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks)
+      ldmatrix_x4(smem_u32(Qs + (lane & 15) * kPitch + ks * 16 + (lane >> 4) * 8), qf[ks][0], qf[ks][1],
+                  qf[ks][2], qf[ks][3]);
+
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
+    const int row_a = q0 + g, row_b = row_a + 8;
+    const int last_row = min(q0 + 15, L - 1);
+
+    for (int j0 = 0; j0 <= last_row; j0 += 64) {
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (j0 + np * 16 > last_row) continue;   // warp-uniform causal skip
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const int id = lane >> 3;
+          uint32_t r0, r1, r2, r3;
+          ldmatrix_x4(smem_u32(Ks + (j0 + np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch + ks * 16 + (id & 1) * 8),
+                      r0, r1, r2, r3);
+          mma_bf16_16816(s[2 * np], qf[ks], r0, r1);
+          mma_bf16_16816(s[2 * np + 1], qf[ks], r2, r3);
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+          const int row = (e < 2) ? row_a : row_b;
+          float v = s[nt][e] * scale_log2e;
+          if (col > row || col >= L) v = -INFINITY;
+          s[nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+      }
+      float alpha[2], m_new[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        m_new[r] = fmaxf(m_run[r], mx[r]);
+        const float m_safe = (m_new[r] == -INFINITY) ? 0.0f : m_new[r];
+        alpha[r] = exp2f(m_run[r] - m_safe);
+        m_run[r] = m_new[r];
+        m_new[r] = m_safe;
+        l_run[r] *= alpha[r];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f(s[nt][e] - m_new[e >> 1]);
+          s[nt][e] = pv;
+          l_run[e >> 1] += pv;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+        o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (j0 + kk * 16 > last_row) continue;   // P is identically zero there
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int np = 0; np < HD / 16; ++np) {
+          const int id = lane >> 3;
+          uint32_t r0, r1, r2, r3;
+          ldmatrix_x4_trans(smem_u32(Vs + (j0 + kk * 16 + (id & 1) * 8 + (lane & 7)) * kPitch + np * 16 + (id >> 1) * 8),
+                            r0, r1, r2, r3);
+          mma_bf16_16816(o[2 * np], pa, r0, r1);
+          mma_bf16_16816(o[2 * np + 1], pa, r2, r3);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv_a = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f;
+    const float inv_b = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
+    __nv_bfloat16* obase = out + (int64_t)b * L * D + (int64_t)h * HD;
+#pragma unroll
+    for (int nt = 0; nt < HD / 8; ++nt) {
+      const int col = nt * 8 + tq * 2;
+      if (row_a < L)
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)row_a * D + col) = pack_bf16(o[nt][0] * inv_a, o[nt][1] * inv_a);
+      if (row_b < L)
+        *reinterpret_cast<uint32_t*>(obase + (int64_t)row_b * D + col) = pack_bf16(o[nt][2] * inv_b, o[nt][3] * inv_b);
+    }
+    if (lse && tq == 0) {
+      if (row_a < L) lse[(int64_t)bh * L + row_a] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
+      if (row_b < L) lse[(int64_t)bh * L + row_b] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
+    }
+    __syncwarp();   // Qs is re-staged by the next strip
+  }
+}
+
+template <int HD>
+static size_t seq_smem_bytes(int L) {
+  const int Lp = (L + 63) & ~63;
+  return (size_t)(2 * Lp + 8 * 16) * (HD + 8) * 2 + 16;
+}
+
 template <int HD>
 static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, uint16_t* out,
                        float* lse, int Bp, int L, int H, float scale, cudaStream_t stream) {
+  if (rc == nullptr && seq_smem_bytes<HD>(L) <= 220 * 1024) {
+    auto ks = attn_causal_fwd_seq_kernel<HD>;
+    static bool seq_attr_done = false;
+    if (!seq_attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn seq)", e);
+      seq_attr_done = true;
+    }
+    ks<<<Bp * H, kSeqThreads, seq_smem_bytes<HD>(L), stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, L, H,
+        scale * 1.4426950408889634f);
+    count_launch();
+    return check_launch("attn_causal_fwd_seq_kernel");
+  }
   constexpr int kSmem = 3 * 64 * (HD + 8) * 2;
   auto kern = attn_causal_fwd_kernel<HD>;
   static bool attr_done = false;
@@ -365,7 +605,7 @@ __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                    const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta,
-                   __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale, int pre_roped) {
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -383,7 +623,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   const __nv_bfloat16* kbase = qbase + D;
   const __nv_bfloat16* vbase = qbase + 2 * D;
   const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
-  const bool rope = rope_cos != nullptr;
+  const bool rope = rope_cos != nullptr && !pre_roped;   // rotate while staging?
+  const bool unrope = rope_cos != nullptr;               // rotate the gradients back on store
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
@@ -425,7 +666,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
     mma_p_b<HD>(dq, s, Ks, lane);
   }
   store_grad_rows<HD>(dq, dqkv + (int64_t)b * L * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq,
-                      rope ? rope_cos : nullptr, rope_sin);
+                      unrope ? rope_cos : nullptr, rope_sin);
 }
 
 template <int HD>
@@ -433,7 +674,7 @@ __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                     const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta,
-                    __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+                    __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale, int pre_roped) {
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -453,7 +694,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   const __nv_bfloat16* kbase = qbase + D;
   const __nv_bfloat16* vbase = qbase + 2 * D;
   const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
-  const bool rope = rope_cos != nullptr;
+  const bool rope = rope_cos != nullptr && !pre_roped;   // rotate while staging?
+  const bool unrope = rope_cos != nullptr;               // rotate the gradients back on store
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
@@ -502,14 +744,14 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     mma_p_b<HD>(dk, dpt, Qs, lane);
   }
   __nv_bfloat16* dbase = dqkv + (int64_t)b * L * ld + (int64_t)h * HD;
-  store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, L, tq, rope ? rope_cos : nullptr, rope_sin);
+  store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, L, tq, unrope ? rope_cos : nullptr, rope_sin);
   store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, L, tq, nullptr, nullptr);
 }
 
 template <int HD>
 static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
                            const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp,
-                           int L, int H, float scale, cudaStream_t stream) {
+                           int L, int H, float scale, int pre_roped, cudaStream_t stream) {
   constexpr int kSmemQ = 4 * 64 * (HD + 8) * 2;
   constexpr int kSmemKV = kSmemQ + 2 * 64 * 4;
   auto kq = attn_bwd_dq_kernel<HD>;
@@ -531,13 +773,13 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
   if (grid_l > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: grid too large");
   kq<<<(int)grid_l, kAttnThreads, kSmemQ, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale, pre_roped);
   count_launch();
   rc_ = check_launch("attn_bwd_dq_kernel");
   if (rc_) return rc_;
   kkv<<<(int)grid_l, kAttnThreads, kSmemKV, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale, pre_roped);
   count_launch();
   return check_launch("attn_bwd_dkv_kernel");
 }
@@ -566,7 +808,7 @@ extern "C" int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const
 extern "C" int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                                    const uint16_t* out, const uint16_t* dout, const float* lse,
                                    float* delta, uint16_t* dqkv, int Bp, int L, int H, int hd,
-                                   float scale, mts_stream_t s) {
+                                   float scale, int pre_roped, mts_stream_t s) {
   if (!qkv || !out || !dout || !lse || !delta || !dqkv || Bp <= 0 || L <= 0 || H <= 0)
     return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: bad args");
   if ((rope_cos == nullptr) != (rope_sin == nullptr))
@@ -575,8 +817,23 @@ extern "C" int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, c
       (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3))
     return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: misaligned pointer");
   switch (hd) {
-    case 64: return launch_attn_bwd<64>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, (cudaStream_t)s);
-    case 128: return launch_attn_bwd<128>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, (cudaStream_t)s);
+    case 64: return launch_attn_bwd<64>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, pre_roped, (cudaStream_t)s);
+    case 128: return launch_attn_bwd<128>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, pre_roped, (cudaStream_t)s);
     default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_bwd: head dim %d (supported: 64, 128)", hd);
   }
+}
+
+extern "C" int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int L, int H,
+                           int hd, mts_stream_t s) {
+  if (!qkv || !rope_cos || !rope_sin || Bp <= 0 || L <= 0 || H <= 0 || hd <= 0 || (hd % 16))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_rope_qk: bad args (hd must be a multiple of 16)");
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) return set_error(MTS_ERR_INVALID_ARG, "mts_rope_qk: misaligned qkv");
+  const int64_t rows = (int64_t)Bp * L;
+  const int64_t total = rows * 2 * H * (hd / 16);
+  int64_t g = (total + 255) / 256;
+  if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
+  rope_qk_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
+                                                     rows, L, H, hd);
+  count_launch();
+  return check_launch("rope_qk_kernel");
 }

@@ -56,7 +56,8 @@ SIGNATURES = {
     "mts_softmax_lastdim": [_p, _i64, _i, _p],
     "mts_rmsnorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
     "mts_layernorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
-    "mts_attn_causal_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
+    "mts_attn_causal_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p],
+    "mts_rope_qk": [_p, _p, _p, _i, _i, _i, _i, _p],
     "mts_swiglu_blk": [_p, _i64, _p, _i64, _i, _i, _p],
     "mts_swiglu_bwd": [_p, _i64, _p, _p, _i64, _i, _i, _p],
     "mts_gelu_new": [_p, _p, _p, _i64, _p],

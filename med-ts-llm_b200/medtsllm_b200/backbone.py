@@ -259,10 +259,12 @@ class KernelBackbone:
                 ops.layernorm(x_in, lay["ln1"], lay["ln1b"], s.eps, out=h)
                 ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"], bias_axis=BIAS_N)
             lse = None
+            if rope is not None:
+                ops.rope_qk_(qkv, Bp, L, H, hd, rope)      # q, k rotated in place; attention stages them as is
             if train:
-                _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att, want_lse=True)
+                _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att, want_lse=True)
             else:
-                ops.attn_causal(qkv, Bp, L, H, hd, rope=rope, out=att)
+                ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att)
             x_mid = torch.empty_like(x_in) if train else x_in
             ops.gemm(att, lay["wo"], x_mid, m=M, n=D, k=D, epilogue=EPI_RESID_ADD, c=x_in if train else None,
                      bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
@@ -336,7 +338,8 @@ class KernelBackbone:
             ops.cast_bf16(dR, out=dRb)
             datt = bf(M, D)
             ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
-            dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope)
+            dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
+                                       pre_roped=rope is not None)
             ops.gemm(dqkv, lay["wqkv_t"], dH, m=M, n=D, k=3 * D)
             norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True)
         return dR

@@ -311,7 +311,17 @@ def layernorm_bwd(x, w, dy, dx, eps, accumulate=True):
     return dx
 
 
-def attn_causal_bwd(qkv, out, dout, lse, Bp, L, H, hd, *, rope=None, scale=None):
+def rope_qk_(qkv, Bp, L, H, hd, rope):
+    """In-place rotate-half RoPE on the q and k sections of qkv bf16 [Bp*L, 3*H*hd]."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    cos, sin = rope
+    if not qkv.is_contiguous() or cos.shape[0] < L or cos.shape[1] != hd // 2:
+        raise MtsError("rope_qk_: contiguous qkv and [>=L, hd/2] tables required")
+    _lib.call("mts_rope_qk", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), Bp, L, H, hd, _stream())
+    return qkv
+
+
+def attn_causal_bwd(qkv, out, dout, lse, Bp, L, H, hd, *, rope=None, scale=None, pre_roped=False):
     _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
     _chk(lse, torch.float32, "lse")
     if scale is None:
@@ -320,7 +330,8 @@ def attn_causal_bwd(qkv, out, dout, lse, Bp, L, H, hd, *, rope=None, scale=None)
     delta = torch.empty(Bp, H, L, device=qkv.device, dtype=torch.float32)
     cos, sin = rope if rope is not None else (None, None)
     _lib.call("mts_attn_causal_bwd", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), dout.data_ptr(),
-              lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, L, H, hd, scale, _stream())
+              lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, L, H, hd, scale, 1 if pre_roped else 0,
+              _stream())
     return dqkv
 
 

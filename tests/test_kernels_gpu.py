@@ -398,3 +398,28 @@ def test_attn_causal_bwd(ops, cuda, Bp, L, H, hd, rope):
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         err = _rel_l2(dqkv[:, sl], gx[:, sl])
         assert err < 1.5e-2, (name, err)     # bf16 P / dS / outputs
+
+
+@pytest.mark.parametrize("Bp,L,H,hd", [(2, 192, 3, 128), (1, 100, 2, 64), (2, 256, 1, 128)])
+def test_rope_kernel_and_seq_attention_match_fused_path(ops, cuda, Bp, L, H, hd):
+    """mts_rope_qk + the single-staging forward (and the pre-roped backward) against the kernels that
+    rotate while staging: same arithmetic, so the results agree to bf16 rounding of the outputs."""
+    g = torch.Generator().manual_seed(L + hd + 1)
+    D = H * hd
+    qkv = (torch.randn(Bp * L, 3 * D, generator=g) * 0.8).to(cuda, torch.bfloat16)
+    dout = torch.randn(Bp * L, D, generator=g).to(cuda, torch.bfloat16)
+    tabs = _rope_tables(L, hd, cuda)
+    out1, lse1 = ops.attn_causal(qkv, Bp, L, H, hd, rope=tabs, want_lse=True)
+    dqkv1 = ops.attn_causal_bwd(qkv, out1, dout, lse1, Bp, L, H, hd, rope=tabs)
+    roped = ops.rope_qk_(qkv.clone(), Bp, L, H, hd, tabs)
+    # the rotation itself: fp32 math on bf16 inputs, rounded once
+    q = qkv[:, :D].float().view(Bp, L, H, hd)
+    cos = torch.cat([tabs[0], tabs[0]], -1)[None, :, None]; sin = torch.cat([tabs[1], tabs[1]], -1)[None, :, None]
+    rot = torch.cat([-q[..., hd // 2:], q[..., :hd // 2]], -1)
+    torch.testing.assert_close(roped[:, :D].float().view(Bp, L, H, hd), q * cos + rot * sin, rtol=8e-3, atol=1e-5)
+    assert torch.equal(roped[:, 2 * D:], qkv[:, 2 * D:])                     # v untouched
+    out2, lse2 = ops.attn_causal(roped, Bp, L, H, hd, rope=None, want_lse=True)
+    torch.testing.assert_close(out2.float(), out1.float(), rtol=2e-2, atol=4e-3)
+    torch.testing.assert_close(lse2, lse1, rtol=1e-4, atol=1e-4)
+    dqkv2 = ops.attn_causal_bwd(roped, out2, dout, lse2, Bp, L, H, hd, rope=tabs, pre_roped=True)
+    assert _rel_l2(dqkv2, dqkv1) < 5e-3
