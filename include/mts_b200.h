@@ -117,7 +117,8 @@ int mts_revin_denorm(float* y, const float* mean, const float* stdev, int B, int
  */
 typedef enum mts_epilogue {
   MTS_EPI_STORE = 0,     /* D = v                      (D bf16 or fp32)                          */
-  MTS_EPI_RESID_ADD = 1, /* D = C + v                  (D, C fp32; C = D when args.c is NULL)     */
+  MTS_EPI_RESID_ADD = 1, /* D = C + v   (D, C fp32; C = D when args.c is NULL) or, with bf16 D,   */
+                         /* D = bf16(D + v) in place (LoRA side GEMMs accumulating into q / v)   */
   MTS_EPI_GELU_NEW = 2,  /* D = gelu_new(v)            (D bf16; HF:activations.py:59-66)         */
   MTS_EPI_SWIGLU = 3     /* D[:, j] = silu(v_gate[j]) * v_up[j]   (D bf16, n/2 columns).  B rows  */
                          /* must be packed by mts_pack_gate_up: blocks of 128 gate rows followed  */
@@ -254,6 +255,8 @@ int mts_softmax_bwd_rows(const uint16_t* p, const float* dp, uint16_t* ds, int64
 /* out[c] = sum_r x[r*ld + c]  (bias gradients); dtype: mts_dtype of x */
 int mts_colsum(const void* x, int dtype, int64_t ld, float* out, int rows, int cols,
                mts_stream_t stream);
+/* out[r] = sum_c x[r*ld + c]  (fp32; mapping-layer bias gradient) */
+int mts_rowsum_f32(const float* x, int64_t ld, float* out, int rows, int cols, mts_stream_t stream);
 /* out[c*ld_out + b*rows + r] = bf16(in[b*in_batch_stride + r*ld_in + c]); dtype: mts_dtype of in */
 int mts_transpose_strided(const void* in, int dtype, int64_t ld_in, int64_t in_batch_stride,
                           uint16_t* out, int64_t ld_out, int batch, int rows, int cols,

@@ -222,6 +222,19 @@ colsum_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int 
   }
 }
 
+// row sums in fp32 (mapping-layer bias gradient = row sums of dSource): one warp per row
+__global__ void __launch_bounds__(256)
+rowsum_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * ld;
+  float acc = 0.f;
+  for (int i = lane; i < cols; i += 32) acc += xr[i];
+  acc = bw_warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 // ------------------------------------------------------------------------------------------
 // general strided transpose with cast to bf16:
 //   out[c * ld_out + (b*rows + r)] = in[b*in_bs + r*ld_in + c]      (b < batch, r < rows, c < cols)
@@ -436,4 +449,12 @@ extern "C" int mts_revin_denorm_bwd(const float* dy, const float* stdev, float* 
   scale_by_std_kernel<<<bw_grid(total, 256), 256, 0, (cudaStream_t)s>>>(dy, stdev, out, total, T, C);
   count_launch();
   return check_launch("scale_by_std_kernel");
+}
+
+extern "C" int mts_rowsum_f32(const float* x, int64_t ld, float* out, int rows, int cols, mts_stream_t s) {
+  if (!x || !out || rows <= 0 || cols <= 0 || ld < cols)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_rowsum_f32: bad args");
+  rowsum_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(x, ld, out, rows, cols);
+  count_launch();
+  return check_launch("rowsum_kernel");
 }

@@ -282,6 +282,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if constexpr (EPI == MTS_EPI_RESID_ADD) val += p.c[off];
                 reinterpret_cast<float*>(p.d)[off] = val;
               } else {
+                if constexpr (EPI == MTS_EPI_RESID_ADD)
+                  val += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.d)[off]);
                 reinterpret_cast<__nv_bfloat16*>(p.d)[off] = __float2bfloat16_rn(val);
               }
             }
@@ -328,8 +330,13 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int ps = 0; ps < 4; ++ps) {
             const int r_g = row0 + ps * 8 + rr;
             if (col_ok && r_g < p.m) {
-              const float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
-              const float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
+              float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
+              float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
+              if constexpr (EPI == MTS_EPI_RESID_ADD) {   // bf16 accumulate (LoRA side GEMMs): D = bf16(D + v)
+                const uint4 old = *reinterpret_cast<const uint4*>(dbase + (int64_t)r_g * p.ldd);
+                a0.x += bf16_lo(old.x); a0.y += bf16_hi(old.x); a0.z += bf16_lo(old.y); a0.w += bf16_hi(old.y);
+                a1.x += bf16_lo(old.z); a1.y += bf16_hi(old.z); a1.z += bf16_lo(old.w); a1.w += bf16_hi(old.w);
+              }
               *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd) =
                   make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
                              pack_bf16(a1.z, a1.w));
@@ -430,8 +437,9 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
     case MTS_EPI_STORE:
       break;
     case MTS_EPI_RESID_ADD:
-      if (!f32 || a->d_transposed)
-        return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: RESID_ADD needs fp32 non-transposed D");
+      if (a->d_transposed || (!f32 && a->c))
+        return set_error(MTS_ERR_INVALID_ARG,
+                         "mts_gemm: RESID_ADD needs a non-transposed D (fp32 with optional C, or bf16 in place)");
       break;
     case MTS_EPI_GELU_NEW:
       if (f32 || a->d_transposed)

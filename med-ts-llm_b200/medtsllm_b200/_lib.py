@@ -63,6 +63,7 @@ SIGNATURES = {
     "mts_gelu_new": [_p, _p, _p, _i64, _p],
     "mts_softmax_bwd_rows": [_p, _p, _p, _i64, _i, _f, _p],
     "mts_colsum": [_p, _i, _i64, _p, _i, _i, _p],
+    "mts_rowsum_f32": [_p, _i64, _p, _i, _i, _p],
     "mts_transpose_strided": [_p, _i, _i64, _i64, _p, _i64, _i, _i, _i, _p],
     "mts_cast_rows_f32_bf16": [_p, _i64, _i64, _p, _i64, _i, _i, _i, _p],
     "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],

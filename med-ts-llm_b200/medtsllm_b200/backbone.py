@@ -229,7 +229,7 @@ class KernelBackbone:
             self._embed_bf16 = ops.cast_bf16(self.embed)
         return self._embed_bf16
 
-    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None):
+    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None, lora=None):
         """x: fp32 residual stream [Bp*L, D].  Inference (stash None): updated IN PLACE layer by layer.
         Training (stash = list): every residual write goes to a fresh buffer (the GEMM epilogue reads
         C = previous stream, writes D = new one) and the per-layer tensors backward() needs are
@@ -247,9 +247,11 @@ class KernelBackbone:
         bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
         h, qkv, att = bf(M, D), bf(M, 3 * D), bf(M, D)
         llama = s.kind == "llama"
-        for lay in self.layers:
+        for li, lay in enumerate(self.layers):
             if train:
                 qkv, att = bf(M, 3 * D), bf(M, D)
+                if lora is not None:
+                    h = bf(M, D)          # the LoRA backward needs this layer's normed input
             x_in = x
             # --- attention half
             if llama:
@@ -258,6 +260,8 @@ class KernelBackbone:
             else:
                 ops.layernorm(x_in, lay["ln1"], lay["ln1b"], s.eps, out=h)
                 ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"], bias_axis=BIAS_N)
+            lora_t = lora.forward_layer(li, h, qkv, M, D) if lora is not None else None
+            h_attn = h
             lse = None
             if rope is not None:
                 ops.rope_qk_(qkv, Bp, L, H, hd, rope)      # q, k rotated in place; attention stages them as is
@@ -270,6 +274,8 @@ class KernelBackbone:
                      bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
             # --- MLP half
             x_out = torch.empty_like(x_in) if train else x_in
+            if train and lora is not None:
+                h = bf(M, D)
             if llama:
                 ops.rmsnorm(x_mid, lay["ln2"], s.eps, out=h)
                 if train:   # keep the gate/up pre-activations (packed column order) for the backward
@@ -296,7 +302,8 @@ class KernelBackbone:
                 ops.gemm(act, lay["wproj"], x_out, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
                          epilogue=EPI_RESID_ADD, c=x_mid if train else None)
             if train:
-                stash.append(dict(x_in=x_in, x_mid=x_mid, qkv=qkv, att=att, lse=lse, pre=pre))
+                stash.append(dict(x_in=x_in, x_mid=x_mid, qkv=qkv, att=att, lse=lse, pre=pre,
+                                  h=h_attn if lora is not None else None, lora_t=lora_t))
             x = x_out
         out = bf(M, D)
         if llama:
@@ -305,9 +312,10 @@ class KernelBackbone:
             ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
         return out, x
 
-    def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int) -> torch.Tensor:
+    def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None):
         """dgrad through the frozen stack: dhid = dL/d(final-norm output) bf16 [Bp*L, D] -> returns
-        dL/d(input residual stream) fp32 [Bp*L, D].  No weight gradients (frozen)."""
+        (dL/d(input residual stream) fp32 [Bp*L, D], LoRA gradients aligned with lora.params() or None).
+        No gradients for the frozen weights."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
         M = Bp * L
@@ -320,7 +328,8 @@ class KernelBackbone:
         dR = torch.empty(M, D, device=dev, dtype=torch.float32)
         norm_bwd(x_final, self.final_norm_w, dhid, dR, s.eps, accumulate=False)
         dRb, dH = bf(M, D), bf(M, D)
-        for lay, st in zip(reversed(self.layers), reversed(stash)):
+        lora_grads = [None] * len(lora.params()) if lora is not None else None
+        for li, lay, st in zip(reversed(range(len(self.layers))), reversed(self.layers), reversed(stash)):
             # --- MLP half: x_out = x_mid + W2 act(W1 norm(x_mid))
             ops.cast_bf16(dR, out=dRb)
             if llama:
@@ -341,8 +350,14 @@ class KernelBackbone:
             dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
                                        pre_roped=rope is not None)
             ops.gemm(dqkv, lay["wqkv_t"], dH, m=M, n=D, k=3 * D)
+            if lora is not None:
+                dAs, dBs = lora.backward_layer(li, st["h"], st["lora_t"], dqkv, dH, M, D)
+                nA = len(lora.A)
+                for t in range(len(lora.targets)):
+                    lora_grads[lora.index(li, t)] = dAs[t]
+                    lora_grads[nA + lora.index(li, t)] = dBs[t]
             norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True)
-        return dR
+        return dR, lora_grads
 
     def flops_per_token_fwd(self, L: int) -> float:
         """Dense algorithmic forward FLOPs per token: 2*W_blk + 4*L*D per layer."""

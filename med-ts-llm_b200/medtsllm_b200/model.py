@@ -170,12 +170,11 @@ class MedTsLLM(nn.Module):
         self.embedding_downsample_mode = _get(mc, "embedding_downsample_mode")
         if self.embedding_downsample_mode == "linear":
             self.embedding_downsample_layer = nn.Linear(self.d_llm, self.d_ff)
-        elif self.embedding_downsample_mode in ("truncate", "average"):
-            raise NotImplementedError(
-                f"embedding_downsample_mode={self.embedding_downsample_mode!r} is listed as next in DESIGN.md "
-                "(shipped configs use 'linear')")
-        else:
+        elif self.embedding_downsample_mode == "average":
+            assert self.d_llm % self.d_ff == 0                                 # models/medtsllm.py:100-101
+        elif self.embedding_downsample_mode != "truncate":
             raise ValueError(f"Unknown embedding downsample mode {self.embedding_downsample_mode}")
+        self._ds_fixed = None      # constant [d_ff, D] selection / averaging matrix for truncate / average
 
         if self.dropout and self.dropout > 0:
             # PatchEmbedding / reprogramming dropout (models/medtsllm.py:93-94) are training-time noise;
@@ -203,7 +202,9 @@ class MedTsLLM(nn.Module):
         lora = _get(mc, "lora")
         self.lora_enabled = bool(lora is not None and _get(lora, "enabled"))
         if self.lora_enabled:
-            raise NotImplementedError("LoRA is listed as next in DESIGN.md")
+            assert _get(lora, "layers") == "auto"                         # models/medtsllm.py:190
+            if _get(lora, "dropout", 0.0):
+                raise NotImplementedError("lora.dropout > 0 (dropout is not implemented on the kernel path)")
         dtype_name = _get(_get(self.config, "setup"), "dtype")
         if dtype_name not in ("float32", "float", "fp32", "32", 32, "mixed"):
             raise NotImplementedError(
@@ -242,6 +243,15 @@ class MedTsLLM(nn.Module):
         if spec.vocab > 100_000:
             raise NotImplementedError("vocabularies > 100k (sub-sampled trainable word_embeddings, "
                                       "models/medtsllm.py:219-222) are outside the BASELINE configs")
+        if self.lora_enabled:
+            from .lora import LoraAdapters
+            init = _get(lora, "init", True)
+            if init not in (True, False):
+                raise NotImplementedError(f"lora.init = {init!r}")
+            llm_config = self.llm.config
+            self.llm = LoraAdapters(spec, _get(lora, "rank"), _get(lora, "alpha"), rslora=_get(lora, "rslora", True),
+                                    init=bool(init))
+            self.llm.config = llm_config
         self.backbone_spec: BackboneSpec = spec
         self.vocab_size = spec.vocab
         self.d_llm = spec.hidden
@@ -261,8 +271,12 @@ class MedTsLLM(nn.Module):
         return self
 
     def state_dict(self, *args, **kwargs):
-        # adapters only, as the reference (models/medtsllm.py:235-246); the backbone is not a Module
-        return super().state_dict(*args, **kwargs)
+        # adapters only, as the reference (models/medtsllm.py:235-246): the frozen backbone is not a Module and
+        # `llm.*` (LoRA pairs; saved separately through llm.save_pretrained, loggers/base_logger.py:42-43) is dropped
+        sd = super().state_dict(*args, **kwargs)
+        for k in [k for k in sd if k.startswith("llm.")]:
+            del sd[k]
+        return sd
 
     def load_pretrained(self, saved_state):
         """models/medtsllm.py:515-527."""
@@ -387,10 +401,35 @@ class MedTsLLM(nn.Module):
         "output_projection.linear.weight", "output_projection.linear.bias",
     )
 
-    def adapter_params(self):
-        """The trainable tensors in PARAM_ORDER (the 15 adapter tensors of the shipped configs)."""
+    def param_order(self):
+        """PARAM_ORDER restricted to the tensors this configuration has (no down-sample Linear for the
+        truncate / average modes)."""
         named = dict(self.named_parameters())
-        return [named[k] for k in self.PARAM_ORDER]
+        return [k for k in self.PARAM_ORDER if k in named]
+
+    def adapter_params(self):
+        """The trainable tensors (15 adapter tensors with the shipped configs) + LoRA pairs if enabled."""
+        named = dict(self.named_parameters())
+        return [named[k] for k in self.param_order()] + (self.llm.params() if self.lora_enabled else [])
+
+    def _downsample_operands(self):
+        """(W bf16 [d_ff, ld], bias fp32 or None) of the down-sample step (models/medtsllm.py:354-363).
+        `linear` is the trainable Linear; `truncate` (dec[:, :, :d_ff]) and `average` (mean over groups of
+        D/d_ff consecutive features) are the same GEMM with a constant selection / averaging matrix — exact
+        in bf16 (entries 1 or 1/g, fp32 accumulation)."""
+        if self.embedding_downsample_mode == "linear":
+            return (self._bf16_weight("wds", self.embedding_downsample_layer.weight),
+                    self.embedding_downsample_layer.bias.detach())
+        if self._ds_fixed is None or self._ds_fixed.device != self.device:
+            E, D = self.d_ff, self.d_llm
+            w = torch.zeros(E, D, dtype=torch.float32)
+            if self.embedding_downsample_mode == "truncate":
+                w[torch.arange(E), torch.arange(E)] = 1.0
+            else:
+                g = D // E
+                w.view(E, E, g)[torch.arange(E), torch.arange(E), :] = 1.0 / g
+            self._ds_fixed = ops.cast_bf16(w.to(self.device))
+        return self._ds_fixed, None
 
     def _bf16_weight(self, name: str, p: torch.Tensor) -> torch.Tensor:
         """bf16 copy [rows, ceil8(cols)] (zero padded: TMA rows must be 16-byte aligned) of a trainable
@@ -518,15 +557,16 @@ class MedTsLLM(nn.Module):
                        source_embeddings=source.clone(), llm_input=X.clone())
         # backbone
         layer_stash = [] if stash is not None else None
-        hid, x_final = bb.forward(X.view(Bp * L, D), Bp, L, stash=layer_stash)   # bf16 [Bp*L, D], final norm applied
+        hid, x_final = bb.forward(X.view(Bp * L, D), Bp, L, stash=layer_stash,
+                                  lora=self.llm if self.lora_enabled else None)   # bf16 [Bp*L, D], final norm applied
         if cap is not None:
             cap["llm"] = hid.view(Bp, L, D).clone()
 
         # K11: last N tokens -> Linear(D -> d_ff), stored transposed as [Bp, d_ff, N] (flatten index f*N+n)
-        wds = self._bf16_weight("wds", self.embedding_downsample_layer.weight)
+        wds, bds = self._downsample_operands()
         flat = torch.empty(Bp, E * N, device=dev, dtype=torch.bfloat16)
         ops.gemm(hid, wds, flat, m=N, n=E, k=D, batch=Bp, a_off=Lp * D, a_bs=L * D, b_bs=0, d_bs=E * N,
-                 d_transposed=True, ldd=N, bias=self.embedding_downsample_layer.bias.detach(), bias_axis=BIAS_N)
+                 d_transposed=True, ldd=N, ldb=wds.shape[1], bias=bds, bias_axis=BIAS_N if bds is not None else 0)
         # K12: flatten head
         wh = self._bf16_weight("wh", self.output_projection.linear.weight)
         out = torch.empty(Bp, self.n_outputs, device=dev, dtype=torch.float32)

@@ -419,3 +419,12 @@ def revin_denorm_bwd(dy, std):
     out = torch.empty_like(dy)
     _lib.call("mts_revin_denorm_bwd", dy.data_ptr(), std.data_ptr(), out.data_ptr(), B, T, Cc, _stream())
     return out
+
+
+def rowsum(x):
+    """fp32 [rows] = row sums of a contiguous fp32 [rows, cols]."""
+    _chk(x, torch.float32, "x")
+    rows, cols = x.shape
+    out = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.call("mts_rowsum_f32", x.data_ptr(), cols, out.data_ptr(), rows, cols, _stream())
+    return out

@@ -87,22 +87,25 @@ class _HotPathFn(torch.autograd.Function):
         dyds = bf(R, E)
         for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
             ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
-        g_bds = ops.colsum(dyds)
-        hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D,
-                                           in_off=Lp * D)                      # [D, ceil8(R)]
-        g_wds = f32(E, D)
-        ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=R, lda=ops.ceil8(R), ldb=hid_last_t.shape[1])
-        wds = m._bf16_weight("wds", m.embedding_downsample_layer.weight)       # [E, D]
+        g_bds = g_wds = None
+        if m.embedding_downsample_mode == "linear":
+            g_bds = ops.colsum(dyds)
+            hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D,
+                                               in_off=Lp * D)                  # [D, ceil8(R)]
+            g_wds = f32(E, D)
+            ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=R, lda=ops.ceil8(R), ldb=hid_last_t.shape[1])
+        wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
         wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
         dhid = zbf(B * L, D)                                                    # zero for prompt rows
         ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
                  d_bs=L * D, ldd=D, d_off=Lp * D)
 
         # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
-        early = dp.GradBucket([g_wh, g_bh, g_wds, g_bds]).launch()
+        early = dp.GradBucket([g_wh, g_bh] + ([g_wds, g_bds] if g_wds is not None else [])).launch()
 
         # ---- frozen backbone (dgrad only)
-        dR = bb.backward(dhid, st["x_final"], st["layers"], B, L)              # fp32 [B*L, D]
+        dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
+                                     lora=m.llm if m.lora_enabled else None)     # fp32 [B*L, D]
 
         # ---- reprogramming out-projection: X[b, Lp+n] = O W_o^T + b_o
         dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D, in_off=Lp * D)   # bf16 [R, D]
@@ -161,11 +164,12 @@ class _HotPathFn(torch.autograd.Function):
         ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
         ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
         dsrc_b = ops.cast_bf16(dsrc)
-        g_bmap = ops.colsum(ops.transpose_strided(dsrc_b, rows=S, cols=D, ld_out=S, out=bf(D, S)))   # row sums of dsrc
+        g_bmap = ops.rowsum(dsrc)                                              # d b_map[s] = sum_d dSource[s, d]
         g_wmap = f32(S, V)
         ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
 
-        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo]).launch()
+        lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
+        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo] + lora_grads).launch()
         early.finish()
         late.finish()
         ctx.stash = None
@@ -179,4 +183,4 @@ class _HotPathFn(torch.autograd.Function):
             "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
             "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
         }
-        return (None, None) + tuple(grads[k] for k in m.PARAM_ORDER)
+        return (None, None) + tuple(grads[k] for k in m.param_order()) + tuple(lora_grads)

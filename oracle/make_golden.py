@@ -52,6 +52,17 @@ CASES = {
         prompting=dict(dataset=True, task=True, clip=True, input_stats=True),
         descriptions=["Patient is sedated .", "Patient is awake and breathing with pressure support ventilation .",
                       "No notes ."]),
+    # the two parameter-free down-sample modes (models/medtsllm.py:354-363), small on purpose
+    "llama_forecast_truncate": dict(
+        kind="llama", llm=dict(hidden_size=128, heads=2, layers=1, intermediate_size=256, vocab_size=256),
+        task="forecasting", T=48, pred=16, C=2, B=2, num_tokens=64, d_ff=64, covariate_mode="concat",
+        downsample="truncate", description="Synthetic two channel series .",
+        prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    "gpt2_reconstruction_average": dict(
+        kind="gpt2", llm=dict(hidden_size=128, heads=2, layers=1, vocab_size=256),
+        task="reconstruction", T=40, pred=40, C=1, B=3, num_tokens=64, d_ff=32, covariate_mode="univariate",
+        downsample="average", description="Synthetic single channel series .",
+        prompting=dict(dataset=True, task=False, clip=False, input_stats=False)),
 }
 
 
@@ -85,7 +96,7 @@ def make_case(name: str, c: dict, out_path: Path):
         prompting.update(c["prompting"])
         cfg = H.make_config(task=c["task"], history_len=c["T"], pred_len=c["pred"], llm_path=llm_dir,
                             d_ff=c["d_ff"], num_tokens=c["num_tokens"], covariate_mode=c["covariate_mode"],
-                            prompting=prompting)
+                            downsample=c.get("downsample", "linear"), prompting=prompting)
         model = H.build_reference_model(cfg, ds, seed=1)
 
         g = torch.Generator().manual_seed(1234)
@@ -124,7 +135,7 @@ def make_case(name: str, c: dict, out_path: Path):
                 "llm_input": stages["llm_input"],
                 "llm": stages["llm"],
                 "llm.hidden_states": stages["llm.hidden_states"],
-                "downsample": stages["embedding_downsample_layer"],
+                "downsample": stages.get("embedding_downsample_layer"),
                 "output_projection": stages["output_projection"],
                 "revin_mean": stages["revin_mean"],
                 "revin_stdev": stages["revin_stdev"],

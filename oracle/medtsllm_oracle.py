@@ -138,8 +138,16 @@ def causal_attention(q, k, v, scale):
     return torch.softmax(s.float(), dim=-1).to(q.dtype) @ v
 
 
+def lora_delta(h, lora, layer: int, t: int):
+    """peft LoRA (restated from its published arithmetic; peft is absent here, models/medtsllm.py:187-204):
+    scale * B (A h), scale = alpha/sqrt(r) with rsLoRA.  `lora` = {"scale", "n_targets", "A": [...], "B": [...]}
+    with the pairs ordered layer-major, target-minor."""
+    i = layer * lora["n_targets"] + t
+    return lora["scale"] * F.linear(F.linear(h, lora["A"][i]), lora["B"][i])
+
+
 def llama_forward(x, sd, *, n_layers: int, n_heads: int, eps: float, theta: float = 10000.0,
-                  return_hidden: bool = False):
+                  return_hidden: bool = False, lora=None):
     """HF LlamaModel.forward on inputs_embeds (HF:models/llama/modeling_llama.py:375-425, decoder
     layer :303-332, attention :251-300, MLP :171-184).  `sd` uses HF parameter names."""
     B, L, D = x.shape
@@ -149,9 +157,13 @@ def llama_forward(x, sd, *, n_layers: int, n_heads: int, eps: float, theta: floa
     for i in range(n_layers):
         p = f"layers.{i}."
         h = rmsnorm(x, sd[p + "input_layernorm.weight"], eps)
-        q = F.linear(h, sd[p + "self_attn.q_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
-        k = F.linear(h, sd[p + "self_attn.k_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
-        v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(B, L, n_heads, hd).transpose(1, 2)
+        q = F.linear(h, sd[p + "self_attn.q_proj.weight"])
+        k = F.linear(h, sd[p + "self_attn.k_proj.weight"])
+        v = F.linear(h, sd[p + "self_attn.v_proj.weight"])
+        if lora is not None:                      # peft default targets for Llama: q_proj, v_proj
+            q = q + lora_delta(h, lora, i, 0)
+            v = v + lora_delta(h, lora, i, 1)
+        q, k, v = (t.view(B, L, n_heads, hd).transpose(1, 2) for t in (q, k, v))
         q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
         a = causal_attention(q, k, v, hd ** -0.5).transpose(1, 2).reshape(B, L, D)
         x = x + F.linear(a, sd[p + "self_attn.o_proj.weight"])
@@ -175,7 +187,8 @@ def conv1d_hf(x, w, b):
     return x @ w + b
 
 
-def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, return_hidden: bool = False):
+def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, return_hidden: bool = False,
+                 lora=None):
     """HF GPT2Model.forward on inputs_embeds, eval mode (HF:models/gpt2/modeling_gpt2.py:522-636:
     + wpe[0..L) :584-585; block :262-309; attention :144-236; MLP :238-243; ln_f :628)."""
     B, L, D = x.shape
@@ -186,6 +199,8 @@ def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, retur
         p = f"h.{i}."
         h = F.layer_norm(x, (D,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
         qkv = conv1d_hf(h, sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"])
+        if lora is not None:                      # peft default target for GPT-2: the fused c_attn
+            qkv = qkv + lora_delta(h, lora, i, 0)
         q, k, v = (t.view(B, L, n_heads, hd).transpose(1, 2) for t in qkv.split(D, dim=-1))
         a = causal_attention(q, k, v, 1.0 / math.sqrt(hd)).transpose(1, 2).reshape(B, L, D)
         x = x + conv1d_hf(a, sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
@@ -199,7 +214,7 @@ def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, retur
 
 # ----------------------------------------------------------------------------- whole path
 def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training: bool = False,
-                     return_stages: bool = False):
+                     return_stages: bool = False, lora=None):
     """MedTsLLM.forward/predict (models/medtsllm.py:248-261, 321-384) for covariate modes
     `concat` / `univariate` and all three down-sample modes, dropout = 0.
 
@@ -235,10 +250,10 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     stages["llm_input"] = llm_in
     if spec["backbone"] == "llama":
         dec, hidden = llama_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
-                                    eps=spec["eps"], theta=spec.get("rope_theta", 10000.0), return_hidden=True)
+                                    eps=spec["eps"], theta=spec.get("rope_theta", 10000.0), return_hidden=True, lora=lora)
     else:
         dec, hidden = gpt2_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
-                                   eps=spec["eps"], return_hidden=True)
+                                   eps=spec["eps"], return_hidden=True, lora=lora)
     stages["llm"] = dec
     stages["llm.hidden_states"] = hidden
 

@@ -15,7 +15,8 @@ for p in (REPO, REPO / "med-ts-llm_b200"):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))
 
-CASES = ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate", "llama_forecast_clip_stats"]
+CASES = ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate", "llama_forecast_clip_stats",
+         "llama_forecast_truncate", "gpt2_reconstruction_average"]
 
 
 def load_case(name: str) -> dict:

@@ -82,9 +82,15 @@ def test_unsupported_options_fail_loudly(tmp_path):
     with pytest.raises(NotImplementedError):
         MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
     cfg = config_for(fix, llm_dir)
-    cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16}
+    cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16, "dropout": 0.1}
     with pytest.raises(NotImplementedError):
         MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    # LoRA itself is supported: adapters live under model.llm and stay out of the checkpoint like the reference
+    cfg["models"]["medtsllm"]["lora"]["dropout"] = 0.0
+    m = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    assert m.lora_enabled and not any(k.startswith("llm.") for k in m.state_dict())
+    n_lora = sum(p.numel() for n, p in m.named_parameters() if n.startswith("llm."))
+    assert n_lora == 2 * 2 * 2 * 8 * 128          # layers x (q, v) x (A, B) x r x D
 
 
 def test_plugin_registers_into_reference_model_lookup(tmp_path):

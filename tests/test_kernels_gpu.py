@@ -423,3 +423,24 @@ def test_rope_kernel_and_seq_attention_match_fused_path(ops, cuda, Bp, L, H, hd)
     torch.testing.assert_close(lse2, lse1, rtol=1e-4, atol=1e-4)
     dqkv2 = ops.attn_causal_bwd(roped, out2, dout, lse2, Bp, L, H, hd, rope=tabs, pre_roped=True)
     assert _rel_l2(dqkv2, dqkv1) < 5e-3
+
+
+def test_gemm_bf16_accumulate_epilogue(ops, cuda):
+    """RESID_ADD with a bf16 destination: D = bf16(D + alpha * A B^T), strided into a wider buffer (the LoRA
+    side GEMMs accumulate into the q / v columns of qkv)."""
+    g = torch.Generator().manual_seed(51)
+    m, n, k, ld = 300, 128, 8, 3 * 128
+    a = torch.randn(m, 16, generator=g).to(cuda, torch.bfloat16)          # lda 16, uses columns 8..15
+    b = torch.randn(n, k, generator=g).to(cuda, torch.bfloat16)
+    d0 = torch.randn(m, ld, generator=g).to(cuda, torch.bfloat16)
+    d = d0.clone()
+    ops.gemm(a, b, d, m=m, n=n, k=k, lda=16, a_off=8, ldb=k, ldd=ld, d_off=2 * 128, alpha=0.37, epilogue=1)
+    ref = d0.float()
+    ref[:, 256:] += 0.37 * (a[:, 8:].float() @ b.float().t())
+    assert torch.equal(d[:, :256], d0[:, :256])
+    torch.testing.assert_close(d[:, 256:].float(), ref[:, 256:], rtol=8e-3, atol=8e-3)
+
+
+def test_rowsum(ops, cuda):
+    x = torch.randn(1024, 333, device=cuda)
+    torch.testing.assert_close(ops.rowsum(x), x.sum(1), rtol=1e-5, atol=1e-4)

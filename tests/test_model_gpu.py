@@ -164,3 +164,60 @@ def test_training_step_gradients(name, tmp_path, cuda):
     with torch.no_grad():
         out2 = model(inputs)
     assert not torch.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize("name,rank", [("llama_forecast_clip_stats", 8), ("gpt2_anomaly_concat", 4)])
+def test_lora_forward_and_gradients(name, rank, tmp_path, cuda):
+    """LoRA (BASELINE config 5).  peft is absent, so parity is pinned two ways: (i) identity at
+    initialisation (B = 0) against the non-LoRA model, bit for bit; (ii) with random non-zero B, forward and
+    all gradients (adapters + every A/B pair) against the oracle's plain-PyTorch LoRA restatement."""
+    from medtsllm_b200.model import MedTsLLM
+    from oracle import medtsllm_oracle as O
+    from _fixtures import oracle_spec
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    base = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    base.load_state_dict(fix["adapters"], strict=True)
+    base = base.to(cuda).eval()
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": rank, "alpha": 16, "rslora": True}
+    torch.manual_seed(3)
+    model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    assert model.lora_enabled and list(model.state_dict().keys()) == list(fix["adapters"].keys())
+    res = model.load_state_dict(fix["adapters"], strict=False)          # as tasks/base.py:300 (LoRA pairs live outside)
+    assert not res.unexpected_keys and all(k.startswith("llm.") for k in res.missing_keys)
+    model = model.to(cuda).eval()
+    with torch.no_grad():
+        assert torch.equal(model(inputs), base(inputs))                       # (i) identity at init
+    with torch.no_grad():
+        for b in model.llm.B:
+            b.normal_(std=0.05)
+    model.train()
+    out = model(inputs)
+    gen = torch.Generator().manual_seed(6)
+    wgt = torch.randn(out.shape, generator=gen)
+    (out * wgt.to(cuda)).sum().backward()
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ad = {k: v.clone().requires_grad_(True) for k, v in fix["adapters"].items()}
+    lora = {"scale": model.llm.scale, "n_targets": len(model.llm.targets),
+            "A": [a.detach().cpu().clone().requires_grad_(True) for a in model.llm.A],
+            "B": [b.detach().cpu().clone().requires_grad_(True) for b in model.llm.B]}
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, oracle_spec(fix), training=True, lora=lora)
+    assert _rel_l2(out, ref) < 2e-2
+    assert _rel_l2(out, base.train()(inputs).detach()) > 1e-3               # the adapters do change the output
+    (ref * wgt).sum().backward()
+    errs = {}
+    for k, p in model.named_parameters():
+        if k.startswith("llm.") or k == "reprogramming_layer.key_projection.bias":
+            continue
+        errs[k] = _rel_l2(p.grad, ad[k].grad)
+    for i, (a, b) in enumerate(zip(model.llm.A, model.llm.B)):
+        errs[f"lora_A[{i}]"] = _rel_l2(a.grad, lora["A"][i].grad)
+        errs[f"lora_B[{i}]"] = _rel_l2(b.grad, lora["B"][i].grad)
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(f"\n[lora parity] {name}: worst {worst[0]} {worst[1]:.1e}; lora_A[0] {errs['lora_A[0]']:.1e} lora_B[0] {errs['lora_B[0]']:.1e}")
+    assert worst[1] < 5e-2, worst
+    model.llm.save_pretrained(tmp_path / "ckpt" / "best-lora.safetensors")
+    assert (tmp_path / "ckpt" / "best-lora.safetensors").exists()

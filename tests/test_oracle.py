@@ -33,7 +33,7 @@ def test_oracle_matches_reference_golden(name):
         "reprogramming_layer": (st["reprogramming_layer"], g["reprogramming_layer"]),
         "llm_input": (st["llm_input"], g["llm_input"]),
         "llm": (st["llm"], g["llm"]),
-        "downsample": (st["downsample"], g["downsample"]),
+        **({"downsample": (st["downsample"], g["downsample"])} if g.get("downsample") is not None else {}),
         "output_projection": (st["output_projection"], g["output_projection"]),
         "output": (out, g["output"]),
     }
