@@ -52,6 +52,9 @@ const char* mts_last_error(void);
 int64_t mts_launch_count(void);
 /* Drop the host-side TMA descriptor cache. */
 int mts_clear_caches(void);
+/* Process-wide switches.  "gemm_2cta" (0/1; default 1, env MTS_GEMM_2CTA=0 turns it off): route 256-wide
+ * GEMM tiles to the CTA-pair kernel (tcgen05 cta_group::2, 256x256 tile per two SMs). */
+int mts_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K1+K2  RevIN + patching + TokenEmbedding (fused front end)                                  */

@@ -13,17 +13,12 @@
 //                     bias / residual-add / gelu_new / silu*up, vectorised global stores
 //
 // Algorithmic work per launch: 2*m*n*k*batch FLOP (roofline: tensor pipe).
-#include "mts_internal.h"
-#include "ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "gemm_common.cuh"
 
 namespace mts {
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
-constexpr int kNumEpiThreads = 128;
-constexpr int kEpiPitch = 36;  // floats per staged row (144 B: 16-byte aligned, bank-conflict free)
 
 template <int BN>
 struct GemmCfg {
@@ -37,40 +32,6 @@ struct GemmCfg {
   static constexpr int kEpiStageBytes = 4 * 32 * kEpiPitch * 4;  // per-epilogue-warp 32x32 fp32 tiles
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kEpiStageBytes + 1024;
 };
-
-struct GemmParams {
-  void* d;
-  const float* bias;
-  int64_t ldd, d_batch_stride;
-  int m, n, k, batch;
-  int a_batched, b_batched;  // 0: operand shared by all batches
-  int bias_axis, d_transposed, d_is_f32, bias_vec, vec_ok;
-  const float* c;  // RESID_ADD: residual source, same layout as d
-  float alpha;
-};
-
-__device__ __forceinline__ float gelu_new_f(float x) {
-  // HF:activations.py:65-66  0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));  // |err| ~ 2^-11: below the bf16 output rounding
-  return 0.5f * x * (1.0f + t);
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-
-// Tile order inside one batch: groups of kGroupM row-blocks, m fastest inside a group.  The ~148
-// tiles in flight then form a roughly square patch (12 x 12 blocks) of the output, so a wave streams
-// ~24 operand strips from L2/HBM instead of 48 + 3 with a plain m-fastest order.
-constexpr int kGroupM = 12;
-__device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
-  const int per_group = kGroupM * n_blocks;
-  const int group = t / per_group;
-  const int first_m = group * kGroupM;
-  const int gsize = min(kGroupM, m_blocks - first_m);
-  const int r = t - group * per_group;
-  n_blk = r / gsize;
-  m_blk = first_m + (r - n_blk * gsize);
-}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -192,158 +153,9 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
 
-      const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
-      const int row = row0 + lane;                       // the accumulator row this thread reads
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      const float bias_m = (p.bias_axis == 2 && row < p.m) ? p.bias[row] : 0.0f;
-
-      constexpr int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : BN / 32;
-      const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
-#pragma unroll 1
-      for (int ci = 0; ci < kChunks; ++ci) {
-        float v[32];
-        int col0;  // first output column of this chunk
-        __syncwarp();  // tcgen05.ld is .sync.aligned; also orders the previous chunk's smem reads
-        if constexpr (EPI == MTS_EPI_SWIGLU) {
-          // columns [0,BN/2) of the tile are gate, [BN/2,BN) the matching up projections
-          uint32_t g[32], u[32];
-          tmem_ld_32x32(taddr + ci * 32, g);
-          tmem_ld_32x32(taddr + BN / 2 + ci * 32, u);
-          tmem_ld_wait();
-          col0 = n_blk * (BN / 2) + ci * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = silu_f(__uint_as_float(g[j]) * p.alpha) * (__uint_as_float(u[j]) * p.alpha);
-        } else {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ci * 32, r);
-          tmem_ld_wait();
-          col0 = n_blk * BN + ci * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_m;
-          if (p.bias_axis == 1 && col0 < p.n) {
-            if (p.bias_vec && col0 + 32 <= p.n) {  // warp-uniform 16-byte loads (broadcast)
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if constexpr (EPI == MTS_EPI_GELU_NEW) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
-          }
-        }
-        if (col0 >= n_store) continue;  // warp-uniform
-
-        if (EPI == MTS_EPI_STORE && p.d_transposed) {
-          // element (row, col) -> d[col*ldd + row]: lanes (= rows) are contiguous in memory
-          if (row < p.m) {
-            if (p.d_is_f32) {
-              float* dptr = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride + row;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.n) dptr[(int64_t)(col0 + j) * p.ldd] = v[j];
-            } else {
-              __nv_bfloat16* dptr =
-                  reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride + row;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.n) dptr[(int64_t)(col0 + j) * p.ldd] = __float2bfloat16_rn(v[j]);
-            }
-          }
-          continue;
-        }
-
-        // stage the 32x32 chunk: thread `lane` owns row `lane` (pitch 36 floats: 16-byte aligned
-        // rows, conflict-free for both the 128-bit writes here and the 128-bit reads below)
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
-              make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-
-        if (!p.vec_ok) {
-          // rows of D are not 16-byte aligned (odd n / ldd): scalar, still row-contiguous per lane
-#pragma unroll 1
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r_g = row0 + rr;
-            const int col = col0 + lane;
-            if (r_g < p.m && col < n_store) {
-              const int64_t off = (int64_t)b * p.d_batch_stride + (int64_t)r_g * p.ldd + col;
-              float val = stage_buf[rr * kEpiPitch + lane];
-              if (p.d_is_f32) {
-                if constexpr (EPI == MTS_EPI_RESID_ADD) val += p.c[off];
-                reinterpret_cast<float*>(p.d)[off] = val;
-              } else {
-                if constexpr (EPI == MTS_EPI_RESID_ADD)
-                  val += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.d)[off]);
-                reinterpret_cast<__nv_bfloat16*>(p.d)[off] = __float2bfloat16_rn(val);
-              }
-            }
-          }
-        } else if (p.d_is_f32) {
-          // 8 lanes x float4 per row, 4 rows per pass
-          const int rr = lane >> 3, cc = (lane & 7) * 4;
-          const int64_t boff = (int64_t)b * p.d_batch_stride + col0 + cc;
-          float* dbase = reinterpret_cast<float*>(p.d) + boff;
-          const bool col_ok = col0 + cc < n_store;
-          if constexpr (EPI == MTS_EPI_RESID_ADD) {
-            const float* cbase = p.c + boff;  // residual source (== D for the in-place form)
-            float4 o[8];
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const int r_g = row0 + ps * 4 + rr;
-              if (col_ok && r_g < p.m) o[ps] = *reinterpret_cast<const float4*>(cbase + (int64_t)r_g * p.ldd);
-            }
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const int r_g = row0 + ps * 4 + rr;
-              if (col_ok && r_g < p.m) {
-                const float4 a = *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr) * kEpiPitch + cc);
-                o[ps].x += a.x; o[ps].y += a.y; o[ps].z += a.z; o[ps].w += a.w;
-                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) = o[ps];
-              }
-            }
-          } else {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const int r_g = row0 + ps * 4 + rr;
-              if (col_ok && r_g < p.m)
-                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) =
-                    *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr) * kEpiPitch + cc);
-            }
-          }
-        } else {
-          // bf16: 4 lanes x 8 columns (16 bytes) per row, 8 rows per pass
-          const int rr = lane >> 2, cc = (lane & 3) * 8;
-          __nv_bfloat16* dbase =
-              reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride + col0 + cc;
-          const bool col_ok = col0 + cc < n_store;
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int r_g = row0 + ps * 8 + rr;
-            if (col_ok && r_g < p.m) {
-              float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
-              float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
-              if constexpr (EPI == MTS_EPI_RESID_ADD) {   // bf16 accumulate (LoRA side GEMMs): D = bf16(D + v)
-                const uint4 old = *reinterpret_cast<const uint4*>(dbase + (int64_t)r_g * p.ldd);
-                a0.x += bf16_lo(old.x); a0.y += bf16_hi(old.x); a0.z += bf16_lo(old.y); a0.w += bf16_hi(old.y);
-                a1.x += bf16_lo(old.z); a1.y += bf16_hi(old.z); a1.z += bf16_lo(old.w); a1.w += bf16_hi(old.w);
-              }
-              *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd) =
-                  make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
-                             pack_bf16(a1.z, a1.w));
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk,
+                             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN),
+                             stage_buf, lane);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -411,7 +223,24 @@ static int pick_block_n(int m, int n, int batch) {
 
 }  // namespace mts
 
+namespace mts {
+int launch_gemm_2cta(int epilogue, const mts_gemm_args* a, const GemmParams& p, cudaStream_t stream);
+static int g_gemm_2cta = -1;
+bool gemm_2cta_enabled() {
+  if (g_gemm_2cta < 0) {
+    const char* e = getenv("MTS_GEMM_2CTA");
+    g_gemm_2cta = (e && e[0] == '0') ? 0 : 1;   // on by default: +5..18 % over the 1-CTA kernel on B200
+  }
+  return g_gemm_2cta == 1;
+}
+}  // namespace mts
+
 using namespace mts;
+
+extern "C" int mts_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
+  return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
+}
 
 extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   if (!a) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: null args");
@@ -495,6 +324,16 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.c = a->c ? a->c : static_cast<const float*>(a->d);
   p.bias_vec = (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
   p.alpha = a->alpha;
+
+  if (bn == 256 && !a->d_transposed && gemm_2cta_enabled()) {
+    // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them
+    // unless the 256-row granularity wastes more than it saves (odd / single 128-row block counts).
+    const long nb256 = (a->n + 255) / 256;
+    const long t1 = (long)((a->m + 127) / 128) * nb256 * a->batch, tp = (long)((a->m + 255) / 256) * nb256 * a->batch;
+    const long cost1 = ((t1 + num_sms() - 1) / num_sms()) * 100;
+    const long costp = ((tp + num_sms() / 2 - 1) / (num_sms() / 2)) * 92;
+    if (costp <= cost1) return launch_gemm_2cta(a->epilogue, a, p, stream);
+  }
 
   const int mb = (a->m + kBlockM - 1) / kBlockM;
   const int nb = (a->n + bn - 1) / bn;

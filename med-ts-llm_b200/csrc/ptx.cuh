@@ -143,6 +143,67 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two SMs of one TPC cooperate on a 256-row tile; only the leader CTA
+// issues the MMAs, each CTA stages its own A rows and HALF of B.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar,
+                                                int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+      "r"(c2), "l"(policy)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem) {  // one whole warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once the MMAs issued so far retire) on the mbarrier at this smem offset in every CTA of `mask`.
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 // K-major, 128B-swizzled shared-memory matrix descriptor (tile rows are 128 bytes, 8-row swizzle
 // atoms are 1024 bytes apart).  Bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled
 // K-major) | [32,46) SBO>>4 | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B).

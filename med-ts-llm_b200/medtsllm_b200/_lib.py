@@ -68,6 +68,7 @@ SIGNATURES = {
     "mts_cast_rows_f32_bf16": [_p, _i64, _i64, _p, _i64, _i, _i, _i, _p],
     "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "mts_clear_caches": [],
+    "mts_set_option": [C.c_char_p, _i],
 }
 _SPECIAL = {
     "mts_version": ([], C.c_int),
@@ -117,3 +118,7 @@ def launch_count() -> int:
 
 def version() -> int:
     return int(load().mts_version())
+
+
+def set_option(name: str, value: int) -> None:
+    call("mts_set_option", name.encode(), int(value))

@@ -444,3 +444,27 @@ def test_gemm_bf16_accumulate_epilogue(ops, cuda):
 def test_rowsum(ops, cuda):
     x = torch.randn(1024, 333, device=cuda)
     torch.testing.assert_close(ops.rowsum(x), x.sum(1), rtol=1e-5, atol=1e-4)
+
+
+def test_gemm_cta_pair_and_single_cta_kernels_agree(ops, cuda):
+    """The cta_group::2 kernel (default for 256-wide tiles) and the 1-CTA kernel compute the same tiles: with the
+    same operands they must agree bit for bit (same MMA shape per k-step, same fp32 accumulation order)."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(61)
+    m, n, k = 900, 1536, 640
+    a = torch.randn(m, k, generator=g).to(cuda, torch.bfloat16)
+    b = torch.randn(n, k, generator=g).to(cuda, torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(cuda)
+    outs = []
+    try:
+        for flag in (1, 0):
+            _lib.set_option("gemm_2cta", flag)
+            d = torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
+            ops.gemm(a, b, d, m=m, n=n, k=k, block_n=256, bias=bias, bias_axis=1)
+            r = torch.randn(m, n, generator=torch.Generator().manual_seed(7)).to(cuda)
+            ops.gemm(a, b, r, m=m, n=n, k=k, block_n=256, epilogue=1)
+            outs.append((d, r))
+    finally:
+        _lib.set_option("gemm_2cta", 1)
+    torch.testing.assert_close(outs[0][0].float(), a.float() @ b.float().t() + bias, rtol=8e-3, atol=8e-2)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
