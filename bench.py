@@ -167,9 +167,21 @@ def run_ours(args):
         step_resident()
     if args.profile_step:
         # for `ncu --profile-from-start off`: exactly one warm step between cudaProfilerStart/Stop
+        fn = step_resident
+        if args.profile_step == "train":
+            model.train()
+            opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+
+            def fn():
+                loss = model(resident).float().pow(2).mean()
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+            for _ in range(2):
+                fn()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step_resident()
+        fn()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -400,7 +412,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
-    ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
+    ap.add_argument("--profile-step", nargs="?", const="fwd", default=None, choices=["fwd", "train"],
+                    help="run one profiled step (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -264,9 +264,24 @@ int mts_rowsum_f32(const float* x, int64_t ld, float* out, int rows, int cols, m
 int mts_transpose_strided(const void* in, int dtype, int64_t ld_in, int64_t in_batch_stride,
                           uint16_t* out, int64_t ld_out, int batch, int rows, int cols,
                           mts_stream_t stream);
-/* out[(b*rows + r)*ld_out + c] = bf16(in[b*in_batch_stride + r*ld_in + c]) */
+/* out[b*out_batch_stride + r*ld_out + c] = bf16(in[b*in_batch_stride + r*ld_in + c])
+ * (out_batch_stride 0 = rows*ld_out, i.e. densely stacked batches) */
 int mts_cast_rows_f32_bf16(const float* in, int64_t ld_in, int64_t in_batch_stride, uint16_t* out,
-                           int64_t ld_out, int batch, int rows, int cols, mts_stream_t stream);
+                           int64_t ld_out, int64_t out_batch_stride, int batch, int rows, int cols,
+                           mts_stream_t stream);
+/* Covariate merges over the feature axis (ref: models/medtsllm.py:284-295 `add` / `weighted-average`,
+ * :369-377 `independent` / `merge-end`).
+ *   group_reduce:  out[b*out_bs + r] = sum_c w[c]*in[(b*C+c)*R + r] + bias[0]   (w NULL: mean; bias may be NULL)
+ *   group_reduce_bwd: din = w[c]*dout (or dout/C); optionally dw[c], dbias[0] (needs `in`)
+ *   merge_end:     y[b,p,o] = sum_{o2,c} W[o, o2*C+c] * h[b,c,p,o2] + bias[o]    (feature_weighting Linear) */
+int mts_group_reduce(const float* in, const float* w, const float* bias, float* out, int64_t out_bs, int B,
+                     int C, int64_t R, int accumulate /* out += ... */, mts_stream_t stream);
+int mts_group_reduce_bwd(const float* dout, int64_t dout_bs, const float* w, const float* in, float* din,
+                         float* dw, float* dbias, int B, int C, int64_t R, mts_stream_t stream);
+int mts_merge_end(const float* h, const float* W, const float* bias, float* y, int B, int C, int P, int O,
+                  mts_stream_t stream);
+int mts_merge_end_bwd(const float* dy, const float* h, const float* W, float* dh, float* dW, float* dbias, int B,
+                      int C, int P, int O, mts_stream_t stream);
 /* out = dy * stdev[b,c]  (backward of RevIN denorm; statistics are detached, RevIN.py:42-43) */
 int mts_revin_denorm_bwd(const float* dy, const float* stdev, float* out, int B, int T, int C,
                          mts_stream_t stream);

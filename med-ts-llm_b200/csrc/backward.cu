@@ -259,10 +259,10 @@ __global__ void transpose_strided_kernel(const TIn* __restrict__ in, int64_t ld_
   }
 }
 
-// strided 3-D gather + cast: out[(b*rows + r)*ld_out + c] = bf16(in[b*in_bs + r*ld_in + c])
+// strided 3-D gather + cast: out[b*out_bs + r*ld_out + c] = bf16(in[b*in_bs + r*ld_in + c])
 __global__ void cast_rows_kernel(const float* __restrict__ in, int64_t ld_in, int64_t in_bs,
-                                 __nv_bfloat16* __restrict__ out, int64_t ld_out, int batch, int rows,
-                                 int cols, int vec_ok) {
+                                 __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t out_bs, int batch,
+                                 int rows, int cols, int vec_ok) {
   if (vec_ok) {
     const int c4n = cols >> 2;
     const int64_t total = (int64_t)batch * rows * c4n;
@@ -273,7 +273,8 @@ __global__ void cast_rows_kernel(const float* __restrict__ in, int64_t ld_in, in
       const int r = (int)(br % rows);
       const int b = (int)(br / rows);
       const float4 v = *reinterpret_cast<const float4*>(in + (int64_t)b * in_bs + (int64_t)r * ld_in + c4 * 4);
-      *reinterpret_cast<uint2*>(out + br * ld_out + c4 * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      *reinterpret_cast<uint2*>(out + (int64_t)b * out_bs + (int64_t)r * ld_out + c4 * 4) =
+          make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
   } else {
     const int64_t total = (int64_t)batch * rows * cols;
@@ -283,7 +284,8 @@ __global__ void cast_rows_kernel(const float* __restrict__ in, int64_t ld_in, in
       const int64_t br = idx / cols;
       const int r = (int)(br % rows);
       const int b = (int)(br / rows);
-      out[br * ld_out + c] = __float2bfloat16_rn(in[(int64_t)b * in_bs + (int64_t)r * ld_in + c]);
+      out[(int64_t)b * out_bs + (int64_t)r * ld_out + c] =
+          __float2bfloat16_rn(in[(int64_t)b * in_bs + (int64_t)r * ld_in + c]);
     }
   }
 }
@@ -428,15 +430,17 @@ extern "C" int mts_transpose_strided(const void* in, int dtype, int64_t ld_in, i
 }
 
 extern "C" int mts_cast_rows_f32_bf16(const float* in, int64_t ld_in, int64_t in_batch_stride,
-                                      uint16_t* out, int64_t ld_out, int batch, int rows, int cols,
-                                      mts_stream_t s) {
+                                      uint16_t* out, int64_t ld_out, int64_t out_batch_stride, int batch,
+                                      int rows, int cols, mts_stream_t s) {
   if (!in || !out || batch <= 0 || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols)
     return set_error(MTS_ERR_INVALID_ARG, "mts_cast_rows_f32_bf16: bad args");
-  const int vec_ok = !(cols % 4) && !(ld_in % 4) && !(in_batch_stride % 4) && !(ld_out % 4) &&
+  if (out_batch_stride == 0) out_batch_stride = (int64_t)rows * ld_out;
+  const int vec_ok = !(cols % 4) && !(ld_in % 4) && !(in_batch_stride % 4) && !(ld_out % 4) && !(out_batch_stride % 4) &&
                      !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 7);
   const int64_t work = (int64_t)batch * rows * (vec_ok ? cols / 4 : cols);
   cast_rows_kernel<<<bw_grid(work, 256), 256, 0, (cudaStream_t)s>>>(
-      in, ld_in, in_batch_stride, reinterpret_cast<__nv_bfloat16*>(out), ld_out, batch, rows, cols, vec_ok);
+      in, ld_in, in_batch_stride, reinterpret_cast<__nv_bfloat16*>(out), ld_out, out_batch_stride, batch, rows, cols,
+      vec_ok);
   count_launch();
   return check_launch("cast_rows_kernel");
 }
@@ -457,4 +461,153 @@ extern "C" int mts_rowsum_f32(const float* x, int64_t ld, float* out, int rows, 
   rowsum_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(x, ld, out, rows, cols);
   count_launch();
   return check_launch("rowsum_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// Covariate merges over the feature axis C (models/medtsllm.py:284-295, 369-377).  All tiny,
+// HBM-bound; one element of the merged output per thread.
+// ------------------------------------------------------------------------------------------
+namespace mts {
+
+// out[b*out_bs + r] = sum_c w[c] * in[(b*C + c)*R + r] + bias   (w == NULL: 1/C; bias may be NULL)
+__global__ void group_reduce_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int64_t out_bs,
+                                    int B, int C, int64_t R, int accumulate) {
+  const int64_t total = (int64_t)B * R;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / R, r = i - b * R;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc += (w ? w[c] : 1.0f / C) * in[(b * C + c) * R + r];
+    out[b * out_bs + r] = acc + b0 + (accumulate ? out[b * out_bs + r] : 0.f);
+  }
+}
+
+// din[(b*C + c)*R + r] = w[c] * dout[b*dout_bs + r]     (w == NULL: 1/C)
+__global__ void group_broadcast_kernel(const float* __restrict__ dout, int64_t dout_bs, const float* __restrict__ w,
+                                       float* __restrict__ din, int B, int C, int64_t R) {
+  const int64_t total = (int64_t)B * C * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i % R;
+    const int64_t bc = i / R;
+    const int c = (int)(bc % C);
+    const int64_t b = bc / C;
+    din[i] = (w ? w[c] : 1.0f / C) * dout[b * dout_bs + r];
+  }
+}
+
+// dw[c] = sum_{b,r} dout[b*dout_bs + r] * in[(b*C + c)*R + r];  dbias = sum dout   (one CTA per c, +1 for the bias)
+__global__ void __launch_bounds__(256)
+group_weight_grad_kernel(const float* __restrict__ dout, int64_t dout_bs, const float* __restrict__ in,
+                         float* __restrict__ dw, float* __restrict__ dbias, int B, int C, int64_t R) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  const int64_t total = (int64_t)B * R;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t b = i / R, r = i - b * R;
+    const float d = dout[b * dout_bs + r];
+    acc += (c < C) ? d * in[(b * C + c) * R + r] : d;
+  }
+  acc = bw_block_sum(acc, red);
+  if (threadIdx.x == 0) { if (c < C) dw[c] = acc; else dbias[0] = acc; }
+}
+
+// merge-end: y[b,p,o] = sum_{o2,c} W[o, o2*C + c] * h[((b*C + c)*P + p)*O + o2] + bias[o]   (Linear(C*O -> O))
+__global__ void merge_end_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
+                                 float* __restrict__ y, int B, int C, int P, int O) {
+  const int64_t total = (int64_t)B * P * O;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % O);
+    const int64_t bp = i / O;
+    const int p = (int)(bp % P);
+    const int64_t b = bp / P;
+    float acc = bias[o];
+    for (int o2 = 0; o2 < O; ++o2)
+      for (int c = 0; c < C; ++c) acc += W[(int64_t)o * O * C + o2 * C + c] * h[((b * C + c) * P + p) * O + o2];
+    y[i] = acc;
+  }
+}
+// dh[((b*C + c)*P + p)*O + o2] = sum_o dy[b,p,o] * W[o, o2*C + c]
+__global__ void merge_end_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                           float* __restrict__ dh, int B, int C, int P, int O) {
+  const int64_t total = (int64_t)B * C * P * O;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o2 = (int)(i % O);
+    int64_t t = i / O;
+    const int p = (int)(t % P); t /= P;
+    const int c = (int)(t % C);
+    const int64_t b = t / C;
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) acc += dy[(b * P + p) * O + o] * W[(int64_t)o * O * C + o2 * C + c];
+    dh[i] = acc;
+  }
+}
+// dW[o, o2*C + c] = sum_{b,p} dy[b,p,o] * h[b,c,p,o2];  dbias[o] = sum_{b,p} dy[b,p,o]   (one CTA per W entry / bias)
+__global__ void __launch_bounds__(128)
+merge_end_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ h, float* __restrict__ dW,
+                            float* __restrict__ dbias, int B, int C, int P, int O) {
+  __shared__ float red[32];
+  const int e = blockIdx.x;               // < O*O*C: weight entry; >= : bias entry
+  const int nW = O * O * C;
+  float acc = 0.f;
+  if (e < nW) {
+    const int o = e / (O * C), o2 = (e / C) % O, c = e % C;
+    for (int64_t i = threadIdx.x; i < (int64_t)B * P; i += blockDim.x) {
+      const int64_t b = i / P; const int p = (int)(i - b * P);
+      acc += dy[(b * P + p) * O + o] * h[((b * C + c) * P + p) * O + o2];
+    }
+  } else {
+    const int o = e - nW;
+    for (int64_t i = threadIdx.x; i < (int64_t)B * P; i += blockDim.x) acc += dy[i * O + o];
+  }
+  acc = bw_block_sum(acc, red);
+  if (threadIdx.x == 0) { if (e < nW) dW[e] = acc; else dbias[e - nW] = acc; }
+}
+
+}  // namespace mts
+
+extern "C" int mts_group_reduce(const float* in, const float* w, const float* bias, float* out, int64_t out_bs,
+                                int B, int C, int64_t R, int accumulate, mts_stream_t s) {
+  if (!in || !out || B <= 0 || C <= 0 || R <= 0 || out_bs < R)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_group_reduce: bad args");
+  group_reduce_kernel<<<bw_grid((int64_t)B * R, 256), 256, 0, (cudaStream_t)s>>>(in, w, bias, out, out_bs, B, C, R, accumulate);
+  count_launch();
+  return check_launch("group_reduce_kernel");
+}
+
+extern "C" int mts_group_reduce_bwd(const float* dout, int64_t dout_bs, const float* w, const float* in, float* din,
+                                    float* dw, float* dbias, int B, int C, int64_t R, mts_stream_t s) {
+  if (!dout || !din || B <= 0 || C <= 0 || R <= 0 || dout_bs < R || ((dw != nullptr) != (in != nullptr)) ||
+      (dw && !dbias))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_group_reduce_bwd: bad args");
+  group_broadcast_kernel<<<bw_grid((int64_t)B * C * R, 256), 256, 0, (cudaStream_t)s>>>(dout, dout_bs, w, din, B, C, R);
+  count_launch();
+  int rc = check_launch("group_broadcast_kernel");
+  if (rc || !dw) return rc;
+  group_weight_grad_kernel<<<C + 1, 256, 0, (cudaStream_t)s>>>(dout, dout_bs, in, dw, dbias, B, C, R);
+  count_launch();
+  return check_launch("group_weight_grad_kernel");
+}
+
+extern "C" int mts_merge_end(const float* h, const float* W, const float* bias, float* y, int B, int C, int P, int O,
+                             mts_stream_t s) {
+  if (!h || !W || !bias || !y || B <= 0 || C <= 0 || P <= 0 || O <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_merge_end: bad args");
+  merge_end_kernel<<<bw_grid((int64_t)B * P * O, 256), 256, 0, (cudaStream_t)s>>>(h, W, bias, y, B, C, P, O);
+  count_launch();
+  return check_launch("merge_end_kernel");
+}
+
+extern "C" int mts_merge_end_bwd(const float* dy, const float* h, const float* W, float* dh, float* dW, float* dbias,
+                                 int B, int C, int P, int O, mts_stream_t s) {
+  if (!dy || !h || !W || !dh || !dW || !dbias || B <= 0 || C <= 0 || P <= 0 || O <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_merge_end_bwd: bad args");
+  merge_end_bwd_input_kernel<<<bw_grid((int64_t)B * C * P * O, 256), 256, 0, (cudaStream_t)s>>>(dy, W, dh, B, C, P, O);
+  count_launch();
+  int rc = check_launch("merge_end_bwd_input_kernel");
+  if (rc) return rc;
+  merge_end_bwd_weight_kernel<<<O * O * C + O, 128, 0, (cudaStream_t)s>>>(dy, h, dW, dbias, B, C, P, O);
+  count_launch();
+  return check_launch("merge_end_bwd_weight_kernel");
 }

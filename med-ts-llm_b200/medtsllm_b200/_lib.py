@@ -65,7 +65,11 @@ SIGNATURES = {
     "mts_colsum": [_p, _i, _i64, _p, _i, _i, _p],
     "mts_rowsum_f32": [_p, _i64, _p, _i, _i, _p],
     "mts_transpose_strided": [_p, _i, _i64, _i64, _p, _i64, _i, _i, _i, _p],
-    "mts_cast_rows_f32_bf16": [_p, _i64, _i64, _p, _i64, _i, _i, _i, _p],
+    "mts_cast_rows_f32_bf16": [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _p],
+    "mts_group_reduce": [_p, _p, _p, _p, _i64, _i, _i, _i64, _i, _p],
+    "mts_group_reduce_bwd": [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i64, _p],
+    "mts_merge_end": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "mts_merge_end_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],

@@ -148,14 +148,19 @@ class MedTsLLM(nn.Module):
             raise ValueError(f"Task {self.task} is not supported.")
         self.n_outputs = self.n_outputs_per_step * self.pred_len
 
+        # covariate modes (models/medtsllm.py:71-87)
         if self.covariate_mode == "univariate":
             assert self.n_features == 1
+        elif self.covariate_mode == "interleave":
+            self.n_patches *= self.n_features
         elif self.covariate_mode == "concat":
             self.d_model *= self.n_features
-        elif self.covariate_mode in ("interleave", "independent", "merge-end", "weighted-average", "add"):
-            raise NotImplementedError(
-                f"covariate_mode={self.covariate_mode!r}: medtsllm_b200 implements the modes used by the shipped "
-                "configs (concat, univariate); the others are listed as next in DESIGN.md")
+        elif self.covariate_mode == "independent" or self.covariate_mode == "add":
+            pass
+        elif self.covariate_mode == "merge-end":
+            self.feature_weighting = nn.Linear(self.n_features * self.n_outputs_per_step, self.n_outputs_per_step)
+        elif self.covariate_mode == "weighted-average":
+            self.feature_weighting = nn.Linear(self.n_features, 1)
         else:
             raise ValueError(f"Unknown covariate mode {self.covariate_mode}")
 
@@ -399,6 +404,7 @@ class MedTsLLM(nn.Module):
         "reprogramming_layer.out_projection.weight", "reprogramming_layer.out_projection.bias",
         "embedding_downsample_layer.weight", "embedding_downsample_layer.bias",
         "output_projection.linear.weight", "output_projection.linear.bias",
+        "feature_weighting.weight", "feature_weighting.bias",
     )
 
     def param_order(self):
@@ -516,27 +522,30 @@ class MedTsLLM(nn.Module):
         D, N, E, H = self.d_llm, self.n_patches, self.d_ff, self.n_attention_heads
         HE = H * E
         rl = self.reprogramming_layer
+        mode = self.covariate_mode
+        per_feature = mode not in ("concat", "univariate")      # features encoded separately: [B*C, N0, 32]
+        N0 = N // C if mode == "interleave" else N               # patches per feature
+        Bp = B * C if mode in ("independent", "merge-end") else B   # sequences through the backbone
 
-        # K5: prompt ids (host) -> backbone input rows [0, Lp)
+        # K5: prompt ids (host) -> backbone input rows [0, Lp); repeated per feature for independent / merge-end
         ids = self.prompt_token_ids(inputs)
         Lp = ids.shape[1]
         L = Lp + N
         ids_dev = ids.to(dev, non_blocking=True) if Lp > 0 else None
-        X = torch.empty(B, L, D, device=dev, dtype=torch.float32)
-        ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=1, Lp=Lp, L=L)
+        X = torch.empty(Bp, L, D, device=dev, dtype=torch.float32)
+        ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L)
 
-        # K1+K2: RevIN + patches + token conv (concat layout for multivariate)
-        concat = self.covariate_mode == "concat"
+        # K1+K2: RevIN + patches + token conv (concat layout [B, N, C*32] or per feature [B*C, N0, 32])
+        concat = mode == "concat"
         enc, _, mean, std = ops.revin_patch_embed(
             x_enc, self.patch_embedding.value_embedding.tokenConv.weight.detach(), self.patch_len, self.stride,
             concat=concat)
-        Bp = enc.shape[0]
-        assert enc.shape[1] == N and Bp == B
+        assert enc.shape[1] == N0
 
         # K3/K4: reprogramming cross-attention on tcgen05 GEMMs
         source, K, Vt = self._source_kv()
         S = self.num_tokens
-        rows = Bp * N
+        rows = enc.shape[0] * N0
         wq = self._bf16_weight("wq", rl.query_projection.weight)
         Q = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
         ops.gemm(enc, wq, Q, m=rows, n=HE, k=self.d_model, ldb=wq.shape[1],
@@ -548,8 +557,26 @@ class MedTsLLM(nn.Module):
         O = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
         ops.gemm(P, Vt, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
         wo = self._bf16_weight("wo", rl.out_projection.weight)
-        ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=L * D, ldd=D, d_off=Lp * D,
-                 ldb=wo.shape[1], bias=rl.out_projection.bias.detach(), bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+        bo = rl.out_projection.bias.detach()
+        Y = None
+        if mode in ("concat", "univariate", "independent", "merge-end"):
+            # one sequence per (sample[, feature]): rows of batch i land at X[i, Lp:, :]
+            ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=L * D, ldd=D, d_off=Lp * D,
+                     ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+        elif mode == "interleave":
+            # token order n-major, c-minor (models/medtsllm.py:292-295): feature c writes rows Lp + n*C + c
+            for c in range(C):
+                ops.gemm(O, wo, X, m=N0, n=D, k=HE, batch=B, a_off=c * N0 * HE, a_bs=C * N0 * HE, b_bs=0,
+                         d_bs=L * D, ldd=C * D, d_off=(Lp + c) * D, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N,
+                         epilogue=EPI_RESID_ADD)
+        else:
+            # add / weighted-average (models/medtsllm.py:284-291): merge the C reprogrammed streams into one
+            Y = torch.empty(rows, D, device=dev, dtype=torch.float32)
+            ops.gemm(O, wo, Y, m=rows, n=D, k=HE, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N)
+            fw = self.feature_weighting if mode == "weighted-average" else None
+            ops.group_reduce(Y, B, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
+                             bias=fw.bias.detach() if fw is not None else None, out=X, out_bs=L * D, out_off=Lp * D,
+                             accumulate=True)       # X's patch rows hold 0 (+ wpe for GPT-2)
 
         cap = self._capture
         if cap is not None:
@@ -569,14 +596,22 @@ class MedTsLLM(nn.Module):
                  d_transposed=True, ldd=N, ldb=wds.shape[1], bias=bds, bias_axis=BIAS_N if bds is not None else 0)
         # K12: flatten head
         wh = self._bf16_weight("wh", self.output_projection.linear.weight)
-        out = torch.empty(Bp, self.n_outputs, device=dev, dtype=torch.float32)
+        head = torch.empty(Bp, self.n_outputs, device=dev, dtype=torch.float32)
         if (E * N) % 8:
             raise MtsError("d_ff * n_patches must be a multiple of 8")
-        ops.gemm(flat, wh, out, m=Bp, n=self.n_outputs, k=E * N, ldb=wh.shape[1],
+        ops.gemm(flat, wh, head, m=Bp, n=self.n_outputs, k=E * N, ldb=wh.shape[1],
                  bias=self.output_projection.linear.bias.detach(), bias_axis=BIAS_N)
         if cap is not None:
-            cap["output_projection"] = out.clone()
-        out = out.view(B, self.pred_len, self.n_outputs_per_step)
+            cap["output_projection"] = head.clone()
+        nops = self.n_outputs_per_step
+        if mode == "independent":          # mean over the feature axis (models/medtsllm.py:369-371)
+            out = ops.group_reduce(head, B, C, self.n_outputs)
+        elif mode == "merge-end":          # Linear over (feature, output) pairs (models/medtsllm.py:372-375)
+            out = ops.merge_end(head, self.feature_weighting.weight.detach(), self.feature_weighting.bias.detach(),
+                                B, C, self.pred_len, nops)
+        else:
+            out = head
+        out = out.view(B, self.pred_len, nops)
         denorm = self.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining")
         if denorm:
             ops.revin_denorm(out, mean, std)
@@ -584,8 +619,8 @@ class MedTsLLM(nn.Module):
             out = out.squeeze(-1)
         if stash is not None:
             stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
-                         hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Bp=Bp,
-                         scale=scale, denorm=denorm, concat=concat)
+                         hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Bp=Bp, B=B, N0=N0,
+                         scale=scale, denorm=denorm, concat=concat, Y=Y, head=head)
         return out
 
 

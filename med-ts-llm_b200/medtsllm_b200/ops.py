@@ -398,7 +398,8 @@ def transpose_strided(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, 
     return out
 
 
-def cast_rows(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, ld_out=None, out=None):
+def cast_rows(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, ld_out=None, out=None, out_bs=0,
+              out_off=0):
     """out[(b*rows + r), :cols] = bf16(x[b][r][:cols]); out [batch*rows, ld_out] (zero padded columns)."""
     _chk(x, torch.float32, "x")
     ld_in = cols if ld_in is None else ld_in
@@ -407,8 +408,8 @@ def cast_rows(x, *, rows, cols, ld_in=None, batch=1, in_bs=0, in_off=0, ld_out=N
     if out is None:
         out = (torch.zeros if ld_out != cols else torch.empty)(batch * rows, ld_out, device=x.device,
                                                                dtype=torch.bfloat16)
-    _lib.call("mts_cast_rows_f32_bf16", x.data_ptr() + 4 * in_off, ld_in, in_bs, out.data_ptr(), ld_out, batch,
-              rows, cols, _stream())
+    _lib.call("mts_cast_rows_f32_bf16", x.data_ptr() + 4 * in_off, ld_in, in_bs, out.data_ptr() + 2 * out_off, ld_out,
+              out_bs, batch, rows, cols, _stream())
     return out
 
 
@@ -428,3 +429,47 @@ def rowsum(x):
     out = torch.empty(rows, device=x.device, dtype=torch.float32)
     _lib.call("mts_rowsum_f32", x.data_ptr(), cols, out.data_ptr(), rows, cols, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# covariate merges over the feature axis
+# ------------------------------------------------------------------------------------------------
+def group_reduce(x, B, C, R, *, w=None, bias=None, out=None, out_bs=None, out_off=0, accumulate=False):
+    """out[b, r] = sum_c w[c] * x[b, c, r] (+ bias); w None = mean.  `out` may be a strided destination."""
+    _chk(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(B, R, device=x.device, dtype=torch.float32)
+    out_bs = R if out_bs is None else out_bs
+    _lib.call("mts_group_reduce", x.data_ptr(), _ptr(w), _ptr(bias), out.data_ptr() + 4 * out_off, out_bs, B, C, R,
+              1 if accumulate else 0, _stream())
+    return out
+
+
+def group_reduce_bwd(dout, B, C, R, *, w=None, x=None, dout_bs=None, dout_off=0):
+    """Returns (din [B*C, R], dw [C] or None, dbias [1] or None)."""
+    _chk(dout, torch.float32, "dout")
+    din = torch.empty(B * C, R, device=dout.device, dtype=torch.float32)
+    dw = dbias = None
+    if x is not None:
+        dw = torch.empty(C, device=dout.device, dtype=torch.float32)
+        dbias = torch.empty(1, device=dout.device, dtype=torch.float32)
+    _lib.call("mts_group_reduce_bwd", dout.data_ptr() + 4 * dout_off, R if dout_bs is None else dout_bs, _ptr(w),
+              _ptr(x), din.data_ptr(), _ptr(dw), _ptr(dbias), B, C, R, _stream())
+    return din, dw, dbias
+
+
+def merge_end(h, W, bias, B, C, P, O):
+    _chk(h, torch.float32, "h")
+    y = torch.empty(B, P, O, device=h.device, dtype=torch.float32)
+    _lib.call("mts_merge_end", h.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), B, C, P, O, _stream())
+    return y
+
+
+def merge_end_bwd(dy, h, W, B, C, P, O):
+    _chk(dy, torch.float32, "dy")
+    dh = torch.empty_like(h)
+    dW = torch.empty_like(W)
+    db = torch.empty(O, device=dy.device, dtype=torch.float32)
+    _lib.call("mts_merge_end_bwd", dy.data_ptr(), h.data_ptr(), W.data_ptr(), dh.data_ptr(), dW.data_ptr(),
+              db.data_ptr(), B, C, P, O, _stream())
+    return dh, dW, db

@@ -56,20 +56,29 @@ class _HotPathFn(torch.autograd.Function):
         dev = dout.device
         if dout.dtype != torch.float32:
             dout = dout.float()
-        B, N, E, H, D = st["Bp"], m.n_patches, m.d_ff, m.n_attention_heads, m.d_llm
-        HE, S, Lp, L, V = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size
-        R = B * N                                   # reprogrammed rows
+        B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
+        HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
+        mode = m.covariate_mode
+        R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
         dm = m.d_model
         rl = m.reprogramming_layer
         f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
         bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)     # noqa: E731
         zbf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)    # noqa: E731
+        g_fw_w = g_fw_b = None
 
         # ---- de-norm / squeeze (models/medtsllm.py:379-382): statistics are detached
-        dout = dout.reshape(B, m.pred_len, m.n_outputs_per_step).contiguous()
+        dout = dout.reshape(B0, m.pred_len, m.n_outputs_per_step).contiguous()
         dy = ops.revin_denorm_bwd(dout, st["std"]) if st["denorm"] else dout
         n_out = m.n_outputs
-        dy2 = dy.view(B, n_out)
+        # ---- merges over the feature axis after the head (models/medtsllm.py:369-377)
+        if mode == "independent":
+            dy2, _, _ = ops.group_reduce_bwd(dy.view(B0, n_out), B0, C, n_out)            # [B0*C, n_out]
+        elif mode == "merge-end":
+            dy2, g_fw_w, g_fw_b = ops.merge_end_bwd(dy, st["head"], m.feature_weighting.weight.detach(), B0, C,
+                                                    m.pred_len, m.n_outputs_per_step)
+        else:
+            dy2 = dy.view(B, n_out)
 
         # ---- flatten head: out = flat W_h^T + b_h
         g_bh = ops.colsum(dy2)
@@ -107,8 +116,21 @@ class _HotPathFn(torch.autograd.Function):
         dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
                                      lora=m.llm if m.lora_enabled else None)     # fp32 [B*L, D]
 
-        # ---- reprogramming out-projection: X[b, Lp+n] = O W_o^T + b_o
-        dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D, in_off=Lp * D)   # bf16 [R, D]
+        # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
+        if mode in ("concat", "univariate", "independent", "merge-end"):
+            dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D, in_off=Lp * D)   # bf16 [R, D]
+        elif mode == "interleave":
+            dxp = bf(R, D)
+            for c in range(C):       # feature c owns rows Lp + n*C + c
+                ops.cast_rows(dR, batch=B0, rows=N0, cols=D, ld_in=C * D, in_bs=L * D, in_off=(Lp + c) * D,
+                              out=dxp, ld_out=D, out_bs=C * N0 * D, out_off=c * N0 * D)
+        else:                        # add / weighted-average: broadcast back over the feature axis
+            fw = m.feature_weighting if mode == "weighted-average" else None
+            dyf, g_w, g_b = ops.group_reduce_bwd(dR, B0, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
+                                                 x=st["Y"] if fw is not None else None, dout_bs=L * D, dout_off=Lp * D)
+            if fw is not None:
+                g_fw_w, g_fw_b = g_w.view(1, C), g_b.view(1)
+            dxp = ops.cast_bf16(dyf.view(R, D))
         g_bo = ops.colsum(dxp)
         Rp = ops.ceil8(R)
         g_wo = f32(D, HE)
@@ -169,7 +191,8 @@ class _HotPathFn(torch.autograd.Function):
         ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
 
         lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
-        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo] + lora_grads).launch()
+        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo, g_fw_w, g_fw_b]
+                             + lora_grads).launch()
         early.finish()
         late.finish()
         ctx.stash = None
@@ -182,5 +205,6 @@ class _HotPathFn(torch.autograd.Function):
             "reprogramming_layer.out_projection.weight": g_wo, "reprogramming_layer.out_projection.bias": g_bo,
             "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
             "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
+            "feature_weighting.weight": g_fw_w, "feature_weighting.bias": g_fw_b,
         }
         return (None, None) + tuple(grads[k] for k in m.param_order()) + tuple(lora_grads)

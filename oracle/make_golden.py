@@ -63,6 +63,27 @@ CASES = {
         task="reconstruction", T=40, pred=40, C=1, B=3, num_tokens=64, d_ff=32, covariate_mode="univariate",
         downsample="average", description="Synthetic single channel series .",
         prompting=dict(dataset=True, task=False, clip=False, input_stats=False)),
+    # the remaining covariate modes (models/medtsllm.py:71-87, 284-295, 343-344, 369-377), small on purpose
+    "llama_forecast_independent": dict(
+        kind="llama", llm=dict(hidden_size=128, heads=2, layers=1, intermediate_size=256, vocab_size=256),
+        task="forecasting", T=48, pred=16, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="independent",
+        description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    "gpt2_forecast_merge_end": dict(
+        kind="gpt2", llm=dict(hidden_size=128, heads=2, layers=1, vocab_size=256),
+        task="forecasting", T=48, pred=16, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="merge-end",
+        description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    "llama_anomaly_add": dict(
+        kind="llama", llm=dict(hidden_size=128, heads=2, layers=1, intermediate_size=256, vocab_size=256),
+        task="anomaly_detection", T=40, pred=40, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="add",
+        description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    "gpt2_anomaly_weighted_average": dict(
+        kind="gpt2", llm=dict(hidden_size=128, heads=2, layers=1, vocab_size=256),
+        task="anomaly_detection", T=40, pred=40, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="weighted-average",
+        description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    "llama_forecast_interleave": dict(
+        kind="llama", llm=dict(hidden_size=128, heads=2, layers=1, intermediate_size=256, vocab_size=256),
+        task="forecasting", T=48, pred=16, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="interleave",
+        description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
 }
 
 

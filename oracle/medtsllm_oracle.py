@@ -215,8 +215,8 @@ def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, retur
 # ----------------------------------------------------------------------------- whole path
 def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training: bool = False,
                      return_stages: bool = False, lora=None):
-    """MedTsLLM.forward/predict (models/medtsllm.py:248-261, 321-384) for covariate modes
-    `concat` / `univariate` and all three down-sample modes, dropout = 0.
+    """MedTsLLM.forward/predict (models/medtsllm.py:248-261, 321-384): all seven covariate modes, all three
+    down-sample modes, optional LoRA; dropout = 0.
 
     spec keys: task, pred_len, patch_len, stride, d_model (per-feature), d_ff, n_heads, covariate_mode,
     downsample, n_outputs_per_step, backbone ("llama"|"gpt2"), n_layers, llm_heads, eps, rope_theta,
@@ -235,17 +235,32 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     enc = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
     N = enc.shape[1]
     stages["patch_embedding"] = enc
-    if spec["covariate_mode"] == "concat":
+    mode = spec["covariate_mode"]
+    if mode == "concat":
         enc = enc.reshape(B, C, N, dm).permute(0, 2, 1, 3).reshape(B, N, C * dm)
-    elif spec["covariate_mode"] != "univariate":
-        raise NotImplementedError(spec["covariate_mode"])
+    elif mode == "univariate":
+        assert C == 1
+    elif mode not in ("interleave", "independent", "merge-end", "add", "weighted-average"):
+        raise ValueError(mode)
     source = mapping(word_emb, adapters["mapping_layer.weight"], adapters["mapping_layer.bias"])
     stages["source_embeddings"] = source
-    enc = reprogramming(enc, source, adapters, spec["n_heads"])
-    stages["reprogramming_layer"] = enc
+    enc = reprogramming(enc, source, adapters, spec["n_heads"])        # [B or B*C, N, D]
+    stages["reprogramming_layer"] = enc                                # (the module's own output, pre-merge)
+    D = enc.shape[-1]
+    if mode == "add":                                                  # models/medtsllm.py:284-286
+        enc = enc.reshape(B, C, N, D).mean(dim=1)
+    elif mode == "weighted-average":                                   # :287-291
+        enc = F.linear(enc.reshape(B, C, N, D).permute(0, 2, 3, 1), adapters["feature_weighting.weight"],
+                       adapters["feature_weighting.bias"]).squeeze(-1)
+    elif mode == "interleave":                                         # :292-295  (n-major, c-minor)
+        enc = enc.reshape(B, C, N, D).permute(0, 2, 1, 3).reshape(B, N * C, D)
+        N = N * C
 
     # prompt + backbone (models/medtsllm.py:330-351)
     prompt = assemble_prompt(prompt_ids, word_emb, spec["pad_id"])
+    if mode in ("independent", "merge-end"):                           # models/medtsllm.py:343-344
+        prompt = prompt.repeat_interleave(C, dim=0)
+    Bp = enc.shape[0]
     llm_in = torch.cat([prompt, enc], dim=1)
     stages["llm_input"] = llm_in
     if spec["backbone"] == "llama":
@@ -264,12 +279,18 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     elif spec["downsample"] == "linear":
         dec = F.linear(dec, adapters["embedding_downsample_layer.weight"], adapters["embedding_downsample_layer.bias"])
     elif spec["downsample"] == "average":
-        dec = dec.reshape(B, N, spec["d_ff"], -1).mean(dim=-1)
+        dec = dec.reshape(Bp, N, spec["d_ff"], -1).mean(dim=-1)
     stages["downsample"] = dec
     dec = dec.permute(0, 2, 1).contiguous().flatten(start_dim=-2)          # k = f*N + n
     dec = F.linear(dec, adapters["output_projection.linear.weight"], adapters["output_projection.linear.bias"])
     stages["output_projection"] = dec
-    dec = dec.view(B, spec["pred_len"], spec["n_outputs_per_step"])
+    nops = spec["n_outputs_per_step"]
+    if mode == "independent":                                          # models/medtsllm.py:369-371
+        dec = dec.view(B, C, spec["pred_len"], nops).mean(dim=1)
+    elif mode == "merge-end":                                          # :372-375
+        dec = dec.view(B, C, spec["pred_len"], nops).permute(0, 2, 3, 1).reshape(B, spec["pred_len"], -1)
+        dec = F.linear(dec, adapters["feature_weighting.weight"], adapters["feature_weighting.bias"])
+    dec = dec.reshape(B, spec["pred_len"], nops)
     if spec["task"] in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
         dec = revin_denorm(dec, mean, stdev)
     else:

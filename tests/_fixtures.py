@@ -16,7 +16,8 @@ for p in (REPO, REPO / "med-ts-llm_b200"):
         sys.path.insert(0, str(p))
 
 CASES = ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate", "llama_forecast_clip_stats",
-         "llama_forecast_truncate", "gpt2_reconstruction_average"]
+         "llama_forecast_truncate", "gpt2_reconstruction_average", "llama_forecast_independent",
+         "gpt2_forecast_merge_end", "llama_anomaly_add", "gpt2_anomaly_weighted_average", "llama_forecast_interleave"]
 
 
 def load_case(name: str) -> dict:

@@ -78,9 +78,13 @@ def test_unsupported_options_fail_loudly(tmp_path):
     fix = load_case("llama_seg_concat")
     llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
     cfg = config_for(fix, llm_dir)
-    cfg["models"]["medtsllm"]["covariate_mode"] = "interleave"
-    with pytest.raises(NotImplementedError):
+    cfg["models"]["medtsllm"]["covariate_mode"] = "stacked"
+    with pytest.raises(ValueError):
         MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    cfg["models"]["medtsllm"]["covariate_mode"] = "concat"
+    cfg["models"]["medtsllm"]["prompting"]["examples"] = True
+    with pytest.raises(NotImplementedError):
+        MedTsLLM(Cfg(cfg), Dataset(fix["dataset"])).build_prompt(fix["inputs"])
     cfg = config_for(fix, llm_dir)
     cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16, "dropout": 0.1}
     with pytest.raises(NotImplementedError):
