@@ -51,13 +51,15 @@ __device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, i
 //   TMEM -> registers (thread = accumulator row, 32 columns per tcgen05.ld) -> bias / activation ->
 //   per-warp padded smem tile -> coalesced 16-byte global accesses.
 //   row0  = global row of the slab's first row,   taddr = TMEM address of (slab lane 0, tile column 0)
+//   col_off / n_cols: the tile may be a column slice [col_off, col_off + n_cols) of the BN-wide block
+//   (tail splitting in the CTA-pair kernel); full tiles pass (0, BN).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int row0, int n_blk, uint32_t taddr,
-                                              float* stage_buf, int lane) {
+                                              float* stage_buf, int lane, int col_off = 0, int n_cols = BN) {
       const int row = row0 + lane;                       // the accumulator row this thread reads
       const float bias_m = (p.bias_axis == 2 && row < p.m) ? p.bias[row] : 0.0f;
 
-      constexpr int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : BN / 32;
+      const int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : n_cols / 32;
       const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
 #pragma unroll 1
       for (int ci = 0; ci < kChunks; ++ci) {
@@ -78,7 +80,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           uint32_t r[32];
           tmem_ld_32x32(taddr + ci * 32, r);
           tmem_ld_wait();
-          col0 = n_blk * BN + ci * 32;
+          col0 = n_blk * BN + col_off + ci * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_m;
           if (p.bias_axis == 1 && col0 < p.n) {

@@ -26,6 +26,40 @@ constexpr int kPairBarrierBytes = 256;
 constexpr int kPairSmemBytes =
     kPairStages * kPairStageBytes + kPairBarrierBytes + 4 * 32 * kEpiPitch * 4 + 1024;
 
+// Work units of the CTA-pair kernel.  Units [0, full) are whole 256x256 tiles.  When the last wave would
+// be mostly empty (e.g. 384 tiles on 74 pairs = 5.19 waves: o-proj / down-proj / every dgrad with N = 4096),
+// its `tail` tiles are split into `split` column slices of 256/split columns each, so the tail wave costs a
+// fraction of a full tile instead of a whole one.
+struct PairSchedule {
+  int full, split, total;   // total = full + tail * split
+};
+__host__ __device__ inline PairSchedule pair_schedule(int num_tiles, int num_pairs, bool allow_split) {
+  PairSchedule s;
+  const int tail = num_tiles % num_pairs;
+  s.split = 1;
+  if (allow_split && num_tiles > num_pairs && tail > 0) {
+    if (tail * 4 <= num_pairs) s.split = 4;
+    else if (tail * 2 <= num_pairs) s.split = 2;
+  }
+  s.full = s.split > 1 ? num_tiles - tail : num_tiles;
+  s.total = s.full + (num_tiles - s.full) * s.split;
+  return s;
+}
+struct PairUnit {
+  int tile, col_off, n_cols;
+};
+__device__ __forceinline__ PairUnit pair_unit(int u, const PairSchedule& s) {
+  PairUnit r;
+  if (u < s.full) { r.tile = u; r.col_off = 0; r.n_cols = kPairBN; }
+  else {
+    const int v = u - s.full;
+    r.tile = s.full + v / s.split;
+    r.n_cols = kPairBN / s.split;
+    r.col_off = (v % s.split) * r.n_cols;
+  }
+  return r;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -56,6 +90,7 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int k_blocks = (p.k + kBlockK - 1) / kBlockK;
   const int tiles_per_batch = m_blocks * n_blocks;
   const int num_tiles = tiles_per_batch * p.batch;
+  const PairSchedule sched = pair_schedule(num_tiles, num_pairs, EPI != MTS_EPI_SWIGLU);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -84,13 +119,15 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int b = tile / tiles_per_batch;
-        const int t = tile - b * tiles_per_batch;
+      for (int unit = pair; unit < sched.total; unit += num_pairs) {
+        const PairUnit pu = pair_unit(unit, sched);
+        const int b = pu.tile / tiles_per_batch;
+        const int t = pu.tile - b * tiles_per_batch;
         int m_blk, n_blk;
         tile_coords(t, m_blocks, n_blocks, m_blk, n_blk);
         const int row_a = m_blk * 2 * kBlockM + (int)rank * kBlockM;
-        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        // this CTA's half of the unit's B columns (the 128-row box over-reads for narrow units: harmless)
+        const int row_b = n_blk * BN + pu.col_off + (int)rank * (pu.n_cols / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * kPairStageBytes);
@@ -106,11 +143,11 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int unit = pair; unit < sched.total; unit += num_pairs, ++it) {
+        const uint32_t idesc = umma_idesc_bf16(2 * kBlockM, (uint32_t)pair_unit(unit, sched).n_cols);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
@@ -136,9 +173,10 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     float* stage_buf = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) +
                        quarter * (32 * kEpiPitch);
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int b = tile / tiles_per_batch;
-      const int t = tile - b * tiles_per_batch;
+    for (int unit = pair; unit < sched.total; unit += num_pairs, ++it) {
+      const PairUnit pu = pair_unit(unit, sched);
+      const int b = pu.tile / tiles_per_batch;
+      const int t = pu.tile - b * tiles_per_batch;
       int m_blk, n_blk;
       tile_coords(t, m_blocks, n_blocks, m_blk, n_blk);
       const int acc = it & 1;
@@ -147,7 +185,7 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       epilogue_tile<BN, EPI>(p, b, m_blk * 2 * kBlockM + (int)rank * kBlockM + quarter * 32, n_blk,
                              tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN),
-                             stage_buf, lane);
+                             stage_buf, lane, pu.col_off, pu.n_cols);
       tc_fence_before();
       if (rank == 0) mbar_arrive(tempty_bar(acc));
       else           mbar_arrive_cluster(tempty_bar(acc), 0);
@@ -174,7 +212,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_done = true;
   }
   const int pairs = num_sms() / 2;
-  const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
+  const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);   // (splitting only applies when tiles > pairs)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);

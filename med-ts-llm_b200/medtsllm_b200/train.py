@@ -93,7 +93,8 @@ class _HotPathFn(torch.autograd.Function):
 
         # ---- down-sample Linear on the last N tokens: flat[b, f, n] = hid[b, Lp+n] . W_ds[f] + b_ds[f]
         # dflat is [B][E][N]; dY_ds[(b, n), f] = dflat[b, f, n] is a per-batch transpose
-        dyds = bf(R, E)
+        Rh = B * N                                  # rows entering the down-sample step: (sequence, token)
+        dyds = bf(Rh, E)
         for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
             ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
         g_bds = g_wds = None
@@ -102,7 +103,7 @@ class _HotPathFn(torch.autograd.Function):
             hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D,
                                                in_off=Lp * D)                  # [D, ceil8(R)]
             g_wds = f32(E, D)
-            ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=R, lda=ops.ceil8(R), ldb=hid_last_t.shape[1])
+            ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
         wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
         wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
         dhid = zbf(B * L, D)                                                    # zero for prompt rows

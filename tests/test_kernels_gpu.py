@@ -449,9 +449,14 @@ def test_rowsum(ops, cuda):
 def test_gemm_cta_pair_and_single_cta_kernels_agree(ops, cuda):
     """The cta_group::2 kernel (default for 256-wide tiles) and the 1-CTA kernel compute the same tiles: with the
     same operands they must agree bit for bit (same MMA shape per k-step, same fp32 accumulation order)."""
+    _pair_vs_single(ops, cuda, 900, 1536, 640)       # 24 pair tiles: one partial wave, no tail split
+    _pair_vs_single(ops, cuda, 4864, 1024, 256)      # 76 pair tiles on 74 pairs: tail of 2 split into 4 column slices
+    _pair_vs_single(ops, cuda, 5000, 2304, 192)      # 180 tiles: tail 32 -> 2 slices; ragged M
+
+
+def _pair_vs_single(ops, cuda, m, n, k):
     from medtsllm_b200 import _lib
     g = torch.Generator().manual_seed(61)
-    m, n, k = 900, 1536, 640
     a = torch.randn(m, k, generator=g).to(cuda, torch.bfloat16)
     b = torch.randn(n, k, generator=g).to(cuda, torch.bfloat16)
     bias = torch.randn(n, generator=g).to(cuda)
