@@ -212,6 +212,11 @@ int mts_prompt_gather(const int32_t* ids, const float* emb, const float* wpe, fl
 int mts_swiglu(const uint16_t* gu, int64_t ldgu, uint16_t* y, int64_t rows, int I,
                mts_stream_t stream);
 
+/* Dropout for the training path (ref: models/layers/embed.py:183,197 PatchEmbedding.dropout; models/medtsllm.py:587
+ * reprogramming attention dropout): y[i] = keep(seed, i) ? x[i] / (1 - p) : 0, counter-based so that the backward
+ * re-creates the mask from the same seed (call it on the gradient).  x == y allowed.  dtype: mts_dtype. */
+int mts_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, mts_stream_t stream);
+
 /* eval-only output activations, in place on fp32 (ref: models/medtsllm.py:251-259):
  *   sigmoid (binary semantic segmentation / boundary prediction), softmax over n classes. */
 int mts_sigmoid(float* y, int64_t n, mts_stream_t stream);

@@ -373,3 +373,50 @@ extern "C" int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t s
   count_launch();
   return check_launch("softmax_lastdim_kernel");
 }
+
+// ------------------------------------------------------------------------------------------
+// Dropout (training only; models/medtsllm.py:93-94 -> PatchEmbedding.dropout, embed.py:183,197, and the
+// reprogramming attention dropout, :587).  Counter-based: the keep/drop decision of element i is a pure
+// function of (seed, i), so the backward re-creates the forward's mask by calling the same kernel on the
+// gradient with the same seed.  y = keep ? x / (1 - p) : 0.
+// ------------------------------------------------------------------------------------------
+namespace mts {
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finaliser, upper bits
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32);
+}
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n,
+                                    uint32_t thresh, float scale, uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool keep = mix32(seed * 0xD1342543DE82EF95ull + (uint64_t)i) >= thresh;
+    y[i] = keep ? __float2bfloat16_rn(__bfloat162float(x[i]) * scale) : __float2bfloat16_rn(0.f);
+  }
+}
+__global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, uint32_t thresh,
+                                   float scale, uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool keep = mix32(seed * 0xD1342543DE82EF95ull + (uint64_t)i) >= thresh;
+    y[i] = keep ? x[i] * scale : 0.f;
+  }
+}
+}  // namespace mts
+
+extern "C" int mts_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, mts_stream_t s) {
+  if (!x || !y || n < 0 || !(p >= 0.f && p < 1.f)) return set_error(MTS_ERR_INVALID_ARG, "mts_dropout: bad args");
+  if (n == 0) return MTS_OK;
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float scale = 1.0f / (1.0f - p);
+  if (dtype == MTS_BF16)
+    dropout_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, thresh, scale, seed);
+  else if (dtype == MTS_F32)
+    dropout_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(static_cast<const float*>(x),
+                                                                     static_cast<float*>(y), n, thresh, scale, seed);
+  else
+    return set_error(MTS_ERR_INVALID_ARG, "mts_dropout: bad dtype");
+  count_launch();
+  return check_launch("dropout_kernel");
+}

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mts_softmax_rows": [_p, _p, _i64, _i, _f, _p],
     "mts_prompt_gather": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mts_swiglu": [_p, _i64, _p, _i64, _i, _p],
+    "mts_dropout": [_p, _p, _i, _i64, _f, C.c_uint64, _p],
     "mts_sigmoid": [_p, _i64, _p],
     "mts_softmax_lastdim": [_p, _i64, _i, _p],
     "mts_rmsnorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],

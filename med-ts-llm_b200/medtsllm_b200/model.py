@@ -496,6 +496,16 @@ class MedTsLLM(nn.Module):
                 ops.sigmoid_(out)
         return out
 
+    def _warn_backbone_dropout(self):
+        cfg = getattr(self.llm, "config", None)
+        pd = max(float(getattr(cfg, k, 0.0) or 0.0) for k in ("attn_pdrop", "embd_pdrop", "resid_pdrop", "attention_dropout")) \
+            if cfg is not None else 0.0
+        if pd > 0 and not getattr(self, "_warned_bb_dropout", False):
+            import warnings
+            warnings.warn(f"the frozen backbone's own dropouts (p={pd}; live in the reference's train mode because "
+                          "model.train() also flips the HF module) are not applied by the kernel path", stacklevel=3)
+            self._warned_bb_dropout = True
+
     def _check_input(self, inputs):
         x_enc = inputs["x_enc"]
         if not x_enc.is_cuda:
@@ -541,6 +551,14 @@ class MedTsLLM(nn.Module):
             x_enc, self.patch_embedding.value_embedding.tokenConv.weight.detach(), self.patch_len, self.stride,
             concat=concat)
         assert enc.shape[1] == N0
+        # train-mode dropout on the patch embeddings and the reprogramming attention (models/layers/embed.py:197,
+        # models/medtsllm.py:587); seeds come from torch's CPU generator so torch.manual_seed reproduces a run
+        p_drop = self._dropout_requested if self.training else 0.0
+        seeds = [int(v) for v in torch.randint(0, 2 ** 62, (2,))] if p_drop > 0 else None
+        self._last_dropout_seeds = seeds
+        if p_drop > 0:
+            self._warn_backbone_dropout()
+            ops.dropout(enc, p_drop, seeds[0], out=enc)
 
         # K3/K4: reprogramming cross-attention on tcgen05 GEMMs
         source, K, Vt = self._source_kv()
@@ -554,8 +572,9 @@ class MedTsLLM(nn.Module):
         ops.gemm(Q, K, scores, m=rows, n=S, k=E, batch=H, lda=HE, ldb=HE, a_bs=E, b_bs=E, d_bs=rows * S)
         scale = 1.0 / math.sqrt(E)
         P = ops.softmax_rows(scores, scale)
+        Pd = ops.dropout(P, p_drop, seeds[1]) if p_drop > 0 else P        # attention actually applied
         O = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
-        ops.gemm(P, Vt, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
+        ops.gemm(Pd, Vt, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
         wo = self._bf16_weight("wo", rl.out_projection.weight)
         bo = rl.out_projection.bias.detach()
         Y = None
@@ -620,7 +639,7 @@ class MedTsLLM(nn.Module):
         if stash is not None:
             stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
                          hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Bp=Bp, B=B, N0=N0,
-                         scale=scale, denorm=denorm, concat=concat, Y=Y, head=head)
+                         scale=scale, denorm=denorm, concat=concat, Y=Y, head=head, Pd=Pd, p_drop=p_drop, seeds=seeds)
         return out
 
 

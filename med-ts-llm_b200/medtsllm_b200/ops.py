@@ -473,3 +473,15 @@ def merge_end_bwd(dy, h, W, B, C, P, O):
     _lib.call("mts_merge_end_bwd", dy.data_ptr(), h.data_ptr(), W.data_ptr(), dh.data_ptr(), dW.data_ptr(),
               db.data_ptr(), B, C, P, O, _stream())
     return dh, dW, db
+
+
+def dropout(x, p, seed, out=None):
+    """y = keep(seed, i) ? x / (1-p) : 0 (bf16 or fp32).  Same (p, seed) on the gradient = the backward."""
+    _chk(x, None, "x")
+    if x.dtype not in (torch.bfloat16, torch.float32) or not x.is_contiguous():
+        raise MtsError("dropout: contiguous bf16 / fp32 tensor required")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("mts_dropout", x.data_ptr(), out.data_ptr(), _dt(x), x.numel(), float(p), int(seed) & (2 ** 64 - 1),
+              _stream())
+    return out

@@ -11,8 +11,8 @@ chain below.  Every contraction is the tcgen05 NT GEMM (mts_gemm) on transposed 
 the rest are the kernels of csrc/backward.cu and the attention backward.
 
 Numerics: bf16 operands / fp32 accumulation like the forward (= the reference's bf16-autocast
-regime); the residual-stream gradient is fp32.  Dropout is not implemented: `training.dropout` must be
-0 (the shipped configs use 0.1 — see DESIGN.md, deviation list).
+regime); the residual-stream gradient is fp32.  `training.dropout` (patch-embedding and reprogramming-attention
+dropout) uses a counter-based mask that the backward re-creates from the step's seeds.
 """
 from __future__ import annotations
 
@@ -23,10 +23,6 @@ from ._lib import BIAS_NONE, EPI_RESID_ADD, MtsError
 
 
 def forward_train(model, inputs):
-    if model._dropout_requested > 0:
-        raise MtsError(
-            f"training.dropout = {model._dropout_requested}: the kernel path implements the deterministic model "
-            "only (PatchEmbedding / reprogramming dropout not built yet); set training.dropout = 0")
     params = model.adapter_params()
     return _HotPathFn.apply(model, inputs, *params)
 
@@ -142,15 +138,18 @@ class _HotPathFn(torch.autograd.Function):
         ops.gemm(dxp, wo_t, dO, m=R, n=HE, k=D, ldb=wo_t.shape[1])
 
         # ---- cross-attention core, per head h: O_h = P_h V_h, P_h = softmax(scale Q_h K_h^T)
-        P, Q, K, Vt = st["P"], st["Q"], st["K"], st["Vt"]
+        P, Pd, Q, K, Vt = st["P"], st["Pd"], st["Q"], st["K"], st["Vt"]
+        p_drop, seeds = st["p_drop"], st["seeds"]
         Vm = ops.transpose_strided(Vt, rows=HE, cols=S)                        # [S, HE]
         dP = f32(H, R, S)
         ops.gemm(dO, Vm, dP, m=R, n=S, k=E, batch=H, lda=HE, a_bs=E, ldb=Vm.shape[1], b_bs=E, d_bs=R * S)
+        if p_drop > 0:
+            ops.dropout(dP, p_drop, seeds[1], out=dP)                          # same mask as the forward's attention dropout
         dS = ops.softmax_bwd_rows(P, dP, st["scale"])                          # bf16 [H, R, S]
         # per-head transposes laid out [S, H*Rp]: head h occupies columns [h*Rp, h*Rp + R)
         P_t, dS_t = zbf(S, H * Rp), zbf(S, H * Rp)
         for h in range(H):
-            ops.transpose_strided(P, rows=R, cols=S, in_off=h * R * S, out=P_t[:, h * Rp:], ld_out=H * Rp)
+            ops.transpose_strided(Pd, rows=R, cols=S, in_off=h * R * S, out=P_t[:, h * Rp:], ld_out=H * Rp)
             ops.transpose_strided(dS, rows=R, cols=S, in_off=h * R * S, out=dS_t[:, h * Rp:], ld_out=H * Rp)
         dO_t, Q_t = _t(dO), _t(Q)                                              # [HE, Rp]
         dV = bf(S, HE)
@@ -171,6 +170,8 @@ class _HotPathFn(torch.autograd.Function):
         wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
         denc = f32(R, dm)
         ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
+        if p_drop > 0:
+            ops.dropout(denc, p_drop, seeds[0], out=denc)                      # patch-embedding dropout mask
         g_conv = ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
                                            m.patch_len, m.stride, m.d_patch, concat=st["concat"])
 

@@ -75,8 +75,9 @@ def mapping(word_emb, w, b):
     return w @ word_emb + b[:, None]
 
 
-def reprogramming(x, source, sd, n_heads: int, prefix="reprogramming_layer."):
-    """models/medtsllm.py:566-591 (dropout = identity at p=0 / eval)."""
+def reprogramming(x, source, sd, n_heads: int, prefix="reprogramming_layer.", attn_mask=None):
+    """models/medtsllm.py:566-591.  `attn_mask` [B, H, L, S]: the multiplicative dropout mask (0 or 1/(1-p)) applied
+    to the attention probabilities in train mode (:587); None = eval / p = 0."""
     B, L, _ = x.shape
     S = source.shape[0]
     q = F.linear(x, sd[prefix + "query_projection.weight"], sd[prefix + "query_projection.bias"]).view(B, L, n_heads, -1)
@@ -85,6 +86,8 @@ def reprogramming(x, source, sd, n_heads: int, prefix="reprogramming_layer."):
     scale = 1.0 / math.sqrt(q.shape[-1])
     scores = torch.einsum("blhe,she->bhls", q, k)
     A = torch.softmax(scale * scores, dim=-1)
+    if attn_mask is not None:
+        A = A * attn_mask
     out = torch.einsum("bhls,she->blhe", A, v).reshape(B, L, -1)
     return F.linear(out, sd[prefix + "out_projection.weight"], sd[prefix + "out_projection.bias"])
 
@@ -214,7 +217,7 @@ def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, retur
 
 # ----------------------------------------------------------------------------- whole path
 def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training: bool = False,
-                     return_stages: bool = False, lora=None):
+                     return_stages: bool = False, lora=None, dropout_masks=None):
     """MedTsLLM.forward/predict (models/medtsllm.py:248-261, 321-384): all seven covariate modes, all three
     down-sample modes, optional LoRA; dropout = 0.
 
@@ -234,6 +237,8 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     xn = revin_norm(x_enc, mean, stdev).permute(0, 2, 1).contiguous()
     enc = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
     N = enc.shape[1]
+    if dropout_masks is not None:       # PatchEmbedding.dropout (models/layers/embed.py:197), mask in [B*C, N, dm] order
+        enc = enc * dropout_masks["patch"]
     stages["patch_embedding"] = enc
     mode = spec["covariate_mode"]
     if mode == "concat":
@@ -244,7 +249,8 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
         raise ValueError(mode)
     source = mapping(word_emb, adapters["mapping_layer.weight"], adapters["mapping_layer.bias"])
     stages["source_embeddings"] = source
-    enc = reprogramming(enc, source, adapters, spec["n_heads"])        # [B or B*C, N, D]
+    enc = reprogramming(enc, source, adapters, spec["n_heads"],
+                        attn_mask=dropout_masks["reprog"] if dropout_masks is not None else None)   # [B or B*C, N, D]
     stages["reprogramming_layer"] = enc                                # (the module's own output, pre-merge)
     D = enc.shape[-1]
     if mode == "add":                                                  # models/medtsllm.py:284-286

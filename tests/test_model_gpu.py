@@ -228,3 +228,51 @@ def test_lora_forward_and_gradients(name, rank, tmp_path, cuda):
     assert worst[1] < tol[worst[0]], worst
     model.llm.save_pretrained(tmp_path / "ckpt" / "best-lora.safetensors")
     assert (tmp_path / "ckpt" / "best-lora.safetensors").exists()
+
+
+def test_training_with_dropout(tmp_path, cuda):
+    """training.dropout = 0.1 (the shipped configs): the masks the kernel path draws are read back (same counter-based
+    function of the step's seeds) and handed to the oracle, so forward and gradients can be compared exactly like the
+    deterministic case; plus the drop rate itself."""
+    from medtsllm_b200 import ops
+    from medtsllm_b200.model import MedTsLLM
+    from oracle import medtsllm_oracle as O
+    from _fixtures import oracle_spec
+    fix = load_case("llama_seg_concat")
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    cfg["training"]["dropout"] = 0.1
+    model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda).train()
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    torch.manual_seed(11)
+    out = model(inputs)
+    s_patch, s_attn = model._last_dropout_seeds
+    wgt = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * wgt.to(cuda)).sum().backward()
+    B, T, C = fix["inputs"]["x_enc"].shape
+    N, H, S, p = model.n_patches, model.n_attention_heads, model.num_tokens, 0.1
+    keep_patch = ops.dropout(torch.ones(B, N, C * 32, device=cuda, dtype=torch.bfloat16), p, s_patch) != 0
+    keep_attn = ops.dropout(torch.ones(H, B * N, S, device=cuda, dtype=torch.bfloat16), p, s_attn) != 0
+    assert abs(1 - keep_attn.float().mean().item() - p) < 2e-3 and abs(1 - keep_patch.float().mean().item() - p) < 3e-2
+    # oracle layouts: patch mask in [B*C, N, 32] (pre-concat) order, attention mask [B, H, N, S]
+    m_patch = (keep_patch.float().cpu() / (1 - p)).view(B, N, C, 32).permute(0, 2, 1, 3).reshape(B * C, N, 32)
+    m_attn = (keep_attn.float().cpu() / (1 - p)).view(H, B, N, S).permute(1, 0, 2, 3)
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ad = {k: v.clone().requires_grad_(True) for k, v in fix["adapters"].items()}
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, oracle_spec(fix), training=True,
+                             dropout_masks={"patch": m_patch, "reprog": m_attn})
+    assert _rel_l2(out, ref) < 2e-2
+    assert _rel_l2(out, fix["stages"]["output_train"]) > 1e-2        # dropout really changed the forward
+    (ref * wgt).sum().backward()
+    for k, prm in model.named_parameters():
+        if k in ("reprogramming_layer.key_projection.bias",):
+            continue
+        e = _rel_l2(prm.grad, ad[k].grad)
+        assert e < (1.5e-1 if k == "mapping_layer.bias" else 5e-2), (k, e)
+    # eval mode: no dropout, deterministic
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model(inputs), model(inputs)) and model._last_dropout_seeds is None
