@@ -526,7 +526,7 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* 
 // C(16 x 64) = A(16 x HD, rows [arow0, +16) of As) * B^T, B = 64 rows of Bs (both [row][HD+8] bf16)
 template <int HD>
 __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* As, int arow0,
-                                         const __nv_bfloat16* Bs, int lane) {
+                                         const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4) {
   constexpr int kPitch = HD + 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
@@ -536,6 +536,7 @@ __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* 
     ldmatrix_x4(smem_u32(As + (arow0 + (lane & 15)) * kPitch + ks * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
+      if (np < g_lo || np >= g_hi) continue;   // warp-uniform: 16-column groups outside the causal range
       const int id = lane >> 3;
       uint32_t r0, r1, r2, r3;
       ldmatrix_x4(smem_u32(Bs + (np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch + ks * 16 + (id & 1) * 8),
@@ -549,10 +550,11 @@ __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* 
 // acc(16 x HD) += P(16 x 64, fp32 C-fragments) * B, B = 64 rows of Bs ([row][HD+8] bf16)
 template <int HD>
 __device__ __forceinline__ void mma_p_b(float (&acc)[HD / 8][4], const float (&pm)[8][4],
-                                        const __nv_bfloat16* Bs, int lane) {
+                                        const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4) {
   constexpr int kPitch = HD + 8;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    if (kk < g_lo || kk >= g_hi) continue;     // P is identically zero in those 16-wide groups
     uint32_t pa[4];
     pa[0] = pack_bf16(pm[2 * kk][0], pm[2 * kk][1]);
     pa[1] = pack_bf16(pm[2 * kk][2], pm[2 * kk][3]);
@@ -748,6 +750,204 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, L, tq, nullptr, nullptr);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward, short sequences: same idea as attn_causal_fwd_seq_kernel.  One CTA per (b, h) keeps the
+// operands every strip needs resident in shared memory (dQ: K and V; dK/dV: Q, dO, lse, delta), staged
+// once with cp.async from the already rotated qkv, and 8 warps pull 16-row strips from a shared counter,
+// heaviest first.  Key / query groups outside a strip's causal range are skipped at 16-row granularity.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__device__ __forceinline__ void stage_rows_async(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, int64_t ld,
+                                                 int L, int Lp, int tid, int nthreads) {
+  constexpr int kPitch = HD + 8;
+  constexpr int kVec = HD / 8;
+  for (int i = tid; i < Lp * kVec; i += nthreads) {
+    const int r = i / kVec, c = (i - r * kVec) * 8;
+    if (r < L) cp_async16(smem_u32(dst + r * kPitch + c), src + (int64_t)r * ld + c);
+    else       *reinterpret_cast<uint4*>(dst + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+  }
+}
+template <int HD>
+__device__ __forceinline__ void stage_strip(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, int64_t ld,
+                                            int row0, int L, int lane) {
+  constexpr int kPitch = HD + 8;
+  constexpr int kVec = HD / 8;
+  for (int i = lane; i < 16 * kVec; i += 32) {
+    const int r = i / kVec, c = (i - r * kVec) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < L) v = *reinterpret_cast<const uint4*>(src + (int64_t)(row0 + r) * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * kPitch + c) = v;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kSeqThreads)
+attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                       const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
+                       const float* __restrict__ lse, const float* __restrict__ delta,
+                       __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int Lp = (L + 63) & ~63;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Vs = Ks + (size_t)Lp * kPitch;
+  __nv_bfloat16* Qw = Vs + (size_t)Lp * kPitch;            // [8 warps][16][kPitch]
+  __nv_bfloat16* dOw = Qw + 8 * 16 * kPitch;               // [8 warps][16][kPitch]
+  int* counter = reinterpret_cast<int*>(dOw + 8 * 16 * kPitch);
+
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+
+  stage_rows_async<HD>(Ks, qbase + D, ld, L, Lp, threadIdx.x, kSeqThreads);
+  stage_rows_async<HD>(Vs, qbase + 2 * D, ld, L, Lp, threadIdx.x, kSeqThreads);
+  cp_async_commit();
+  if (threadIdx.x == 0) *counter = 0;
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int n_strips = (L + 15) >> 4;
+  __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
+  __nv_bfloat16* dOs = dOw + warp * 16 * kPitch;
+  while (true) {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counter, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_strips) break;
+    const int q0 = (n_strips - 1 - ticket) * 16;
+    stage_strip<HD>(Qs, qbase, ld, q0, L, lane);
+    stage_strip<HD>(dOs, dobase, D, q0, L, lane);
+    __syncwarp();
+    const int row_a = q0 + g, row_b = row_a + 8;
+    const float lse_a = row_a < L ? lse[(int64_t)bh * L + row_a] * 1.4426950408889634f : INFINITY;
+    const float lse_b = row_b < L ? lse[(int64_t)bh * L + row_b] * 1.4426950408889634f : INFINITY;
+    const float del_a = row_a < L ? delta[(int64_t)bh * L + row_a] : 0.f;
+    const float del_b = row_b < L ? delta[(int64_t)bh * L + row_b] : 0.f;
+    float dq[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+    const int last_row = min(q0 + 15, L - 1);
+    for (int j0 = 0; j0 <= last_row; j0 += 64) {
+      const int g_hi = min(4, (last_row - j0) / 16 + 1);
+      float s[8][4], dp[8][4];
+      mma_a_bt<HD>(s, Qs, 0, Ks + j0 * kPitch, lane, 0, g_hi);
+      mma_a_bt<HD>(dp, dOs, 0, Vs + j0 * kPitch, lane, 0, g_hi);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+          const int row = (e < 2) ? row_a : row_b;
+          const float pv = (col > row || col >= L) ? 0.f : exp2f(s[nt][e] * scale_log2e - ((e < 2) ? lse_a : lse_b));
+          s[nt][e] = pv * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * scale;
+        }
+      }
+      mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi);
+    }
+    store_grad_rows<HD>(dq, dqkv + (int64_t)b * L * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq, rope_cos, rope_sin);
+    __syncwarp();
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kSeqThreads)
+attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                        const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
+                        const float* __restrict__ lse, const float* __restrict__ delta,
+                        __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  constexpr int kPitch = HD + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int Lp = (L + 63) & ~63;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* dOs = Qs + (size_t)Lp * kPitch;
+  __nv_bfloat16* Kw = dOs + (size_t)Lp * kPitch;           // [8 warps][16][kPitch]
+  __nv_bfloat16* Vw = Kw + 8 * 16 * kPitch;
+  float* lse_s = reinterpret_cast<float*>(Vw + 8 * 16 * kPitch);
+  float* del_s = lse_s + Lp;
+  int* counter = reinterpret_cast<int*>(del_s + Lp);
+
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
+  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+
+  stage_rows_async<HD>(Qs, qbase, ld, L, Lp, threadIdx.x, kSeqThreads);
+  stage_rows_async<HD>(dOs, dobase, D, L, Lp, threadIdx.x, kSeqThreads);
+  cp_async_commit();
+  for (int i = threadIdx.x; i < Lp; i += kSeqThreads) {
+    lse_s[i] = i < L ? lse[(int64_t)bh * L + i] * 1.4426950408889634f : INFINITY;
+    del_s[i] = i < L ? delta[(int64_t)bh * L + i] : 0.f;
+  }
+  if (threadIdx.x == 0) *counter = 0;
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int n_strips = (L + 15) >> 4;
+  __nv_bfloat16* Ks = Kw + warp * 16 * kPitch;
+  __nv_bfloat16* Vs = Vw + warp * 16 * kPitch;
+  while (true) {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counter, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_strips) break;
+    const int k0 = ticket * 16;                 // earliest keys see the most queries: heaviest first
+    stage_strip<HD>(Ks, qbase + D, ld, k0, L, lane);
+    stage_strip<HD>(Vs, qbase + 2 * D, ld, k0, L, lane);
+    __syncwarp();
+    const int key_a = k0 + g, key_b = key_a + 8;
+    float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    for (int i0 = (k0 / 64) * 64; i0 < L; i0 += 64) {
+      // query groups of 16 entirely before this key strip cannot attend to it
+      const int g_lo = max(0, (k0 - i0) / 16);
+      const int g_hi = min(4, (L - 1 - i0) / 16 + 1);
+      float st[8][4], dpt[8][4];                 // rows = keys, cols = queries
+      mma_a_bt<HD>(st, Ks, 0, Qs + i0 * kPitch, lane, g_lo, g_hi);
+      mma_a_bt<HD>(dpt, Vs, 0, dOs + i0 * kPitch, lane, g_lo, g_hi);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qrow = i0 + nt * 8 + tq * 2 + (e & 1);
+          const int key = (e < 2) ? key_a : key_b;
+          const bool dead = key > qrow || key >= L || qrow >= L || (nt >> 1) < g_lo || (nt >> 1) >= g_hi;
+          const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_s[min(qrow, Lp - 1)]);
+          st[nt][e] = pv;
+          dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_s[min(qrow, Lp - 1)]) * scale;
+        }
+      }
+      mma_p_b<HD>(dv, st, dOs + i0 * kPitch, lane, g_lo, g_hi);
+      mma_p_b<HD>(dk, dpt, Qs + i0 * kPitch, lane, g_lo, g_hi);
+    }
+    __nv_bfloat16* dbase = dqkv + (int64_t)b * L * ld + (int64_t)h * HD;
+    store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, L, tq, rope_cos, rope_sin);
+    store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, L, tq, nullptr, nullptr);
+    __syncwarp();
+  }
+}
+
+template <int HD>
+static size_t seq_bwd_smem_bytes(int L) {
+  const int Lp = (L + 63) & ~63;
+  return (size_t)(2 * Lp + 2 * 8 * 16) * (HD + 8) * 2 + (size_t)2 * Lp * 4 + 16;
+}
+
 template <int HD>
 static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
                            const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp,
@@ -769,6 +969,32 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
   count_launch();
   int rc_ = check_launch("attn_bwd_delta_kernel");
   if (rc_) return rc_;
+  if (pre_roped || rc == nullptr) {
+    // q / k in `qkv` are final (rotated or rope-free): short sequences take the sequence-resident kernels
+    if (seq_bwd_smem_bytes<HD>(L) <= 220 * 1024) {
+      auto sq = attn_bwd_dq_seq_kernel<HD>;
+      auto skv = attn_bwd_dkv_seq_kernel<HD>;
+      static bool seq_attr = false;
+      if (!seq_attr) {
+        cudaError_t e = cudaFuncSetAttribute(sq, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(skv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd seq)", e);
+        seq_attr = true;
+      }
+      const size_t smem = seq_bwd_smem_bytes<HD>(L);
+      sq<<<Bp * H, kSeqThreads, smem, stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+      count_launch();
+      rc_ = check_launch("attn_bwd_dq_seq_kernel");
+      if (rc_) return rc_;
+      skv<<<Bp * H, kSeqThreads, smem, stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+      count_launch();
+      return check_launch("attn_bwd_dkv_seq_kernel");
+    }
+  }
   const int64_t grid_l = (int64_t)((L + 63) / 64) * Bp * H;
   if (grid_l > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: grid too large");
   kq<<<(int)grid_l, kAttnThreads, kSmemQ, stream>>>(
