@@ -123,9 +123,12 @@ typedef enum mts_epilogue {
   MTS_EPI_RESID_ADD = 1, /* D = C + v   (D, C fp32; C = D when args.c is NULL) or, with bf16 D,   */
                          /* D = bf16(D + v) in place (LoRA side GEMMs accumulating into q / v)   */
   MTS_EPI_GELU_NEW = 2,  /* D = gelu_new(v)            (D bf16; HF:activations.py:59-66)         */
-  MTS_EPI_SWIGLU = 3     /* D[:, j] = silu(v_gate[j]) * v_up[j]   (D bf16, n/2 columns).  B rows  */
+  MTS_EPI_SWIGLU = 3,    /* D[:, j] = silu(v_gate[j]) * v_up[j]   (D bf16, n/2 columns).  B rows  */
                          /* must be packed by mts_pack_gate_up: blocks of 128 gate rows followed  */
                          /* by the matching 128 up rows (HF:models/llama/modeling_llama.py:182-184) */
+  MTS_EPI_ROPE_QK = 4    /* fused qkv projection with rotate-half RoPE applied (in fp32, from the   */
+                         /* accumulators) to output columns < rope_cols; D bf16; head dim 64 / 128, */
+                         /* position = row % rope_L (HF:models/llama/modeling_llama.py:139-168)     */
 } mts_epilogue;
 
 typedef enum mts_bias_axis { MTS_BIAS_NONE = 0, MTS_BIAS_N = 1, MTS_BIAS_M = 2 } mts_bias_axis;
@@ -145,6 +148,10 @@ typedef struct mts_gemm_args {
   int32_t d_transposed; /* STORE only: element (row i, col j) goes to d[j*ldd + i]               */
   int32_t block_n;      /* 0 = choose; else 64 / 128 / 256                                        */
   float alpha;
+  /* MTS_EPI_ROPE_QK only: fp32 tables [>= rope_L, rope_hd/2], sequence length, head dim, #rotated columns */
+  const float* rope_cos;
+  const float* rope_sin;
+  int32_t rope_L, rope_hd, rope_cols, reserved_;
 } mts_gemm_args;
 
 int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);

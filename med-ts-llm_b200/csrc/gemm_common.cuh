@@ -22,6 +22,10 @@ struct GemmParams {
   int bias_axis, d_transposed, d_is_f32, bias_vec, vec_ok;
   const float* c;  // RESID_ADD: residual source, same layout as d
   float alpha;
+  // ROPE_QK: rotate-half RoPE on output columns < rope_cols (the q | k sections of a fused qkv projection)
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_L, rope_hd, rope_cols;
 };
 
 __device__ __forceinline__ float gelu_new_f(float x) {
@@ -57,6 +61,74 @@ template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int row0, int n_blk, uint32_t taddr,
                                               float* stage_buf, int lane, int col_off = 0, int n_cols = BN) {
       const int row = row0 + lane;                       // the accumulator row this thread reads
+      if constexpr (EPI == MTS_EPI_ROPE_QK) {
+        // q/k columns are rotated in fp32 straight from the accumulators: x1' = x1 cos - x2 sin,
+        // x2' = x2 cos + x1 sin with x2 = the column hd/2 further (HF:models/llama/modeling_llama.py:139-168),
+        // position = row index inside the sample.  Chunk pairs (c, c + hd/64) of 32 columns hold (x1, x2).
+        const int half_chunks = p.rope_hd / 64;           // 1 (hd 64) or 2 (hd 128)
+        const int pos = row % p.rope_L;
+        const float* cr = p.rope_cos + (int64_t)pos * (p.rope_hd / 2);
+        const float* sr = p.rope_sin + (int64_t)pos * (p.rope_hd / 2);
+        __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride;
+        const int rr = lane >> 2, cc = (lane & 3) * 8;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 32; c0 += 2 * half_chunks) {        // one head (hd columns) per iteration
+#pragma unroll 1
+          for (int h = 0; h < half_chunks; ++h) {
+            const int ca = c0 + h, cb = ca + half_chunks;
+            uint32_t xa[32], xb[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + ca * 32, xa);
+            tmem_ld_32x32(taddr + cb * 32, xb);
+            tmem_ld_wait();
+            const int col_a = n_blk * BN + ca * 32, col_b = n_blk * BN + cb * 32;
+            if (col_a >= p.n) continue;                                 // warp-uniform
+            float va[32], vb[32];
+            if (col_a < p.rope_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + h * 32 + j));
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(sr + h * 32 + j));
+                const float cs[4] = {cv.x, cv.y, cv.z, cv.w}, sn[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float x1 = __uint_as_float(xa[j + q]) * p.alpha, x2 = __uint_as_float(xb[j + q]) * p.alpha;
+                  va[j + q] = x1 * cs[q] - x2 * sn[q];
+                  vb[j + q] = x2 * cs[q] + x1 * sn[q];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                va[j] = __uint_as_float(xa[j]) * p.alpha;
+                vb[j] = __uint_as_float(xb[j]) * p.alpha;
+              }
+            }
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const float* v = half ? vb : va;
+              const int col0 = half ? col_b : col_a;
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int ps = 0; ps < 4; ++ps) {
+                const int r_g = row0 + ps * 8 + rr;
+                if (col0 + cc < p.n && r_g < p.m) {
+                  const float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
+                  const float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
+                  *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd + col0 + cc) =
+                      make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
+                                 pack_bf16(a1.z, a1.w));
+                }
+              }
+            }
+          }
+        }
+        return;
+      }
       const float bias_m = (p.bias_axis == 2 && row < p.m) ? p.bias[row] : 0.0f;
 
       const int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : n_cols / 32;

@@ -274,6 +274,16 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
       if (f32 || a->d_transposed)
         return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: GELU_NEW needs bf16 non-transposed D");
       break;
+    case MTS_EPI_ROPE_QK:
+      if (f32 || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || !a->rope_cos || !a->rope_sin ||
+          (a->rope_hd != 64 && a->rope_hd != 128) || a->rope_L <= 0 || (a->rope_cols % a->rope_hd) ||
+          (a->n % a->rope_hd) || (bn != 0 && bn != 256) || (n_store % 8) || (a->ldd % 8) ||
+          (reinterpret_cast<uintptr_t>(a->rope_cos) & 15) || (reinterpret_cast<uintptr_t>(a->rope_sin) & 15))
+        return set_error(MTS_ERR_INVALID_ARG,
+                         "mts_gemm: ROPE_QK needs bf16 D, no bias, 16-byte aligned tables, head dim 64/128 dividing n "
+                         "and rope_cols, block_n 256");
+      bn = 256;
+      break;
     case MTS_EPI_SWIGLU:
       if (f32 || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || (a->n % 256) ||
           (bn != 0 && bn != 256))
@@ -324,6 +334,8 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.c = a->c ? a->c : static_cast<const float*>(a->d);
   p.bias_vec = (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
   p.alpha = a->alpha;
+  p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
+  p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols;
 
   if (bn == 256 && !a->d_transposed && gemm_2cta_enabled()) {
     // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them
@@ -342,6 +354,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   const int tiles = (int)tiles_l;
 
   if (a->epilogue == MTS_EPI_SWIGLU) return launch_gemm<256, MTS_EPI_SWIGLU>(ta, tb, p, tiles, stream);
+  if (a->epilogue == MTS_EPI_ROPE_QK) return launch_gemm<256, MTS_EPI_ROPE_QK>(ta, tb, p, tiles, stream);
   switch (bn) {
     case 256: return dispatch_epi<256>(a->epilogue, ta, tb, p, tiles, stream);
     case 128: return dispatch_epi<128>(a->epilogue, ta, tb, p, tiles, stream);

@@ -90,7 +90,7 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int k_blocks = (p.k + kBlockK - 1) / kBlockK;
   const int tiles_per_batch = m_blocks * n_blocks;
   const int num_tiles = tiles_per_batch * p.batch;
-  const PairSchedule sched = pair_schedule(num_tiles, num_pairs, EPI != MTS_EPI_SWIGLU);
+  const PairSchedule sched = pair_schedule(num_tiles, num_pairs, EPI != MTS_EPI_SWIGLU && EPI != MTS_EPI_ROPE_QK);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -248,6 +248,7 @@ int launch_gemm_2cta(int epilogue, const mts_gemm_args* a, const GemmParams& p, 
     case MTS_EPI_RESID_ADD: return launch_pair<MTS_EPI_RESID_ADD>(ta, tb, p, tiles, stream);
     case MTS_EPI_GELU_NEW: return launch_pair<MTS_EPI_GELU_NEW>(ta, tb, p, tiles, stream);
     case MTS_EPI_SWIGLU: return launch_pair<MTS_EPI_SWIGLU>(ta, tb, p, tiles, stream);
+    case MTS_EPI_ROPE_QK: return launch_pair<MTS_EPI_ROPE_QK>(ta, tb, p, tiles, stream);
     default: return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: unknown epilogue");
   }
 }

@@ -13,7 +13,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmtsb200.so"
 
 MTS_OK = 0
 MTS_BF16, MTS_F32 = 0, 1
-EPI_STORE, EPI_RESID_ADD, EPI_GELU_NEW, EPI_SWIGLU = 0, 1, 2, 3
+EPI_STORE, EPI_RESID_ADD, EPI_GELU_NEW, EPI_SWIGLU, EPI_ROPE_QK = 0, 1, 2, 3, 4
 BIAS_NONE, BIAS_N, BIAS_M = 0, 1, 2
 
 
@@ -29,6 +29,8 @@ class GemmArgs(C.Structure):
         ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("batch", C.c_int32),
         ("d_dtype", C.c_int32), ("epilogue", C.c_int32), ("bias_axis", C.c_int32),
         ("d_transposed", C.c_int32), ("block_n", C.c_int32), ("alpha", C.c_float),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("rope_L", C.c_int32), ("rope_hd", C.c_int32), ("rope_cols", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -22,7 +22,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import ops
-from ._lib import BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_STORE, EPI_SWIGLU, MtsError
+from ._lib import BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_ROPE_QK, EPI_STORE, EPI_SWIGLU, MtsError
 
 
 @dataclass
@@ -254,16 +254,21 @@ class KernelBackbone:
                     h = bf(M, D)          # the LoRA backward needs this layer's normed input
             x_in = x
             # --- attention half
+            fused_rope = llama and lora is None      # RoPE must follow the LoRA update of q: keep it separate then
             if llama:
                 ops.rmsnorm(x_in, lay["ln1"], s.eps, out=h)
-                ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D)
+                if fused_rope:   # q | k rotated in fp32 straight from the accumulators, in the GEMM epilogue
+                    ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, epilogue=EPI_ROPE_QK, rope=rope, rope_L=L,
+                             rope_hd=hd, rope_cols=2 * D)
+                else:
+                    ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D)
             else:
                 ops.layernorm(x_in, lay["ln1"], lay["ln1b"], s.eps, out=h)
                 ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"], bias_axis=BIAS_N)
             lora_t = lora.forward_layer(li, h, qkv, M, D) if lora is not None else None
             h_attn = h
             lse = None
-            if rope is not None:
+            if rope is not None and not fused_rope:
                 ops.rope_qk_(qkv, Bp, L, H, hd, rope)      # q, k rotated in place; attention stages them as is
             if train:
                 _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att, want_lse=True)

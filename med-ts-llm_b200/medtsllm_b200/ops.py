@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (BIAS_M, BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_STORE, EPI_SWIGLU,
+from ._lib import (BIAS_M, BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_ROPE_QK, EPI_STORE, EPI_SWIGLU,
                    MTS_BF16, MTS_F32, GemmArgs, MtsError)
 
 __all__ = [
@@ -42,7 +42,7 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
-         block_n=0, a_off=0, b_off=0, d_off=0, c=None):
+         block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0):
     """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
     if d.dtype not in (torch.bfloat16, torch.float32):
@@ -67,6 +67,9 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.d_transposed = 1 if d_transposed else 0
     args.block_n = block_n
     args.alpha = alpha
+    if rope is not None:
+        args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+        args.rope_L, args.rope_hd, args.rope_cols = rope_L, rope_hd, rope_cols
     _lib.call("mts_gemm", C.byref(args), _stream())
     return d
 

@@ -473,3 +473,28 @@ def _pair_vs_single(ops, cuda, m, n, k):
         _lib.set_option("gemm_2cta", 1)
     torch.testing.assert_close(outs[0][0].float(), a.float() @ b.float().t() + bias, rtol=8e-3, atol=8e-2)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("Bp,L,H,hd,pair", [(2, 192, 4, 128, 1), (3, 70, 6, 64, 1), (2, 192, 4, 128, 0)])
+def test_gemm_rope_epilogue(ops, cuda, Bp, L, H, hd, pair):
+    """Fused qkv projection + RoPE (MTS_EPI_ROPE_QK): q | k columns rotated in fp32 from the accumulators, v untouched."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(hd + L)
+    D, M = H * hd, Bp * L
+    x = (torch.randn(M, D, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    w = (torch.randn(3 * D, D, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    tabs = _rope_tables(max(L, 512), hd, cuda)
+    out = torch.full((M, 3 * D), float("nan"), device=cuda, dtype=torch.bfloat16)
+    try:
+        _lib.set_option("gemm_2cta", pair)
+        ops.gemm(x, w, out, m=M, n=3 * D, k=D, epilogue=4, rope=tabs, rope_L=L, rope_hd=hd, rope_cols=2 * D)
+    finally:
+        _lib.set_option("gemm_2cta", 1)
+    ref = (x.float() @ w.float().t()).view(Bp, L, 3, H, hd)
+    cos = torch.cat([tabs[0][:L], tabs[0][:L]], -1)[None, :, None, None]
+    sin = torch.cat([tabs[1][:L], tabs[1][:L]], -1)[None, :, None, None]
+    qk = ref[:, :, :2]
+    rot = torch.cat([-qk[..., hd // 2:], qk[..., :hd // 2]], -1)
+    ref = torch.cat([qk * cos + rot * sin, ref[:, :, 2:]], dim=2).reshape(M, 3 * D)
+    torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=2e-2)
+    assert _rel_l2(out, ref) < 3e-3

@@ -192,7 +192,10 @@ def test_lora_forward_and_gradients(name, rank, tmp_path, cuda):
     assert not res.unexpected_keys and all(k.startswith("llm.") for k in res.missing_keys)
     model = model.to(cuda).eval()
     with torch.no_grad():
-        assert torch.equal(model(inputs), base(inputs))                       # (i) identity at init
+        # (i) identity at init: B = 0 makes the LoRA update exactly zero.  Not bit-identical to `base` only because
+        # the LoRA path rotates q/k with the separate RoPE kernel (on bf16 q/k, after the LoRA accumulate) while
+        # the plain path rotates the fp32 accumulators in the QKV epilogue: rounding-level difference.
+        assert _rel_l2(model(inputs), base(inputs)) < 1e-3
     with torch.no_grad():
         for b in model.llm.B:
             b.normal_(std=0.05)
