@@ -279,3 +279,61 @@ def test_training_with_dropout(tmp_path, cuda):
     model.eval()
     with torch.no_grad():
         assert torch.equal(model(inputs), model(inputs)) and model._last_dropout_seeds is None
+
+
+def test_edge_inputs_empty_prompt_2d_input_batch_of_one(tmp_path, cuda):
+    """Edge cases of the reference path: no prompt at all (models/medtsllm.py:338-339 -> [B, 0, D]), a 2-D univariate
+    window tensor (:264-265), and a batch of one."""
+    from medtsllm_b200.model import MedTsLLM
+    from oracle import medtsllm_oracle as O
+    from _fixtures import oracle_spec
+    fix = load_case("llama_semseg_univariate")
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["prompting"].update(dataset=False, task=False, clip=False, input_stats=False)
+    model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda).eval()
+    x = fix["inputs"]["x_enc"][:1]                                   # [1, T, 1]
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    ref = O.medtsllm_forward(x, [[]], fix["adapters"], sd, oracle_spec(fix))
+    with torch.no_grad():
+        out3 = model({"x_enc": x.to(cuda)})
+        out2 = model({"x_enc": x[:, :, 0].to(cuda)})                 # 2-D input -> unsqueeze
+    assert out3.shape == ref.shape and torch.equal(out2, out3)
+    assert _rel_l2(out3, ref) < 2e-2
+    # and it trains: one backward with an empty prompt
+    model.train()
+    out = model({"x_enc": x.to(cuda)})
+    out.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_long_sequence_falls_back_to_tiled_attention(cuda):
+    """L beyond the shared-memory-resident attention kernels (hd 128: L > ~350) takes the 64x64-tiled kernels
+    (forward and backward) and still matches the oracle's Llama restatement."""
+    from medtsllm_b200.backbone import BackboneSpec, KernelBackbone
+    from oracle import medtsllm_oracle as O
+    spec = BackboneSpec("llama", hidden=256, layers=1, heads=2, inter=256, vocab=64, eps=1e-5, max_pos=1024)
+    bb = KernelBackbone.random_init(spec, cuda, seed=5)
+    lay = bb.layers[0]
+    wqkv = lay["wqkv"].float().cpu()
+    wgu = lay["wgu"].float().cpu().view(-1, 2, 128, 256)
+    sd = {"layers.0.self_attn.q_proj.weight": wqkv[:256], "layers.0.self_attn.k_proj.weight": wqkv[256:512],
+          "layers.0.self_attn.v_proj.weight": wqkv[512:], "layers.0.self_attn.o_proj.weight": lay["wo"].float().cpu(),
+          "layers.0.mlp.gate_proj.weight": wgu[:, 0].reshape(-1, 256)[:256],
+          "layers.0.mlp.up_proj.weight": wgu[:, 1].reshape(-1, 256)[:256],
+          "layers.0.mlp.down_proj.weight": lay["wdown"].float().cpu()[:, :256],
+          "layers.0.input_layernorm.weight": lay["ln1"].cpu(), "layers.0.post_attention_layernorm.weight": lay["ln2"].cpu(),
+          "norm.weight": bb.final_norm_w.cpu()}
+    Bp, L = 2, 420
+    x = torch.randn(Bp, L, 256, generator=torch.Generator().manual_seed(1))
+    xr = x.clone().requires_grad_(True)
+    ref = O.llama_forward(xr, sd, n_layers=1, n_heads=2, eps=1e-5)
+    stash = []
+    got, x_final = bb.forward(x.to(cuda).view(Bp * L, 256).contiguous(), Bp, L, stash=stash)
+    assert _rel_l2(got.float().cpu().view(Bp, L, 256), ref) < 1e-2
+    w = torch.randn(Bp, L, 256, generator=torch.Generator().manual_seed(2))
+    (ref * w).sum().backward()
+    dR, _ = bb.backward(w.to(cuda, torch.bfloat16).view(Bp * L, 256).contiguous(), x_final, stash, Bp, L)
+    assert _rel_l2(dR.cpu().view(Bp, L, 256), xr.grad) < 2e-2
