@@ -233,6 +233,13 @@ def run_ours(args):
         del opt
         torch.cuda.empty_cache()
 
+    # ---- HBM-bound kernels of the forward ("fwd HBM GB/s vs peak"): each timed alone with CUDA events on the
+    # launching stream over 20 back-to-back launches at this workload's shapes; algorithmic bytes per launch as
+    # stated in DESIGN.md section 3
+    hbm = None
+    if rank == 0:
+        hbm = hbm_kernels(model, w, dev)
+
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every mts_gemm launch,
     # recorded on the launching stream over instrumented steps of the same workload
     gemm_ms, gemm_flops = None, None
@@ -292,11 +299,51 @@ def run_ours(args):
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "gemm_ms_per_step": round(gemm_ms, 3), "gemm_share_of_step": round(gemm_ms / ms_step, 3),
                          "gemm_flops_per_step": gemm_flops, "algorithmic_fwd_flops": fl["total"]},
+            "hbm_roofline": hbm,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_kernels(model, w, dev):
+    from medtsllm_b200 import ops
+    peak = _peaks()["hbm_gbs"]
+    s = w.backbone
+    M, D = w.B * w.seq, s.hidden
+    x = torch.randn(M, D, device=dev)
+    wn = torch.ones(D, device=dev)
+    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    xe = torch.randn(w.B, w.T, w.C, device=dev)
+    wc = model.patch_embedding.value_embedding.tokenConv.weight.detach()
+    ids = torch.randint(3, s.vocab, (w.B, w.prompt_len), device=dev, dtype=torch.int32)
+    X = torch.empty(w.B, w.seq, D, device=dev)
+    bb = model._backbone
+    norm = (lambda: ops.rmsnorm(x, wn, 1e-5, out=out)) if s.kind == "llama" else (lambda: ops.layernorm(x, wn, wn, 1e-5, out=out))
+    cases = [
+        ("norm_rows_kernel", norm, M * D * 6.0),
+        ("prompt_gather_kernel", lambda: ops.prompt_gather(ids, bb.embed, bb.wpe, X, rep=1, Lp=w.prompt_len, L=w.seq),
+         w.B * w.prompt_len * D * 4.0 * (2 if bb.wpe is not None else 1) + w.B * w.seq * D * 4.0),
+        ("revin_patch_embed_kernel", lambda: ops.revin_patch_embed(xe, wc, 16, 8, concat=w.covariate_mode == "concat"),
+         w.B * w.T * w.C * 4.0 + w.B * w.C * w.n_patches * 32 * 2.0 + w.B * w.C * 8.0),
+    ]
+    res = []
+    for name, fn, nbytes in cases:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        res.append({"kernel": name, "bytes_per_launch": nbytes, "us_per_launch": round(us, 2),
+                    "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(nbytes / us / 1e3 / peak, 4)})
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
