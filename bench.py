@@ -333,10 +333,17 @@ def hbm_kernels(model, w, dev):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        # 20 launches captured in a CUDA graph and replayed: the events then bracket device time only (the
+        # smallest of these kernels runs for a few microseconds, less than one Python-side launch takes)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                fn()
+        graph.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20):
-            fn()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3

@@ -152,6 +152,10 @@ typedef struct mts_gemm_args {
   const float* rope_cos;
   const float* rope_sin;
   int32_t rope_L, rope_hd, rope_cols, reserved_;
+  /* MTS_EPI_SWIGLU only, optional: bf16 [m, ld_aux >= n] copy of the gate/up pre-activations (same packed   */
+  /* column order as the weight rows) kept for the backward; batch must be 1 when used                       */
+  void* aux;
+  int64_t ld_aux;
 } mts_gemm_args;
 
 int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);
@@ -238,11 +242,12 @@ int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t stream);
  * are mts_gemm on transposed operands; the kernels below are the rest.                           */
 
 /* dx (+)= d(RMSNorm)/dx^T (w*dy) and the LayerNorm analogue; x fp32 [rows, ldx], dy bf16 [rows, D],
- * dx fp32 [rows, D]; accumulate != 0 adds into dx (residual-stream gradient). */
+ * dx fp32 [rows, D]; accumulate != 0 adds into dx (residual-stream gradient).  dx_bf16 (optional, [rows, D]):
+ * bf16 copy of the updated dx = the A operand of the next dgrad GEMM (saves a separate cast pass). */
 int mts_rmsnorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy, float* dx,
-                    int rows, int D, float eps, int accumulate, mts_stream_t stream);
+                    uint16_t* dx_bf16, int rows, int D, float eps, int accumulate, mts_stream_t stream);
 int mts_layernorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy, float* dx,
-                      int rows, int D, float eps, int accumulate, mts_stream_t stream);
+                      uint16_t* dx_bf16, int rows, int D, float eps, int accumulate, mts_stream_t stream);
 
 /* Causal attention backward (ref: autograd of HF eager attention, HF:models/llama/modeling_llama.py:
  * 199-221).  qkv/out/lse as produced by mts_attn_causal; dout bf16 [Bp*L, H*hd]; delta fp32 [Bp,H,L]

@@ -31,8 +31,8 @@ __device__ __forceinline__ float bw_block_sum(float v, float* red) {
 template <bool kLayerNorm>
 __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
-                const __nv_bfloat16* __restrict__ dy, float* __restrict__ dx, int D, float eps,
-                int accumulate) {
+                const __nv_bfloat16* __restrict__ dy, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+                int D, float eps, int accumulate) {
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const float* xr = x + row * ldx;
@@ -89,6 +89,8 @@ norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restric
       out.x += prev.x; out.y += prev.y; out.z += prev.z; out.w += prev.w;
     }
     reinterpret_cast<float4*>(dxr)[i] = out;
+    if (dx_bf16)   // bf16 copy of the updated gradient: the A operand of the next dgrad GEMM
+      reinterpret_cast<uint2*>(dx_bf16 + row * D)[i] = make_uint2(pack_bf16(out.x, out.y), pack_bf16(out.z, out.w));
   }
 }
 
@@ -314,7 +316,7 @@ static int bw_grid(int64_t n, int per_block) {
 using namespace mts;
 
 static int norm_bwd_common(bool ln, const float* x, int64_t ldx, const float* w, const uint16_t* dy,
-                           float* dx, int rows, int D, float eps, int accumulate, mts_stream_t s) {
+                           float* dx, uint16_t* dx_bf16, int rows, int D, float eps, int accumulate, mts_stream_t s) {
   const char* name = ln ? "mts_layernorm_bwd" : "mts_rmsnorm_bwd";
   if (!x || !w || !dy || !dx || rows < 0 || D <= 0 || (D % 4) || (ldx % 4) || ldx < D)
     return set_error(MTS_ERR_INVALID_ARG, "%s: bad args", name);
@@ -324,21 +326,25 @@ static int norm_bwd_common(bool ln, const float* x, int64_t ldx, const float* w,
   if (rows == 0) return MTS_OK;
   if (ln)
     norm_bwd_kernel<true><<<rows, 256, 0, (cudaStream_t)s>>>(
-        x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, D, eps, accumulate);
+        x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), D, eps,
+        accumulate);
   else
     norm_bwd_kernel<false><<<rows, 256, 0, (cudaStream_t)s>>>(
-        x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, D, eps, accumulate);
+        x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), D, eps,
+        accumulate);
   count_launch();
   return check_launch(name);
 }
 
 extern "C" int mts_rmsnorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy,
-                               float* dx, int rows, int D, float eps, int accumulate, mts_stream_t s) {
-  return norm_bwd_common(false, x, ldx, w, dy, dx, rows, D, eps, accumulate, s);
+                               float* dx, uint16_t* dx_bf16, int rows, int D, float eps, int accumulate,
+                               mts_stream_t s) {
+  return norm_bwd_common(false, x, ldx, w, dy, dx, dx_bf16, rows, D, eps, accumulate, s);
 }
 extern "C" int mts_layernorm_bwd(const float* x, int64_t ldx, const float* w, const uint16_t* dy,
-                                 float* dx, int rows, int D, float eps, int accumulate, mts_stream_t s) {
-  return norm_bwd_common(true, x, ldx, w, dy, dx, rows, D, eps, accumulate, s);
+                                 float* dx, uint16_t* dx_bf16, int rows, int D, float eps, int accumulate,
+                                 mts_stream_t s) {
+  return norm_bwd_common(true, x, ldx, w, dy, dx, dx_bf16, rows, D, eps, accumulate, s);
 }
 
 extern "C" int mts_swiglu_blk(const uint16_t* gu, int64_t ld, uint16_t* y, int64_t rows, int I, int blk,

@@ -26,6 +26,10 @@ struct GemmParams {
   const float* rope_cos;
   const float* rope_sin;
   int rope_L, rope_hd, rope_cols;
+  // SWIGLU: optional bf16 copy of the gate/up pre-activations (packed column order, row stride ld_aux) that the
+  // training path keeps for the backward
+  __nv_bfloat16* aux;
+  int64_t ld_aux;
 };
 
 __device__ __forceinline__ float gelu_new_f(float x) {
@@ -145,9 +149,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           tmem_ld_32x32(taddr + BN / 2 + ci * 32, u);
           tmem_ld_wait();
           col0 = n_blk * (BN / 2) + ci * 32;
+          if (p.aux != nullptr && row < p.m && n_blk * BN + ci * 32 < p.n) {
+            // pre-activations for the backward: 64 contiguous bytes per thread and half (16-byte stores)
+            __nv_bfloat16* ag = p.aux + (int64_t)b * p.m * p.ld_aux + (int64_t)row * p.ld_aux + n_blk * BN + ci * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = silu_f(__uint_as_float(g[j]) * p.alpha) * (__uint_as_float(u[j]) * p.alpha);
+            for (int j = 0; j < 32; j += 8) {
+              *reinterpret_cast<uint4*>(ag + j) = make_uint4(
+                  pack_bf16(__uint_as_float(g[j]) * p.alpha, __uint_as_float(g[j + 1]) * p.alpha),
+                  pack_bf16(__uint_as_float(g[j + 2]) * p.alpha, __uint_as_float(g[j + 3]) * p.alpha),
+                  pack_bf16(__uint_as_float(g[j + 4]) * p.alpha, __uint_as_float(g[j + 5]) * p.alpha),
+                  pack_bf16(__uint_as_float(g[j + 6]) * p.alpha, __uint_as_float(g[j + 7]) * p.alpha));
+              *reinterpret_cast<uint4*>(ag + BN / 2 + j) = make_uint4(
+                  pack_bf16(__uint_as_float(u[j]) * p.alpha, __uint_as_float(u[j + 1]) * p.alpha),
+                  pack_bf16(__uint_as_float(u[j + 2]) * p.alpha, __uint_as_float(u[j + 3]) * p.alpha),
+                  pack_bf16(__uint_as_float(u[j + 4]) * p.alpha, __uint_as_float(u[j + 5]) * p.alpha),
+                  pack_bf16(__uint_as_float(u[j + 6]) * p.alpha, __uint_as_float(u[j + 7]) * p.alpha));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // the activation is computed from the bf16-rounded pre-activations when they are kept, so that the
+            // saved tensors reproduce exactly what the forward used
+            float gv = __uint_as_float(g[j]) * p.alpha, uv = __uint_as_float(u[j]) * p.alpha;
+            if (p.aux != nullptr) { gv = __bfloat162float(__float2bfloat16_rn(gv)); uv = __bfloat162float(__float2bfloat16_rn(uv)); }
+            v[j] = silu_f(gv) * uv;
+          }
         } else {
           uint32_t r[32];
           tmem_ld_32x32(taddr + ci * 32, r);

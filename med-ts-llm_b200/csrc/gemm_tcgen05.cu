@@ -336,6 +336,13 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.alpha = a->alpha;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
   p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols;
+  p.aux = nullptr; p.ld_aux = 0;
+  if (a->aux) {
+    if (a->epilogue != MTS_EPI_SWIGLU || a->batch != 1 || a->ld_aux < a->n || (a->ld_aux % 8) ||
+        (reinterpret_cast<uintptr_t>(a->aux) & 15))
+      return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: aux needs the SWIGLU epilogue, batch 1, ld_aux >= n, 16-byte rows");
+    p.aux = static_cast<__nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
+  }
 
   if (bn == 256 && !a->d_transposed && gemm_2cta_enabled()) {
     // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("d_transposed", C.c_int32), ("block_n", C.c_int32), ("alpha", C.c_float),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_L", C.c_int32), ("rope_hd", C.c_int32), ("rope_cols", C.c_int32), ("reserved_", C.c_int32),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64),
     ]
 
 
@@ -57,8 +58,8 @@ SIGNATURES = {
     "mts_dropout": [_p, _p, _i, _i64, _f, C.c_uint64, _p],
     "mts_sigmoid": [_p, _i64, _p],
     "mts_softmax_lastdim": [_p, _i64, _i, _p],
-    "mts_rmsnorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
-    "mts_layernorm_bwd": [_p, _i64, _p, _p, _p, _i, _i, _f, _i, _p],
+    "mts_rmsnorm_bwd": [_p, _i64, _p, _p, _p, _p, _i, _i, _f, _i, _p],
+    "mts_layernorm_bwd": [_p, _i64, _p, _p, _p, _p, _i, _i, _f, _i, _p],
     "mts_attn_causal_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p],
     "mts_rope_qk": [_p, _p, _p, _i, _i, _i, _i, _p],
     "mts_swiglu_blk": [_p, _i64, _p, _i64, _i, _i, _p],

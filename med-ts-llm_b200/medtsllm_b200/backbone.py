@@ -283,10 +283,10 @@ class KernelBackbone:
                 h = bf(M, D)
             if llama:
                 ops.rmsnorm(x_mid, lay["ln2"], s.eps, out=h)
-                if train:   # keep the gate/up pre-activations (packed column order) for the backward
+                if train:   # the SwiGLU epilogue also keeps the gate/up pre-activations (packed column order)
                     pre = bf(M, 2 * self.i_pad)
-                    ops.gemm(h, lay["wgu"], pre, m=M, n=2 * self.i_pad, k=D, block_n=256)
-                    act = ops.swiglu_blk(pre, self.i_pad, 128)
+                    act = bf(M, self.i_pad)
+                    ops.gemm(h, lay["wgu"], act, m=M, n=2 * self.i_pad, k=D, epilogue=EPI_SWIGLU, block_n=256, aux=pre)
                 else:
                     pre = None
                     act = bf(M, self.i_pad)
@@ -331,12 +331,11 @@ class KernelBackbone:
         norm_bwd = ops.rmsnorm_bwd if llama else ops.layernorm_bwd
         bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
         dR = torch.empty(M, D, device=dev, dtype=torch.float32)
-        norm_bwd(x_final, self.final_norm_w, dhid, dR, s.eps, accumulate=False)
-        dRb, dH = bf(M, D), bf(M, D)
+        dRb, dH = bf(M, D), bf(M, D)       # dRb: bf16 copy of dR, refreshed by every norm backward
+        norm_bwd(x_final, self.final_norm_w, dhid, dR, s.eps, accumulate=False, dx_bf16=dRb)
         lora_grads = [None] * len(lora.params()) if lora is not None else None
         for li, lay, st in zip(reversed(range(len(self.layers))), reversed(self.layers), reversed(stash)):
             # --- MLP half: x_out = x_mid + W2 act(W1 norm(x_mid))
-            ops.cast_bf16(dR, out=dRb)
             if llama:
                 dact = bf(M, self.i_pad)
                 ops.gemm(dRb, lay["wdown_t"], dact, m=M, n=self.i_pad, k=D)
@@ -347,9 +346,8 @@ class KernelBackbone:
                 ops.gemm(dRb, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
                 dpre = ops.gelu_new(st["pre"], dact)
                 ops.gemm(dpre, lay["wfc_t"], dH, m=M, n=D, k=s.inter)
-            norm_bwd(st["x_mid"], lay["ln2"], dH, dR, s.eps, accumulate=True)
+            norm_bwd(st["x_mid"], lay["ln2"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
             # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
-            ops.cast_bf16(dR, out=dRb)
             datt = bf(M, D)
             ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
             dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
@@ -361,7 +359,7 @@ class KernelBackbone:
                 for t in range(len(lora.targets)):
                     lora_grads[lora.index(li, t)] = dAs[t]
                     lora_grads[nA + lora.index(li, t)] = dBs[t]
-            norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True)
+            norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
         return dR, lora_grads
 
     def flops_per_token_fwd(self, L: int) -> float:

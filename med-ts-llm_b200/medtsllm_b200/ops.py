@@ -42,7 +42,8 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
-         block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0):
+         block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0,
+         aux=None):
     """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
     if d.dtype not in (torch.bfloat16, torch.float32):
@@ -70,6 +71,9 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     if rope is not None:
         args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
         args.rope_L, args.rope_hd, args.rope_cols = rope_L, rope_hd, rope_cols
+    if aux is not None:
+        _chk(aux, torch.bfloat16, "aux")
+        args.aux, args.ld_aux = aux.data_ptr(), aux.shape[-1]
     _lib.call("mts_gemm", C.byref(args), _stream())
     return d
 
@@ -297,19 +301,19 @@ def _dt(t):
     return MTS_F32 if t.dtype == torch.float32 else MTS_BF16
 
 
-def rmsnorm_bwd(x, w, dy, dx, eps, accumulate=True):
-    """dx (+)= J_rmsnorm(x)^T (w*dy); x fp32 [rows,D], dy bf16, dx fp32."""
+def rmsnorm_bwd(x, w, dy, dx, eps, accumulate=True, dx_bf16=None):
+    """dx (+)= J_rmsnorm(x)^T (w*dy); x fp32 [rows,D], dy bf16, dx fp32; dx_bf16: optional bf16 copy of the result."""
     _chk(x, torch.float32, "x"); _chk(dy, torch.bfloat16, "dy"); _chk(dx, torch.float32, "dx")
     D = x.shape[-1]
-    _lib.call("mts_rmsnorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+    _lib.call("mts_rmsnorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(), _ptr(dx_bf16),
               x.numel() // D, D, eps, 1 if accumulate else 0, _stream())
     return dx
 
 
-def layernorm_bwd(x, w, dy, dx, eps, accumulate=True):
+def layernorm_bwd(x, w, dy, dx, eps, accumulate=True, dx_bf16=None):
     _chk(x, torch.float32, "x"); _chk(dy, torch.bfloat16, "dy"); _chk(dx, torch.float32, "dx")
     D = x.shape[-1]
-    _lib.call("mts_layernorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+    _lib.call("mts_layernorm_bwd", x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(), _ptr(dx_bf16),
               x.numel() // D, D, eps, 1 if accumulate else 0, _stream())
     return dx
 

@@ -498,3 +498,26 @@ def test_gemm_rope_epilogue(ops, cuda, Bp, L, H, hd, pair):
     ref = torch.cat([qk * cos + rot * sin, ref[:, :, 2:]], dim=2).reshape(M, 3 * D)
     torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=2e-2)
     assert _rel_l2(out, ref) < 3e-3
+
+
+def test_swiglu_epilogue_keeps_preactivations_and_norm_bwd_bf16_copy(ops, cuda):
+    g = torch.Generator().manual_seed(71)
+    m, I, k = 300, 256, 192
+    x = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    wg = (torch.randn(I, k, generator=g) * 0.1).to(cuda, torch.bfloat16)
+    wu = (torch.randn(I, k, generator=g) * 0.1).to(cuda, torch.bfloat16)
+    packed = ops.pack_gate_up(wg, wu)
+    act = torch.empty(m, I, device=cuda, dtype=torch.bfloat16)
+    pre = torch.full((m, 2 * I), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.gemm(x, packed, act, m=m, n=2 * I, k=k, epilogue=3, aux=pre)
+    plain = torch.empty(m, 2 * I, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(x, packed, plain, m=m, n=2 * I, k=k, block_n=256)
+    assert torch.equal(pre, plain)                                    # same bf16 pre-activations as a plain GEMM
+    assert torch.equal(act, ops.swiglu_blk(plain, I, 128))            # and the activation computed from them
+    # norm backward emitting the bf16 copy of the accumulated gradient
+    rows, D = 40, 512
+    xx = torch.randn(rows, D, generator=g).to(cuda); w = torch.randn(D, generator=g).to(cuda)
+    dy = torch.randn(rows, D, generator=g).to(cuda, torch.bfloat16)
+    dx = torch.randn(rows, D, generator=g).to(cuda); dxb = torch.empty(rows, D, device=cuda, dtype=torch.bfloat16)
+    ops.rmsnorm_bwd(xx, w, dy, dx, 1e-5, accumulate=True, dx_bf16=dxb)
+    assert torch.equal(dxb, dx.to(torch.bfloat16))
