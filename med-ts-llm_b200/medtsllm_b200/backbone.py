@@ -16,13 +16,12 @@ adds promote to fp32); GEMM operands are bf16, accumulation fp32 in TMEM.
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 
 from . import ops
-from ._lib import BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_ROPE_QK, EPI_STORE, EPI_SWIGLU, MtsError
+from ._lib import BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_ROPE_QK, EPI_SWIGLU, MtsError
 
 
 @dataclass
@@ -74,10 +73,9 @@ class KernelBackbone:
     """Device-resident frozen decoder stack.  Not an nn.Module on purpose: `.to(dtype)` from the
     Trainer (tasks/base.py:41) must not re-cast the bf16 kernel weights."""
 
-    def __init__(self, spec: BackboneSpec, device, keep_transposed: bool = False):
+    def __init__(self, spec: BackboneSpec, device):
         self.spec = spec
         self.device = torch.device(device)
-        self.keep_transposed = keep_transposed
         self.layers: list[dict] = []
         self.final_norm_w = None
         self.final_norm_b = None
@@ -136,11 +134,11 @@ class KernelBackbone:
         self.layers.append(lay)
 
     @classmethod
-    def from_hf(cls, hf_model, device, keep_transposed=False) -> "KernelBackbone":
+    def from_hf(cls, hf_model, device) -> "KernelBackbone":
         """Converts a HuggingFace LlamaModel / GPT2Model (as loaded by the reference's setup_llm,
         models/medtsllm.py:175-185) layer by layer."""
         spec = spec_from_hf_config(hf_model.config)
-        self = cls(spec, device, keep_transposed)
+        self = cls(spec, device)
         sd = hf_model.state_dict()
         if spec.kind == "llama":
             for i in range(spec.layers):
@@ -168,10 +166,10 @@ class KernelBackbone:
         return self
 
     @classmethod
-    def random_init(cls, spec: BackboneSpec, device, seed=0, keep_transposed=False, std=0.02):
+    def random_init(cls, spec: BackboneSpec, device, seed=0, std=0.02):
         """Seeded random-init stack generated directly on the device (no checkpoints exist offline;
         HF `initializer_range` = 0.02, norms = 1, biases = 0)."""
-        self = cls(spec, device, keep_transposed)
+        self = cls(spec, device)
         g = torch.Generator(device=self.device).manual_seed(seed)
         D, I = spec.hidden, spec.inter
 
@@ -221,7 +219,6 @@ class KernelBackbone:
             else:
                 lay["wfc_t"] = ops.transpose_to_bf16(lay["wfc"])     # [D, I]
                 lay["wproj_t"] = ops.transpose_to_bf16(lay["wproj"])  # [I, D]
-        self.keep_transposed = True
 
     def embed_bf16(self):
         """bf16 [V, D] copy of the embedding table (B operand of dW_map = dSource E^T)."""

@@ -269,7 +269,7 @@ class MedTsLLM(nn.Module):
         dev = self.mapping_layer.weight.device
         if dev.type == "cuda":
             if self._backbone is None:
-                self._backbone = KernelBackbone.from_hf(self._hf_model, dev, keep_transposed=False)
+                self._backbone = KernelBackbone.from_hf(self._hf_model, dev)
                 object.__setattr__(self, "_hf_model", None)
             elif self._backbone.device != dev:
                 raise MtsError("the kernel backbone lives on another device")

@@ -11,8 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (BIAS_M, BIAS_N, BIAS_NONE, EPI_GELU_NEW, EPI_RESID_ADD, EPI_ROPE_QK, EPI_STORE, EPI_SWIGLU,
-                   MTS_BF16, MTS_F32, GemmArgs, MtsError)
+from ._lib import BIAS_N, BIAS_NONE, EPI_STORE, EPI_SWIGLU, MTS_BF16, MTS_F32, GemmArgs, MtsError
 
 __all__ = [
     "gemm", "linear_bf16", "revin_patch_embed", "patch_gather", "revin_patch_embed_bwd",

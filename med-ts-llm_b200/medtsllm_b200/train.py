@@ -19,7 +19,7 @@ from __future__ import annotations
 import torch
 
 from . import dp, ops
-from ._lib import BIAS_NONE, EPI_RESID_ADD, MtsError
+from ._lib import EPI_RESID_ADD
 
 
 def forward_train(model, inputs):

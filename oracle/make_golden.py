@@ -8,7 +8,6 @@ Nothing at test time needs /root/reference.
 """
 from __future__ import annotations
 
-import json
 import zlib
 import shutil
 import sys

@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import contextlib
 import importlib
-import json
 import sys
 import types
 from pathlib import Path
