@@ -4,9 +4,13 @@ unmodified reference (tests/golden/*.pt).
 
 Tolerance (stated, per SURVEY.md §7 "hard parts"): the kernels compute GEMM operands in bf16 with
 fp32 accumulation and an fp32 residual stream — the reference's own GPU regime under bf16 autocast
-(tasks/forecasting.py:22) — while oracle/goldens are fp32.  Metric: relative L2 per stage.
+(tasks/forecasting.py:22) — while oracle/goldens are fp32.  Metric: relative L2.
   front end (fp32 math, bf16 store) ............ < 4e-3
-  reprogramming / backbone hidden / final ...... < 2e-2   (bf16 operand rounding through 5-9 GEMMs)
+  intermediate stages (pre-activation) ......... < 1e-2   (measured 0.7e-3 .. 4.9e-3)
+  final output ................................. < 3e-3   (measured 2.8e-4 .. 1.5e-3)
+Yardstick (oracle/yardstick.py, run on the unmodified reference): the reference's OWN bf16-autocast forward
+differs from its fp32 forward by 0.8e-3 .. 2.2e-3 on these cases, i.e. the kernel path sits inside the
+reference's own mixed-precision noise.  north_star's 1e-3 is met by 9 of the 11 cases and missed by at most 1.5x.
 The fixtures' backbone weights are bf16-representable, so weight rounding is not in this budget.
 """
 import pytest
@@ -64,10 +68,10 @@ def test_forward_parity(name, tmp_path, cuda):
     for key in ("source_embeddings", "llm_input", "llm", "output_projection"):
         e_o = _rel_l2(cap[key].float().view(st[key].shape), st[key])
         e_g = _rel_l2(cap[key].float().view(g[key].shape), g[key])
-        assert e_o < 2e-2 and e_g < 2e-2, (name, key, e_o, e_g)
+        assert e_o < 1e-2 and e_g < 1e-2, (name, key, e_o, e_g)
     e_out = _rel_l2(out, g["output"])
-    assert e_out < 2e-2, (name, e_out)
-    assert _rel_l2(out, ref_out) < 2e-2
+    assert e_out < 3e-3, (name, e_out)
+    assert _rel_l2(out, ref_out) < 3e-3
     # determinism: same inputs -> bit-identical output (no atomics on the forward path)
     with torch.no_grad():
         out2 = model(inputs)
@@ -76,7 +80,7 @@ def test_forward_parity(name, tmp_path, cuda):
     model.train()
     with torch.no_grad():
         out_t = model(inputs)
-    assert _rel_l2(out_t, g["output_train"]) < 2e-2
+    assert _rel_l2(out_t, g["output_train"]) < 1e-2       # pre-activation (logits) in train mode
     print(f"\n[parity] {name}: rel-L2 output {e_out:.2e}  " +
           "  ".join(f"{k} {_rel_l2(cap[k].float().view(g[k].shape), g[k]):.1e}" for k in
                     ("source_embeddings", "llm_input", "llm", "output_projection")))
