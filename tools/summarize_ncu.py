@@ -42,7 +42,8 @@ out.append(f"| **total** | {sum(a[0] for a in agg.values())} | {total / 1e3:.3f}
 (REPO / "profiles").mkdir(exist_ok=True)
 (REPO / "profiles" / f"{tag}_launches.md").write_text("\n".join(out) + "\n")
 gemm_bytes = sum(a[2] for k, a in agg.items() if k.startswith("gemm_bf16_nt"))
-(REPO / "profiles" / "gemm_traffic.json").write_text(json.dumps(
+if "train" not in tag:   # bench.py's roofline.traffic is the FORWARD step's GEMM traffic
+  (REPO / "profiles" / "gemm_traffic.json").write_text(json.dumps(
     {"dram_bytes_per_step": gemm_bytes, "source": f"profiles/{tag}_launches.md (ncu dram__bytes_read.sum + dram__bytes_write.sum "
      "summed over every gemm_bf16_nt_* launch of one forward step)"}, indent=1) + "\n")
 print("\n".join(out))
