@@ -164,6 +164,11 @@ def run_ours(args):
             out_host.copy_(y, non_blocking=True)                  # D2H of the predictions
         torch.cuda.current_stream().synchronize()
 
+    if args.per_sample_prompts:
+        model.share_prompt_prefix = False
+    ids_tab = model.prompt_token_ids(resident)
+    Lc = model._shared_prefix_len(ids_tab, w.B, w.seq)      # prompt positions computed once per batch (0 = off)
+    rows_per_step = Lc + w.B * (w.seq - Lc)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     if args.profile_step:
@@ -199,6 +204,21 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
 
+    # ---- the same forward with every sample's prompt rows computed separately (the reference's own row count:
+    # B*L rows through the backbone instead of Lc + B*(L-Lc)); outputs are bit-identical (tests/test_model_gpu.py)
+    plain = None
+    if Lc > 0:
+        model.share_prompt_prefix = False
+        n_pl = max(3, args.steps // 2)
+        for _ in range(2):
+            step_resident()
+        ms_pl = timed(step_resident, n_pl) / n_pl
+        ms_pl_e2e = timed(step_e2e, n_pl) / n_pl
+        plain = {"value": round(world * w.B / (ms_pl * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms_pl, 3),
+                 "e2e": round(world * w.B / (ms_pl_e2e * 1e-3), 2), "steps": n_pl, "backbone_rows_per_step": w.B * w.seq,
+                 "what": "share_prompt_prefix=False: every sample carries its own copy of the prompt rows"}
+        model.share_prompt_prefix = True
+
     # ---- training step (same workload): forward with activation stash + backward through the frozen
     # backbone to all 15 adapter tensors + (N>1) gradient all-reduce + Adam step + loss read-back, through
     # the public API exactly like the reference Trainer loop (tasks/forecasting.py:19-30)
@@ -228,6 +248,13 @@ def run_ours(args):
                  "steps": n_tr, "gpu_launches_per_step": int((_lib.launch_count() - n1) // n_tr),
                  "what": "fwd + bwd (dgrad through all frozen blocks, 15 adapter grads) + Adam step + loss.item(), "
                          "host windows/labels copied in every step; dropout 0"}
+        if Lc > 0:
+            model.share_prompt_prefix = False
+            for _ in range(2):
+                step_train()
+            ms_tp = timed(step_train, n_tr) / n_tr
+            train["per_sample_prompts"] = {"value": round(world * w.B / (ms_tp * 1e-3), 2), "ms_per_step": round(ms_tp, 3)}
+            model.share_prompt_prefix = True
         model.eval()
         opt.zero_grad(set_to_none=True)
         del opt
@@ -275,6 +302,11 @@ def run_ours(args):
         if tf.exists():
             traffic = json.loads(tf.read_text()).get("dram_bytes_per_step")
         cpu = cpu_baseline(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+        ref_gpu = None
+        if world == 1 and not args.no_ref_gpu:
+            del model, backbone
+            torch.cuda.empty_cache()
+            ref_gpu = hf_gpu_backbone(w, dev)
         Lp = w.prompt_len
         line = {
             "metric": METRIC, "value": round(world * w.B / (ms_step * 1e-3), 2), "unit": "samples/s",
@@ -284,6 +316,11 @@ def run_ours(args):
                                    f"x{w.backbone.layers} layers random-init, B={w.B}/GPU T={w.T} C={w.C} "
                                    f"patches={w.n_patches} prompt={Lp} tokens (L={w.seq})",
                        "per_gpu_batch": w.B, "seq_len": w.T, "n_vars": w.C, "tokens_per_step": w.B * w.seq,
+                       "backbone_rows_per_step": rows_per_step, "shared_prompt_prefix": Lc,
+                       "prompt_sharing": (f"the {Lc} prompt positions that are identical in all {w.B} samples of a batch are "
+                                          f"computed once per batch ({rows_per_step} backbone rows instead of {w.B * w.seq}); "
+                                          "outputs bit-identical to per-sample prompts, which 'per_sample_prompts' times")
+                                         if Lc else "off",
                        "l2_policy": f"inputs larger than L2: {weight_gb:.1f} GB of weights streamed per step",
                        "parallelism": f"dp{world} (batch sharded, frozen backbone replicated, no forward collective)",
                        "build_s": round(t_build, 1)},
@@ -291,6 +328,7 @@ def run_ours(args):
             "e2e": {"value": round(world * w.B / (ms_e2e * 1e-3), 2), "unit": "samples/s",
                     "h2d_bytes_per_step": host["x_enc"].numel() * 4 + w.B * Lp * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e, 3)},
+            "per_sample_prompts": plain,
             "train_step": train,
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_nt_2cta_kernel / gemm_bf16_nt_kernel (tcgen05 cta_group::2 / ::1)", "achieved": round(achieved, 1),
@@ -301,10 +339,65 @@ def run_ours(args):
                          "gemm_flops_per_step": gemm_flops, "algorithmic_fwd_flops": fl["total"]},
             "hbm_roofline": hbm,
             "cpu_baseline": cpu,
+            "ref_gpu_backbone": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hf_gpu_backbone(w, dev, steps: int = 3):
+    """The reference's own backbone call on this GPU: HuggingFace `transformers` (the reference's third-party
+    backbone, models/medtsllm.py:175-185) with eager attention (:159-160), fp32 weights (`setup.dtype = mixed`,
+    :154), `output_hidden_states=True` (:147) and the default KV cache, on inputs_embeds of this workload's
+    [B, L, D] — (a) as the reference Trainer evaluates (no autocast, TF32 allowed: tasks/base.py:20-22) and (b)
+    under bf16 autocast (its training regime, tasks/forecasting.py:22).  Backbone only: >= 96 % of the
+    reference path's FLOPs, so these are UPPER bounds on the reference GPU path's samples/s.  Third-party
+    library code only; nothing of ours and nothing of oracle/ runs here."""
+    try:
+        import transformers
+        s = w.backbone
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.set_float32_matmul_precision("medium")
+        if s.kind == "llama":
+            cfg = transformers.LlamaConfig(hidden_size=s.hidden, intermediate_size=s.inter, num_hidden_layers=s.layers,
+                                           num_attention_heads=s.heads, num_key_value_heads=s.heads, vocab_size=s.vocab,
+                                           rms_norm_eps=s.eps, max_position_embeddings=s.max_pos)
+            cls = transformers.LlamaModel
+        else:
+            cfg = transformers.GPT2Config(n_embd=s.hidden, n_layer=s.layers, n_head=s.heads, vocab_size=s.vocab,
+                                          n_positions=s.max_pos)
+            cls = transformers.GPT2Model
+        cfg.output_hidden_states = True
+        cfg._attn_implementation = "eager"
+        with torch.device(dev):
+            hf = cls(cfg)
+        hf = hf.to(dev, torch.float32).eval()
+        x = torch.randn(w.B, w.seq, s.hidden, device=dev)
+        res = {}
+        for name, autocast in (("eval_tf32", False), ("autocast_bf16", True)):
+            def step():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return hf(inputs_embeds=x).last_hidden_state
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"value": round(w.B / (ms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms, 3)}
+        res["what"] = (f"transformers {transformers.__version__} {cls.__name__} (eager attention, fp32 weights, "
+                       f"output_hidden_states, KV cache) forward on inputs_embeds [{w.B}, {w.seq}, {s.hidden}], {steps} timed "
+                       "steps after 1 warm-up; backbone only = upper bound on the reference GPU path")
+        del hf
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # the baseline is informative only; never fail the bench line over it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 def hbm_kernels(model, w, dev):
@@ -467,6 +560,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the HuggingFace-on-GPU backbone baseline")
+    ap.add_argument("--per-sample-prompts", action="store_true",
+                    help="disable the shared prompt prefix for the whole run (every sample carries its own prompt rows)")
     ap.add_argument("--profile-step", nargs="?", const="fwd", default=None, choices=["fwd", "train"],
                     help="run one profiled step (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()

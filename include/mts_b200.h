@@ -128,7 +128,8 @@ typedef enum mts_epilogue {
                          /* by the matching 128 up rows (HF:models/llama/modeling_llama.py:182-184) */
   MTS_EPI_ROPE_QK = 4    /* fused qkv projection with rotate-half RoPE applied (in fp32, from the   */
                          /* accumulators) to output columns < rope_cols; D bf16; head dim 64 / 128, */
-                         /* position = row % rope_L (HF:models/llama/modeling_llama.py:139-168)     */
+                         /* position = row % rope_L (HF:models/llama/modeling_llama.py:139-168);    */
+                         /* see rope_prefix for the shared-prefix row layout                         */
 } mts_epilogue;
 
 typedef enum mts_bias_axis { MTS_BIAS_NONE = 0, MTS_BIAS_N = 1, MTS_BIAS_M = 2 } mts_bias_axis;
@@ -151,7 +152,8 @@ typedef struct mts_gemm_args {
   /* MTS_EPI_ROPE_QK only: fp32 tables [>= rope_L, rope_hd/2], sequence length, head dim, #rotated columns */
   const float* rope_cos;
   const float* rope_sin;
-  int32_t rope_L, rope_hd, rope_cols, reserved_;
+  int32_t rope_L, rope_hd, rope_cols;
+  int32_t rope_prefix; /* shared-prefix row layout: position = row (row < rope_prefix), else rope_prefix + (row - rope_prefix) % rope_L */
   /* MTS_EPI_SWIGLU only, optional: bf16 [m, ld_aux >= n] copy of the gate/up pre-activations (same packed   */
   /* column order as the weight rows) kept for the backward; batch must be 1 when used                       */
   void* aux;
@@ -202,6 +204,28 @@ int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rop
 int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int L, int H,
                 int hd, mts_stream_t stream);
 
+/* Shared-prefix row layout (in-batch prompt de-duplication).  The reference embeds the same dataset / task
+ * prompt in front of every sample (models/medtsllm.py:386-439, :330-339) and, the backbone mask being causal
+ * with no padding mask (:350), the states of those Lc leading positions are identical for all samples at every
+ * layer.  They are therefore kept ONCE: rows [0, Lc) = the shared prefix (positions 0..Lc-1), rows
+ * Lc + b*Ls + t = token t of sample b at position Lc + t (Ls = L - Lc own tokens per sample, Bp samples,
+ * Lc + Bp*Ls rows in total).  Every row-wise kernel and GEMM works on that layout unchanged (see
+ * mts_gemm_args.rope_prefix); only attention needs to know about it:
+ *   qkv bf16 [Lc + Bp*Ls, 3*H*hd] with q / k ALREADY rotated (MTS_EPI_ROPE_QK or mts_rope_qk_shared);
+ *   out bf16 [Lc + Bp*Ls, H*hd];  lse fp32 [H*Lc + Bp*H*Ls] (prefix [H, Lc] first, then [Bp, H, Ls]) or NULL.
+ * All Lc + Ls positions of one head must fit in shared memory (<= ~350 positions at hd 128, ~700 at hd 64). */
+int mts_attn_causal_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
+                           int hd, float scale, mts_stream_t stream);
+/* Backward for the samples' own tokens only (the prefix has no trainable ancestor when the backbone is frozen):
+ * qkv as above (all rows); out_own / dout_own bf16 [Bp*Ls, H*hd], lse_own / delta fp32 [Bp, H, Ls],
+ * dqkv_own bf16 [Bp*Ls, 3*H*hd] = the rows from Lc on.  rope tables fp32 [>= Lc+Ls, hd/2] (rotate dq/dk back) or NULL. */
+int mts_attn_causal_shared_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                               const uint16_t* out_own, const uint16_t* dout_own, const float* lse_own,
+                               float* delta, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
+                               float scale, mts_stream_t stream);
+int mts_rope_qk_shared(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int Lc, int Ls,
+                       int H, int hd, mts_stream_t stream);
+
 /* row softmax with scale: p = softmax(scale * s) over the last axis.
  *   s fp32 [rows, n], p bf16 [rows, n]   (ref: models/medtsllm.py:587, reprogramming scores) */
 int mts_softmax_rows(const float* s, uint16_t* p, int64_t rows, int n, float scale,
@@ -217,6 +241,11 @@ int mts_softmax_rows(const float* s, uint16_t* p, int64_t rows, int n, float sca
  *        sample b is written to rows b*rep .. b*rep+rep-1 (repeat_interleave, :343-344). */
 int mts_prompt_gather(const int32_t* ids, const float* emb, const float* wpe, float* x, int B,
                       int rep, int Lp, int L, int D, mts_stream_t stream);
+/* Same, shared-prefix row layout: the first Lc (<= Lp) prompt tokens are identical in every row of `ids`
+ * (host-checked) and are written once to x rows [0, Lc); sample b, replica r owns rows
+ * Lc + (b*rep + r)*(L-Lc) + [0, L-Lc).  x fp32 [Lc + B*rep*(L-Lc), D]. */
+int mts_prompt_gather_shared(const int32_t* ids, const float* emb, const float* wpe, float* x, int B,
+                             int rep, int Lp, int L, int Lc, int D, mts_stream_t stream);
 
 /* y = silu(g) * u on bf16, g/u being the two halves of a [rows, 2*I] (ld = ldgu) buffer laid out
  * [g | u];  (training path keeps g,u for the backward; ref HF llama :182-184) */

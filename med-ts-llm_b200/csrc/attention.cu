@@ -233,7 +233,7 @@ attn_causal_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
 // row index inside the sample).  16 bytes per access; bytes: 8*M*D read + written.
 // ---------------------------------------------------------------------------------------------
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cosb,
-                               const float* __restrict__ sinb, int64_t rows, int L, int H, int hd) {
+                               const float* __restrict__ sinb, int64_t rows, int L, int Lc, int H, int hd) {
   const int half = hd >> 1;
   const int vec_per_head = half >> 3;                 // 8 column pairs per item
   const int64_t per_row = (int64_t)2 * H * vec_per_head;  // q heads then k heads
@@ -245,7 +245,7 @@ __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __r
     const int rem = (int)(idx - row * per_row);
     const int head = rem / vec_per_head;              // 0..2H-1 (>= H: key heads)
     const int j = (rem - head * vec_per_head) * 8;
-    const int pos = (int)(row % L);
+    const int pos = row < Lc ? (int)row : Lc + (int)((row - Lc) % L);   // Lc: shared-prefix rows (0 = plain layout)
     __nv_bfloat16* base = qkv + row * 3 * D + (int64_t)head * hd;  // k section follows q contiguously
     const uint4 a = *reinterpret_cast<const uint4*>(base + j);
     const uint4 b = *reinterpret_cast<const uint4*>(base + half + j);
@@ -284,7 +284,10 @@ constexpr int kSeqThreads = 256;
 template <int HD>
 __global__ void __launch_bounds__(kSeqThreads)
 attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                           float* __restrict__ lse, int L, int H, float scale_log2e) {
+                           float* __restrict__ lse, int L, int Lc, int H, float scale_log2e) {
+  // Shared-prefix layout (Lc > 0): rows [0, Lc) of qkv / out hold ONE copy of the prompt prefix every sample
+  // shares, rows Lc + b*Ls + t (Ls = L - Lc) the own tokens of sample b at positions Lc + t.  Keys are all L
+  // positions, queries only the sample's own Ls tokens.  Lc = 0 is the plain [Bp, L] layout.
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   const int Lp = (L + 63) & ~63;
@@ -297,9 +300,10 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   const int b = bh / H, h = bh - b * H;
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
-  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
-  const __nv_bfloat16* kbase = qbase + D;
-  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const int Ls = L - Lc;
+  // row of position p: p (shared prefix) or p + b*Ls (own tokens) -> two bases indexed by position
+  const __nv_bfloat16* pbase = qkv + (int64_t)h * HD;
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * Ls * ld + (int64_t)h * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
 
@@ -307,8 +311,9 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   for (int i = threadIdx.x; i < Lp * kVec; i += kSeqThreads) {
     const int r = i / kVec, c = (i - r * kVec) * 8;
     if (r < L) {
-      cp_async16(smem_u32(Ks + r * kPitch + c), kbase + (int64_t)r * ld + c);
-      cp_async16(smem_u32(Vs + r * kPitch + c), vbase + (int64_t)r * ld + c);
+      const __nv_bfloat16* src = (r < Lc ? pbase : qbase) + (int64_t)r * ld + c;
+      cp_async16(smem_u32(Ks + r * kPitch + c), src + D);
+      cp_async16(smem_u32(Vs + r * kPitch + c), src + 2 * D);
     } else {
       *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
@@ -319,14 +324,14 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   cp_async_wait<0>();
   __syncthreads();
 
-  const int n_strips = (L + 15) >> 4;
+  const int n_strips = (Ls + 15) >> 4;
   __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
   while (true) {
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(counter, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= n_strips) break;
-    const int q0 = (n_strips - 1 - ticket) * 16;   // heaviest strips first
+    const int q0 = Lc + (n_strips - 1 - ticket) * 16;   // heaviest strips first (positions, >= Lc)
     // stage this warp's 16 query rows
     for (int i = lane; i < 16 * kVec; i += 32) {
       const int r = i / kVec, c = (i - r * kVec) * 8;
@@ -430,7 +435,7 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     }
     const float inv_a = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f;
     const float inv_b = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
-    __nv_bfloat16* obase = out + (int64_t)b * L * D + (int64_t)h * HD;
+    __nv_bfloat16* obase = out + (int64_t)b * Ls * D + (int64_t)h * HD;
 #pragma unroll
     for (int nt = 0; nt < HD / 8; ++nt) {
       const int col = nt * 8 + tq * 2;
@@ -439,9 +444,9 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
       if (row_b < L)
         *reinterpret_cast<uint32_t*>(obase + (int64_t)row_b * D + col) = pack_bf16(o[nt][2] * inv_b, o[nt][3] * inv_b);
     }
-    if (lse && tq == 0) {
-      if (row_a < L) lse[(int64_t)bh * L + row_a] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
-      if (row_b < L) lse[(int64_t)bh * L + row_b] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
+    if (lse && tq == 0) {   // lse is [Bp, H, Ls], indexed by the token's place among the sample's own tokens
+      if (row_a < L) lse[(int64_t)bh * Ls + row_a - Lc] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
+      if (row_b < L) lse[(int64_t)bh * Ls + row_b - Lc] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
     }
     __syncwarp();   // Qs is re-staged by the next strip
   }
@@ -453,23 +458,29 @@ static size_t seq_smem_bytes(int L) {
   return (size_t)(2 * Lp + 8 * 16) * (HD + 8) * 2 + 16;
 }
 
+// Sequence-resident forward over Bp samples of L positions whose first Lc are a shared prefix stored once.
+template <int HD>
+static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H,
+                           float scale, cudaStream_t stream) {
+  auto ks = attn_causal_fwd_seq_kernel<HD>;
+  static bool seq_attr_done = false;
+  if (!seq_attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn seq)", e);
+    seq_attr_done = true;
+  }
+  ks<<<Bp * H, kSeqThreads, seq_smem_bytes<HD>(L), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, L, Lc, H,
+      scale * 1.4426950408889634f);
+  count_launch();
+  return check_launch("attn_causal_fwd_seq_kernel");
+}
+
 template <int HD>
 static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, uint16_t* out,
                        float* lse, int Bp, int L, int H, float scale, cudaStream_t stream) {
-  if (rc == nullptr && seq_smem_bytes<HD>(L) <= 220 * 1024) {
-    auto ks = attn_causal_fwd_seq_kernel<HD>;
-    static bool seq_attr_done = false;
-    if (!seq_attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn seq)", e);
-      seq_attr_done = true;
-    }
-    ks<<<Bp * H, kSeqThreads, seq_smem_bytes<HD>(L), stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, L, H,
-        scale * 1.4426950408889634f);
-    count_launch();
-    return check_launch("attn_causal_fwd_seq_kernel");
-  }
+  if (rc == nullptr && seq_smem_bytes<HD>(L) <= 220 * 1024)
+    return launch_attn_seq<HD>(qkv, out, lse, Bp, L, 0, H, scale, stream);
   constexpr int kSmem = 3 * 64 * (HD + 8) * 2;
   auto kern = attn_causal_fwd_kernel<HD>;
   static bool attr_done = false;
@@ -786,7 +797,10 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                        const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                        const float* __restrict__ lse, const float* __restrict__ delta,
-                       __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+                       __nv_bfloat16* __restrict__ dqkv, int L, int Lc, int H, float scale) {
+  // Lc > 0: shared-prefix layout as in attn_causal_fwd_seq_kernel.  qkv holds every row (prefix rows once,
+  // then Ls = L - Lc own rows per sample); dout / lse / delta / dqkv hold the samples' own rows only
+  // ([Bp*Ls, ...]): the prefix has no trainable ancestor, so no gradient is produced for it.
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   const int Lp = (L + 63) & ~63;
@@ -800,20 +814,34 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
   const int b = bh / H, h = bh - b * H;
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
-  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
-  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
+  const int Ls = L - Lc;
+  const __nv_bfloat16* pbase = qkv + (int64_t)h * HD;                           // indexed by position < Lc
+  const __nv_bfloat16* qbase = qkv + (int64_t)b * Ls * ld + (int64_t)h * HD;    // indexed by position >= Lc
+  const __nv_bfloat16* dobase = dout + (int64_t)b * Ls * D + (int64_t)h * HD;   // indexed by position - Lc
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
 
-  stage_rows_async<HD>(Ks, qbase + D, ld, L, Lp, threadIdx.x, kSeqThreads);
-  stage_rows_async<HD>(Vs, qbase + 2 * D, ld, L, Lp, threadIdx.x, kSeqThreads);
+  {
+    constexpr int kVec = HD / 8;
+    for (int i = threadIdx.x; i < Lp * kVec; i += kSeqThreads) {
+      const int r = i / kVec, c = (i - r * kVec) * 8;
+      if (r < L) {
+        const __nv_bfloat16* src = (r < Lc ? pbase : qbase) + (int64_t)r * ld + c;
+        cp_async16(smem_u32(Ks + r * kPitch + c), src + D);
+        cp_async16(smem_u32(Vs + r * kPitch + c), src + 2 * D);
+      } else {
+        *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
   cp_async_commit();
   if (threadIdx.x == 0) *counter = 0;
   cp_async_wait<0>();
   __syncthreads();
 
-  const int n_strips = (L + 15) >> 4;
+  const int n_strips = (Ls + 15) >> 4;
   __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
   __nv_bfloat16* dOs = dOw + warp * 16 * kPitch;
   while (true) {
@@ -821,15 +849,15 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
     if (lane == 0) ticket = atomicAdd(counter, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= n_strips) break;
-    const int q0 = (n_strips - 1 - ticket) * 16;
+    const int q0 = Lc + (n_strips - 1 - ticket) * 16;      // positions
     stage_strip<HD>(Qs, qbase, ld, q0, L, lane);
-    stage_strip<HD>(dOs, dobase, D, q0, L, lane);
+    stage_strip<HD>(dOs, dobase, D, q0 - Lc, Ls, lane);
     __syncwarp();
     const int row_a = q0 + g, row_b = row_a + 8;
-    const float lse_a = row_a < L ? lse[(int64_t)bh * L + row_a] * 1.4426950408889634f : INFINITY;
-    const float lse_b = row_b < L ? lse[(int64_t)bh * L + row_b] * 1.4426950408889634f : INFINITY;
-    const float del_a = row_a < L ? delta[(int64_t)bh * L + row_a] : 0.f;
-    const float del_b = row_b < L ? delta[(int64_t)bh * L + row_b] : 0.f;
+    const float lse_a = row_a < L ? lse[(int64_t)bh * Ls + row_a - Lc] * 1.4426950408889634f : INFINITY;
+    const float lse_b = row_b < L ? lse[(int64_t)bh * Ls + row_b - Lc] * 1.4426950408889634f : INFINITY;
+    const float del_a = row_a < L ? delta[(int64_t)bh * Ls + row_a - Lc] : 0.f;
+    const float del_b = row_b < L ? delta[(int64_t)bh * Ls + row_b - Lc] : 0.f;
     float dq[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
@@ -851,7 +879,8 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
       }
       mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi);
     }
-    store_grad_rows<HD>(dq, dqkv + (int64_t)b * L * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq, rope_cos, rope_sin);
+    // dqkv rows are the samples' own rows: row of position p = b*Ls + p - Lc (store_grad_rows indexes by position)
+    store_grad_rows<HD>(dq, dqkv + ((int64_t)b * Ls - Lc) * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq, rope_cos, rope_sin);
     __syncwarp();
   }
 }
@@ -984,7 +1013,7 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
       const size_t smem = seq_bwd_smem_bytes<HD>(L);
       sq<<<Bp * H, kSeqThreads, smem, stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, 0, H, scale);
       count_launch();
       rc_ = check_launch("attn_bwd_dq_seq_kernel");
       if (rc_) return rc_;
@@ -1010,9 +1039,99 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
   return check_launch("attn_bwd_dkv_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-prefix variants: the first Lc positions of every sample are the same prompt tokens (static dataset /
+// task prompt, models/medtsllm.py:386-439) and, the mask being causal, their states at every layer are the same
+// for all samples.  They are kept ONCE in rows [0, Lc); sample b owns rows Lc + b*Ls + [0, Ls).
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+static int launch_attn_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
+                              float scale, cudaStream_t stream) {
+  const int L = Lc + Ls;
+  if (seq_smem_bytes<HD>(L) > 220 * 1024)
+    return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared: %d positions do not fit in shared memory", L);
+  // the prefix as one ordinary sequence of Lc positions, then every sample's own tokens
+  int rc_ = launch_attn_seq<HD>(qkv, out, lse, 1, Lc, 0, H, scale, stream);
+  if (rc_) return rc_;
+  return launch_attn_seq<HD>(qkv, out, lse ? lse + (int64_t)H * Lc : nullptr, Bp, L, Lc, H, scale, stream);
+}
+
+template <int HD>
+static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own,
+                                  const uint16_t* dout_own, const float* lse_own, float* delta, uint16_t* dqkv_own,
+                                  int Bp, int Lc, int Ls, int H, float scale, cudaStream_t stream) {
+  const int L = Lc + Ls;
+  const int D = H * HD;
+  if (seq_bwd_smem_bytes<HD>(L) > 220 * 1024)
+    return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd: %d positions do not fit in shared memory", L);
+  auto sq = attn_bwd_dq_seq_kernel<HD>;
+  auto skv = attn_bwd_dkv_seq_kernel<HD>;
+  static bool seq_attr = false;
+  if (!seq_attr) {
+    cudaError_t e = cudaFuncSetAttribute(sq, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(skv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd seq)", e);
+    seq_attr = true;
+  }
+  const int64_t nwarps = (int64_t)Bp * Ls * H;
+  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out_own), reinterpret_cast<const __nv_bfloat16*>(dout_own), delta, Ls, H, HD,
+      nwarps);
+  count_launch();
+  int rc_ = check_launch("attn_bwd_delta_kernel");
+  if (rc_) return rc_;
+  // dQ of the own tokens: keys = prefix + own
+  sq<<<Bp * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own,
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), L, Lc, H, scale);
+  count_launch();
+  rc_ = check_launch("attn_bwd_dq_seq_kernel");
+  if (rc_) return rc_;
+  // dK / dV of the own tokens only (queries = own tokens; the log-sum-exp already covers the prefix keys):
+  // the plain kernel on the own rows, RoPE tables shifted to position Lc
+  const int half = HD / 2;
+  skv<<<Bp * H, kSeqThreads, seq_bwd_smem_bytes<HD>(Ls), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv) + (int64_t)Lc * 3 * D, rc ? rc + (int64_t)Lc * half : nullptr,
+      rs ? rs + (int64_t)Lc * half : nullptr, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv_own), Ls, H, scale);
+  count_launch();
+  return check_launch("attn_bwd_dkv_seq_kernel");
+}
+
 }  // namespace mts
 
 using namespace mts;
+
+extern "C" int mts_attn_causal_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
+                                      int hd, float scale, mts_stream_t s) {
+  if (!qkv || !out || Bp <= 0 || Lc <= 0 || Ls <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared: bad args");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared: misaligned pointer");
+  switch (hd) {
+    case 64: return launch_attn_shared<64>(qkv, out, lse, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    case 128: return launch_attn_shared<128>(qkv, out, lse, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared: head dim %d (supported: 64, 128)", hd);
+  }
+}
+
+extern "C" int mts_attn_causal_shared_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                                          const uint16_t* out_own, const uint16_t* dout_own, const float* lse_own,
+                                          float* delta, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
+                                          float scale, mts_stream_t s) {
+  if (!qkv || !out_own || !dout_own || !lse_own || !delta || !dqkv_own || Bp <= 0 || Lc <= 0 || Ls <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd: bad args");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd: rope_cos and rope_sin go together");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dout_own) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv_own) & 15) || (reinterpret_cast<uintptr_t>(out_own) & 3))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd: misaligned pointer");
+  switch (hd) {
+    case 64: return launch_attn_shared_bwd<64>(qkv, rope_cos, rope_sin, out_own, dout_own, lse_own, delta, dqkv_own, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    case 128: return launch_attn_shared_bwd<128>(qkv, rope_cos, rope_sin, out_own, dout_own, lse_own, delta, dqkv_own, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd: head dim %d (supported: 64, 128)", hd);
+  }
+}
 
 extern "C" int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                                uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
@@ -1059,7 +1178,22 @@ extern "C" int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* ro
   int64_t g = (total + 255) / 256;
   if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
   rope_qk_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
-                                                     rows, L, H, hd);
+                                                     rows, L, 0, H, hd);
+  count_launch();
+  return check_launch("rope_qk_kernel");
+}
+
+extern "C" int mts_rope_qk_shared(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int Lc, int Ls,
+                                  int H, int hd, mts_stream_t s) {
+  if (!qkv || !rope_cos || !rope_sin || Bp <= 0 || Lc < 0 || Ls <= 0 || H <= 0 || hd <= 0 || (hd % 16))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_rope_qk_shared: bad args (hd must be a multiple of 16)");
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) return set_error(MTS_ERR_INVALID_ARG, "mts_rope_qk_shared: misaligned qkv");
+  const int64_t rows = (int64_t)Lc + (int64_t)Bp * Ls;
+  const int64_t total = rows * 2 * H * (hd / 16);
+  int64_t g = (total + 255) / 256;
+  if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
+  rope_qk_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
+                                                     rows, Ls, Lc, H, hd);
   count_launch();
   return check_launch("rope_qk_kernel");
 }

@@ -25,7 +25,7 @@ struct GemmParams {
   // ROPE_QK: rotate-half RoPE on output columns < rope_cols (the q | k sections of a fused qkv projection)
   const float* rope_cos;
   const float* rope_sin;
-  int rope_L, rope_hd, rope_cols;
+  int rope_L, rope_hd, rope_cols, rope_prefix;
   // SWIGLU: optional bf16 copy of the gate/up pre-activations (packed column order, row stride ld_aux) that the
   // training path keeps for the backward
   __nv_bfloat16* aux;
@@ -70,7 +70,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
         // x2' = x2 cos + x1 sin with x2 = the column hd/2 further (HF:models/llama/modeling_llama.py:139-168),
         // position = row index inside the sample.  Chunk pairs (c, c + hd/64) of 32 columns hold (x1, x2).
         const int half_chunks = p.rope_hd / 64;           // 1 (hd 64) or 2 (hd 128)
-        const int pos = row % p.rope_L;
+        // shared-prefix layout: rows < rope_prefix are positions themselves, then rope_L own rows per sample
+        const int pos = row < p.rope_prefix ? row : p.rope_prefix + (row - p.rope_prefix) % p.rope_L;
         const float* cr = p.rope_cos + (int64_t)pos * (p.rope_hd / 2);
         const float* sr = p.rope_sin + (int64_t)pos * (p.rope_hd / 2);
         __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride;

@@ -276,7 +276,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
       break;
     case MTS_EPI_ROPE_QK:
       if (f32 || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || !a->rope_cos || !a->rope_sin ||
-          (a->rope_hd != 64 && a->rope_hd != 128) || a->rope_L <= 0 || (a->rope_cols % a->rope_hd) ||
+          (a->rope_hd != 64 && a->rope_hd != 128) || a->rope_L <= 0 || a->rope_prefix < 0 || (a->rope_cols % a->rope_hd) ||
           (a->n % a->rope_hd) || (bn != 0 && bn != 256) || (n_store % 8) || (a->ldd % 8) ||
           (reinterpret_cast<uintptr_t>(a->rope_cos) & 15) || (reinterpret_cast<uintptr_t>(a->rope_sin) & 15))
         return set_error(MTS_ERR_INVALID_ARG,
@@ -335,7 +335,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.bias_vec = (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
   p.alpha = a->alpha;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
-  p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols;
+  p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols; p.rope_prefix = a->rope_prefix;
   p.aux = nullptr; p.ld_aux = 0;
   if (a->aux) {
     if (a->epilogue != MTS_EPI_SWIGLU || a->batch != 1 || a->ld_aux < a->n || (a->ld_aux % 8) ||

@@ -189,8 +189,20 @@ __global__ void pack_gate_up_kernel(const __nv_bfloat16* __restrict__ gate,
 __global__ void __launch_bounds__(256)
 prompt_gather_kernel(const int32_t* __restrict__ ids, const float* __restrict__ emb,
                      const float* __restrict__ wpe, float* __restrict__ x, int rep, int Lp, int L,
-                     int D) {
-  const int b = blockIdx.x / L, l = blockIdx.x - b * L;
+                     int Lc, int D) {
+  // Lc > 0 (shared-prefix layout): the first Lc prompt tokens are the same for every sample and are written
+  // once, to rows [0, Lc) (taken from ids row 0); sample b then owns rows Lc + b*(L-Lc) + [0, L-Lc).
+  const int Ls = L - Lc;
+  int b, l;
+  int64_t row0;          // output row of (b, replica 0, l)
+  int64_t rep_stride;    // rows between replicas
+  if ((int)blockIdx.x < Lc) {
+    b = 0; l = blockIdx.x; row0 = l; rep_stride = 0; rep = 1;
+  } else {
+    const int j = blockIdx.x - Lc;
+    b = j / Ls; l = Lc + (j - b * Ls);
+    row0 = (int64_t)Lc + (int64_t)b * rep * Ls + (l - Lc); rep_stride = Ls;
+  }
   const int D4 = D >> 2;
   const float4* src = nullptr;
   if (l < Lp) src = reinterpret_cast<const float4*>(emb + (int64_t)ids[(int64_t)b * Lp + l] * D);
@@ -202,7 +214,7 @@ prompt_gather_kernel(const int32_t* __restrict__ ids, const float* __restrict__ 
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
     for (int r = 0; r < rep; ++r)
-      reinterpret_cast<float4*>(x + ((int64_t)(b * rep + r) * L + l) * D)[i] = v;
+      reinterpret_cast<float4*>(x + (row0 + r * rep_stride) * D)[i] = v;
   }
 }
 
@@ -353,7 +365,19 @@ extern "C" int mts_prompt_gather(const int32_t* ids, const float* emb, const flo
   if ((D % 4) || (reinterpret_cast<uintptr_t>(emb) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) ||
       (wpe && (reinterpret_cast<uintptr_t>(wpe) & 15)))
     return set_error(MTS_ERR_INVALID_ARG, "mts_prompt_gather: D % 4 and 16-byte alignment required");
-  prompt_gather_kernel<<<B * L, 256, 0, (cudaStream_t)s>>>(ids, emb, wpe, x, rep, Lp, L, D);
+  prompt_gather_kernel<<<B * L, 256, 0, (cudaStream_t)s>>>(ids, emb, wpe, x, rep, Lp, L, 0, D);
+  count_launch();
+  return check_launch("prompt_gather_kernel");
+}
+
+extern "C" int mts_prompt_gather_shared(const int32_t* ids, const float* emb, const float* wpe, float* x,
+                                        int B, int rep, int Lp, int L, int Lc, int D, mts_stream_t s) {
+  if (!emb || !x || !ids || B <= 0 || rep <= 0 || Lp <= 0 || L < Lp || Lc <= 0 || Lc > Lp || Lc >= L || D <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_prompt_gather_shared: bad args (0 < Lc <= Lp <= L, Lc < L)");
+  if ((D % 4) || (reinterpret_cast<uintptr_t>(emb) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (wpe && (reinterpret_cast<uintptr_t>(wpe) & 15)))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_prompt_gather_shared: D % 4 and 16-byte alignment required");
+  prompt_gather_kernel<<<Lc + B * (L - Lc), 256, 0, (cudaStream_t)s>>>(ids, emb, wpe, x, rep, Lp, L, Lc, D);
   count_launch();
   return check_launch("prompt_gather_kernel");
 }

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("d_dtype", C.c_int32), ("epilogue", C.c_int32), ("bias_axis", C.c_int32),
         ("d_transposed", C.c_int32), ("block_n", C.c_int32), ("alpha", C.c_float),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
-        ("rope_L", C.c_int32), ("rope_hd", C.c_int32), ("rope_cols", C.c_int32), ("reserved_", C.c_int32),
+        ("rope_L", C.c_int32), ("rope_hd", C.c_int32), ("rope_cols", C.c_int32), ("rope_prefix", C.c_int32),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
     ]
 
@@ -75,6 +75,10 @@ SIGNATURES = {
     "mts_merge_end": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mts_merge_end_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "mts_attn_causal_shared": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "mts_attn_causal_shared_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "mts_rope_qk_shared": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mts_prompt_gather_shared": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],
 }

@@ -226,14 +226,20 @@ class KernelBackbone:
             self._embed_bf16 = ops.cast_bf16(self.embed)
         return self._embed_bf16
 
-    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None, lora=None):
+    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None, lora=None, Lc: int = 0):
         """x: fp32 residual stream [Bp*L, D].  Inference (stash None): updated IN PLACE layer by layer.
         Training (stash = list): every residual write goes to a fresh buffer (the GEMM epilogue reads
         C = previous stream, writes D = new one) and the per-layer tensors backward() needs are
-        appended to `stash`.  Returns (final-norm output bf16 [Bp*L, D], final residual stream fp32)."""
+        appended to `stash`.  Returns (final-norm output bf16 [Bp*L, D], final residual stream fp32).
+
+        Lc > 0: shared-prefix row layout (include/mts_b200.h, mts_attn_causal_shared) — the Lc leading prompt
+        positions every sample shares are carried once: x is [Lc + Bp*(L-Lc), D], rows [0, Lc) the prefix, then
+        L-Lc own rows per sample.  All row-wise kernels and GEMMs are layout-agnostic; RoPE positions and
+        attention are told about it."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
-        M = Bp * L
+        Ls = L - Lc
+        M = Lc + Bp * Ls
         if x.shape != (M, D) or x.dtype != torch.float32 or not x.is_contiguous():
             raise MtsError("backbone.forward expects a contiguous fp32 [Bp*L, D] residual stream")
         if s.kind == "gpt2" and L > s.max_pos:
@@ -255,8 +261,8 @@ class KernelBackbone:
             if llama:
                 ops.rmsnorm(x_in, lay["ln1"], s.eps, out=h)
                 if fused_rope:   # q | k rotated in fp32 straight from the accumulators, in the GEMM epilogue
-                    ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, epilogue=EPI_ROPE_QK, rope=rope, rope_L=L,
-                             rope_hd=hd, rope_cols=2 * D)
+                    ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D, epilogue=EPI_ROPE_QK, rope=rope, rope_L=Ls,
+                             rope_hd=hd, rope_cols=2 * D, rope_prefix=Lc)
                 else:
                     ops.gemm(h, lay["wqkv"], qkv, m=M, n=3 * D, k=D)
             else:
@@ -265,9 +271,17 @@ class KernelBackbone:
             lora_t = lora.forward_layer(li, h, qkv, M, D) if lora is not None else None
             h_attn = h
             lse = None
-            if rope is not None and not fused_rope:
-                ops.rope_qk_(qkv, Bp, L, H, hd, rope)      # q, k rotated in place; attention stages them as is
-            if train:
+            if rope is not None and not fused_rope:    # q, k rotated in place; attention stages them as is
+                if Lc:
+                    ops.rope_qk_shared_(qkv, Bp, Lc, Ls, H, hd, rope)
+                else:
+                    ops.rope_qk_(qkv, Bp, L, H, hd, rope)
+            if Lc:
+                if train:
+                    _, lse = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, out=att, want_lse=True)
+                else:
+                    ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, out=att)
+            elif train:
                 _, lse = ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att, want_lse=True)
             else:
                 ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att)
@@ -314,13 +328,22 @@ class KernelBackbone:
             ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
         return out, x
 
-    def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None):
+    def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None,
+                 Lc: int = 0):
         """dgrad through the frozen stack: dhid = dL/d(final-norm output) bf16 [Bp*L, D] -> returns
         (dL/d(input residual stream) fp32 [Bp*L, D], LoRA gradients aligned with lora.params() or None).
-        No gradients for the frozen weights."""
+        No gradients for the frozen weights.
+
+        Lc > 0 (shared-prefix layout, frozen backbone without LoRA): the prefix rows have no trainable
+        ancestor, so the whole chain runs on the samples' own rows only — dhid and the result are
+        [Bp*(L-Lc), D] and every stashed tensor is read from row Lc on."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
-        M = Bp * L
+        Ls = L - Lc
+        M = Bp * Ls
+        if Lc and lora is not None:
+            raise MtsError("the shared-prefix backward assumes a frozen backbone (no LoRA)")
+        own = slice(Lc, None)
         self.ensure_transposed()
         rope = self.rope(L)
         dev = dhid.device
@@ -329,26 +352,30 @@ class KernelBackbone:
         bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
         dR = torch.empty(M, D, device=dev, dtype=torch.float32)
         dRb, dH = bf(M, D), bf(M, D)       # dRb: bf16 copy of dR, refreshed by every norm backward
-        norm_bwd(x_final, self.final_norm_w, dhid, dR, s.eps, accumulate=False, dx_bf16=dRb)
+        norm_bwd(x_final[own], self.final_norm_w, dhid, dR, s.eps, accumulate=False, dx_bf16=dRb)
         lora_grads = [None] * len(lora.params()) if lora is not None else None
         for li, lay, st in zip(reversed(range(len(self.layers))), reversed(self.layers), reversed(stash)):
             # --- MLP half: x_out = x_mid + W2 act(W1 norm(x_mid))
             if llama:
                 dact = bf(M, self.i_pad)
                 ops.gemm(dRb, lay["wdown_t"], dact, m=M, n=self.i_pad, k=D)
-                dpre = ops.swiglu_bwd(st["pre"], dact, self.i_pad, 128)
+                dpre = ops.swiglu_bwd(st["pre"][own], dact, self.i_pad, 128)
                 ops.gemm(dpre, lay["wgu_t"], dH, m=M, n=D, k=2 * self.i_pad)
             else:
                 dact = bf(M, s.inter)
                 ops.gemm(dRb, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
-                dpre = ops.gelu_new(st["pre"], dact)
+                dpre = ops.gelu_new(st["pre"][own], dact)
                 ops.gemm(dpre, lay["wfc_t"], dH, m=M, n=D, k=s.inter)
-            norm_bwd(st["x_mid"], lay["ln2"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
+            norm_bwd(st["x_mid"][own], lay["ln2"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
             # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
             datt = bf(M, D)
             ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
-            dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
-                                       pre_roped=rope is not None)
+            if Lc:
+                dqkv = ops.attn_causal_shared_bwd(st["qkv"], st["att"][own], datt, st["lse"], Bp, Lc, Ls, H, hd,
+                                                  rope=rope)
+            else:
+                dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
+                                           pre_roped=rope is not None)
             ops.gemm(dqkv, lay["wqkv_t"], dH, m=M, n=D, k=3 * D)
             if lora is not None:
                 dAs, dBs = lora.backward_layer(li, st["h"], st["lora_t"], dqkv, dH, M, D)
@@ -356,7 +383,7 @@ class KernelBackbone:
                 for t in range(len(lora.targets)):
                     lora_grads[lora.index(li, t)] = dAs[t]
                     lora_grads[nA + lora.index(li, t)] = dBs[t]
-            norm_bwd(st["x_in"], lay["ln1"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
+            norm_bwd(st["x_in"][own], lay["ln1"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
         return dR, lora_grads
 
     def flops_per_token_fwd(self, L: int) -> float:

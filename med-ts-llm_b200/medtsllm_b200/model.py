@@ -188,6 +188,9 @@ class MedTsLLM(nn.Module):
         else:
             self._dropout_requested = 0.0
 
+        # in-batch prompt de-duplication (shared-prefix row layout, include/mts_b200.h): on by default,
+        # MTS_SHARE_PREFIX=0 or `model.share_prompt_prefix = False` computes every sample's prompt rows
+        self.share_prompt_prefix = os.environ.get("MTS_SHARE_PREFIX", "1") != "0"
         self._capture = None       # tests: dict filled with per-stage tensors
         self._ids_cache = None     # (prompt parts, host id table, device id table)
         self._prompt_cache: dict[str, list[int]] = {}
@@ -396,8 +399,41 @@ class MedTsLLM(nn.Module):
         for b, ids in enumerate(per_sample):
             if ids:
                 table[b, Lp - len(ids):] = torch.tensor(ids, dtype=torch.int32)
-        self._ids_cache = (key, table, None)
+        self._ids_cache = (key, table, None)     # (+ shared-prefix length once _shared_prefix_len has run)
         return table
+
+    def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int) -> int:
+        """Number of leading prompt positions (left padding included) that hold the same token in every
+        sample of the batch.  The backbone is causal and the reference passes no padding mask
+        (models/medtsllm.py:350), so the hidden states of those positions are the same for every sample
+        at every layer: they are computed once per batch instead of once per sample.  0 = plain layout."""
+        if not self.share_prompt_prefix or Bp < 2 or ids.shape[1] == 0:
+            return 0
+        if self.lora_enabled and torch.is_grad_enabled():
+            return 0               # LoRA weights receive gradient through the prompt rows too
+        c = self._ids_cache
+        if c is not None and c[1] is ids and len(c) > 3:
+            Lc = c[3]
+        else:
+            same = (ids == ids[0:1]).all(dim=0)
+            Lc = int(same.to(torch.int8).cumprod(0).sum())
+            if c is not None and c[1] is ids:
+                self._ids_cache = (c[0], c[1], c[2], Lc)
+        if Lc < 16:
+            return 0
+        # the sequence-resident attention kernels keep all L positions of one head in shared memory
+        hd = self.backbone_spec.head_dim
+        L64 = (L + 63) // 64 * 64
+        smem = (2 * L64 + 256) * (hd + 8) * 2 + 2 * L64 * 4 + 16
+        return Lc if smem <= 220 * 1024 else 0
+
+    @staticmethod
+    def _expand_rows(t: torch.Tensor, Bp: int, L: int, Lc: int) -> torch.Tensor:
+        """[Lc + Bp*(L-Lc), D] shared-prefix rows -> [Bp, L, D] (tests / captures only)."""
+        D = t.shape[-1]
+        if Lc == 0:
+            return t.view(Bp, L, D).clone()
+        return torch.cat([t[:Lc].unsqueeze(0).expand(Bp, Lc, D), t[Lc:].view(Bp, L - Lc, D)], dim=1).contiguous()
 
     # ------------------------------------------------------------------------------------------ weights
     PARAM_ORDER = (
@@ -556,9 +592,12 @@ class MedTsLLM(nn.Module):
             else:
                 ids_dev = ids.to(dev, non_blocking=True)
                 if c is not None and c[1] is ids:
-                    self._ids_cache = (c[0], c[1], ids_dev)
-        X = torch.empty(Bp, L, D, device=dev, dtype=torch.float32)
-        ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L)
+                    self._ids_cache = (c[0], c[1], ids_dev) + tuple(c[3:])
+        # shared-prefix row layout: Lc leading prompt positions once, then Ls = L - Lc own rows per sequence
+        Lc = self._shared_prefix_len(ids, Bp, L)
+        Ls = L - Lc
+        X = torch.empty(Lc + Bp * Ls, D, device=dev, dtype=torch.float32)
+        ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L, Lc=Lc, B=B)
 
         # K1+K2: RevIN + patches + token conv (concat layout [B, N, C*32] or per feature [B*C, N0, 32])
         concat = mode == "concat"
@@ -595,13 +634,13 @@ class MedTsLLM(nn.Module):
         Y = None
         if mode in ("concat", "univariate", "independent", "merge-end"):
             # one sequence per (sample[, feature]): rows of batch i land at X[i, Lp:, :]
-            ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=L * D, ldd=D, d_off=Lp * D,
+            ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=Ls * D, ldd=D, d_off=Lp * D,
                      ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
         elif mode == "interleave":
             # token order n-major, c-minor (models/medtsllm.py:292-295): feature c writes rows Lp + n*C + c
             for c in range(C):
                 ops.gemm(O, wo, X, m=N0, n=D, k=HE, batch=B, a_off=c * N0 * HE, a_bs=C * N0 * HE, b_bs=0,
-                         d_bs=L * D, ldd=C * D, d_off=(Lp + c) * D, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N,
+                         d_bs=Ls * D, ldd=C * D, d_off=(Lp + c) * D, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N,
                          epilogue=EPI_RESID_ADD)
         else:
             # add / weighted-average (models/medtsllm.py:284-291): merge the C reprogrammed streams into one
@@ -609,24 +648,25 @@ class MedTsLLM(nn.Module):
             ops.gemm(O, wo, Y, m=rows, n=D, k=HE, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N)
             fw = self.feature_weighting if mode == "weighted-average" else None
             ops.group_reduce(Y, B, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
-                             bias=fw.bias.detach() if fw is not None else None, out=X, out_bs=L * D, out_off=Lp * D,
+                             bias=fw.bias.detach() if fw is not None else None, out=X, out_bs=Ls * D, out_off=Lp * D,
                              accumulate=True)       # X's patch rows hold 0 (+ wpe for GPT-2)
 
         cap = self._capture
         if cap is not None:
             cap.update(revin_mean=mean.clone(), revin_stdev=std.clone(), patch_embedding=enc.clone(),
-                       source_embeddings=source.clone(), llm_input=X.clone())
+                       source_embeddings=source.clone(), llm_input=self._expand_rows(X, Bp, L, Lc))
         # backbone
         layer_stash = [] if stash is not None else None
-        hid, x_final = bb.forward(X.view(Bp * L, D), Bp, L, stash=layer_stash,
-                                  lora=self.llm if self.lora_enabled else None)   # bf16 [Bp*L, D], final norm applied
+        hid, x_final = bb.forward(X, Bp, L, stash=layer_stash, lora=self.llm if self.lora_enabled else None,
+                                  Lc=Lc)                                          # bf16 rows like X, final norm applied
         if cap is not None:
-            cap["llm"] = hid.view(Bp, L, D).clone()
+            cap["llm"] = self._expand_rows(hid, Bp, L, Lc)
+            cap["shared_prefix"] = Lc
 
         # K11: last N tokens -> Linear(D -> d_ff), stored transposed as [Bp, d_ff, N] (flatten index f*N+n)
         wds, bds = self._downsample_operands()
         flat = torch.empty(Bp, E * N, device=dev, dtype=torch.bfloat16)
-        ops.gemm(hid, wds, flat, m=N, n=E, k=D, batch=Bp, a_off=Lp * D, a_bs=L * D, b_bs=0, d_bs=E * N,
+        ops.gemm(hid, wds, flat, m=N, n=E, k=D, batch=Bp, a_off=Lp * D, a_bs=Ls * D, b_bs=0, d_bs=E * N,
                  d_transposed=True, ldd=N, ldb=wds.shape[1], bias=bds, bias_axis=BIAS_N if bds is not None else 0)
         # K12: flatten head
         wh = self._bf16_weight("wh", self.output_projection.linear.weight)
@@ -653,7 +693,7 @@ class MedTsLLM(nn.Module):
             out = out.squeeze(-1)
         if stash is not None:
             stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
-                         hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Bp=Bp, B=B, N0=N0,
+                         hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Lc=Lc, Bp=Bp, B=B, N0=N0,
                          scale=scale, denorm=denorm, concat=concat, Y=Y, head=head, Pd=Pd, p_drop=p_drop, seeds=seeds)
         return out
 

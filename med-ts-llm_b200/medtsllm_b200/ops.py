@@ -42,7 +42,7 @@ def _ptr(t):
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
          block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0,
-         aux=None):
+         rope_prefix=0, aux=None):
     """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
     if d.dtype not in (torch.bfloat16, torch.float32):
@@ -69,7 +69,9 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.alpha = alpha
     if rope is not None:
         args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
-        args.rope_L, args.rope_hd, args.rope_cols = rope_L, rope_hd, rope_cols
+        args.rope_L, args.rope_hd, args.rope_cols, args.rope_prefix = rope_L, rope_hd, rope_cols, rope_prefix
+        if rope[0].shape[0] < rope_prefix + rope_L:
+            raise MtsError("rope tables shorter than the sequence")
     if aux is not None:
         _chk(aux, torch.bfloat16, "aux")
         args.aux, args.ld_aux = aux.data_ptr(), aux.shape[-1]
@@ -200,6 +202,43 @@ def attn_causal(qkv, Bp, L, H, hd, *, rope=None, scale=None, want_lse=False, out
     return (out, lse) if want_lse else out
 
 
+def attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, *, scale=None, want_lse=False, out=None):
+    """Causal attention on the shared-prefix row layout (include/mts_b200.h): qkv bf16 [Lc + Bp*Ls, 3*H*hd]
+    with q / k already rotated -> out bf16 [Lc + Bp*Ls, H*hd]; lse (own tokens) fp32 [Bp, H, Ls]."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    M = Lc + Bp * Ls
+    if not qkv.is_contiguous() or qkv.shape != (M, 3 * H * hd):
+        raise MtsError("attn_causal_shared needs contiguous qkv [Lc + Bp*Ls, 3*H*hd]")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty(M, H * hd, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(H * Lc + Bp * H * Ls, device=qkv.device, dtype=torch.float32) if want_lse else None
+    _lib.call("mts_attn_causal_shared", qkv.data_ptr(), out.data_ptr(), _ptr(lse), Bp, Lc, Ls, H, hd, scale, _stream())
+    return (out, lse[H * Lc:].view(Bp, H, Ls)) if want_lse else out
+
+
+def attn_causal_shared_bwd(qkv, out_own, dout_own, lse_own, Bp, Lc, Ls, H, hd, *, rope=None, scale=None):
+    """Gradient w.r.t. the own-token rows of the (un-rotated) qkv projection: bf16 [Bp*Ls, 3*H*hd]."""
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out_own, torch.bfloat16, "out"); _chk(dout_own, torch.bfloat16, "dout")
+    _chk(lse_own, torch.float32, "lse")
+    for t, cols in ((out_own, H * hd), (dout_own, H * hd)):
+        if not t.is_contiguous() or t.shape != (Bp * Ls, cols):
+            raise MtsError("attn_causal_shared_bwd: own-row tensors must be contiguous [Bp*Ls, H*hd]")
+    if not qkv.is_contiguous() or not lse_own.is_contiguous() or lse_own.numel() != Bp * H * Ls:
+        raise MtsError("attn_causal_shared_bwd: contiguous qkv and lse [Bp, H, Ls] required")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    dqkv = torch.empty(Bp * Ls, 3 * H * hd, device=qkv.device, dtype=torch.bfloat16)
+    delta = torch.empty(Bp, H, Ls, device=qkv.device, dtype=torch.float32)
+    cos, sin = rope if rope is not None else (None, None)
+    if cos is not None and cos.shape[0] < Lc + Ls:
+        raise MtsError("rope tables shorter than the sequence")
+    _lib.call("mts_attn_causal_shared_bwd", qkv.data_ptr(), _ptr(cos), _ptr(sin), out_own.data_ptr(), dout_own.data_ptr(),
+              lse_own.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, Lc, Ls, H, hd, scale, _stream())
+    return dqkv
+
+
 def softmax_rows(s, scale, out=None):
     _chk(s, torch.float32, "s")
     if not s.is_contiguous():
@@ -212,10 +251,19 @@ def softmax_rows(s, scale, out=None):
     return out
 
 
-def prompt_gather(ids, emb, wpe, x, *, rep, Lp, L):
-    """Fills x fp32 [B*rep, L, D]: rows <Lp from emb[ids] (+wpe), rows >=Lp zero (+wpe)."""
+def prompt_gather(ids, emb, wpe, x, *, rep, Lp, L, Lc=0, B=None):
+    """Fills x fp32 [B*rep, L, D]: rows <Lp from emb[ids] (+wpe), rows >=Lp zero (+wpe).  Lc > 0: shared-prefix
+    row layout, x fp32 [Lc + B*rep*(L-Lc), D] (B must then be given)."""
     _chk(emb, torch.float32, "emb"); _chk(x, torch.float32, "x")
     D = emb.shape[1]
+    if Lc > 0:
+        _chk(ids, torch.int32, "ids")
+        if not ids.is_contiguous() or ids.shape != (B, Lp) or not x.is_contiguous() or not emb.is_contiguous() \
+                or x.numel() != (Lc + B * rep * (L - Lc)) * D:
+            raise MtsError("prompt_gather (shared prefix): ids [B, Lp] and x [Lc + B*rep*(L-Lc), D] contiguous required")
+        _lib.call("mts_prompt_gather_shared", ids.data_ptr(), emb.data_ptr(), _ptr(wpe), x.data_ptr(), B, rep, Lp, L,
+                  Lc, D, _stream())
+        return x
     B = x.shape[0] // rep
     if Lp > 0:
         _chk(ids, torch.int32, "ids")
@@ -324,6 +372,16 @@ def rope_qk_(qkv, Bp, L, H, hd, rope):
     if not qkv.is_contiguous() or cos.shape[0] < L or cos.shape[1] != hd // 2:
         raise MtsError("rope_qk_: contiguous qkv and [>=L, hd/2] tables required")
     _lib.call("mts_rope_qk", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), Bp, L, H, hd, _stream())
+    return qkv
+
+
+def rope_qk_shared_(qkv, Bp, Lc, Ls, H, hd, rope):
+    """rope_qk_ on the shared-prefix row layout (qkv bf16 [Lc + Bp*Ls, 3*H*hd])."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    cos, sin = rope
+    if not qkv.is_contiguous() or cos.shape[0] < Lc + Ls or cos.shape[1] != hd // 2:
+        raise MtsError("rope_qk_shared_: contiguous qkv and [>=Lc+Ls, hd/2] tables required")
+    _lib.call("mts_rope_qk_shared", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), Bp, Lc, Ls, H, hd, _stream())
     return qkv
 
 

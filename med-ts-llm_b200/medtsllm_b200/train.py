@@ -54,6 +54,8 @@ class _HotPathFn(torch.autograd.Function):
             dout = dout.float()
         B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
         HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
+        Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only
+        Ls, own_off = L - Lc, Lp - Lc   # own rows per sequence; first patch row among them
         mode = m.covariate_mode
         R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
         dm = m.d_model
@@ -96,35 +98,35 @@ class _HotPathFn(torch.autograd.Function):
         g_bds = g_wds = None
         if m.embedding_downsample_mode == "linear":
             g_bds = ops.colsum(dyds)
-            hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D,
+            hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D,
                                                in_off=Lp * D)                  # [D, ceil8(R)]
             g_wds = f32(E, D)
             ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
         wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
         wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
-        dhid = zbf(B * L, D)                                                    # zero for prompt rows
+        dhid = zbf(B * Ls, D)                                                   # zero for prompt rows
         ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
-                 d_bs=L * D, ldd=D, d_off=Lp * D)
+                 d_bs=Ls * D, ldd=D, d_off=own_off * D)
 
         # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
         early = dp.GradBucket([g_wh, g_bh] + ([g_wds, g_bds] if g_wds is not None else [])).launch()
 
         # ---- frozen backbone (dgrad only)
         dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
-                                     lora=m.llm if m.lora_enabled else None)     # fp32 [B*L, D]
+                                     lora=m.llm if m.lora_enabled else None, Lc=Lc)   # fp32 [B*Ls, D]
 
         # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
         if mode in ("concat", "univariate", "independent", "merge-end"):
-            dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=L * D, in_off=Lp * D)   # bf16 [R, D]
+            dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D, in_off=own_off * D)   # bf16 [R, D]
         elif mode == "interleave":
             dxp = bf(R, D)
             for c in range(C):       # feature c owns rows Lp + n*C + c
-                ops.cast_rows(dR, batch=B0, rows=N0, cols=D, ld_in=C * D, in_bs=L * D, in_off=(Lp + c) * D,
+                ops.cast_rows(dR, batch=B0, rows=N0, cols=D, ld_in=C * D, in_bs=Ls * D, in_off=(own_off + c) * D,
                               out=dxp, ld_out=D, out_bs=C * N0 * D, out_off=c * N0 * D)
         else:                        # add / weighted-average: broadcast back over the feature axis
             fw = m.feature_weighting if mode == "weighted-average" else None
             dyf, g_w, g_b = ops.group_reduce_bwd(dR, B0, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
-                                                 x=st["Y"] if fw is not None else None, dout_bs=L * D, dout_off=Lp * D)
+                                                 x=st["Y"] if fw is not None else None, dout_bs=Ls * D, dout_off=own_off * D)
             if fw is not None:
                 g_fw_w, g_fw_b = g_w.view(1, C), g_b.view(1)
             dxp = ops.cast_bf16(dyf.view(R, D))

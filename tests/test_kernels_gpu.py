@@ -521,3 +521,72 @@ def test_swiglu_epilogue_keeps_preactivations_and_norm_bwd_bf16_copy(ops, cuda):
     dx = torch.randn(rows, D, generator=g).to(cuda); dxb = torch.empty(rows, D, device=cuda, dtype=torch.bfloat16)
     ops.rmsnorm_bwd(xx, w, dy, dx, 1e-5, accumulate=True, dx_bf16=dxb)
     assert torch.equal(dxb, dx.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------- shared-prefix row layout
+def _expand_shared(t, Bp, Lc, Ls):
+    """[Lc + Bp*Ls, W] (prefix once, then own rows per sample) -> [Bp*(Lc+Ls), W] plain layout."""
+    W = t.shape[1]
+    return torch.cat([t[:Lc].unsqueeze(0).expand(Bp, Lc, W), t[Lc:].view(Bp, Ls, W)], dim=1).reshape(Bp * (Lc + Ls), W).contiguous()
+
+
+@pytest.mark.parametrize("Bp,Lc,Ls,H,hd", [(3, 128, 64, 2, 128), (4, 37, 12, 3, 64), (2, 16, 100, 2, 64), (5, 130, 33, 1, 128)])
+def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
+    """The prefix rows are stored once; results must equal the plain kernels run on the layout with the
+    prefix repeated in front of every sample (same kernel, same key order: bit-identical forward)."""
+    g = torch.Generator().manual_seed(Lc * 7 + Ls)
+    D, L = H * hd, Lc + Ls
+    M = Lc + Bp * Ls
+    qkv = (torch.randn(M, 3 * D, generator=g) * 0.8).to(cuda, torch.bfloat16)
+    out, lse = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, want_lse=True)
+    qkv_p = _expand_shared(qkv, Bp, Lc, Ls)
+    out_p, lse_p = ops.attn_causal(qkv_p, Bp, L, H, hd, rope=None, want_lse=True)
+    assert torch.equal(_expand_shared(out, Bp, Lc, Ls), out_p)
+    assert torch.equal(lse, lse_p[:, :, Lc:])
+    # backward: gradient only enters through the samples' own rows
+    tabs = _rope_tables(L, hd, cuda)
+    dout = torch.randn(Bp * Ls, D, generator=g).to(cuda, torch.bfloat16)
+    dqkv = ops.attn_causal_shared_bwd(qkv, out[Lc:], dout, lse, Bp, Lc, Ls, H, hd, rope=tabs)
+    dout_p = torch.zeros(Bp, L, D, device=cuda, dtype=torch.bfloat16)
+    dout_p[:, Lc:] = dout.view(Bp, Ls, D)
+    dqkv_p = ops.attn_causal_bwd(qkv_p, out_p, dout_p.view(Bp * L, D), lse_p, Bp, L, H, hd, rope=tabs, pre_roped=True)
+    own = dqkv_p.view(Bp, L, 3 * D)[:, Lc:].reshape(Bp * Ls, 3 * D)
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        assert _rel_l2(dqkv[:, sl], own[:, sl]) < 1e-6, name
+
+
+def test_prompt_gather_and_rope_shared_prefix(ops, cuda):
+    g = torch.Generator().manual_seed(5)
+    B, rep, Lp, Lc, N, D, V = 3, 2, 20, 17, 6, 64, 50
+    L, Ls = Lp + N, Lp + N - Lc
+    ids = torch.randint(0, V, (B, Lp), generator=g, dtype=torch.int32)
+    ids[:, :Lc] = ids[0, :Lc]
+    ids = ids.to(cuda)
+    emb = torch.randn(V, D, generator=g).to(cuda)
+    wpe = torch.randn(L + 3, D, generator=g).to(cuda)
+    for pe in (None, wpe):
+        plain = torch.full((B * rep, L, D), float("nan"), device=cuda)
+        ops.prompt_gather(ids, emb, pe, plain, rep=rep, Lp=Lp, L=L)
+        shared = torch.full((Lc + B * rep * Ls, D), float("nan"), device=cuda)
+        ops.prompt_gather(ids, emb, pe, shared, rep=rep, Lp=Lp, L=L, Lc=Lc, B=B)
+        assert torch.equal(_expand_shared(shared, B * rep, Lc, Ls).view(B * rep, L, D), plain)
+    # RoPE positions: fused GEMM epilogue and the in-place kernel
+    H, hd = 2, 64
+    Dm = H * hd
+    Bp = B * rep
+    M = Lc + Bp * Ls
+    tabs = _rope_tables(L, hd, cuda)
+    a = torch.randn(M, 64, generator=g).to(cuda, torch.bfloat16)
+    w = torch.randn(3 * Dm, 64, generator=g).to(cuda, torch.bfloat16)
+    qkv = torch.empty(M, 3 * Dm, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, qkv, m=M, n=3 * Dm, k=64, epilogue=4, rope=tabs, rope_L=Ls, rope_hd=hd, rope_cols=2 * Dm, rope_prefix=Lc)
+    a_p = _expand_shared(a, Bp, Lc, Ls)
+    qkv_p = torch.empty(Bp * L, 3 * Dm, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a_p, w, qkv_p, m=Bp * L, n=3 * Dm, k=64, epilogue=4, rope=tabs, rope_L=L, rope_hd=hd, rope_cols=2 * Dm)
+    assert torch.equal(_expand_shared(qkv, Bp, Lc, Ls), qkv_p)
+    raw = torch.empty(M, 3 * Dm, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, raw, m=M, n=3 * Dm, k=64)
+    raw_p = _expand_shared(raw, Bp, Lc, Ls)
+    ops.rope_qk_shared_(raw, Bp, Lc, Ls, H, hd, tabs)
+    ops.rope_qk_(raw_p, Bp, L, H, hd, tabs)
+    assert torch.equal(_expand_shared(raw, Bp, Lc, Ls), raw_p)

@@ -341,3 +341,55 @@ def test_long_sequence_falls_back_to_tiled_attention(cuda):
     (ref * w).sum().backward()
     dR, _ = bb.backward(w.to(cuda, torch.bfloat16).view(Bp * L, 256).contiguous(), x_final, stash, Bp, L)
     assert _rel_l2(dR.cpu().view(Bp, L, 256), xr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("name,partial", [("llama_seg_concat", 0), ("gpt2_anomaly_concat", 0), ("llama_forecast_independent", 0),
+                                          ("llama_forecast_interleave", 0), ("gpt2_anomaly_weighted_average", 0),
+                                          ("llama_seg_concat", 21), ("gpt2_forecast_merge_end", 17)])
+def test_shared_prompt_prefix_equals_per_sample_prompts(name, partial, tmp_path, cuda):
+    """In-batch prompt de-duplication (shared-prefix row layout): the leading prompt positions that are the
+    same in every sample are carried once through the backbone.  Output and every adapter gradient must equal
+    the plain per-sample computation (the reference's, models/medtsllm.py:330-351) — the kernels do the same
+    arithmetic per row in the same order, so the forward is compared bit for bit.  `partial` > 0 makes the
+    prompts differ from that position on (per-sample clip descriptions / input statistics)."""
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda, torch.float32)
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    if partial:
+        table = model.prompt_token_ids(inputs).clone()
+        g = torch.Generator().manual_seed(partial)
+        table[:, partial:] = torch.randint(3, model.vocab_size, table[:, partial:].shape, generator=g, dtype=torch.int32)
+        table[1, partial] = table[0, partial] + 1          # the prefix ends exactly here
+        model.prompt_token_ids = lambda _inputs: table
+    res = {}
+    for share in (True, False):
+        model.share_prompt_prefix = share
+        model.eval()
+        model._capture = {}
+        with torch.no_grad():
+            out = model(inputs)
+        cap, model._capture = model._capture, None
+        model.train()
+        model.zero_grad(set_to_none=True)
+        y = model(inputs)
+        wgt = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(cuda)
+        (y * wgt).sum().backward()
+        torch.cuda.synchronize()
+        res[share] = (out, cap, {k: p.grad.clone() for k, p in model.named_parameters()})
+    (o1, c1, g1), (o0, c0, g0) = res[True], res[False]
+    assert c0["shared_prefix"] == 0
+    assert c1["shared_prefix"] == (partial if partial else len(fix["prompt_ids"][0])), c1["shared_prefix"]
+    assert torch.equal(c1["llm_input"], c0["llm_input"])
+    assert torch.equal(c1["llm"], c0["llm"])
+    assert torch.equal(o1, o0)
+    for k in g0:
+        # the backward skips the prefix rows (no trainable ancestor): same sums, fewer zero terms
+        e = _rel_l2(g1[k], g0[k])
+        # structurally zero gradients (key-projection bias, ...: see test_training_step_gradients) hold rounding
+        # noise on both sides -> absolute check against the sibling weight gradient
+        sib = g0.get(k.rsplit(".", 1)[0] + ".weight", g0[k]).abs().max().item()
+        assert e < 2e-3 or (g1[k] - g0[k]).abs().max().item() <= 1e-3 * sib, (k, e)
