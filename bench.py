@@ -166,6 +166,8 @@ def run_ours(args):
 
     if args.per_sample_prompts:
         model.share_prompt_prefix = False
+    if args.no_cuda_graph:
+        model.use_cuda_graph = False
     ids_tab = model.prompt_token_ids(resident)
     Lc = model._shared_prefix_len(ids_tab, w.B, w.seq)      # prompt positions computed once per batch (0 = off)
     rows_per_step = Lc + w.B * (w.seq - Lc)
@@ -283,12 +285,14 @@ def run_ours(args):
             return r
 
         ops.gemm = traced_gemm
+        model.use_cuda_graph = False            # kernel by kernel, so that every GEMM launch is bracketed by events
         try:
             for _ in range(3):
                 step_resident()
             torch.cuda.synchronize()
         finally:
             ops.gemm = real_gemm
+            model.use_cuda_graph = True
         gemm_ms = sum(s.elapsed_time(e) for s, e in ev) / 3
         gemm_flops = sum(fl) / 3
     barrier()
@@ -317,6 +321,7 @@ def run_ours(args):
                                    f"patches={w.n_patches} prompt={Lp} tokens (L={w.seq})",
                        "per_gpu_batch": w.B, "seq_len": w.T, "n_vars": w.C, "tokens_per_step": w.B * w.seq,
                        "backbone_rows_per_step": rows_per_step, "shared_prompt_prefix": Lc,
+                       "cuda_graph": "off" if args.no_cuda_graph else "inference steps replay one captured graph of the whole path",
                        "prompt_sharing": (f"the {Lc} prompt positions that are identical in all {w.B} samples of a batch are "
                                           f"computed once per batch ({rows_per_step} backbone rows instead of {w.B * w.seq}); "
                                           "outputs bit-identical to per-sample prompts, which 'per_sample_prompts' times")
@@ -561,6 +566,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the HuggingFace-on-GPU backbone baseline")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch the inference path kernel by kernel")
     ap.add_argument("--per-sample-prompts", action="store_true",
                     help="disable the shared prompt prefix for the whole run (every sample carries its own prompt rows)")
     ap.add_argument("--profile-step", nargs="?", const="fwd", default=None, choices=["fwd", "train"],

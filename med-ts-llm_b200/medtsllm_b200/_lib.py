@@ -124,8 +124,18 @@ def call(name: str, *args) -> None:
         raise MtsError(f"{name} failed (status {rc}): {msg}")
 
 
+_replayed = 0
+
+
 def launch_count() -> int:
-    return int(load().mts_launch_count())
+    """Kernels launched by the library so far: launches it issued itself (counted in C, including the ones
+    recorded into a CUDA graph at capture time) plus the kernel nodes of every graph replay since."""
+    return int(load().mts_launch_count()) + _replayed
+
+
+def note_replay(n_kernels: int) -> None:
+    global _replayed
+    _replayed += int(n_kernels)
 
 
 def version() -> int:

@@ -264,7 +264,10 @@ def prompt_gather(ids, emb, wpe, x, *, rep, Lp, L, Lc=0, B=None):
         _lib.call("mts_prompt_gather_shared", ids.data_ptr(), emb.data_ptr(), _ptr(wpe), x.data_ptr(), B, rep, Lp, L,
                   Lc, D, _stream())
         return x
-    B = x.shape[0] // rep
+    if B is None:
+        B = x.shape[0] // rep
+    if x.numel() != B * rep * L * D:
+        raise MtsError("prompt_gather: x must hold B*rep*L rows of D")
     if Lp > 0:
         _chk(ids, torch.int32, "ids")
         if not ids.is_contiguous() or ids.shape != (B, Lp):

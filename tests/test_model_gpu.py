@@ -393,3 +393,39 @@ def test_shared_prompt_prefix_equals_per_sample_prompts(name, partial, tmp_path,
         # noise on both sides -> absolute check against the sibling weight gradient
         sib = g0.get(k.rsplit(".", 1)[0] + ".weight", g0[k]).abs().max().item()
         assert e < 2e-3 or (g1[k] - g0[k]).abs().max().item() <= 1e-3 * sib, (k, e)
+
+
+@pytest.mark.parametrize("name", ["llama_seg_concat", "gpt2_anomaly_concat", "llama_forecast_clip_stats"])
+def test_cuda_graph_replay_matches_kernel_by_kernel(name, tmp_path, cuda):
+    """Inference replays a captured CUDA graph once the same (shape, prompt table, weights) key repeats.  Call 1 runs
+    kernel by kernel, call 2 captures, call 3 replays; each must equal the kernel-by-kernel result for ITS input bit
+    for bit, and an optimizer-style in-place weight update must invalidate the graph.  (clip_stats: prompts change
+    with every batch -> never captured.)"""
+    from medtsllm_b200 import _lib
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda, torch.float32).eval()
+    base = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    xs = [base["x_enc"] * (1.0 + 0.1 * i) + 0.3 * i for i in range(4)]
+
+    def run(x, graph):
+        model.use_cuda_graph = graph
+        with torch.no_grad():
+            return model({**base, "x_enc": x}).clone()
+
+    want = [run(x, False) for x in xs]
+    n0 = _lib.launch_count()
+    got = [run(x, True) for x in xs]
+    per_call = (_lib.launch_count() - n0) / len(xs)
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+    dynamic = name == "llama_forecast_clip_stats"
+    assert (model._graph is None) == dynamic
+    assert per_call > 20                                        # replays are counted as launches too
+    with torch.no_grad():
+        model.output_projection.linear.bias.add_(0.25)          # what optimizer.step() does: bumps ._version
+    after = run(xs[3], True)
+    assert torch.equal(after, run(xs[3], False)) and not torch.equal(after, got[3])
