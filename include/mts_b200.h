@@ -99,6 +99,18 @@ int mts_revin_patch_embed_bwd(const float* x, const float* mean, const float* st
 int mts_revin_denorm(float* y, const float* mean, const float* stdev, int B, int T, int C,
                      mts_stream_t stream);
 
+/* GPT4TS front end (BASELINE configs[0]; ref: models/gpt4ts.py:126-138, :151-164, :200-212, :230-242 and
+ * models/layers/embed.py:8-46, 109-131 with x_mark = None): per-(sample, channel) normalisation over time
+ * (mean, sqrt(biased var + eps)), the 3-tap circular TokenEmbedding conv over TIME with the C variables as
+ * in-channels, plus the fixed sinusoid table pe [T, d_model].
+ *   x fp32 [B,T,C]; w_conv fp32 [d_model, C, 3]; mean, stdev fp32 [B, C] out
+ *   mode 0: out_t bf16 [B, d_model, ld_t] (transposed; columns T..ld_t-1 zero) — B operand of the time-axis Linear
+ *   mode 1: out_x fp32 [B, T, D] = embedding, zero-padded to D columns (:212), + wpe[t] (HF GPT-2 position table)
+ * (anomaly_detection needs no front end: its per-time-step "segments" centre the series to exactly zero, :155-164.) */
+int mts_gpt4ts_embed(const float* x, const float* w_conv, const float* pe, const float* wpe, float* mean,
+                     float* stdev, uint16_t* out_t, float* out_x, int B, int T, int C, int d_model, int D,
+                     int ld_t, int mode, float eps, mts_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* K3/K4/K7/K9/K10/K11/K12/K13  tcgen05 GEMM with fused epilogues                              */
 /* ------------------------------------------------------------------------------------------ */

@@ -10,6 +10,8 @@
 // softmax in fp32 registers with quad shuffles.  The big GEMMs are the tcgen05 kernels.
 //
 // Algorithmic work: 4*Bp*H*L*L*hd FLOP (dense; the causal half is skipped in practice).
+#include <algorithm>
+
 #include "mts_internal.h"
 #include "ptx.cuh"
 
@@ -274,44 +276,61 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
-// Forward, short sequences (the whole K and V of one (sample, head) fit in shared memory, L <= ~350
-// at hd = 128): one CTA per (b, h), K/V staged ONCE with cp.async (q/k already rotated by
-// rope_qk_kernel), 8 warps pull 16-query strips from a shared counter, heaviest (latest) strips
-// first.  Key tiles beyond a strip's causal limit are skipped at 16-key granularity.
+// Forward, short sequences (the K and V a CTA needs fit in shared memory, L <= ~350 at hd = 128): K/V
+// staged ONCE with cp.async (q/k already rotated by the qkv GEMM epilogue / rope_qk_kernel), 8 warps pull
+// 16-query strips from a shared counter, heaviest (latest) strips first.  Key tiles beyond a strip's causal
+// limit are skipped at 16-key granularity.
+//
+// Row layouts.  Plain (Lc = 0): sample b owns rows b*L + [0, L); one CTA per (b, h).
+// Shared prefix (Lc > 0): rows [0, Lc) hold ONE copy of the prompt prefix every sample shares (positions
+// 0..Lc-1), rows Lc + b*Ls + t the own token t of sample b at position Lc + t (Ls = L - Lc).  A CTA then
+// serves `spc` consecutive samples of one head: the prefix K/V are staged once for all of them, followed by
+// the samples' own K/V (shared-memory row of key position p of sample i: p if p < Lc, else p + i*Ls — the
+// same formula as the global row, which is why the staging loop is one contiguous copy), and the strips of
+// all spc samples feed the 8 warps.  The first H CTAs of a shared-prefix launch compute the prefix itself
+// (an ordinary causal sequence of Lc positions).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSeqThreads = 256;
 
 template <int HD>
 __global__ void __launch_bounds__(kSeqThreads)
 attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                           float* __restrict__ lse, int L, int Lc, int H, float scale_log2e) {
-  // Shared-prefix layout (Lc > 0): rows [0, Lc) of qkv / out hold ONE copy of the prompt prefix every sample
-  // shares, rows Lc + b*Ls + t (Ls = L - Lc) the own tokens of sample b at positions Lc + t.  Keys are all L
-  // positions, queries only the sample's own Ls tokens.  Lc = 0 is the plain [Bp, L] layout.
+                           float* __restrict__ lse, int Bp, int L_all, int Lc_all, int spc, int rows_alloc, int H,
+                           float scale_log2e) {
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  const int Lp = (L + 63) & ~63;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
-  __nv_bfloat16* Vs = Ks + (size_t)Lp * kPitch;
-  __nv_bfloat16* Qw = Vs + (size_t)Lp * kPitch;           // [8 warps][16][kPitch]
+  __nv_bfloat16* Vs = Ks + (size_t)rows_alloc * kPitch;
+  __nv_bfloat16* Qw = Vs + (size_t)rows_alloc * kPitch;           // [8 warps][16][kPitch]
   int* counter = reinterpret_cast<int*>(Qw + 8 * 16 * kPitch);
 
-  const int bh = blockIdx.x;
-  const int b = bh / H, h = bh - b * H;
+  // job of this CTA: (L keys per sample, of which Lc shared; samples b0 .. b0+nb-1; head h)
+  int L = L_all, Lc = Lc_all, b0, nb, h;
+  float* lse_job = lse;
+  if (Lc_all > 0 && (int)blockIdx.x < H) {          // the prefix as one sequence
+    h = blockIdx.x; L = Lc_all; Lc = 0; b0 = 0; nb = 1;
+  } else {
+    const int j = Lc_all > 0 ? blockIdx.x - H : blockIdx.x;
+    const int grp = j / H;
+    h = j - grp * H;
+    b0 = grp * spc;
+    nb = min(spc, Bp - b0);
+    if (lse && Lc_all > 0) lse_job = lse + (int64_t)H * Lc_all;
+  }
+  const int Ls = L - Lc;
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
-  const int Ls = L - Lc;
-  // row of position p: p (shared prefix) or p + b*Ls (own tokens) -> two bases indexed by position
-  const __nv_bfloat16* pbase = qkv + (int64_t)h * HD;
-  const __nv_bfloat16* qbase = qkv + (int64_t)b * Ls * ld + (int64_t)h * HD;
+  // global row of (sample b, position p): p (p < Lc) or p + b*Ls; shared-memory row of (i = b - b0, p): p or p + i*Ls
+  const __nv_bfloat16* gbase = qkv + (int64_t)h * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
 
   constexpr int kVec = HD / 8;
-  for (int i = threadIdx.x; i < Lp * kVec; i += kSeqThreads) {
+  const int rows_used = Lc + nb * Ls;
+  for (int i = threadIdx.x; i < rows_alloc * kVec; i += kSeqThreads) {
     const int r = i / kVec, c = (i - r * kVec) * 8;
-    if (r < L) {
-      const __nv_bfloat16* src = (r < Lc ? pbase : qbase) + (int64_t)r * ld + c;
+    if (r < rows_used) {
+      const __nv_bfloat16* src = gbase + ((int64_t)r + (r < Lc ? 0 : (int64_t)b0 * Ls)) * ld + c;
       cp_async16(smem_u32(Ks + r * kPitch + c), src + D);
       cp_async16(smem_u32(Vs + r * kPitch + c), src + 2 * D);
     } else {
@@ -324,19 +343,22 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   cp_async_wait<0>();
   __syncthreads();
 
-  const int n_strips = (Ls + 15) >> 4;
+  const int n_strips = (Ls + 15) >> 4;              // per sample
   __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
   while (true) {
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(counter, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= n_strips) break;
-    const int q0 = Lc + (n_strips - 1 - ticket) * 16;   // heaviest strips first (positions, >= Lc)
+    if (ticket >= n_strips * nb) break;
+    const int si = ticket % nb;                                   // sample within the CTA
+    const int q0 = Lc + (n_strips - 1 - ticket / nb) * 16;        // heaviest strips first (positions, >= Lc)
+    const int soff = si * Ls;                                     // shared-memory row offset of own keys
+    const int64_t grow = (int64_t)(b0 + si) * Ls;                 // global row offset of own rows
     // stage this warp's 16 query rows
     for (int i = lane; i < 16 * kVec; i += 32) {
       const int r = i / kVec, c = (i - r * kVec) * 8;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (q0 + r < L) v = *reinterpret_cast<const uint4*>(qbase + (int64_t)(q0 + r) * ld + c);
+      if (q0 + r < L) v = *reinterpret_cast<const uint4*>(gbase + (grow + q0 + r) * ld + c);
       *reinterpret_cast<uint4*>(Qs + r * kPitch + c) = v;
     }
     __syncwarp();
@@ -360,12 +382,13 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         if (j0 + np * 16 > last_row) continue;   // warp-uniform causal skip
+        const int id = lane >> 3;
+        const int kp = j0 + np * 16 + (id >> 1) * 8 + (lane & 7);          // key position of this lane's row
+        const __nv_bfloat16* krow = Ks + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id & 1) * 8;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
-          const int id = lane >> 3;
           uint32_t r0, r1, r2, r3;
-          ldmatrix_x4(smem_u32(Ks + (j0 + np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch + ks * 16 + (id & 1) * 8),
-                      r0, r1, r2, r3);
+          ldmatrix_x4(smem_u32(krow + ks * 16), r0, r1, r2, r3);
           mma_bf16_16816(s[2 * np], qf[ks], r0, r1);
           mma_bf16_16816(s[2 * np + 1], qf[ks], r2, r3);
         }
@@ -417,12 +440,13 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
         pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
         pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
         pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int id = lane >> 3;
+        const int kp = j0 + kk * 16 + (id & 1) * 8 + (lane & 7);
+        const __nv_bfloat16* vrow = Vs + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id >> 1) * 8;
 #pragma unroll
         for (int np = 0; np < HD / 16; ++np) {
-          const int id = lane >> 3;
           uint32_t r0, r1, r2, r3;
-          ldmatrix_x4_trans(smem_u32(Vs + (j0 + kk * 16 + (id & 1) * 8 + (lane & 7)) * kPitch + np * 16 + (id >> 1) * 8),
-                            r0, r1, r2, r3);
+          ldmatrix_x4_trans(smem_u32(vrow + np * 16), r0, r1, r2, r3);
           mma_bf16_16816(o[2 * np], pa, r0, r1);
           mma_bf16_16816(o[2 * np + 1], pa, r2, r3);
         }
@@ -435,7 +459,7 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     }
     const float inv_a = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f;
     const float inv_b = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
-    __nv_bfloat16* obase = out + (int64_t)b * Ls * D + (int64_t)h * HD;
+    __nv_bfloat16* obase = out + grow * D + (int64_t)h * HD;
 #pragma unroll
     for (int nt = 0; nt < HD / 8; ++nt) {
       const int col = nt * 8 + tq * 2;
@@ -444,21 +468,26 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
       if (row_b < L)
         *reinterpret_cast<uint32_t*>(obase + (int64_t)row_b * D + col) = pack_bf16(o[nt][2] * inv_b, o[nt][3] * inv_b);
     }
-    if (lse && tq == 0) {   // lse is [Bp, H, Ls], indexed by the token's place among the sample's own tokens
-      if (row_a < L) lse[(int64_t)bh * Ls + row_a - Lc] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
-      if (row_b < L) lse[(int64_t)bh * Ls + row_b - Lc] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
+    if (lse_job && tq == 0) {   // lse is [samples, H, Ls], indexed by the token's place among the sample's own tokens
+      float* lrow = lse_job + ((int64_t)(b0 + si) * H + h) * Ls - Lc;
+      if (row_a < L) lrow[row_a] = (m_run[0] + log2f(l_run[0])) * 0.6931471805599453f;
+      if (row_b < L) lrow[row_b] = (m_run[1] + log2f(l_run[1])) * 0.6931471805599453f;
     }
     __syncwarp();   // Qs is re-staged by the next strip
   }
 }
 
+// rows of K (and of V) a CTA keeps: the positions of spc samples sharing Lc of their L; the 64-key tiles of the
+// last sample may overrun its L positions into a zero tail
+static int seq_rows_alloc(int L, int Lc, int spc) { return ((L + 63) & ~63) + (spc - 1) * (L - Lc); }
+
 template <int HD>
-static size_t seq_smem_bytes(int L) {
-  const int Lp = (L + 63) & ~63;
-  return (size_t)(2 * Lp + 8 * 16) * (HD + 8) * 2 + 16;
+static size_t seq_smem_bytes(int L, int Lc = 0, int spc = 1) {
+  return (size_t)(2 * seq_rows_alloc(L, Lc, spc) + 8 * 16) * (HD + 8) * 2 + 16;
 }
 
-// Sequence-resident forward over Bp samples of L positions whose first Lc are a shared prefix stored once.
+// Sequence-resident forward over Bp samples of L positions whose first Lc are a shared prefix stored once
+// (Lc > 0: the launch also computes the prefix rows themselves; lse = [H, Lc] followed by [Bp, H, Ls]).
 template <int HD>
 static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H,
                            float scale, cudaStream_t stream) {
@@ -469,9 +498,20 @@ static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int B
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn seq)", e);
     seq_attr_done = true;
   }
-  ks<<<Bp * H, kSeqThreads, seq_smem_bytes<HD>(L), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, L, Lc, H,
-      scale * 1.4426950408889634f);
+  // samples per CTA: enough 16-query strips to occupy the 8 warps, as far as shared memory allows
+  int spc = 1;
+  if (Lc > 0) {
+    const int n_strips = (L - Lc + 15) / 16;
+    const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);
+    while (spc < want && seq_smem_bytes<HD>(L, Lc, spc + 1) <= 220 * 1024) ++spc;
+  }
+  const int groups = (Bp + spc - 1) / spc;
+  const int grid = (groups + (Lc > 0 ? 1 : 0)) * H;
+  const int rows_alloc = std::max(seq_rows_alloc(L, Lc, spc), Lc > 0 ? seq_rows_alloc(Lc, 0, 1) : 0);
+  const size_t smem = (size_t)(2 * rows_alloc + 8 * 16) * (HD + 8) * 2 + 16;
+  ks<<<grid, kSeqThreads, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, Bp, L, Lc, spc,
+      rows_alloc, H, scale * 1.4426950408889634f);
   count_launch();
   return check_launch("attn_causal_fwd_seq_kernel");
 }
@@ -1050,10 +1090,8 @@ static int launch_attn_shared(const uint16_t* qkv, uint16_t* out, float* lse, in
   const int L = Lc + Ls;
   if (seq_smem_bytes<HD>(L) > 220 * 1024)
     return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared: %d positions do not fit in shared memory", L);
-  // the prefix as one ordinary sequence of Lc positions, then every sample's own tokens
-  int rc_ = launch_attn_seq<HD>(qkv, out, lse, 1, Lc, 0, H, scale, stream);
-  if (rc_) return rc_;
-  return launch_attn_seq<HD>(qkv, out, lse ? lse + (int64_t)H * Lc : nullptr, Bp, L, Lc, H, scale, stream);
+  // one launch: H CTAs for the prefix as an ordinary sequence of Lc positions, the rest for the samples' own tokens
+  return launch_attn_seq<HD>(qkv, out, lse, Bp, L, Lc, H, scale, stream);
 }
 
 template <int HD>

@@ -169,9 +169,80 @@ static int fe_check(const char* name, int B, int T, int C, int P, int S) {
   return MTS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GPT4TS front end (ref: models/gpt4ts.py:126-138, :151-164, :200-212; models/layers/embed.py:29-46, 109-131):
+// per-(sample, channel) normalisation over time, then per time step the 3-tap circular TokenEmbedding conv over
+// TIME (in-channels = the C variables) + the fixed sinusoid table, written in the layout the next step wants:
+//   mode 0  bf16, transposed [B, d_model, ld_t] — the K-major B operand of the time-axis Linear (forecasting)
+//   mode 1  fp32 [B, T, D] residual-stream rows: embedding (+ zero pad to D) + wpe[t]   (segmentation tasks)
+// grid (chunks, B): every CTA loads and normalises its sample's whole window (it is tiny) and emits a chunk of
+// time steps.  HBM bytes per sample: 4*T*C read, 2*T*d_model (mode 0) or 4*T*D (mode 1) written.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gpt4ts_embed_kernel(const float* __restrict__ x, const float* __restrict__ w_conv, const float* __restrict__ pe,
+                    const float* __restrict__ wpe, float* __restrict__ mean, float* __restrict__ stdev,
+                    __nv_bfloat16* __restrict__ out_t, float* __restrict__ out_x, int T, int C, int d_model, int D,
+                    int ld_t, int mode, float eps) {
+  extern __shared__ __align__(16) float fe_smem[];
+  float* xs = fe_smem;
+  float* s_mean = xs + ((T * C + 3) & ~3);
+  float* s_std = s_mean + C;
+  const int b = blockIdx.y;
+  load_and_normalise(x + (int64_t)b * T * C, xs, s_mean, s_std, T, C, eps, nullptr, nullptr);
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { mean[b * C + c] = s_mean[c]; stdev[b * C + c] = s_std[c]; }
+  const int per = (T + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(T, t0 + per);
+  const int width = mode == 0 ? d_model : D;
+  for (int d = threadIdx.x; d < width; d += blockDim.x) {
+    const float* wd = w_conv + (int64_t)d * C * 3;     // [d][c][k]
+    for (int t = t0; t < t1; ++t) {
+      float acc = 0.f;
+      if (d < d_model) {
+        const float* xp = xs + (t == 0 ? T - 1 : t - 1) * C;
+        const float* xc = xs + t * C;
+        const float* xn = xs + (t == T - 1 ? 0 : t + 1) * C;
+        for (int c = 0; c < C; ++c) acc += wd[c * 3] * xp[c] + wd[c * 3 + 1] * xc[c] + wd[c * 3 + 2] * xn[c];
+        acc += pe[(int64_t)t * d_model + d];
+      }
+      if (mode == 0) out_t[((int64_t)b * d_model + d) * ld_t + t] = __float2bfloat16_rn(acc);
+      else           out_x[((int64_t)b * T + t) * D + d] = acc + wpe[(int64_t)t * D + d];
+    }
+  }
+  if (mode == 0 && blockIdx.x == 0 && ld_t > T)   // zero the row padding (the GEMM's TMA extent stops at T anyway)
+    for (int i = threadIdx.x; i < d_model * (ld_t - T); i += blockDim.x)
+      out_t[((int64_t)b * d_model + i / (ld_t - T)) * ld_t + T + i % (ld_t - T)] = __float2bfloat16_rn(0.f);
+}
+
 }  // namespace mts
 
 using namespace mts;
+
+extern "C" int mts_gpt4ts_embed(const float* x, const float* w_conv, const float* pe, const float* wpe, float* mean,
+                                float* stdev, uint16_t* out_t, float* out_x, int B, int T, int C, int d_model, int D,
+                                int ld_t, int mode, float eps, mts_stream_t s) {
+  if (!x || !mean || !stdev || !w_conv || !pe || B <= 0 || T <= 0 || C <= 0 || d_model <= 0 || mode < 0 || mode > 1)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gpt4ts_embed: bad args");
+  if (mode == 0 && (!out_t || ld_t < T))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gpt4ts_embed: mode 0 needs out_t and ld_t >= T");
+  if (mode == 1 && (!out_x || !wpe || D < d_model))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gpt4ts_embed: mode 1 needs out_x, wpe and D >= d_model");
+  const size_t smem = sizeof(float) * ((((size_t)T * C + 3) & ~(size_t)3) + 2 * (size_t)C);
+  if (smem > 200 * 1024) return set_error(MTS_ERR_UNSUPPORTED, "mts_gpt4ts_embed: window too large");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(gpt4ts_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(gpt4ts embed)", e);
+    smem_set = 200 * 1024;
+  }
+  int chunks = (2 * num_sms() + B - 1) / B;
+  if (chunks > T) chunks = T;
+  if (chunks < 1) chunks = 1;
+  gpt4ts_embed_kernel<<<dim3(chunks, B), 256, smem, (cudaStream_t)s>>>(
+      x, w_conv, pe, wpe, mean, stdev, reinterpret_cast<__nv_bfloat16*>(out_t), out_x, T, C, d_model, D, ld_t, mode, eps);
+  count_launch();
+  return check_launch("gpt4ts_embed_kernel");
+}
 
 extern "C" int mts_revin_patch_embed(const float* x, const float* w_conv, float* mean, float* stdev,
                                      uint16_t* out_bf16, float* out_f32, int B, int T, int C, int P,

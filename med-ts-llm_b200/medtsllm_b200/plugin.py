@@ -29,6 +29,11 @@ def register(reference_root: str | None = None):
     from .model import MedTsLLM
     models.model_lookup["medtsllm"] = MedTsLLM
     models.model_lookup["timellm"] = MedTsLLM
+    if os.environ.get("MTS_REGISTER_GPT4TS", "0") == "1":
+        # opt-in: medtsllm_b200.GPT4TS runs inference only (evaluation of a trained run / `--test`); the
+        # reference's Trainer.train() on it raises, loudly
+        from .gpt4ts import GPT4TS
+        models.model_lookup["gpt4ts"] = GPT4TS
     return models.model_lookup
 
 

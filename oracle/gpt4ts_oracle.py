@@ -56,11 +56,17 @@ def gpt4ts_forward(x_enc, params, gpt2_sd, spec, *, training: bool = False, retu
     stages = {}
     if task not in ("forecasting", "anomaly_detection", "semantic_segmentation", "segmentation"):
         raise ValueError("Task name is not valid")          # models/gpt4ts.py:103-104 (e.g. "reconstruction")
-    xn, mean, stdev = instance_norm(x_enc)
     D = gpt2_sd["wpe.weight"].shape[1]
-    if task == "anomaly_detection":                          # :151-177: the normalised series IS the embedding
-        enc = xn
+    if task == "anomaly_detection":
+        # :151-164.  The "segments" the statistics are taken over have length seg_num = 1 (:155-159), i.e. every
+        # time step is its own segment: mean = x, the centred series is identically ZERO, stdev = sqrt(0 + 1e-5).
+        # The GPT-2 therefore sees only its position table and the prediction is dec * sqrt(1e-5) + x (:172-175).
+        mean = x_enc
+        xc = x_enc - mean
+        stdev = torch.sqrt(torch.var(xc.unsqueeze(2), dim=2, unbiased=False) + 1e-5)
+        enc = xc / stdev
     else:
+        xn, mean, stdev = instance_norm(x_enc)
         enc = data_embedding(xn, params["enc_embedding.value_embedding.tokenConv.weight"])
         if task == "forecasting":                            # :137: Linear along time, T -> T + pred
             enc = F.linear(enc.permute(0, 2, 1), params["predict_linear_pre.weight"],

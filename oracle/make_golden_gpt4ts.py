@@ -67,7 +67,7 @@ def main():
             g = torch.Generator().manual_seed(12)
             for n, p in hf.named_parameters():
                 if "ln" in n or n.endswith(".bias"):
-                    p.add_((torch.randn(p.shape, generator=g) * 0.05).to(torch.bfloat16).float())
+                    p.copy_((p + torch.randn(p.shape, generator=g) * 0.05).to(torch.bfloat16).float())
         (tmp / "gpt2").mkdir()
         hf.save_pretrained(str(tmp / "gpt2"))
         os.chdir(tmp)

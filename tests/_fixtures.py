@@ -110,3 +110,33 @@ def run_oracle(fix, training=False, prompt_ids=None):
     sd = {k: v.float() for k, v in fix["backbone_state"].items()}
     return O.medtsllm_forward(fix["inputs"]["x_enc"], prompt_ids or fix["prompt_ids"], fix["adapters"], sd,
                               oracle_spec(fix), training=training, return_stages=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPT4TS
+GPT4TS_CASES = ["gpt4ts_forecast_etth1", "gpt4ts_anomaly", "gpt4ts_semseg", "gpt4ts_segmentation"]
+
+
+def load_gpt4ts_backbone():
+    """Backbone shared by the GPT4TS fixtures (tests/golden/gpt4ts_backbone.pt, made by
+    oracle/make_golden_gpt4ts.py): HF config + the state of the blocks GPT4TS keeps, bf16-representable."""
+    return torch.load(GOLDEN / "gpt4ts_backbone.pt", weights_only=False)
+
+
+def gpt4ts_spec(fix, bb) -> dict:
+    cfg = fix["config"]
+    return dict(task=cfg["task"], pred_len=cfg["pred_len"], d_ff=cfg["models"]["gpt4ts"]["d_ff"],
+                gpt_layers=cfg["models"]["gpt4ts"]["gpt_layers"], n_heads=bb["hf_config"]["n_head"],
+                eps=bb["hf_config"]["layer_norm_epsilon"], n_classes=fix["dataset"]["n_classes"],
+                seg_mode=cfg["tasks"]["segmentation"]["mode"])
+
+
+def gpt4ts_hf_model(bb, n_layers):
+    """HF GPT2Model holding the fixture backbone (wte is unused by GPT4TS and not stored: left at its random init)."""
+    import transformers
+    d = dict(bb["hf_config"])
+    d.pop("model_type", None); d.pop("transformers_version", None)
+    d["n_layer"] = n_layers
+    model = transformers.GPT2Model(transformers.GPT2Config(**d))
+    res = model.load_state_dict({k: v.float() for k, v in bb["state"].items()}, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("wte") for k in res.missing_keys), res
+    return model.eval()

@@ -119,3 +119,24 @@ def test_plugin_registers_into_reference_model_lookup(tmp_path):
         assert list(model.state_dict().keys()) == list(fix["adapters"].keys())
     finally:
         models.model_lookup.clear(); models.model_lookup.update(original)
+
+
+def test_gpt4ts_surface_matches_reference_names():
+    """Constructor / parameter names of medtsllm_b200.GPT4TS against the state captured from the unmodified
+    models/gpt4ts.py (tests/golden/gpt4ts_*.pt); CPU tensors are refused (no fallback)."""
+    import pytest
+    from _fixtures import Cfg, Dataset, GPT4TS_CASES, load_case
+    from medtsllm_b200._lib import MtsError
+    from medtsllm_b200.backbone import BackboneSpec, KernelBackbone
+    from medtsllm_b200.gpt4ts import GPT4TS
+    bb = KernelBackbone(BackboneSpec("gpt2", 768, 2, 12, 768, 64, 1e-5), "cpu")     # never run: surface only
+    for name in GPT4TS_CASES:
+        fix = load_case(name)
+        model = GPT4TS(Cfg(fix["config"]), Dataset(fix["dataset"]), backbone=bb)
+        own = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.endswith("position_embedding.pe")}
+        assert own == {k: tuple(v.shape) for k, v in fix["params"].items()}, name
+        with pytest.raises(MtsError):
+            model({"x_enc": fix["inputs"]["x_enc"]})
+    cfg = dict(load_case("gpt4ts_anomaly")["config"]); cfg["task"] = "reconstruction"
+    with pytest.raises(ValueError):      # models/gpt4ts.py:103-104: listed in supported_tasks, rejected by forward
+        GPT4TS(Cfg(cfg), Dataset(fix["dataset"]), backbone=bb)({"x_enc": fix["inputs"]["x_enc"]})

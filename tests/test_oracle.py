@@ -102,3 +102,34 @@ def test_gelu_new_and_rope_tables():
     cos, sin = O.rope_tables(7, 8)
     assert cos.shape == (7, 4) and torch.allclose(cos[0], torch.ones(4)) and torch.allclose(sin[0], torch.zeros(4))
     assert math.isclose(cos[1, 0].item(), math.cos(1.0), rel_tol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ GPT4TS
+from _fixtures import GPT4TS_CASES, gpt4ts_spec, load_gpt4ts_backbone  # noqa: E402
+from oracle import gpt4ts_oracle as G  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GPT4TS_CASES)
+def test_gpt4ts_oracle_matches_reference_golden(name):
+    """oracle/gpt4ts_oracle.py against tensors captured from the unmodified models/gpt4ts.py (BASELINE configs[0] =
+    gpt4ts_forecast_etth1: seq_len = pred_len = 96, 7 variables, batch 8)."""
+    fix = load_case(name)
+    bb = load_gpt4ts_backbone()
+    sd = {k: v.float() for k, v in bb["state"].items()}
+    spec = gpt4ts_spec(fix, bb)
+    out, st = G.gpt4ts_forward(fix["inputs"]["x_enc"], fix["params"], sd, spec, return_stages=True)
+    g = fix["stages"]
+    D = sd["wpe.weight"].shape[1]
+    emb = torch.nn.functional.pad(st["embedding"], (0, D - st["embedding"].shape[-1]))
+    torch.testing.assert_close(emb, g["gpt2_input"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(st["gpt2"], g["gpt2"], rtol=1e-4, atol=5e-5)
+    assert out.shape == g["output"].shape
+    torch.testing.assert_close(out, g["output"], rtol=1e-4, atol=5e-5)
+    assert _rel_l2(out, g["output"]) < 2e-5
+    out_t = G.gpt4ts_forward(fix["inputs"]["x_enc"], fix["params"], sd, spec, training=True)
+    torch.testing.assert_close(out_t, g["output_train"], rtol=1e-4, atol=5e-5)
+
+
+def test_gpt4ts_rejects_reconstruction_like_the_reference():
+    with pytest.raises(ValueError):
+        G.gpt4ts_forward(torch.zeros(1, 8, 2), {}, {}, dict(task="reconstruction"))
