@@ -575,9 +575,12 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* 
 }
 
 // C(16 x 64) = A(16 x HD, rows [arow0, +16) of As) * B^T, B = 64 rows of Bs (both [row][HD+8] bf16)
+// Rows of Bs at or beyond `thr` (relative to Bs) lie `shift` rows further down: the shared-prefix layout keeps the
+// own keys of sample i of a CTA i*Ls rows behind the prefix keys (thr = INT_MAX: plain contiguous rows).
 template <int HD>
 __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* As, int arow0,
-                                         const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4) {
+                                         const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4,
+                                         int thr = 0x7fffffff, int shift = 0) {
   constexpr int kPitch = HD + 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
@@ -589,9 +592,10 @@ __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* 
     for (int np = 0; np < 4; ++np) {
       if (np < g_lo || np >= g_hi) continue;   // warp-uniform: 16-column groups outside the causal range
       const int id = lane >> 3;
+      int brow = np * 16 + (id >> 1) * 8 + (lane & 7);
+      brow += brow >= thr ? shift : 0;
       uint32_t r0, r1, r2, r3;
-      ldmatrix_x4(smem_u32(Bs + (np * 16 + (id >> 1) * 8 + (lane & 7)) * kPitch + ks * 16 + (id & 1) * 8),
-                  r0, r1, r2, r3);
+      ldmatrix_x4(smem_u32(Bs + brow * kPitch + ks * 16 + (id & 1) * 8), r0, r1, r2, r3);
       mma_bf16_16816(c[2 * np], a, r0, r1);
       mma_bf16_16816(c[2 * np + 1], a, r2, r3);
     }
@@ -601,7 +605,8 @@ __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* 
 // acc(16 x HD) += P(16 x 64, fp32 C-fragments) * B, B = 64 rows of Bs ([row][HD+8] bf16)
 template <int HD>
 __device__ __forceinline__ void mma_p_b(float (&acc)[HD / 8][4], const float (&pm)[8][4],
-                                        const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4) {
+                                        const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4,
+                                        int thr = 0x7fffffff, int shift = 0) {
   constexpr int kPitch = HD + 8;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
@@ -614,9 +619,10 @@ __device__ __forceinline__ void mma_p_b(float (&acc)[HD / 8][4], const float (&p
 #pragma unroll
     for (int np = 0; np < HD / 16; ++np) {
       const int id = lane >> 3;
+      int brow = kk * 16 + (id & 1) * 8 + (lane & 7);
+      brow += brow >= thr ? shift : 0;
       uint32_t r0, r1, r2, r3;
-      ldmatrix_x4_trans(smem_u32(Bs + (kk * 16 + (id & 1) * 8 + (lane & 7)) * kPitch + np * 16 + (id >> 1) * 8),
-                        r0, r1, r2, r3);
+      ldmatrix_x4_trans(smem_u32(Bs + brow * kPitch + np * 16 + (id >> 1) * 8), r0, r1, r2, r3);
       mma_bf16_16816(acc[2 * np], pa, r0, r1);
       mma_bf16_16816(acc[2 * np + 1], pa, r2, r3);
     }
@@ -837,37 +843,37 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                        const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                        const float* __restrict__ lse, const float* __restrict__ delta,
-                       __nv_bfloat16* __restrict__ dqkv, int L, int Lc, int H, float scale) {
-  // Lc > 0: shared-prefix layout as in attn_causal_fwd_seq_kernel.  qkv holds every row (prefix rows once,
-  // then Ls = L - Lc own rows per sample); dout / lse / delta / dqkv hold the samples' own rows only
-  // ([Bp*Ls, ...]): the prefix has no trainable ancestor, so no gradient is produced for it.
+                       __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int Lc, int spc, int rows_alloc, int H,
+                       float scale) {
+  // Lc > 0: shared-prefix layout as in attn_causal_fwd_seq_kernel (a CTA serves spc samples of one head; the prefix
+  // K/V are staged once).  qkv holds every row (prefix rows once, then Ls = L - Lc own rows per sample); dout / lse /
+  // delta / dqkv hold the samples' own rows only ([Bp*Ls, ...]): the prefix has no trainable ancestor, so no gradient
+  // is produced for it.
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  const int Lp = (L + 63) & ~63;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
-  __nv_bfloat16* Vs = Ks + (size_t)Lp * kPitch;
-  __nv_bfloat16* Qw = Vs + (size_t)Lp * kPitch;            // [8 warps][16][kPitch]
+  __nv_bfloat16* Vs = Ks + (size_t)rows_alloc * kPitch;
+  __nv_bfloat16* Qw = Vs + (size_t)rows_alloc * kPitch;    // [8 warps][16][kPitch]
   __nv_bfloat16* dOw = Qw + 8 * 16 * kPitch;               // [8 warps][16][kPitch]
   int* counter = reinterpret_cast<int*>(dOw + 8 * 16 * kPitch);
 
-  const int bh = blockIdx.x;
-  const int b = bh / H, h = bh - b * H;
+  const int grp = blockIdx.x / H, h = blockIdx.x - grp * H;
+  const int b0 = grp * spc, nb = min(spc, Bp - b0);
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
   const int Ls = L - Lc;
-  const __nv_bfloat16* pbase = qkv + (int64_t)h * HD;                           // indexed by position < Lc
-  const __nv_bfloat16* qbase = qkv + (int64_t)b * Ls * ld + (int64_t)h * HD;    // indexed by position >= Lc
-  const __nv_bfloat16* dobase = dout + (int64_t)b * Ls * D + (int64_t)h * HD;   // indexed by position - Lc
+  const __nv_bfloat16* gbase = qkv + (int64_t)h * HD;      // row of (sample b, position p): p (p < Lc) or p + b*Ls
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
 
   {
     constexpr int kVec = HD / 8;
-    for (int i = threadIdx.x; i < Lp * kVec; i += kSeqThreads) {
+    const int rows_used = Lc + nb * Ls;
+    for (int i = threadIdx.x; i < rows_alloc * kVec; i += kSeqThreads) {
       const int r = i / kVec, c = (i - r * kVec) * 8;
-      if (r < L) {
-        const __nv_bfloat16* src = (r < Lc ? pbase : qbase) + (int64_t)r * ld + c;
+      if (r < rows_used) {
+        const __nv_bfloat16* src = gbase + ((int64_t)r + (r < Lc ? 0 : (int64_t)b0 * Ls)) * ld + c;
         cp_async16(smem_u32(Ks + r * kPitch + c), src + D);
         cp_async16(smem_u32(Vs + r * kPitch + c), src + 2 * D);
       } else {
@@ -881,23 +887,27 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
   cp_async_wait<0>();
   __syncthreads();
 
-  const int n_strips = (Ls + 15) >> 4;
+  const int n_strips = (Ls + 15) >> 4;                      // per sample
   __nv_bfloat16* Qs = Qw + warp * 16 * kPitch;
   __nv_bfloat16* dOs = dOw + warp * 16 * kPitch;
   while (true) {
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(counter, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= n_strips) break;
-    const int q0 = Lc + (n_strips - 1 - ticket) * 16;      // positions
-    stage_strip<HD>(Qs, qbase, ld, q0, L, lane);
-    stage_strip<HD>(dOs, dobase, D, q0 - Lc, Ls, lane);
+    if (ticket >= n_strips * nb) break;
+    const int si = ticket % nb;
+    const int b = b0 + si;
+    const int soff = si * Ls;                               // shared-memory row offset of this sample's own keys
+    const int q0 = Lc + (n_strips - 1 - ticket / nb) * 16;  // positions
+    const int64_t bh = (int64_t)b * H + h;
+    stage_strip<HD>(Qs, gbase + (int64_t)b * Ls * ld, ld, q0, L, lane);
+    stage_strip<HD>(dOs, dout + (int64_t)b * Ls * D + (int64_t)h * HD, D, q0 - Lc, Ls, lane);
     __syncwarp();
     const int row_a = q0 + g, row_b = row_a + 8;
-    const float lse_a = row_a < L ? lse[(int64_t)bh * Ls + row_a - Lc] * 1.4426950408889634f : INFINITY;
-    const float lse_b = row_b < L ? lse[(int64_t)bh * Ls + row_b - Lc] * 1.4426950408889634f : INFINITY;
-    const float del_a = row_a < L ? delta[(int64_t)bh * Ls + row_a - Lc] : 0.f;
-    const float del_b = row_b < L ? delta[(int64_t)bh * Ls + row_b - Lc] : 0.f;
+    const float lse_a = row_a < L ? lse[bh * Ls + row_a - Lc] * 1.4426950408889634f : INFINITY;
+    const float lse_b = row_b < L ? lse[bh * Ls + row_b - Lc] * 1.4426950408889634f : INFINITY;
+    const float del_a = row_a < L ? delta[bh * Ls + row_a - Lc] : 0.f;
+    const float del_b = row_b < L ? delta[bh * Ls + row_b - Lc] : 0.f;
     float dq[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
@@ -905,8 +915,8 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
     for (int j0 = 0; j0 <= last_row; j0 += 64) {
       const int g_hi = min(4, (last_row - j0) / 16 + 1);
       float s[8][4], dp[8][4];
-      mma_a_bt<HD>(s, Qs, 0, Ks + j0 * kPitch, lane, 0, g_hi);
-      mma_a_bt<HD>(dp, dOs, 0, Vs + j0 * kPitch, lane, 0, g_hi);
+      mma_a_bt<HD>(s, Qs, 0, Ks + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
+      mma_a_bt<HD>(dp, dOs, 0, Vs + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -917,7 +927,7 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
           s[nt][e] = pv * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * scale;
         }
       }
-      mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi);
+      mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
     }
     // dqkv rows are the samples' own rows: row of position p = b*Ls + p - Lc (store_grad_rows indexes by position)
     store_grad_rows<HD>(dq, dqkv + ((int64_t)b * Ls - Lc) * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq, rope_cos, rope_sin);
@@ -1016,6 +1026,11 @@ static size_t seq_bwd_smem_bytes(int L) {
   const int Lp = (L + 63) & ~63;
   return (size_t)(2 * Lp + 2 * 8 * 16) * (HD + 8) * 2 + (size_t)2 * Lp * 4 + 16;
 }
+// dQ kernel: K/V rows of spc samples sharing Lc of their L positions + Q / dO strip staging
+template <int HD>
+static size_t seq_dq_smem_bytes(int L, int Lc, int spc) {
+  return (size_t)(2 * seq_rows_alloc(L, Lc, spc) + 2 * 8 * 16) * (HD + 8) * 2 + 16;
+}
 
 template <int HD>
 static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
@@ -1053,7 +1068,7 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
       const size_t smem = seq_bwd_smem_bytes<HD>(L);
       sq<<<Bp * H, kSeqThreads, smem, stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, 0, H, scale);
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, 0, 1, seq_rows_alloc(L, 0, 1), H, scale);
       count_launch();
       rc_ = check_launch("attn_bwd_dq_seq_kernel");
       if (rc_) return rc_;
@@ -1118,10 +1133,16 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   count_launch();
   int rc_ = check_launch("attn_bwd_delta_kernel");
   if (rc_) return rc_;
-  // dQ of the own tokens: keys = prefix + own
-  sq<<<Bp * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L), stream>>>(
+  // dQ of the own tokens: keys = prefix + own; spc samples per CTA (enough strips for the 8 warps, if they fit)
+  int spc = 1;
+  {
+    const int n_strips = (Ls + 15) / 16;
+    const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);
+    while (spc < want && seq_dq_smem_bytes<HD>(L, Lc, spc + 1) <= 220 * 1024) ++spc;
+  }
+  sq<<<((Bp + spc - 1) / spc) * H, kSeqThreads, seq_dq_smem_bytes<HD>(L, Lc, spc), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), L, Lc, H, scale);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, L, Lc, spc, seq_rows_alloc(L, Lc, spc), H, scale);
   count_launch();
   rc_ = check_launch("attn_bwd_dq_seq_kernel");
   if (rc_) return rc_;
