@@ -141,3 +141,25 @@ class LoraAdapters(nn.Module):
         import os
         os.makedirs(os.path.dirname(str(path)) or ".", exist_ok=True)
         save_file(tensors, str(path))
+
+    def load_pretrained(self, path):
+        """Inverse of save_pretrained: reads the A/B pairs back from `<name>-lora.safetensors` (the reference saves
+        them, loggers/base_logger.py:42-43, but `BaseTask.from_run_id` never restores them, tasks/base.py:283-306 —
+        a maintainer calls `trainer.model.llm.load_pretrained(path)` after it).  Strict: every pair must be present
+        with the right shape."""
+        from safetensors.torch import load_file
+        tensors = load_file(str(path))
+        nt = len(self.targets)
+        with torch.no_grad():
+            for i in range(len(self.A) // nt):
+                for t, name in enumerate(self.targets):
+                    mod = {"q": "self_attn.q_proj", "v": "self_attn.v_proj", "c_attn": "attn.c_attn"}[name]
+                    prefix = ("base_model.model.layers." if self.kind == "llama" else "base_model.model.h.") + f"{i}.{mod}"
+                    for which, plist in (("lora_A", self.A), ("lora_B", self.B)):
+                        src = tensors[f"{prefix}.{which}.weight"]
+                        dst = plist[self.index(i, t)]
+                        if src.shape != dst.shape:
+                            raise ValueError(f"{prefix}.{which}: shape {tuple(src.shape)} != {tuple(dst.shape)}")
+                        dst.copy_(src.to(dst.device, dst.dtype))      # in place: bumps ._version -> bf16 caches refresh
+        return sorted(tensors)
+

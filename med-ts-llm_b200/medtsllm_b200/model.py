@@ -95,7 +95,7 @@ class _LLMHandle:
         self.config = config
 
     def save_pretrained(self, path, *a, **k):
-        raise MtsError("LoRA adapters are not implemented in medtsllm_b200 yet")
+        raise MtsError("model.llm.save_pretrained is only meaningful with lora.enabled (loggers/base_logger.py:42-43)")
 
 
 class MedTsLLM(nn.Module):
@@ -209,7 +209,10 @@ class MedTsLLM(nn.Module):
         llm_cfg = _get(mc, "llm")
         self.llm_enabled = _get(llm_cfg, "enabled")
         if not self.llm_enabled:
-            raise NotImplementedError("llm.enabled = false (llm_replacement MLP) is outside the accelerated path")
+            # (the reference builds an `llm_replacement` MLP for this flag, models/medtsllm.py:103-109, but never calls
+            # it: what the flag really does is skip the freeze at :227-233, i.e. fine-tune the whole LLM)
+            raise NotImplementedError("llm.enabled = false leaves the whole backbone trainable (models/medtsllm.py:227-233); "
+                                      "backbone weight gradients are outside the accelerated path")
         self.llm_id = _get(llm_cfg, "llm")
         self.llm_layers = _get(llm_cfg, "llm_layers")
         if _get(llm_cfg, "load_in_4bit") or _get(llm_cfg, "load_in_8bit"):
@@ -371,11 +374,19 @@ class MedTsLLM(nn.Module):
             insert, s = f"feature {d}", ""
             xs = xs[:, :, d]
         with torch.no_grad():
-            mins = torch.min(xs, dim=1).values.tolist()
-            maxs = torch.max(xs, dim=1).values.tolist()
-            meds = torch.median(xs.float(), dim=1).values.tolist()
-            trends = (xs.diff(dim=1).sum(dim=1) > 0).tolist()
-            lags = _calcute_lags(xs.float(), self.n_lags).tolist()
+            # same torch reductions as the reference (:477-481); its five `.tolist()` device syncs become one read-back
+            mins, maxs = torch.min(xs, dim=1).values, torch.max(xs, dim=1).values
+            meds = torch.median(xs.float(), dim=1).values
+            trends = xs.diff(dim=1).sum(dim=1) > 0
+            lags = _calcute_lags(xs.float(), self.n_lags)                 # [B, n_lags]
+            B = xs.size(0)
+            packed = torch.cat([t.reshape(B, -1).double() for t in (mins, maxs, meds, trends, lags)], dim=1).cpu()
+            w = mins.reshape(B, -1).shape[1]
+            shape = list(mins.shape[1:])
+            unpack = lambda k: packed[:, k * w:(k + 1) * w].reshape([B] + shape)      # noqa: E731
+            mins, maxs, meds = (unpack(k).to(xs.dtype).tolist() for k in range(3))
+            trends = unpack(3).bool().tolist()
+            lags = packed[:, 4 * w:].long().tolist()
         return [
             f"Input statistics ({insert}): min value{s} = {fmt_float(mins[b])}, max value{s} = {fmt_float(maxs[b])}, "
             f"median value{s} = {fmt_float(meds[b])}, the trend of input is {fmt_trend(trends[b])}, "

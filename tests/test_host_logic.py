@@ -140,3 +140,23 @@ def test_gpt4ts_surface_matches_reference_names():
     cfg = dict(load_case("gpt4ts_anomaly")["config"]); cfg["task"] = "reconstruction"
     with pytest.raises(ValueError):      # models/gpt4ts.py:103-104: listed in supported_tasks, rejected by forward
         GPT4TS(Cfg(cfg), Dataset(fix["dataset"]), backbone=bb)({"x_enc": fix["inputs"]["x_enc"]})
+
+
+def test_lora_save_load_round_trip(tmp_path):
+    """`model.llm.save_pretrained` (what loggers/base_logger.py:42-43 calls) and its inverse."""
+    import torch
+    from medtsllm_b200.backbone import BackboneSpec
+    from medtsllm_b200.lora import LoraAdapters
+    spec = BackboneSpec("llama", 64, 2, 2, 128, 100, 1e-5)
+    a = LoraAdapters(spec, rank=4, alpha=8, rslora=True, init=True)
+    with torch.no_grad():
+        for p in a.params():
+            p.copy_(torch.randn(p.shape))
+    path = tmp_path / "run" / "latest-lora.safetensors"
+    a.save_pretrained(path)
+    b = LoraAdapters(spec, rank=4, alpha=8, rslora=True, init=True)
+    v0 = [p._version for p in b.params()]
+    keys = b.load_pretrained(path)
+    assert len(keys) == len(a.params())
+    for pa, pb, v in zip(a.params(), b.params(), v0):
+        assert torch.equal(pa, pb) and pb._version > v
