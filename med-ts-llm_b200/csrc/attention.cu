@@ -940,48 +940,60 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                         const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                         const float* __restrict__ lse, const float* __restrict__ delta,
-                        __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+                        __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int spc, int H, float scale) {
+  // A CTA serves spc consecutive samples of one head (short own-token runs would otherwise leave most of the 8
+  // warps without a key strip): sample i keeps its Q / dO / lse / delta rows at [i*Lp, i*Lp + L).
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   const int Lp = (L + 63) & ~63;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);
-  __nv_bfloat16* dOs = Qs + (size_t)Lp * kPitch;
-  __nv_bfloat16* Kw = dOs + (size_t)Lp * kPitch;           // [8 warps][16][kPitch]
+  __nv_bfloat16* dOs = Qs + (size_t)spc * Lp * kPitch;
+  __nv_bfloat16* Kw = dOs + (size_t)spc * Lp * kPitch;     // [8 warps][16][kPitch]
   __nv_bfloat16* Vw = Kw + 8 * 16 * kPitch;
   float* lse_s = reinterpret_cast<float*>(Vw + 8 * 16 * kPitch);
-  float* del_s = lse_s + Lp;
-  int* counter = reinterpret_cast<int*>(del_s + Lp);
+  float* del_s = lse_s + spc * Lp;
+  int* counter = reinterpret_cast<int*>(del_s + spc * Lp);
 
-  const int bh = blockIdx.x;
-  const int b = bh / H, h = bh - b * H;
+  const int grp = blockIdx.x / H, h = blockIdx.x - grp * H;
+  const int b0 = grp * spc, nb = min(spc, Bp - b0);
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
-  const __nv_bfloat16* qbase = qkv + (int64_t)b * L * ld + (int64_t)h * HD;
-  const __nv_bfloat16* dobase = dout + (int64_t)b * L * D + (int64_t)h * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
 
-  stage_rows_async<HD>(Qs, qbase, ld, L, Lp, threadIdx.x, kSeqThreads);
-  stage_rows_async<HD>(dOs, dobase, D, L, Lp, threadIdx.x, kSeqThreads);
+  for (int si = 0; si < nb; ++si) {
+    const int64_t b = b0 + si;
+    stage_rows_async<HD>(Qs + (size_t)si * Lp * kPitch, qkv + b * L * ld + (int64_t)h * HD, ld, L, Lp, threadIdx.x, kSeqThreads);
+    stage_rows_async<HD>(dOs + (size_t)si * Lp * kPitch, dout + b * L * D + (int64_t)h * HD, D, L, Lp, threadIdx.x, kSeqThreads);
+  }
   cp_async_commit();
-  for (int i = threadIdx.x; i < Lp; i += kSeqThreads) {
-    lse_s[i] = i < L ? lse[(int64_t)bh * L + i] * 1.4426950408889634f : INFINITY;
-    del_s[i] = i < L ? delta[(int64_t)bh * L + i] : 0.f;
+  for (int i = threadIdx.x; i < nb * Lp; i += kSeqThreads) {
+    const int si = i / Lp, r = i - si * Lp;
+    const int64_t bh = (int64_t)(b0 + si) * H + h;
+    lse_s[i] = r < L ? lse[bh * L + r] * 1.4426950408889634f : INFINITY;
+    del_s[i] = r < L ? delta[bh * L + r] : 0.f;
   }
   if (threadIdx.x == 0) *counter = 0;
   cp_async_wait<0>();
   __syncthreads();
 
-  const int n_strips = (L + 15) >> 4;
+  const int n_strips = (L + 15) >> 4;           // per sample
   __nv_bfloat16* Ks = Kw + warp * 16 * kPitch;
   __nv_bfloat16* Vs = Vw + warp * 16 * kPitch;
   while (true) {
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(counter, 1);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= n_strips) break;
-    const int k0 = ticket * 16;                 // earliest keys see the most queries: heaviest first
+    if (ticket >= n_strips * nb) break;
+    const int si = ticket % nb;
+    const int k0 = (ticket / nb) * 16;          // earliest keys see the most queries: heaviest first
+    const int64_t b = b0 + si;
+    const __nv_bfloat16* qbase = qkv + b * L * ld + (int64_t)h * HD;
+    const __nv_bfloat16* Qb = Qs + (size_t)si * Lp * kPitch;
+    const __nv_bfloat16* dOb = dOs + (size_t)si * Lp * kPitch;
+    const float* lse_b = lse_s + si * Lp;
+    const float* del_b = del_s + si * Lp;
     stage_strip<HD>(Ks, qbase + D, ld, k0, L, lane);
     stage_strip<HD>(Vs, qbase + 2 * D, ld, k0, L, lane);
     __syncwarp();
@@ -997,8 +1009,8 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       const int g_lo = max(0, (k0 - i0) / 16);
       const int g_hi = min(4, (L - 1 - i0) / 16 + 1);
       float st[8][4], dpt[8][4];                 // rows = keys, cols = queries
-      mma_a_bt<HD>(st, Ks, 0, Qs + i0 * kPitch, lane, g_lo, g_hi);
-      mma_a_bt<HD>(dpt, Vs, 0, dOs + i0 * kPitch, lane, g_lo, g_hi);
+      mma_a_bt<HD>(st, Ks, 0, Qb + i0 * kPitch, lane, g_lo, g_hi);
+      mma_a_bt<HD>(dpt, Vs, 0, dOb + i0 * kPitch, lane, g_lo, g_hi);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -1006,15 +1018,15 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
           const int qrow = i0 + nt * 8 + tq * 2 + (e & 1);
           const int key = (e < 2) ? key_a : key_b;
           const bool dead = key > qrow || key >= L || qrow >= L || (nt >> 1) < g_lo || (nt >> 1) >= g_hi;
-          const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_s[min(qrow, Lp - 1)]);
+          const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_b[min(qrow, Lp - 1)]);
           st[nt][e] = pv;
-          dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_s[min(qrow, Lp - 1)]) * scale;
+          dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_b[min(qrow, Lp - 1)]) * scale;
         }
       }
-      mma_p_b<HD>(dv, st, dOs + i0 * kPitch, lane, g_lo, g_hi);
-      mma_p_b<HD>(dk, dpt, Qs + i0 * kPitch, lane, g_lo, g_hi);
+      mma_p_b<HD>(dv, st, dOb + i0 * kPitch, lane, g_lo, g_hi);
+      mma_p_b<HD>(dk, dpt, Qb + i0 * kPitch, lane, g_lo, g_hi);
     }
-    __nv_bfloat16* dbase = dqkv + (int64_t)b * L * ld + (int64_t)h * HD;
+    __nv_bfloat16* dbase = dqkv + b * L * ld + (int64_t)h * HD;
     store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, L, tq, rope_cos, rope_sin);
     store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, L, tq, nullptr, nullptr);
     __syncwarp();
@@ -1022,9 +1034,18 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 }
 
 template <int HD>
-static size_t seq_bwd_smem_bytes(int L) {
-  const int Lp = (L + 63) & ~63;
+static size_t seq_bwd_smem_bytes(int L, int spc = 1) {
+  const int Lp = spc * ((L + 63) & ~63);
   return (size_t)(2 * Lp + 2 * 8 * 16) * (HD + 8) * 2 + (size_t)2 * Lp * 4 + 16;
+}
+// samples per CTA of the dK/dV kernel: enough 16-key strips for the 8 warps, as far as shared memory allows
+template <int HD>
+static int seq_dkv_spc(int Bp, int L) {
+  const int n_strips = (L + 15) / 16;
+  const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);
+  int spc = 1;
+  while (spc < want && seq_bwd_smem_bytes<HD>(L, spc + 1) <= 220 * 1024) ++spc;
+  return spc;
 }
 // dQ kernel: K/V rows of spc samples sharing Lc of their L positions + Q / dO strip staging
 template <int HD>
@@ -1072,9 +1093,10 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
       count_launch();
       rc_ = check_launch("attn_bwd_dq_seq_kernel");
       if (rc_) return rc_;
-      skv<<<Bp * H, kSeqThreads, smem, stream>>>(
+      const int spc = seq_dkv_spc<HD>(Bp, L);
+      skv<<<((Bp + spc - 1) / spc) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L, spc), stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, scale);
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, spc, H, scale);
       count_launch();
       return check_launch("attn_bwd_dkv_seq_kernel");
     }
@@ -1149,10 +1171,11 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   // dK / dV of the own tokens only (queries = own tokens; the log-sum-exp already covers the prefix keys):
   // the plain kernel on the own rows, RoPE tables shifted to position Lc
   const int half = HD / 2;
-  skv<<<Bp * H, kSeqThreads, seq_bwd_smem_bytes<HD>(Ls), stream>>>(
+  const int spc_kv = seq_dkv_spc<HD>(Bp, Ls);
+  skv<<<((Bp + spc_kv - 1) / spc_kv) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(Ls, spc_kv), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv) + (int64_t)Lc * 3 * D, rc ? rc + (int64_t)Lc * half : nullptr,
       rs ? rs + (int64_t)Lc * half : nullptr, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv_own), Ls, H, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, Ls, spc_kv, H, scale);
   count_launch();
   return check_launch("attn_bwd_dkv_seq_kernel");
 }
