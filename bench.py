@@ -351,6 +351,109 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def gpt4ts_cpu_baseline(w, layers, x, n_cpu: int = 5):
+    """The oracle restatement of the reference's models/gpt4ts.py on all host cores, full batch (the config the
+    reference itself runs on CPU)."""
+    from oracle import gpt4ts_oracle as G
+    s = w.backbone
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    rnd = lambda *shape: torch.randn(*shape, generator=g) * 0.02          # noqa: E731
+    D, I = s.hidden, s.inter
+    sd = {"wpe.weight": rnd(s.max_pos, D), "ln_f.weight": torch.ones(D), "ln_f.bias": torch.zeros(D)}
+    for i in range(layers):
+        pfx = f"h.{i}."
+        sd.update({pfx + "attn.c_attn.weight": rnd(D, 3 * D), pfx + "attn.c_attn.bias": torch.zeros(3 * D),
+                   pfx + "attn.c_proj.weight": rnd(D, D), pfx + "attn.c_proj.bias": torch.zeros(D),
+                   pfx + "mlp.c_fc.weight": rnd(D, I), pfx + "mlp.c_fc.bias": torch.zeros(I),
+                   pfx + "mlp.c_proj.weight": rnd(I, D), pfx + "mlp.c_proj.bias": torch.zeros(D),
+                   pfx + "ln_1.weight": torch.ones(D), pfx + "ln_1.bias": torch.zeros(D),
+                   pfx + "ln_2.weight": torch.ones(D), pfx + "ln_2.bias": torch.zeros(D)})
+    params = {"enc_embedding.value_embedding.tokenConv.weight": rnd(768, w.C, 3) * 10,
+              "predict_linear_pre.weight": rnd(w.T + w.pred, w.T), "predict_linear_pre.bias": torch.zeros(w.T + w.pred),
+              "out_layer.weight": rnd(w.C, 768), "out_layer.bias": torch.zeros(w.C)}
+    ospec = dict(task="forecasting", pred_len=w.pred, d_ff=768, gpt_layers=layers, n_heads=s.heads, eps=s.eps)
+    with torch.no_grad():
+        G.gpt4ts_forward(x, params, sd, ospec)
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            G.gpt4ts_forward(x, params, sd, ospec)
+        dt = (time.perf_counter() - t0) / n_cpu
+    return {"value": round(w.B / dt, 2), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"oracle restatement of models/gpt4ts.py (plain PyTorch fp32, {cores} threads), full batch of {w.B}, "
+                      f"{n_cpu} timed forwards after 1 warm-up; {dt * 1e3:.1f} ms per forward", "s_per_step": round(dt, 4)}
+
+
+def run_gpt4ts(args):
+    """--workload etth1_gpt4ts: medtsllm_b200.GPT4TS on BASELINE configs[0]'s shape (ETTh1 forecasting, seq_len = pred_len
+    = 96, 7 variables, batch 8, the first 6 blocks of a GPT-2-small; random-init weights, synthetic windows) next to the
+    oracle restatement of the reference's models/gpt4ts.py on the host cores — the config the reference itself runs on CPU."""
+    from medtsllm_b200 import _lib
+    from medtsllm_b200.backbone import BackboneSpec, KernelBackbone
+    from medtsllm_b200.gpt4ts import GPT4TS
+    from medtsllm_b200.synthetic import WORKLOADS, AttrDict, SyntheticDataset, make_inputs
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    w = WORKLOADS["etth1_gpt4ts"]
+    layers = 6
+    s = w.backbone
+    spec = BackboneSpec("gpt2", s.hidden, layers, s.heads, s.inter, 64, s.eps, max_pos=s.max_pos)   # wte is unused
+    backbone = KernelBackbone.random_init(spec, dev, seed=0)
+    cfg = {"task": "forecasting", "model": "gpt4ts", "history_len": w.T, "pred_len": w.pred, "training": {"dropout": 0.0},
+           "setup": {"dtype": "float32"}, "tasks": {"segmentation": {"mode": "boundary-prediction"}},
+           "models": {"gpt4ts": {"d_ff": 768, "d_model": 768, "gpt_layers": layers, "train_mlp": False,
+                                 "patching": {"patch_len": 1, "stride": 1}}}}
+    torch.manual_seed(0)
+    model = GPT4TS(AttrDict(cfg), SyntheticDataset(w), backbone=backbone).to(dev, torch.float32).eval()
+    host = make_inputs(w, seed=1234, pin=True)
+    resident = host["x_enc"].to(dev)
+    with torch.no_grad():
+        out_host = torch.empty(model({"x_enc": resident}).shape).pin_memory()
+
+    def step_resident():
+        with torch.no_grad():
+            model({"x_enc": resident})
+
+    def step_e2e():
+        with torch.no_grad():
+            y = model({"x_enc": host["x_enc"].to(dev, non_blocking=True)})
+            out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    cpu = None if args.no_cpu_baseline else gpt4ts_cpu_baseline(w, layers, host["x_enc"].clone())
+    line = {"metric": METRIC, "value": round(w.B / (ms * 1e-3), 2), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"etth1_gpt4ts: GPT4TS.forward (eval, forecasting), GPT-2-small first {layers} blocks random-init, "
+                                   f"B={w.B} T={w.T} pred={w.pred} C={w.C} ({w.T + w.pred} tokens per window)",
+                       "cuda_graph": "inference steps replay one captured graph", "l2_policy": "launch-latency bound: "
+                       f"{launches // max(args.steps, 1)} kernels of a few microseconds per step"},
+            "e2e": {"value": round(w.B / (ms_e2e * 1e-3), 2), "unit": "samples/s", "h2d_bytes_per_step": host["x_enc"].numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e, 4)},
+            "gpu_launches": int(launches), "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def hf_gpu_backbone(w, dev, steps: int = 3):
     """The reference's own backbone call on this GPU: HuggingFace `transformers` (the reference's third-party
     backbone, models/medtsllm.py:175-185) with eager attention (:159-160), fp32 weights (`setup.dtype = mixed`,
@@ -543,7 +646,11 @@ def run_reference(args):
     w = WORKLOADS[args.workload]
     # bounded: the whole --steps/--warmup run must end within a few minutes
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    cpu = cpu_baseline(args.workload, steps=steps, warmup=warmup)
+    if args.workload == "etth1_gpt4ts":
+        from medtsllm_b200.synthetic import make_inputs
+        cpu = gpt4ts_cpu_baseline(w, 6, make_inputs(w)["x_enc"], n_cpu=steps)
+    else:
+        cpu = cpu_baseline(args.workload, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "samples/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup,
@@ -574,6 +681,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "etth1_gpt4ts":
+        run_gpt4ts(args)
     else:
         run_ours(args)
 

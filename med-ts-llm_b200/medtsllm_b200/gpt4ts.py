@@ -17,6 +17,7 @@ Linear, KernelBackbone for the GPT-2 blocks, mts_revin_denorm for the de-normali
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -24,6 +25,7 @@ import torch.nn as nn
 from . import _lib, ops
 from ._lib import BIAS_M, BIAS_N, EPI_RESID_ADD, MtsError
 from .backbone import KernelBackbone
+from .graph import GraphReplay
 from .model import _get
 
 
@@ -125,6 +127,8 @@ class GPT4TS(nn.Module):
             object.__setattr__(self, "_hf_model", hf)
         self.device = None
         self._w_cache: dict[str, tuple] = {}
+        self.use_cuda_graph = os.environ.get("MTS_CUDA_GRAPH", "1") != "0"      # see graph.GraphReplay
+        self._graph = GraphReplay()
 
     def _apply(self, fn, *args, **kwargs):
         super()._apply(fn, *args, **kwargs)
@@ -163,6 +167,13 @@ class GPT4TS(nn.Module):
         x = x.contiguous()
         B, T, C = x.shape
         assert T == self.seq_len and C == self.enc_in
+        if not self.use_cuda_graph:
+            return self._forward_impl(x)
+        key = (tuple(x.shape), x.device.index, self.training, tuple((p._version, p.data_ptr()) for p in self.parameters()))
+        return self._graph.run(key, x, self._forward_impl)
+
+    def _forward_impl(self, x):
+        B, T, C = x.shape
         bb = self._backbone
         D, dev = bb.spec.hidden, x.device
         if self.d_model > D or self.d_ff > D or C > D:

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import BIAS_M, BIAS_N, EPI_RESID_ADD, MtsError
-from ._lib import launch_count as _lib_launch_count, note_replay as _lib_note_replay
+from .graph import GraphReplay
 from .backbone import BackboneSpec, KernelBackbone, spec_from_hf_config
 
 os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
@@ -195,8 +195,7 @@ class MedTsLLM(nn.Module):
         # inference replays a captured CUDA graph of the whole path once the same (shape, prompt table, weights)
         # has been seen twice in a row (MTS_CUDA_GRAPH=0 / `model.use_cuda_graph = False`: launch kernel by kernel)
         self.use_cuda_graph = os.environ.get("MTS_CUDA_GRAPH", "1") != "0"
-        self._graph = None         # {"key", "graph", "x", "out", "ids"}
-        self._graph_seen = None    # (key, ids) of the previous eager call
+        self._graph = GraphReplay()
         self._capture = None       # tests: dict filled with per-stage tensors
         self._ids_cache = None     # (prompt parts, host id table, device id table)
         self._prompt_cache: dict[str, list[int]] = {}
@@ -555,30 +554,7 @@ class MedTsLLM(nn.Module):
         params = list(self.parameters()) + (self.llm.params() if self.lora_enabled else [])
         key = (tuple(x_enc.shape), x_enc.device.index, self.training, id(ids), self.share_prompt_prefix,
                tuple((p._version, p.data_ptr()) for p in params))
-        g = self._graph
-        if g is not None and g["key"] == key:
-            g["x"].copy_(x_enc)
-            g["graph"].replay()
-            _lib_note_replay(g["launches"])
-            return g["out"].clone()
-        if self._graph_seen is None or self._graph_seen[0] != key:
-            # first sighting: run kernel by kernel (this also refreshes the weight / prototype / id caches);
-            # holding `ids` keeps its id() unique while the key is remembered
-            self._graph_seen = (key, ids)
-            return self._predict_eager(inputs, ids)
-        # second sighting in a row: capture
-        self._graph = None
-        static = dict(inputs)
-        static["x_enc"] = x_enc.clone()
-        graph = torch.cuda.CUDAGraph()
-        n0 = _lib_launch_count()
-        with torch.cuda.graph(graph):
-            out = self._predict_eager(static, ids)
-        # (capturing records the launches without running them; the counter then follows the replays)
-        self._graph = {"key": key, "graph": graph, "x": static["x_enc"], "out": out, "ids": ids,
-                       "launches": _lib_launch_count() - n0}
-        graph.replay()
-        return out.clone()
+        return self._graph.run(key, x_enc, lambda xs: self._predict_eager({**inputs, "x_enc": xs}, ids), hold=ids)
 
     def _predict_eager(self, inputs, ids=None):
         out = self._forward_impl(inputs, None, ids)

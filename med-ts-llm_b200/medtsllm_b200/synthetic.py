@@ -30,6 +30,7 @@ class Workload:
     covariate_mode: str = "concat"
     description: str = ""
     prompt_len: int = 128
+    lora_rank: int = 0          # > 0: LoRA fine-tuning of the backbone's q/v (Llama) or c_attn (GPT-2) projections
 
     @property
     def n_patches(self):
@@ -51,9 +52,12 @@ WORKLOADS = {
     # configs[3]
     "psm_gpt2_medium": Workload("psm_gpt2_medium", GPT2_MEDIUM, "anomaly_detection", B=64, T=100, pred=100, C=25,
                                 description="PSM is a server machine dataset from eBay."),
-    # configs[4] (without LoRA: not implemented yet)
+    # configs[4]: LoRA fine-tune (rank 8, alpha 16, rsLoRA; the shipped configs carry no LoRA block of their own)
     "ventilator_llama2_7b": Workload("ventilator_llama2_7b", LLAMA2_7B, "forecasting", B=16, T=336, pred=96, C=2,
-                                     description="Ventilator pressure and flow waveforms."),
+                                     description="Ventilator pressure and flow waveforms.", lora_rank=8),
+    # configs[0]'s shape for medtsllm_b200.GPT4TS (bench.py --workload etth1_gpt4ts): GPT-2-small, 6 blocks
+    "etth1_gpt4ts": Workload("etth1_gpt4ts", GPT2_SMALL, "forecasting", B=8, T=96, pred=96, C=7, d_ff=768,
+                             description="ETTh1", prompt_len=0),
     # tiny shape for smoke tests / CPU-side checks
     "mini_llama": Workload("mini_llama", LLAMA_MINI, "forecasting", B=4, T=96, pred=24, C=3, prompt_len=32,
                            description="Synthetic mini workload."),
@@ -74,6 +78,8 @@ def experiment_config(w: Workload, llm_path: str = "<injected>") -> dict:
             "prompting": {"dataset": True, "task": True, "clip": False, "input_stats": False, "examples": False,
                           "input_stats_dim": 0, "input_stats_select": "all"},
             "llm": {"enabled": True, "llm": llm_path, "llm_layers": -1, "load_in_4bit": False, "load_in_8bit": False},
+            **({"lora": {"enabled": True, "layers": "auto", "rank": w.lora_rank, "alpha": 16, "init": True,
+                         "dropout": 0.0, "rslora": True}} if w.lora_rank else {}),
         }},
     }
 
