@@ -235,6 +235,15 @@ int mts_attn_causal_shared_bwd(const uint16_t* qkv, const float* rope_cos, const
                                const uint16_t* out_own, const uint16_t* dout_own, const float* lse_own,
                                float* delta, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
                                float scale, mts_stream_t stream);
+/* Backward for ALL rows of the shared-prefix layout (something trainable sits inside the backbone: LoRA): the
+ * prefix rows receive gradient through the K / V they contribute to every sample's attention.  out, dout bf16
+ * [Lc + Bp*Ls, H*hd]; lse, delta fp32 [H*Lc + Bp*H*Ls] laid out as mts_attn_causal_shared writes lse; dqkv bf16
+ * [Lc + Bp*Ls, 3*H*hd].  dK / dV of the prefix keys sum over every query row of the batch (one CTA per head and
+ * 128 keys sweeps them; no atomics). */
+int mts_attn_causal_shared_bwd_full(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                                    const uint16_t* out, const uint16_t* dout, const float* lse, float* delta,
+                                    uint16_t* dqkv, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                                    mts_stream_t stream);
 int mts_rope_qk_shared(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int Bp, int Lc, int Ls,
                        int H, int hd, mts_stream_t stream);
 

@@ -1033,6 +1033,134 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-prefix layout, dK / dV of the PREFIX keys (needed when something trainable sits inside the backbone:
+// LoRA).  Every query of the batch attends to the prefix — the prefix's own Lc queries causally, the Bp*Ls own
+// tokens of all samples without a mask — and in the shared-prefix row layout all those queries are simply the
+// rows [0, Lc + Bp*Ls) of qkv.  One CTA per (head, block of 128 prefix keys): each of the 8 warps owns a 16-key
+// strip (K, V strip staged once) and sweeps over all query rows in chunks of 64 (Q, dO, lse, delta of the next
+// chunk are fetched with cp.async while the current one is in the tensor cores).  No atomics.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kSeqThreads)
+attn_bwd_dkv_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                           const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
+                           const float* __restrict__ lse, const float* __restrict__ delta,
+                           __nv_bfloat16* __restrict__ dqkv, int Bp, int Lc, int Ls, int H, float scale) {
+  // lse / delta: [H, Lc] for the prefix rows followed by [Bp, H, Ls] for the own rows
+  constexpr int kPitch = HD + 8;
+  constexpr int kVec = HD / 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attn_smem);     // [2 stages][64][kPitch]
+  __nv_bfloat16* dOs = Qs + 2 * 64 * kPitch;                            // [2 stages][64][kPitch]
+  __nv_bfloat16* Kw = dOs + 2 * 64 * kPitch;                            // [8 warps][16][kPitch]
+  __nv_bfloat16* Vw = Kw + 8 * 16 * kPitch;
+  float* lse_s = reinterpret_cast<float*>(Vw + 8 * 16 * kPitch);        // [2][64]
+  float* del_s = lse_s + 2 * 64;
+
+  const int kblocks = (Lc + 127) / 128;
+  const int h = blockIdx.x / kblocks, kb = blockIdx.x - h * kblocks;
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const int M = Lc + Bp * Ls;
+  const __nv_bfloat16* qbase = qkv + (int64_t)h * HD;
+  const __nv_bfloat16* dobase = dout + (int64_t)h * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+  const float* lse_own = lse + (int64_t)H * Lc;
+  const float* del_own = delta + (int64_t)H * Lc;
+
+  auto stage_chunk = [&](int stage, int i0) {
+    __nv_bfloat16* q = Qs + stage * 64 * kPitch;
+    __nv_bfloat16* d = dOs + stage * 64 * kPitch;
+    for (int i = threadIdx.x; i < 64 * kVec; i += kSeqThreads) {
+      const int r = i / kVec, c = (i - r * kVec) * 8;
+      if (i0 + r < M) {
+        cp_async16(smem_u32(q + r * kPitch + c), qbase + (int64_t)(i0 + r) * ld + c);
+        cp_async16(smem_u32(d + r * kPitch + c), dobase + (int64_t)(i0 + r) * D + c);
+      } else {
+        *reinterpret_cast<uint4*>(q + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(d + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (threadIdx.x < 64) {
+      const int row = i0 + threadIdx.x;
+      float l = INFINITY, dl = 0.f;
+      if (row < Lc) {
+        l = lse[(int64_t)h * Lc + row]; dl = delta[(int64_t)h * Lc + row];
+      } else if (row < M) {
+        const int o = row - Lc, b = o / Ls, t = o - b * Ls;
+        l = lse_own[((int64_t)b * H + h) * Ls + t]; dl = del_own[((int64_t)b * H + h) * Ls + t];
+      }
+      lse_s[stage * 64 + threadIdx.x] = l * 1.4426950408889634f;
+      del_s[stage * 64 + threadIdx.x] = dl;
+    }
+  };
+
+  const int k0 = kb * 128 + warp * 16;            // this warp's key strip (positions = rows)
+  __nv_bfloat16* Ks = Kw + warp * 16 * kPitch;
+  __nv_bfloat16* Vs = Vw + warp * 16 * kPitch;
+  stage_strip<HD>(Ks, qbase + D, ld, k0, Lc, lane);
+  stage_strip<HD>(Vs, qbase + 2 * D, ld, k0, Lc, lane);
+  // prefix queries before this CTA's first key cannot attend to it: start at the 64-row chunk holding that key
+  const int i_begin = (kb * 128 / 64) * 64;
+  stage_chunk(0, i_begin);
+  cp_async_commit();
+
+  const int key_a = k0 + g, key_b = key_a + 8;
+  float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+  int stage = 0;
+  for (int i0 = i_begin; i0 < M; i0 += 64, stage ^= 1) {
+    if (i0 + 64 < M) stage_chunk(stage ^ 1, i0 + 64);     // (that buffer was released by the barrier ending the previous turn)
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (k0 < Lc) {
+      const __nv_bfloat16* Qb = Qs + stage * 64 * kPitch;
+      const __nv_bfloat16* dOb = dOs + stage * 64 * kPitch;
+      const float* lse_b = lse_s + stage * 64;
+      const float* del_b = del_s + stage * 64;
+      const int g_hi = min(4, (M - 1 - i0) / 16 + 1);
+      float st[8][4], dpt[8][4];                 // rows = keys, cols = queries
+      mma_a_bt<HD>(st, Ks, 0, Qb, lane, 0, g_hi);
+      mma_a_bt<HD>(dpt, Vs, 0, dOb, lane, 0, g_hi);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qi = nt * 8 + tq * 2 + (e & 1);
+          const int qrow = i0 + qi;
+          const int key = (e < 2) ? key_a : key_b;
+          // prefix queries are causal, own tokens (rows >= Lc, positions >= Lc) see every prefix key
+          const bool dead = key >= Lc || qrow >= M || (qrow < Lc && key > qrow) || (nt >> 1) >= g_hi;
+          const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_b[qi]);
+          st[nt][e] = pv;
+          dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_b[qi]) * scale;
+        }
+      }
+      mma_p_b<HD>(dv, st, dOb, lane, 0, g_hi);
+      mma_p_b<HD>(dk, dpt, Qb, lane, 0, g_hi);
+    }
+    __syncthreads();                              // everyone is done with this stage before it is refilled
+  }
+  if (k0 < Lc) {
+    __nv_bfloat16* dbase = dqkv + (int64_t)h * HD;
+    store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, Lc, tq, rope_cos, rope_sin);
+    store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, Lc, tq, nullptr, nullptr);
+  }
+}
+
+template <int HD>
+static size_t dkv_prefix_smem_bytes() {
+  return (size_t)(4 * 64 + 2 * 8 * 16) * (HD + 8) * 2 + (size_t)4 * 64 * 4;
+}
+
 template <int HD>
 static size_t seq_bwd_smem_bytes(int L, int spc = 1) {
   const int Lp = spc * ((L + 63) & ~63);
@@ -1180,9 +1308,67 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   return check_launch("attn_bwd_dkv_seq_kernel");
 }
 
+// Full backward on the shared-prefix layout: gradients for the prefix rows too (out / dout / dqkv hold ALL rows,
+// lse / delta = [H, Lc] followed by [Bp, H, Ls]).
+template <int HD>
+static int launch_attn_shared_bwd_full(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
+                                       const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp,
+                                       int Lc, int Ls, int H, float scale, cudaStream_t stream) {
+  const int D = H * HD;
+  // own rows: dQ (prefix + own keys) and dK / dV of the own keys
+  int rc_ = launch_attn_shared_bwd<HD>(qkv, rc, rs, out + (int64_t)Lc * D, dout + (int64_t)Lc * D, lse + (int64_t)H * Lc,
+                                       delta + (int64_t)H * Lc, dqkv + (int64_t)Lc * 3 * D, Bp, Lc, Ls, H, scale, stream);
+  if (rc_) return rc_;
+  // prefix rows: delta, then dQ of the prefix as one causal sequence of Lc positions
+  const int64_t nwarps = (int64_t)Lc * H;
+  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, Lc, H, HD, nwarps);
+  count_launch();
+  rc_ = check_launch("attn_bwd_delta_kernel");
+  if (rc_) return rc_;
+  auto sq = attn_bwd_dq_seq_kernel<HD>;
+  sq<<<H, kSeqThreads, seq_dq_smem_bytes<HD>(Lc, 0, 1), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv), 1, Lc, 0, 1, seq_rows_alloc(Lc, 0, 1), H, scale);
+  count_launch();
+  rc_ = check_launch("attn_bwd_dq_seq_kernel");
+  if (rc_) return rc_;
+  // dK / dV of the prefix keys: every query row of the batch contributes
+  auto kp = attn_bwd_dkv_prefix_kernel<HD>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_prefix_smem_bytes<HD>());
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd prefix)", e);
+    attr = true;
+  }
+  kp<<<H * ((Lc + 127) / 128), kSeqThreads, dkv_prefix_smem_bytes<HD>(), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, Lc, Ls, H, scale);
+  count_launch();
+  return check_launch("attn_bwd_dkv_prefix_kernel");
+}
+
 }  // namespace mts
 
 using namespace mts;
+
+extern "C" int mts_attn_causal_shared_bwd_full(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                                               const uint16_t* out, const uint16_t* dout, const float* lse, float* delta,
+                                               uint16_t* dqkv, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                                               mts_stream_t s) {
+  if (!qkv || !out || !dout || !lse || !delta || !dqkv || Bp <= 0 || Lc <= 0 || Ls <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd_full: bad args");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd_full: rope_cos and rope_sin go together");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_shared_bwd_full: misaligned pointer");
+  switch (hd) {
+    case 64: return launch_attn_shared_bwd_full<64>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    case 128: return launch_attn_shared_bwd_full<128>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, Lc, Ls, H, scale, (cudaStream_t)s);
+    default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd_full: head dim %d (supported: 64, 128)", hd);
+  }
+}
 
 extern "C" int mts_attn_causal_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
                                       int hd, float scale, mts_stream_t s) {

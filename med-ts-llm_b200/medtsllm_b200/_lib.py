@@ -77,6 +77,7 @@ SIGNATURES = {
     "mts_revin_denorm_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "mts_attn_causal_shared": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mts_attn_causal_shared_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "mts_attn_causal_shared_bwd_full": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mts_rope_qk_shared": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mts_prompt_gather_shared": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mts_gpt4ts_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],

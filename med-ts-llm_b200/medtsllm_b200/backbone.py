@@ -334,16 +334,17 @@ class KernelBackbone:
         (dL/d(input residual stream) fp32 [Bp*L, D], LoRA gradients aligned with lora.params() or None).
         No gradients for the frozen weights.
 
-        Lc > 0 (shared-prefix layout, frozen backbone without LoRA): the prefix rows have no trainable
-        ancestor, so the whole chain runs on the samples' own rows only — dhid and the result are
-        [Bp*(L-Lc), D] and every stashed tensor is read from row Lc on."""
+        Lc > 0 (shared-prefix layout): with a frozen backbone the prefix rows have no trainable ancestor,
+        so the whole chain runs on the samples' own rows only — dhid and the result are [Bp*(L-Lc), D] and
+        every stashed tensor is read from row Lc on.  With LoRA the prefix rows matter (they reach the A/B
+        pairs): dhid and the result then hold all Lc + Bp*(L-Lc) rows."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
         Ls = L - Lc
-        M = Bp * Ls
-        if Lc and lora is not None:
-            raise MtsError("the shared-prefix backward assumes a frozen backbone (no LoRA)")
-        own = slice(Lc, None)
+        # LoRA: the A/B pairs receive gradient through the prefix rows as well -> the chain runs on all rows
+        full = Lc > 0 and lora is not None
+        M = Lc + Bp * Ls if full else Bp * Ls
+        own = slice(0 if full else Lc, None)
         self.ensure_transposed()
         rope = self.rope(L)
         dev = dhid.device
@@ -370,9 +371,11 @@ class KernelBackbone:
             # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
             datt = bf(M, D)
             ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
-            if Lc:
-                dqkv = ops.attn_causal_shared_bwd(st["qkv"], st["att"][own], datt, st["lse"], Bp, Lc, Ls, H, hd,
-                                                  rope=rope)
+            if full:
+                dqkv = ops.attn_causal_shared_bwd_full(st["qkv"], st["att"], datt, st["lse"], Bp, Lc, Ls, H, hd, rope=rope)
+            elif Lc:
+                dqkv = ops.attn_causal_shared_bwd(st["qkv"], st["att"][own], datt,
+                                                  ops.lse_own_view(st["lse"], Bp, Lc, Ls, H), Bp, Lc, Ls, H, hd, rope=rope)
             else:
                 dqkv = ops.attn_causal_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, rope=rope,
                                            pre_roped=rope is not None)

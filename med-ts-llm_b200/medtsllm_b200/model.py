@@ -418,15 +418,13 @@ class MedTsLLM(nn.Module):
         self._ids_cache = (key, table, None)     # (+ shared-prefix length once _shared_prefix_len has run)
         return table
 
-    def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int, with_grad: bool = False) -> int:
+    def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int) -> int:
         """Number of leading prompt positions (left padding included) that hold the same token in every
         sample of the batch.  The backbone is causal and the reference passes no padding mask
         (models/medtsllm.py:350), so the hidden states of those positions are the same for every sample
         at every layer: they are computed once per batch instead of once per sample.  0 = plain layout."""
         if not self.share_prompt_prefix or Bp < 2 or ids.shape[1] == 0:
             return 0
-        if self.lora_enabled and with_grad:
-            return 0               # LoRA weights receive gradient through the prompt rows too
         c = self._ids_cache
         if c is not None and c[1] is ids and len(c) > 3:
             Lc = c[3]
@@ -627,7 +625,7 @@ class MedTsLLM(nn.Module):
                 if c is not None and c[1] is ids:
                     self._ids_cache = (c[0], c[1], ids_dev) + tuple(c[3:])
         # shared-prefix row layout: Lc leading prompt positions once, then Ls = L - Lc own rows per sequence
-        Lc = self._shared_prefix_len(ids, Bp, L, with_grad=stash is not None)
+        Lc = self._shared_prefix_len(ids, Bp, L)
         Ls = L - Lc
         X = torch.empty(Lc + Bp * Ls, D, device=dev, dtype=torch.float32)
         ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L, Lc=Lc, B=B)

@@ -204,7 +204,8 @@ def attn_causal(qkv, Bp, L, H, hd, *, rope=None, scale=None, want_lse=False, out
 
 def attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, *, scale=None, want_lse=False, out=None):
     """Causal attention on the shared-prefix row layout (include/mts_b200.h): qkv bf16 [Lc + Bp*Ls, 3*H*hd]
-    with q / k already rotated -> out bf16 [Lc + Bp*Ls, H*hd]; lse (own tokens) fp32 [Bp, H, Ls]."""
+    with q / k already rotated -> out bf16 [Lc + Bp*Ls, H*hd]; lse fp32 [H*Lc + Bp*H*Ls] (prefix [H, Lc] first, then
+    the own tokens [Bp, H, Ls]: `lse_own_view`)."""
     _chk(qkv, torch.bfloat16, "qkv")
     M = Lc + Bp * Ls
     if not qkv.is_contiguous() or qkv.shape != (M, 3 * H * hd):
@@ -215,7 +216,35 @@ def attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, *, scale=None, want_lse=False, ou
         out = torch.empty(M, H * hd, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(H * Lc + Bp * H * Ls, device=qkv.device, dtype=torch.float32) if want_lse else None
     _lib.call("mts_attn_causal_shared", qkv.data_ptr(), out.data_ptr(), _ptr(lse), Bp, Lc, Ls, H, hd, scale, _stream())
-    return (out, lse[H * Lc:].view(Bp, H, Ls)) if want_lse else out
+    return (out, lse) if want_lse else out
+
+
+def lse_own_view(lse, Bp, Lc, Ls, H):
+    """The own-token part [Bp, H, Ls] of the lse buffer written by attn_causal_shared."""
+    return lse[H * Lc:].view(Bp, H, Ls)
+
+
+def attn_causal_shared_bwd_full(qkv, out, dout, lse, Bp, Lc, Ls, H, hd, *, rope=None, scale=None):
+    """Gradient w.r.t. ALL rows of the (un-rotated) qkv projection on the shared-prefix layout: bf16
+    [Lc + Bp*Ls, 3*H*hd] (LoRA training: the prefix rows matter too)."""
+    M = Lc + Bp * Ls
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
+    _chk(lse, torch.float32, "lse")
+    for t, cols in ((out, H * hd), (dout, H * hd), (qkv, 3 * H * hd)):
+        if not t.is_contiguous() or t.shape != (M, cols):
+            raise MtsError("attn_causal_shared_bwd_full: tensors must be contiguous with Lc + Bp*Ls rows")
+    if not lse.is_contiguous() or lse.numel() != H * Lc + Bp * H * Ls:
+        raise MtsError("attn_causal_shared_bwd_full: lse must be the full buffer of attn_causal_shared")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    cos, sin = rope if rope is not None else (None, None)
+    if cos is not None and cos.shape[0] < Lc + Ls:
+        raise MtsError("rope tables shorter than the sequence")
+    _lib.call("mts_attn_causal_shared_bwd_full", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), dout.data_ptr(),
+              lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, Lc, Ls, H, hd, scale, _stream())
+    return dqkv
 
 
 def attn_causal_shared_bwd(qkv, out_own, dout_own, lse_own, Bp, Lc, Ls, H, hd, *, rope=None, scale=None):

@@ -54,8 +54,10 @@ class _HotPathFn(torch.autograd.Function):
             dout = dout.float()
         B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
         HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
-        Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only
-        Ls, own_off = L - Lc, Lp - Lc   # own rows per sequence; first patch row among them
+        Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only ...
+        Ls = L - Lc                 # own rows per sequence
+        row0 = Lc if (Lc and m.lora_enabled) else 0    # ... unless LoRA needs the prefix rows too (all rows then)
+        own_off = Lp - Lc + row0    # first patch row of sequence 0 in dhid / dR
         mode = m.covariate_mode
         R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
         dm = m.d_model
@@ -104,7 +106,7 @@ class _HotPathFn(torch.autograd.Function):
             ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
         wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
         wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
-        dhid = zbf(B * Ls, D)                                                   # zero for prompt rows
+        dhid = zbf(row0 + B * Ls, D)                                            # zero for prompt rows
         ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
                  d_bs=Ls * D, ldd=D, d_off=own_off * D)
 

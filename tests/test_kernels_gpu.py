@@ -542,7 +542,10 @@ def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
     qkv_p = _expand_shared(qkv, Bp, Lc, Ls)
     out_p, lse_p = ops.attn_causal(qkv_p, Bp, L, H, hd, rope=None, want_lse=True)
     assert torch.equal(_expand_shared(out, Bp, Lc, Ls), out_p)
+    lse_full = lse
+    lse = ops.lse_own_view(lse_full, Bp, Lc, Ls, H)
     assert torch.equal(lse, lse_p[:, :, Lc:])
+    assert torch.equal(lse_full[:H * Lc].view(H, Lc), lse_p[0, :, :Lc])
     # backward: gradient only enters through the samples' own rows
     tabs = _rope_tables(L, hd, cuda)
     dout = torch.randn(Bp * Ls, D, generator=g).to(cuda, torch.bfloat16)
@@ -553,6 +556,20 @@ def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
     own = dqkv_p.view(Bp, L, 3 * D)[:, Lc:].reshape(Bp * Ls, 3 * D)
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         assert _rel_l2(dqkv[:, sl], own[:, sl]) < 1e-6, name
+    # full backward (LoRA): gradient also enters at the prefix rows' outputs, and the prefix rows' q/k/v receive what
+    # all the samples send back.  Equivalent plain computation: Bp private copies of the prefix; the gradient of the
+    # shared rows is the sum over the copies (the upstream gradient of the prefix outputs is given to copy 0).
+    dout_all = torch.randn(M, D, generator=g).to(cuda, torch.bfloat16)
+    dqkv_all = ops.attn_causal_shared_bwd_full(qkv, out, dout_all, lse_full, Bp, Lc, Ls, H, hd, rope=tabs)
+    dout_p = torch.zeros(Bp, L, D, device=cuda, dtype=torch.bfloat16)
+    dout_p[:, Lc:] = dout_all[Lc:].view(Bp, Ls, D)
+    dout_p[0, :Lc] = dout_all[:Lc]
+    ref = ops.attn_causal_bwd(qkv_p, out_p, dout_p.view(Bp * L, D), lse_p, Bp, L, H, hd, rope=tabs, pre_roped=True)
+    ref = ref.view(Bp, L, 3 * D).float()
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        assert _rel_l2(dqkv_all[Lc:, sl], ref[:, Lc:, sl].reshape(Bp * Ls, -1)) < 1e-6, name
+        e = _rel_l2(dqkv_all[:Lc, sl], ref[:, :Lc, sl].sum(0))
+        assert e < 1.5e-2, (name, e)          # the plain side rounds each copy's share to bf16 before the sum
 
 
 def test_prompt_gather_and_rope_shared_prefix(ops, cuda):

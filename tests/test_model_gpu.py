@@ -395,6 +395,48 @@ def test_shared_prompt_prefix_equals_per_sample_prompts(name, partial, tmp_path,
         assert e < 2e-3 or (g1[k] - g0[k]).abs().max().item() <= 1e-3 * sib, (k, e)
 
 
+@pytest.mark.parametrize("name,rank", [("llama_seg_concat", 8), ("gpt2_anomaly_concat", 4)])
+def test_lora_training_on_shared_prefix_equals_per_sample_prompts(name, rank, tmp_path, cuda):
+    """LoRA fine-tuning (BASELINE config 5) keeps the shared-prefix layout: the A/B pairs receive gradient through the
+    prompt rows too, so the backward runs on all rows and the prefix keys collect dK / dV from every sample
+    (attn_bwd_dkv_prefix_kernel).  Every gradient — adapters and all LoRA pairs — must equal the per-sample-prompt run."""
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": rank, "alpha": 16, "rslora": True}
+    torch.manual_seed(3)
+    model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=False)
+    model = model.to(cuda, torch.float32).train()
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for p in model.llm.B:                      # non-zero B: the LoRA path is live
+            p.copy_((torch.randn(p.shape, generator=gen) * 0.05).to(cuda))
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    res = {}
+    for share in (True, False):
+        model.share_prompt_prefix = share
+        model.zero_grad(set_to_none=True)
+        y = model(inputs)
+        wgt = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(cuda)
+        (y * wgt).sum().backward()
+        torch.cuda.synchronize()
+        named = dict(model.named_parameters())
+        res[share] = (y.detach().clone(), {k: p.grad.clone() for k, p in named.items() if p.grad is not None})
+    (y1, g1), (y0, g0) = res[True], res[False]
+    assert torch.equal(y1, y0)
+    assert set(g1) == set(g0) and any(k.startswith("llm.") for k in g1)
+    worst = {}
+    for k in g0:
+        e = _rel_l2(g1[k], g0[k])
+        sib = g0.get(k.rsplit(".", 1)[0] + ".weight", g0[k]).abs().max().item()
+        worst[k] = e
+        # per-sample prompts round every copy's prefix contribution to bf16 before summing; shared rows sum in fp32
+        assert e < 2e-2 or (g1[k] - g0[k]).abs().max().item() <= 1e-3 * sib, (k, e)
+    print(f"\n[lora shared-prefix] {name}: worst rel-L2 {max(worst.values()):.2e} over {len(worst)} tensors")
+
+
 @pytest.mark.parametrize("name", ["llama_seg_concat", "gpt2_anomaly_concat", "llama_forecast_clip_stats"])
 def test_cuda_graph_replay_matches_kernel_by_kernel(name, tmp_path, cuda):
     """Inference replays a captured CUDA graph once the same (shape, prompt table, weights) key repeats.  Call 1 runs
