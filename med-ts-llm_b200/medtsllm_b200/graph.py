@@ -36,7 +36,9 @@ class GraphReplay:
         static_x = x.clone()
         graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
-        with torch.cuda.graph(graph):
+        # thread_local: the reference's DataLoaders run a pin_memory thread in this process (tasks/base.py:175-197);
+        # its cudaHostAlloc calls during our capture must not be treated as capture violations
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             out = fn(static_x)
         # (capturing records the launches without running them; the launch counter then follows the replays)
         self.entry = {"key": key, "graph": graph, "x": static_x, "out": out, "launches": launch_count() - n0, "hold": hold}
