@@ -53,6 +53,7 @@ class LoraAdapters(nn.Module):
                 self.A.append(nn.Parameter(a))
                 self.B.append(nn.Parameter(b))
         self._cache = {}
+        self._force_recast = False      # graph capture of a training step: cast even if the cache would hit
 
     def params(self):
         return list(self.A) + list(self.B)
@@ -68,7 +69,7 @@ class LoraAdapters(nn.Module):
         ps = [self.A[self.index(layer, t)] for t in range(nt)] + [self.B[self.index(layer, t)] for t in range(nt)]
         key = tuple((p._version, p.data_ptr()) for p in ps)
         hit = self._cache.get(layer)
-        if hit is not None and hit[0] == key:
+        if hit is not None and hit[0] == key and not self._force_recast:
             return hit[1]
         dev = ps[0].device
         D = ps[0].shape[1]

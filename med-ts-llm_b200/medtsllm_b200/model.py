@@ -196,6 +196,12 @@ class MedTsLLM(nn.Module):
         # has been seen twice in a row (MTS_CUDA_GRAPH=0 / `model.use_cuda_graph = False`: launch kernel by kernel)
         self.use_cuda_graph = os.environ.get("MTS_CUDA_GRAPH", "1") != "0"
         self._graph = GraphReplay()
+        # training steps replay two captured graphs (forward with its stash, backward chain) where the step is bound by
+        # the host issuing launches: "auto" = single process, or a GPT-2-sized backbone / LoRA under data parallelism
+        # (the gradient all-reduce then runs after the backward graph instead of underneath it); "1" / "0" force it
+        self.use_train_graph = os.environ.get("MTS_TRAIN_GRAPH", "auto")
+        self._train_graph = None
+        self._force_recast = False
         self._capture = None       # tests: dict filled with per-stage tensors
         self._ids_cache = None     # (prompt parts, host id table, device id table)
         self._prompt_cache: dict[str, list[int]] = {}
@@ -492,13 +498,32 @@ class MedTsLLM(nn.Module):
             self._ds_fixed = ops.cast_bf16(w.to(self.device))
         return self._ds_fixed, None
 
+    def train_graph_enabled(self) -> bool:
+        """Whether this training forward may run on the captured step graphs (train.TrainGraph)."""
+        mode = self.use_train_graph
+        if mode in (False, "0", "off") or self._capture is not None or self._dropout_requested > 0:
+            return False            # (dropout draws fresh host seeds every step)
+        if mode == "auto":
+            from . import dp
+            if dp.is_active() and not (self.lora_enabled or self.backbone_spec.hidden < 2048):
+                return False        # GPU-bound step: keep the all-reduce overlapped with the backbone dgrad
+        if self._train_graph is None:
+            from .train import TrainGraph
+            self._train_graph = TrainGraph()
+        return True
+
+    def _set_force_recast(self, flag: bool):
+        self._force_recast = flag
+        if self.lora_enabled:
+            self.llm._force_recast = flag
+
     def _bf16_weight(self, name: str, p: torch.Tensor) -> torch.Tensor:
         """bf16 copy [rows, ceil8(cols)] (zero padded: TMA rows must be 16-byte aligned) of a trainable
         fp32 master, re-cast by our kernel only when the optimizer has changed it (`_version` bumps on
         every in-place update)."""
         key = (p._version, p.data_ptr())
         hit = self._w_cache.get(name)
-        if hit is not None and hit[0] == key:
+        if hit is not None and hit[0] == key and not self._force_recast:
             return hit[1]
         rows, cols = p.shape
         w = ops.cast_rows(p.detach().contiguous(), rows=rows, cols=cols)
@@ -512,7 +537,7 @@ class MedTsLLM(nn.Module):
         plist = [self.mapping_layer.weight, self.mapping_layer.bias, rl.key_projection.weight,
                  rl.key_projection.bias, rl.value_projection.weight, rl.value_projection.bias]
         key = tuple((p._version, p.data_ptr()) for p in plist)
-        if self._src_cache is not None and self._src_cache[0] == key:
+        if self._src_cache is not None and self._src_cache[0] == key and not self._force_recast:
             return self._src_cache[1:]
         bb = self._backbone
         S, D, HE, V = self.num_tokens, self.d_llm, self.d_ff * self.n_attention_heads, self.vocab_size

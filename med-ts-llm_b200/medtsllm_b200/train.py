@@ -19,12 +19,87 @@ from __future__ import annotations
 import torch
 
 from . import dp, ops
-from ._lib import EPI_RESID_ADD
+from ._lib import EPI_RESID_ADD, MtsError, launch_count, note_replay
 
 
 def forward_train(model, inputs):
     params = model.adapter_params()
     return _HotPathFn.apply(model, inputs, *params)
+
+
+class TrainGraph:
+    """CUDA-graph replay of the training step's device work: one graph for the forward (with its activation
+    stash), one for the backward chain.  The launch-bound configurations (GPT-2 backbones, LoRA: 600-1450 short
+    kernels per step) are otherwise limited by the host issuing the launches.
+
+    Key = input shape, prompt-id table, row layout and the ADDRESS of every trainable tensor — not its version:
+    the optimizer updates the fp32 masters in place and the captured forward re-casts them to bf16 every replay
+    (`model._force_recast` makes the capture include every cast / prototype GEMM even if a cache would hit).
+    The gradients come back in static buffers and are handed to autograd as copies.  With data parallelism the
+    all-reduce runs after the backward graph (NCCL stays outside the capture)."""
+
+    def __init__(self):
+        self.entry = None
+        self.seen = None
+        self.generation = 0
+
+    @staticmethod
+    def key_of(model, x_enc, ids):
+        return (tuple(x_enc.shape), x_enc.device.index, id(ids), model.share_prompt_prefix,
+                tuple(p.data_ptr() for p in model.adapter_params()))
+
+    def forward(self, model, inputs, x_enc, ids):
+        """Returns (out, True) when the step runs on the graph, (None, False) when the caller must run eagerly."""
+        key = self.key_of(model, x_enc, ids)
+        e = self.entry
+        if e is not None and e["key"] == key:
+            e["x"].copy_(x_enc)
+            e["fwd"].replay()
+            note_replay(e["fwd_launches"])
+            self.generation += 1
+            return e["out"].clone(), True
+        if self.seen is None or self.seen[0] != key:
+            self.seen = (key, ids)
+            return None, False
+        self.entry = None
+        static_x = x_enc.clone()
+        stash = {}
+        graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        model._set_force_recast(True)
+        try:
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out = model._forward_impl({**inputs, "x_enc": static_x}, stash, ids)
+        finally:
+            model._set_force_recast(False)
+        self.entry = {"key": key, "fwd": graph, "x": static_x, "out": out, "stash": stash, "ids": ids,
+                      "fwd_launches": launch_count() - n0, "bwd": None}
+        graph.replay()
+        self.generation += 1
+        return out.clone(), True
+
+    def backward(self, model, dout, generation):
+        e = self.entry
+        if e is None or generation != self.generation:
+            raise MtsError("backward() of a training step whose activations were overwritten by a later forward on "
+                           "the captured graph (set model.use_train_graph = False for this usage pattern)")
+        if e["bwd"] is None:
+            e["dout"] = dout.clone()
+            graph = torch.cuda.CUDAGraph()
+            n0 = launch_count()
+            with torch.cuda.graph(graph, pool=e["fwd"].pool(), capture_error_mode="thread_local"):
+                e["grads"] = _backward_chain(model, e["stash"], e["dout"], use_dp=False)
+            e["bwd"], e["bwd_launches"] = graph, launch_count() - n0
+            graph.replay()
+        else:
+            e["dout"].copy_(dout)
+            e["bwd"].replay()
+            note_replay(e["bwd_launches"])
+        grads = [g.clone() if g is not None else None for g in e["grads"]]
+        if dp.is_active():
+            bucket = dp.GradBucket(grads).launch()
+            bucket.finish()
+        return grads
 
 
 def _t(x, **kw):
@@ -37,180 +112,205 @@ class _HotPathFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, inputs, *params):
-        stash = {}
-        out = model._forward_impl(inputs, stash)
         ctx.model = model
+        ctx.graph_generation = None
+        if model.train_graph_enabled():
+            x_enc = model._check_input(inputs)
+            ids = model.prompt_token_ids(inputs)
+            out, on_graph = model._train_graph.forward(model, inputs, x_enc, ids)
+            if on_graph:
+                ctx.graph_generation = model._train_graph.generation
+                ctx.stash = None
+                return out
+            stash = {}
+            out = model._forward_impl(inputs, stash, ids)
+        else:
+            stash = {}
+            out = model._forward_impl(inputs, stash)
         ctx.stash = stash
-        ctx.out_shape = out.shape
         return out
 
     @staticmethod
     @torch.no_grad()
     def backward(ctx, dout):
-        m, st = ctx.model, ctx.stash
-        bb = m._backbone
-        dev = dout.device
+        m = ctx.model
         if dout.dtype != torch.float32:
             dout = dout.float()
-        B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
-        HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
-        Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only ...
-        Ls = L - Lc                 # own rows per sequence
-        row0 = Lc if (Lc and m.lora_enabled) else 0    # ... unless LoRA needs the prefix rows too (all rows then)
-        own_off = Lp - Lc + row0    # first patch row of sequence 0 in dhid / dR
-        mode = m.covariate_mode
-        R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
-        dm = m.d_model
-        rl = m.reprogramming_layer
-        f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
-        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)     # noqa: E731
-        zbf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)    # noqa: E731
-        g_fw_w = g_fw_b = None
-
-        # ---- de-norm / squeeze (models/medtsllm.py:379-382): statistics are detached
-        dout = dout.reshape(B0, m.pred_len, m.n_outputs_per_step).contiguous()
-        dy = ops.revin_denorm_bwd(dout, st["std"]) if st["denorm"] else dout
-        n_out = m.n_outputs
-        # ---- merges over the feature axis after the head (models/medtsllm.py:369-377)
-        if mode == "independent":
-            dy2, _, _ = ops.group_reduce_bwd(dy.view(B0, n_out), B0, C, n_out)            # [B0*C, n_out]
-        elif mode == "merge-end":
-            dy2, g_fw_w, g_fw_b = ops.merge_end_bwd(dy, st["head"], m.feature_weighting.weight.detach(), B0, C,
-                                                    m.pred_len, m.n_outputs_per_step)
+        if ctx.graph_generation is not None:
+            grads = m._train_graph.backward(m, dout.contiguous(), ctx.graph_generation)
         else:
-            dy2 = dy.view(B, n_out)
+            grads = _backward_chain(m, ctx.stash, dout, use_dp=True)
+            ctx.stash = None
+        return (None, None) + tuple(grads)
 
-        # ---- flatten head: out = flat W_h^T + b_h
-        g_bh = ops.colsum(dy2)
-        dy_b = ops.cast_rows(dy2, rows=B, cols=n_out)                          # bf16 [B, ceil8(n_out)]
-        wh = m._bf16_weight("wh", m.output_projection.linear.weight)           # [n_out, ceil8(EN)]
-        EN = E * N
-        g_wh = f32(n_out, EN)
-        ops.gemm(_t(dy2), _t(st["flat"]), g_wh, m=n_out, n=EN, k=B, lda=ops.ceil8(B), ldb=ops.ceil8(B))
-        wh_t = ops.transpose_strided(wh, rows=n_out, cols=EN, ld_in=wh.shape[1])   # [EN, ceil8(n_out)]
-        dflat = bf(B, EN)                                                       # [B, E, N]
-        ops.gemm(dy_b, wh_t, dflat, m=B, n=EN, k=n_out, lda=dy_b.shape[1], ldb=wh_t.shape[1])
 
-        # ---- down-sample Linear on the last N tokens: flat[b, f, n] = hid[b, Lp+n] . W_ds[f] + b_ds[f]
-        # dflat is [B][E][N]; dY_ds[(b, n), f] = dflat[b, f, n] is a per-batch transpose
-        Rh = B * N                                  # rows entering the down-sample step: (sequence, token)
-        dyds = bf(Rh, E)
-        for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
-            ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
-        g_bds = g_wds = None
-        if m.embedding_downsample_mode == "linear":
-            g_bds = ops.colsum(dyds)
-            hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D,
-                                               in_off=Lp * D)                  # [D, ceil8(R)]
-            g_wds = f32(E, D)
-            ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
-        wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
-        wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
-        dhid = zbf(row0 + B * Ls, D)                                            # zero for prompt rows
-        ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
-                 d_bs=Ls * D, ldd=D, d_off=own_off * D)
+def _backward_chain(m, st, dout, use_dp=True):
+    """The manual backward of the hot path (see the module docstring): returns the gradients aligned with
+    `m.adapter_params()`.  `use_dp`: overlap the gradient all-reduce with the chain (eager path); the graph path
+    captures the chain without collectives and all-reduces afterwards."""
+    bb = m._backbone
+    dev = dout.device
+    B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
+    HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
+    Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only ...
+    Ls = L - Lc                 # own rows per sequence
+    row0 = Lc if (Lc and m.lora_enabled) else 0    # ... unless LoRA needs the prefix rows too (all rows then)
+    own_off = Lp - Lc + row0    # first patch row of sequence 0 in dhid / dR
+    mode = m.covariate_mode
+    R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
+    dm = m.d_model
+    rl = m.reprogramming_layer
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
+    bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)     # noqa: E731
+    zbf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)    # noqa: E731
+    g_fw_w = g_fw_b = None
 
-        # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
-        early = dp.GradBucket([g_wh, g_bh] + ([g_wds, g_bds] if g_wds is not None else [])).launch()
+    # ---- de-norm / squeeze (models/medtsllm.py:379-382): statistics are detached
+    dout = dout.reshape(B0, m.pred_len, m.n_outputs_per_step).contiguous()
+    dy = ops.revin_denorm_bwd(dout, st["std"]) if st["denorm"] else dout
+    n_out = m.n_outputs
+    # ---- merges over the feature axis after the head (models/medtsllm.py:369-377)
+    if mode == "independent":
+        dy2, _, _ = ops.group_reduce_bwd(dy.view(B0, n_out), B0, C, n_out)            # [B0*C, n_out]
+    elif mode == "merge-end":
+        dy2, g_fw_w, g_fw_b = ops.merge_end_bwd(dy, st["head"], m.feature_weighting.weight.detach(), B0, C,
+                                                m.pred_len, m.n_outputs_per_step)
+    else:
+        dy2 = dy.view(B, n_out)
 
-        # ---- frozen backbone (dgrad only)
-        dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
-                                     lora=m.llm if m.lora_enabled else None, Lc=Lc)   # fp32 [B*Ls, D]
+    # ---- flatten head: out = flat W_h^T + b_h
+    g_bh = ops.colsum(dy2)
+    dy_b = ops.cast_rows(dy2, rows=B, cols=n_out)                          # bf16 [B, ceil8(n_out)]
+    wh = m._bf16_weight("wh", m.output_projection.linear.weight)           # [n_out, ceil8(EN)]
+    EN = E * N
+    g_wh = f32(n_out, EN)
+    ops.gemm(_t(dy2), _t(st["flat"]), g_wh, m=n_out, n=EN, k=B, lda=ops.ceil8(B), ldb=ops.ceil8(B))
+    wh_t = ops.transpose_strided(wh, rows=n_out, cols=EN, ld_in=wh.shape[1])   # [EN, ceil8(n_out)]
+    dflat = bf(B, EN)                                                       # [B, E, N]
+    ops.gemm(dy_b, wh_t, dflat, m=B, n=EN, k=n_out, lda=dy_b.shape[1], ldb=wh_t.shape[1])
 
-        # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
-        if mode in ("concat", "univariate", "independent", "merge-end"):
-            dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D, in_off=own_off * D)   # bf16 [R, D]
-        elif mode == "interleave":
-            dxp = bf(R, D)
-            for c in range(C):       # feature c owns rows Lp + n*C + c
-                ops.cast_rows(dR, batch=B0, rows=N0, cols=D, ld_in=C * D, in_bs=Ls * D, in_off=(own_off + c) * D,
-                              out=dxp, ld_out=D, out_bs=C * N0 * D, out_off=c * N0 * D)
-        else:                        # add / weighted-average: broadcast back over the feature axis
-            fw = m.feature_weighting if mode == "weighted-average" else None
-            dyf, g_w, g_b = ops.group_reduce_bwd(dR, B0, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
-                                                 x=st["Y"] if fw is not None else None, dout_bs=Ls * D, dout_off=own_off * D)
-            if fw is not None:
-                g_fw_w, g_fw_b = g_w.view(1, C), g_b.view(1)
-            dxp = ops.cast_bf16(dyf.view(R, D))
-        g_bo = ops.colsum(dxp)
-        Rp = ops.ceil8(R)
-        g_wo = f32(D, HE)
-        ops.gemm(_t(dxp), _t(st["O"]), g_wo, m=D, n=HE, k=R, lda=Rp, ldb=Rp)
-        wo = m._bf16_weight("wo", rl.out_projection.weight)                    # [D, HE]
-        wo_t = ops.transpose_strided(wo, rows=D, cols=HE, ld_in=wo.shape[1])   # [HE, D]
-        dO = bf(R, HE)
-        ops.gemm(dxp, wo_t, dO, m=R, n=HE, k=D, ldb=wo_t.shape[1])
+    # ---- down-sample Linear on the last N tokens: flat[b, f, n] = hid[b, Lp+n] . W_ds[f] + b_ds[f]
+    # dflat is [B][E][N]; dY_ds[(b, n), f] = dflat[b, f, n] is a per-batch transpose
+    Rh = B * N                                  # rows entering the down-sample step: (sequence, token)
+    dyds = bf(Rh, E)
+    for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
+        ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
+    g_bds = g_wds = None
+    if m.embedding_downsample_mode == "linear":
+        g_bds = ops.colsum(dyds)
+        hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D,
+                                           in_off=Lp * D)                  # [D, ceil8(R)]
+        g_wds = f32(E, D)
+        ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
+    wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
+    wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
+    dhid = zbf(row0 + B * Ls, D)                                            # zero for prompt rows
+    ops.gemm(dyds, wds_t, dhid, m=N, n=D, k=E, batch=B, a_bs=N * E, b_bs=0, ldb=wds_t.shape[1],
+             d_bs=Ls * D, ldd=D, d_off=own_off * D)
 
-        # ---- cross-attention core, per head h: O_h = P_h V_h, P_h = softmax(scale Q_h K_h^T)
-        P, Pd, Q, K, Vt = st["P"], st["Pd"], st["Q"], st["K"], st["Vt"]
-        p_drop, seeds = st["p_drop"], st["seeds"]
-        Vm = ops.transpose_strided(Vt, rows=HE, cols=S)                        # [S, HE]
-        dP = f32(H, R, S)
-        ops.gemm(dO, Vm, dP, m=R, n=S, k=E, batch=H, lda=HE, a_bs=E, ldb=Vm.shape[1], b_bs=E, d_bs=R * S)
-        if p_drop > 0:
-            ops.dropout(dP, p_drop, seeds[1], out=dP)                          # same mask as the forward's attention dropout
-        dS = ops.softmax_bwd_rows(P, dP, st["scale"])                          # bf16 [H, R, S]
-        # per-head transposes laid out [S, H*Rp]: head h occupies columns [h*Rp, h*Rp + R)
-        P_t, dS_t = zbf(S, H * Rp), zbf(S, H * Rp)
-        for h in range(H):
-            ops.transpose_strided(Pd, rows=R, cols=S, in_off=h * R * S, out=P_t[:, h * Rp:], ld_out=H * Rp)
-            ops.transpose_strided(dS, rows=R, cols=S, in_off=h * R * S, out=dS_t[:, h * Rp:], ld_out=H * Rp)
-        dO_t, Q_t = _t(dO), _t(Q)                                              # [HE, Rp]
-        dV = bf(S, HE)
-        ops.gemm(P_t, dO_t, dV, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
-        dK = bf(S, HE)
-        ops.gemm(dS_t, Q_t, dK, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
-        K_t = _t(K)                                                            # [HE, S]
-        dQ = bf(R, HE)
-        ops.gemm(dS, K_t, dQ, m=R, n=E, k=S, batch=H, a_bs=R * S, lda=S, ldb=K_t.shape[1], b_bs=E * K_t.shape[1],
-                 ldd=HE, d_bs=E)
+    # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
+    early = dp.GradBucket([g_wh, g_bh] + ([g_wds, g_bds] if g_wds is not None else []))
+    if use_dp:
+        early.launch()
 
-        # ---- query projection + front end
-        g_bq = ops.colsum(dQ)
-        enc2 = st["enc"].view(R, dm)
-        g_wq = f32(HE, dm)
-        ops.gemm(_t(dQ), _t(enc2), g_wq, m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
-        wq = m._bf16_weight("wq", rl.query_projection.weight)                  # [HE, ceil8(dm)]
-        wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
-        denc = f32(R, dm)
-        ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
-        if p_drop > 0:
-            ops.dropout(denc, p_drop, seeds[0], out=denc)                      # patch-embedding dropout mask
-        g_conv = ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
-                                           m.patch_len, m.stride, m.d_patch, concat=st["concat"])
+    # ---- frozen backbone (dgrad only)
+    dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
+                                 lora=m.llm if m.lora_enabled else None, Lc=Lc)   # fp32 [B*Ls, D]
 
-        # ---- key / value projections of the prototypes, then the mapping layer
-        source = st["source"]
-        src_t = _t(source)                                                     # [D, S]
-        g_bk, g_bv = ops.colsum(dK), ops.colsum(dV)
-        g_wk, g_wv = f32(HE, D), f32(HE, D)
-        ops.gemm(_t(dK), src_t, g_wk, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
-        ops.gemm(_t(dV), src_t, g_wv, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
-        wk = m._bf16_weight("wk", rl.key_projection.weight)                    # [HE, D]
-        wv = m._bf16_weight("wv", rl.value_projection.weight)
-        dsrc = f32(S, D)
-        ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
-        ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
-        dsrc_b = ops.cast_bf16(dsrc)
-        g_bmap = ops.rowsum(dsrc)                                              # d b_map[s] = sum_d dSource[s, d]
-        g_wmap = f32(S, V)
-        ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
+    # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
+    if mode in ("concat", "univariate", "independent", "merge-end"):
+        dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D, in_off=own_off * D)   # bf16 [R, D]
+    elif mode == "interleave":
+        dxp = bf(R, D)
+        for c in range(C):       # feature c owns rows Lp + n*C + c
+            ops.cast_rows(dR, batch=B0, rows=N0, cols=D, ld_in=C * D, in_bs=Ls * D, in_off=(own_off + c) * D,
+                          out=dxp, ld_out=D, out_bs=C * N0 * D, out_off=c * N0 * D)
+    else:                        # add / weighted-average: broadcast back over the feature axis
+        fw = m.feature_weighting if mode == "weighted-average" else None
+        dyf, g_w, g_b = ops.group_reduce_bwd(dR, B0, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
+                                             x=st["Y"] if fw is not None else None, dout_bs=Ls * D, dout_off=own_off * D)
+        if fw is not None:
+            g_fw_w, g_fw_b = g_w.view(1, C), g_b.view(1)
+        dxp = ops.cast_bf16(dyf.view(R, D))
+    g_bo = ops.colsum(dxp)
+    Rp = ops.ceil8(R)
+    g_wo = f32(D, HE)
+    ops.gemm(_t(dxp), _t(st["O"]), g_wo, m=D, n=HE, k=R, lda=Rp, ldb=Rp)
+    wo = m._bf16_weight("wo", rl.out_projection.weight)                    # [D, HE]
+    wo_t = ops.transpose_strided(wo, rows=D, cols=HE, ld_in=wo.shape[1])   # [HE, D]
+    dO = bf(R, HE)
+    ops.gemm(dxp, wo_t, dO, m=R, n=HE, k=D, ldb=wo_t.shape[1])
 
-        lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
+    # ---- cross-attention core, per head h: O_h = P_h V_h, P_h = softmax(scale Q_h K_h^T)
+    P, Pd, Q, K, Vt = st["P"], st["Pd"], st["Q"], st["K"], st["Vt"]
+    p_drop, seeds = st["p_drop"], st["seeds"]
+    Vm = ops.transpose_strided(Vt, rows=HE, cols=S)                        # [S, HE]
+    dP = f32(H, R, S)
+    ops.gemm(dO, Vm, dP, m=R, n=S, k=E, batch=H, lda=HE, a_bs=E, ldb=Vm.shape[1], b_bs=E, d_bs=R * S)
+    if p_drop > 0:
+        ops.dropout(dP, p_drop, seeds[1], out=dP)                          # same mask as the forward's attention dropout
+    dS = ops.softmax_bwd_rows(P, dP, st["scale"])                          # bf16 [H, R, S]
+    # per-head transposes laid out [S, H*Rp]: head h occupies columns [h*Rp, h*Rp + R)
+    P_t, dS_t = zbf(S, H * Rp), zbf(S, H * Rp)
+    for h in range(H):
+        ops.transpose_strided(Pd, rows=R, cols=S, in_off=h * R * S, out=P_t[:, h * Rp:], ld_out=H * Rp)
+        ops.transpose_strided(dS, rows=R, cols=S, in_off=h * R * S, out=dS_t[:, h * Rp:], ld_out=H * Rp)
+    dO_t, Q_t = _t(dO), _t(Q)                                              # [HE, Rp]
+    dV = bf(S, HE)
+    ops.gemm(P_t, dO_t, dV, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
+    dK = bf(S, HE)
+    ops.gemm(dS_t, Q_t, dK, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
+    K_t = _t(K)                                                            # [HE, S]
+    dQ = bf(R, HE)
+    ops.gemm(dS, K_t, dQ, m=R, n=E, k=S, batch=H, a_bs=R * S, lda=S, ldb=K_t.shape[1], b_bs=E * K_t.shape[1],
+             ldd=HE, d_bs=E)
+
+    # ---- query projection + front end
+    g_bq = ops.colsum(dQ)
+    enc2 = st["enc"].view(R, dm)
+    g_wq = f32(HE, dm)
+    ops.gemm(_t(dQ), _t(enc2), g_wq, m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
+    wq = m._bf16_weight("wq", rl.query_projection.weight)                  # [HE, ceil8(dm)]
+    wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
+    denc = f32(R, dm)
+    ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
+    if p_drop > 0:
+        ops.dropout(denc, p_drop, seeds[0], out=denc)                      # patch-embedding dropout mask
+    g_conv = ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
+                                       m.patch_len, m.stride, m.d_patch, concat=st["concat"])
+
+    # ---- key / value projections of the prototypes, then the mapping layer
+    source = st["source"]
+    src_t = _t(source)                                                     # [D, S]
+    g_bk, g_bv = ops.colsum(dK), ops.colsum(dV)
+    g_wk, g_wv = f32(HE, D), f32(HE, D)
+    ops.gemm(_t(dK), src_t, g_wk, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
+    ops.gemm(_t(dV), src_t, g_wv, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
+    wk = m._bf16_weight("wk", rl.key_projection.weight)                    # [HE, D]
+    wv = m._bf16_weight("wv", rl.value_projection.weight)
+    dsrc = f32(S, D)
+    ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
+    ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
+    dsrc_b = ops.cast_bf16(dsrc)
+    g_bmap = ops.rowsum(dsrc)                                              # d b_map[s] = sum_d dSource[s, d]
+    g_wmap = f32(S, V)
+    ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
+
+    lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
+    if use_dp:
         late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo, g_fw_w, g_fw_b]
                              + lora_grads).launch()
         early.finish()
         late.finish()
-        ctx.stash = None
-        grads = {
-            "patch_embedding.value_embedding.tokenConv.weight": g_conv,
-            "mapping_layer.weight": g_wmap, "mapping_layer.bias": g_bmap,
-            "reprogramming_layer.query_projection.weight": g_wq, "reprogramming_layer.query_projection.bias": g_bq,
-            "reprogramming_layer.key_projection.weight": g_wk, "reprogramming_layer.key_projection.bias": g_bk,
-            "reprogramming_layer.value_projection.weight": g_wv, "reprogramming_layer.value_projection.bias": g_bv,
-            "reprogramming_layer.out_projection.weight": g_wo, "reprogramming_layer.out_projection.bias": g_bo,
-            "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
-            "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
-            "feature_weighting.weight": g_fw_w, "feature_weighting.bias": g_fw_b,
-        }
-        return (None, None) + tuple(grads[k] for k in m.param_order()) + tuple(lora_grads)
+    grads = {
+        "patch_embedding.value_embedding.tokenConv.weight": g_conv,
+        "mapping_layer.weight": g_wmap, "mapping_layer.bias": g_bmap,
+        "reprogramming_layer.query_projection.weight": g_wq, "reprogramming_layer.query_projection.bias": g_bq,
+        "reprogramming_layer.key_projection.weight": g_wk, "reprogramming_layer.key_projection.bias": g_bk,
+        "reprogramming_layer.value_projection.weight": g_wv, "reprogramming_layer.value_projection.bias": g_bv,
+        "reprogramming_layer.out_projection.weight": g_wo, "reprogramming_layer.out_projection.bias": g_bo,
+        "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
+        "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
+        "feature_weighting.weight": g_fw_w, "feature_weighting.bias": g_fw_b,
+    }
+    return [grads[k] for k in m.param_order()] + list(lora_grads)

@@ -516,3 +516,60 @@ def test_gpt4ts_forward_parity(name, cuda):
     with pytest.raises(MtsError):
         with torch.no_grad():
             model({"x_enc": x.cpu()})
+
+
+@pytest.mark.parametrize("name,lora", [("llama_seg_concat", False), ("gpt2_anomaly_concat", False), ("llama_seg_concat", True)])
+def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda):
+    """Training steps replay two captured CUDA graphs (forward + stash, backward chain) once the same step shape
+    repeats: step 0 runs kernel by kernel, step 1 captures, steps 2.. replay.  Losses and the parameters after
+    5 Adam steps must be bit-identical to the kernel-by-kernel run (same kernels, same order), the captured forward
+    must pick up every optimizer update (bf16 re-casts are part of the graph), and a backward() whose activations
+    were overwritten by a later forward must raise."""
+    from medtsllm_b200._lib import MtsError
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    if lora:
+        cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16, "rslora": True}
+    base = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+
+    def run(mode):
+        torch.manual_seed(3)
+        model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+        model.load_state_dict(fix["adapters"], strict=False)
+        model = model.to(cuda, torch.float32).train()
+        model.use_train_graph = mode
+        if lora:
+            gen = torch.Generator().manual_seed(11)
+            with torch.no_grad():
+                for p in model.llm.B:
+                    p.copy_((torch.randn(p.shape, generator=gen) * 0.05).to(cuda))
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+        losses = []
+        for step in range(5):
+            y = model({**base, "x_enc": base["x_enc"] * (1.0 + 0.05 * step)})
+            loss = y.float().pow(2).mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            losses.append(loss.item())
+        return model, losses
+
+    m0, l0 = run("0")
+    m1, l1 = run("1")
+    assert m0._train_graph is None and m1._train_graph.entry is not None and m1._train_graph.entry["bwd"] is not None
+    assert l0 == l1, (l0, l1)
+    assert l0[0] != l0[-1]
+    for (k, p0), (_, p1) in zip(m0.named_parameters(), m1.named_parameters()):
+        assert torch.equal(p0, p1), k
+    # evaluation after training on the graph sees the trained weights
+    m0.eval(); m1.eval()
+    with torch.no_grad():
+        assert torch.equal(m0(base), m1(base))
+    # stale activations: two forwards on the graph, backward through the first
+    m1.train()
+    ya = m1(base)
+    m1(base)
+    with pytest.raises(MtsError):
+        ya.sum().backward()
