@@ -522,7 +522,7 @@ def test_gpt4ts_forward_parity(name, cuda):
 def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda):
     """Training steps replay two captured CUDA graphs (forward + stash, backward chain) once the same step shape
     repeats: step 0 runs kernel by kernel, step 1 captures, steps 2.. replay.  Losses and the parameters after
-    5 Adam steps must be bit-identical to the kernel-by-kernel run (same kernels, same order), the captured forward
+    5 Adam steps must equal the kernel-by-kernel run (same kernels, same order), the captured forward
     must pick up every optimizer update (bf16 re-casts are part of the graph), and a backward() whose activations
     were overwritten by a later forward must raise."""
     from medtsllm_b200._lib import MtsError
@@ -559,14 +559,16 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
     m0, l0 = run("0")
     m1, l1 = run("1")
     assert m0._train_graph is None and m1._train_graph.entry is not None and m1._train_graph.entry["bwd"] is not None
-    assert l0 == l1, (l0, l1)
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
     assert l0[0] != l0[-1]
     for (k, p0), (_, p1) in zip(m0.named_parameters(), m1.named_parameters()):
-        assert torch.equal(p0, p1), k
+        # (not torch.equal: the patch-embedding conv gradient is reduced with fp32 atomics, whose summation order —
+        # hence the last bits of that gradient and of everything Adam derives from it — varies from run to run)
+        torch.testing.assert_close(p0, p1, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
     # evaluation after training on the graph sees the trained weights
     m0.eval(); m1.eval()
     with torch.no_grad():
-        assert torch.equal(m0(base), m1(base))
+        torch.testing.assert_close(m0(base), m1(base), rtol=1e-4, atol=1e-6)
     # stale activations: two forwards on the graph, backward through the first
     m1.train()
     ya = m1(base)
