@@ -236,6 +236,8 @@ attn_causal_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
 // ---------------------------------------------------------------------------------------------
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cosb,
                                const float* __restrict__ sinb, int64_t rows, int L, int Lc, int H, int hd) {
+  pdl_wait();
+  pdl_trigger();
   const int half = hd >> 1;
   const int vec_per_head = half >> 3;                 // 8 column pairs per item
   const int64_t per_row = (int64_t)2 * H * vec_per_head;  // q heads then k heads
@@ -297,6 +299,8 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                            float* __restrict__ lse, int Bp, int L_all, int Lc_all, int spc, int rows_alloc, int H,
                            float scale_log2e) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kPitch = HD + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -509,7 +513,8 @@ static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int B
   const int grid = (groups + (Lc > 0 ? 1 : 0)) * H;
   const int rows_alloc = std::max(seq_rows_alloc(L, Lc, spc), Lc > 0 ? seq_rows_alloc(Lc, 0, 1) : 0);
   const size_t smem = (size_t)(2 * rows_alloc + 8 * 16) * (HD + 8) * 2 + 16;
-  ks<<<grid, kSeqThreads, smem, stream>>>(
+  LAUNCH_PDL(ks, grid, kSeqThreads, smem, stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, Bp, L, Lc, spc,
       rows_alloc, H, scale * 1.4426950408889634f);
   count_launch();
@@ -553,6 +558,8 @@ static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, ui
 __global__ void __launch_bounds__(256)
 attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                       float* __restrict__ delta, int L, int H, int hd, int64_t total) {
+  pdl_wait();
+  pdl_trigger();
   // one warp per (b, l, h); delta laid out [b, h, l]
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= total) return;
@@ -845,6 +852,8 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
                        const float* __restrict__ lse, const float* __restrict__ delta,
                        __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int Lc, int spc, int rows_alloc, int H,
                        float scale) {
+  pdl_wait();
+  pdl_trigger();
   // Lc > 0: shared-prefix layout as in attn_causal_fwd_seq_kernel (a CTA serves spc samples of one head; the prefix
   // K/V are staged once).  qkv holds every row (prefix rows once, then Ls = L - Lc own rows per sample); dout / lse /
   // delta / dqkv hold the samples' own rows only ([Bp*Ls, ...]): the prefix has no trainable ancestor, so no gradient
@@ -941,6 +950,8 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                         const float* __restrict__ lse, const float* __restrict__ delta,
                         __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int spc, int H, float scale) {
+  pdl_wait();
+  pdl_trigger();
   // A CTA serves spc consecutive samples of one head (short own-token runs would otherwise leave most of the 8
   // warps without a key strip): sample i keeps its Q / dO / lse / delta rows at [i*Lp, i*Lp + L).
   constexpr int kPitch = HD + 8;
@@ -1047,6 +1058,8 @@ attn_bwd_dkv_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, const float* _
                            const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                            const float* __restrict__ lse, const float* __restrict__ delta,
                            __nv_bfloat16* __restrict__ dqkv, int Bp, int Lc, int Ls, int H, float scale) {
+  pdl_wait();
+  pdl_trigger();
   // lse / delta: [H, Lc] for the prefix rows followed by [Bp, H, Ls] for the own rows
   constexpr int kPitch = HD + 8;
   constexpr int kVec = HD / 8;
@@ -1197,7 +1210,8 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
     attr_done = true;
   }
   const int64_t nwarps = (int64_t)Bp * L * H;
-  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+  LAUNCH_PDL(attn_bwd_delta_kernel, (int)((nwarps + 7) / 8), 256, 0, stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, L, H, HD, nwarps);
   count_launch();
   int rc_ = check_launch("attn_bwd_delta_kernel");
@@ -1215,14 +1229,16 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
         seq_attr = true;
       }
       const size_t smem = seq_bwd_smem_bytes<HD>(L);
-      sq<<<Bp * H, kSeqThreads, smem, stream>>>(
+      LAUNCH_PDL(sq, Bp * H, kSeqThreads, smem, stream,
+      
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
           delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, 0, 1, seq_rows_alloc(L, 0, 1), H, scale);
       count_launch();
       rc_ = check_launch("attn_bwd_dq_seq_kernel");
       if (rc_) return rc_;
       const int spc = seq_dkv_spc<HD>(Bp, L);
-      skv<<<((Bp + spc - 1) / spc) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L, spc), stream>>>(
+      LAUNCH_PDL(skv, ((Bp + spc - 1) / spc) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L, spc), stream,
+      
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
           delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, spc, H, scale);
       count_launch();
@@ -1277,7 +1293,8 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
     seq_attr = true;
   }
   const int64_t nwarps = (int64_t)Bp * Ls * H;
-  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+  LAUNCH_PDL(attn_bwd_delta_kernel, (int)((nwarps + 7) / 8), 256, 0, stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(out_own), reinterpret_cast<const __nv_bfloat16*>(dout_own), delta, Ls, H, HD,
       nwarps);
   count_launch();
@@ -1290,7 +1307,8 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
     const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);
     while (spc < want && seq_dq_smem_bytes<HD>(L, Lc, spc + 1) <= 220 * 1024) ++spc;
   }
-  sq<<<((Bp + spc - 1) / spc) * H, kSeqThreads, seq_dq_smem_bytes<HD>(L, Lc, spc), stream>>>(
+  LAUNCH_PDL(sq, ((Bp + spc - 1) / spc) * H, kSeqThreads, seq_dq_smem_bytes<HD>(L, Lc, spc), stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own,
       delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, L, Lc, spc, seq_rows_alloc(L, Lc, spc), H, scale);
   count_launch();
@@ -1300,7 +1318,8 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   // the plain kernel on the own rows, RoPE tables shifted to position Lc
   const int half = HD / 2;
   const int spc_kv = seq_dkv_spc<HD>(Bp, Ls);
-  skv<<<((Bp + spc_kv - 1) / spc_kv) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(Ls, spc_kv), stream>>>(
+  LAUNCH_PDL(skv, ((Bp + spc_kv - 1) / spc_kv) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(Ls, spc_kv), stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(qkv) + (int64_t)Lc * 3 * D, rc ? rc + (int64_t)Lc * half : nullptr,
       rs ? rs + (int64_t)Lc * half : nullptr, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own, delta,
       reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, Ls, spc_kv, H, scale);
@@ -1321,13 +1340,15 @@ static int launch_attn_shared_bwd_full(const uint16_t* qkv, const float* rc, con
   if (rc_) return rc_;
   // prefix rows: delta, then dQ of the prefix as one causal sequence of Lc positions
   const int64_t nwarps = (int64_t)Lc * H;
-  attn_bwd_delta_kernel<<<(int)((nwarps + 7) / 8), 256, 0, stream>>>(
+  LAUNCH_PDL(attn_bwd_delta_kernel, (int)((nwarps + 7) / 8), 256, 0, stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, Lc, H, HD, nwarps);
   count_launch();
   rc_ = check_launch("attn_bwd_delta_kernel");
   if (rc_) return rc_;
   auto sq = attn_bwd_dq_seq_kernel<HD>;
-  sq<<<H, kSeqThreads, seq_dq_smem_bytes<HD>(Lc, 0, 1), stream>>>(
+  LAUNCH_PDL(sq, H, kSeqThreads, seq_dq_smem_bytes<HD>(Lc, 0, 1), stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
       reinterpret_cast<__nv_bfloat16*>(dqkv), 1, Lc, 0, 1, seq_rows_alloc(Lc, 0, 1), H, scale);
   count_launch();
@@ -1341,7 +1362,8 @@ static int launch_attn_shared_bwd_full(const uint16_t* qkv, const float* rc, con
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd prefix)", e);
     attr = true;
   }
-  kp<<<H * ((Lc + 127) / 128), kSeqThreads, dkv_prefix_smem_bytes<HD>(), stream>>>(
+  LAUNCH_PDL(kp, H * ((Lc + 127) / 128), kSeqThreads, dkv_prefix_smem_bytes<HD>(), stream,
+      
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
       reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, Lc, Ls, H, scale);
   count_launch();
@@ -1445,7 +1467,8 @@ extern "C" int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* ro
   const int64_t total = rows * 2 * H * (hd / 16);
   int64_t g = (total + 255) / 256;
   if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
-  rope_qk_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
+  LAUNCH_PDL(rope_qk_kernel, (int)g, 256, 0, (cudaStream_t)s,
+      reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
                                                      rows, L, 0, H, hd);
   count_launch();
   return check_launch("rope_qk_kernel");
@@ -1460,7 +1483,8 @@ extern "C" int mts_rope_qk_shared(uint16_t* qkv, const float* rope_cos, const fl
   const int64_t total = rows * 2 * H * (hd / 16);
   int64_t g = (total + 255) / 256;
   if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
-  rope_qk_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
+  LAUNCH_PDL(rope_qk_kernel, (int)g, 256, 0, (cudaStream_t)s,
+      reinterpret_cast<__nv_bfloat16*>(qkv), rope_cos, rope_sin,
                                                      rows, Ls, Lc, H, hd);
   count_launch();
   return check_launch("rope_qk_kernel");

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                 const __nv_bfloat16* __restrict__ dy, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                 int D, float eps, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const float* xr = x + row * ldx;
@@ -124,6 +126,8 @@ __global__ void swiglu_blk_kernel(const __nv_bfloat16* __restrict__ gu, int64_t 
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_t ld,
                                   const __nv_bfloat16* __restrict__ dact, __nv_bfloat16* __restrict__ dgu,
                                   int64_t rows, int I, int blk) {
+  pdl_wait();
+  pdl_trigger();
   const int I8 = I >> 3;
   const int64_t total = rows * I8;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -161,6 +165,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_t 
 // ------------------------------------------------------------------------------------------
 __global__ void gelu_new_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dact,
                                 __nv_bfloat16* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_trigger();
   // dact == nullptr: out = gelu_new(pre); else out = dact * gelu_new'(pre)
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n;
        i += (int64_t)gridDim.x * blockDim.x * 2) {
@@ -325,11 +331,13 @@ static int norm_bwd_common(bool ln, const float* x, int64_t ldx, const float* w,
     return set_error(MTS_ERR_INVALID_ARG, "%s: misaligned pointer", name);
   if (rows == 0) return MTS_OK;
   if (ln)
-    norm_bwd_kernel<true><<<rows, 256, 0, (cudaStream_t)s>>>(
+    LAUNCH_PDL(norm_bwd_kernel<true>, rows, 256, 0, (cudaStream_t)s,
+      
         x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), D, eps,
         accumulate);
   else
-    norm_bwd_kernel<false><<<rows, 256, 0, (cudaStream_t)s>>>(
+    LAUNCH_PDL(norm_bwd_kernel<false>, rows, 256, 0, (cudaStream_t)s,
+      
         x, ldx, w, reinterpret_cast<const __nv_bfloat16*>(dy), dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), D, eps,
         accumulate);
   count_launch();
@@ -365,7 +373,8 @@ extern "C" int mts_swiglu_bwd(const uint16_t* gu, int64_t ld, const uint16_t* da
       (I % blk) || ld < 2 * (int64_t)I)
     return set_error(MTS_ERR_INVALID_ARG, "mts_swiglu_bwd: bad args");
   if (rows == 0) return MTS_OK;
-  swiglu_bwd_kernel<<<bw_grid(rows * (I / 8), 256), 256, 0, (cudaStream_t)s>>>(
+  LAUNCH_PDL(swiglu_bwd_kernel, bw_grid(rows * (I / 8), 256), 256, 0, (cudaStream_t)s,
+      
       reinterpret_cast<const __nv_bfloat16*>(gu), ld, reinterpret_cast<const __nv_bfloat16*>(dact),
       reinterpret_cast<__nv_bfloat16*>(dgu), rows, I, blk);
   count_launch();
@@ -377,7 +386,8 @@ extern "C" int mts_gelu_new(const uint16_t* pre, const uint16_t* dact, uint16_t*
   if (!pre || !out || n < 0 || (n % 2))
     return set_error(MTS_ERR_INVALID_ARG, "mts_gelu_new: bad args (n must be even)");
   if (n == 0) return MTS_OK;
-  gelu_new_kernel<<<bw_grid(n / 2, 256), 256, 0, (cudaStream_t)s>>>(
+  LAUNCH_PDL(gelu_new_kernel, bw_grid(n / 2, 256), 256, 0, (cudaStream_t)s,
+      
       reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact),
       reinterpret_cast<__nv_bfloat16*>(out), n);
   count_launch();

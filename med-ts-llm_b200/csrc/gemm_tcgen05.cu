@@ -84,6 +84,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are
+  // needed from here on.  The successor may be scheduled as soon as every CTA of this grid got this far.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -186,7 +190,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_done = true;
   }
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p);
+  if (le != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_kernel)", le);
   count_launch();
   return check_launch("gemm_bf16_nt_kernel");
 }
@@ -233,12 +238,21 @@ bool gemm_2cta_enabled() {
   }
   return g_gemm_2cta == 1;
 }
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MTS_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;          // on by default
+  }
+  return g_pdl == 1;
+}
 }  // namespace mts
 
 using namespace mts;
 
 extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
+  if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }
 

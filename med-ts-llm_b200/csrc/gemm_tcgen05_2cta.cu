@@ -113,6 +113,8 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();       // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -218,13 +220,15 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = kPairSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
   count_launch();
   if (e != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_2cta_kernel)", e);

@@ -249,3 +249,15 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
 }  // namespace mts
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched with the programmatic-stream-serialization attribute
+// (mts::launch_pdl) may start while its predecessor on the stream is still draining: its CTAs run their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in pdl_wait() until the
+// predecessor has completed and its memory is visible.  pdl_trigger() tells the scheduler this CTA no longer
+// needs the successor held back; the successor launches once every CTA of this grid has triggered or exited.
+// Both are no-ops in a launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+

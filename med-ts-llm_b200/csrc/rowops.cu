@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(256)
 norm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y_bf16,
                  float* __restrict__ y_f32, int D, float eps) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const float* xr = x + (int64_t)blockIdx.x * ldx;
   const int D4 = D >> 2;  // D % 4 == 0 enforced on the host
@@ -303,10 +305,10 @@ static int norm_common(bool ln, const float* x, int64_t ldx, const float* w, con
     return set_error(MTS_ERR_INVALID_ARG, "%s: D, ldx must be multiples of 4 and pointers 16-byte aligned", name);
   if (rows == 0) return MTS_OK;
   if (ln)
-    norm_rows_kernel<true><<<rows, 256, 0, (cudaStream_t)s>>>(
+    LAUNCH_PDL(norm_rows_kernel<true>, rows, 256, 0, s,
         x, ldx, w, b, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, D, eps);
   else
-    norm_rows_kernel<false><<<rows, 256, 0, (cudaStream_t)s>>>(
+    LAUNCH_PDL(norm_rows_kernel<false>, rows, 256, 0, s,
         x, ldx, w, nullptr, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, D, eps);
   count_launch();
   return check_launch(name);

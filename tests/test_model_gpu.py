@@ -559,7 +559,7 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
     m0, l0 = run("0")
     m1, l1 = run("1")
     assert m0._train_graph is None and m1._train_graph.entry is not None and m1._train_graph.entry["bwd"] is not None
-    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
     assert l0[0] != l0[-1]
     for (k, p0), (_, p1) in zip(m0.named_parameters(), m1.named_parameters()):
         # (not torch.equal: the patch-embedding conv gradient is reduced with fp32 atomics, whose summation order —
