@@ -1,0 +1,83 @@
+"""Parity at BASELINE.json's FULL sizes, through size-independent properties (the oracle needs minutes per forward
+at these sizes, so it checks the small fixtures; here the kernel path is checked against itself and against
+invariances of the reference's algorithm):
+
+  * in-batch prompt sharing == per-sample prompt rows, bit for bit (forward), and to rounding (adapter gradients);
+  * CUDA-graph replay == kernel-by-kernel launches, bit for bit;
+  * samples are independent: permuting the batch permutes the predictions, bit for bit (no cross-sample leakage
+    through the shared-prefix layout, the multi-sample attention CTAs or the batched GEMM tiles);
+  * RevIN equivariance (models/layers/RevIN.py:37-69): for the de-normalised tasks a per-channel affine map of the
+    window, x -> a*x + c with a > 0, maps the prediction the same way (up to the eps = 1e-5 inside the variance).
+
+Random-init backbones of the named architectures (BASELINE configs[1] Llama-2-7B shape, configs[3] GPT-2-medium)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(workload, cuda, seed=0):
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.model import MedTsLLM
+    from medtsllm_b200.synthetic import WORKLOADS, AttrDict, FixedLengthTokenizer, SyntheticDataset, experiment_config, make_inputs
+    w = WORKLOADS[workload]
+    bb = KernelBackbone.random_init(w.backbone, cuda, seed=seed)
+    torch.manual_seed(0)
+    model = MedTsLLM(AttrDict(experiment_config(w)), SyntheticDataset(w), backbone=bb,
+                     tokenizer=FixedLengthTokenizer(w.backbone.vocab, w.prompt_len)).to(cuda, torch.float32).eval()
+    return w, model, make_inputs(w)["x_enc"].to(cuda)
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("workload", ["bidmc_llama2_7b", "psm_gpt2_medium"])
+def test_full_size_forward_properties(workload, cuda):
+    w, model, x = _build(workload, cuda)
+
+    def fwd(xx, share=True, graph=False):
+        model.share_prompt_prefix, model.use_cuda_graph = share, graph
+        with torch.no_grad():
+            return model({"x_enc": xx}).clone()
+
+    ref = fwd(x)
+    assert ref.shape[0] == w.B and torch.isfinite(ref).all()
+    ids = model.prompt_token_ids({"x_enc": x})
+    assert model._shared_prefix_len(ids, w.B, w.seq) == w.prompt_len          # the whole prompt is shared
+    assert torch.equal(fwd(x, share=False), ref)                              # prompt sharing
+    for _ in range(3):                                                        # eager, capture, replay
+        assert torch.equal(fwd(x, graph=True), ref)
+    perm = torch.randperm(w.B, generator=torch.Generator().manual_seed(1)).to(cuda)
+    assert torch.equal(fwd(x[perm].contiguous()), ref[perm])                  # independent samples
+    if w.task in ("forecasting", "reconstruction", "anomaly_detection"):
+        g = torch.Generator().manual_seed(2)
+        a = (torch.rand(w.C, generator=g) * 3 + 0.5).to(cuda)
+        c = (torch.rand(w.C, generator=g) * 40 - 20).to(cuda)
+        out = fwd(x * a + c)
+        want = ref * a + c
+        assert _rel(out - c, want - c) < 2e-3, _rel(out - c, want - c)         # RevIN equivariance
+    else:
+        assert (ref >= 0).all() and (ref <= 1).all()                          # boundary probabilities (sigmoid)
+
+
+def test_full_size_training_gradients_shared_vs_per_sample(cuda):
+    """BASELINE configs[1] at full size: every adapter gradient with the shared-prefix backward (own rows only)
+    against the per-sample-prompt backward (all 6144 rows)."""
+    w, model, x = _build("bidmc_llama2_7b", cuda)
+    model.train()
+    model.use_train_graph = "0"
+    wgt = torch.randn(w.B, w.pred, generator=torch.Generator().manual_seed(5)).to(cuda)
+    grads = {}
+    for share in (True, False):
+        model.share_prompt_prefix = share
+        model.zero_grad(set_to_none=True)
+        y = model({"x_enc": x})
+        (y * wgt).sum().backward()
+        torch.cuda.synchronize()
+        grads[share] = {k: p.grad.clone() for k, p in model.named_parameters()}
+        assert all(torch.isfinite(g).all() for g in grads[share].values())
+    for k, g0 in grads[False].items():
+        e = _rel(grads[True][k], g0)
+        sib = grads[False].get(k.rsplit(".", 1)[0] + ".weight", g0).abs().max().item()
+        assert e < 5e-3 or (grads[True][k] - g0).abs().max().item() <= 1e-3 * sib, (k, e)
