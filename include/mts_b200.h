@@ -108,8 +108,20 @@ int mts_revin_denorm(float* y, const float* mean, const float* stdev, int B, int
  *   mode 1: out_x fp32 [B, T, D] = embedding, zero-padded to D columns (:212), + wpe[t] (HF GPT-2 position table)
  * (anomaly_detection needs no front end: its per-time-step "segments" centre the series to exactly zero, :155-164.) */
 int mts_gpt4ts_embed(const float* x, const float* w_conv, const float* pe, const float* wpe, float* mean,
-                     float* stdev, uint16_t* out_t, float* out_x, int B, int T, int C, int d_model, int D,
-                     int ld_t, int mode, float eps, mts_stream_t stream);
+                     float* stdev, uint16_t* out_t, float* out_x, uint16_t* out_nt, int B, int T, int C, int d_model,
+                     int D, int ld_t, int mode, float eps, mts_stream_t stream);
+/* (mode 0 only, optional) out_nt bf16 [B, T, d_model]: the same embedding, not transposed — the B operand of the
+ * time-axis Linear's weight gradient in training. */
+/* Gradient of the TokenEmbedding conv weight (autograd of models/layers/embed.py:29-46 as GPT4TS calls it):
+ * dw[d, c, k] = sum_{b,t} denc(b, d, t) * xn[b, (t+k-1) mod T, c];  denc fp32, element (b, d, t) at b*sb + d*sd + t*st
+ * ([B, d_model, T] after the time-axis Linear, [B, T, D] straight from the residual stream); dw fp32 [d_model, C, 3]. */
+int mts_gpt4ts_conv_wgrad(const float* x, const float* mean, const float* stdev, const float* denc, float* dw,
+                          int B, int T, int C, int d_model, int64_t sb, int64_t sd, int64_t st, mts_stream_t stream);
+/* LayerNorm (layernorm != 0) / RMSNorm parameter gradients, stage 1: partial fp32 [ceil(rows/32), 2*D] =
+ * per-32-row sums of dy * xhat (first D columns) and dy (last D columns); sum the partials with mts_colsum.
+ * GPT4TS trains the GPT-2 LayerNorms (models/gpt4ts.py:47-53).  x fp32 [rows, ldx], dy bf16 [rows, D]. */
+int mts_norm_wgrad_partial(const float* x, int64_t ldx, const uint16_t* dy, float* partial, int rows, int D,
+                           float eps, int layernorm, mts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K3/K4/K7/K9/K10/K11/K12/K13  tcgen05 GEMM with fused epilogues                              */

@@ -407,6 +407,70 @@ extern "C" int mts_softmax_bwd_rows(const uint16_t* p, const float* dp, uint16_t
   return check_launch("softmax_bwd_rows_kernel");
 }
 
+// ------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm parameter gradients (GPT4TS trains the GPT-2 LayerNorms, models/gpt4ts.py:47-53):
+//   dgamma[d] = sum_r dy[r, d] * xhat[r, d],  dbeta[d] = sum_r dy[r, d],  xhat recomputed from x.
+// Stage 1 (this kernel): one CTA per 32 rows writes its partial sums [2*D] (row statistics by one warp per row,
+// then one thread per column); stage 2 = mts_colsum over the partials.  Deterministic.
+// ------------------------------------------------------------------------------------------
+namespace mts {
+template <bool kLayerNorm>
+__global__ void __launch_bounds__(256)
+norm_wgrad_partial_kernel(const float* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ dy,
+                          float* __restrict__ partial, int rows, int D, float eps) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int r0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < 32; j += 8) {
+    const int r = r0 + j;
+    float mean = 0.f, rstd = 0.f;
+    if (r < rows) {
+      const float* xr = x + (int64_t)r * ldx;
+      float sum = 0.f;
+      if (kLayerNorm) {
+        for (int i = lane; i < D; i += 32) sum += xr[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mean = sum / D;
+      }
+      float ss = 0.f;
+      for (int i = lane; i < D; i += 32) { const float v = xr[i] - mean; ss += v * v; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      rstd = rsqrtf(ss / D + eps);
+    }
+    if (lane == 0) { s_mean[j] = mean; s_rstd[j] = rstd; }
+  }
+  __syncthreads();
+  const int nr = min(32, rows - r0);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float g = 0.f, b = 0.f;
+    for (int j = 0; j < nr; ++j) {
+      const float dyv = __bfloat162float(dy[(int64_t)(r0 + j) * D + d]);
+      g += dyv * (x[(int64_t)(r0 + j) * ldx + d] - s_mean[j]) * s_rstd[j];
+      b += dyv;
+    }
+    partial[(int64_t)blockIdx.x * 2 * D + d] = g;
+    partial[(int64_t)blockIdx.x * 2 * D + D + d] = b;
+  }
+}
+}  // namespace mts
+
+extern "C" int mts_norm_wgrad_partial(const float* x, int64_t ldx, const uint16_t* dy, float* partial, int rows, int D,
+                                      float eps, int layernorm, mts_stream_t s) {
+  if (!x || !dy || !partial || rows <= 0 || D <= 0 || ldx < D)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_norm_wgrad_partial: bad args");
+  const int grid = (rows + 31) / 32;
+  if (layernorm)
+    norm_wgrad_partial_kernel<true><<<grid, 256, 0, (cudaStream_t)s>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                      partial, rows, D, eps);
+  else
+    norm_wgrad_partial_kernel<false><<<grid, 256, 0, (cudaStream_t)s>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                       partial, rows, D, eps);
+  count_launch();
+  return check_launch("norm_wgrad_partial_kernel");
+}
+
 extern "C" int mts_colsum(const void* x, int dtype, int64_t ld, float* out, int rows, int cols,
                           mts_stream_t s) {
   if (!x || !out || rows <= 0 || cols <= 0 || ld < cols)

@@ -181,8 +181,8 @@ static int fe_check(const char* name, int B, int T, int C, int P, int S) {
 __global__ void __launch_bounds__(256)
 gpt4ts_embed_kernel(const float* __restrict__ x, const float* __restrict__ w_conv, const float* __restrict__ pe,
                     const float* __restrict__ wpe, float* __restrict__ mean, float* __restrict__ stdev,
-                    __nv_bfloat16* __restrict__ out_t, float* __restrict__ out_x, int T, int C, int d_model, int D,
-                    int ld_t, int mode, float eps) {
+                    __nv_bfloat16* __restrict__ out_t, float* __restrict__ out_x, __nv_bfloat16* __restrict__ out_nt,
+                    int T, int C, int d_model, int D, int ld_t, int mode, float eps) {
   extern __shared__ __align__(16) float fe_smem[];
   float* xs = fe_smem;
   float* s_mean = xs + ((T * C + 3) & ~3);
@@ -205,8 +205,12 @@ gpt4ts_embed_kernel(const float* __restrict__ x, const float* __restrict__ w_con
         for (int c = 0; c < C; ++c) acc += wd[c * 3] * xp[c] + wd[c * 3 + 1] * xc[c] + wd[c * 3 + 2] * xn[c];
         acc += pe[(int64_t)t * d_model + d];
       }
-      if (mode == 0) out_t[((int64_t)b * d_model + d) * ld_t + t] = __float2bfloat16_rn(acc);
-      else           out_x[((int64_t)b * T + t) * D + d] = acc + wpe[(int64_t)t * D + d];
+      if (mode == 0) {
+        out_t[((int64_t)b * d_model + d) * ld_t + t] = __float2bfloat16_rn(acc);
+        if (out_nt) out_nt[((int64_t)b * T + t) * d_model + d] = __float2bfloat16_rn(acc);   // [B, T, d_model] (training)
+      } else {
+        out_x[((int64_t)b * T + t) * D + d] = acc + wpe[(int64_t)t * D + d];
+      }
     }
   }
   if (mode == 0 && blockIdx.x == 0 && ld_t > T)   // zero the row padding (the GEMM's TMA extent stops at T anyway)
@@ -214,13 +218,47 @@ gpt4ts_embed_kernel(const float* __restrict__ x, const float* __restrict__ w_con
       out_t[((int64_t)b * d_model + i / (ld_t - T)) * ld_t + T + i % (ld_t - T)] = __float2bfloat16_rn(0.f);
 }
 
+// Weight gradient of that conv: dW[d, c, k] = sum_{b,t} denc(b, d, t) * xn[b, (t + k - 1) mod T, c], xn recomputed from
+// the raw window and the saved statistics.  One CTA per output channel d, one thread per (c, k); deterministic.
+__global__ void __launch_bounds__(128)
+gpt4ts_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdev,
+                         const float* __restrict__ denc, float* __restrict__ dw, int B, int T, int C, int d_model,
+                         int64_t sb, int64_t sd, int64_t st) {
+  const int d = blockIdx.x;
+  for (int j = threadIdx.x; j < 3 * C; j += blockDim.x) {
+    const int c = j / 3, k = j - c * 3;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float mu = mean[b * C + c], inv = 1.0f / stdev[b * C + c];
+      const float* g = denc + b * sb + d * sd;          // element (b, d, t) at b*sb + d*sd + t*st
+      const float* xb = x + (int64_t)b * T * C + c;
+      for (int t = 0; t < T; ++t) {
+        int ts = t + k - 1;
+        ts = ts < 0 ? T - 1 : (ts >= T ? 0 : ts);
+        acc += g[t * st] * ((xb[(int64_t)ts * C] - mu) * inv);
+      }
+    }
+    dw[((int64_t)d * C + c) * 3 + k] = acc;
+  }
+}
+
 }  // namespace mts
 
 using namespace mts;
 
+extern "C" int mts_gpt4ts_conv_wgrad(const float* x, const float* mean, const float* stdev, const float* denc,
+                                     float* dw, int B, int T, int C, int d_model, int64_t sb, int64_t sd, int64_t st,
+                                     mts_stream_t s) {
+  if (!x || !mean || !stdev || !denc || !dw || B <= 0 || T <= 0 || C <= 0 || d_model <= 0 || sb <= 0 || sd <= 0 || st <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gpt4ts_conv_wgrad: bad args");
+  gpt4ts_conv_wgrad_kernel<<<d_model, 128, 0, (cudaStream_t)s>>>(x, mean, stdev, denc, dw, B, T, C, d_model, sb, sd, st);
+  count_launch();
+  return check_launch("gpt4ts_conv_wgrad_kernel");
+}
+
 extern "C" int mts_gpt4ts_embed(const float* x, const float* w_conv, const float* pe, const float* wpe, float* mean,
-                                float* stdev, uint16_t* out_t, float* out_x, int B, int T, int C, int d_model, int D,
-                                int ld_t, int mode, float eps, mts_stream_t s) {
+                                float* stdev, uint16_t* out_t, float* out_x, uint16_t* out_nt, int B, int T, int C,
+                                int d_model, int D, int ld_t, int mode, float eps, mts_stream_t s) {
   if (!x || !mean || !stdev || !w_conv || !pe || B <= 0 || T <= 0 || C <= 0 || d_model <= 0 || mode < 0 || mode > 1)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gpt4ts_embed: bad args");
   if (mode == 0 && (!out_t || ld_t < T))
@@ -239,7 +277,8 @@ extern "C" int mts_gpt4ts_embed(const float* x, const float* w_conv, const float
   if (chunks > T) chunks = T;
   if (chunks < 1) chunks = 1;
   gpt4ts_embed_kernel<<<dim3(chunks, B), 256, smem, (cudaStream_t)s>>>(
-      x, w_conv, pe, wpe, mean, stdev, reinterpret_cast<__nv_bfloat16*>(out_t), out_x, T, C, d_model, D, ld_t, mode, eps);
+      x, w_conv, pe, wpe, mean, stdev, reinterpret_cast<__nv_bfloat16*>(out_t), out_x,
+      reinterpret_cast<__nv_bfloat16*>(out_nt), T, C, d_model, D, ld_t, mode, eps);
   count_launch();
   return check_launch("gpt4ts_embed_kernel");
 }

@@ -80,7 +80,9 @@ SIGNATURES = {
     "mts_attn_causal_shared_bwd_full": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mts_rope_qk_shared": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mts_prompt_gather_shared": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "mts_gpt4ts_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "mts_gpt4ts_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "mts_gpt4ts_conv_wgrad": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _p],
+    "mts_norm_wgrad_partial": [_p, _i64, _p, _p, _i, _i, _f, _i, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],
 }

@@ -329,7 +329,7 @@ class KernelBackbone:
         return out, x
 
     def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None,
-                 Lc: int = 0):
+                 Lc: int = 0, norm_grads: dict | None = None):
         """dgrad through the frozen stack: dhid = dL/d(final-norm output) bf16 [Bp*L, D] -> returns
         (dL/d(input residual stream) fp32 [Bp*L, D], LoRA gradients aligned with lora.params() or None).
         No gradients for the frozen weights.
@@ -337,7 +337,10 @@ class KernelBackbone:
         Lc > 0 (shared-prefix layout): with a frozen backbone the prefix rows have no trainable ancestor,
         so the whole chain runs on the samples' own rows only — dhid and the result are [Bp*(L-Lc), D] and
         every stashed tensor is read from row Lc on.  With LoRA the prefix rows matter (they reach the A/B
-        pairs): dhid and the result then hold all Lc + Bp*(L-Lc) rows."""
+        pairs): dhid and the result then hold all Lc + Bp*(L-Lc) rows.
+
+        `norm_grads` (dict): also collect the (weight, bias) gradients of every norm — keys ("ln_f",), (layer, "ln1"),
+        (layer, "ln2") — for models that train them (GPT4TS, models/gpt4ts.py:47-53)."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
         Ls = L - Lc
@@ -353,6 +356,8 @@ class KernelBackbone:
         bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
         dR = torch.empty(M, D, device=dev, dtype=torch.float32)
         dRb, dH = bf(M, D), bf(M, D)       # dRb: bf16 copy of dR, refreshed by every norm backward
+        if norm_grads is not None:
+            norm_grads[("ln_f",)] = ops.norm_wgrad(x_final[own], dhid, s.eps, layernorm=not llama)
         norm_bwd(x_final[own], self.final_norm_w, dhid, dR, s.eps, accumulate=False, dx_bf16=dRb)
         lora_grads = [None] * len(lora.params()) if lora is not None else None
         for li, lay, st in zip(reversed(range(len(self.layers))), reversed(self.layers), reversed(stash)):
@@ -367,6 +372,8 @@ class KernelBackbone:
                 ops.gemm(dRb, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
                 dpre = ops.gelu_new(st["pre"][own], dact)
                 ops.gemm(dpre, lay["wfc_t"], dH, m=M, n=D, k=s.inter)
+            if norm_grads is not None:
+                norm_grads[(li, "ln2")] = ops.norm_wgrad(st["x_mid"][own], dH, s.eps, layernorm=not llama)
             norm_bwd(st["x_mid"][own], lay["ln2"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
             # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
             datt = bf(M, D)
@@ -386,6 +393,8 @@ class KernelBackbone:
                 for t in range(len(lora.targets)):
                     lora_grads[lora.index(li, t)] = dAs[t]
                     lora_grads[nA + lora.index(li, t)] = dBs[t]
+            if norm_grads is not None:
+                norm_grads[(li, "ln1")] = ops.norm_wgrad(st["x_in"][own], dH, s.eps, layernorm=not llama)
             norm_bwd(st["x_in"][own], lay["ln1"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
         return dR, lora_grads
 

@@ -407,6 +407,19 @@ def rope_qk_(qkv, Bp, L, H, hd, rope):
     return qkv
 
 
+def norm_wgrad(x, dy, eps, layernorm=True):
+    """(dgamma, dbeta) fp32 [D] of a LayerNorm / RMSNorm whose output gradient is dy bf16 [rows, D] (x fp32 [rows, D])."""
+    _chk(x, torch.float32, "x"); _chk(dy, torch.bfloat16, "dy")
+    rows, D = dy.shape
+    if not dy.is_contiguous() or x.shape != (rows, D) or x.stride(1) != 1:
+        raise MtsError("norm_wgrad: x fp32 [rows, D] (unit column stride) and contiguous dy bf16 [rows, D] required")
+    partial = torch.empty((rows + 31) // 32, 2 * D, device=x.device, dtype=torch.float32)
+    _lib.call("mts_norm_wgrad_partial", x.data_ptr(), x.stride(0), dy.data_ptr(), partial.data_ptr(), rows, D, eps,
+              1 if layernorm else 0, _stream())
+    both = colsum(partial)
+    return both[:D], both[D:]
+
+
 def rope_qk_shared_(qkv, Bp, Lc, Ls, H, hd, rope):
     """rope_qk_ on the shared-prefix row layout (qkv bf16 [Lc + Bp*Ls, 3*H*hd])."""
     _chk(qkv, torch.bfloat16, "qkv")
