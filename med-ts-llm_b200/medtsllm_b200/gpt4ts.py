@@ -4,9 +4,9 @@ GPT-2 kernel stack as MedTsLLM.
 
 Same constructor `(config, dataset)`, same `forward(inputs: dict) -> Tensor`, same config keys
 (`models.gpt4ts.{d_ff,d_model,gpt_layers,train_mlp,patching}`), same parameter names for the model's own
-tensors.  Inference only in this round: the reference also trains GPT-2's LayerNorm / position parameters
-(models/gpt4ts.py:47-53), which needs weight gradients inside the backbone — calling it with autograd
-enabled raises instead of silently returning a tensor without a graph.  Tasks: the four the reference's
+tensors and for the GPT-2 tensors the reference trains (every LayerNorm and the position table,
+models/gpt4ts.py:47-53; `train_mlp = true` is not implemented).  Inference and training
+(`loss.backward()` through one autograd.Function with a manual backward, like train.py).  Tasks: the four the reference's
 Trainers can run it on (forecasting, anomaly_detection, semantic_segmentation, segmentation); like the
 reference, `reconstruction` is listed in `supported_tasks` but rejected by `forward` (models/gpt4ts.py:103-104).
 
@@ -119,6 +119,8 @@ class GPT4TS(nn.Module):
             raise ValueError("GPT4TS needs patching.patch_len = 1 (the reference's conv shape mismatch otherwise)")
         self._backbone = backbone
         object.__setattr__(self, "_hf_model", None)
+        if backbone is not None and backbone.device.type == "cuda":
+            self._mirror_gpt2_parameters()
         if backbone is None:
             from transformers.models.gpt2.modeling_gpt2 import GPT2Model
             hf = GPT2Model.from_pretrained("gpt2", output_attentions=True, output_hidden_states=True)
@@ -137,6 +139,7 @@ class GPT4TS(nn.Module):
             if self._backbone is None:
                 self._backbone = KernelBackbone.from_hf(self._hf_model, dev)
                 object.__setattr__(self, "_hf_model", None)
+                self._mirror_gpt2_parameters()
             elif self._backbone.device != dev:
                 raise MtsError("the kernel backbone lives on another device")
             self.device = dev
@@ -159,39 +162,76 @@ class GPT4TS(nn.Module):
             raise ValueError("Task name is not valid")                      # models/gpt4ts.py:103-104
         if not x.is_cuda or self._backbone is None:
             raise MtsError("medtsllm_b200.GPT4TS runs on a CUDA device only (no CPU fallback); call .to('cuda')")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise MtsError("GPT4TS: the training path (LayerNorm / wpe gradients inside the GPT-2 blocks) is not "
-                           "implemented on the kernel stack; run inference under torch.no_grad()")
         if x.dtype != torch.float32:
             raise MtsError(f"x_enc must be fp32, got {x.dtype}")
         x = x.contiguous()
         B, T, C = x.shape
         assert T == self.seq_len and C == self.enc_in
+        bb = self._backbone
+        if self.d_model > bb.spec.hidden or self.d_ff > bb.spec.hidden or C > bb.spec.hidden:
+            raise MtsError(f"d_model / d_ff / n_features must not exceed the GPT-2 width {bb.spec.hidden}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            names, params = zip(*self._trainable())
+            return _GPT4TSFn.apply(self, x, names, *params)                 # autograd path
         if not self.use_cuda_graph:
             return self._forward_impl(x)
         key = (tuple(x.shape), x.device.index, self.training, tuple((p._version, p.data_ptr()) for p in self.parameters()))
         return self._graph.run(key, x, self._forward_impl)
 
-    def _forward_impl(self, x):
+    # ------------------------------------------------------------------------------------------ parameters
+    def _mirror_gpt2_parameters(self):
+        """The reference trains GPT-2's LayerNorm and position parameters (models/gpt4ts.py:47-53: every `ln*` and `wpe`
+        tensor has requires_grad = True).  They live in the kernel backbone; this exposes them as nn.Parameters UNDER THE
+        REFERENCE'S NAMES (gpt2.wpe.weight, gpt2.h.<i>.ln_1.weight, ..., gpt2.ln_f.bias) sharing the backbone's storage,
+        so an optimizer step on them is seen by the kernels directly."""
+        if self.train_mlp:
+            raise NotImplementedError("models.gpt4ts.train_mlp = true (GPT-2 MLP weight gradients) is not implemented")
+        bb = self._backbone
+
+        def holder(**tensors):
+            m = nn.Module()
+            for k, t in tensors.items():
+                m.register_parameter(k, nn.Parameter(t, requires_grad=True))
+            return m
+
+        g = nn.Module()
+        g.wpe = holder(weight=bb.wpe)
+        g.h = nn.ModuleList()
+        for lay in bb.layers:
+            blk = nn.Module()
+            blk.ln_1 = holder(weight=lay["ln1"], bias=lay["ln1b"])
+            blk.ln_2 = holder(weight=lay["ln2"], bias=lay["ln2b"])
+            g.h.append(blk)
+        g.ln_f = holder(weight=bb.final_norm_w, bias=bb.final_norm_b)
+        self.gpt2 = g
+
+    def _trainable(self):
+        return [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _forward_impl(self, x, stash=None):
+        """`stash` (dict): keep what the backward needs (training)."""
         B, T, C = x.shape
         bb = self._backbone
         D, dev = bb.spec.hidden, x.device
-        if self.d_model > D or self.d_ff > D or C > D:
-            raise MtsError(f"d_model / d_ff / n_features must not exceed the GPT-2 width {D}")
         T2 = T + self.pred_len
         if self.task == "anomaly_detection":
-            return self._anomaly_detection(x)
+            return self._anomaly_detection(x, stash)
         mean = torch.empty(B, C, device=dev, dtype=torch.float32)
         std = torch.empty(B, C, device=dev, dtype=torch.float32)
         w_conv = self.enc_embedding.value_embedding.tokenConv.weight.detach()
         pe = self.enc_embedding.position_embedding.pe[0, :T]
         X = torch.empty(B * T2, D, device=dev, dtype=torch.float32)
         stream = torch.cuda.current_stream().cuda_stream
+        enc_nt = None
         if self.task == "forecasting":
             ld_t = ops.ceil8(T)
             enc_t = torch.empty(B, self.d_model, ld_t, device=dev, dtype=torch.bfloat16)
+            if stash is not None:     # non-transposed copy: B operand of the time-axis Linear's weight gradient
+                enc_nt = torch.empty(B, T, self.d_model, device=dev, dtype=torch.bfloat16)
             _lib.call("mts_gpt4ts_embed", x.data_ptr(), w_conv.data_ptr(), pe.data_ptr(), 0, mean.data_ptr(),
-                      std.data_ptr(), enc_t.data_ptr(), 0, B, T, C, self.d_model, D, ld_t, 0, 1e-5, stream)
+                      std.data_ptr(), enc_t.data_ptr(), 0, 0 if enc_nt is None else enc_nt.data_ptr(), B, T, C,
+                      self.d_model, D, ld_t, 0, 1e-5, stream)
             # rows of X = wpe[t] (+ 0): HF's GPT2Model adds the position table to inputs_embeds (modeling_gpt2.py:584-585)
             ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T2, B=B)
             # Linear along time (models/gpt4ts.py:137): X[b, t', :d_model] += W_pre[t', :] . enc[b, :, :] + b_pre[t']
@@ -201,8 +241,10 @@ class GPT4TS(nn.Module):
                      bias_axis=BIAS_M, epilogue=EPI_RESID_ADD)
         else:
             _lib.call("mts_gpt4ts_embed", x.data_ptr(), w_conv.data_ptr(), pe.data_ptr(), bb.wpe.data_ptr(),
-                      mean.data_ptr(), std.data_ptr(), 0, X.data_ptr(), B, T, C, self.d_model, D, 0, 1, 1e-5, stream)
-        out = self._blocks_and_out_layer(X, B, T2)
+                      mean.data_ptr(), std.data_ptr(), 0, X.data_ptr(), 0, B, T, C, self.d_model, D, 0, 1, 1e-5, stream)
+        out = self._blocks_and_out_layer(X, B, T2, stash)
+        if stash is not None:
+            stash.update(x=x, mean=mean, std=std, enc_nt=enc_nt, B=B, T2=T2)
         if self.task == "forecasting":
             ops.revin_denorm(out, mean, std)                                           # :146-147
             return out[:, -self.pred_len:, :].contiguous()
@@ -218,19 +260,22 @@ class GPT4TS(nn.Module):
                 ops.sigmoid_(out)
         return out
 
-    def _blocks_and_out_layer(self, X, B, T2):
+    def _blocks_and_out_layer(self, X, B, T2, stash=None):
         """GPT-2 blocks + ln_f, then out_layer on the first d_ff features (models/gpt4ts.py:140-143): fp32 [B, T2, n_out]."""
         bb = self._backbone
         D = bb.spec.hidden
-        hid, _ = bb.forward(X, B, T2)                                                  # bf16 [B*T2, D], ln_f applied
+        layers = [] if stash is not None else None
+        hid, x_final = bb.forward(X, B, T2, stash=layers)                              # bf16 [B*T2, D], ln_f applied
         n_out = self.out_layer.weight.shape[0]
         w_out = self._bf16_weight("out", self.out_layer.weight)                        # [n_out, ceil8(d_ff)]
         out = torch.empty(B * T2, n_out, device=X.device, dtype=torch.float32)
         ops.gemm(hid, w_out, out, m=B * T2, n=n_out, k=self.d_ff, lda=D, ldb=w_out.shape[1],
                  bias=self.out_layer.bias.detach(), bias_axis=BIAS_N)
+        if stash is not None:
+            stash.update(layers=layers, hid=hid, x_final=x_final, rows=B * T2)
         return out.view(B, T2, n_out)
 
-    def _anomaly_detection(self, x):
+    def _anomaly_detection(self, x, stash=None):
         """models/gpt4ts.py:151-177.  The statistics are taken over "segments" of seg_num = 1 time step (:155-159):
         mean = x, the centred series is identically zero, stdev = sqrt(1e-5).  The GPT-2 therefore sees the same
         input for every sample — zeros plus its position table — and the prediction is dec * sqrt(1e-5) + x
@@ -239,8 +284,113 @@ class GPT4TS(nn.Module):
         bb = self._backbone
         X = torch.empty(T, bb.spec.hidden, device=x.device, dtype=torch.float32)
         ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T, B=1)            # 0 + wpe[t]
-        dec = self._blocks_and_out_layer(X, 1, T)                                      # [1, T, C]
+        dec = self._blocks_and_out_layer(X, 1, T, stash)                               # [1, T, C]
         out = dec.expand(B, T, C).contiguous()
         std = torch.full((1, B * T * C), float(torch.tensor(1e-5, dtype=torch.float32).sqrt()), device=x.device)
         ops.revin_denorm(out.view(1, 1, -1), x.reshape(1, -1), std)                    # out * sqrt(1e-5) + x
+        if stash is not None:
+            stash.update(x=x, B=B, T2=T)
         return out
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _backward_impl(self, st, dout):
+        """Manual backward of `_forward_impl` (the reference gets it from autograd): gradients of the model's own
+        tensors and of GPT-2's LayerNorm / position parameters, keyed by parameter name.  Every contraction is the
+        tcgen05 NT GEMM on transposed operands, as in train.py."""
+        bb = self._backbone
+        dev = dout.device
+        D, dm, dff = bb.spec.hidden, self.d_model, self.d_ff
+        B, T, C = st["x"].shape
+        T2 = st["T2"]
+        f32 = lambda *s_: torch.empty(*s_, device=dev, dtype=torch.float32)          # noqa: E731
+        anomaly = self.task == "anomaly_detection"
+        n_out = self.out_layer.weight.shape[0]
+        grads = {}
+        # ---- output side: de-normalisation / slicing / squeeze
+        if self.task == "forecasting":
+            full = torch.zeros(B, T2, C, device=dev, dtype=torch.float32)
+            full[:, -self.pred_len:, :] = dout                                       # only the last pred_len steps are returned
+            dy = ops.revin_denorm_bwd(full, st["std"]).view(B * T2, n_out)            # d dec = dout * std
+        elif anomaly:
+            # out[b] = dec * sqrt(1e-5) + x[b] with ONE dec for the whole batch: d dec = sqrt(1e-5) * sum_b dout[b]
+            summed = ops.colsum(dout.reshape(B, T * C).contiguous()).view(1, T * C)
+            dy = ops.revin_denorm_bwd(summed.view(1, 1, -1), torch.full((1, T * C), float(torch.tensor(1e-5).sqrt()),
+                                                                        device=dev)).view(T, n_out)
+        else:
+            dy = dout.reshape(B * T2, n_out).contiguous()
+        M = dy.shape[0]                                                              # rows through the blocks
+        Bb = M // T2                                                                 # sequences through the blocks
+        # ---- out_layer: dec = hid[:, :d_ff] W_out^T + b
+        grads["out_layer.bias"] = ops.colsum(dy)
+        Mp = ops.ceil8(M)
+        hid_t = ops.transpose_strided(st["hid"], rows=M, cols=dff, ld_in=D)           # [d_ff, Mp]
+        dy_t = ops.transpose_strided(dy, rows=M, cols=n_out)                          # [n_out, Mp]
+        g_wout = f32(n_out, dff)
+        ops.gemm(dy_t, hid_t, g_wout, m=n_out, n=dff, k=M, lda=Mp, ldb=Mp)
+        grads["out_layer.weight"] = g_wout
+        dy_b = ops.cast_rows(dy, rows=M, cols=n_out)                                  # [M, ceil8(n_out)]
+        w_out = self._bf16_weight("out", self.out_layer.weight)                       # [n_out, ceil8(d_ff)]
+        w_out_t = ops.transpose_strided(w_out, rows=n_out, cols=dff, ld_in=w_out.shape[1])   # [d_ff, ceil8(n_out)]
+        dhid = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+        ops.gemm(dy_b, w_out_t, dhid, m=M, n=dff, k=n_out, lda=dy_b.shape[1], ldb=w_out_t.shape[1], ldd=D)
+        # ---- GPT-2 blocks: dgrad + LayerNorm parameter gradients
+        ng = {}
+        dX, _ = bb.backward(dhid, st["x_final"], st["layers"], Bb, T2, norm_grads=ng)  # fp32 [M, D]
+        grads["gpt2.ln_f.weight"], grads["gpt2.ln_f.bias"] = ng[("ln_f",)]
+        for li in range(len(bb.layers)):
+            grads[f"gpt2.h.{li}.ln_1.weight"], grads[f"gpt2.h.{li}.ln_1.bias"] = ng[(li, "ln1")]
+            grads[f"gpt2.h.{li}.ln_2.weight"], grads[f"gpt2.h.{li}.ln_2.bias"] = ng[(li, "ln2")]
+        # ---- position table: X[b, t] = emb[b, t] + wpe[t]
+        g_pos = ops.colsum(dX.view(Bb, T2 * D)).view(T2, D) if Bb > 1 else dX.view(T2, D)
+        g_wpe = torch.zeros_like(bb.wpe)
+        g_wpe[:T2] = g_pos
+        grads["gpt2.wpe.weight"] = g_wpe
+        if anomaly:
+            return grads
+        # ---- embedding side
+        x, mean, std = st["x"], st["mean"], st["std"]
+        g_conv = f32(dm, C, 3)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.task == "forecasting":
+            # X[b, t', :dm] = sum_t W_pre[t', t] enc[b, t, :] + b_pre[t']
+            dXb = ops.cast_bf16(dX)                                                   # [B*T2, D]
+            g_wpre = f32(T2, T)
+            for b in range(B):                                                        # sum over the batch, in place
+                ops.gemm(dXb, st["enc_nt"], g_wpre, m=T2, n=T, k=dm, lda=D, a_off=b * T2 * D, ldb=dm, b_off=b * T * dm,
+                         epilogue=EPI_RESID_ADD if b else 0)
+            grads["predict_linear_pre.weight"] = g_wpre
+            grads["predict_linear_pre.bias"] = ops.rowsum(g_pos[:, :dm].contiguous())
+            w_pre = self._bf16_weight("pre", self.predict_linear_pre.weight)          # [T2, ceil8(T)]
+            w_pre_t = ops.transpose_strided(w_pre, rows=T2, cols=T, ld_in=w_pre.shape[1])     # [T, ceil8(T2)]
+            denc_t = f32(B, dm, T)                                                    # d enc, transposed like enc_t
+            for b in range(B):
+                dx_t = ops.transpose_strided(dX, rows=T2, cols=dm, ld_in=D, in_off=b * T2 * D)   # [dm, ceil8(T2)]
+                ops.gemm(dx_t, w_pre_t, denc_t[b], m=dm, n=T, k=T2, lda=dx_t.shape[1], ldb=w_pre_t.shape[1])
+            _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), denc_t.data_ptr(),
+                      g_conv.data_ptr(), B, T, C, dm, dm * T, T, 1, stream)
+        else:
+            # the embedding went straight into the residual stream: d enc[b, t, d] = dX[b, t, d]
+            _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), dX.data_ptr(),
+                      g_conv.data_ptr(), B, T, C, dm, T * D, 1, D, stream)
+        grads["enc_embedding.value_embedding.tokenConv.weight"] = g_conv
+        return grads
+
+
+class _GPT4TSFn(torch.autograd.Function):
+    """`loss.backward()` of the reference's Trainer (tasks/forecasting.py:26) through GPT4TS on the kernel stack."""
+
+    @staticmethod
+    def forward(ctx, model, x, names, *params):
+        stash = {}
+        out = model._forward_impl(x, stash)
+        ctx.model, ctx.stash, ctx.names = model, stash, names
+        return out
+
+    @staticmethod
+    @torch.no_grad()
+    def backward(ctx, dout):
+        grads = ctx.model._backward_impl(ctx.stash, dout.float().contiguous())
+        ctx.stash = None
+        # parameters the forward never reads (temporal_embedding, predict_linear, ln / ln_proj: unused by the
+        # reference's forward too) get no gradient, exactly as under autograd
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)

@@ -492,7 +492,8 @@ def test_gpt4ts_forward_parity(name, cuda):
     backbone = KernelBackbone.from_hf(gpt4ts_hf_model(bbf, n_layers), cuda)
     model = GPT4TS(Cfg(fix["config"]), Dataset(fix["dataset"]), backbone=backbone)
     res = model.load_state_dict(fix["params"], strict=False)
-    assert not res.unexpected_keys and res.missing_keys == ["enc_embedding.position_embedding.pe"], res
+    assert not res.unexpected_keys and all(k == "enc_embedding.position_embedding.pe" or k.startswith("gpt2.")
+                                           for k in res.missing_keys), res
     model = model.to(cuda, torch.float32).eval()
     x = fix["inputs"]["x_enc"].to(cuda)
     with torch.no_grad():
@@ -511,11 +512,56 @@ def test_gpt4ts_forward_parity(name, cuda):
         # the prediction is x + sqrt(1e-5) * dec: check the model part on its own as well
         xin = fix["inputs"]["x_enc"]
         assert _rel_l2(out.cpu() - xin, g["output"] - xin) < 1e-2
-    with pytest.raises(MtsError):           # trainable LayerNorm / wpe inside the blocks: not on the kernel stack yet
-        model({"x_enc": x})
     with pytest.raises(MtsError):
         with torch.no_grad():
             model({"x_enc": x.cpu()})
+
+
+@pytest.mark.parametrize("name", GPT4TS_CASES)
+def test_gpt4ts_training_gradients(name, cuda):
+    """loss.backward() through medtsllm_b200.GPT4TS vs autograd through the oracle (fp32, CPU): the model's own tensors and
+    the GPT-2 tensors the reference trains (every LayerNorm weight / bias and the position table, models/gpt4ts.py:47-53).
+    Tolerance: relative L2 < 5e-2 per tensor (bf16 operands forward and backward); one Adam step must move the
+    LayerNorms inside the kernel backbone (the parameters share its storage)."""
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.gpt4ts import GPT4TS
+    from oracle import gpt4ts_oracle as G
+    fix = load_case(name)
+    bbf = load_gpt4ts_backbone()
+    n_layers = fix["config"]["models"]["gpt4ts"]["gpt_layers"]
+    backbone = KernelBackbone.from_hf(gpt4ts_hf_model(bbf, n_layers), cuda)
+    model = GPT4TS(Cfg(fix["config"]), Dataset(fix["dataset"]), backbone=backbone)
+    model.load_state_dict(fix["params"], strict=False)
+    model = model.to(cuda, torch.float32).train()
+    x = fix["inputs"]["x_enc"]
+    out = model({"x_enc": x.to(cuda)})
+    assert out.requires_grad
+    wgt = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * wgt.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    # oracle side
+    params = {k: v.clone().requires_grad_(True) for k, v in fix["params"].items()}
+    sd = {k: v.float().requires_grad_(k.startswith("ln_f") or ".ln_" in k or k.startswith("wpe")) for k, v in bbf["state"].items()}
+    ref = G.gpt4ts_forward(x, params, sd, gpt4ts_spec(fix, bbf), training=True)
+    assert _rel_l2(out, ref) < 1e-2
+    (ref * wgt).sum().backward()
+    report, bad, checked = [], [], 0
+    for k, p in model.named_parameters():
+        gref = sd[k[5:]].grad if k.startswith("gpt2.") else params[k].grad
+        if gref is None or gref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max().item() == 0, k        # unused by the forward on both sides
+            continue
+        assert p.grad is not None, k
+        e = _rel_l2(p.grad, gref)
+        checked += 1
+        report.append(f"{k.replace('gpt2.', '').replace('enc_embedding.value_embedding.', '')} {e:.1e}")
+        if not e < 5e-2:
+            bad.append((k, e))
+    print(f"\n[gpt4ts grad parity] {name}: " + "  ".join(report))
+    assert not bad and checked >= 5 + 4 * n_layers, (name, bad, checked)
+    before = backbone.layers[0]["ln1"].clone()
+    torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-2).step()
+    assert not torch.equal(backbone.layers[0]["ln1"], before)
 
 
 @pytest.mark.parametrize("name,lora", [("llama_seg_concat", False), ("gpt2_anomaly_concat", False), ("llama_seg_concat", True)])
