@@ -552,9 +552,20 @@ def test_gpt4ts_training_gradients(name, cuda):
             assert p.grad is None or p.grad.abs().max().item() == 0, k        # unused by the forward on both sides
             continue
         assert p.grad is not None, k
-        e = _rel_l2(p.grad, gref)
         checked += 1
-        report.append(f"{k.replace('gpt2.', '').replace('enc_embedding.value_embedding.', '')} {e:.1e}")
+        tag = k.replace('gpt2.', '').replace('enc_embedding.value_embedding.', '')
+        sib = k.rsplit(".", 1)[0] + ".weight"
+        if k == "predict_linear_pre.bias" and gref.abs().max() < 1e-4 * params[sib].grad.abs().max():
+            # structurally ZERO: the bias shifts all d_model features of a token by the same amount, which every LayerNorm
+            # reading the residual stream (ln_1, ln_2, ln_f) removes.  Both sides hold rounding noise only.
+            scale = dict(model.named_parameters())[sib].grad.abs().max().item()
+            e = p.grad.abs().max().item() / max(scale, 1e-30)
+            report.append(f"{tag} |g|/|gW| {e:.1e}")
+            if not e < 1e-1:
+                bad.append((k, e))
+            continue
+        e = _rel_l2(p.grad, gref)
+        report.append(f"{tag} {e:.1e}")
         if not e < 5e-2:
             bad.append((k, e))
     print(f"\n[gpt4ts grad parity] {name}: " + "  ".join(report))
