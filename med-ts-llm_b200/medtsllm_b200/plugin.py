@@ -30,8 +30,8 @@ def register(reference_root: str | None = None):
     models.model_lookup["medtsllm"] = MedTsLLM
     models.model_lookup["timellm"] = MedTsLLM
     if os.environ.get("MTS_REGISTER_GPT4TS", "0") == "1":
-        # opt-in: medtsllm_b200.GPT4TS runs inference only (evaluation of a trained run / `--test`); the
-        # reference's Trainer.train() on it raises, loudly
+        # opt-in: medtsllm_b200.GPT4TS keeps only its trainable tensors in state_dict() (not the frozen GPT-2
+        # weights), so checkpoints written by the reference's own GPT4TS do not load into it
         from .gpt4ts import GPT4TS
         models.model_lookup["gpt4ts"] = GPT4TS
     return models.model_lookup
