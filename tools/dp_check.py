@@ -58,4 +58,23 @@ if rank == 0:
     print(f"[dp_check] world={world} shard sizes={[len(list(dp.shard_batch(B, r, world))) for r in range(world)]} "
           f"worst rel-L2 (DP mean vs full-batch/world) = {t.item():.2e}")
     assert t.item() < 2e-2, t.item()      # bf16 GEMMs over different batch splits: summation-order noise
+
+# training-step graphs under data parallelism (GPT-2-sized backbone -> "auto" uses them): the same shard three times
+# (kernel by kernel, capture, replay; the all-reduce then runs after the backward graph) against the overlapped
+# kernel-by-kernel path
+model.use_train_graph = "1"
+for _ in range(3):
+    g_graph = grads(shard, sync=True)
+assert model._train_graph is not None and model._train_graph.entry is not None and model._train_graph.entry["bwd"] is not None
+model.use_train_graph = "0"
+g_eager = grads(shard, sync=True)
+worst2 = 0.0
+for k in g_eager:
+    if k != "reprogramming_layer.key_projection.bias":
+        worst2 = max(worst2, ((g_graph[k] - g_eager[k]).norm() / g_eager[k].norm().clamp_min(1e-20)).item())
+t = torch.tensor([worst2], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"[dp_check] graph replay + all-reduce vs overlapped kernel-by-kernel path: worst rel-L2 = {t.item():.2e}")
+    assert t.item() < 1e-4, t.item()      # same kernels; only the atomically reduced conv gradient differs in its last bits
 dist.destroy_process_group()
