@@ -25,6 +25,9 @@ model = MedTsLLM(Cfg(config_for(fix, materialize_llm_dir(fix, tmp / "llm"))), Da
 model.load_state_dict(fix["adapters"])
 model = model.to(dev).train()
 x = fix["inputs"]["x_enc"].to(dev)
+if x.shape[0] < 2 * world:            # every rank gets at least two windows (the fixture holds four)
+    reps = -(-2 * world // x.shape[0])
+    x = (x.repeat(reps, 1, 1) * torch.linspace(0.8, 1.2, reps * x.shape[0], device=dev)[:, None, None])[:2 * world].contiguous()
 B = x.shape[0]
 w = torch.randn(B, fix["config"]["pred_len"], generator=torch.Generator().manual_seed(1)).to(dev)
 
