@@ -13,12 +13,6 @@ import torch
 from . import _lib
 from ._lib import BIAS_N, BIAS_NONE, EPI_STORE, EPI_SWIGLU, MTS_BF16, MTS_F32, GemmArgs, MtsError
 
-__all__ = [
-    "gemm", "linear_bf16", "revin_patch_embed", "patch_gather", "revin_patch_embed_bwd",
-    "revin_denorm", "rmsnorm", "layernorm", "attn_causal", "softmax_rows", "prompt_gather",
-    "cast_bf16", "cast_f32", "transpose_to_bf16", "pack_gate_up", "swiglu", "sigmoid_", "softmax_lastdim_",
-]
-
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
