@@ -11,6 +11,7 @@
 //
 // Algorithmic work: 4*Bp*H*L*L*hd FLOP (dense; the causal half is skipped in practice).
 #include <algorithm>
+#include <cstdlib>
 
 #include "mts_internal.h"
 #include "ptx.cuh"
@@ -1045,6 +1046,193 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-prefix layout, frozen backbone: the whole backward of the samples' own tokens in ONE kernel.  A CTA
+// serves spc samples of one head and keeps everything resident — K and V of the prefix and of its samples, Q and
+// dO of its samples — staged once with cp.async.  It first computes delta = rowsum(dO * O) for its rows (the
+// separate delta pass disappears), then its 8 warps pull jobs from a shared counter: the dQ strips (16 own queries
+// against prefix + own keys), then the dK/dV strips (16 own keys against the sample's own queries).  Operands
+// come straight from the resident arrays: no per-warp staging, no second launch, no second staging of K/V/Q/dO.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kSeqThreads)
+attn_bwd_own_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
+                          const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ out_own,
+                          const __nv_bfloat16* __restrict__ dout_own, const float* __restrict__ lse_own,
+                          __nv_bfloat16* __restrict__ dqkv_own, int Bp, int L, int Lc, int spc, int rows_alloc, int H,
+                          float scale) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int kPitch = HD + 8;
+  constexpr int kVec = HD / 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int Ls = L - Lc;
+  const int Lq = (Ls + 63) & ~63;                           // rows kept per sample for Q / dO (zero padded)
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Vs = Ks + (size_t)rows_alloc * kPitch;
+  __nv_bfloat16* Qs = Vs + (size_t)rows_alloc * kPitch;     // [spc][Lq][kPitch]
+  __nv_bfloat16* dOs = Qs + (size_t)spc * Lq * kPitch;
+  float* lse_s = reinterpret_cast<float*>(dOs + (size_t)spc * Lq * kPitch);   // [spc][Lq], pre-multiplied by log2(e)
+  float* del_s = lse_s + spc * Lq;
+  int* counter = reinterpret_cast<int*>(del_s + spc * Lq);
+
+  const int grp = blockIdx.x / H, h = blockIdx.x - grp * H;
+  const int b0 = grp * spc, nb = min(spc, Bp - b0);
+  const int D = H * HD;
+  const int64_t ld = 3 * (int64_t)D;
+  const __nv_bfloat16* gbase = qkv + (int64_t)h * HD;      // row of (sample b, position p): p (p < Lc) or p + b*Ls
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale_log2e = scale * 1.4426950408889634f;
+
+  // ---- stage K, V (prefix + own rows of the nb samples: one contiguous range of global rows after the prefix)
+  const int rows_used = Lc + nb * Ls;
+  for (int i = threadIdx.x; i < rows_alloc * kVec; i += kSeqThreads) {
+    const int r = i / kVec, c = (i - r * kVec) * 8;
+    if (r < rows_used) {
+      const __nv_bfloat16* src = gbase + ((int64_t)r + (r < Lc ? 0 : (int64_t)b0 * Ls)) * ld + c;
+      cp_async16(smem_u32(Ks + r * kPitch + c), src + D);
+      cp_async16(smem_u32(Vs + r * kPitch + c), src + 2 * D);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // ---- stage Q, dO of the samples' own tokens
+  for (int i = threadIdx.x; i < spc * Lq * kVec; i += kSeqThreads) {
+    const int rr = i / kVec, c = (i - rr * kVec) * 8;
+    const int si = rr / Lq, t = rr - si * Lq;
+    if (si < nb && t < Ls) {
+      const int64_t own_row = (int64_t)(b0 + si) * Ls + t;                  // row among the own rows
+      cp_async16(smem_u32(Qs + rr * kPitch + c), gbase + (own_row + Lc) * ld + c);
+      cp_async16(smem_u32(dOs + rr * kPitch + c), dout_own + own_row * D + (int64_t)h * HD + c);
+    } else {
+      *reinterpret_cast<uint4*>(Qs + rr * kPitch + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dOs + rr * kPitch + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  if (threadIdx.x == 0) *counter = 0;
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- delta = rowsum(dO * O) and lse of the own rows (one warp per row; O read once from global)
+  for (int rr = warp; rr < spc * Lq; rr += kSeqThreads / 32) {
+    const int si = rr / Lq, t = rr - si * Lq;
+    float acc = 0.f, l = INFINITY;
+    if (si < nb && t < Ls) {
+      const int64_t own_row = (int64_t)(b0 + si) * Ls + t;
+      const __nv_bfloat16* op = out_own + own_row * D + (int64_t)h * HD;
+      const __nv_bfloat16* dp = dOs + rr * kPitch;
+      for (int i = lane * 2; i < HD; i += 64) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(op + i);
+        const uint32_t d = *reinterpret_cast<const uint32_t*>(dp + i);
+        acc += bf16_lo(a) * bf16_lo(d) + bf16_hi(a) * bf16_hi(d);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      l = lse_own[((int64_t)(b0 + si) * H + h) * Ls + t] * 1.4426950408889634f;
+    }
+    if (lane == 0) { del_s[rr] = acc; lse_s[rr] = l; }
+  }
+  __syncthreads();
+
+  const int n_strips = (Ls + 15) >> 4;                      // per sample, for both job kinds
+  const int n_dq = n_strips * nb;
+  while (true) {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counter, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= 2 * n_dq) break;
+    if (ticket < n_dq) {
+      // ------------------------------------------------------------ dQ strip: 16 own queries x (prefix + own keys)
+      const int si = ticket % nb;
+      const int t0 = (n_strips - 1 - ticket / nb) * 16;     // heaviest (latest) strips first
+      const int q0 = Lc + t0;                               // positions
+      const int soff = si * Ls;
+      const __nv_bfloat16* Qb = Qs + (size_t)si * Lq * kPitch;
+      const __nv_bfloat16* dOb = dOs + (size_t)si * Lq * kPitch;
+      const int row_a = q0 + g, row_b = row_a + 8;
+      const float lse_a = row_a < L ? lse_s[si * Lq + t0 + g] : INFINITY;
+      const float lse_b = row_b < L ? lse_s[si * Lq + t0 + g + 8] : INFINITY;
+      const float del_a = row_a < L ? del_s[si * Lq + t0 + g] : 0.f;
+      const float del_b = row_b < L ? del_s[si * Lq + t0 + g + 8] : 0.f;
+      float dq[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+      const int last_row = min(q0 + 15, L - 1);
+      for (int j0 = 0; j0 <= last_row; j0 += 64) {
+        const int g_hi = min(4, (last_row - j0) / 16 + 1);
+        float s[8][4], dp[8][4];
+        mma_a_bt<HD>(s, Qb, t0, Ks + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
+        mma_a_bt<HD>(dp, dOb, t0, Vs + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+            const int row = (e < 2) ? row_a : row_b;
+            const float pv = (col > row || col >= L) ? 0.f : exp2f(s[nt][e] * scale_log2e - ((e < 2) ? lse_a : lse_b));
+            s[nt][e] = pv * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * scale;
+          }
+        }
+        mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
+      }
+      store_grad_rows<HD>(dq, dqkv_own + ((int64_t)(b0 + si) * Ls - Lc) * ld + (int64_t)h * HD, ld, row_a, row_b, L, tq,
+                          rope_cos, rope_sin);
+    } else {
+      // ------------------------------------------------------------ dK / dV strip: 16 own keys x the sample's own queries
+      const int tk = ticket - n_dq;
+      const int si = tk % nb;
+      const int k0 = (tk / nb) * 16;                        // own-token index of the first key; earliest = heaviest
+      const __nv_bfloat16* Qb = Qs + (size_t)si * Lq * kPitch;
+      const __nv_bfloat16* dOb = dOs + (size_t)si * Lq * kPitch;
+      const float* lse_b = lse_s + si * Lq;
+      const float* del_b = del_s + si * Lq;
+      const int krow = Lc + si * Ls + k0;                   // shared-memory row of the strip's first key
+      const int key_a = k0 + g, key_b = key_a + 8;
+      float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+      }
+      for (int i0 = (k0 / 64) * 64; i0 < Ls; i0 += 64) {
+        const int g_lo = max(0, (k0 - i0) / 16);
+        const int g_hi = min(4, (Ls - 1 - i0) / 16 + 1);
+        float st[8][4], dpt[8][4];                          // rows = keys, cols = queries
+        mma_a_bt<HD>(st, Ks, krow, Qb + i0 * kPitch, lane, g_lo, g_hi);
+        mma_a_bt<HD>(dpt, Vs, krow, dOb + i0 * kPitch, lane, g_lo, g_hi);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qrow = i0 + nt * 8 + tq * 2 + (e & 1);
+            const int key = (e < 2) ? key_a : key_b;
+            const bool dead = key > qrow || key >= Ls || qrow >= Ls || (nt >> 1) < g_lo || (nt >> 1) >= g_hi;
+            const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_b[min(qrow, Lq - 1)]);
+            st[nt][e] = pv;
+            dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_b[min(qrow, Lq - 1)]) * scale;
+          }
+        }
+        mma_p_b<HD>(dv, st, dOb + i0 * kPitch, lane, g_lo, g_hi);
+        mma_p_b<HD>(dk, dpt, Qb + i0 * kPitch, lane, g_lo, g_hi);
+      }
+      // own rows of dqkv; RoPE position of own token t is Lc + t
+      __nv_bfloat16* dbase = dqkv_own + (int64_t)(b0 + si) * Ls * ld + (int64_t)h * HD;
+      const int half = HD / 2;
+      store_grad_rows<HD>(dk, dbase + D, ld, key_a, key_b, Ls, tq, rope_cos ? rope_cos + (int64_t)Lc * half : nullptr,
+                          rope_sin ? rope_sin + (int64_t)Lc * half : nullptr);
+      store_grad_rows<HD>(dv, dbase + 2 * D, ld, key_a, key_b, Ls, tq, nullptr, nullptr);
+    }
+  }
+}
+
+template <int HD>
+static size_t fused_bwd_smem_bytes(int L, int Lc, int spc) {
+  const int Lq = ((L - Lc) + 63) & ~63;
+  return (size_t)(2 * seq_rows_alloc(L, Lc, spc) + 2 * spc * Lq) * (HD + 8) * 2 + (size_t)2 * spc * Lq * 4 + 16;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Shared-prefix layout, dK / dV of the PREFIX keys (needed when something trainable sits inside the backbone:
 // LoRA).  Every query of the batch attends to the prefix — the prefix's own Lc queries causally, the Bp*Ls own
 // tokens of all samples without a mask — and in the shared-prefix row layout all those queries are simply the
@@ -1174,6 +1362,15 @@ static size_t dkv_prefix_smem_bytes() {
   return (size_t)(4 * 64 + 2 * 8 * 16) * (HD + 8) * 2 + (size_t)4 * 64 * 4;
 }
 
+static int g_fused_bwd = -1;
+static bool fused_bwd_enabled() {        // MTS_ATTN_FUSED_BWD=0: separate delta / dQ / dK,dV kernels
+  if (g_fused_bwd < 0) {
+    const char* e = getenv("MTS_ATTN_FUSED_BWD");
+    g_fused_bwd = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fused_bwd == 1;
+}
+
 template <int HD>
 static size_t seq_bwd_smem_bytes(int L, int spc = 1) {
   const int Lp = spc * ((L + 63) & ~63);
@@ -1291,6 +1488,26 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
     if (e == cudaSuccess) e = cudaFuncSetAttribute(skv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd seq)", e);
     seq_attr = true;
+  }
+  // everything of one CTA's samples resident at once?  then one fused kernel does delta, dQ and dK/dV
+  if (fused_bwd_enabled() && fused_bwd_smem_bytes<HD>(L, Lc, 1) <= 220 * 1024) {
+    int spc = 1;
+    const int n_strips = (Ls + 15) / 16;
+    const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);      // 8 dQ strips (+ 8 lighter dK/dV strips) for 8 warps
+    while (spc < want && fused_bwd_smem_bytes<HD>(L, Lc, spc + 1) <= 220 * 1024) ++spc;
+    auto kf = attn_bwd_own_fused_kernel<HD>;
+    static bool fattr = false;
+    if (!fattr) {
+      cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd fused)", e);
+      fattr = true;
+    }
+    LAUNCH_PDL(kf, ((Bp + spc - 1) / spc) * H, kSeqThreads, fused_bwd_smem_bytes<HD>(L, Lc, spc), stream,
+               reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(out_own),
+               reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own, reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, L,
+               Lc, spc, seq_rows_alloc(L, Lc, spc), H, scale);
+    count_launch();
+    return check_launch("attn_bwd_own_fused_kernel");
   }
   const int64_t nwarps = (int64_t)Bp * Ls * H;
   LAUNCH_PDL(attn_bwd_delta_kernel, (int)((nwarps + 7) / 8), 256, 0, stream,
