@@ -1475,7 +1475,10 @@ static int launch_attn_shared(const uint16_t* qkv, uint16_t* out, float* lse, in
 template <int HD>
 static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own,
                                   const uint16_t* dout_own, const float* lse_own, float* delta, uint16_t* dqkv_own,
-                                  int Bp, int Lc, int Ls, int H, float scale, cudaStream_t stream) {
+                                  int Bp, int Lc, int Ls, int H, float scale, cudaStream_t stream,
+                                  bool delta_needed_later = false) {
+  // delta_needed_later: the caller reads `delta` of the own rows afterwards (full backward: dK/dV of the prefix keys),
+  // so the fused kernel — which keeps delta in shared memory only — cannot be used
   const int L = Lc + Ls;
   const int D = H * HD;
   if (seq_bwd_smem_bytes<HD>(L) > 220 * 1024)
@@ -1490,7 +1493,7 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
     seq_attr = true;
   }
   // everything of one CTA's samples resident at once?  then one fused kernel does delta, dQ and dK/dV
-  if (fused_bwd_enabled() && fused_bwd_smem_bytes<HD>(L, Lc, 1) <= 220 * 1024) {
+  if (!delta_needed_later && fused_bwd_enabled() && fused_bwd_smem_bytes<HD>(L, Lc, 1) <= 220 * 1024) {
     int spc = 1;
     const int n_strips = (Ls + 15) / 16;
     const int want = std::min(Bp, (8 + n_strips - 1) / n_strips);      // 8 dQ strips (+ 8 lighter dK/dV strips) for 8 warps
@@ -1553,7 +1556,8 @@ static int launch_attn_shared_bwd_full(const uint16_t* qkv, const float* rc, con
   const int D = H * HD;
   // own rows: dQ (prefix + own keys) and dK / dV of the own keys
   int rc_ = launch_attn_shared_bwd<HD>(qkv, rc, rs, out + (int64_t)Lc * D, dout + (int64_t)Lc * D, lse + (int64_t)H * Lc,
-                                       delta + (int64_t)H * Lc, dqkv + (int64_t)Lc * 3 * D, Bp, Lc, Ls, H, scale, stream);
+                                       delta + (int64_t)H * Lc, dqkv + (int64_t)Lc * 3 * D, Bp, Lc, Ls, H, scale, stream,
+                                       /*delta_needed_later=*/true);
   if (rc_) return rc_;
   // prefix rows: delta, then dQ of the prefix as one causal sequence of Lc positions
   const int64_t nwarps = (int64_t)Lc * H;
