@@ -1114,24 +1114,33 @@ attn_bwd_own_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __
   if (threadIdx.x == 0) *counter = 0;
   cp_async_wait<0>();
   __syncthreads();
-  // ---- delta = rowsum(dO * O) and lse of the own rows (one warp per row; O read once from global)
-  for (int rr = warp; rr < spc * Lq; rr += kSeqThreads / 32) {
+  // ---- delta = rowsum(dO * O) and lse of the own rows: two threads per row, each with its half row of O in flight
+  // as independent 16-byte loads (one global round trip for the whole CTA)
+  for (int idx = threadIdx.x; idx < 2 * spc * Lq; idx += kSeqThreads) {
+    const int rr = idx >> 1, part = idx & 1;
     const int si = rr / Lq, t = rr - si * Lq;
-    float acc = 0.f, l = INFINITY;
-    if (si < nb && t < Ls) {
+    const bool live = si < nb && t < Ls;
+    float acc = 0.f;
+    if (live) {
       const int64_t own_row = (int64_t)(b0 + si) * Ls + t;
-      const __nv_bfloat16* op = out_own + own_row * D + (int64_t)h * HD;
-      const __nv_bfloat16* dp = dOs + rr * kPitch;
-      for (int i = lane * 2; i < HD; i += 64) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(op + i);
-        const uint32_t d = *reinterpret_cast<const uint32_t*>(dp + i);
-        acc += bf16_lo(a) * bf16_lo(d) + bf16_hi(a) * bf16_hi(d);
-      }
+      const uint4* op = reinterpret_cast<const uint4*>(out_own + own_row * D + (int64_t)h * HD + part * (HD / 2));
+      const uint4* dp = reinterpret_cast<const uint4*>(dOs + rr * kPitch + part * (HD / 2));
+      uint4 ov[HD / 16];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      l = lse_own[((int64_t)(b0 + si) * H + h) * Ls + t] * 1.4426950408889634f;
+      for (int i = 0; i < HD / 16; ++i) ov[i] = __ldg(op + i);
+#pragma unroll
+      for (int i = 0; i < HD / 16; ++i) {
+        const uint4 d = dp[i];
+        const uint32_t aw[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += bf16_lo(aw[q]) * bf16_lo(dw[q]) + bf16_hi(aw[q]) * bf16_hi(dw[q]);
+      }
     }
-    if (lane == 0) { del_s[rr] = acc; lse_s[rr] = l; }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (part == 0) {
+      del_s[rr] = acc;
+      lse_s[rr] = live ? lse_own[((int64_t)(b0 + si) * H + h) * Ls + t] * 1.4426950408889634f : INFINITY;
+    }
   }
   __syncthreads();
 
