@@ -621,11 +621,12 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
     for (k, p0), (_, p1) in zip(m0.named_parameters(), m1.named_parameters()):
         # (not torch.equal: the patch-embedding conv gradient is reduced with fp32 atomics, whose summation order —
         # hence the last bits of that gradient and of everything Adam derives from it — varies from run to run)
-        torch.testing.assert_close(p0, p1, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+        # (Adam divides by sqrt(v): where a gradient is ~0 the last-bit noise moves a weight by a visible fraction of lr)
+        torch.testing.assert_close(p0, p1, rtol=1e-4, atol=5e-5, msg=lambda m, k=k: f"{k}: {m}")
     # evaluation after training on the graph sees the trained weights
     m0.eval(); m1.eval()
     with torch.no_grad():
-        torch.testing.assert_close(m0(base), m1(base), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(m0(base), m1(base), rtol=1e-3, atol=1e-5)
     # stale activations: two forwards on the graph, backward through the first
     m1.train()
     ya = m1(base)
