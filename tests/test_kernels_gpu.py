@@ -556,6 +556,8 @@ def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
     own = dqkv_p.view(Bp, L, 3 * D)[:, Lc:].reshape(Bp * Ls, 3 * D)
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         assert _rel_l2(dqkv[:, sl], own[:, sl]) < 1e-6, name
+    for _ in range(3):      # deterministic (no atomics; the job-to-warp assignment must not matter)
+        assert torch.equal(ops.attn_causal_shared_bwd(qkv, out[Lc:], dout, lse, Bp, Lc, Ls, H, hd, rope=tabs), dqkv)
     # full backward (LoRA): gradient also enters at the prefix rows' outputs, and the prefix rows' q/k/v receive what
     # all the samples send back.  Equivalent plain computation: Bp private copies of the prefix; the gradient of the
     # shared rows is the sum over the copies (the upstream gradient of the prefix outputs is given to copy 0).
