@@ -86,5 +86,7 @@ def test_full_size_training_gradients_shared_vs_per_sample(cuda):
         e = _rel(grads[True][k], g0)
         worst[k] = e
         sib = grads[False].get(k.rsplit(".", 1)[0] + ".weight", g0).abs().max().item()
-        assert e < 3e-2 or (grads[True][k] - g0).abs().max().item() <= 1e-3 * sib, (k, e)
+        # key_projection.bias: structurally zero (softmax shift invariance), rounding noise on both sides
+        slack = 1e-1 if k.endswith("key_projection.bias") else 1e-3
+        assert e < 3e-2 or (grads[True][k] - g0).abs().max().item() <= slack * sib, (k, e)
     print("\n[full-size grads, shared vs per-sample] " + "  ".join(f"{k.split('.')[-2][:8]}.{k.split('.')[-1][0]} {e:.1e}" for k, e in worst.items()))
