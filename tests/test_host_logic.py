@@ -160,3 +160,30 @@ def test_lora_save_load_round_trip(tmp_path):
     assert len(keys) == len(a.params())
     for pa, pb, v in zip(a.params(), b.params(), v0):
         assert torch.equal(pa, pb) and pb._version > v
+
+
+def test_shared_prefix_length_host_logic(tmp_path):
+    """`MedTsLLM._shared_prefix_len`: number of leading prompt positions (left padding included) holding the same token
+    in every sample — the rows carried once through the backbone.  Host logic only."""
+    from _fixtures import Cfg, Dataset, config_for, load_case, materialize_llm_dir
+    from medtsllm_b200.model import MedTsLLM
+    fix = load_case("llama_seg_concat")
+    model = MedTsLLM(Cfg(config_for(fix, materialize_llm_dir(fix, tmp_path / "llm"))), Dataset(fix["dataset"]))
+    B, Lp, N = 6, 40, 13
+    L = Lp + N
+    same = torch.randint(3, 300, (1, Lp), dtype=torch.int32).repeat(B, 1)
+    assert model._shared_prefix_len(same, B, L) == Lp                    # static dataset / task prompt: all of it
+    t = same.clone(); t[3, 25] += 1
+    assert model._shared_prefix_len(t, B, L) == 25                       # per-sample text from position 25 on
+    t = same.clone(); t[1, 9] += 1
+    assert model._shared_prefix_len(t, B, L) == 0                        # fewer than 16 shared positions: not worth a launch
+    t = same.clone(); t[2, :4] = 2; t[2, 4:] = same[0, : Lp - 4]         # a shorter prompt, left-padded: nothing lines up
+    assert model._shared_prefix_len(t, B, L) == 0
+    assert model._shared_prefix_len(same, 1, L) == 0                     # a single sequence has nothing to share with
+    assert model._shared_prefix_len(same[:, :0], B, N) == 0              # no prompt
+    model.share_prompt_prefix = False
+    assert model._shared_prefix_len(same, B, L) == 0
+    model.share_prompt_prefix = True
+    # the sequence-resident attention kernels must hold all L positions of one head in shared memory
+    long = torch.randint(3, 300, (1, 600), dtype=torch.int32).repeat(B, 1)
+    assert model._shared_prefix_len(long, B, 600 + N) == 0
