@@ -579,7 +579,7 @@ def test_gpt4ts_training_gradients(name, cuda):
 def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda):
     """Training steps replay two captured CUDA graphs (forward + stash, backward chain) once the same step shape
     repeats: step 0 runs kernel by kernel, step 1 captures, steps 2.. replay.  Losses and the parameters after
-    5 Adam steps must equal the kernel-by-kernel run (same kernels, same order), the captured forward
+    5 SGD steps must equal the kernel-by-kernel run (same kernels, same order), the captured forward
     must pick up every optimizer update (bf16 re-casts are part of the graph), and a backward() whose activations
     were overwritten by a later forward must raise."""
     from medtsllm_b200._lib import MtsError
@@ -602,7 +602,10 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
             with torch.no_grad():
                 for p in model.llm.B:
                     p.copy_((torch.randn(p.shape, generator=gen) * 0.05).to(cuda))
-        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+        # plain SGD: the update is linear in the gradient, so the last-bit run-to-run noise of the atomically reduced conv
+        # gradient stays last-bit (Adam's g / sqrt(v) turns noise-only gradients — the structurally zero key bias — into
+        # +-lr steps and makes any comparison of the two runs meaningless)
+        opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-2)
         losses = []
         for step in range(5):
             y = model({**base, "x_enc": base["x_enc"] * (1.0 + 0.05 * step)})
@@ -621,8 +624,7 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
     for (k, p0), (_, p1) in zip(m0.named_parameters(), m1.named_parameters()):
         # (not torch.equal: the patch-embedding conv gradient is reduced with fp32 atomics, whose summation order —
         # hence the last bits of that gradient and of everything Adam derives from it — varies from run to run)
-        # (Adam divides by sqrt(v): where a gradient is ~0 the last-bit noise moves a weight by a visible fraction of lr)
-        torch.testing.assert_close(p0, p1, rtol=1e-4, atol=5e-5, msg=lambda m, k=k: f"{k}: {m}")
+        torch.testing.assert_close(p0, p1, rtol=1e-4, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
     # evaluation after training on the graph sees the trained weights
     m0.eval(); m1.eval()
     with torch.no_grad():
