@@ -133,3 +133,20 @@ def test_gpt4ts_oracle_matches_reference_golden(name):
 def test_gpt4ts_rejects_reconstruction_like_the_reference():
     with pytest.raises(ValueError):
         G.gpt4ts_forward(torch.zeros(1, 8, 2), {}, {}, dict(task="reconstruction"))
+
+
+@pytest.mark.parametrize("name", ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate"])
+def test_reference_prompt_rows_are_identical_across_samples(name):
+    """The premise of in-batch prompt sharing, checked on tensors captured from the UNMODIFIED reference:
+    with a static dataset / task prompt the backbone is causal and unmasked, so at every layer the hidden states of the
+    prompt positions are the same for every sample of the batch (the reference computes them once per sample anyway)."""
+    fix = load_case(name)
+    Lp = len(fix["prompt_ids"][0])
+    assert all(p == fix["prompt_ids"][0] for p in fix["prompt_ids"])
+    hs = fix["stages"]["llm.hidden_states"]
+    assert len(hs) >= 2
+    for h in hs:
+        assert h.shape[0] >= 2
+        for b in range(1, h.shape[0]):
+            torch.testing.assert_close(h[b, :Lp], h[0, :Lp], rtol=1e-5, atol=1e-6)
+        assert not torch.allclose(h[1, Lp:], h[0, Lp:])          # the patch rows do differ
