@@ -238,6 +238,7 @@ bool gemm_2cta_enabled() {
   }
   return g_gemm_2cta == 1;
 }
+static int g_gemm_force = 0;      // mts_set_option("gemm_force", 0 auto | 1 single-CTA kernel | 2 CTA-pair kernel): experiments
 static int g_pdl = -1;
 bool pdl_enabled() {
   if (g_pdl < 0) {
@@ -253,6 +254,7 @@ using namespace mts;
 extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
+  if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
@@ -365,7 +367,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
     const long t1 = (long)((a->m + 127) / 128) * nb256 * a->batch, tp = (long)((a->m + 255) / 256) * nb256 * a->batch;
     const long cost1 = ((t1 + num_sms() - 1) / num_sms()) * 100;
     const long costp = ((tp + num_sms() / 2 - 1) / (num_sms() / 2)) * 92;
-    if (costp <= cost1) return launch_gemm_2cta(a->epilogue, a, p, stream);
+    if (g_gemm_force == 2 || (g_gemm_force == 0 && costp <= cost1)) return launch_gemm_2cta(a->epilogue, a, p, stream);
   }
 
   const int mb = (a->m + kBlockM - 1) / kBlockM;

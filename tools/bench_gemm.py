@@ -8,6 +8,11 @@ from medtsllm_b200 import ops
 
 dev = torch.device("cuda:0")
 shapes = [  # (name, m, n, k, epilogue, block_n)
+    # shared-prefix row counts of the BIDMC step (128 + 32*64 rows)
+    ("sp_qkv", 2176, 12288, 4096, 0, 0),
+    ("sp_o_resid", 2176, 4096, 4096, 1, 0),
+    ("sp_gateup_swiglu", 2176, 22016, 4096, 3, 256),
+    ("sp_down_resid", 2176, 4096, 11008, 1, 0),
     ("llama_qkv", 6144, 12288, 4096, 0, 0),
     ("llama_o_resid", 6144, 4096, 4096, 1, 0),
     ("llama_gateup_swiglu", 6144, 22016, 4096, 3, 256),
@@ -18,8 +23,13 @@ shapes = [  # (name, m, n, k, epilogue, block_n)
     ("gpt2m_proj_resid", 8960, 1024, 4096, 1, 0),
     ("mapping", 1024, 4096, 32000, 0, 0),
 ]
+from medtsllm_b200 import _lib
 res = []
-for name, m, n, k, epi, bn in shapes:
+force_modes = [0, 1, 2] if "--force-sweep" in sys.argv else [0]      # auto / single-CTA kernel / CTA-pair kernel
+if "--shared-prefix-only" in sys.argv:
+    shapes = shapes[:4]
+for (name, m, n, k, epi, bn), force in ((sh, f) for sh in shapes for f in force_modes):
+    _lib.set_option("gemm_force", force)
     nrot = 3
     A = [torch.randn(m, k, device=dev).to(torch.bfloat16) for _ in range(nrot)]
     B = [(torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16) for _ in range(nrot)]
@@ -45,7 +55,7 @@ for name, m, n, k, epi, bn in shapes:
     e1.record(); torch.cuda.synchronize()
     ms_cublas = e0.elapsed_time(e1) / iters
     fl = 2.0 * m * n * k
-    r = dict(name=name, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+    r = dict(name=name, force=force, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
              cublas_ms=round(ms_cublas, 4), cublas_tflops=round(fl / ms_cublas / 1e9, 1))
     print(json.dumps(r), flush=True)
     res.append(r)
