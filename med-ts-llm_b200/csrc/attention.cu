@@ -1080,7 +1080,7 @@ attn_bwd_own_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __
   const int D = H * HD;
   const int64_t ld = 3 * (int64_t)D;
   const __nv_bfloat16* gbase = qkv + (int64_t)h * HD;      // row of (sample b, position p): p (p < Lc) or p + b*Ls
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
 
