@@ -1275,7 +1275,7 @@ attn_bwd_dkv_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, const float* _
   const int M = Lc + Bp * Ls;
   const __nv_bfloat16* qbase = qkv + (int64_t)h * HD;
   const __nv_bfloat16* dobase = dout + (int64_t)h * HD;
-  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float scale_log2e = scale * 1.4426950408889634f;
   const float* lse_own = lse + (int64_t)H * Lc;

@@ -138,35 +138,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
 
       const int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : n_cols / 32;
       const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
-      // fp32 residual add: the residual values of chunk ci+1 are fetched while chunk ci is processed, so their global
-      // latency (the epilogue of a CTA's LAST tile is not hidden by any main loop) overlaps TMEM reads, staging and stores
-      [[maybe_unused]] float4 c_pre[8];
-      [[maybe_unused]] const bool c_prefetch = EPI == MTS_EPI_RESID_ADD && p.d_is_f32 && p.vec_ok;
-      auto fetch_c = [&](int ci_, float4 (&dst)[8]) {
-        const int rr_ = lane >> 3, cc_ = (lane & 7) * 4;
-        const int c0_ = n_blk * BN + col_off + ci_ * 32;
-        const float* cb_ = p.c + (int64_t)b * p.d_batch_stride + c0_ + cc_;
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int r_g = row0 + ps * 4 + rr_;
-          if (c0_ + cc_ < n_store && r_g < p.m) dst[ps] = *reinterpret_cast<const float4*>(cb_ + (int64_t)r_g * p.ldd);
-        }
-      };
-      if constexpr (EPI == MTS_EPI_RESID_ADD) {
-        if (c_prefetch && kChunks > 0) fetch_c(0, c_pre);
-      }
 #pragma unroll 1
       for (int ci = 0; ci < kChunks; ++ci) {
         float v[32];
         int col0;  // first output column of this chunk
-        [[maybe_unused]] float4 c_cur[8];
-        if constexpr (EPI == MTS_EPI_RESID_ADD) {
-          if (c_prefetch) {
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) c_cur[ps] = c_pre[ps];
-            if (ci + 1 < kChunks) fetch_c(ci + 1, c_pre);
-          }
-        }
         __syncwarp();  // tcgen05.ld is .sync.aligned; also orders the previous chunk's smem reads
         if constexpr (EPI == MTS_EPI_SWIGLU) {
           // columns [0,BN/2) of the tile are gate, [BN/2,BN) the matching up projections
@@ -280,15 +255,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           float* dbase = reinterpret_cast<float*>(p.d) + boff;
           const bool col_ok = col0 + cc < n_store;
           if constexpr (EPI == MTS_EPI_RESID_ADD) {
-            // residual source (== D for the in-place form), fetched one chunk ahead into c_cur
+            const float* cbase = p.c + boff;  // residual source (== D for the in-place form)
+            float4 o[8];
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r_g = row0 + ps * 4 + rr;
+              if (col_ok && r_g < p.m) o[ps] = *reinterpret_cast<const float4*>(cbase + (int64_t)r_g * p.ldd);
+            }
 #pragma unroll
             for (int ps = 0; ps < 8; ++ps) {
               const int r_g = row0 + ps * 4 + rr;
               if (col_ok && r_g < p.m) {
                 const float4 a = *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr) * kEpiPitch + cc);
-                float4 o = c_cur[ps];
-                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) = o;
+                o[ps].x += a.x; o[ps].y += a.y; o[ps].z += a.z; o[ps].w += a.w;
+                *reinterpret_cast<float4*>(dbase + (int64_t)r_g * p.ldd) = o[ps];
               }
             }
           } else {
