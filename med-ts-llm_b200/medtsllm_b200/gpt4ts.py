@@ -170,9 +170,9 @@ class GPT4TS(nn.Module):
         bb = self._backbone
         if self.d_model > bb.spec.hidden or self.d_ff > bb.spec.hidden or C > bb.spec.hidden:
             raise MtsError(f"d_model / d_ff / n_features must not exceed the GPT-2 width {bb.spec.hidden}")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             names, params = zip(*self._trainable())
-            return _GPT4TSFn.apply(self, x, names, *params)                 # autograd path
+            return _GPT4TSFn.apply(self, x, names, *params)                 # autograd path (training-mode forwards)
         if not self.use_cuda_graph:
             return self._forward_impl(x)
         key = (tuple(x.shape), x.device.index, self.training, tuple((p._version, p.data_ptr()) for p in self.parameters()))

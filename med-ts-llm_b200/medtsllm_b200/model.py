@@ -557,8 +557,11 @@ class MedTsLLM(nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            from .train import forward_train  # autograd path (adapter gradients)
+        # autograd path (adapter gradients) for training-mode forwards under enabled gradients — what the reference's
+        # Trainers differentiate (tasks/forecasting.py:18-26).  Evaluation-mode forwards take the inference path, which
+        # also applies the eval-only sigmoid / softmax (models/medtsllm.py:251-259) and returns a tensor without a graph.
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .train import forward_train
             return forward_train(self, inputs)
         return self.predict(inputs)
 
