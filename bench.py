@@ -548,9 +548,12 @@ def hbm_kernels(model, w, dev):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        res.append({"kernel": name, "bytes_per_launch": nbytes, "us_per_launch": round(us, 2),
-                    "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(nbytes / us / 1e3 / peak, 4)})
+        row = {"kernel": name, "bytes_per_launch": nbytes, "us_per_launch": round(us, 2),
+               "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
+               "frac": round(nbytes / us / 1e3 / peak, 4)}
+        if nbytes < 8e6:     # a few hundred KB per launch: the launch itself (~5-10 us) dominates, not the bytes
+            row["note"] = "launch-latency bound at this size: %.1f MB per launch" % (nbytes / 1e6)
+        res.append(row)
     return res
 
 
