@@ -52,8 +52,15 @@ const char* mts_last_error(void);
 int64_t mts_launch_count(void);
 /* Drop the host-side TMA descriptor cache. */
 int mts_clear_caches(void);
-/* Process-wide switches.  "gemm_2cta" (0/1; default 1, env MTS_GEMM_2CTA=0 turns it off): route 256-wide
- * GEMM tiles to the CTA-pair kernel (tcgen05 cta_group::2, 256x256 tile per two SMs). */
+/* Process-wide switches.
+ *   "gemm_2cta" (0/1; default 1, env MTS_GEMM_2CTA=0): route 256-wide GEMM tiles to the CTA-pair kernel
+ *               (tcgen05 cta_group::2, 256x256 tile per two SMs) when the cost model prefers it.
+ *   "gemm_force" (0 auto | 1 single-CTA kernel | 2 CTA-pair kernel; default 0): override that cost model (experiments,
+ *               tools/bench_gemm.py --force-sweep).
+ *   "pdl"       (0/1; default 1, env MTS_PDL=0): launch the per-layer kernels with programmatic stream serialization
+ *               (their prologues overlap the previous kernel's tail; they block in griddepcontrol.wait before
+ *               touching its results).
+ * Environment only: MTS_ATTN_FUSED_BWD=0 keeps the separate delta / dQ / dK,dV attention-backward kernels. */
 int mts_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------ */
