@@ -267,7 +267,7 @@ def run_ours(args):
     # stated in DESIGN.md section 3
     hbm = None
     if rank == 0:
-        hbm = hbm_kernels(model, w, dev)
+        hbm = hbm_kernels(model, w, dev, Lc)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every mts_gemm launch,
     # recorded on the launching stream over instrumented steps of the same workload
@@ -508,24 +508,40 @@ def hf_gpu_backbone(w, dev, steps: int = 3):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
-def hbm_kernels(model, w, dev):
+def hbm_kernels(model, w, dev, Lc=0):
+    """The HBM-bound kernels of the forward at the row counts the step actually runs them on (shared prompt prefix:
+    Lc + B*(L-Lc) rows), and — for the two row kernels — at the per-sample-prompt row count B*L as well."""
     from medtsllm_b200 import ops
     peak = _peaks()["hbm_gbs"]
     s = w.backbone
-    M, D = w.B * w.seq, s.hidden
-    x = torch.randn(M, D, device=dev)
+    D = s.hidden
+    M_full = w.B * w.seq
+    M = Lc + w.B * (w.seq - Lc)
+    x = torch.randn(M_full, D, device=dev)
     wn = torch.ones(D, device=dev)
-    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(M_full, D, device=dev, dtype=torch.bfloat16)
     xe = torch.randn(w.B, w.T, w.C, device=dev)
     wc = model.patch_embedding.value_embedding.tokenConv.weight.detach()
-    ids = torch.randint(3, s.vocab, (w.B, w.prompt_len), device=dev, dtype=torch.int32)
-    X = torch.empty(w.B, w.seq, D, device=dev)
+    ids = torch.randint(3, s.vocab, (1, w.prompt_len), device=dev, dtype=torch.int32).repeat(w.B, 1).contiguous()
+    X = torch.empty(M_full, D, device=dev)
     bb = model._backbone
-    norm = (lambda: ops.rmsnorm(x, wn, 1e-5, out=out)) if s.kind == "llama" else (lambda: ops.layernorm(x, wn, wn, 1e-5, out=out))
-    cases = [
-        ("norm_rows_kernel", norm, M * D * 6.0),
-        ("prompt_gather_kernel", lambda: ops.prompt_gather(ids, bb.embed, bb.wpe, X, rep=1, Lp=w.prompt_len, L=w.seq),
-         w.B * w.prompt_len * D * 4.0 * (2 if bb.wpe is not None else 1) + w.B * w.seq * D * 4.0),
+    pe = 2 if bb.wpe is not None else 1
+
+    def norm(rows):
+        if s.kind == "llama":
+            return lambda: ops.rmsnorm(x[:rows], wn, 1e-5, out=out[:rows])
+        return lambda: ops.layernorm(x[:rows], wn, wn, 1e-5, out=out[:rows])
+
+    cases = [(f"norm_rows_kernel ({M} rows)", norm(M), M * D * 6.0)]
+    if Lc:
+        cases.append((f"norm_rows_kernel ({M_full} rows: per-sample prompt rows)", norm(M_full), M_full * D * 6.0))
+        cases.append((f"prompt_gather_kernel ({M} rows)",
+                      lambda: ops.prompt_gather(ids, bb.embed, bb.wpe, X[:M], rep=1, Lp=w.prompt_len, L=w.seq, Lc=Lc, B=w.B),
+                      (Lc + w.B * (w.prompt_len - Lc)) * D * 4.0 + (M * D * 4.0 if pe == 2 else 0.0) + M * D * 4.0))
+    cases += [
+        (f"prompt_gather_kernel ({M_full} rows{': per-sample prompt rows' if Lc else ''})",
+         lambda: ops.prompt_gather(ids, bb.embed, bb.wpe, X, rep=1, Lp=w.prompt_len, L=w.seq, B=w.B),
+         w.B * w.prompt_len * D * 4.0 + (M_full * D * 4.0 if pe == 2 else 0.0) + M_full * D * 4.0),
         ("revin_patch_embed_kernel", lambda: ops.revin_patch_embed(xe, wc, 16, 8, concat=w.covariate_mode == "concat"),
          w.B * w.T * w.C * 4.0 + w.B * w.C * w.n_patches * 32 * 2.0 + w.B * w.C * 8.0),
     ]

@@ -81,46 +81,78 @@ norm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
                  float* __restrict__ y_f32, int D, float eps) {
   pdl_wait();
   pdl_trigger();
+  // One CTA per row.  The row (up to 4096 columns: 4 float4 per thread) and the norm weights are fetched ONCE, all
+  // loads in flight together, and stay in registers through the reductions; wider rows re-read the remainder.
+  constexpr int kCache = 4;
   __shared__ float red[32];
   const float* xr = x + (int64_t)blockIdx.x * ldx;
   const int D4 = D >> 2;  // D % 4 == 0 enforced on the host
+  float4 v[kCache], g[kCache];
+#pragma unroll
+  for (int k = 0; k < kCache; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < D4) {
+      v[k] = reinterpret_cast<const float4*>(xr)[i];
+      g[k] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    } else {
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      g[k] = v[k];
+    }
+  }
   float s = 0.0f, ss = 0.0f;
-  for (int i = threadIdx.x; i < D4; i += blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(xr)[i];
-    if (kLayerNorm) s += (v.x + v.y) + (v.z + v.w);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+  for (int k = 0; k < kCache; ++k) {
+    if (kLayerNorm) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+  }
+  for (int i = threadIdx.x + kCache * 256; i < D4; i += 256) {          // D > 4096 only
+    const float4 t = reinterpret_cast<const float4*>(xr)[i];
+    if (kLayerNorm) s += (t.x + t.y) + (t.z + t.w);
+    ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
   }
   float mean = 0.0f, rstd;
   if (kLayerNorm) {
     mean = block_sum(s, red) / D;
     // second pass for the variance: matches torch's two-pass numerics better than E[x^2]-m^2
     float vs = 0.0f;
-    for (int i = threadIdx.x; i < D4; i += blockDim.x) {
-      const float4 v = reinterpret_cast<const float4*>(xr)[i];
-      const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+#pragma unroll
+    for (int k = 0; k < kCache; ++k) {
+      if (threadIdx.x + k * 256 < D4) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        vs += a * a + b * b + c * c + d * d;
+      }
+    }
+    for (int i = threadIdx.x + kCache * 256; i < D4; i += 256) {
+      const float4 t = reinterpret_cast<const float4*>(xr)[i];
+      const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
       vs += a * a + b * b + c * c + d * d;
     }
     rstd = rsqrtf(block_sum(vs, red) / D + eps);
   } else {
     rstd = rsqrtf(block_sum(ss, red) / D + eps);
   }
-  for (int i = threadIdx.x; i < D4; i += blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(xr)[i];
-    const float4 g = reinterpret_cast<const float4*>(w)[i];
+  auto emit = [&](int i, const float4& t, const float4& gw) {
     float4 o;
-    o.x = (v.x - mean) * rstd * g.x;
-    o.y = (v.y - mean) * rstd * g.y;
-    o.z = (v.z - mean) * rstd * g.z;
-    o.w = (v.w - mean) * rstd * g.w;
+    o.x = (t.x - mean) * rstd * gw.x;
+    o.y = (t.y - mean) * rstd * gw.y;
+    o.z = (t.z - mean) * rstd * gw.z;
+    o.w = (t.w - mean) * rstd * gw.w;
     if (kLayerNorm) {
-      const float4 bb = reinterpret_cast<const float4*>(bias)[i];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + i);
       o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
     }
     if (y_bf16)
       reinterpret_cast<uint2*>(y_bf16 + (int64_t)blockIdx.x * D)[i] =
           make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     if (y_f32) reinterpret_cast<float4*>(y_f32 + (int64_t)blockIdx.x * D)[i] = o;
+  };
+#pragma unroll
+  for (int k = 0; k < kCache; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < D4) emit(i, v[k], g[k]);
   }
+  for (int i = threadIdx.x + kCache * 256; i < D4; i += 256)
+    emit(i, reinterpret_cast<const float4*>(xr)[i], __ldg(reinterpret_cast<const float4*>(w) + i));
 }
 
 // ------------------------------------------------------------------------------------------
