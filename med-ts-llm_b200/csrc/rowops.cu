@@ -75,29 +75,24 @@ __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ in, __nv_bfloat
 // RMSNorm / LayerNorm: one CTA per row (bytes per row: 4*D read + 2*D (or 4*D) written)
 // ------------------------------------------------------------------------------------------
 template <bool kLayerNorm>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 norm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y_bf16,
                  float* __restrict__ y_f32, int D, float eps) {
   pdl_wait();
   pdl_trigger();
-  // One CTA per row.  The row (up to 4096 columns: 4 float4 per thread) and the norm weights are fetched ONCE, all
-  // loads in flight together, and stay in registers through the reductions; wider rows re-read the remainder.
+  // One CTA per row.  The row (up to 4096 columns: 4 float4 per thread) is fetched ONCE, all loads in flight together,
+  // and stays in registers through the reductions; wider rows re-read the remainder.  (The 16 KB of norm weights come
+  // from L1/L2 in the last pass: caching them too costs the registers that keep 6 CTAs per SM resident.)
   constexpr int kCache = 4;
   __shared__ float red[32];
   const float* xr = x + (int64_t)blockIdx.x * ldx;
   const int D4 = D >> 2;  // D % 4 == 0 enforced on the host
-  float4 v[kCache], g[kCache];
+  float4 v[kCache];
 #pragma unroll
   for (int k = 0; k < kCache; ++k) {
     const int i = threadIdx.x + k * 256;
-    if (i < D4) {
-      v[k] = reinterpret_cast<const float4*>(xr)[i];
-      g[k] = __ldg(reinterpret_cast<const float4*>(w) + i);
-    } else {
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      g[k] = v[k];
-    }
+    v[k] = i < D4 ? reinterpret_cast<const float4*>(xr)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float s = 0.0f, ss = 0.0f;
 #pragma unroll
@@ -149,7 +144,7 @@ norm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
 #pragma unroll
   for (int k = 0; k < kCache; ++k) {
     const int i = threadIdx.x + k * 256;
-    if (i < D4) emit(i, v[k], g[k]);
+    if (i < D4) emit(i, v[k], __ldg(reinterpret_cast<const float4*>(w) + i));
   }
   for (int i = threadIdx.x + kCache * 256; i < D4; i += 256)
     emit(i, reinterpret_cast<const float4*>(xr)[i], __ldg(reinterpret_cast<const float4*>(w) + i));
