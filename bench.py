@@ -569,6 +569,10 @@ def hbm_kernels(model, w, dev, Lc=0):
                "frac": round(nbytes / us / 1e3 / peak, 4)}
         if nbytes < 8e6:     # a few hundred KB per launch: the launch itself (~5-10 us) dominates, not the bytes
             row["note"] = "launch-latency bound at this size: %.1f MB per launch" % (nbytes / 1e6)
+        elif row["frac"] > 1.0:
+            row["note"] = ("above the HBM figure: part of the %.0f MB working set is served by the 126 MB L2 (identical prompt "
+                           "rows are gathered from the same table rows; back-to-back launches reuse the buffers), as it is "
+                           "inside the step where the previous kernel has just written the rows" % (nbytes / 1e6))
         res.append(row)
     return res
 
