@@ -313,6 +313,31 @@ def test_edge_inputs_empty_prompt_2d_input_batch_of_one(tmp_path, cuda):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
 
 
+def test_llm_layers_truncates_the_backbone(tmp_path, cuda):
+    """`models.medtsllm.llm.llm_layers = k` keeps the first k blocks of the checkpoint (models/medtsllm.py:144-146:
+    `llm_config.num_hidden_layers = llm_layers` before `AutoModel.from_pretrained`)."""
+    from medtsllm_b200.model import MedTsLLM
+    from _fixtures import oracle_spec
+    fix = load_case("llama_seg_concat")                                  # 2-block backbone
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    cfg = config_for(fix, llm_dir)
+    cfg["models"]["medtsllm"]["llm"]["llm_layers"] = 1
+    model = MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda).eval()
+    assert len(model._backbone.layers) == 1
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    with torch.no_grad():
+        out = model(inputs)
+    from oracle import medtsllm_oracle as O
+    spec = dict(oracle_spec(fix), n_layers=1)
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, fix["adapters"], {k: v.float() for k, v in fix["backbone_state"].items()}, spec)
+    full = run_oracle(fix)[0]
+    assert _rel_l2(out, ref) < 3e-3
+    assert _rel_l2(ref, full) > 1e-2                                    # the second block does matter
+
+
 def test_long_sequence_falls_back_to_tiled_attention(cuda):
     """L beyond the shared-memory-resident attention kernels (hd 128: L > ~350) takes the 64x64-tiled kernels
     (forward and backward) and still matches the oracle's Llama restatement."""
