@@ -73,7 +73,12 @@ class KernelBackbone:
     """Device-resident frozen decoder stack.  Not an nn.Module on purpose: `.to(dtype)` from the
     Trainer (tasks/base.py:41) must not re-cast the bf16 kernel weights."""
 
-    def __init__(self, spec: BackboneSpec, device):
+    def __init__(self, spec: BackboneSpec, device, precision: str = "bf16"):
+        """`precision`: which operand copies of the frozen weights to keep — "bf16" (default path: bf16 operands, fp32
+        accumulation), "tf32" (evaluation parity mode: fp32 weights rounded to TF32, tcgen05 kind::tf32) or "both"."""
+        if precision not in ("bf16", "tf32", "both"):
+            raise MtsError(f"precision {precision!r}: expected 'bf16', 'tf32' or 'both'")
+        self.precision = precision
         self.spec = spec
         self.device = torch.device(device)
         self.layers: list[dict] = []
@@ -83,6 +88,7 @@ class KernelBackbone:
         self.embed_t = None     # bf16 [D, V] (K-major operand of the mapping GEMM)
         self.wpe = None         # GPT-2 only, fp32 [max_pos, D]
         self._rope = None
+        self.cache_gen = 0      # bumped when a lazily built device table (RoPE) is replaced: captured graphs point into it
         self.i_pad = ((spec.inter + 127) // 128) * 128 if spec.kind == "llama" else spec.inter
 
     # ---------------------------------------------------------------------------------- building
@@ -166,10 +172,10 @@ class KernelBackbone:
         return self
 
     @classmethod
-    def random_init(cls, spec: BackboneSpec, device, seed=0, std=0.02):
+    def random_init(cls, spec: BackboneSpec, device, seed=0, std=0.02, precision="bf16"):
         """Seeded random-init stack generated directly on the device (no checkpoints exist offline;
-        HF `initializer_range` = 0.02, norms = 1, biases = 0)."""
-        self = cls(spec, device)
+        HF `initializer_range` = 0.02, norms = 1, biases = 0).  `precision`: "bf16" | "tf32" | "both" (see __init__)."""
+        self = cls(spec, device, precision=precision)
         g = torch.Generator(device=self.device).manual_seed(seed)
         D, I = spec.hidden, spec.inter
 
@@ -197,6 +203,7 @@ class KernelBackbone:
             return None
         if self._rope is None or self._rope[0].shape[0] < L:
             self._rope = _rope_tables(max(L, 512), self.spec.head_dim, self.spec.rope_theta, self.device)
+            self.cache_gen += 1
         return self._rope
 
     def weight_bytes(self) -> int:

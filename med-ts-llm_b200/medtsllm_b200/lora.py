@@ -53,6 +53,7 @@ class LoraAdapters(nn.Module):
                 self.A.append(nn.Parameter(a))
                 self.B.append(nn.Parameter(b))
         self._cache = {}
+        self._cache_gen = 0             # bumped whenever a cached operand set is replaced (graph-replay key)
         self._force_recast = False      # graph capture of a training step: cast even if the cache would hit
 
     def params(self):
@@ -84,6 +85,7 @@ class LoraAdapters(nn.Module):
             b_t.append(ops.transpose_strided(bb, rows=B.shape[0], cols=self.rp))        # [rp, out]
         d = dict(a_cat=a_cat, a_cat_t=ops.transpose_strided(a_cat, rows=nt * self.rp, cols=D), b=b, b_t=b_t)
         self._cache[layer] = (key, d)
+        self._cache_gen += 1
         return d
 
     # ------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -96,6 +97,30 @@ class _LLMHandle:
 
     def save_pretrained(self, path, *a, **k):
         raise MtsError("model.llm.save_pretrained is only meaningful with lora.enabled (loggers/base_logger.py:42-43)")
+
+
+_LIVE_MODELS: "weakref.WeakSet" = weakref.WeakSet()
+_HOOK_INSTALLED = False
+
+
+def _install_optimizer_hook():
+    """Every `optimizer.step()` of any torch optimizer bumps `_opt_steps` of the live models, which is part of every
+    weight-cache key: optimizers that update through `p.data` (no `_version` bump — older / third-party ones such as
+    the Ranger21 the reference allows, tasks/base.py:12) still invalidate the bf16 copies and captured graphs."""
+    global _HOOK_INSTALLED
+    if _HOOK_INSTALLED:
+        return
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+    except ImportError:      # very old torch: `model.invalidate_caches()` stays available
+        return
+
+    def _bump(optimizer, args, kwargs):
+        for m in list(_LIVE_MODELS):
+            m._opt_steps += 1
+
+    register_optimizer_step_post_hook(_bump)
+    _HOOK_INSTALLED = True
 
 
 class MedTsLLM(nn.Module):
@@ -207,6 +232,12 @@ class MedTsLLM(nn.Module):
         self._prompt_cache: dict[str, list[int]] = {}
         self._src_cache = None     # (versions, source_bf16, K_bf16, Vt_bf16)
         self._w_cache: dict[str, tuple[int, torch.Tensor]] = {}
+        # generation of the device-side caches (bf16 weight copies, prototype K/V, constant down-sample matrix, RoPE
+        # tables, LoRA operands): part of the graph-replay key, because a captured graph holds raw pointers into them
+        self._cache_gen = 0
+        self._opt_steps = 0        # optimizer steps seen by the global hook (part of every weight-cache key)
+        _LIVE_MODELS.add(self)
+        _install_optimizer_hook()
 
     # ------------------------------------------------------------------------------------------ LLM
     def setup_llm(self, backbone=None, tokenizer=None):
@@ -496,6 +527,7 @@ class MedTsLLM(nn.Module):
                 g = D // E
                 w.view(E, E, g)[torch.arange(E), torch.arange(E), :] = 1.0 / g
             self._ds_fixed = ops.cast_bf16(w.to(self.device))
+            self._cache_gen += 1
         return self._ds_fixed, None
 
     def train_graph_enabled(self) -> bool:
@@ -521,14 +553,27 @@ class MedTsLLM(nn.Module):
         """bf16 copy [rows, ceil8(cols)] (zero padded: TMA rows must be 16-byte aligned) of a trainable
         fp32 master, re-cast by our kernel only when the optimizer has changed it (`_version` bumps on
         every in-place update)."""
-        key = (p._version, p.data_ptr())
+        key = (p._version, p.data_ptr(), self._opt_steps)
         hit = self._w_cache.get(name)
         if hit is not None and hit[0] == key and not self._force_recast:
             return hit[1]
         rows, cols = p.shape
         w = ops.cast_rows(p.detach().contiguous(), rows=rows, cols=cols)
         self._w_cache[name] = (key, w)
+        self._cache_gen += 1
         return w
+
+    def invalidate_caches(self):
+        """Drops every derived device-side copy (bf16 adapter weights, prototype K / V, LoRA operands) and the captured
+        graphs.  Needed only after weight surgery that neither bumps `Parameter._version` nor goes through a torch
+        optimizer's `step()` (e.g. `p.data.copy_(...)` by hand, EMA weight swaps): see INTEGRATION.md."""
+        self._w_cache.clear()
+        self._src_cache = None
+        self._cache_gen += 1
+        self._graph = GraphReplay()
+        self._train_graph = None
+        if self.lora_enabled:
+            self.llm._cache.clear()
 
     def _source_kv(self):
         """Prototype path (models/medtsllm.py:281, :574-575): source = W_map E + b; K = W_k source + b_k;
@@ -536,9 +581,10 @@ class MedTsLLM(nn.Module):
         rl = self.reprogramming_layer
         plist = [self.mapping_layer.weight, self.mapping_layer.bias, rl.key_projection.weight,
                  rl.key_projection.bias, rl.value_projection.weight, rl.value_projection.bias]
-        key = tuple((p._version, p.data_ptr()) for p in plist)
+        key = tuple((p._version, p.data_ptr()) for p in plist) + (self._opt_steps,)
         if self._src_cache is not None and self._src_cache[0] == key and not self._force_recast:
             return self._src_cache[1:]
+        self._cache_gen += 1
         bb = self._backbone
         S, D, HE, V = self.num_tokens, self.d_llm, self.d_ff * self.n_attention_heads, self.vocab_size
         dev = self.device
@@ -579,7 +625,8 @@ class MedTsLLM(nn.Module):
         ids = self.prompt_token_ids(inputs)
         params = list(self.parameters()) + (self.llm.params() if self.lora_enabled else [])
         key = (tuple(x_enc.shape), x_enc.device.index, self.training, id(ids), self.share_prompt_prefix,
-               tuple((p._version, p.data_ptr()) for p in params))
+               tuple((p._version, p.data_ptr()) for p in params), self._opt_steps, self._cache_gen,
+               self._backbone.cache_gen, self.llm._cache_gen if self.lora_enabled else 0)
         return self._graph.run(key, x_enc, lambda xs: self._predict_eager({**inputs, "x_enc": xs}, ids), hold=ids)
 
     def _predict_eager(self, inputs, ids=None):

@@ -125,11 +125,13 @@ def patch_gather(x, P, S):
     return out
 
 
-def revin_patch_embed_bwd(x, mean, std, dout, P, S, dm, *, concat):
+def revin_patch_embed_bwd(x, mean, std, dout, P, S, dm, *, concat, out=None):
     _chk(x, torch.float32, "x"); _chk(dout, torch.float32, "dout")
     x = x.contiguous(); dout = dout.contiguous()
     B, T, Cc = x.shape
-    dw = torch.empty(dm, P, 3, device=x.device, dtype=torch.float32)
+    dw = torch.empty(dm, P, 3, device=x.device, dtype=torch.float32) if out is None else out
+    if dw.shape != (dm, P, 3) or dw.dtype != torch.float32 or not dw.is_contiguous():
+        raise MtsError("revin_patch_embed_bwd: out must be contiguous fp32 [d_model, P, 3]")
     _lib.call("mts_revin_patch_embed_bwd", x.data_ptr(), mean.data_ptr(), std.data_ptr(),
               dout.data_ptr(), dw.data_ptr(), B, T, Cc, P, S, dm, 1 if concat else 0, _stream())
     return dw
@@ -471,13 +473,16 @@ def softmax_bwd_rows(p, dp, scale):
     return ds
 
 
-def colsum(x, rows=None, cols=None, ld=None):
+def colsum(x, rows=None, cols=None, ld=None, out=None):
     """fp32 [cols] = column sums of a (possibly strided) 2-D view of x."""
     _chk(x, None, "x")
     if rows is None:
         cols = x.shape[-1]; rows = x.numel() // cols
     ld = cols if ld is None else ld
-    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    elif out.numel() != cols or out.dtype != torch.float32 or not out.is_contiguous():
+        raise MtsError("colsum: out must be contiguous fp32 [cols]")
     _lib.call("mts_colsum", x.data_ptr(), _dt(x), ld, out.data_ptr(), rows, cols, _stream())
     return out
 

@@ -46,8 +46,10 @@ WORKLOADS = {
     "bidmc_llama2_7b": Workload("bidmc_llama2_7b", LLAMA2_7B, "segmentation", B=32, T=512, pred=512, C=3,
                                 description="The BIDMC dataset contains PPG, ECG and respiration signals."),
     # configs[2]
-    "ludb_llama2_7b": Workload("ludb_llama2_7b", LLAMA2_7B, "semantic_segmentation", B=16, T=1024, pred=1024, C=1,
-                               d_ff=128, n_classes=4, covariate_mode="univariate",
+    # (BASELINE.json names n_vars = 12; the shipped ludb.toml reads one lead at a time with covariate_mode "univariate" —
+    # SURVEY.md section 8 sizes this config as 12 leads concatenated: d_model' = 384, 4 x 1024 outputs per window)
+    "ludb_llama2_7b": Workload("ludb_llama2_7b", LLAMA2_7B, "semantic_segmentation", B=16, T=1024, pred=1024, C=12,
+                               d_ff=128, n_classes=4, covariate_mode="concat",
                                description="LUDB is an ECG signal database with marked boundaries of waves."),
     # configs[3]
     "psm_gpt2_medium": Workload("psm_gpt2_medium", GPT2_MEDIUM, "anomaly_detection", B=64, T=100, pred=100, C=25,

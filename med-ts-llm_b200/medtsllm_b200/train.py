@@ -36,7 +36,7 @@ class TrainGraph:
     the optimizer updates the fp32 masters in place and the captured forward re-casts them to bf16 every replay
     (`model._force_recast` makes the capture include every cast / prototype GEMM even if a cache would hit).
     The gradients come back in static buffers and are handed to autograd as copies.  With data parallelism the
-    all-reduce runs after the backward graph (NCCL stays outside the capture)."""
+    all-reduces run between the two backward graphs (NCCL stays outside the capture)."""
 
     def __init__(self):
         self.entry = None
@@ -83,23 +83,44 @@ class TrainGraph:
         if e is None or generation != self.generation:
             raise MtsError("backward() of a training step whose activations were overwritten by a later forward on "
                            "the captured graph (set model.use_train_graph = False for this usage pattern)")
+        # two graphs: everything up to the exchanged gradients, then the mapping-layer gradient from the (averaged)
+        # dSource.  The collectives run between them, in the same order as on the kernel-by-kernel path, so ranks
+        # that disagree on graph vs eager (a per-rank decision) still issue matching NCCL sequences.
         if e["bwd"] is None:
             e["dout"] = dout.clone()
             graph = torch.cuda.CUDAGraph()
             n0 = launch_count()
             with torch.cuda.graph(graph, pool=e["fwd"].pool(), capture_error_mode="thread_local"):
-                e["grads"] = _backward_chain(model, e["stash"], e["dout"], use_dp=False)
+                e["ctx"] = _backward_part1(model, e["stash"], e["dout"], use_dp=False)
             e["bwd"], e["bwd_launches"] = graph, launch_count() - n0
             graph.replay()
         else:
             e["dout"].copy_(dout)
             e["bwd"].replay()
             note_replay(e["bwd_launches"])
-        grads = [g.clone() if g is not None else None for g in e["grads"]]
-        if dp.is_active():
-            bucket = dp.GradBucket(grads).launch()
-            bucket.finish()
-        return grads
+        ctx = e["ctx"]
+        active = dp.is_active()
+        if active:
+            ctx["early"].launch()
+            ctx["dsrc_arena"].launch()
+            ctx["late"].launch()
+            lora_bucket = dp.GradBucket(ctx["lora_grads"]).launch()
+            ctx["dsrc_arena"].finish()
+        if e.get("bwd2") is None:
+            graph = torch.cuda.CUDAGraph()
+            n0 = launch_count()
+            with torch.cuda.graph(graph, pool=e["fwd"].pool(), capture_error_mode="thread_local"):
+                e["grads"] = _backward_part2(model, ctx)
+            e["bwd2"], e["bwd2_launches"] = graph, launch_count() - n0
+            graph.replay()
+        else:
+            e["bwd2"].replay()
+            note_replay(e["bwd2_launches"])
+        if active:
+            ctx["early"].finish()
+            ctx["late"].finish()
+            lora_bucket.finish()
+        return [g.clone() if g is not None else None for g in e["grads"]]
 
 
 def _t(x, **kw):
@@ -144,14 +165,49 @@ class _HotPathFn(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+def _arena_layout(m):
+    """(early, late) name/shape lists of the adapter gradients.  `early` = final before the backbone dgrad starts
+    (head, down-sample, merge-end weighting); `late` = everything in front of the backbone except the mapping layer,
+    whose weight gradient is derived AFTER the exchange from the averaged `dsrc` (see dp.py)."""
+    named = dict(m.named_parameters())
+    mode = m.covariate_mode
+    early = ["output_projection.linear.weight", "output_projection.linear.bias"]
+    if m.embedding_downsample_mode == "linear":
+        early += ["embedding_downsample_layer.weight", "embedding_downsample_layer.bias"]
+    if mode == "merge-end":
+        early += ["feature_weighting.weight", "feature_weighting.bias"]
+    late = ["patch_embedding.value_embedding.tokenConv.weight"]
+    for proj in ("query", "key", "value", "out"):
+        late += [f"reprogramming_layer.{proj}_projection.weight", f"reprogramming_layer.{proj}_projection.bias"]
+    if mode == "weighted-average":
+        late += ["feature_weighting.weight", "feature_weighting.bias"]
+    shape = lambda names: [(k, tuple(named[k].shape)) for k in names]      # noqa: E731
+    return shape(early), shape(late)
+
+
 def _backward_chain(m, st, dout, use_dp=True):
     """The manual backward of the hot path (see the module docstring): returns the gradients aligned with
-    `m.adapter_params()`.  `use_dp`: overlap the gradient all-reduce with the chain (eager path); the graph path
-    captures the chain without collectives and all-reduces afterwards."""
+    `m.adapter_params()`.  Kernel-by-kernel path; with data parallelism the three exchanges (early arena, dSource,
+    late arena — always in this order, the graph path issues the same sequence) overlap the chain."""
+    ctx = _backward_part1(m, st, dout, use_dp=use_dp)
+    if use_dp:
+        ctx["dsrc_arena"].finish()
+    grads = _backward_part2(m, ctx)
+    if use_dp:
+        lora_bucket = dp.GradBucket(ctx["lora_grads"]).launch()
+        ctx["early"].finish()
+        ctx["late"].finish()
+        lora_bucket.finish()
+    return grads
+
+
+def _backward_part1(m, st, dout, use_dp):
+    """Everything up to the gradients that are exchanged between ranks: fills the early / late arenas and `dsrc`
+    (gradient of the prototype matrix `source`), launching their all-reduces as they become final when `use_dp`."""
     bb = m._backbone
     dev = dout.device
     B0, B, N, N0, E, H, D = st["B"], st["Bp"], m.n_patches, st["N0"], m.d_ff, m.n_attention_heads, m.d_llm
-    HE, S, Lp, L, V, C = H * E, m.num_tokens, st["Lp"], st["L"], m.vocab_size, m.n_features
+    HE, S, Lp, L, C = H * E, m.num_tokens, st["Lp"], st["L"], m.n_features
     Lc = st["Lc"]               # shared-prefix rows: the backward runs on the sequences' own rows only ...
     Ls = L - Lc                 # own rows per sequence
     row0 = Lc if (Lc and m.lora_enabled) else 0    # ... unless LoRA needs the prefix rows too (all rows then)
@@ -163,7 +219,10 @@ def _backward_chain(m, st, dout, use_dp=True):
     f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
     bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)     # noqa: E731
     zbf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)    # noqa: E731
-    g_fw_w = g_fw_b = None
+    early_l, late_l = _arena_layout(m)
+    early, late = dp.GradArena(early_l, dev), dp.GradArena(late_l, dev)
+    dsrc_arena = dp.GradArena([("dsrc", (S, D))], dev)
+    gv = lambda k: (early if k in early else late).view(k)                # noqa: E731
 
     # ---- de-norm / squeeze (models/medtsllm.py:379-382): statistics are detached
     dout = dout.reshape(B0, m.pred_len, m.n_outputs_per_step).contiguous()
@@ -175,16 +234,18 @@ def _backward_chain(m, st, dout, use_dp=True):
     elif mode == "merge-end":
         dy2, g_fw_w, g_fw_b = ops.merge_end_bwd(dy, st["head"], m.feature_weighting.weight.detach(), B0, C,
                                                 m.pred_len, m.n_outputs_per_step)
+        gv("feature_weighting.weight").copy_(g_fw_w)
+        gv("feature_weighting.bias").copy_(g_fw_b)
     else:
         dy2 = dy.view(B, n_out)
 
     # ---- flatten head: out = flat W_h^T + b_h
-    g_bh = ops.colsum(dy2)
+    ops.colsum(dy2, out=gv("output_projection.linear.bias"))
     dy_b = ops.cast_rows(dy2, rows=B, cols=n_out)                          # bf16 [B, ceil8(n_out)]
     wh = m._bf16_weight("wh", m.output_projection.linear.weight)           # [n_out, ceil8(EN)]
     EN = E * N
-    g_wh = f32(n_out, EN)
-    ops.gemm(_t(dy2), _t(st["flat"]), g_wh, m=n_out, n=EN, k=B, lda=ops.ceil8(B), ldb=ops.ceil8(B))
+    ops.gemm(_t(dy2), _t(st["flat"]), gv("output_projection.linear.weight"), m=n_out, n=EN, k=B,
+             lda=ops.ceil8(B), ldb=ops.ceil8(B))
     wh_t = ops.transpose_strided(wh, rows=n_out, cols=EN, ld_in=wh.shape[1])   # [EN, ceil8(n_out)]
     dflat = bf(B, EN)                                                       # [B, E, N]
     ops.gemm(dy_b, wh_t, dflat, m=B, n=EN, k=n_out, lda=dy_b.shape[1], ldb=wh_t.shape[1])
@@ -195,13 +256,12 @@ def _backward_chain(m, st, dout, use_dp=True):
     dyds = bf(Rh, E)
     for b in range(B):   # B small launches of a tiny kernel (B*N*E elements in total)
         ops.transpose_strided(dflat, rows=E, cols=N, in_off=b * EN, out=dyds[b * N:(b + 1) * N], ld_out=E)
-    g_bds = g_wds = None
     if m.embedding_downsample_mode == "linear":
-        g_bds = ops.colsum(dyds)
+        ops.colsum(dyds, out=gv("embedding_downsample_layer.bias"))
         hid_last_t = ops.transpose_strided(st["hid"], batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D,
                                            in_off=Lp * D)                  # [D, ceil8(R)]
-        g_wds = f32(E, D)
-        ops.gemm(_t(dyds), hid_last_t, g_wds, m=E, n=D, k=Rh, lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
+        ops.gemm(_t(dyds), hid_last_t, gv("embedding_downsample_layer.weight"), m=E, n=D, k=Rh,
+                 lda=ops.ceil8(Rh), ldb=hid_last_t.shape[1])
     wds, _ = m._downsample_operands()                                       # [E, D] (trainable or constant)
     wds_t = ops.transpose_strided(wds, rows=E, cols=D, ld_in=wds.shape[1])  # [D, ceil8(E)]
     dhid = zbf(row0 + B * Ls, D)                                            # zero for prompt rows
@@ -209,7 +269,6 @@ def _backward_chain(m, st, dout, use_dp=True):
              d_bs=Ls * D, ldd=D, d_off=own_off * D)
 
     # ---- DP: the head / down-sample gradients are final -> all-reduce them underneath the backbone dgrad
-    early = dp.GradBucket([g_wh, g_bh] + ([g_wds, g_bds] if g_wds is not None else []))
     if use_dp:
         early.launch()
 
@@ -230,12 +289,12 @@ def _backward_chain(m, st, dout, use_dp=True):
         dyf, g_w, g_b = ops.group_reduce_bwd(dR, B0, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
                                              x=st["Y"] if fw is not None else None, dout_bs=Ls * D, dout_off=own_off * D)
         if fw is not None:
-            g_fw_w, g_fw_b = g_w.view(1, C), g_b.view(1)
+            gv("feature_weighting.weight").copy_(g_w.view(1, C))
+            gv("feature_weighting.bias").copy_(g_b.view(1))
         dxp = ops.cast_bf16(dyf.view(R, D))
-    g_bo = ops.colsum(dxp)
+    ops.colsum(dxp, out=gv("reprogramming_layer.out_projection.bias"))
     Rp = ops.ceil8(R)
-    g_wo = f32(D, HE)
-    ops.gemm(_t(dxp), _t(st["O"]), g_wo, m=D, n=HE, k=R, lda=Rp, ldb=Rp)
+    ops.gemm(_t(dxp), _t(st["O"]), gv("reprogramming_layer.out_projection.weight"), m=D, n=HE, k=R, lda=Rp, ldb=Rp)
     wo = m._bf16_weight("wo", rl.out_projection.weight)                    # [D, HE]
     wo_t = ops.transpose_strided(wo, rows=D, cols=HE, ld_in=wo.shape[1])   # [HE, D]
     dO = bf(R, HE)
@@ -260,57 +319,68 @@ def _backward_chain(m, st, dout, use_dp=True):
     ops.gemm(P_t, dO_t, dV, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
     dK = bf(S, HE)
     ops.gemm(dS_t, Q_t, dK, m=S, n=E, k=R, batch=H, lda=H * Rp, a_bs=Rp, ldb=Rp, b_bs=E * Rp, ldd=HE, d_bs=E)
+
+    # ---- gradient of the prototypes `source` (through the key / value projections): exchanged between ranks in place
+    # of the mapping-layer weight gradient derived from it (part 2)
+    wk = m._bf16_weight("wk", rl.key_projection.weight)                    # [HE, D]
+    wv = m._bf16_weight("wv", rl.value_projection.weight)
+    dsrc = dsrc_arena.view("dsrc")
+    ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
+    ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
+    if use_dp:
+        dsrc_arena.launch()
+
     K_t = _t(K)                                                            # [HE, S]
     dQ = bf(R, HE)
     ops.gemm(dS, K_t, dQ, m=R, n=E, k=S, batch=H, a_bs=R * S, lda=S, ldb=K_t.shape[1], b_bs=E * K_t.shape[1],
              ldd=HE, d_bs=E)
 
     # ---- query projection + front end
-    g_bq = ops.colsum(dQ)
+    ops.colsum(dQ, out=gv("reprogramming_layer.query_projection.bias"))
     enc2 = st["enc"].view(R, dm)
-    g_wq = f32(HE, dm)
-    ops.gemm(_t(dQ), _t(enc2), g_wq, m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
+    ops.gemm(_t(dQ), _t(enc2), gv("reprogramming_layer.query_projection.weight"), m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
     wq = m._bf16_weight("wq", rl.query_projection.weight)                  # [HE, ceil8(dm)]
     wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
     denc = f32(R, dm)
     ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
     if p_drop > 0:
         ops.dropout(denc, p_drop, seeds[0], out=denc)                      # patch-embedding dropout mask
-    g_conv = ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
-                                       m.patch_len, m.stride, m.d_patch, concat=st["concat"])
+    ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
+                              m.patch_len, m.stride, m.d_patch, concat=st["concat"],
+                              out=gv("patch_embedding.value_embedding.tokenConv.weight"))
 
-    # ---- key / value projections of the prototypes, then the mapping layer
+    # ---- key / value projections of the prototypes
     source = st["source"]
     src_t = _t(source)                                                     # [D, S]
-    g_bk, g_bv = ops.colsum(dK), ops.colsum(dV)
-    g_wk, g_wv = f32(HE, D), f32(HE, D)
-    ops.gemm(_t(dK), src_t, g_wk, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
-    ops.gemm(_t(dV), src_t, g_wv, m=HE, n=D, k=S, lda=ops.ceil8(S), ldb=src_t.shape[1])
-    wk = m._bf16_weight("wk", rl.key_projection.weight)                    # [HE, D]
-    wv = m._bf16_weight("wv", rl.value_projection.weight)
-    dsrc = f32(S, D)
-    ops.gemm(dK, _t(wk), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE))
-    ops.gemm(dV, _t(wv), dsrc, m=S, n=D, k=HE, ldb=ops.ceil8(HE), epilogue=EPI_RESID_ADD)
+    ops.colsum(dK, out=gv("reprogramming_layer.key_projection.bias"))
+    ops.colsum(dV, out=gv("reprogramming_layer.value_projection.bias"))
+    ops.gemm(_t(dK), src_t, gv("reprogramming_layer.key_projection.weight"), m=HE, n=D, k=S, lda=ops.ceil8(S),
+             ldb=src_t.shape[1])
+    ops.gemm(_t(dV), src_t, gv("reprogramming_layer.value_projection.weight"), m=HE, n=D, k=S, lda=ops.ceil8(S),
+             ldb=src_t.shape[1])
+    if use_dp:
+        late.launch()
+    lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
+    return {"early": early, "late": late, "dsrc_arena": dsrc_arena, "lora_grads": lora_grads}
+
+
+def _backward_part2(m, ctx):
+    """Mapping layer (models/medtsllm.py:281) from the — under DP already averaged — gradient of `source`:
+    d W_map = dSource E, d b_map = rowsum(dSource).  Returns all gradients in `m.adapter_params()` order."""
+    bb = m._backbone
+    dsrc = ctx["dsrc_arena"].view("dsrc")
+    S, V = m.num_tokens, m.vocab_size
     dsrc_b = ops.cast_bf16(dsrc)
     g_bmap = ops.rowsum(dsrc)                                              # d b_map[s] = sum_d dSource[s, d]
-    g_wmap = f32(S, V)
-    ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=D)
-
-    lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
-    if use_dp:
-        late = dp.GradBucket([g_conv, g_wmap, g_bmap, g_wq, g_bq, g_wk, g_bk, g_wv, g_bv, g_wo, g_bo, g_fw_w, g_fw_b]
-                             + lora_grads).launch()
-        early.finish()
-        late.finish()
-    grads = {
-        "patch_embedding.value_embedding.tokenConv.weight": g_conv,
-        "mapping_layer.weight": g_wmap, "mapping_layer.bias": g_bmap,
-        "reprogramming_layer.query_projection.weight": g_wq, "reprogramming_layer.query_projection.bias": g_bq,
-        "reprogramming_layer.key_projection.weight": g_wk, "reprogramming_layer.key_projection.bias": g_bk,
-        "reprogramming_layer.value_projection.weight": g_wv, "reprogramming_layer.value_projection.bias": g_bv,
-        "reprogramming_layer.out_projection.weight": g_wo, "reprogramming_layer.out_projection.bias": g_bo,
-        "embedding_downsample_layer.weight": g_wds, "embedding_downsample_layer.bias": g_bds,
-        "output_projection.linear.weight": g_wh, "output_projection.linear.bias": g_bh,
-        "feature_weighting.weight": g_fw_w, "feature_weighting.bias": g_fw_b,
-    }
-    return [grads[k] for k in m.param_order()] + list(lora_grads)
+    g_wmap = torch.empty(S, V, device=dsrc.device, dtype=torch.float32)
+    ops.gemm(dsrc_b, bb.embed_bf16(), g_wmap, m=S, n=V, k=m.d_llm)
+    early, late = ctx["early"], ctx["late"]
+    out = []
+    for k in m.param_order():
+        if k == "mapping_layer.weight":
+            out.append(g_wmap)
+        elif k == "mapping_layer.bias":
+            out.append(g_bmap)
+        else:
+            out.append((early if k in early else late).view(k))
+    return out + list(ctx["lora_grads"])

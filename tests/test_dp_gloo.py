@@ -34,6 +34,17 @@ def _worker(rank, world, port, ret):
             parts = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(parts, mine[i])
             torch.testing.assert_close(t, torch.stack(parts).mean(0), rtol=1e-6, atol=1e-6)
+        # gradient arena: kernels write straight into slices of one flat buffer, all-reduced in place (no cat / copy)
+        arena = dp.GradArena([("w", (4, 3)), ("b", (5,)), ("c", (2, 2))], "cpu")
+        assert all(arena.offsets[k][0] % 4 == 0 for k in arena.offsets)          # 16-byte aligned slices
+        local = {k: torch.randn(arena.view(k).shape, generator=g) for k in ("w", "b", "c")}
+        for k, t in local.items():
+            arena.view(k).copy_(t)
+        arena.launch().finish()
+        for k, t in local.items():
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            torch.testing.assert_close(arena.view(k), torch.stack(parts).mean(0), rtol=1e-6, atol=1e-6)
         # batch sharding covers every item exactly once
         shards = [list(dp.shard_batch(11, r, world)) for r in range(world)]
         assert sorted(sum(shards, [])) == list(range(11)) and abs(len(shards[0]) - len(shards[1])) <= 1
@@ -45,7 +56,14 @@ def _worker(rank, world, port, ret):
         all_seen = [torch.empty_like(seen) for _ in range(world)]
         dist.all_gather(all_seen, seen)
         assert sorted(torch.cat(all_seen).tolist()) == list(range(20))
-        assert dl.batch_size == 4
+        assert dl.batch_size == 4 and len(dl) == 3
+        # every pass is a new epoch: a different permutation (the reference's shuffle=True reshuffles per epoch,
+        # tasks/base.py:175-182), still a partition of the dataset across ranks
+        seen2 = torch.cat([b[0] for b in dl])
+        assert not torch.equal(seen, seen2)
+        all_seen2 = [torch.empty_like(seen2) for _ in range(world)]
+        dist.all_gather(all_seen2, seen2)
+        assert sorted(torch.cat(all_seen2).tolist()) == list(range(20))
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

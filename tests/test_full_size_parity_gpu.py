@@ -1,0 +1,131 @@
+"""GPU-vs-oracle parity at the REAL backbone architectures of BASELINE.json's configs (Llama-2-7B shape: D = 4096,
+I = 11008, 32 layers, head dim 128; GPT-2-medium: D = 1024, 24 layers) — the shapes the toy fixtures under
+tests/golden/ (D <= 256, <= 2 layers) cannot speak for: 32 layers of rounding growth, the BIDMC / LUDB / PSM /
+Ventilator GEMM shapes (K = 4096 / 11008, the 5.19-wave tail split), head dim 128 attention over 170 - 256 positions.
+
+What is compared (relative L2 against the CPU oracle, oracle/medtsllm_oracle.py, run on the SAME weights pulled back
+from the device one layer at a time, the same prompt ids and the same windows; batch reduced to 2 so that the fp32 CPU
+forward takes seconds):
+  * the residual stream after 1, 2, 4, 8, 16 layers, the final-norm output (`llm`), the model output;
+  * in both precisions of the kernel path: "bf16" (bf16 operands / fp32 accumulate = the reference's bf16-autocast
+    training regime, tasks/forecasting.py:22) and "tf32" (fp32 operands on tcgen05 kind::tf32 = the reference's
+    evaluation regime, tasks/base.py:19-22);
+  * YARDSTICK: HuggingFace's own LlamaModel / GPT2Model on the same weights on the same GPU (eager attention, as the
+    reference configures it) in true fp32, TF32 and bf16-autocast against the same oracle.
+
+Stated tolerances (asserted below):
+  tf32 mode  : output rel-L2 <= 1e-3 (BASELINE.json north_star), final-norm hidden states <= 2e-3
+  bf16 mode  : output and hidden states no worse than 1.5x HuggingFace's own bf16-autocast forward on the same
+               weights, and output <= 2e-2 absolute (two bf16 implementations of a 32-layer stack differ by ~1e-2;
+               SURVEY.md section 7 "hard parts")
+The measured table is printed and written to gpurun_out/parity_fullsize_<workload>_<precision>.json.
+"""
+import json
+import os
+from pathlib import Path
+
+import pytest
+import torch
+
+from _fullsize import LazyBackboneState, build, hf_backbone_on_gpu, hf_regimes, oracle_spec, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+REPO = Path(__file__).resolve().parent.parent
+DEPTHS = (1, 2, 4, 8, 16)
+
+
+def _kernel_hidden_states(model, llm_input, Bp, L, precision):
+    """Residual stream entering every layer + final-norm output of the kernel backbone on `llm_input` [Bp, L, D]."""
+    bb = model._backbone
+    D = bb.spec.hidden
+    x = llm_input.reshape(Bp * L, D).contiguous().clone()
+    if precision == "tf32":
+        hidden = []
+        out = bb.forward_tf32(x, Bp, L, hidden=hidden)
+        return hidden, out.float().view(Bp, L, D)
+    stash = []
+    out, x_final = bb.forward(x, Bp, L, stash=stash)
+    hidden = [st["x_in"].view(Bp, L, D) for st in stash] + [x_final.view(Bp, L, D)]
+    return hidden, out.float().view(Bp, L, D)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("workload", ["bidmc_llama2_7b", "ludb_llama2_7b", "psm_gpt2_medium", "ventilator_llama2_7b"])
+def test_full_depth_forward_vs_oracle(workload, precision, cuda):
+    from oracle import medtsllm_oracle as O
+    batch = 2
+    w, model, inputs = build(workload, cuda, batch, precision=precision)
+    model.precision = precision
+    if w.lora_rank:        # Ventilator + LoRA: non-trivial B so that the LoRA path contributes (identity at init otherwise)
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            for p in model.llm.B:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(cuda))
+    x_dev = inputs["x_enc"].to(cuda)
+    model._capture = {}
+    with torch.no_grad():
+        out = model({"x_enc": x_dev})
+    torch.cuda.synchronize()
+    cap, model._capture = model._capture, None
+
+    # ---- the oracle on the same weights (CPU, fp32)
+    bb = model._backbone
+    sd = LazyBackboneState(bb, precision=precision)
+    adapters = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ids = model.prompt_token_ids({"x_enc": x_dev}).tolist()
+    lora = None
+    if w.lora_rank:
+        lora = {"scale": model.llm.scale, "n_targets": len(model.llm.targets),
+                "A": [p.detach().cpu() for p in model.llm.A], "B": [p.detach().cpu() for p in model.llm.B]}
+    with torch.no_grad():
+        ref_out, st = O.medtsllm_forward(inputs["x_enc"], ids, adapters, sd, oracle_spec(w, model), return_stages=True,
+                                         lora=lora)
+    hid_ref = st["llm.hidden_states"]
+    Bp, L, D = st["llm_input"].shape
+    n_layers = bb.spec.layers
+
+    # ---- kernel path: per-layer residual stream on the oracle's own backbone input (isolates the backbone)
+    llm_in = st["llm_input"].to(cuda)
+    if bb.spec.kind == "gpt2":
+        llm_in = llm_in + bb.wpe[:L][None]           # the kernel path folds wpe into its gather; the oracle adds it inside
+    rows = {}
+    if lora is None:
+        hid_k, fin_k = _kernel_hidden_states(model, llm_in, Bp, L, precision)
+        rows["kernel"] = {f"L{d}": rel_l2(hid_k[d], hid_ref[d]) for d in DEPTHS if d < n_layers}
+        rows["kernel"]["llm"] = rel_l2(fin_k, st["llm"])
+    else:
+        rows["kernel"] = {}
+    # whole model (front end + prompt gather + backbone + head), as the user calls it
+    rows["kernel"]["llm_e2e"] = rel_l2(cap["llm"].float().view(st["llm"].shape), st["llm"])
+    rows["kernel"]["llm_input"] = rel_l2(
+        (cap["llm_input"] - (bb.wpe[:L][None] if bb.spec.kind == "gpt2" else 0)).view(st["llm_input"].shape), st["llm_input"])
+    rows["kernel"]["output"] = rel_l2(out, ref_out)
+
+    # ---- yardstick: HuggingFace on the same GPU, same weights, three regimes
+    if lora is None and os.environ.get("MTS_SKIP_HF_YARDSTICK", "0") != "1":
+        del model
+        torch.cuda.empty_cache()
+        hf = hf_backbone_on_gpu(bb, cuda, precision=precision)
+        res = hf_regimes(hf, st["llm_input"].to(cuda), bb.spec.kind)
+        for name, (hs, last) in res.items():
+            rows["hf_" + name] = {f"L{d}": rel_l2(hs[d], hid_ref[d]) for d in DEPTHS if d < n_layers}
+            rows["hf_" + name]["llm"] = rel_l2(last, st["llm"])
+        del hf, res
+
+    report = {"workload": workload, "precision": precision, "batch": batch, "backbone": bb.spec.kind, "layers": n_layers,
+              "D": D, "L": L, "rel_l2_vs_cpu_oracle": rows}
+    print("\n[full-size parity] " + json.dumps(report))
+    outdir = REPO / "gpurun_out"
+    outdir.mkdir(exist_ok=True)
+    (outdir / f"parity_fullsize_{workload}_{precision}.json").write_text(json.dumps(report, indent=1))
+
+    k = rows["kernel"]
+    assert torch.isfinite(out).all()
+    if precision == "tf32":
+        assert k["output"] <= 1e-3, k                     # north_star: outputs within 1e-3 rel of the reference
+        assert k["llm_e2e"] <= 2e-3, k
+    else:
+        assert k["output"] <= 2e-2, k
+        if "hf_bf16_autocast" in rows:
+            assert k["llm"] <= 1.5 * rows["hf_bf16_autocast"]["llm"] + 1e-3, rows
