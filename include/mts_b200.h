@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTS_ABI_VERSION 1
+#define MTS_ABI_VERSION 2
 
 typedef void* mts_stream_t; /* cudaStream_t */
 
@@ -189,6 +189,20 @@ typedef struct mts_gemm_args {
   /* column order as the weight rows) kept for the backward; batch must be 1 when used                       */
   void* aux;
   int64_t ld_aux;
+  /* ABI 2 — evaluation parity mode (the reference evaluates with fp32 weights and TF32 matmuls, tasks/base.py:19-22):
+   * ab_dtype = MTS_F32: A and B are fp32 (lda / ldb / batch strides multiples of 4) and the contraction runs on
+   * tcgen05 kind::tf32 (operands should already be TF32-representable: mts_round_tf32, round_tf32 below — the tensor
+   * core ignores the low 13 mantissa bits); MTS_BF16 (0) = the default bf16 path.
+   * round_tf32 != 0 with an fp32 D (not RESID_ADD): store D rounded to nearest TF32, ready to be the next GEMM's operand.
+   * With fp32 operands the GELU_NEW / SWIGLU / ROPE_QK epilogues write fp32 D (ROPE_QK always TF32-rounded). */
+  int32_t ab_dtype;
+  int32_t round_tf32;
+  /* fp32-grade contraction out of TF32 pieces ("3xTF32"): when a_lo and b_lo are given (fp32 operands only; same
+   * shapes / strides as a and b), the operands are A = a + a_lo, B = b + b_lo with every piece TF32-representable
+   * (mts_split_tf32) and the kernel accumulates a*b + a_lo*b + a*b_lo into one fp32 accumulator — relative error
+   * ~2^-21 instead of TF32's 2^-11 at three times the tensor work.  NULL (both) = plain TF32. */
+  const void* a_lo;
+  const void* b_lo;
 } mts_gemm_args;
 
 int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);
@@ -301,6 +315,28 @@ int mts_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t 
  *   sigmoid (binary semantic segmentation / boundary prediction), softmax over n classes. */
 int mts_sigmoid(float* y, int64_t n, mts_stream_t stream);
 int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Evaluation parity modes (ABI 2): fp32 activations, contractions on tcgen05 kind::tf32         */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference evaluates with fp32 weights and TF32 matmuls (tasks/base.py:19-22; `setup.dtype` "mixed" and
+ * "float32" alike).  "tf32" mode follows that regime: every GEMM is mts_gemm with ab_dtype = MTS_F32 on operands
+ * rounded to nearest TF32; "fp32" mode runs the same kernels with the 3xTF32 split (a_lo / b_lo), i.e. fp32-grade
+ * contractions.  Norms, softmax, RoPE, SwiGLU / GELU and attention are computed in fp32 in both. */
+/* y[i] = nearest TF32-representable value of x[i] (y == x allowed). */
+int mts_round_tf32(const float* x, float* y, int64_t n, mts_stream_t stream);
+/* x = hi + lo with both pieces TF32-representable (hi = tf32(x), lo = tf32(x - hi)): the operands of a 3xTF32 GEMM. */
+int mts_split_tf32(const float* x, float* hi, float* lo, int64_t n, mts_stream_t stream);
+/* fp32 row softmax with scale: p = softmax(scale * s) over the last axis; s, p fp32 [rows, n]
+ * (ref: models/medtsllm.py:587, reprogramming scores). */
+int mts_softmax_rows_f32(const float* s, float* p, int64_t rows, int n, float scale, mts_stream_t stream);
+/* fp32 causal self-attention, eager semantics (ref: HF:models/llama/modeling_llama.py:199-221,
+ * HF:models/gpt2/modeling_gpt2.py:54-72; no padding mask, models/medtsllm.py:350), plain FMA arithmetic.
+ *   qkv fp32 [Lc + Bp*Ls, 3*H*hd] (q / k already rotated for Llama), out fp32 [Lc + Bp*Ls, H*hd]
+ *   Lc = 0: plain layout, Ls = L.  Lc > 0: shared-prefix row layout (see mts_attn_causal_shared).
+ *   round_out != 0: store the result rounded to TF32 (operand of the out-projection in "tf32" mode).  hd in {64, 128}. */
+int mts_attn_causal_f32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                        int round_out, mts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Training path (adapter gradients; dgrad through the frozen backbone)                        */

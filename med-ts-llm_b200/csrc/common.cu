@@ -74,6 +74,7 @@ struct TmapKey {
   const void* base;
   int64_t k, rows, batch, ld, bstride;
   int box_k, box_rows;
+  int64_t elem_bytes;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -93,10 +94,15 @@ static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 
 int get_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t k, int64_t rows, int64_t batch,
                      int64_t ld, int64_t batch_stride, int box_k, int box_rows) {
+  return get_tmap_3d(out, base, k, rows, batch, ld, batch_stride, box_k, box_rows, 2);
+}
+
+int get_tmap_3d(CUtensorMap* out, const void* base, int64_t k, int64_t rows, int64_t batch,
+                int64_t ld, int64_t batch_stride, int box_k, int box_rows, int elem_bytes) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base; key.k = k; key.rows = rows; key.batch = batch; key.ld = ld;
-  key.bstride = batch_stride; key.box_k = box_k; key.box_rows = box_rows;
+  key.bstride = batch_stride; key.box_k = box_k; key.box_rows = box_rows; key.elem_bytes = elem_bytes;
   {
     std::lock_guard<std::mutex> lock(g_tmap_mu);
     auto it = g_tmaps.find(key);
@@ -105,10 +111,11 @@ int get_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t k, int64_t rows
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(MTS_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)batch_stride * elem_bytes};
   cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

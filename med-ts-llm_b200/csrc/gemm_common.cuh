@@ -30,6 +30,8 @@ struct GemmParams {
   // training path keeps for the backward
   __nv_bfloat16* aux;
   int64_t ld_aux;
+  int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
+  int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
 };
 
 __device__ __forceinline__ float gelu_new_f(float x) {
@@ -114,6 +116,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
               const float* v = half ? vb : va;
               const int col0 = half ? col_b : col_a;
               __syncwarp();
+              if (p.d_is_f32) {
+                // fp32 output (TF32 parity mode): values rounded to TF32, 8 lanes x float4 per row, 4 rows per pass
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
+                      make_float4(round_tf32(v[j]), round_tf32(v[j + 1]), round_tf32(v[j + 2]), round_tf32(v[j + 3]));
+                __syncwarp();
+                float* fbase = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride;
+                const int rr4 = lane >> 3, cc4 = (lane & 7) * 4;
+#pragma unroll
+                for (int ps = 0; ps < 8; ++ps) {
+                  const int r_g = row0 + ps * 4 + rr4;
+                  if (col0 + cc4 < p.n && r_g < p.m)
+                    *reinterpret_cast<float4*>(fbase + (int64_t)r_g * p.ldd + col0 + cc4) =
+                        *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr4) * kEpiPitch + cc4);
+                }
+                continue;
+              }
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -201,6 +221,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           }
         }
         if (col0 >= n_store) continue;  // warp-uniform
+        if constexpr (EPI != MTS_EPI_RESID_ADD) {
+          if (p.round_tf32) {   // fp32 result that is the operand of a kind::tf32 GEMM: round to nearest, not truncate
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+        }
 
         if (EPI == MTS_EPI_STORE && p.d_transposed) {
           // element (row, col) -> d[col*ldd + row]: lanes (= rows) are contiguous in memory

@@ -33,12 +33,22 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kEpiStageBytes + 1024;
 };
 
-template <int BN, int EPI>
+// TF32 = true: A and B are fp32 in global / shared memory and the tensor cores read them as TF32 (kind::tf32, K = 8 per
+// instruction).  A 128-byte swizzled smem row then holds 32 elements instead of 64, so a stage covers half the K extent
+// with the same bytes, the same descriptors and the same 4 MMAs; everything else is shared with the bf16 kernel.
+template <int BN, int EPI, bool TF32 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p,
+                    const __grid_constant__ CUtensorMap tmap_a_lo,
+                    const __grid_constant__ CUtensorMap tmap_b_lo) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kBK = TF32 ? kBlockK / 2 : kBlockK;   // elements per 128-byte smem row
+  // p.split3 (TF32 only): fp32-grade contraction from TF32 pieces, A = A_hi + A_lo, B = B_hi + B_lo (each piece
+  // TF32-representable, mts_split_tf32): the k loop runs three times — A_hi B_hi, A_lo B_hi, A_hi B_lo — into the same
+  // accumulator (the A_lo B_lo term is below fp32 resolution).  Only the producer's choice of tensor map changes.
+  const int k_segments = (TF32 && p.split3) ? 3 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -60,7 +70,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int m_blocks = (p.m + kBlockM - 1) / kBlockM;
   const int n_blocks = (p.n + BN - 1) / BN;
-  const int k_blocks = (p.k + kBlockK - 1) / kBlockK;
+  const int k_blocks = (p.k + kBK - 1) / kBK;
   const int tiles_per_batch = m_blocks * n_blocks;
   const int num_tiles = tiles_per_batch * p.batch;
 
@@ -78,6 +88,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (k_segments > 1) {
+      tma_prefetch_desc(&tmap_a_lo);
+      tma_prefetch_desc(&tmap_b_lo);
+    }
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
@@ -99,21 +113,25 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int t = tile - b * tiles_per_batch;
         int m_blk, n_blk;
         tile_coords(t, m_blocks, n_blocks, m_blk, n_blk);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, full_bar(stage), kb * kBlockK,
-                      m_blk * kBlockM, p.a_batched ? b : 0, kEvictNormal);
-          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_b, full_bar(stage), kb * kBlockK,
-                      n_blk * BN, p.b_batched ? b : 0, kEvictNormal);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        for (int seg = 0; seg < k_segments; ++seg) {
+          const CUtensorMap* ma = (seg == 1) ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* mb = (seg == 2) ? &tmap_b_lo : &tmap_b;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_3d(smem_a + stage * Cfg::kABytes, ma, full_bar(stage), kb * kBK,
+                        m_blk * kBlockM, p.a_batched ? b : 0, kEvictNormal);
+            tma_load_3d(smem_b + stage * Cfg::kBBytes, mb, full_bar(stage), kb * kBK,
+                        n_blk * BN, p.b_batched ? b : 0, kEvictNormal);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(kBlockM, BN) : umma_idesc_bf16(kBlockM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -123,15 +141,16 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks * k_segments; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_a + stage * Cfg::kABytes);
           const uint64_t bdesc = umma_desc_sw128(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in (addr >> 4)
-            umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            // advance 16 bf16 (8 tf32) = 32 bytes inside the 128-byte swizzled row: +2 in (addr >> 4)
+            if constexpr (TF32) umma_tf32(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else                umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -177,11 +196,15 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+// lo maps of the fp32-grade split (TF32 kernels with p.split3); the plain kernels get the main maps again (unused)
+static thread_local const CUtensorMap* g_ta_lo = nullptr;
+static thread_local const CUtensorMap* g_tb_lo = nullptr;
+
+template <int BN, int EPI, bool TF32 = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_nt_kernel<BN, EPI>;
+  auto kern = gemm_bf16_nt_kernel<BN, EPI, TF32>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e =
@@ -190,19 +213,20 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_done = true;
   }
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p,
+                              (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
   if (le != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_kernel)", le);
   count_launch();
   return check_launch("gemm_bf16_nt_kernel");
 }
 
-template <int BN>
+template <int BN, bool TF32 = false>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int num_tiles, cudaStream_t stream) {
   switch (epi) {
-    case MTS_EPI_STORE: return launch_gemm<BN, MTS_EPI_STORE>(ta, tb, p, num_tiles, stream);
-    case MTS_EPI_RESID_ADD: return launch_gemm<BN, MTS_EPI_RESID_ADD>(ta, tb, p, num_tiles, stream);
-    case MTS_EPI_GELU_NEW: return launch_gemm<BN, MTS_EPI_GELU_NEW>(ta, tb, p, num_tiles, stream);
+    case MTS_EPI_STORE: return launch_gemm<BN, MTS_EPI_STORE, TF32>(ta, tb, p, num_tiles, stream);
+    case MTS_EPI_RESID_ADD: return launch_gemm<BN, MTS_EPI_RESID_ADD, TF32>(ta, tb, p, num_tiles, stream);
+    case MTS_EPI_GELU_NEW: return launch_gemm<BN, MTS_EPI_GELU_NEW, TF32>(ta, tb, p, num_tiles, stream);
     default: return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: unknown epilogue");
   }
 }
@@ -251,6 +275,8 @@ bool pdl_enabled() {
 
 using namespace mts;
 
+static_assert(sizeof(mts_gemm_args) == 200, "mts_gemm_args layout is part of the C ABI (ctypes mirror: _lib.GemmArgs)");
+
 extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
@@ -264,12 +290,16 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   if (a->m <= 0 || a->n <= 0 || a->k <= 0 || a->batch <= 0)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: m, n, k, batch must be positive");
   if (!a->a || !a->b || !a->d) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: null operand");
-  if ((a->lda % 8) || (a->ldb % 8) || a->lda < a->k || a->ldb < a->k)
-    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: lda/ldb must be >= k and multiples of 8");
+  if (a->ab_dtype != MTS_BF16 && a->ab_dtype != MTS_F32)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: bad ab_dtype");
+  const bool tf32 = a->ab_dtype == MTS_F32;
+  const int ab_vec = tf32 ? 4 : 8;          // elements per 16 bytes of an operand row
+  if ((a->lda % ab_vec) || (a->ldb % ab_vec) || a->lda < a->k || a->ldb < a->k)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: lda/ldb must be >= k and multiples of 16 bytes");
   if ((reinterpret_cast<uintptr_t>(a->a) & 15) || (reinterpret_cast<uintptr_t>(a->b) & 15))
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: a and b must be 16-byte aligned");
-  if ((a->a_batch_stride % 8) || (a->b_batch_stride % 8))
-    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: batch strides must be multiples of 8");
+  if ((a->a_batch_stride % ab_vec) || (a->b_batch_stride % ab_vec))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: batch strides must be multiples of 16 bytes");
   if (a->bias_axis != MTS_BIAS_NONE && !a->bias)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: bias_axis set but bias is null");
   const bool f32 = a->d_dtype == MTS_F32;
@@ -287,25 +317,26 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
                          "mts_gemm: RESID_ADD needs a non-transposed D (fp32 with optional C, or bf16 in place)");
       break;
     case MTS_EPI_GELU_NEW:
-      if (f32 || a->d_transposed)
-        return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: GELU_NEW needs bf16 non-transposed D");
+      if ((f32 && !tf32) || a->d_transposed)
+        return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: GELU_NEW needs a non-transposed D (bf16; fp32 with fp32 operands)");
       break;
     case MTS_EPI_ROPE_QK:
-      if (f32 || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || !a->rope_cos || !a->rope_sin ||
+      if ((f32 != tf32) || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || !a->rope_cos || !a->rope_sin ||
           (a->rope_hd != 64 && a->rope_hd != 128) || a->rope_L <= 0 || a->rope_prefix < 0 || (a->rope_cols % a->rope_hd) ||
-          (a->n % a->rope_hd) || (bn != 0 && bn != 256) || (n_store % 8) || (a->ldd % 8) ||
+          (a->n % a->rope_hd) || (bn != 0 && bn != 256) || (n_store % 8) || (a->ldd % 8) || (a->d_batch_stride % 8) ||
+          (reinterpret_cast<uintptr_t>(a->d) & 15) ||
           (reinterpret_cast<uintptr_t>(a->rope_cos) & 15) || (reinterpret_cast<uintptr_t>(a->rope_sin) & 15))
         return set_error(MTS_ERR_INVALID_ARG,
-                         "mts_gemm: ROPE_QK needs bf16 D, no bias, 16-byte aligned tables, head dim 64/128 dividing n "
-                         "and rope_cols, block_n 256");
+                         "mts_gemm: ROPE_QK needs D of the operand precision (bf16 / fp32), no bias, 16-byte aligned tables "
+                         "and rows, head dim 64/128 dividing n and rope_cols, block_n 256");
       bn = 256;
       break;
     case MTS_EPI_SWIGLU:
-      if (f32 || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || (a->n % 256) ||
+      if ((f32 != tf32) || a->d_transposed || a->bias_axis != MTS_BIAS_NONE || (a->n % 256) ||
           (bn != 0 && bn != 256))
         return set_error(MTS_ERR_INVALID_ARG,
-                         "mts_gemm: SWIGLU needs bf16 D, no bias, n % 256 == 0 (packed gate/up), "
-                         "block_n 256");
+                         "mts_gemm: SWIGLU needs D of the operand precision (bf16 / fp32), no bias, n % 256 == 0 "
+                         "(packed gate/up), block_n 256");
       bn = 256;
       break;
     default:
@@ -328,12 +359,12 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   const int a_batched = (a->batch > 1 && a->a_batch_stride != 0) ? 1 : 0;
   const int b_batched = (a->batch > 1 && a->b_batch_stride != 0) ? 1 : 0;
   CUtensorMap ta, tb;
-  int rc = get_tmap_bf16_3d(&ta, a->a, a->k, a->m, a_batched ? a->batch : 1, a->lda,
-                            a_batched ? a->a_batch_stride : (int64_t)a->m * a->lda, kBlockK,
-                            kBlockM);
+  const int elem = tf32 ? 4 : 2, box_k = tf32 ? kBlockK / 2 : kBlockK;
+  int rc = get_tmap_3d(&ta, a->a, a->k, a->m, a_batched ? a->batch : 1, a->lda,
+                       a_batched ? a->a_batch_stride : (int64_t)a->m * a->lda, box_k, kBlockM, elem);
   if (rc) return rc;
-  rc = get_tmap_bf16_3d(&tb, a->b, a->k, a->n, b_batched ? a->batch : 1, a->ldb,
-                        b_batched ? a->b_batch_stride : (int64_t)a->n * a->ldb, kBlockK, bn);
+  rc = get_tmap_3d(&tb, a->b, a->k, a->n, b_batched ? a->batch : 1, a->ldb,
+                   b_batched ? a->b_batch_stride : (int64_t)a->n * a->ldb, box_k, bn, elem);
   if (rc) return rc;
 
   GemmParams p;
@@ -352,7 +383,9 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.alpha = a->alpha;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
   p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols; p.rope_prefix = a->rope_prefix;
+  p.round_tf32 = (a->round_tf32 && f32) ? 1 : 0;
   p.aux = nullptr; p.ld_aux = 0;
+  if (a->aux && tf32) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: aux is a training (bf16) feature");
   if (a->aux) {
     if (a->epilogue != MTS_EPI_SWIGLU || a->batch != 1 || a->ld_aux < a->n || (a->ld_aux % 8) ||
         (reinterpret_cast<uintptr_t>(a->aux) & 15))
@@ -360,6 +393,33 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
     p.aux = static_cast<__nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
   }
 
+  p.split3 = 0;
+  CUtensorMap ta_lo, tb_lo;
+  g_ta_lo = g_tb_lo = nullptr;
+  if (a->a_lo || a->b_lo) {
+    if (!tf32 || !a->a_lo || !a->b_lo || (reinterpret_cast<uintptr_t>(a->a_lo) & 15) || (reinterpret_cast<uintptr_t>(a->b_lo) & 15))
+      return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: a_lo / b_lo need fp32 operands, both given, 16-byte aligned");
+    rc = get_tmap_3d(&ta_lo, a->a_lo, a->k, a->m, a_batched ? a->batch : 1, a->lda,
+                     a_batched ? a->a_batch_stride : (int64_t)a->m * a->lda, box_k, kBlockM, elem);
+    if (rc) return rc;
+    rc = get_tmap_3d(&tb_lo, a->b_lo, a->k, a->n, b_batched ? a->batch : 1, a->ldb,
+                     b_batched ? a->b_batch_stride : (int64_t)a->n * a->ldb, box_k, bn, elem);
+    if (rc) return rc;
+    g_ta_lo = &ta_lo; g_tb_lo = &tb_lo;
+    p.split3 = 1;
+  }
+  if (tf32) {
+    // evaluation parity mode (fp32 operands as TF32): single-CTA kernel only
+    const long tl = (long)((a->m + kBlockM - 1) / kBlockM) * ((a->n + bn - 1) / bn) * a->batch;
+    if (tl > 0x7fffffffL) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: too many tiles");
+    if (a->epilogue == MTS_EPI_SWIGLU) return launch_gemm<256, MTS_EPI_SWIGLU, true>(ta, tb, p, (int)tl, stream);
+    if (a->epilogue == MTS_EPI_ROPE_QK) return launch_gemm<256, MTS_EPI_ROPE_QK, true>(ta, tb, p, (int)tl, stream);
+    switch (bn) {
+      case 256: return dispatch_epi<256, true>(a->epilogue, ta, tb, p, (int)tl, stream);
+      case 128: return dispatch_epi<128, true>(a->epilogue, ta, tb, p, (int)tl, stream);
+      default: return dispatch_epi<64, true>(a->epilogue, ta, tb, p, (int)tl, stream);
+    }
+  }
   if (bn == 256 && !a->d_transposed && gemm_2cta_enabled()) {
     // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them
     // unless the 256-row granularity wastes more than it saves (odd / single 128-row block counts).

@@ -22,6 +22,9 @@ int num_sms();
 //   128-byte swizzle, zero fill out of bounds.
 int get_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t k, int64_t rows, int64_t batch,
                      int64_t ld, int64_t batch_stride, int box_k, int box_rows);
+// Same for elements of `elem_bytes` (2 = bf16, 4 = fp32 read by the tensor cores as TF32).
+int get_tmap_3d(CUtensorMap* out, const void* base, int64_t k, int64_t rows, int64_t batch,
+                int64_t ld, int64_t batch_stride, int box_k, int box_rows, int elem_bytes);
 
 // Launches `kernel` with programmatic stream serialization (see pdl_wait() in ptx.cuh).  ONLY for kernels whose every
 // thread executes pdl_wait() before touching global memory another kernel may have written.  mts_set_option("pdl", 0)

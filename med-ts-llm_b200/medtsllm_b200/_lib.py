@@ -32,6 +32,8 @@ class GemmArgs(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_L", C.c_int32), ("rope_hd", C.c_int32), ("rope_cols", C.c_int32), ("rope_prefix", C.c_int32),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
+        ("ab_dtype", C.c_int32), ("round_tf32", C.c_int32),
+        ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
     ]
 
 
@@ -83,6 +85,10 @@ SIGNATURES = {
     "mts_gpt4ts_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
     "mts_gpt4ts_conv_wgrad": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _p],
     "mts_norm_wgrad_partial": [_p, _i64, _p, _p, _i, _i, _f, _i, _p],
+    "mts_round_tf32": [_p, _p, _i64, _p],
+    "mts_split_tf32": [_p, _p, _p, _i64, _p],
+    "mts_softmax_rows_f32": [_p, _p, _i64, _i, _f, _p],
+    "mts_attn_causal_f32": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],
 }

@@ -75,9 +75,11 @@ class KernelBackbone:
 
     def __init__(self, spec: BackboneSpec, device, precision: str = "bf16"):
         """`precision`: which operand copies of the frozen weights to keep — "bf16" (default path: bf16 operands, fp32
-        accumulation), "tf32" (evaluation parity mode: fp32 weights rounded to TF32, tcgen05 kind::tf32) or "both"."""
-        if precision not in ("bf16", "tf32", "both"):
-            raise MtsError(f"precision {precision!r}: expected 'bf16', 'tf32' or 'both'")
+        accumulation), "tf32" (evaluation parity mode, the reference's own evaluation regime: fp32 weights rounded to TF32,
+        tcgen05 kind::tf32; the bf16 copies are kept too, training stays on them) or "fp32" (same, plus the low
+        TF32 pieces for the 3xTF32 fp32-grade contraction)."""
+        if precision not in ("bf16", "tf32", "fp32"):
+            raise MtsError(f"precision {precision!r}: expected 'bf16', 'tf32' or 'fp32'")
         self.precision = precision
         self.spec = spec
         self.device = torch.device(device)
@@ -102,6 +104,37 @@ class KernelBackbone:
     def _f32(self, w):
         return w.detach().to(self.device, torch.float32).contiguous()
 
+    # ---- evaluation parity modes: fp32 operands of the kind::tf32 GEMM
+    def operand(self, x: torch.Tensor, inplace: bool = False):
+        """fp32 tensor -> GEMM operand pair (hi, lo): "tf32" = (nearest TF32, None); "fp32" = the 3xTF32 split."""
+        if self.precision == "fp32":
+            return ops.split_tf32(x)
+        return (ops.round_tf32(x, out=x if inplace else None), None)
+
+    def _w32(self, w: torch.Tensor):
+        """Frozen fp32 weight [n, k] (any device) -> operand pair on the target device."""
+        t = w.detach().to(self.device, torch.float32).contiguous()
+        if t.data_ptr() == w.data_ptr():
+            t = t.clone()                  # never round the caller's tensor in place
+        return self.operand(t, inplace=True)
+
+    @property
+    def precise(self) -> bool:
+        return self.precision != "bf16"
+
+    def gemm32(self, a_op, w_op, d, **kw):
+        """mts_gemm on fp32 operand pairs (kind::tf32; 3xTF32 when the pairs carry low pieces)."""
+        return ops.gemm(a_op[0], w_op[0], d, a_lo=a_op[1], b_lo=w_op[1], **kw)
+
+    def embed_t_f32(self):
+        """fp32 [D, ceil4(V)] operand pair of the mapping GEMM (built on first use: 0.5 GB for Llama-2-7B)."""
+        if getattr(self, "_embed_t_f32", None) is None:
+            V, D = self.embed.shape
+            t = torch.zeros(D, (V + 3) // 4 * 4, device=self.device, dtype=torch.float32)
+            t[:, :V] = self.embed.t()
+            self._embed_t_f32 = self.operand(t, inplace=True)
+        return self._embed_t_f32
+
     def _finish_embeddings(self, emb: torch.Tensor):
         self.embed = self._f32(emb)
         V, D = self.embed.shape
@@ -122,6 +155,17 @@ class KernelBackbone:
         lay["wdown"] = wd_b
         lay["ln1"] = self._f32(ln1)
         lay["ln2"] = self._f32(ln2)
+        if self.precise:
+            D, I, Ip = s.hidden, s.inter, self.i_pad
+            lay["wqkv_f32"] = self._w32(torch.cat([wq, wk, wv], dim=0))
+            lay["wo_f32"] = self._w32(wo)
+            gu = torch.zeros(2, Ip, D, device=self.device, dtype=torch.float32)
+            gu[0, :I], gu[1, :I] = wg.to(self.device, torch.float32), wu.to(self.device, torch.float32)
+            # same packing as mts_pack_gate_up: blocks of 128 gate rows followed by the matching 128 up rows
+            lay["wgu_f32"] = self._w32(gu.view(2, Ip // 128, 128, D).permute(1, 0, 2, 3).reshape(2 * Ip, D))
+            wd32 = torch.zeros(D, Ip, device=self.device, dtype=torch.float32)
+            wd32[:, :I] = wd.to(self.device, torch.float32)
+            lay["wdown_f32"] = self._w32(wd32)
         self.layers.append(lay)
 
     def _add_gpt2_layer(self, c_attn_w, c_attn_b, c_proj_w, c_proj_b, fc_w, fc_b, proj_w, proj_b,
@@ -137,14 +181,17 @@ class KernelBackbone:
         lay["bproj"] = self._f32(proj_b)
         lay["ln1"], lay["ln1b"] = self._f32(ln1w), self._f32(ln1b)
         lay["ln2"], lay["ln2b"] = self._f32(ln2w), self._f32(ln2b)
+        if self.precise:           # Conv1D weights are [in, out]: K-major operands are their transposes
+            for name, w in (("wqkv", c_attn_w), ("wo", c_proj_w), ("wfc", fc_w), ("wproj", proj_w)):
+                lay[name + "_f32"] = self._w32(w.to(self.device, torch.float32).t())
         self.layers.append(lay)
 
     @classmethod
-    def from_hf(cls, hf_model, device) -> "KernelBackbone":
+    def from_hf(cls, hf_model, device, precision: str = "bf16") -> "KernelBackbone":
         """Converts a HuggingFace LlamaModel / GPT2Model (as loaded by the reference's setup_llm,
         models/medtsllm.py:175-185) layer by layer."""
         spec = spec_from_hf_config(hf_model.config)
-        self = cls(spec, device)
+        self = cls(spec, device, precision=precision)
         sd = hf_model.state_dict()
         if spec.kind == "llama":
             for i in range(spec.layers):
@@ -174,7 +221,7 @@ class KernelBackbone:
     @classmethod
     def random_init(cls, spec: BackboneSpec, device, seed=0, std=0.02, precision="bf16"):
         """Seeded random-init stack generated directly on the device (no checkpoints exist offline;
-        HF `initializer_range` = 0.02, norms = 1, biases = 0).  `precision`: "bf16" | "tf32" | "both" (see __init__)."""
+        HF `initializer_range` = 0.02, norms = 1, biases = 0).  `precision`: "bf16" | "tf32" | "fp32" (see __init__)."""
         self = cls(spec, device, precision=precision)
         g = torch.Generator(device=self.device).manual_seed(seed)
         D, I = spec.hidden, spec.inter
@@ -207,9 +254,10 @@ class KernelBackbone:
         return self._rope
 
     def weight_bytes(self) -> int:
+        """Bytes of the bf16 operand copies + norm / bias vectors one forward streams (default path)."""
         n = 0
         for lay in self.layers:
-            n += sum(t.numel() * t.element_size() for t in lay.values())
+            n += sum(t.numel() * t.element_size() for k, t in lay.items() if isinstance(t, torch.Tensor) and not k.endswith("_t"))
         return n
 
     def ensure_transposed(self):
@@ -334,6 +382,67 @@ class KernelBackbone:
         else:
             ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
         return out, x
+
+    def forward_f32(self, x: torch.Tensor, Bp: int, L: int, Lc: int = 0, hidden: list | None = None, lora=None):
+        """Evaluation parity modes ("tf32" / "fp32", see __init__): the same blocks with fp32 activations end to end,
+        every contraction on tcgen05 kind::tf32 (3xTF32 in "fp32" mode), fp32 attention.  x: fp32 residual stream
+        [Lc + Bp*(L-Lc), D], updated in place; returns the final-norm output fp32 (same rows).  `hidden` (list): receives
+        a copy of the residual stream entering every layer plus the final one (tests).  Inference only."""
+        if not self.precise:
+            raise MtsError("this backbone was built without fp32 operands (precision='bf16')")
+        s = self.spec
+        D, H, hd = s.hidden, s.heads, s.head_dim
+        Ls = L - Lc
+        M = Lc + Bp * Ls
+        if x.shape != (M, D) or x.dtype != torch.float32 or not x.is_contiguous():
+            raise MtsError("backbone.forward_f32 expects a contiguous fp32 [rows, D] residual stream")
+        if s.kind == "gpt2" and L > s.max_pos:
+            raise IndexError(f"sequence length {L} exceeds GPT-2 position table {s.max_pos}")
+        rope = self.rope(L)
+        dev = x.device
+        f32 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)  # noqa: E731
+        h, qkv, att = f32(M, D), f32(M, 3 * D), f32(M, D)
+        llama = s.kind == "llama"
+        tf32 = self.precision == "tf32"
+        for li, lay in enumerate(self.layers):
+            if hidden is not None:
+                hidden.append(x.clone())
+            wqkv = lay["wqkv_f32"] if lora is None else lora.folded_qkv(li, lay["wqkv_f32"], self)
+            if llama:
+                ops.rmsnorm(x, lay["ln1"], s.eps, out=h)
+                self.gemm32(self.operand(h, inplace=True), wqkv, qkv, m=M, n=3 * D, k=D, epilogue=EPI_ROPE_QK,
+                            rope=rope, rope_L=Ls, rope_hd=hd, rope_cols=2 * D, rope_prefix=Lc)
+            else:
+                ops.layernorm(x, lay["ln1"], lay["ln1b"], s.eps, out=h)
+                self.gemm32(self.operand(h, inplace=True), wqkv, qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"],
+                            bias_axis=BIAS_N)
+            ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, out=att)
+            self.gemm32(self.operand(att, inplace=True), lay["wo_f32"], x, m=M, n=D, k=D, epilogue=EPI_RESID_ADD,
+                        bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
+            if llama:
+                ops.rmsnorm(x, lay["ln2"], s.eps, out=h)
+                act = f32(M, self.i_pad)
+                self.gemm32(self.operand(h, inplace=True), lay["wgu_f32"], act, m=M, n=2 * self.i_pad, k=D,
+                            epilogue=EPI_SWIGLU, block_n=256, round_tf32=tf32)
+                a_op = (act, None) if tf32 else self.operand(act)
+                self.gemm32(a_op, lay["wdown_f32"], x, m=M, n=D, k=self.i_pad, epilogue=EPI_RESID_ADD)
+            else:
+                ops.layernorm(x, lay["ln2"], lay["ln2b"], s.eps, out=h)
+                act = f32(M, s.inter)
+                self.gemm32(self.operand(h, inplace=True), lay["wfc_f32"], act, m=M, n=s.inter, k=D, bias=lay["bfc"],
+                            bias_axis=BIAS_N, epilogue=EPI_GELU_NEW, round_tf32=tf32)
+                a_op = (act, None) if tf32 else self.operand(act)
+                self.gemm32(a_op, lay["wproj_f32"], x, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
+                            epilogue=EPI_RESID_ADD)
+            del act, a_op
+        if hidden is not None:
+            hidden.append(x.clone())
+        out = f32(M, D)
+        if llama:
+            ops.rmsnorm(x, self.final_norm_w, s.eps, out=out)
+        else:
+            ops.layernorm(x, self.final_norm_w, self.final_norm_b, s.eps, out=out)
+        return out
 
     def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None,
                  Lc: int = 0, norm_grads: dict | None = None):

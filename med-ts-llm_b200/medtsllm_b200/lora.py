@@ -53,6 +53,8 @@ class LoraAdapters(nn.Module):
                 self.A.append(nn.Parameter(a))
                 self.B.append(nn.Parameter(b))
         self._cache = {}
+        self._fold_cache = {}           # evaluation parity modes: per-layer operand pair of W_qkv + scale * B A
+        self._opt_steps = 0             # bumped by the model's global optimizer-step hook (see model._install_optimizer_hook)
         self._cache_gen = 0             # bumped whenever a cached operand set is replaced (graph-replay key)
         self._force_recast = False      # graph capture of a training step: cast even if the cache would hit
 
@@ -68,7 +70,7 @@ class LoraAdapters(nn.Module):
         b[t] [out, rp], b_t[t] [rp, out]."""
         nt = len(self.targets)
         ps = [self.A[self.index(layer, t)] for t in range(nt)] + [self.B[self.index(layer, t)] for t in range(nt)]
-        key = tuple((p._version, p.data_ptr()) for p in ps)
+        key = tuple((p._version, p.data_ptr()) for p in ps) + (self._opt_steps,)
         hit = self._cache.get(layer)
         if hit is not None and hit[0] == key and not self._force_recast:
             return hit[1]
@@ -87,6 +89,34 @@ class LoraAdapters(nn.Module):
         self._cache[layer] = (key, d)
         self._cache_gen += 1
         return d
+
+    def folded_qkv(self, layer: int, wqkv_op, bb):
+        """Evaluation parity modes (fp32 activations): the operand pair of W_qkv + scale * B A.  In fp32 the low-rank
+        update can be folded into the frozen weight without losing it to rounding (unlike the bf16 path, which keeps the
+        LoRA branch separate); B A itself is a 3xTF32 mts_gemm accumulated onto a copy of W.  Cached until A / B change."""
+        nt = len(self.targets)
+        ps = [self.A[self.index(layer, t)] for t in range(nt)] + [self.B[self.index(layer, t)] for t in range(nt)]
+        key = tuple((p._version, p.data_ptr()) for p in ps) + (self._opt_steps, bb.precision)
+        hit = self._fold_cache.get(layer)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        W = wqkv_op[0].clone() if wqkv_op[1] is None else wqkv_op[0] + wqkv_op[1]        # fp32 [3D, D]
+        D = W.shape[1]
+        for t, (off, width) in enumerate(self.out_slices(D)):
+            A, B = ps[t].detach(), ps[nt + t].detach()                                     # [r, D], [width, r]
+            r4 = (self.rank + 3) // 4 * 4
+            Bp = torch.zeros(width, r4, device=W.device, dtype=torch.float32)
+            Bp[:, :self.rank] = B
+            At = torch.zeros(D, r4, device=W.device, dtype=torch.float32)
+            At[:, :self.rank] = A.t()
+            b_hi, b_lo = ops.split_tf32(Bp)
+            a_hi, a_lo = ops.split_tf32(At)
+            ops.gemm(b_hi, a_hi, W, m=width, n=D, k=self.rank, lda=r4, ldb=r4, ldd=D, d_off=off * D, a_lo=b_lo, b_lo=a_lo,
+                     alpha=self.scale, epilogue=EPI_RESID_ADD)
+        op = bb.operand(W, inplace=True)
+        self._fold_cache[layer] = (key, op)
+        self._cache_gen += 1
+        return op
 
     # ------------------------------------------------------------------------------------------
     def out_slices(self, D):

@@ -118,6 +118,8 @@ def _install_optimizer_hook():
     def _bump(optimizer, args, kwargs):
         for m in list(_LIVE_MODELS):
             m._opt_steps += 1
+            if getattr(m, "lora_enabled", False):
+                m.llm._opt_steps += 1
 
     register_optimizer_step_post_hook(_bump)
     _HOOK_INSTALLED = True
@@ -265,6 +267,15 @@ class MedTsLLM(nn.Module):
                 f"setup.dtype={dtype_name!r}: adapters are fp32 masters and kernels compute in bf16 with fp32 "
                 "accumulation; use 'mixed' (the shipped configs) or 'float32'")
 
+        # precision of evaluation-mode forwards (precise.py): "bf16" = the fast path (the reference's bf16-autocast
+        # numerics); "tf32" = the reference's own evaluation regime (fp32 weights, TF32 matmuls, tasks/base.py:19-22);
+        # "fp32" = fp32-grade contractions (3xTF32).  `setup.dtype = "float32"` asks the reference for fp32 weights
+        # without autocast, so it maps to "tf32"; "mixed" (the shipped configs) stays on the fast path.  MTS_PRECISION
+        # overrides; an injected backbone decides by how it was built.  Training always runs the bf16 path.
+        want = os.environ.get("MTS_PRECISION") or ("bf16" if dtype_name == "mixed" else "tf32")
+        if want not in ("bf16", "tf32", "fp32"):
+            raise ValueError(f"MTS_PRECISION={want!r}: expected bf16, tf32 or fp32")
+        self.precision = want if backbone is None else backbone.precision
         if backbone is not None:
             self._backbone = backbone
             object.__setattr__(self, "_hf_model", None)
@@ -317,7 +328,7 @@ class MedTsLLM(nn.Module):
         dev = self.mapping_layer.weight.device
         if dev.type == "cuda":
             if self._backbone is None:
-                self._backbone = KernelBackbone.from_hf(self._hf_model, dev)
+                self._backbone = KernelBackbone.from_hf(self._hf_model, dev, precision=self.precision)
                 object.__setattr__(self, "_hf_model", None)
             elif self._backbone.device != dev:
                 raise MtsError("the kernel backbone lives on another device")
@@ -455,7 +466,7 @@ class MedTsLLM(nn.Module):
         self._ids_cache = (key, table, None)     # (+ shared-prefix length once _shared_prefix_len has run)
         return table
 
-    def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int) -> int:
+    def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int, precise: bool = False) -> int:
         """Number of leading prompt positions (left padding included) that hold the same token in every
         sample of the batch.  The backbone is causal and the reference passes no padding mask
         (models/medtsllm.py:350), so the hidden states of those positions are the same for every sample
@@ -472,6 +483,8 @@ class MedTsLLM(nn.Module):
                 self._ids_cache = (c[0], c[1], c[2], Lc)
         if Lc < 16:
             return 0
+        if precise:           # the fp32 attention kernel tiles the keys: no length limit
+            return Lc
         # the sequence-resident attention kernels keep all L positions of one head in shared memory
         hd = self.backbone_spec.head_dim
         L64 = (L + 63) // 64 * 64
@@ -574,6 +587,7 @@ class MedTsLLM(nn.Module):
         self._train_graph = None
         if self.lora_enabled:
             self.llm._cache.clear()
+            self.llm._fold_cache.clear()
 
     def _source_kv(self):
         """Prototype path (models/medtsllm.py:281, :574-575): source = W_map E + b; K = W_k source + b_k;
@@ -624,13 +638,17 @@ class MedTsLLM(nn.Module):
         x_enc = self._check_input(inputs)
         ids = self.prompt_token_ids(inputs)
         params = list(self.parameters()) + (self.llm.params() if self.lora_enabled else [])
-        key = (tuple(x_enc.shape), x_enc.device.index, self.training, id(ids), self.share_prompt_prefix,
+        key = (tuple(x_enc.shape), x_enc.device.index, self.training, id(ids), self.share_prompt_prefix, self.precision,
                tuple((p._version, p.data_ptr()) for p in params), self._opt_steps, self._cache_gen,
                self._backbone.cache_gen, self.llm._cache_gen if self.lora_enabled else 0)
         return self._graph.run(key, x_enc, lambda xs: self._predict_eager({**inputs, "x_enc": xs}, ids), hold=ids)
 
     def _predict_eager(self, inputs, ids=None):
-        out = self._forward_impl(inputs, None, ids)
+        if self.precision != "bf16" and not self.training:
+            from .precise import forward_precise
+            out = forward_precise(self, inputs, ids)
+        else:
+            out = self._forward_impl(inputs, None, ids)
         if not self.training:
             if self.task == "semantic_segmentation":
                 if self.n_classes > 2:

@@ -36,14 +36,20 @@ def _ptr(t):
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
          block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0,
-         rope_prefix=0, aux=None):
-    """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements."""
-    _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b"); _chk(d, None, "d")
+         rope_prefix=0, aux=None, a_lo=None, b_lo=None, round_tf32=False):
+    """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements.
+    a / b bf16 (default path) or both fp32 (evaluation parity modes: tcgen05 kind::tf32; with `a_lo` / `b_lo` the
+    3xTF32 fp32-grade contraction on split operands)."""
+    ab = a.dtype
+    if ab not in (torch.bfloat16, torch.float32):
+        raise MtsError("a must be bf16 or fp32")
+    _chk(a, ab, "a"); _chk(b, ab, "b"); _chk(d, None, "d")
+    es = a.element_size()
     if d.dtype not in (torch.bfloat16, torch.float32):
         raise MtsError("d must be bf16 or fp32")
     args = GemmArgs()
-    args.a = a.data_ptr() + 2 * a_off
-    args.b = b.data_ptr() + 2 * b_off
+    args.a = a.data_ptr() + es * a_off
+    args.b = b.data_ptr() + es * b_off
     args.d = d.data_ptr() + d.element_size() * d_off
     args.bias = _ptr(bias)
     args.c = 0 if c is None else _chk(c, torch.float32, "c").data_ptr() + 4 * d_off
@@ -61,6 +67,16 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.d_transposed = 1 if d_transposed else 0
     args.block_n = block_n
     args.alpha = alpha
+    args.ab_dtype = MTS_F32 if ab == torch.float32 else MTS_BF16
+    args.round_tf32 = 1 if round_tf32 else 0
+    if (a_lo is None) != (b_lo is None):
+        raise MtsError("a_lo and b_lo go together (3xTF32 split)")
+    if a_lo is not None:
+        _chk(a_lo, torch.float32, "a_lo"); _chk(b_lo, torch.float32, "b_lo")
+        if a_lo.shape != a.shape or b_lo.shape != b.shape or a_lo.stride() != a.stride() or b_lo.stride() != b.stride():
+            raise MtsError("a_lo / b_lo must be laid out like a / b")
+        args.a_lo = a_lo.data_ptr() + 4 * a_off
+        args.b_lo = b_lo.data_ptr() + 4 * b_off
     if rope is not None:
         args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
         args.rope_L, args.rope_hd, args.rope_cols, args.rope_prefix = rope_L, rope_hd, rope_cols, rope_prefix
@@ -591,5 +607,55 @@ def dropout(x, p, seed, out=None):
     if out is None:
         out = torch.empty_like(x)
     _lib.call("mts_dropout", x.data_ptr(), out.data_ptr(), _dt(x), x.numel(), float(p), int(seed) & (2 ** 64 - 1),
+              _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation parity modes (fp32 activations, kind::tf32 contractions)
+# ------------------------------------------------------------------------------------------------
+def round_tf32(x, out=None):
+    """Nearest TF32-representable fp32 values (in place when out is x)."""
+    _chk(x, torch.float32, "x")
+    if not x.is_contiguous():
+        raise MtsError("round_tf32 needs a contiguous tensor")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("mts_round_tf32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def split_tf32(x):
+    """(hi, lo) with x ~ hi + lo, both TF32-representable: operands of the 3xTF32 GEMM."""
+    _chk(x, torch.float32, "x")
+    if not x.is_contiguous():
+        raise MtsError("split_tf32 needs a contiguous tensor")
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _lib.call("mts_split_tf32", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    return hi, lo
+
+
+def softmax_rows_f32(s, scale, out=None):
+    _chk(s, torch.float32, "s")
+    if not s.is_contiguous():
+        raise MtsError("softmax_rows_f32 needs contiguous input")
+    n = s.shape[-1]
+    if out is None:
+        out = torch.empty_like(s)
+    _lib.call("mts_softmax_rows_f32", s.data_ptr(), out.data_ptr(), s.numel() // n, n, scale, _stream())
+    return out
+
+
+def attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, *, scale=None, out=None, round_out=False):
+    """fp32 causal attention: qkv fp32 [Lc + Bp*Ls, 3*H*hd] (q / k rotated) -> out fp32 [Lc + Bp*Ls, H*hd]."""
+    _chk(qkv, torch.float32, "qkv")
+    M = Lc + Bp * Ls
+    if not qkv.is_contiguous() or qkv.shape != (M, 3 * H * hd):
+        raise MtsError("attn_causal_f32 needs contiguous qkv [Lc + Bp*Ls, 3*H*hd]")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty(M, H * hd, device=qkv.device, dtype=torch.float32)
+    _lib.call("mts_attn_causal_f32", qkv.data_ptr(), out.data_ptr(), Bp, Lc, Ls, H, hd, scale, 1 if round_out else 0,
               _stream())
     return out

@@ -1,0 +1,189 @@
+"""Evaluation parity modes of `MedTsLLM` ("tf32" and "fp32").
+
+The reference evaluates with fp32 weights and TF32 matmuls whatever `setup.dtype` says (tasks/base.py:19-22 set
+`allow_tf32` / `set_float32_matmul_precision("medium")` process-wide; autocast is only entered in the train loops,
+tasks/forecasting.py:22).  The default kernel path computes in bf16 (the reference's *training* regime); these modes
+follow its *evaluation* regime instead:
+
+  * "tf32": every contraction is mts_gemm on fp32 operands rounded to nearest TF32, tcgen05 `kind::tf32`, fp32
+    accumulation in TMEM — what cuBLAS does for the reference;
+  * "fp32": the same kernels with the 3xTF32 split (A = A_hi + A_lo, B = B_hi + B_lo; a_hi b_hi + a_lo b_hi + a_hi b_lo),
+    i.e. fp32-grade contractions — the mode the 1e-3 parity bound of BASELINE.json is asserted in at full depth.
+
+Activations stay fp32 end to end; norms, softmax, RoPE, SwiGLU / GELU and attention are fp32 arithmetic.  Inference
+only: training keeps the bf16 path (= the reference's bf16 autocast).  Same row layouts (shared prompt prefix included),
+same covariate / down-sample modes, same kernels for everything that is not a contraction.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from ._lib import BIAS_M, BIAS_N, EPI_RESID_ADD, MtsError
+
+
+def _f32_weight(m, name: str, p: torch.Tensor):
+    """Operand pair of a trainable fp32 master [rows, cols] (row pitch padded to 4 elements: TMA rows are 16-byte
+    multiples), refreshed when the parameter changes."""
+    bb = m._backbone
+    key = (p._version, p.data_ptr(), m._opt_steps, bb.precision)
+    hit = m._w_cache.get("f32:" + name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    rows, cols = p.shape
+    ld = (cols + 3) // 4 * 4
+    w = torch.zeros(rows, ld, device=p.device, dtype=torch.float32)
+    w[:, :cols] = p.detach()
+    op = bb.operand(w, inplace=True)
+    m._w_cache["f32:" + name] = (key, op)
+    m._cache_gen += 1
+    return op
+
+
+def _source_kv(m):
+    """Prototype path in fp32 (models/medtsllm.py:281, :574-575), cached like MedTsLLM._source_kv."""
+    rl = m.reprogramming_layer
+    bb = m._backbone
+    plist = [m.mapping_layer.weight, m.mapping_layer.bias, rl.key_projection.weight, rl.key_projection.bias,
+             rl.value_projection.weight, rl.value_projection.bias]
+    key = tuple((p._version, p.data_ptr()) for p in plist) + (m._opt_steps, bb.precision)
+    c = getattr(m, "_src_cache_f32", None)
+    if c is not None and c[0] == key:
+        return c[1:]
+    S, D, HE, V = m.num_tokens, m.d_llm, m.d_ff * m.n_attention_heads, m.vocab_size
+    dev = m.device
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)      # noqa: E731
+    w_map = _f32_weight(m, "map", m.mapping_layer.weight)                   # [S, ceil4(V)]
+    emb_t = bb.embed_t_f32()                                                # [D, ceil4(V)]
+    ldv = w_map[0].shape[1]
+    source = f32(S, D)
+    bb.gemm32(w_map, emb_t, source, m=S, n=D, k=V, lda=ldv, ldb=ldv, bias=m.mapping_layer.bias.detach(), bias_axis=BIAS_M)
+    src_op = bb.operand(source.clone(), inplace=True)
+    K = f32(S, HE)
+    bb.gemm32(src_op, _f32_weight(m, "wk", rl.key_projection.weight), K, m=S, n=HE, k=D,
+              bias=rl.key_projection.bias.detach(), bias_axis=BIAS_N)
+    Vt = f32(HE, S)
+    bb.gemm32(_f32_weight(m, "wv", rl.value_projection.weight), src_op, Vt, m=HE, n=S, k=D,
+              bias=rl.value_projection.bias.detach(), bias_axis=BIAS_M)
+    m._src_cache_f32 = (key, source, bb.operand(K, inplace=True), bb.operand(Vt, inplace=True))
+    m._cache_gen += 1
+    return m._src_cache_f32[1:]
+
+
+def _downsample_operands(m):
+    if m.embedding_downsample_mode == "linear":
+        return _f32_weight(m, "wds", m.embedding_downsample_layer.weight), m.embedding_downsample_layer.bias.detach()
+    c = getattr(m, "_ds_fixed_f32", None)
+    if c is None or c[0] != m._backbone.precision:
+        E, D = m.d_ff, m.d_llm
+        w = torch.zeros(E, D, dtype=torch.float32)
+        if m.embedding_downsample_mode == "truncate":
+            w[torch.arange(E), torch.arange(E)] = 1.0
+        else:
+            g = D // E
+            w.view(E, E, g)[torch.arange(E), torch.arange(E), :] = 1.0 / g
+        m._ds_fixed_f32 = (m._backbone.precision, m._backbone.operand(w.to(m.device), inplace=True))
+        m._cache_gen += 1
+    return m._ds_fixed_f32[1], None
+
+
+def forward_precise(m, inputs, ids=None):
+    """MedTsLLM._forward_impl (models/medtsllm.py:321-382) in the fp32-activation regime; inference only."""
+    bb = m._backbone
+    if not bb.precise:
+        raise MtsError(f"precision {m.precision!r} needs a backbone built with fp32 operands "
+                       "(set MTS_PRECISION / setup.dtype before the model is moved to the GPU)")
+    x_enc = m._check_input(inputs)
+    B, T, C = x_enc.shape
+    dev = x_enc.device
+    D, N, E, H = m.d_llm, m.n_patches, m.d_ff, m.n_attention_heads
+    HE = H * E
+    rl = m.reprogramming_layer
+    mode = m.covariate_mode
+    N0 = N // C if mode == "interleave" else N
+    Bp = B * C if mode in ("independent", "merge-end") else B
+    op, gemm = bb.operand, bb.gemm32
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)      # noqa: E731
+
+    if ids is None:
+        ids = m.prompt_token_ids(inputs)
+    Lp = ids.shape[1]
+    L = Lp + N
+    ids_dev = ids.to(dev, non_blocking=True) if Lp > 0 else None
+    Lc = m._shared_prefix_len(ids, Bp, L, precise=True)
+    Ls = L - Lc
+    X = f32(Lc + Bp * Ls, D)
+    ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L, Lc=Lc, B=B)
+
+    concat = mode == "concat"
+    _, enc, mean, std = ops.revin_patch_embed(
+        x_enc, m.patch_embedding.value_embedding.tokenConv.weight.detach(), m.patch_len, m.stride, concat=concat,
+        want_bf16=False, want_f32=True)
+    assert enc.shape[1] == N0
+
+    source, K_op, Vt_op = _source_kv(m)
+    S = m.num_tokens
+    rows = enc.shape[0] * N0
+    Q = f32(rows, HE)
+    gemm(op(enc.view(rows, -1).clone(), inplace=True), _f32_weight(m, "wq", rl.query_projection.weight), Q,
+         m=rows, n=HE, k=m.d_model, bias=rl.query_projection.bias.detach(), bias_axis=BIAS_N)
+    scores = f32(H, rows, S)
+    gemm(op(Q, inplace=True), K_op, scores, m=rows, n=S, k=E, batch=H, lda=HE, ldb=HE, a_bs=E, b_bs=E, d_bs=rows * S)
+    scale = 1.0 / math.sqrt(E)
+    P = ops.softmax_rows_f32(scores, scale)
+    O = f32(rows, HE)
+    gemm(op(P, inplace=True), Vt_op, O, m=rows, n=E, k=S, batch=H, a_bs=rows * S, ldb=S, b_bs=E * S, ldd=HE, d_bs=E)
+    O_op = op(O, inplace=True)
+    wo = _f32_weight(m, "wo", rl.out_projection.weight)
+    bo = rl.out_projection.bias.detach()
+    if mode in ("concat", "univariate", "independent", "merge-end"):
+        gemm(O_op, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=Ls * D, ldd=D, d_off=Lp * D,
+             bias=bo, bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+    elif mode == "interleave":
+        for c in range(C):
+            gemm(O_op, wo, X, m=N0, n=D, k=HE, batch=B, a_off=c * N0 * HE, a_bs=C * N0 * HE, b_bs=0,
+                 d_bs=Ls * D, ldd=C * D, d_off=(Lp + c) * D, bias=bo, bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+    else:
+        Y = f32(rows, D)
+        gemm(O_op, wo, Y, m=rows, n=D, k=HE, bias=bo, bias_axis=BIAS_N)
+        fw = m.feature_weighting if mode == "weighted-average" else None
+        ops.group_reduce(Y, B, C, N0 * D, w=fw.weight.detach().view(-1) if fw is not None else None,
+                         bias=fw.bias.detach() if fw is not None else None, out=X, out_bs=Ls * D, out_off=Lp * D,
+                         accumulate=True)
+
+    cap = m._capture
+    if cap is not None:
+        cap.update(revin_mean=mean.clone(), revin_stdev=std.clone(), patch_embedding=enc.clone(),
+                   source_embeddings=source.clone(), llm_input=m._expand_rows(X, Bp, L, Lc))
+    hid = bb.forward_f32(X, Bp, L, Lc=Lc, lora=m.llm if m.lora_enabled else None)
+    if cap is not None:
+        cap["llm"] = m._expand_rows(hid, Bp, L, Lc)
+        cap["shared_prefix"] = Lc
+
+    wds, bds = _downsample_operands(m)
+    flat = f32(Bp, E * N)
+    gemm(op(hid, inplace=True), wds, flat, m=N, n=E, k=D, batch=Bp, a_off=Lp * D, a_bs=Ls * D, b_bs=0, d_bs=E * N,
+         d_transposed=True, ldd=N, bias=bds, bias_axis=BIAS_N if bds is not None else 0)
+    if (E * N) % 4:
+        raise MtsError("d_ff * n_patches must be a multiple of 4")
+    head = f32(Bp, m.n_outputs)
+    gemm(op(flat, inplace=True), _f32_weight(m, "wh", m.output_projection.linear.weight), head, m=Bp, n=m.n_outputs,
+         k=E * N, bias=m.output_projection.linear.bias.detach(), bias_axis=BIAS_N)
+    if cap is not None:
+        cap["output_projection"] = head.clone()
+    nops = m.n_outputs_per_step
+    if mode == "independent":
+        out = ops.group_reduce(head, B, C, m.n_outputs)
+    elif mode == "merge-end":
+        out = ops.merge_end(head, m.feature_weighting.weight.detach(), m.feature_weighting.bias.detach(),
+                            B, C, m.pred_len, nops)
+    else:
+        out = head
+    out = out.view(B, m.pred_len, nops)
+    if m.task in ("forecasting", "reconstruction", "anomaly_detection", "pretraining"):
+        ops.revin_denorm(out, mean, std)
+    else:
+        out = out.squeeze(-1)
+    return out

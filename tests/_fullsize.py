@@ -43,7 +43,10 @@ class LazyBackboneState:
     def _w(self, lay, name):
         """The weight as the oracle's arithmetic sees it: what the kernels multiply by (bf16-rounded in bf16 mode,
         fp32/tf32-rounded in the parity mode)."""
-        return (lay[name + "_f32"] if self.precision == "tf32" else lay[name]).float().cpu()
+        if self.precision == "bf16":
+            return lay[name].float().cpu()
+        hi, lo = lay[name + "_f32"]                     # operand pair of the kind::tf32 GEMM (lo: 3xTF32 split only)
+        return (hi if lo is None else hi + lo).cpu()
 
     def _load_layer(self, i):
         bb, s = self.bb, self.bb.spec

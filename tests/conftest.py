@@ -9,6 +9,12 @@ for p in (REPO, REPO / "med-ts-llm_b200"):
         sys.path.insert(0, str(p))
 
 
+# the fixtures' configs say setup.dtype = "float32", which maps to the "tf32" evaluation mode by default; the suite
+# exercises the default bf16 path unless a test asks for a parity mode explicitly (monkeypatch.setenv)
+import os  # noqa: E402
+os.environ.setdefault("MTS_PRECISION", "bf16")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

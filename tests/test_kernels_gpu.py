@@ -609,3 +609,136 @@ def test_prompt_gather_and_rope_shared_prefix(ops, cuda):
     ops.rope_qk_shared_(raw, Bp, Lc, Ls, H, hd, tabs)
     ops.rope_qk_(raw_p, Bp, L, H, hd, tabs)
     assert torch.equal(_expand_shared(raw, Bp, Lc, Ls), raw_p)
+
+
+# --------------------------------------------------------------------------------------------- evaluation parity modes
+def _tf32(x):
+    """Nearest TF32 (ties away from zero), the contract of mts_round_tf32 / cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def test_round_and_split_tf32(ops, cuda):
+    g = torch.Generator().manual_seed(20)
+    x = (torch.randn(1000 * 37 + 3, generator=g) * 3).to(cuda)
+    x[:4] = torch.tensor([0.0, -0.0, 1.0, -2.5], device=cuda)
+    r = ops.round_tf32(x)
+    assert torch.equal(r, _tf32(x))                                    # bit-exact
+    assert (r.view(torch.int32) & 0x1FFF).eq(0).all()
+    hi, lo = ops.split_tf32(x)
+    assert torch.equal(hi, r) and (lo.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert torch.equal(lo, _tf32(x - r))
+    assert ((hi.double() + lo.double() - x.double()).abs() <= x.double().abs() * 2.0 ** -21).all()
+    y = x.clone()
+    assert ops.round_tf32(y, out=y) is y and torch.equal(y, r)         # in place
+
+
+@pytest.mark.parametrize("m,n,k,bn", [(128, 256, 32, 256), (128, 64, 64, 64), (300, 264, 200, 0), (1, 8, 8, 64),
+                                       (77, 1024, 100, 0), (2176, 4096, 1024, 0), (640, 768, 4096, 128)])
+def test_gemm_tf32_and_3xtf32(ops, cuda, m, n, k, bn):
+    """fp32 operands on tcgen05 kind::tf32.  Operands pre-rounded to TF32 => the only error left is fp32 accumulation
+    order (rtol 1e-5); with the 3xTF32 split on full-precision operands the contraction is fp32-grade (vs an fp64
+    reference: rel-L2 < 2e-6, where plain TF32 on the same data gives ~3e-4)."""
+    g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    b = torch.randn(n, k, generator=g).to(cuda)
+    if k % 4:
+        pytest.skip("lda must be a multiple of 4")
+    ar, br = ops.round_tf32(a), ops.round_tf32(b)
+    d = torch.full((m, n), float("nan"), device=cuda)
+    ops.gemm(ar, br, d, m=m, n=n, k=k, block_n=bn)
+    ref = (ar.double() @ br.double().t())
+    assert _rel_l2(d.double(), ref) < 2e-6
+    torch.testing.assert_close(d.double(), ref, rtol=1e-4, atol=1e-4 * math.sqrt(k))
+    # 3xTF32 on the unrounded operands
+    a_hi, a_lo = ops.split_tf32(a)
+    b_hi, b_lo = ops.split_tf32(b)
+    d3 = torch.empty(m, n, device=cuda)
+    ops.gemm(a_hi, b_hi, d3, m=m, n=n, k=k, block_n=bn, a_lo=a_lo, b_lo=b_lo)
+    ref3 = a.double() @ b.double().t()
+    e3, e1 = _rel_l2(d3.double(), ref3), _rel_l2(d.double(), ref3)
+    assert e3 < 2e-6, (e3, e1)
+    if k >= 32:
+        assert e1 > 20 * e3                                            # what the split buys over plain TF32
+
+
+def test_gemm_tf32_epilogues(ops, cuda):
+    g = torch.Generator().manual_seed(31)
+    m, k = 200, 256
+    x = ops.round_tf32((torch.randn(m, k, generator=g) * 0.5).to(cuda))
+    # SwiGLU (packed gate / up rows), fp32 D rounded to TF32
+    I = 320
+    wg = ops.round_tf32((torch.randn(I, k, generator=g) * 0.1).to(cuda))
+    wu = ops.round_tf32((torch.randn(I, k, generator=g) * 0.1).to(cuda))
+    Ip = 384
+    gu = torch.zeros(2, Ip, k, device=cuda)
+    gu[0, :I], gu[1, :I] = wg, wu
+    packed = gu.view(2, Ip // 128, 128, k).permute(1, 0, 2, 3).reshape(2 * Ip, k).contiguous()
+    d = torch.full((m, Ip), float("nan"), device=cuda)
+    ops.gemm(x, packed, d, m=m, n=2 * Ip, k=k, epilogue=3, round_tf32=True)
+    ref = torch.nn.functional.silu(x.double() @ wg.double().t()) * (x.double() @ wu.double().t())
+    torch.testing.assert_close(d[:, :I].double(), ref, rtol=6e-4, atol=1e-5)      # TF32 output rounding: 2^-11
+    assert (d.view(torch.int32) & 0x1FFF).eq(0).all() and torch.all(d[:, I:] == 0)
+    # gelu_new + bias, fp32 D unrounded
+    n = 384
+    w = ops.round_tf32((torch.randn(n, k, generator=g) * 0.3).to(cuda))
+    bias = torch.randn(n, generator=g).to(cuda)
+    d = torch.empty(m, n, device=cuda)
+    ops.gemm(x, w, d, m=m, n=n, k=k, bias=bias, bias_axis=1, epilogue=2)
+    z = x.double() @ w.double().t() + bias.double()
+    ref = 0.5 * z * (1 + torch.tanh(math.sqrt(2 / math.pi) * (z + 0.044715 * z ** 3)))
+    torch.testing.assert_close(d.double(), ref, rtol=2e-3, atol=2e-3)             # tanh.approx in the epilogue
+    # residual add with bias, transposed store
+    r0 = torch.randn(m, n, generator=g).to(cuda)
+    r = r0.clone()
+    ops.gemm(x, w, r, m=m, n=n, k=k, bias=bias, bias_axis=1, epilogue=1)
+    torch.testing.assert_close(r.double(), r0.double() + z, rtol=1e-5, atol=1e-4)
+    dt = torch.empty(n, m, device=cuda)
+    ops.gemm(x, w, dt, m=m, n=n, k=k, d_transposed=True, ldd=m)
+    torch.testing.assert_close(dt.double(), (x.double() @ w.double().t()).t(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("hd,Lc", [(128, 0), (128, 40), (64, 0), (64, 17)])
+def test_gemm_tf32_rope_epilogue_and_attn_f32(ops, cuda, hd, Lc):
+    """Fused qkv projection + RoPE (fp32 out) and the fp32 causal attention, plain and shared-prefix row layouts,
+    against the oracle's fp64 arithmetic."""
+    from oracle import medtsllm_oracle as O
+    H, Bp, Ls = 2, 3, 45
+    D = H * hd
+    L = Lc + Ls
+    M = Lc + Bp * Ls
+    g = torch.Generator().manual_seed(hd + Lc)
+    # per-sample sequences [Bp, L, D]; with a shared prefix the first Lc positions are the same rows for every sample
+    xs = torch.randn(Bp, L, D, generator=g) * 0.5
+    if Lc:
+        xs[:, :Lc] = xs[0, :Lc]
+    w = torch.randn(3 * D, D, generator=g) * (1.0 / math.sqrt(D))
+    rows = torch.cat([xs[0, :Lc], xs[:, Lc:].reshape(Bp * Ls, D)], 0) if Lc else xs.reshape(Bp * L, D)
+    x_dev = ops.round_tf32(rows.contiguous().to(cuda))
+    w_dev = ops.round_tf32(w.to(cuda))
+    cos, sin = O.rope_tables(L, hd)
+    qkv = torch.empty(M, 3 * D, device=cuda)
+    ops.gemm(x_dev, w_dev, qkv, m=M, n=3 * D, k=D, epilogue=4, rope=(cos.to(cuda).contiguous(), sin.to(cuda).contiguous()),
+             rope_L=Ls, rope_hd=hd, rope_cols=2 * D, rope_prefix=Lc)
+    out = ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd)
+    # reference in fp64 on the per-sample view
+    expand = (lambda t: torch.cat([t[:Lc].unsqueeze(0).expand(Bp, Lc, -1), t[Lc:].view(Bp, Ls, -1)], 1)) if Lc else \
+        (lambda t: t.view(Bp, L, -1))
+    xe = expand(x_dev.cpu()).double()
+    q, k, v = (xe @ w_dev.cpu().double().t()).split(D, dim=-1)
+    q, k, v = (t.view(Bp, L, H, hd).transpose(1, 2) for t in (q, k, v))
+    q, k = O.apply_rope(q, cos.double(), sin.double()), O.apply_rope(k, cos.double(), sin.double())
+    ref = O.causal_attention(q, k, v, hd ** -0.5).transpose(1, 2).reshape(Bp, L, D)
+    got_qkv = expand(qkv.cpu())
+    ref_qkv = torch.cat([t.transpose(1, 2).reshape(Bp, L, D) for t in (q, k, v)], -1)
+    assert _rel_l2(got_qkv.double(), ref_qkv) < 4e-4                   # q / k / v stored rounded to TF32
+    assert _rel_l2(expand(out.cpu()).double(), ref) < 5e-4
+    if Lc:   # the shared rows are computed once and identical for every sample by construction
+        assert torch.isfinite(out).all()
+
+
+def test_softmax_rows_f32(ops, cuda):
+    g = torch.Generator().manual_seed(9)
+    s = (torch.randn(37, 1024, generator=g) * 4).to(cuda)
+    p = ops.softmax_rows_f32(s, 0.125)
+    torch.testing.assert_close(p.double(), torch.softmax(s.double() * 0.125, -1), rtol=1e-5, atol=1e-8)

@@ -26,9 +26,18 @@ def _rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+# per-precision tolerances: (intermediate stages, final output)
+_TOL = {"bf16": (1e-2, 3e-3), "tf32": (2e-3, 1e-3), "fp32": (1e-4, 1e-4)}
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
 @pytest.mark.parametrize("name", CASES)
-def test_forward_parity(name, tmp_path, cuda):
+def test_forward_parity(name, precision, tmp_path, cuda, monkeypatch):
+    """precision "bf16": the default path.  "tf32" / "fp32": the evaluation parity modes (precise.py) — here the
+    asserted output tolerance is north_star's 1e-3 (tf32: the reference's own evaluation regime) and 1e-4 (fp32)."""
     from medtsllm_b200.model import MedTsLLM
+    monkeypatch.setenv("MTS_PRECISION", precision)
+    tol_stage, tol_out = _TOL[precision]
     fix = load_case(name)
     llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
     model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
@@ -58,7 +67,8 @@ def test_forward_parity(name, tmp_path, cuda):
     if fix["config"]["models"]["medtsllm"]["covariate_mode"] == "concat":
         N = pe.shape[1]
         pe = pe.reshape(B, C, N, -1).permute(0, 2, 1, 3).reshape(B, N, -1)
-    assert _rel_l2(cap["patch_embedding"], pe) < 4e-3
+    assert _rel_l2(cap["patch_embedding"], pe) < (4e-3 if precision == "bf16" else 1e-5)
+    assert model.precision == precision
     # stages: vs oracle (run here) and vs the reference goldens
     if fix["kind"] == "gpt2":
         # the kernel path folds GPT-2's position embedding into the gather (HF adds wpe inside the model,
@@ -68,10 +78,10 @@ def test_forward_parity(name, tmp_path, cuda):
     for key in ("source_embeddings", "llm_input", "llm", "output_projection"):
         e_o = _rel_l2(cap[key].float().view(st[key].shape), st[key])
         e_g = _rel_l2(cap[key].float().view(g[key].shape), g[key])
-        assert e_o < 1e-2 and e_g < 1e-2, (name, key, e_o, e_g)
+        assert e_o < tol_stage and e_g < tol_stage, (name, key, e_o, e_g)
     e_out = _rel_l2(out, g["output"])
-    assert e_out < 3e-3, (name, e_out)
-    assert _rel_l2(out, ref_out) < 3e-3
+    assert e_out < tol_out, (name, e_out)
+    assert _rel_l2(out, ref_out) < tol_out
     # determinism: same inputs -> bit-identical output (no atomics on the forward path)
     with torch.no_grad():
         out2 = model(inputs)
@@ -81,7 +91,7 @@ def test_forward_parity(name, tmp_path, cuda):
     with torch.no_grad():
         out_t = model(inputs)
     assert _rel_l2(out_t, g["output_train"]) < 1e-2       # pre-activation (logits) in train mode
-    print(f"\n[parity] {name}: rel-L2 output {e_out:.2e}  " +
+    print(f"\n[parity] {name} [{precision}]: rel-L2 output {e_out:.2e}  " +
           "  ".join(f"{k} {_rel_l2(cap[k].float().view(g[k].shape), g[k]):.1e}" for k in
                     ("source_embeddings", "llm_input", "llm", "output_projection")))
 
