@@ -194,7 +194,8 @@ typedef struct mts_gemm_args {
    * tcgen05 kind::tf32 (operands should already be TF32-representable: mts_round_tf32, round_tf32 below — the tensor
    * core ignores the low 13 mantissa bits); MTS_BF16 (0) = the default bf16 path.
    * round_tf32 != 0 with an fp32 D (not RESID_ADD): store D rounded to nearest TF32, ready to be the next GEMM's operand.
-   * With fp32 operands the GELU_NEW / SWIGLU / ROPE_QK epilogues write fp32 D (ROPE_QK always TF32-rounded). */
+   * With fp32 operands the GELU_NEW / SWIGLU / ROPE_QK epilogues write fp32 D and evaluate expf / tanhf at library
+ * accuracy (the bf16 path uses the approximate units, whose error sits below the bf16 output rounding). */
   int32_t ab_dtype;
   int32_t round_tf32;
   /* fp32-grade contraction out of TF32 pieces ("3xTF32"): when a_lo and b_lo are given (fp32 operands only; same

@@ -30,6 +30,7 @@ struct GemmParams {
   // training path keeps for the backward
   __nv_bfloat16* aux;
   int64_t ld_aux;
+  int precise;     // fp32 operands (evaluation parity modes): accurate expf / tanhf in the activation epilogues
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
 };
@@ -42,6 +43,12 @@ __device__ __forceinline__ float gelu_new_f(float x) {
   return 0.5f * x * (1.0f + t);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// evaluation parity modes (fp32 operands): library-accurate transcendentals instead of the approximate units
+__device__ __forceinline__ float gelu_new_precise_f(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float silu_precise_f(float x) { return x / (1.0f + expf(-x)); }
 
 // Tile order inside one batch: groups of kGroupM row-blocks, m fastest inside a group.  The ~148
 // tiles in flight then form a roughly square patch (12 x 12 blocks) of the output, so a wave streams
@@ -117,11 +124,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
               const int col0 = half ? col_b : col_a;
               __syncwarp();
               if (p.d_is_f32) {
-                // fp32 output (TF32 parity mode): values rounded to TF32, 8 lanes x float4 per row, 4 rows per pass
+                // fp32 output (evaluation parity modes; q / k / v feed the fp32 attention unrounded unless asked):
+                // 8 lanes x float4 per row, 4 rows per pass
+                const bool rnd = p.round_tf32 != 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                   *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
-                      make_float4(round_tf32(v[j]), round_tf32(v[j + 1]), round_tf32(v[j + 2]), round_tf32(v[j + 3]));
+                      rnd ? make_float4(round_tf32(v[j]), round_tf32(v[j + 1]), round_tf32(v[j + 2]), round_tf32(v[j + 3]))
+                          : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
                 float* fbase = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride;
                 const int rr4 = lane >> 3, cc4 = (lane & 7) * 4;
@@ -193,7 +203,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
             // saved tensors reproduce exactly what the forward used
             float gv = __uint_as_float(g[j]) * p.alpha, uv = __uint_as_float(u[j]) * p.alpha;
             if (p.aux != nullptr) { gv = __bfloat162float(__float2bfloat16_rn(gv)); uv = __bfloat162float(__float2bfloat16_rn(uv)); }
-            v[j] = silu_f(gv) * uv;
+            v[j] = (p.precise ? silu_precise_f(gv) : silu_f(gv)) * uv;
           }
         } else {
           uint32_t r[32];
@@ -216,8 +226,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
             }
           }
           if constexpr (EPI == MTS_EPI_GELU_NEW) {
+            if (p.precise) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_new_precise_f(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+            }
           }
         }
         if (col0 >= n_store) continue;  // warp-uniform

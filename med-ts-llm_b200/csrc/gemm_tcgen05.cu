@@ -384,6 +384,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
   p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols; p.rope_prefix = a->rope_prefix;
   p.round_tf32 = (a->round_tf32 && f32) ? 1 : 0;
+  p.precise = tf32 ? 1 : 0;
   p.aux = nullptr; p.ld_aux = 0;
   if (a->aux && tf32) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: aux is a training (bf16) feature");
   if (a->aux) {

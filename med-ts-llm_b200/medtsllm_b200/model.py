@@ -616,7 +616,20 @@ class MedTsLLM(nn.Module):
         return source, K, Vt
 
     # ------------------------------------------------------------------------------------------ forward
+    accepts_host_mirror = True      # plugin.HostMirrorBatch (evaluation batches whose host copies stay addressable)
+
     def forward(self, inputs):
+        dev_batch = getattr(inputs, "device_batch", None)
+        if dev_batch is not None:
+            # plugin.HostMirrorBatch: compute on the device copies; in evaluation hand the predictions back on the host
+            # with ONE copy, so that the per-sample `.cpu()` of the reference's predict() loops are no-ops
+            if self.training:
+                return self.forward(dev_batch)
+            out = self.predict(dev_batch)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(out.device).synchronize()
+            return host
         # autograd path (adapter gradients) for training-mode forwards under enabled gradients — what the reference's
         # Trainers differentiate (tasks/forecasting.py:18-26).  Evaluation-mode forwards take the inference path, which
         # also applies the eval-only sigmoid / softmax (models/medtsllm.py:251-259) and returns a tensor without a graph.

@@ -8,16 +8,25 @@ unchanged:
     python -m medtsllm_b200.plugin /path/to/med-ts-llm/train.py configs/datasets/bidmc.toml
     torchrun --nproc-per-node 8 -m medtsllm_b200.plugin /path/to/med-ts-llm/train.py cfg.toml   # DP
 
-With WORLD_SIZE > 1 the launcher also (1) initialises NCCL, (2) swaps each trainer's
-`train_dataloader` for a DistributedSampler-backed one right after BaseTask.__init__ (the reference has
-`shuffle=True` and no sampler, tasks/base.py:175-182), and (3) keeps real logging on rank 0 only.
-Gradient all-reduce happens inside the model's backward (medtsllm_b200/dp.py).
+`patch_trainer()` (called by the launcher) wraps three `BaseTask` methods without touching tasks/*:
+  * `from_run_id` (tasks/base.py:283-306) also restores the LoRA pairs that `logger.save_state` wrote next to the
+    checkpoint (loggers/base_logger.py:42-43) — the reference saves them but never loads them back;
+  * `prepare_batch` (tasks/base.py:200-211), evaluation only: returns a `HostMirrorBatch` — the pinned host tensors the
+    DataLoader produced, with their device copies attached.  The model computes on the device copies and returns its
+    predictions on the host (ONE device->host copy per batch), so the per-sample `.cpu()` calls of the reference's
+    `predict()` scatter loops (tasks/forecasting.py:72-78, anomaly_detection.py:106-113, semantic_segmentation.py:98-104,
+    segmentation.py:92-97: up to 3 B device syncs per batch) all become no-ops.  Same values, same loop.
+    `MTS_HOST_MIRROR=0` turns it off.
+  * with WORLD_SIZE > 1, `__init__`: NCCL init, `train_dataloader` swapped for a DistributedSampler-backed one that
+    reshuffles every epoch (the reference has `shuffle=True` and no sampler, tasks/base.py:175-182), real logging on
+    rank 0 only.  Gradient all-reduce happens inside the model's backward (medtsllm_b200/dp.py).
 """
 from __future__ import annotations
 
 import os
 import runpy
 import sys
+from pathlib import Path
 
 
 def register(reference_root: str | None = None):
@@ -35,6 +44,72 @@ def register(reference_root: str | None = None):
         from .gpt4ts import GPT4TS
         models.model_lookup["gpt4ts"] = GPT4TS
     return models.model_lookup
+
+
+class HostMirrorBatch(dict):
+    """The batch as the DataLoader produced it (host tensors, pinned when `pin_memory=True`) with the device copies
+    `BaseTask.prepare_batch` made attached as `.device_batch`.  Indexing it yields HOST tensors."""
+
+    device_batch: dict
+
+
+def lora_checkpoint_path(basepath, run_id, ckpt="latest") -> Path:
+    """Where loggers/base_logger.py:29-43 writes the LoRA pairs of checkpoint `ckpt`."""
+    return Path(basepath) / run_id / "checkpoints" / f"{ckpt}-lora.safetensors"
+
+
+def patch_trainer(base_task_cls=None):
+    """Wraps `BaseTask.from_run_id` and `BaseTask.prepare_batch` (see the module docstring).  Idempotent."""
+    if base_task_cls is None:
+        import tasks.base as tb
+        base_task_cls = tb.BaseTask
+    cls = base_task_cls
+    if getattr(cls, "_mts_patched", False):
+        return cls
+    import torch
+
+    orig_from_run_id = cls.from_run_id.__func__
+    orig_prepare = cls.prepare_batch
+
+    def from_run_id(klass, run_id, cfg=None, ckpt="latest", basepath=None):
+        trainer = orig_from_run_id(klass, run_id, cfg, ckpt, basepath)
+        model = trainer.model
+        if getattr(model, "lora_enabled", False) and hasattr(model.llm, "load_pretrained"):
+            ckpt_name = ckpt or "latest"
+            if basepath is None:      # the default of tasks/base.py:286-287 and loggers/base_logger.py:14-17
+                import tasks.base as tb
+                base = Path(tb.__file__).parent / "../outputs/logs"
+            else:
+                base = Path(basepath)
+            path = lora_checkpoint_path(base, run_id, ckpt_name)
+            if path.exists():
+                model.llm.load_pretrained(path)
+            else:
+                import warnings
+                warnings.warn(f"lora.enabled but {path} does not exist: the LoRA pairs keep their initial values")
+        return trainer
+
+    def prepare_batch(self, batch):
+        dev_batch = orig_prepare(self, batch)
+        model = getattr(self, "model", None)
+        if (os.environ.get("MTS_HOST_MIRROR", "1") == "0" or model is None or model.training
+                or not getattr(model, "accepts_host_mirror", False) or not isinstance(batch, dict)
+                or not isinstance(dev_batch, dict) or getattr(self.device, "type", "cpu") != "cuda"):
+            return dev_batch
+        host = HostMirrorBatch()
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                # what the reference's loop would read back with .cpu(): same values, trainer dtype (tasks/base.py:206-208)
+                host[k] = v.to(self.dtype) if v.dtype.is_floating_point and v.dtype != self.dtype else v
+            else:
+                host[k] = dev_batch[k]
+        host.device_batch = dev_batch
+        return host
+
+    cls.from_run_id = classmethod(from_run_id)
+    cls.prepare_batch = prepare_batch
+    cls._mts_patched = True
+    return cls
 
 
 def _patch_trainer_for_dp():
@@ -70,6 +145,7 @@ def main(argv=None):
     root = os.path.dirname(script)
     sys.path.insert(0, root)
     register(root)
+    patch_trainer()
     _patch_trainer_for_dp()
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")

@@ -236,3 +236,48 @@ def run_reference_with_stages(model, inputs: dict, train_mode: bool = False):
     stages["revin_stdev"] = model.normalize_layers.stdev.detach().clone()
     stages["output"] = out.detach().clone()
     return out, stages
+
+
+# --------------------------------------------------------------------------------------------------
+# The reference's Trainer (tasks/*, datasets/*, loggers/*), imported unmodified
+# --------------------------------------------------------------------------------------------------
+_trainer_ns = None
+
+
+def import_trainer():
+    """Imports the reference's `tasks`, `datasets` and `loggers` packages as they are.  In-memory stubs stand in only
+    for third-party packages that are absent from this image and that the Trainer imports at module level without
+    using them on the paths exercised here: `pytorch_optimizer` (tasks/base.py:12, Ranger21 only), `bayes_opt`
+    (tasks/anomaly_detection.py:14), `plotly.graph_objects` (:16), `wfdb` (datasets/ludb.py)."""
+    global _trainer_ns
+    if _trainer_ns is not None:
+        return _trainer_ns
+    ref = import_reference()
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+
+    for name, attrs in (("pytorch_optimizer", {"Ranger21": _Dummy}), ("bayes_opt", {"BayesianOptimization": _Dummy}),
+                        ("plotly", {}), ("plotly.graph_objects", {"Figure": _Dummy}), ("wfdb", {})):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                _stub(name, **attrs)
+    if "plotly" in sys.modules and not hasattr(sys.modules["plotly"], "graph_objects"):
+        sys.modules["plotly"].graph_objects = sys.modules["plotly.graph_objects"]
+    # the reference's top-level `datasets` package must win over HuggingFace `datasets` if that was imported earlier
+    for name in ("datasets", "tasks", "loggers"):
+        mod = sys.modules.get(name)
+        if mod is not None and not str(getattr(mod, "__file__", "")).startswith(str(REFERENCE)):
+            del sys.modules[name]
+    datasets = importlib.import_module("datasets")
+    tasks = importlib.import_module("tasks")
+    loggers = importlib.import_module("loggers")
+    tasks_base = importlib.import_module("tasks.base")
+    datasets_base = importlib.import_module("datasets.base")
+    _trainer_ns = types.SimpleNamespace(ref=ref, datasets=datasets, tasks=tasks, loggers=loggers,
+                                        tasks_base=tasks_base, datasets_base=datasets_base,
+                                        dict_to_object=ref.dict_to_object)
+    return _trainer_ns

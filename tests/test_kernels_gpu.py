@@ -638,7 +638,7 @@ def test_round_and_split_tf32(ops, cuda):
 def test_gemm_tf32_and_3xtf32(ops, cuda, m, n, k, bn):
     """fp32 operands on tcgen05 kind::tf32.  Operands pre-rounded to TF32 => the only error left is fp32 accumulation
     order (rtol 1e-5); with the 3xTF32 split on full-precision operands the contraction is fp32-grade (vs an fp64
-    reference: rel-L2 < 2e-6, where plain TF32 on the same data gives ~3e-4)."""
+    reference: rel-L2 < 5e-6 = fp32 accumulation noise, where plain TF32 on the same data gives ~3e-4)."""
     g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
     a = torch.randn(m, k, generator=g).to(cuda)
     b = torch.randn(n, k, generator=g).to(cuda)
@@ -648,7 +648,7 @@ def test_gemm_tf32_and_3xtf32(ops, cuda, m, n, k, bn):
     d = torch.full((m, n), float("nan"), device=cuda)
     ops.gemm(ar, br, d, m=m, n=n, k=k, block_n=bn)
     ref = (ar.double() @ br.double().t())
-    assert _rel_l2(d.double(), ref) < 2e-6
+    assert _rel_l2(d.double(), ref) < 5e-6
     torch.testing.assert_close(d.double(), ref, rtol=1e-4, atol=1e-4 * math.sqrt(k))
     # 3xTF32 on the unrounded operands
     a_hi, a_lo = ops.split_tf32(a)
@@ -657,7 +657,7 @@ def test_gemm_tf32_and_3xtf32(ops, cuda, m, n, k, bn):
     ops.gemm(a_hi, b_hi, d3, m=m, n=n, k=k, block_n=bn, a_lo=a_lo, b_lo=b_lo)
     ref3 = a.double() @ b.double().t()
     e3, e1 = _rel_l2(d3.double(), ref3), _rel_l2(d.double(), ref3)
-    assert e3 < 2e-6, (e3, e1)
+    assert e3 < 5e-6, (e3, e1)
     if k >= 32:
         assert e1 > 20 * e3                                            # what the split buys over plain TF32
 
@@ -687,7 +687,7 @@ def test_gemm_tf32_epilogues(ops, cuda):
     ops.gemm(x, w, d, m=m, n=n, k=k, bias=bias, bias_axis=1, epilogue=2)
     z = x.double() @ w.double().t() + bias.double()
     ref = 0.5 * z * (1 + torch.tanh(math.sqrt(2 / math.pi) * (z + 0.044715 * z ** 3)))
-    torch.testing.assert_close(d.double(), ref, rtol=2e-3, atol=2e-3)             # tanh.approx in the epilogue
+    torch.testing.assert_close(d.double(), ref, rtol=1e-5, atol=1e-5)             # tanhf at library accuracy
     # residual add with bias, transposed store
     r0 = torch.randn(m, n, generator=g).to(cuda)
     r = r0.clone()
@@ -731,8 +731,8 @@ def test_gemm_tf32_rope_epilogue_and_attn_f32(ops, cuda, hd, Lc):
     ref = O.causal_attention(q, k, v, hd ** -0.5).transpose(1, 2).reshape(Bp, L, D)
     got_qkv = expand(qkv.cpu())
     ref_qkv = torch.cat([t.transpose(1, 2).reshape(Bp, L, D) for t in (q, k, v)], -1)
-    assert _rel_l2(got_qkv.double(), ref_qkv) < 4e-4                   # q / k / v stored rounded to TF32
-    assert _rel_l2(expand(out.cpu()).double(), ref) < 5e-4
+    assert _rel_l2(got_qkv.double(), ref_qkv) < 5e-6                   # q / k / v stay unrounded fp32
+    assert _rel_l2(expand(out.cpu()).double(), ref) < 5e-6
     if Lc:   # the shared rows are computed once and identical for every sample by construction
         assert torch.isfinite(out).all()
 
