@@ -302,6 +302,17 @@ int mts_prompt_gather(const int32_t* ids, const float* emb, const float* wpe, fl
 int mts_prompt_gather_shared(const int32_t* ids, const float* emb, const float* wpe, float* x, int B,
                              int rep, int Lp, int L, int Lc, int D, mts_stream_t stream);
 
+/* Numbers of the "input statistics" prompt (ref: models/medtsllm.py:441-495 build_input_stats_prompt, :530-538
+ * calcute_lags), for features [f0, f0 + C_sel) of x fp32 [B, T, C]:
+ *   stats fp32 [B, C_sel, 4] = (min, max, lower median as torch.median, trend: 1 if sum(diff(x)) > 0 else 0)
+ *   corr  fp64 [B, C_sel, T] workspace: circular autocorrelation sum_t x[t] x[(t+k) mod T] (= irfft(rfft conj rfft) for
+ *         even T; the caller keeps the reference's FFT route for odd T, where irfft returns T-1 points)
+ *   lags  int32 [B, n_lags]: indices of the n_lags largest values of mean_c corr[b, c, :], descending; the pairs
+ *         corr[k] == corr[T-k], which the reference's FFT orders by rounding noise, resolve to the smaller index
+ * Two launches; the host reads stats and lags back in one copy instead of the reference's five `.tolist()` syncs. */
+int mts_input_stats(const float* x, float* stats, double* corr, int32_t* lags, int B, int T, int C, int f0, int C_sel,
+                    int n_lags, mts_stream_t stream);
+
 /* y = silu(g) * u on bf16, g/u being the two halves of a [rows, 2*I] (ld = ldgu) buffer laid out
  * [g | u];  (training path keeps g,u for the backward; ref HF llama :182-184) */
 int mts_swiglu(const uint16_t* gu, int64_t ldgu, uint16_t* y, int64_t rows, int I,

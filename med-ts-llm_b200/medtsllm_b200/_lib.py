@@ -89,6 +89,7 @@ SIGNATURES = {
     "mts_split_tf32": [_p, _p, _p, _i64, _p],
     "mts_softmax_rows_f32": [_p, _p, _i64, _i, _f, _p],
     "mts_attn_causal_f32": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
+    "mts_input_stats": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],
 }

@@ -420,20 +420,37 @@ class MedTsLLM(nn.Module):
             d = flags["input_stats_dim"]
             insert, s = f"feature {d}", ""
             xs = xs[:, :, d]
+        B, T = xs.size(0), xs.size(1)
         with torch.no_grad():
-            # same torch reductions as the reference (:477-481); its five `.tolist()` device syncs become one read-back
-            mins, maxs = torch.min(xs, dim=1).values, torch.max(xs, dim=1).values
-            meds = torch.median(xs.float(), dim=1).values
-            trends = xs.diff(dim=1).sum(dim=1) > 0
-            lags = _calcute_lags(xs.float(), self.n_lags)                 # [B, n_lags]
-            B = xs.size(0)
-            packed = torch.cat([t.reshape(B, -1).double() for t in (mins, maxs, meds, trends, lags)], dim=1).cpu()
-            w = mins.reshape(B, -1).shape[1]
-            shape = list(mins.shape[1:])
-            unpack = lambda k: packed[:, k * w:(k + 1) * w].reshape([B] + shape)      # noqa: E731
-            mins, maxs, meds = (unpack(k).to(xs.dtype).tolist() for k in range(3))
-            trends = unpack(3).bool().tolist()
-            lags = packed[:, 4 * w:].long().tolist()
+            if xs.is_cuda and xs.dtype == torch.float32 and T % 2 == 0 and T <= 12288:
+                # one fused kernel pair + ONE packed read-back (the reference: five `.tolist()` device syncs, :477-481)
+                x3 = inputs["x_enc"].detach()
+                x3 = x3.unsqueeze(-1) if x3.ndim == 2 else x3
+                if flags["input_stats_dim"] == "all":
+                    stats, lags_d = ops.input_stats(x3, n_lags=self.n_lags)
+                else:
+                    stats, lags_d = ops.input_stats(x3, f0=int(flags["input_stats_dim"]), n_features=1, n_lags=self.n_lags)
+                w = stats.shape[1]
+                packed = torch.cat([stats.reshape(B, 4 * w), lags_d.to(torch.float32)], dim=1).cpu()
+                st = packed[:, :4 * w].reshape(B, w, 4)
+                pick = (lambda k: st[:, :, k]) if flags["input_stats_dim"] == "all" else (lambda k: st[:, 0, k])
+                mins, maxs, meds = (pick(k).tolist() for k in range(3))
+                trends = (pick(3) > 0.5).tolist()
+                lags = packed[:, 4 * w:].long().tolist()
+            else:
+                # odd window lengths (irfft then returns T-1 points) and host tensors: the reference's own torch route,
+                # with its five read-backs packed into one
+                mins, maxs = torch.min(xs, dim=1).values, torch.max(xs, dim=1).values
+                meds = torch.median(xs.float(), dim=1).values
+                trends = xs.diff(dim=1).sum(dim=1) > 0
+                lags = _calcute_lags(xs.float(), self.n_lags)                 # [B, n_lags]
+                packed = torch.cat([t.reshape(B, -1).double() for t in (mins, maxs, meds, trends, lags)], dim=1).cpu()
+                w = mins.reshape(B, -1).shape[1]
+                shape = list(mins.shape[1:])
+                unpack = lambda k: packed[:, k * w:(k + 1) * w].reshape([B] + shape)      # noqa: E731
+                mins, maxs, meds = (unpack(k).to(xs.dtype).tolist() for k in range(3))
+                trends = unpack(3).bool().tolist()
+                lags = packed[:, 4 * w:].long().tolist()
         return [
             f"Input statistics ({insert}): min value{s} = {fmt_float(mins[b])}, max value{s} = {fmt_float(maxs[b])}, "
             f"median value{s} = {fmt_float(meds[b])}, the trend of input is {fmt_trend(trends[b])}, "

@@ -659,3 +659,21 @@ def attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, *, scale=None, out=None, round_out=F
     _lib.call("mts_attn_causal_f32", qkv.data_ptr(), out.data_ptr(), Bp, Lc, Ls, H, hd, scale, 1 if round_out else 0,
               _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# prompt statistics
+# ------------------------------------------------------------------------------------------------
+def input_stats(x, *, f0=0, n_features=None, n_lags=5):
+    """Device side of build_input_stats_prompt (models/medtsllm.py:441-495): x fp32 [B, T, C] ->
+    (stats fp32 [B, C_sel, 4] = min / max / median / trend, lags int32 [B, n_lags]), both still on the device."""
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    B, T, Cc = x.shape
+    C_sel = Cc - f0 if n_features is None else n_features
+    stats = torch.empty(B, C_sel, 4, device=x.device, dtype=torch.float32)
+    corr = torch.empty(B, C_sel, T, device=x.device, dtype=torch.float64)
+    lags = torch.empty(B, n_lags, device=x.device, dtype=torch.int32)
+    _lib.call("mts_input_stats", x.data_ptr(), stats.data_ptr(), corr.data_ptr(), lags.data_ptr(), B, T, Cc, f0, C_sel,
+              n_lags, _stream())
+    return stats, lags

@@ -133,3 +133,58 @@ def test_full_depth_forward_vs_oracle(workload, precision, cuda):
         assert k["output"] <= 2e-2, k
         if "hf_bf16_autocast" in rows:
             assert k["llm"] <= 1.5 * rows["hf_bf16_autocast"]["llm"] + 1e-3, rows
+
+
+@pytest.mark.parametrize("workload", ["bidmc_llama2_7b", "psm_gpt2_medium"])
+def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
+    """loss.backward() through the full-depth kernel stack (bf16 path: the reference trains under bf16 autocast,
+    tasks/forecasting.py:22) against autograd through the fp32 CPU oracle on the same weights / windows / loss, batch 2.
+    YARDSTICK: the oracle's own arithmetic executed on the GPU under `torch.autocast(bfloat16)` — the reference's training
+    regime — against the same fp32 gradients.  Asserted: every adapter gradient within 2x the yardstick's error (+ 2e-2),
+    i.e. the kernel path's gradients are as close to exact arithmetic as the reference's own mixed-precision training."""
+    from oracle import medtsllm_oracle as O
+    w, model, inputs = build(workload, cuda, 2)
+    model.train()
+    model.use_train_graph = "0"
+    x_dev = inputs["x_enc"].to(cuda)
+    wgt = torch.randn(model({"x_enc": x_dev}).shape, generator=torch.Generator().manual_seed(5))
+    model.zero_grad(set_to_none=True)
+    out = model({"x_enc": x_dev})
+    (out * wgt.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    ids = model.prompt_token_ids({"x_enc": x_dev}).tolist()
+    spec = oracle_spec(w, model)
+    bb = model._backbone
+
+    def oracle_grads(device, autocast):
+        sd_cpu = LazyBackboneState(bb, keep=(device == "cpu"))
+        if device == "cpu":
+            sd = sd_cpu
+        else:                                           # same fp32 tensors, resident on the GPU for the autocast run
+            class _Dev(dict):
+                def __missing__(self, key):
+                    self[key] = sd_cpu[key].to(device)
+                    return self[key]
+            sd = _Dev()
+        ad = {k: v.detach().to(device).clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            o = O.medtsllm_forward(inputs["x_enc"].to(device), ids, ad, sd, spec, training=True)
+        (o.float() * wgt.to(device)).sum().backward()
+        return {k: v.grad.detach().float().cpu() for k, v in ad.items()}
+
+    ref = oracle_grads("cpu", False)
+    del model
+    torch.cuda.empty_cache()
+    yard = oracle_grads(cuda, True)
+    table = {}
+    for k, g0 in ref.items():
+        table[k] = {"kernel": rel_l2(got[k], g0), "oracle_bf16_autocast": rel_l2(yard[k], g0)}
+    report = {"workload": workload, "batch": 2, "layers": bb.spec.layers, "rel_l2_vs_cpu_fp32_autograd": table}
+    print("\n[full-size gradients] " + json.dumps(report))
+    (REPO / "gpurun_out").mkdir(exist_ok=True)
+    (REPO / "gpurun_out" / f"parity_fullsize_grads_{workload}.json").write_text(json.dumps(report, indent=1))
+    for k, row in table.items():
+        if k.endswith("key_projection.bias"):          # structurally zero (softmax shift invariance): noise on both sides
+            continue
+        assert row["kernel"] <= 2.0 * row["oracle_bf16_autocast"] + 2e-2, (k, row)
