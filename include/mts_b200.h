@@ -204,6 +204,12 @@ typedef struct mts_gemm_args {
    * ~2^-21 instead of TF32's 2^-11 at three times the tensor work.  NULL (both) = plain TF32. */
   const void* a_lo;
   const void* b_lo;
+  /* RESID_ADD only: D = C + dropout(alpha * A B^T + bias) with keep probability 1 - drop_p and the counter-based mask
+   * of mts_dropout (element (row, col) of the [m, n] result has index row*n + col): the residual dropouts that stay
+   * live in the reference's train mode for GPT-2 backbones (tasks/forecasting.py:18 flips the HF module;
+   * HF:models/gpt2/modeling_gpt2.py:233, :243 resid_dropout).  0 = off. */
+  float drop_p;
+  uint64_t drop_seed;
 } mts_gemm_args;
 
 int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);
@@ -244,6 +250,16 @@ int mts_layernorm(const float* x, int64_t ldx, const float* w, const float* b, u
 int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                     uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
                     mts_stream_t stream);
+/* Same attention with dropout on the probabilities after the softmax (train mode of the frozen backbone: GPT-2
+ * attn_pdrop, HF:models/gpt2/modeling_gpt2.py:67-68; Llama attention_dropout, HF:models/llama/modeling_llama.py:217).
+ * Counter-based mask as mts_dropout: element (b, h, q, k) has index ((b*H + h)*L + q)*L + k.  q / k already rotated,
+ * plain row layout, sequences that fit the sequence-resident kernels.  lse is of the UNMASKED scores. */
+int mts_attn_causal_dropout(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
+                            float p, uint64_t seed, mts_stream_t stream);
+/* Its backward (rope tables only rotate dq / dk back; NULL for GPT-2): dP = mask * (dO V^T), dV = (mask * P)^T dO. */
+int mts_attn_causal_dropout_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin, const uint16_t* out,
+                                const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp, int L,
+                                int H, int hd, float scale, float p, uint64_t seed, mts_stream_t stream);
 /* RoPE applied in place to the q and k sections of qkv (same tables / convention as above).  After it,
  * call mts_attn_causal with NULL tables: short sequences (K and V of one head fit in shared memory)
  * then take the single-staging kernel. */

@@ -299,7 +299,11 @@ template <int HD>
 __global__ void __launch_bounds__(kSeqThreads)
 attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                            float* __restrict__ lse, int Bp, int L_all, int Lc_all, int spc, int rows_alloc, int H,
-                           float scale_log2e) {
+                           float scale_log2e, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
+  // drop_thresh != 0 (plain layout only): dropout on the attention probabilities after the softmax
+  // (HF:models/gpt2/modeling_gpt2.py:67-68, HF:models/llama/modeling_llama.py:217): the normaliser l and the saved
+  // log-sum-exp use the unmasked P, the P V contraction the masked one; element (b, h, q, k) has index
+  // ((b*H + h)*L + q)*L + k in the counter-based mask.
   pdl_wait();
   pdl_trigger();
   constexpr int kPitch = HD + 8;
@@ -432,6 +436,18 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
           l_run[e >> 1] += pv;
         }
       }
+      if (drop_thresh != 0) {
+        const uint64_t base = ((uint64_t)(b0 + si) * H + h) * (uint64_t)L * (uint64_t)L;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = j0 + nt * 8 + tq * 2 + (e & 1);
+            const int row = (e < 2) ? row_a : row_b;
+            s[nt][e] = dropout_keep(drop_seed, base + (uint64_t)row * L + col, drop_thresh) ? s[nt][e] * drop_scale : 0.0f;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) {
         o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
@@ -495,7 +511,8 @@ static size_t seq_smem_bytes(int L, int Lc = 0, int spc = 1) {
 // (Lc > 0: the launch also computes the prefix rows themselves; lse = [H, Lc] followed by [Bp, H, Ls]).
 template <int HD>
 static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H,
-                           float scale, cudaStream_t stream) {
+                           float scale, cudaStream_t stream, uint32_t drop_thresh = 0, float drop_scale = 1.0f,
+                           uint64_t drop_seed = 0) {
   auto ks = attn_causal_fwd_seq_kernel<HD>;
   static bool seq_attr_done = false;
   if (!seq_attr_done) {
@@ -517,7 +534,7 @@ static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int B
   LAUNCH_PDL(ks, grid, kSeqThreads, smem, stream,
       
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, Bp, L, Lc, spc,
-      rows_alloc, H, scale * 1.4426950408889634f);
+      rows_alloc, H, scale * 1.4426950408889634f, drop_thresh, drop_scale, drop_seed);
   count_launch();
   return check_launch("attn_causal_fwd_seq_kernel");
 }
@@ -852,9 +869,11 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
                        const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                        const float* __restrict__ lse, const float* __restrict__ delta,
                        __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int Lc, int spc, int rows_alloc, int H,
-                       float scale) {
+                       float scale, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
   pdl_wait();
   pdl_trigger();
+  // drop_thresh != 0 (plain layout): the forward dropped attention probabilities (see attn_causal_fwd_seq_kernel):
+  // dP = mask * (dO V^T), dS = P * (dP - delta) with delta = rowsum(dO * O) unchanged.
   // Lc > 0: shared-prefix layout as in attn_causal_fwd_seq_kernel (a CTA serves spc samples of one head; the prefix
   // K/V are staged once).  qkv holds every row (prefix rows once, then Ls = L - Lc own rows per sample); dout / lse /
   // delta / dqkv hold the samples' own rows only ([Bp*Ls, ...]): the prefix has no trainable ancestor, so no gradient
@@ -934,7 +953,10 @@ attn_bwd_dq_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
           const int col = j0 + nt * 8 + tq * 2 + (e & 1);
           const int row = (e < 2) ? row_a : row_b;
           const float pv = (col > row || col >= L) ? 0.f : exp2f(s[nt][e] * scale_log2e - ((e < 2) ? lse_a : lse_b));
-          s[nt][e] = pv * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * scale;
+          float dpv = dp[nt][e];
+          if (drop_thresh != 0)
+            dpv = dropout_keep(drop_seed, ((uint64_t)bh * L + row) * (uint64_t)L + col, drop_thresh) ? dpv * drop_scale : 0.f;
+          s[nt][e] = pv * (dpv - ((e < 2) ? del_a : del_b)) * scale;
         }
       }
       mma_p_b<HD>(dq, s, Ks + j0 * kPitch, lane, 0, g_hi, Lc - j0, soff);
@@ -950,9 +972,11 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rope_cos,
                         const float* __restrict__ rope_sin, const __nv_bfloat16* __restrict__ dout,
                         const float* __restrict__ lse, const float* __restrict__ delta,
-                        __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int spc, int H, float scale) {
+                        __nv_bfloat16* __restrict__ dqkv, int Bp, int L, int spc, int H, float scale,
+                        uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
   pdl_wait();
   pdl_trigger();
+  // drop_thresh != 0: attention-probability dropout of the forward: dV = (mask * P)^T dO, dS from the masked dP.
   // A CTA serves spc consecutive samples of one head (short own-token runs would otherwise leave most of the 8
   // warps without a key strip): sample i keeps its Q / dO / lse / delta rows at [i*Lp, i*Lp + L).
   constexpr int kPitch = HD + 8;
@@ -1031,8 +1055,14 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
           const int key = (e < 2) ? key_a : key_b;
           const bool dead = key > qrow || key >= L || qrow >= L || (nt >> 1) < g_lo || (nt >> 1) >= g_hi;
           const float pv = dead ? 0.f : exp2f(st[nt][e] * scale_log2e - lse_b[min(qrow, Lp - 1)]);
-          st[nt][e] = pv;
-          dpt[nt][e] = dead ? 0.f : pv * (dpt[nt][e] - del_b[min(qrow, Lp - 1)]) * scale;
+          float pd = pv, dpv = dpt[nt][e];
+          if (drop_thresh != 0 && !dead) {
+            const bool keep = dropout_keep(drop_seed, (((uint64_t)b * H + h) * L + qrow) * (uint64_t)L + key, drop_thresh);
+            pd = keep ? pv * drop_scale : 0.f;
+            dpv = keep ? dpv * drop_scale : 0.f;
+          }
+          st[nt][e] = pd;
+          dpt[nt][e] = dead ? 0.f : pv * (dpv - del_b[min(qrow, Lp - 1)]) * scale;
         }
       }
       mma_p_b<HD>(dv, st, dOb + i0 * kPitch, lane, g_lo, g_hi);
@@ -1403,7 +1433,8 @@ static size_t seq_dq_smem_bytes(int L, int Lc, int spc) {
 template <int HD>
 static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out,
                            const uint16_t* dout, const float* lse, float* delta, uint16_t* dqkv, int Bp,
-                           int L, int H, float scale, int pre_roped, cudaStream_t stream) {
+                           int L, int H, float scale, int pre_roped, cudaStream_t stream, uint32_t drop_thresh = 0,
+                           float drop_scale = 1.0f, uint64_t drop_seed = 0) {
   constexpr int kSmemQ = 4 * 64 * (HD + 8) * 2;
   constexpr int kSmemKV = kSmemQ + 2 * 64 * 4;
   auto kq = attn_bwd_dq_kernel<HD>;
@@ -1438,7 +1469,8 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
       LAUNCH_PDL(sq, Bp * H, kSeqThreads, smem, stream,
       
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, 0, 1, seq_rows_alloc(L, 0, 1), H, scale);
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, 0, 1, seq_rows_alloc(L, 0, 1), H, scale, drop_thresh,
+          drop_scale, drop_seed);
       count_launch();
       rc_ = check_launch("attn_bwd_dq_seq_kernel");
       if (rc_) return rc_;
@@ -1446,11 +1478,14 @@ static int launch_attn_bwd(const uint16_t* qkv, const float* rc, const float* rs
       LAUNCH_PDL(skv, ((Bp + spc - 1) / spc) * H, kSeqThreads, seq_bwd_smem_bytes<HD>(L, spc), stream,
       
           reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, spc, H, scale);
+          delta, reinterpret_cast<__nv_bfloat16*>(dqkv), Bp, L, spc, H, scale, drop_thresh, drop_scale, drop_seed);
       count_launch();
       return check_launch("attn_bwd_dkv_seq_kernel");
     }
   }
+  if (drop_thresh != 0)
+    return set_error(MTS_ERR_UNSUPPORTED, "attention-probability dropout needs pre-rotated q / k and a sequence that fits "
+                                          "the sequence-resident kernels (%d positions do not)", L);
   const int64_t grid_l = (int64_t)((L + 63) / 64) * Bp * H;
   if (grid_l > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_bwd: grid too large");
   kq<<<(int)grid_l, kAttnThreads, kSmemQ, stream>>>(
@@ -1539,7 +1574,7 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   LAUNCH_PDL(sq, ((Bp + spc - 1) / spc) * H, kSeqThreads, seq_dq_smem_bytes<HD>(L, Lc, spc), stream,
       
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, L, Lc, spc, seq_rows_alloc(L, Lc, spc), H, scale);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, L, Lc, spc, seq_rows_alloc(L, Lc, spc), H, scale, 0u, 1.0f, (uint64_t)0);
   count_launch();
   rc_ = check_launch("attn_bwd_dq_seq_kernel");
   if (rc_) return rc_;
@@ -1551,7 +1586,7 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
       
       reinterpret_cast<const __nv_bfloat16*>(qkv) + (int64_t)Lc * 3 * D, rc ? rc + (int64_t)Lc * half : nullptr,
       rs ? rs + (int64_t)Lc * half : nullptr, reinterpret_cast<const __nv_bfloat16*>(dout_own), lse_own, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, Ls, spc_kv, H, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv_own), Bp, Ls, spc_kv, H, scale, 0u, 1.0f, (uint64_t)0);
   count_launch();
   return check_launch("attn_bwd_dkv_seq_kernel");
 }
@@ -1580,7 +1615,7 @@ static int launch_attn_shared_bwd_full(const uint16_t* qkv, const float* rc, con
   LAUNCH_PDL(sq, H, kSeqThreads, seq_dq_smem_bytes<HD>(Lc, 0, 1), stream,
       
       reinterpret_cast<const __nv_bfloat16*>(qkv), rc, rs, reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv), 1, Lc, 0, 1, seq_rows_alloc(Lc, 0, 1), H, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv), 1, Lc, 0, 1, seq_rows_alloc(Lc, 0, 1), H, scale, 0u, 1.0f, (uint64_t)0);
   count_launch();
   rc_ = check_launch("attn_bwd_dq_seq_kernel");
   if (rc_) return rc_;
@@ -1668,6 +1703,40 @@ extern "C" int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const
     case 128: return launch_attn<128>(qkv, rope_cos, rope_sin, out, lse, Bp, L, H, scale, (cudaStream_t)s);
     default: return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal: head dim %d (supported: 64, 128)", hd);
   }
+}
+
+// Attention with dropout on the probabilities (train-mode HF GPT-2: attn_pdrop, HF:models/gpt2/modeling_gpt2.py:67-68;
+// Llama: attention_dropout).  q / k pre-rotated, plain row layout, sequence-resident kernels only.
+extern "C" int mts_attn_causal_dropout(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int H, int hd,
+                                       float scale, float p, uint64_t seed, mts_stream_t stream_) {
+  if (!qkv || !out || Bp <= 0 || L <= 0 || H <= 0 || !(p >= 0.f && p < 1.f))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_dropout: bad arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float dscale = 1.0f / (1.0f - p);
+  if (hd == 64) {
+    if (seq_smem_bytes<64>(L) > 220 * 1024) return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_dropout: sequence too long");
+    return launch_attn_seq<64>(qkv, out, lse, Bp, L, 0, H, scale, stream, thresh, dscale, seed);
+  }
+  if (hd == 128) {
+    if (seq_smem_bytes<128>(L) > 220 * 1024) return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_dropout: sequence too long");
+    return launch_attn_seq<128>(qkv, out, lse, Bp, L, 0, H, scale, stream, thresh, dscale, seed);
+  }
+  return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_dropout: head dim must be 64 or 128");
+}
+
+extern "C" int mts_attn_causal_dropout_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
+                                           const uint16_t* out, const uint16_t* dout, const float* lse, float* delta,
+                                           uint16_t* dqkv, int Bp, int L, int H, int hd, float scale, float p,
+                                           uint64_t seed, mts_stream_t stream_) {
+  if (!qkv || !out || !dout || !lse || !delta || !dqkv || Bp <= 0 || L <= 0 || H <= 0 || !(p >= 0.f && p < 1.f))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_dropout_bwd: bad arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  const float dscale = 1.0f / (1.0f - p);
+  if (hd == 64) return launch_attn_bwd<64>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, 1, stream, thresh, dscale, seed);
+  if (hd == 128) return launch_attn_bwd<128>(qkv, rope_cos, rope_sin, out, dout, lse, delta, dqkv, Bp, L, H, scale, 1, stream, thresh, dscale, seed);
+  return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_dropout_bwd: head dim must be 64 or 128");
 }
 
 extern "C" int mts_attn_causal_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,

@@ -30,6 +30,12 @@ struct GemmParams {
   // training path keeps for the backward
   __nv_bfloat16* aux;
   int64_t ld_aux;
+  // RESID_ADD with dropout on the projected value: D = C + dropout(alpha * A B^T + bias) — the train-mode residual
+  // dropouts of HF GPT-2 (resid_pdrop: HF:models/gpt2/modeling_gpt2.py:233, :243); element (row, col) of the [m, n]
+  // result has index row*n + col in the counter-based mask (the backward calls mts_dropout on the [m, n] gradient)
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t drop_seed;
   int precise;     // fp32 operands (evaluation parity modes): accurate expf / tanhf in the activation epilogues
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
@@ -236,6 +242,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           }
         }
         if (col0 >= n_store) continue;  // warp-uniform
+        if constexpr (EPI == MTS_EPI_RESID_ADD) {
+          if (p.drop_thresh != 0) {
+            const uint64_t base = ((uint64_t)b * p.m + (uint64_t)row) * (uint64_t)p.n + (uint64_t)col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = dropout_keep(p.drop_seed, base + j, p.drop_thresh) ? v[j] * p.drop_scale : 0.0f;
+          }
+        }
         if constexpr (EPI != MTS_EPI_RESID_ADD) {
           if (p.round_tf32) {   // fp32 result that is the operand of a kind::tf32 GEMM: round to nearest, not truncate
 #pragma unroll

@@ -275,7 +275,7 @@ bool pdl_enabled() {
 
 using namespace mts;
 
-static_assert(sizeof(mts_gemm_args) == 200, "mts_gemm_args layout is part of the C ABI (ctypes mirror: _lib.GemmArgs)");
+static_assert(sizeof(mts_gemm_args) == 216, "mts_gemm_args layout is part of the C ABI (ctypes mirror: _lib.GemmArgs)");
 
 extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
@@ -383,6 +383,14 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   p.alpha = a->alpha;
   p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
   p.rope_L = a->rope_L; p.rope_hd = a->rope_hd; p.rope_cols = a->rope_cols; p.rope_prefix = a->rope_prefix;
+  p.drop_thresh = 0; p.drop_scale = 1.0f; p.drop_seed = 0;
+  if (a->drop_p != 0.0f) {
+    if (a->epilogue != MTS_EPI_RESID_ADD || !(a->drop_p > 0.0f && a->drop_p < 1.0f))
+      return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: drop_p needs the RESID_ADD epilogue and 0 <= p < 1");
+    p.drop_thresh = (uint32_t)((double)a->drop_p * 4294967296.0);
+    p.drop_scale = 1.0f / (1.0f - a->drop_p);
+    p.drop_seed = a->drop_seed;
+  }
   p.round_tf32 = (a->round_tf32 && f32) ? 1 : 0;
   p.precise = tf32 ? 1 : 0;
   p.aux = nullptr; p.ld_aux = 0;

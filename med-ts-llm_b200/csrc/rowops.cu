@@ -434,13 +434,7 @@ extern "C" int mts_softmax_lastdim(float* y, int64_t rows, int n, mts_stream_t s
 // gradient with the same seed.  y = keep ? x / (1 - p) : 0.
 // ------------------------------------------------------------------------------------------
 namespace mts {
-__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finaliser, upper bits
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 32);
-}
+// (mix32 / dropout_keep: ptx.cuh — shared with the attention and GEMM-epilogue dropouts)
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n,
                                     uint32_t thresh, float scale, uint64_t seed) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

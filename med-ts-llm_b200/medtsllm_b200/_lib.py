@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
         ("ab_dtype", C.c_int32), ("round_tf32", C.c_int32),
         ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint64),
     ]
 
 
@@ -90,6 +91,8 @@ SIGNATURES = {
     "mts_softmax_rows_f32": [_p, _p, _i64, _i, _f, _p],
     "mts_attn_causal_f32": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mts_input_stats": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mts_attn_causal_dropout": [_p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _p],
+    "mts_attn_causal_dropout_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _p],
     "mts_clear_caches": [],
     "mts_set_option": [C.c_char_p, _i],
 }

@@ -281,7 +281,8 @@ class KernelBackbone:
             self._embed_bf16 = ops.cast_bf16(self.embed)
         return self._embed_bf16
 
-    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None, lora=None, Lc: int = 0):
+    def forward(self, x: torch.Tensor, Bp: int, L: int, stash: list | None = None, lora=None, Lc: int = 0,
+                dropout: dict | None = None):
         """x: fp32 residual stream [Bp*L, D].  Inference (stash None): updated IN PLACE layer by layer.
         Training (stash = list): every residual write goes to a fresh buffer (the GEMM epilogue reads
         C = previous stream, writes D = new one) and the per-layer tensors backward() needs are
@@ -290,7 +291,14 @@ class KernelBackbone:
         Lc > 0: shared-prefix row layout (include/mts_b200.h, mts_attn_causal_shared) — the Lc leading prompt
         positions every sample shares are carried once: x is [Lc + Bp*(L-Lc), D], rows [0, Lc) the prefix, then
         L-Lc own rows per sample.  All row-wise kernels and GEMMs are layout-agnostic; RoPE positions and
-        attention are told about it."""
+        attention are told about it.
+
+        `dropout` = {"embd": p, "attn": p, "resid": p, "seeds": [1 + 3*layers ints]}: the frozen backbone's OWN dropouts,
+        which stay live in the reference's train mode because `model.train()` also flips the HF module
+        (tasks/forecasting.py:18): GPT-2 embd_pdrop on inputs_embeds + wpe (HF:models/gpt2/modeling_gpt2.py:612),
+        attn_pdrop on the attention probabilities (:67-68), resid_pdrop on both projected branches (:233, :243); Llama
+        attention_dropout (HF:models/llama/modeling_llama.py:217).  Counter-based masks (mts_dropout) re-created by
+        backward() from the same seeds.  Plain row layout only: the masks differ per sample, prompt rows included."""
         s = self.spec
         D, H, hd = s.hidden, s.heads, s.head_dim
         Ls = L - Lc
@@ -305,7 +313,16 @@ class KernelBackbone:
         bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
         h, qkv, att = bf(M, D), bf(M, 3 * D), bf(M, D)
         llama = s.kind == "llama"
+        p_embd = p_attn = p_resid = 0.0
+        if dropout is not None:
+            if Lc:
+                raise MtsError("backbone dropout needs the plain row layout (masks differ per sample)")
+            p_embd, p_attn, p_resid = dropout["embd"], dropout["attn"], dropout["resid"]
+            seeds = dropout["seeds"]
+            if p_embd > 0:
+                ops.dropout(x, p_embd, seeds[0], out=x)
         for li, lay in enumerate(self.layers):
+            s_attn, s_r1, s_r2 = seeds[1 + 3 * li: 4 + 3 * li] if dropout is not None else (0, 0, 0)
             if train:
                 qkv, att = bf(M, 3 * D), bf(M, D)
                 if lora is not None:
@@ -331,7 +348,9 @@ class KernelBackbone:
                     ops.rope_qk_shared_(qkv, Bp, Lc, Ls, H, hd, rope)
                 else:
                     ops.rope_qk_(qkv, Bp, L, H, hd, rope)
-            if Lc:
+            if p_attn > 0:
+                _, lse = ops.attn_causal_dropout(qkv, Bp, L, H, hd, p_attn, s_attn, out=att)
+            elif Lc:
                 if train:
                     _, lse = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, out=att, want_lse=True)
                 else:
@@ -342,7 +361,8 @@ class KernelBackbone:
                 ops.attn_causal(qkv, Bp, L, H, hd, rope=None, out=att)
             x_mid = torch.empty_like(x_in) if train else x_in
             ops.gemm(att, lay["wo"], x_mid, m=M, n=D, k=D, epilogue=EPI_RESID_ADD, c=x_in if train else None,
-                     bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
+                     bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N,
+                     drop_p=p_resid, drop_seed=s_r1)
             # --- MLP half
             x_out = torch.empty_like(x_in) if train else x_in
             if train and lora is not None:
@@ -371,7 +391,7 @@ class KernelBackbone:
                     ops.gemm(h, lay["wfc"], act, m=M, n=s.inter, k=D, bias=lay["bfc"], bias_axis=BIAS_N,
                              epilogue=EPI_GELU_NEW)
                 ops.gemm(act, lay["wproj"], x_out, m=M, n=D, k=s.inter, bias=lay["bproj"], bias_axis=BIAS_N,
-                         epilogue=EPI_RESID_ADD, c=x_mid if train else None)
+                         epilogue=EPI_RESID_ADD, c=x_mid if train else None, drop_p=p_resid, drop_seed=s_r2)
             if train:
                 stash.append(dict(x_in=x_in, x_mid=x_mid, qkv=qkv, att=att, lse=lse, pre=pre,
                                   h=h_attn if lora is not None else None, lora_t=lora_t))
@@ -445,7 +465,7 @@ class KernelBackbone:
         return out
 
     def backward(self, dhid: torch.Tensor, x_final: torch.Tensor, stash: list, Bp: int, L: int, lora=None,
-                 Lc: int = 0, norm_grads: dict | None = None):
+                 Lc: int = 0, norm_grads: dict | None = None, dropout: dict | None = None):
         """dgrad through the frozen stack: dhid = dL/d(final-norm output) bf16 [Bp*L, D] -> returns
         (dL/d(input residual stream) fp32 [Bp*L, D], LoRA gradients aligned with lora.params() or None).
         No gradients for the frozen weights.
@@ -476,16 +496,23 @@ class KernelBackbone:
             norm_grads[("ln_f",)] = ops.norm_wgrad(x_final[own], dhid, s.eps, layernorm=not llama)
         norm_bwd(x_final[own], self.final_norm_w, dhid, dR, s.eps, accumulate=False, dx_bf16=dRb)
         lora_grads = [None] * len(lora.params()) if lora is not None else None
+        p_embd = p_attn = p_resid = 0.0
+        if dropout is not None:                 # the forward's backbone dropouts (plain layout): same seeds, same masks
+            p_embd, p_attn, p_resid = dropout["embd"], dropout["attn"], dropout["resid"]
+            seeds = dropout["seeds"]
         for li, lay, st in zip(reversed(range(len(self.layers))), reversed(self.layers), reversed(stash)):
+            s_attn, s_r1, s_r2 = seeds[1 + 3 * li: 4 + 3 * li] if dropout is not None else (0, 0, 0)
+            # gradient entering a residual branch = dR masked like the branch's output was (resid dropout)
+            d_mlp = ops.dropout(dRb, p_resid, s_r2) if p_resid > 0 else dRb
             # --- MLP half: x_out = x_mid + W2 act(W1 norm(x_mid))
             if llama:
                 dact = bf(M, self.i_pad)
-                ops.gemm(dRb, lay["wdown_t"], dact, m=M, n=self.i_pad, k=D)
+                ops.gemm(d_mlp, lay["wdown_t"], dact, m=M, n=self.i_pad, k=D)
                 dpre = ops.swiglu_bwd(st["pre"][own], dact, self.i_pad, 128)
                 ops.gemm(dpre, lay["wgu_t"], dH, m=M, n=D, k=2 * self.i_pad)
             else:
                 dact = bf(M, s.inter)
-                ops.gemm(dRb, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
+                ops.gemm(d_mlp, lay["wproj_t"], dact, m=M, n=s.inter, k=D)
                 dpre = ops.gelu_new(st["pre"][own], dact)
                 ops.gemm(dpre, lay["wfc_t"], dH, m=M, n=D, k=s.inter)
             if norm_grads is not None:
@@ -493,8 +520,12 @@ class KernelBackbone:
             norm_bwd(st["x_mid"][own], lay["ln2"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
             # --- attention half: x_mid = x_in + Wo attn(Wqkv norm(x_in))
             datt = bf(M, D)
-            ops.gemm(dRb, lay["wo_t"], datt, m=M, n=D, k=D)
-            if full:
+            d_att = ops.dropout(dRb, p_resid, s_r1) if p_resid > 0 else dRb
+            ops.gemm(d_att, lay["wo_t"], datt, m=M, n=D, k=D)
+            if p_attn > 0:
+                dqkv = ops.attn_causal_dropout_bwd(st["qkv"], st["att"], datt, st["lse"], Bp, L, H, hd, p_attn, s_attn,
+                                                   rope=rope)
+            elif full:
                 dqkv = ops.attn_causal_shared_bwd_full(st["qkv"], st["att"], datt, st["lse"], Bp, Lc, Ls, H, hd, rope=rope)
             elif Lc:
                 dqkv = ops.attn_causal_shared_bwd(st["qkv"], st["att"][own], datt,
@@ -512,6 +543,8 @@ class KernelBackbone:
             if norm_grads is not None:
                 norm_grads[(li, "ln1")] = ops.norm_wgrad(st["x_in"][own], dH, s.eps, layernorm=not llama)
             norm_bwd(st["x_in"][own], lay["ln1"], dH, dR, s.eps, accumulate=True, dx_bf16=dRb)
+        if p_embd > 0:
+            ops.dropout(dR, p_embd, seeds[0], out=dR)
         return dR, lora_grads
 
     def flops_per_token_fwd(self, L: int) -> float:

@@ -127,6 +127,10 @@ class GPT4TS(nn.Module):
             hf.h = hf.h[: self.gpt_layers]
             hf.config.n_layer = len(hf.h)
             object.__setattr__(self, "_hf_model", hf)
+        hf_cfg = getattr(getattr(self, "_hf_model", None), "config", None)
+        # (an injected random-init backbone stands for the "gpt2" checkpoint, whose config carries 0.1 everywhere)
+        self._hf_pdrop = max(float(getattr(hf_cfg, k, 0.1) or 0.0) for k in ("embd_pdrop", "attn_pdrop", "resid_pdrop")) \
+            if hf_cfg is not None else 0.1
         self.device = None
         self._w_cache: dict[str, tuple] = {}
         self.use_cuda_graph = os.environ.get("MTS_CUDA_GRAPH", "1") != "0"      # see graph.GraphReplay
@@ -170,6 +174,8 @@ class GPT4TS(nn.Module):
         bb = self._backbone
         if self.d_model > bb.spec.hidden or self.d_ff > bb.spec.hidden or C > bb.spec.hidden:
             raise MtsError(f"d_model / d_ff / n_features must not exceed the GPT-2 width {bb.spec.hidden}")
+        if self.training:
+            self._warn_dropout_once()
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             names, params = zip(*self._trainable())
             return _GPT4TSFn.apply(self, x, names, *params)                 # autograd path (training-mode forwards)
@@ -177,6 +183,21 @@ class GPT4TS(nn.Module):
             return self._forward_impl(x)
         key = (tuple(x.shape), x.device.index, self.training, tuple((p._version, p.data_ptr()) for p in self.parameters()))
         return self._graph.run(key, x, self._forward_impl)
+
+    def _warn_dropout_once(self):
+        """Known divergence: the reference's GPT4TS regularises training with
+        `DataEmbedding.dropout(training.dropout)` (models/layers/embed.py:113, :120-131) and with GPT-2's own 0.1
+        embd / attn / resid dropouts, live because `model.train()` flips the HF module.  This class trains WITHOUT them
+        (MedTsLLM implements both kinds); say so once instead of silently dropping the regularisation."""
+        if getattr(self, "_warned_dropout", False):
+            return
+        p_cfg = float(_get(_get(self.config, "training"), "dropout", 0.0) or 0.0)
+        if p_cfg > 0 or self._hf_pdrop > 0:
+            import warnings
+            warnings.warn(f"medtsllm_b200.GPT4TS trains without dropout: training.dropout={p_cfg} (DataEmbedding) and the "
+                          f"GPT-2 backbone's own dropouts (p={self._hf_pdrop}) are not applied on the kernel path",
+                          stacklevel=3)
+        self._warned_dropout = True
 
     # ------------------------------------------------------------------------------------------ parameters
     def _mirror_gpt2_parameters(self):

@@ -563,7 +563,8 @@ class MedTsLLM(nn.Module):
     def train_graph_enabled(self) -> bool:
         """Whether this training forward may run on the captured step graphs (train.TrainGraph)."""
         mode = self.use_train_graph
-        if mode in (False, "0", "off") or self._capture is not None or self._dropout_requested > 0:
+        if (mode in (False, "0", "off") or self._capture is not None or self._dropout_requested > 0
+                or self._has_backbone_dropout()):
             return False            # (dropout draws fresh host seeds every step)
         if mode == "auto":
             from . import dp
@@ -663,7 +664,8 @@ class MedTsLLM(nn.Module):
         batches whose prompt rows are shared, so a steady stream of same-shaped batches (the Trainer's val / test
         loops, tasks/forecasting.py:55-78) replays ONE captured CUDA graph: the windows are copied into the
         graph's input buffer, the graph runs, the predictions are copied out."""
-        if not self.use_cuda_graph or self._capture is not None or (self.training and self._dropout_requested > 0):
+        if (not self.use_cuda_graph or self._capture is not None
+                or (self.training and (self._dropout_requested > 0 or self._has_backbone_dropout()))):
             return self._predict_eager(inputs)          # (train-mode dropout draws fresh host seeds every call)
         x_enc = self._check_input(inputs)
         ids = self.prompt_token_ids(inputs)
@@ -689,15 +691,36 @@ class MedTsLLM(nn.Module):
                 ops.sigmoid_(out)
         return out
 
-    def _warn_backbone_dropout(self):
+    def _backbone_dropout(self):
+        """The frozen backbone's own train-mode dropouts (tasks/forecasting.py:18: `model.train()` flips the HF module
+        too, so GPT-2 checkpoints' embd / attn / resid 0.1 are live while the reference trains; Llama-2 carries
+        attention_dropout 0).  Returns {"embd", "attn", "resid", "seeds"} with fresh seeds from torch's generator, or None
+        in evaluation / when every probability is zero.  `self.backbone_dropout = {...}` overrides the HF config (injected
+        backbones carry none)."""
+        if not self.training:
+            return None
+        probs = getattr(self, "backbone_dropout", None)
+        if probs is None:
+            cfg = getattr(self.llm, "config", None)
+            g = lambda k: float(getattr(cfg, k, 0.0) or 0.0) if cfg is not None else 0.0      # noqa: E731
+            if self.backbone_spec.kind == "gpt2":
+                probs = {"embd": g("embd_pdrop"), "attn": g("attn_pdrop"), "resid": g("resid_pdrop")}
+            else:
+                probs = {"embd": 0.0, "attn": g("attention_dropout"), "resid": 0.0}
+        if max(probs["embd"], probs["attn"], probs["resid"]) <= 0:
+            return None
+        n = 1 + 3 * self.backbone_spec.layers
+        return {**probs, "seeds": [int(v) for v in torch.randint(0, 2 ** 62, (n,))]}
+
+    def _has_backbone_dropout(self) -> bool:
+        probs = getattr(self, "backbone_dropout", None)
+        if probs is not None:
+            return max(probs.values()) > 0
         cfg = getattr(self.llm, "config", None)
-        pd = max(float(getattr(cfg, k, 0.0) or 0.0) for k in ("attn_pdrop", "embd_pdrop", "resid_pdrop", "attention_dropout")) \
-            if cfg is not None else 0.0
-        if pd > 0 and not getattr(self, "_warned_bb_dropout", False):
-            import warnings
-            warnings.warn(f"the frozen backbone's own dropouts (p={pd}; live in the reference's train mode because "
-                          "model.train() also flips the HF module) are not applied by the kernel path", stacklevel=3)
-            self._warned_bb_dropout = True
+        if cfg is None:
+            return False
+        keys = ("embd_pdrop", "attn_pdrop", "resid_pdrop") if self.backbone_spec.kind == "gpt2" else ("attention_dropout",)
+        return max(float(getattr(cfg, k, 0.0) or 0.0) for k in keys) > 0
 
     def _check_input(self, inputs):
         x_enc = inputs["x_enc"]
@@ -748,7 +771,10 @@ class MedTsLLM(nn.Module):
                 if c is not None and c[1] is ids:
                     self._ids_cache = (c[0], c[1], ids_dev) + tuple(c[3:])
         # shared-prefix row layout: Lc leading prompt positions once, then Ls = L - Lc own rows per sequence
-        Lc = self._shared_prefix_len(ids, Bp, L)
+        # (not with live backbone dropouts: their masks differ per sample on the prompt rows too)
+        bb_drop = self._backbone_dropout()
+        self._last_backbone_dropout = bb_drop
+        Lc = 0 if bb_drop is not None else self._shared_prefix_len(ids, Bp, L)
         Ls = L - Lc
         X = torch.empty(Lc + Bp * Ls, D, device=dev, dtype=torch.float32)
         ops.prompt_gather(ids_dev, bb.embed, bb.wpe, X, rep=Bp // B, Lp=Lp, L=L, Lc=Lc, B=B)
@@ -765,7 +791,6 @@ class MedTsLLM(nn.Module):
         seeds = [int(v) for v in torch.randint(0, 2 ** 62, (2,))] if p_drop > 0 else None
         self._last_dropout_seeds = seeds
         if p_drop > 0:
-            self._warn_backbone_dropout()
             ops.dropout(enc, p_drop, seeds[0], out=enc)
 
         # K3/K4: reprogramming cross-attention on tcgen05 GEMMs
@@ -812,7 +837,7 @@ class MedTsLLM(nn.Module):
         # backbone
         layer_stash = [] if stash is not None else None
         hid, x_final = bb.forward(X, Bp, L, stash=layer_stash, lora=self.llm if self.lora_enabled else None,
-                                  Lc=Lc)                                          # bf16 rows like X, final norm applied
+                                  Lc=Lc, dropout=bb_drop)                         # bf16 rows like X, final norm applied
         if cap is not None:
             cap["llm"] = self._expand_rows(hid, Bp, L, Lc)
             cap["shared_prefix"] = Lc
@@ -848,7 +873,8 @@ class MedTsLLM(nn.Module):
         if stash is not None:
             stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
                          hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Lc=Lc, Bp=Bp, B=B, N0=N0,
-                         scale=scale, denorm=denorm, concat=concat, Y=Y, head=head, Pd=Pd, p_drop=p_drop, seeds=seeds)
+                         scale=scale, denorm=denorm, concat=concat, Y=Y, head=head, Pd=Pd, p_drop=p_drop, seeds=seeds,
+                         bb_drop=bb_drop)
         return out
 
 

@@ -36,7 +36,7 @@ def _ptr(t):
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
          block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0,
-         rope_prefix=0, aux=None, a_lo=None, b_lo=None, round_tf32=False):
+         rope_prefix=0, aux=None, a_lo=None, b_lo=None, round_tf32=False, drop_p=0.0, drop_seed=0):
     """Raw mts_gemm: D[b] = epi(alpha * A[b] @ B[b]^T + bias).  Offsets/strides in elements.
     a / b bf16 (default path) or both fp32 (evaluation parity modes: tcgen05 kind::tf32; with `a_lo` / `b_lo` the
     3xTF32 fp32-grade contraction on split operands)."""
@@ -69,6 +69,7 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.alpha = alpha
     args.ab_dtype = MTS_F32 if ab == torch.float32 else MTS_BF16
     args.round_tf32 = 1 if round_tf32 else 0
+    args.drop_p, args.drop_seed = float(drop_p), int(drop_seed) & (2 ** 64 - 1)
     if (a_lo is None) != (b_lo is None):
         raise MtsError("a_lo and b_lo go together (3xTF32 split)")
     if a_lo is not None:
@@ -212,6 +213,36 @@ def attn_causal(qkv, Bp, L, H, hd, *, rope=None, scale=None, want_lse=False, out
     _lib.call("mts_attn_causal", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), _ptr(lse),
               Bp, L, H, hd, scale, _stream())
     return (out, lse) if want_lse else out
+
+
+def attn_causal_dropout(qkv, Bp, L, H, hd, p, seed, *, scale=None, out=None):
+    """attn_causal with dropout (probability p, counter-based mask from `seed`) on the attention probabilities; q / k
+    already rotated.  Returns (out, lse) — training only."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    if not qkv.is_contiguous() or qkv.shape != (Bp * L, 3 * H * hd):
+        raise MtsError("attn_causal_dropout needs contiguous qkv [Bp*L, 3*H*hd]")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    if out is None:
+        out = torch.empty(Bp * L, H * hd, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(Bp, H, L, device=qkv.device, dtype=torch.float32)
+    _lib.call("mts_attn_causal_dropout", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bp, L, H, hd, scale, float(p),
+              int(seed) & (2 ** 64 - 1), _stream())
+    return out, lse
+
+
+def attn_causal_dropout_bwd(qkv, out, dout, lse, Bp, L, H, hd, p, seed, *, rope=None, scale=None):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
+    _chk(lse, torch.float32, "lse")
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(Bp, H, L, device=qkv.device, dtype=torch.float32)
+    cos, sin = rope if rope is not None else (None, None)
+    _lib.call("mts_attn_causal_dropout_bwd", qkv.data_ptr(), _ptr(cos), _ptr(sin), out.data_ptr(), dout.data_ptr(),
+              lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), Bp, L, H, hd, scale, float(p), int(seed) & (2 ** 64 - 1),
+              _stream())
+    return dqkv
 
 
 def attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, *, scale=None, want_lse=False, out=None):

@@ -274,7 +274,7 @@ def _backward_part1(m, st, dout, use_dp):
 
     # ---- frozen backbone (dgrad only)
     dR, lora_grads = bb.backward(dhid, st["x_final"], st["layers"], B, L,
-                                 lora=m.llm if m.lora_enabled else None, Lc=Lc)   # fp32 [B*Ls, D]
+                                 lora=m.llm if m.lora_enabled else None, Lc=Lc, dropout=st.get("bb_drop"))   # fp32 [B*Ls, D]
 
     # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
     if mode in ("concat", "univariate", "independent", "merge-end"):

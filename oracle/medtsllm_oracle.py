@@ -131,14 +131,18 @@ def apply_rope(t, cos, sin):
     return t * cos + rot * sin
 
 
-def causal_attention(q, k, v, scale):
+def causal_attention(q, k, v, scale, prob_mask=None):
     """HF:models/llama/modeling_llama.py:199-221 / HF:models/gpt2/modeling_gpt2.py:54-72 — eager,
-    causal, no padding mask (models/medtsllm.py:350 passes none)."""
+    causal, no padding mask (models/medtsllm.py:350 passes none).  `prob_mask` [B, H, L, L]: the multiplicative
+    dropout mask (0 or 1/(1-p)) HF applies to the probabilities in train mode (attn_dropout, gpt2 :67-68; llama :217)."""
     L = q.shape[-2]
     s = (q @ k.transpose(-1, -2)) * scale
     mask = torch.ones(L, L, dtype=torch.bool, device=q.device).tril()
     s = s.masked_fill(~mask, torch.finfo(s.dtype).min)
-    return torch.softmax(s.float(), dim=-1).to(q.dtype) @ v
+    p = torch.softmax(s.float(), dim=-1).to(q.dtype)
+    if prob_mask is not None:
+        p = p * prob_mask
+    return p @ v
 
 
 def lora_delta(h, lora, layer: int, t: int):
@@ -150,12 +154,12 @@ def lora_delta(h, lora, layer: int, t: int):
 
 
 def llama_forward(x, sd, *, n_layers: int, n_heads: int, eps: float, theta: float = 10000.0,
-                  return_hidden: bool = False, lora=None):
+                  return_hidden: bool = False, lora=None, dropout=None):
     """HF LlamaModel.forward on inputs_embeds (HF:models/llama/modeling_llama.py:375-425, decoder
     layer :303-332, attention :251-300, MLP :171-184).  `sd` uses HF parameter names."""
     B, L, D = x.shape
     hd = D // n_heads
-    cos, sin = rope_tables(L, hd, theta)
+    cos, sin = (t.to(x.device) for t in rope_tables(L, hd, theta))
     hidden = [x]
     for i in range(n_layers):
         p = f"layers.{i}."
@@ -168,7 +172,8 @@ def llama_forward(x, sd, *, n_layers: int, n_heads: int, eps: float, theta: floa
             v = v + lora_delta(h, lora, i, 1)
         q, k, v = (t.view(B, L, n_heads, hd).transpose(1, 2) for t in (q, k, v))
         q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
-        a = causal_attention(q, k, v, hd ** -0.5).transpose(1, 2).reshape(B, L, D)
+        a = causal_attention(q, k, v, hd ** -0.5, dropout["attn"][i] if dropout is not None else None)
+        a = a.transpose(1, 2).reshape(B, L, D)
         x = x + F.linear(a, sd[p + "self_attn.o_proj.weight"])
         h = rmsnorm(x, sd[p + "post_attention_layernorm.weight"], eps)
         g = F.linear(h, sd[p + "mlp.gate_proj.weight"])
@@ -191,12 +196,16 @@ def conv1d_hf(x, w, b):
 
 
 def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, return_hidden: bool = False,
-                 lora=None):
-    """HF GPT2Model.forward on inputs_embeds, eval mode (HF:models/gpt2/modeling_gpt2.py:522-636:
-    + wpe[0..L) :584-585; block :262-309; attention :144-236; MLP :238-243; ln_f :628)."""
+                 lora=None, dropout=None):
+    """HF GPT2Model.forward on inputs_embeds (HF:models/gpt2/modeling_gpt2.py:522-636: + wpe[0..L) :584-585; block
+    :262-309; attention :144-236; MLP :238-243; ln_f :628).  `dropout` = the train-mode masks (multiplicative, 0 or
+    1/(1-p)): {"embd": [B,L,D] (:612), "attn": [layers][B,H,L,L] (:67-68), "resid_attn" / "resid_mlp": [layers][B,L,D]
+    (:233, :243)}; None = eval mode."""
     B, L, D = x.shape
     hd = D // n_heads
     x = x + sd["wpe.weight"][:L][None]
+    if dropout is not None:
+        x = x * dropout["embd"]
     hidden = [x]
     for i in range(n_layers):
         p = f"h.{i}."
@@ -205,11 +214,13 @@ def gpt2_forward(x, sd, *, n_layers: int, n_heads: int, eps: float = 1e-5, retur
         if lora is not None:                      # peft default target for GPT-2: the fused c_attn
             qkv = qkv + lora_delta(h, lora, i, 0)
         q, k, v = (t.view(B, L, n_heads, hd).transpose(1, 2) for t in qkv.split(D, dim=-1))
-        a = causal_attention(q, k, v, 1.0 / math.sqrt(hd)).transpose(1, 2).reshape(B, L, D)
-        x = x + conv1d_hf(a, sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
+        a = causal_attention(q, k, v, 1.0 / math.sqrt(hd), dropout["attn"][i] if dropout is not None else None)
+        a = conv1d_hf(a.transpose(1, 2).reshape(B, L, D), sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
+        x = x + (a * dropout["resid_attn"][i] if dropout is not None else a)
         h = F.layer_norm(x, (D,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
         h = gelu_new(conv1d_hf(h, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
-        x = x + conv1d_hf(h, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        h = conv1d_hf(h, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        x = x + (h * dropout["resid_mlp"][i] if dropout is not None else h)
         hidden.append(x)
     out = F.layer_norm(x, (D,), sd["ln_f.weight"], sd["ln_f.bias"], eps)
     return (out, hidden) if return_hidden else out
@@ -237,7 +248,7 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     xn = revin_norm(x_enc, mean, stdev).permute(0, 2, 1).contiguous()
     enc = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
     N = enc.shape[1]
-    if dropout_masks is not None:       # PatchEmbedding.dropout (models/layers/embed.py:197), mask in [B*C, N, dm] order
+    if dropout_masks is not None and "patch" in dropout_masks:   # PatchEmbedding.dropout (models/layers/embed.py:197), [B*C, N, dm]
         enc = enc * dropout_masks["patch"]
     stages["patch_embedding"] = enc
     mode = spec["covariate_mode"]
@@ -250,7 +261,7 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     source = mapping(word_emb, adapters["mapping_layer.weight"], adapters["mapping_layer.bias"])
     stages["source_embeddings"] = source
     enc = reprogramming(enc, source, adapters, spec["n_heads"],
-                        attn_mask=dropout_masks["reprog"] if dropout_masks is not None else None)   # [B or B*C, N, D]
+                        attn_mask=dropout_masks.get("reprog") if dropout_masks is not None else None)   # [B or B*C, N, D]
     stages["reprogramming_layer"] = enc                                # (the module's own output, pre-merge)
     D = enc.shape[-1]
     if mode == "add":                                                  # models/medtsllm.py:284-286
@@ -269,12 +280,14 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     Bp = enc.shape[0]
     llm_in = torch.cat([prompt, enc], dim=1)
     stages["llm_input"] = llm_in
+    bb_masks = dropout_masks.get("backbone") if dropout_masks is not None else None
     if spec["backbone"] == "llama":
         dec, hidden = llama_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
-                                    eps=spec["eps"], theta=spec.get("rope_theta", 10000.0), return_hidden=True, lora=lora)
+                                    eps=spec["eps"], theta=spec.get("rope_theta", 10000.0), return_hidden=True, lora=lora,
+                                    dropout=bb_masks)
     else:
         dec, hidden = gpt2_forward(llm_in, backbone_sd, n_layers=spec["n_layers"], n_heads=spec["llm_heads"],
-                                   eps=spec["eps"], return_hidden=True, lora=lora)
+                                   eps=spec["eps"], return_hidden=True, lora=lora, dropout=bb_masks)
     stages["llm"] = dec
     stages["llm.hidden_states"] = hidden
 

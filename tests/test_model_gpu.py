@@ -295,6 +295,69 @@ def test_training_with_dropout(tmp_path, cuda):
         assert torch.equal(model(inputs), model(inputs)) and model._last_dropout_seeds is None
 
 
+@pytest.mark.parametrize("name", ["gpt2_anomaly_concat", "llama_seg_concat"])
+def test_training_with_backbone_dropout(name, tmp_path, cuda):
+    """The frozen backbone's own dropouts (GPT-2 checkpoints: embd / attn / resid 0.1, live in the reference's train mode
+    because tasks/forecasting.py:18 flips the HF module; Llama: attention_dropout) on the kernel path: the counter-based
+    masks are read back from the step's seeds and replayed in the oracle (whose placement of them is pinned against live
+    HF, tests/test_oracle.py), so forward and adapter gradients compare like the deterministic case."""
+    from medtsllm_b200 import ops
+    from medtsllm_b200.model import MedTsLLM
+    from oracle import medtsllm_oracle as O
+    from _fixtures import oracle_spec
+    fix = load_case(name)
+    llm_dir = materialize_llm_dir(fix, tmp_path / "llm")
+    model = MedTsLLM(Cfg(config_for(fix, llm_dir)), Dataset(fix["dataset"]))
+    model.load_state_dict(fix["adapters"], strict=True)
+    model = model.to(cuda).train()
+    p = 0.1
+    gpt2 = fix["kind"] == "gpt2"
+    model.backbone_dropout = {"embd": p, "attn": p, "resid": p} if gpt2 else {"embd": 0.0, "attn": p, "resid": 0.0}
+    inputs = {k: (v.to(cuda) if isinstance(v, torch.Tensor) else v) for k, v in fix["inputs"].items()}
+    torch.manual_seed(3)
+    out = model(inputs)
+    drop = model._last_backbone_dropout
+    wgt = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * wgt.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    spec = oracle_spec(fix)
+    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    B = fix["inputs"]["x_enc"].shape[0]
+    L = len(ids[0]) + model.n_patches
+    D, H, n_layers = model.d_llm, spec["llm_heads"], spec["n_layers"]
+    seeds = drop["seeds"]
+    assert len(seeds) == 1 + 3 * n_layers
+
+    def mask(shape, prob, seed):
+        if prob <= 0:
+            return torch.ones(shape)
+        keep = ops.dropout(torch.ones(shape, device=cuda), prob, seed) != 0
+        assert abs(1 - keep.float().mean().item() - prob) < 2e-2
+        return keep.float().cpu() / (1 - prob)
+
+    masks = {"attn": [mask((B, H, L, L), p, seeds[1 + 3 * i]) for i in range(n_layers)]}
+    if gpt2:
+        masks.update(embd=mask((B, L, D), p, seeds[0]),
+                     resid_attn=[mask((B, L, D), p, seeds[2 + 3 * i]) for i in range(n_layers)],
+                     resid_mlp=[mask((B, L, D), p, seeds[3 + 3 * i]) for i in range(n_layers)])
+    ad = {k: v.clone().requires_grad_(True) for k, v in fix["adapters"].items()}
+    sd = {k: v.float() for k, v in fix["backbone_state"].items()}
+    ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, spec, training=True, dropout_masks={"backbone": masks})
+    e = _rel_l2(out, ref)
+    assert e < 2e-2, e
+    assert _rel_l2(out, fix["stages"]["output_train"]) > 5e-3          # the dropouts really changed the forward
+    (ref * wgt).sum().backward()
+    for k, prm in model.named_parameters():
+        if k in ("reprogramming_layer.key_projection.bias",):
+            continue
+        eg = _rel_l2(prm.grad, ad[k].grad)
+        assert eg < (1.5e-1 if k == "mapping_layer.bias" else 5e-2), (k, eg)
+    # evaluation: no dropout, shared prompt prefix and graph replay are back
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model(inputs), model(inputs)) and model._last_backbone_dropout is None
+
+
 def test_edge_inputs_empty_prompt_2d_input_batch_of_one(tmp_path, cuda):
     """Edge cases of the reference path: no prompt at all (models/medtsllm.py:338-339 -> [B, 0, D]), a 2-D univariate
     window tensor (:264-265), and a batch of one."""

@@ -68,6 +68,54 @@ def test_oracle_backbone_matches_live_hf(name):
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("kind", ["gpt2", "llama"])
+def test_oracle_train_mode_backbone_dropout_matches_live_hf(kind, monkeypatch):
+    """The frozen backbone's own dropouts are live in the reference's train mode (tasks/forecasting.py:18 flips the HF
+    module): pin WHERE the oracle applies them — embd, attention probabilities, both residual branches — against
+    HuggingFace itself run in train mode, by routing every torch dropout call of the HF forward through recorded masks
+    and replaying the same masks in the oracle."""
+    import transformers
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    D, H, Lyr, L, B, p = 64, 2, 2, 10, 3, 0.25
+    if kind == "gpt2":
+        cfg = transformers.GPT2Config(n_embd=D, n_layer=Lyr, n_head=H, vocab_size=8, n_positions=32, attn_pdrop=p,
+                                      embd_pdrop=p, resid_pdrop=p)
+        hf = transformers.GPT2Model(cfg)
+    else:
+        cfg = transformers.LlamaConfig(hidden_size=D, intermediate_size=96, num_hidden_layers=Lyr, num_attention_heads=H,
+                                       num_key_value_heads=H, vocab_size=8, rms_norm_eps=1e-5, attention_dropout=p)
+        hf = transformers.LlamaModel(cfg)
+    hf.config._attn_implementation = "eager"
+    hf.train()
+    x = torch.randn(B, L, D)
+    calls = []
+    g = torch.Generator().manual_seed(1)
+
+    def recorded_dropout(inp, p=0.5, training=True, inplace=False):
+        if not training or p == 0:
+            return inp
+        mask = (torch.rand(inp.shape, generator=g) >= p).to(inp.dtype) / (1 - p)
+        calls.append(mask)
+        return inp * mask
+
+    monkeypatch.setattr(F, "dropout", recorded_dropout)
+    monkeypatch.setattr(torch.nn.functional, "dropout", recorded_dropout)
+    with torch.no_grad():
+        ref = hf(inputs_embeds=x).last_hidden_state
+    monkeypatch.undo()
+    sd = {k: v for k, v in hf.state_dict().items()}
+    if kind == "gpt2":
+        assert len(calls) == 1 + 3 * Lyr                         # embd, then per block: attention probs, attn resid, mlp resid
+        masks = {"embd": calls[0], "attn": calls[1::3], "resid_attn": calls[2::3], "resid_mlp": calls[3::3]}
+        assert masks["attn"][0].shape == (B, H, L, L) and masks["resid_mlp"][1].shape == (B, L, D)
+        got = O.gpt2_forward(x, sd, n_layers=Lyr, n_heads=H, dropout=masks)
+    else:
+        assert len(calls) == Lyr and calls[0].shape == (B, H, L, L)
+        got = O.llama_forward(x, sd, n_layers=Lyr, n_heads=H, eps=1e-5, dropout={"attn": calls})
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5)
+
+
 @pytest.mark.parametrize("T,P,S", [(96, 16, 8), (100, 16, 8), (336, 16, 8), (512, 16, 8), (1024, 16, 8), (17, 16, 8), (64, 8, 4)])
 def test_patch_index_is_unfold_of_replication_padded(T, P, S):
     """Bit-exact index contract (models/layers/embed.py:155-163,188-189; n_patches models/medtsllm.py:52)."""
