@@ -305,7 +305,9 @@ int mts_softmax_rows(const float* s, uint16_t* p, int64_t rows, int n, float sca
 /* K5  prompt gather + left padding + (GPT-2) position embedding, building the backbone input
  *     (ref: models/medtsllm.py:299-311 encode_text/pad_sequence, :331-337, :349 cat;
  *      HF:models/gpt2/modeling_gpt2.py:584-585 wpe add).
- *   ids  int32 [B, Lp]  (already left-padded with the pad id by the host)
+ *   ids  int32 [B, Lp]  (already left-padded with the pad id by the host); a NEGATIVE id marks a position that is
+ *        not a token — a time-series example part of the prompt (`encode_part`'s tensor branch, models/medtsllm.py:
+ *        313-319): its row is written as zero (+wpe) and filled by the reprogramming out-projection afterwards
  *   emb  fp32 [V, D] input-embedding table
  *   wpe  fp32 [>=L, D] or NULL
  *   x    fp32 [B*rep, L, D] out: rows [0,Lp) = emb[ids] (+wpe), rows [Lp,L) = 0 (+wpe);

@@ -234,7 +234,12 @@ prompt_gather_kernel(const int32_t* __restrict__ ids, const float* __restrict__ 
   }
   const int D4 = D >> 2;
   const float4* src = nullptr;
-  if (l < Lp) src = reinterpret_cast<const float4*>(emb + (int64_t)ids[(int64_t)b * Lp + l] * D);
+  if (l < Lp) {
+    // a negative id marks a prompt position that is not a token (a time-series example part, models/medtsllm.py:
+    // 313-319): the row starts as zero (+ wpe) and the reprogramming out-projection accumulates onto it
+    const int32_t id = ids[(int64_t)b * Lp + l];
+    if (id >= 0) src = reinterpret_cast<const float4*>(emb + (int64_t)id * D);
+  }
   const float4* pe = wpe ? reinterpret_cast<const float4*>(wpe + (int64_t)l * D) : nullptr;
   for (int i = threadIdx.x; i < D4; i += blockDim.x) {
     float4 v = src ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);

@@ -377,17 +377,18 @@ class MedTsLLM(nn.Module):
         if not (flags["dataset"] or flags["clip"] or flags["input_stats"] or flags["task"] or flags["examples"]):
             return [[] for _ in range(bs)]
         dataset_prompt = f"Dataset: {self.dataset_description}" if flags["dataset"] else ""
-        if flags["examples"]:
-            raise NotImplementedError("prompting.examples (time-series example parts) is listed as next in DESIGN.md")
+        # prompting.examples (:402-405, datasets/ecg.py:140-166): per sample a tuple of parts, strings or time-series
+        # tensors [1, T_ex, C] that `encode_part` (:313-319) runs through encode_ts like the window itself
+        example_prompts = inputs["examples"] if flags["examples"] else [("",)] * bs
         clip_prompts = inputs.get("descriptions", [""] * bs) if flags["clip"] else [""] * bs
         stats_prompts = self.build_input_stats_prompt(flags, inputs) if flags["input_stats"] else [""] * bs
         task_prompt = f"Task: {self.task_description}" if flags["task"] else ""
         bos = self.tokenizer.bos_token if self.tokenizer.bos_token is not None else ""
         prompts = []
         for b in range(bs):
-            parts = [bos, dataset_prompt, clip_prompts[b], stats_prompts[b], task_prompt, "Time series:"]
-            parts = [p for p in parts if p != ""]
-            parts = [(p + " " if i != 0 else p) for i, p in enumerate(parts)]
+            parts = [bos, dataset_prompt, *example_prompts[b], clip_prompts[b], stats_prompts[b], task_prompt, "Time series:"]
+            parts = [p for p in parts if not (isinstance(p, str) and p == "")]
+            parts = [(p + " " if isinstance(p, str) and i != 0 else p) for i, p in enumerate(parts)]
             prompts.append(parts)
         return prompts
 
@@ -468,19 +469,40 @@ class MedTsLLM(nn.Module):
         return ids
 
     def prompt_token_ids(self, inputs):
-        """Host token-id table [B, Lp] (int32, LEFT-padded with the pad id, models/medtsllm.py:304-311)."""
+        """Host token-id table [B, Lp] (int32, LEFT-padded with the pad id, models/medtsllm.py:304-311).  Positions that
+        hold a time-series example part instead of a token carry a negative id (-(b+1): distinct per sample, so they
+        never count as a shared prefix); the parts themselves hang off the table as `.example_segments` =
+        [(sample, first position, tensor [1, T_ex, C])]."""
         prompts = self.build_prompt(inputs)
-        key = tuple(tuple(parts) for parts in prompts)
-        if self._ids_cache is not None and self._ids_cache[0] == key:       # static prompts: same table every batch
+        has_ts = any(isinstance(p, torch.Tensor) for parts in prompts for p in parts)
+        key = None if has_ts else tuple(tuple(parts) for parts in prompts)
+        if key is not None and self._ids_cache is not None and self._ids_cache[0] == key:   # static prompts: same table every batch
             return self._ids_cache[1]
-        per_sample = [[t for part in parts for t in self._tokenize_part(part)] for parts in prompts]
+        per_sample, segs = [], []
+        for b, parts in enumerate(prompts):
+            row = []
+            for part in parts:
+                if isinstance(part, torch.Tensor):
+                    if self.covariate_mode not in ("concat", "univariate"):
+                        raise NotImplementedError("prompting.examples needs covariate_mode concat / univariate (the "
+                                                  "reference's torch.cat of prompt parts breaks for the others, :332)")
+                    ts = part.unsqueeze(-1) if part.ndim == 2 else part
+                    if ts.ndim != 3 or ts.shape[0] != 1 or ts.shape[2] != self.n_features:
+                        raise ValueError(f"example part must be [1, T, {self.n_features}], got {tuple(part.shape)}")
+                    n = ops.n_patches(ts.shape[1], self.patch_len, self.stride)
+                    segs.append((b, len(row), ts))
+                    row.extend([-(b + 1)] * n)
+                else:
+                    row.extend(self._tokenize_part(part))
+            per_sample.append(row)
         Lp = max((len(p) for p in per_sample), default=0)
         pad = self.tokenizer.pad_token_id if self.tokenizer is not None else 0
         table = torch.full((len(per_sample), Lp), pad if pad is not None else 0, dtype=torch.int32)
         for b, ids in enumerate(per_sample):
             if ids:
                 table[b, Lp - len(ids):] = torch.tensor(ids, dtype=torch.int32)
-        self._ids_cache = (key, table, None)     # (+ shared-prefix length once _shared_prefix_len has run)
+        table.example_segments = [(b, Lp - len(per_sample[b]) + off, ts) for b, off, ts in segs]
+        self._ids_cache = (key if key is not None else object(), table, None)   # (+ shared-prefix length once measured)
         return table
 
     def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int, precise: bool = False) -> int:
@@ -788,18 +810,39 @@ class MedTsLLM(nn.Module):
         # train-mode dropout on the patch embeddings and the reprogramming attention (models/layers/embed.py:197,
         # models/medtsllm.py:587); seeds come from torch's CPU generator so torch.manual_seed reproduces a run
         p_drop = self._dropout_requested if self.training else 0.0
-        seeds = [int(v) for v in torch.randint(0, 2 ** 62, (2,))] if p_drop > 0 else None
-        self._last_dropout_seeds = seeds
+        seeds = [int(v) for v in torch.randint(0, 2 ** 62, (3,))] if p_drop > 0 else None
+        self._last_dropout_seeds = seeds[:2] if seeds is not None else None
         if p_drop > 0:
             ops.dropout(enc, p_drop, seeds[0], out=enc)
+
+        # time-series example parts of the prompt (`encode_part`'s tensor branch, models/medtsllm.py:313-319): each goes
+        # through encode_ts like the window itself — own RevIN statistics, patches, token conv — and its patches join
+        # the reprogramming rows of the batch (the layer is row-wise); the out-projection writes them to their prompt rows
+        rows_main = enc.shape[0] * N0
+        segs = getattr(ids, "example_segments", None) or []
+        ex_meta = []
+        enc_all = enc.view(rows_main, -1)
+        if segs:
+            conv_w = self.patch_embedding.value_embedding.tokenConv.weight.detach()
+            ex_encs, r0 = [], rows_main
+            for (b, pos, ts) in segs:
+                ts = ts.to(dev, torch.float32).contiguous()
+                e, _, m_e, s_e = ops.revin_patch_embed(ts, conv_w, self.patch_len, self.stride, concat=concat)
+                ex_encs.append(e.view(e.shape[1], -1))
+                ex_meta.append(dict(b=b, pos=pos, n=e.shape[1], r0=r0, ts=ts, mean=m_e, std=s_e))
+                r0 += e.shape[1]
+            ex_cat = torch.cat(ex_encs)
+            if p_drop > 0:
+                ops.dropout(ex_cat, p_drop, seeds[2], out=ex_cat)
+            enc_all = torch.cat([enc_all, ex_cat])
 
         # K3/K4: reprogramming cross-attention on tcgen05 GEMMs
         source, K, Vt = self._source_kv()
         S = self.num_tokens
-        rows = enc.shape[0] * N0
+        rows = enc_all.shape[0]
         wq = self._bf16_weight("wq", rl.query_projection.weight)
         Q = torch.empty(rows, HE, device=dev, dtype=torch.bfloat16)
-        ops.gemm(enc, wq, Q, m=rows, n=HE, k=self.d_model, ldb=wq.shape[1],
+        ops.gemm(enc_all, wq, Q, m=rows, n=HE, k=self.d_model, ldb=wq.shape[1],
                  bias=rl.query_projection.bias.detach(), bias_axis=BIAS_N)
         scores = torch.empty(H, rows, S, device=dev, dtype=torch.float32)
         ops.gemm(Q, K, scores, m=rows, n=S, k=E, batch=H, lda=HE, ldb=HE, a_bs=E, b_bs=E, d_bs=rows * S)
@@ -815,6 +858,10 @@ class MedTsLLM(nn.Module):
             # one sequence per (sample[, feature]): rows of batch i land at X[i, Lp:, :]
             ops.gemm(O, wo, X, m=N, n=D, k=HE, batch=Bp, a_bs=N * HE, b_bs=0, d_bs=Ls * D, ldd=D, d_off=Lp * D,
                      ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N, epilogue=EPI_RESID_ADD)
+            for ex in ex_meta:      # example patches -> their rows inside the prompt (zero + wpe from the gather)
+                ops.gemm(O, wo, X, m=ex["n"], n=D, k=HE, a_off=ex["r0"] * HE, ldd=D,
+                         d_off=(Lc + ex["b"] * Ls + ex["pos"] - Lc) * D, ldb=wo.shape[1], bias=bo, bias_axis=BIAS_N,
+                         epilogue=EPI_RESID_ADD)
         elif mode == "interleave":
             # token order n-major, c-minor (models/medtsllm.py:292-295): feature c writes rows Lp + n*C + c
             for c in range(C):
@@ -874,7 +921,7 @@ class MedTsLLM(nn.Module):
             stash.update(x_enc=x_enc, mean=mean, std=std, enc=enc, source=source, K=K, Vt=Vt, Q=Q, P=P, O=O,
                          hid=hid, x_final=x_final, flat=flat, layers=layer_stash, Lp=Lp, L=L, Lc=Lc, Bp=Bp, B=B, N0=N0,
                          scale=scale, denorm=denorm, concat=concat, Y=Y, head=head, Pd=Pd, p_drop=p_drop, seeds=seeds,
-                         bb_drop=bb_drop)
+                         bb_drop=bb_drop, enc_all=enc_all, ex_meta=ex_meta, rows_main=rows_main)
         return out
 
 

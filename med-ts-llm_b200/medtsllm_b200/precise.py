@@ -109,6 +109,8 @@ def forward_precise(m, inputs, ids=None):
 
     if ids is None:
         ids = m.prompt_token_ids(inputs)
+    if getattr(ids, "example_segments", None):
+        raise NotImplementedError("prompting.examples is implemented on the bf16 path only (set MTS_PRECISION=bf16)")
     Lp = ids.shape[1]
     L = Lp + N
     ids_dev = ids.to(dev, non_blocking=True) if Lp > 0 else None

@@ -213,7 +213,9 @@ def _backward_part1(m, st, dout, use_dp):
     row0 = Lc if (Lc and m.lora_enabled) else 0    # ... unless LoRA needs the prefix rows too (all rows then)
     own_off = Lp - Lc + row0    # first patch row of sequence 0 in dhid / dR
     mode = m.covariate_mode
-    R = st["enc"].shape[0] * N0                 # reprogrammed rows, ordered (sample, [feature,] patch)
+    R_main = st["enc"].shape[0] * N0            # reprogrammed rows of the windows, ordered (sample, [feature,] patch)
+    ex_meta = st.get("ex_meta") or []           # + the patches of time-series example parts inside the prompts
+    R = st["enc_all"].shape[0] if ex_meta else R_main
     dm = m.d_model
     rl = m.reprogramming_layer
     f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)     # noqa: E731
@@ -278,7 +280,11 @@ def _backward_part1(m, st, dout, use_dp):
 
     # ---- reprogramming out-projection: rows (sample, [feature,] patch) of O W_o^T + b_o feed X's patch rows
     if mode in ("concat", "univariate", "independent", "merge-end"):
-        dxp = ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D, in_off=own_off * D)   # bf16 [R, D]
+        dxp = bf(R, D)
+        ops.cast_rows(dR, batch=B, rows=N, cols=D, ld_in=D, in_bs=Ls * D, in_off=own_off * D, out=dxp, ld_out=D)
+        for ex in ex_meta:       # gradient rows of the example patches: prompt position `pos` of sample b
+            ops.cast_rows(dR, rows=ex["n"], cols=D, ld_in=D, in_off=(row0 + ex["b"] * Ls + ex["pos"] - Lc) * D,
+                          out=dxp, ld_out=D, out_off=ex["r0"] * D)
     elif mode == "interleave":
         dxp = bf(R, D)
         for c in range(C):       # feature c owns rows Lp + n*C + c
@@ -337,17 +343,24 @@ def _backward_part1(m, st, dout, use_dp):
 
     # ---- query projection + front end
     ops.colsum(dQ, out=gv("reprogramming_layer.query_projection.bias"))
-    enc2 = st["enc"].view(R, dm)
+    enc2 = st["enc_all"] if ex_meta else st["enc"].view(R, dm)
     ops.gemm(_t(dQ), _t(enc2), gv("reprogramming_layer.query_projection.weight"), m=HE, n=dm, k=R, lda=Rp, ldb=Rp)
     wq = m._bf16_weight("wq", rl.query_projection.weight)                  # [HE, ceil8(dm)]
     wq_t = ops.transpose_strided(wq, rows=HE, cols=dm, ld_in=wq.shape[1])  # [dm, HE]
     denc = f32(R, dm)
     ops.gemm(dQ, wq_t, denc, m=R, n=dm, k=HE, ldb=wq_t.shape[1])
+    denc_main = denc[:R_main]
     if p_drop > 0:
-        ops.dropout(denc, p_drop, seeds[0], out=denc)                      # patch-embedding dropout mask
-    ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc.view(st["enc"].shape),
-                              m.patch_len, m.stride, m.d_patch, concat=st["concat"],
-                              out=gv("patch_embedding.value_embedding.tokenConv.weight"))
+        ops.dropout(denc_main, p_drop, seeds[0], out=denc_main)            # patch-embedding dropout mask
+        if ex_meta:
+            ops.dropout(denc[R_main:], p_drop, seeds[2], out=denc[R_main:])
+    g_conv = gv("patch_embedding.value_embedding.tokenConv.weight")
+    ops.revin_patch_embed_bwd(st["x_enc"], st["mean"], st["std"], denc_main.view(st["enc"].shape),
+                              m.patch_len, m.stride, m.d_patch, concat=st["concat"], out=g_conv)
+    for ex in ex_meta:           # the conv weight also sees the example parts (each with its own RevIN statistics)
+        g_conv += ops.revin_patch_embed_bwd(ex["ts"], ex["mean"], ex["std"],
+                                            denc[ex["r0"]:ex["r0"] + ex["n"]].view(1, ex["n"], dm).contiguous(),
+                                            m.patch_len, m.stride, m.d_patch, concat=st["concat"])
 
     # ---- key / value projections of the prototypes
     source = st["source"]

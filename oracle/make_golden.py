@@ -79,6 +79,13 @@ CASES = {
         kind="gpt2", llm=dict(hidden_size=128, heads=2, layers=1, vocab_size=256),
         task="anomaly_detection", T=40, pred=40, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="weighted-average",
         description="Synthetic three channel series .", prompting=dict(dataset=True, task=True, clip=False, input_stats=False)),
+    # prompting.examples (models/medtsllm.py:402-405, :313-319; datasets/ecg.py:140-166): every sample carries
+    # ("Example segment:", tensor [1, T_ex, C]) with its own T_ex -> ragged prompts, time-series rows inside the prompt
+    "llama_seg_examples": dict(
+        kind="llama", llm=dict(hidden_size=128, heads=2, layers=2, intermediate_size=256, vocab_size=384),
+        task="segmentation", T=96, pred=96, C=2, B=3, num_tokens=128, d_ff=64, covariate_mode="concat",
+        description="ECG recordings with annotated beats .", example_lens=[40, 56, 24],
+        prompting=dict(dataset=True, task=True, clip=False, input_stats=False, examples=True)),
     "llama_forecast_interleave": dict(
         kind="llama", llm=dict(hidden_size=128, heads=2, layers=1, intermediate_size=256, vocab_size=256),
         task="forecasting", T=48, pred=16, C=3, B=2, num_tokens=64, d_ff=64, covariate_mode="interleave",
@@ -102,7 +109,7 @@ def make_case(name: str, c: dict, out_path: Path):
                  "Reconstruct the past steps of data as accurately as possible using the following information .",
                  "Classify Identify the change points in to segment sequence . Time series:",
                  "Input statistics ( feature 0 ): min value = , max median the trend of input is upward downward top 5 lags are"]
-        texts += c.get("descriptions", [])
+        texts += c.get("descriptions", []) + ["Example segment:"]
         texts += [str(c["T"]), str(c["pred"])]
         llm_dir = H.build_llm_dir(c["kind"], tmp / "llm", texts, seed=zlib.crc32(name.encode()) % 1000, **c["llm"])
         # round the backbone to bf16-representable values so that weight rounding is not part of the
@@ -126,9 +133,14 @@ def make_case(name: str, c: dict, out_path: Path):
         inputs = {"x_enc": z * scale + offset}
         if "descriptions" in c:
             inputs["descriptions"] = list(c["descriptions"])
+        if "example_lens" in c:      # what datasets/ecg.py's collate_fn hands over: (text, tensor [1, T_ex, C]) per sample
+            inputs["examples"] = [("Example segment:", (torch.randn(1, n, c["C"], generator=g) * scale + offset))
+                                  for n in c["example_lens"]]
         out, stages = H.run_reference_with_stages(model, inputs)
         prompts = model.build_prompt(inputs)
-        prompt_ids = [[t for part in parts for t in model.tokenizer(part, padding=False, truncation=False).input_ids]
+        # flat per-sample lists: token ids, with time-series example parts kept as tensors in their place
+        prompt_ids = [[t for part in parts for t in ([part] if isinstance(part, torch.Tensor) else
+                                                     model.tokenizer(part, padding=False, truncation=False).input_ids)]
                       for parts in prompts]
         # train-mode forward (dropout 0): no eval-only activation — the tensor the loss sees
         out_train, _ = H.run_reference_with_stages(model, inputs, train_mode=True)
@@ -166,7 +178,7 @@ def make_case(name: str, c: dict, out_path: Path):
         }
         torch.save(fixture, out_path)
         print(f"{name}: wrote {out_path} ({out_path.stat().st_size / 1e6:.2f} MB), output {tuple(out.shape)}, "
-              f"Lp={[len(p) for p in prompt_ids]}")
+              f"Lp={[len(p) for p in prompt_ids]}, llm_input {tuple(stages['llm_input'].shape)}")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -93,19 +93,32 @@ def reprogramming(x, source, sd, n_heads: int, prefix="reprogramming_layer.", at
 
 
 # ----------------------------------------------------------------------------- prompt (K5)
-def assemble_prompt(ids_per_sample, word_emb, pad_id: int):
-    """models/medtsllm.py:299-311, 331-337: embed, LEFT-pad with the pad-token embedding, stack."""
+def assemble_prompt(ids_per_sample, word_emb, pad_id: int, encode_part=None):
+    """models/medtsllm.py:299-319, 331-337: embed every part, cat, LEFT-pad with the pad-token embedding, stack.
+    A sample's prompt is a flat list whose items are token ids or — `prompting.examples` — time-series tensors
+    [1, T_ex, C], which `encode_part` (:313-319 -> encode_ts) turns into their reprogrammed patch rows [N_ex, D]."""
     B = len(ids_per_sample)
     D = word_emb.shape[1]
-    Lp = max((len(i) for i in ids_per_sample), default=0)
-    out = word_emb.new_zeros(B, Lp, D)
-    for b, ids in enumerate(ids_per_sample):
-        pad = Lp - len(ids)
-        if pad:
-            out[b, :pad] = word_emb[pad_id]
-        if len(ids):
-            out[b, pad:] = word_emb[torch.as_tensor(ids, dtype=torch.long)]
-    return out
+    rows = []
+    for items in ids_per_sample:
+        pieces, run = [], []
+        for it in items:
+            if isinstance(it, torch.Tensor):
+                if run:
+                    pieces.append(word_emb[torch.as_tensor(run, dtype=torch.long)])
+                    run = []
+                pieces.append(encode_part(it)[0])
+            else:
+                run.append(int(it))
+        if run:
+            pieces.append(word_emb[torch.as_tensor(run, dtype=torch.long)])
+        rows.append(torch.cat(pieces, dim=0) if pieces else word_emb.new_zeros(0, D))
+    Lp = max((r.shape[0] for r in rows), default=0)
+    out = []
+    for r in rows:
+        pad = Lp - r.shape[0]
+        out.append(torch.cat([word_emb[pad_id][None].expand(pad, D), r], dim=0) if pad else r)
+    return torch.stack(out) if B else word_emb.new_zeros(0, Lp, D)
 
 
 # ----------------------------------------------------------------------------- Llama backbone (K6-K10)
@@ -243,38 +256,53 @@ def medtsllm_forward(x_enc, prompt_ids, adapters, backbone_sd, spec, *, training
     word_emb = backbone_sd[emb_key]
     stages = {}
 
-    # encode_ts (models/medtsllm.py:263-297)
-    mean, stdev = revin_stats(x_enc)
-    xn = revin_norm(x_enc, mean, stdev).permute(0, 2, 1).contiguous()
-    enc = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
-    N = enc.shape[1]
-    if dropout_masks is not None and "patch" in dropout_masks:   # PatchEmbedding.dropout (models/layers/embed.py:197), [B*C, N, dm]
-        enc = enc * dropout_masks["patch"]
-    stages["patch_embedding"] = enc
+    def encode_ts(x, masks=None):
+        """models/medtsllm.py:262-297 — also run on every time-series example part of the prompt (:313-319)."""
+        bs = x.shape[0]
+        mean_, stdev_ = revin_stats(x)
+        xn = revin_norm(x, mean_, stdev_).permute(0, 2, 1).contiguous()
+        e = token_conv(patchify(xn, P, S), adapters["patch_embedding.value_embedding.tokenConv.weight"])
+        n = e.shape[1]
+        if masks is not None and "patch" in masks:   # PatchEmbedding.dropout (models/layers/embed.py:197), [B*C, N, dm]
+            e = e * masks["patch"]
+        pe = e
+        if mode == "concat":
+            e = e.reshape(bs, C, n, dm).permute(0, 2, 1, 3).reshape(bs, n, C * dm)
+        elif mode == "univariate":
+            assert C == 1
+        elif mode not in ("interleave", "independent", "merge-end", "add", "weighted-average"):
+            raise ValueError(mode)
+        e = reprogramming(e, source, adapters, spec["n_heads"], attn_mask=masks.get("reprog") if masks is not None else None)
+        rp = e
+        Dm = e.shape[-1]
+        if mode == "add":                                                  # models/medtsllm.py:284-286
+            e = e.reshape(bs, C, n, Dm).mean(dim=1)
+        elif mode == "weighted-average":                                   # :287-291
+            e = F.linear(e.reshape(bs, C, n, Dm).permute(0, 2, 3, 1), adapters["feature_weighting.weight"],
+                         adapters["feature_weighting.bias"]).squeeze(-1)
+        elif mode == "interleave":                                         # :292-295  (n-major, c-minor)
+            e = e.reshape(bs, C, n, Dm).permute(0, 2, 1, 3).reshape(bs, n * C, Dm)
+        return e, mean_, stdev_, pe, rp
+
     mode = spec["covariate_mode"]
-    if mode == "concat":
-        enc = enc.reshape(B, C, N, dm).permute(0, 2, 1, 3).reshape(B, N, C * dm)
-    elif mode == "univariate":
-        assert C == 1
-    elif mode not in ("interleave", "independent", "merge-end", "add", "weighted-average"):
-        raise ValueError(mode)
     source = mapping(word_emb, adapters["mapping_layer.weight"], adapters["mapping_layer.bias"])
     stages["source_embeddings"] = source
-    enc = reprogramming(enc, source, adapters, spec["n_heads"],
-                        attn_mask=dropout_masks.get("reprog") if dropout_masks is not None else None)   # [B or B*C, N, D]
-    stages["reprogramming_layer"] = enc                                # (the module's own output, pre-merge)
-    D = enc.shape[-1]
-    if mode == "add":                                                  # models/medtsllm.py:284-286
-        enc = enc.reshape(B, C, N, D).mean(dim=1)
-    elif mode == "weighted-average":                                   # :287-291
-        enc = F.linear(enc.reshape(B, C, N, D).permute(0, 2, 3, 1), adapters["feature_weighting.weight"],
-                       adapters["feature_weighting.bias"]).squeeze(-1)
-    elif mode == "interleave":                                         # :292-295  (n-major, c-minor)
-        enc = enc.reshape(B, C, N, D).permute(0, 2, 1, 3).reshape(B, N * C, D)
-        N = N * C
+    ex_masks = dropout_masks.get("examples") if dropout_masks is not None else None   # per example part, in prompt order
+    ex_counter = [0]
+
+    def encode_example(ts):
+        m = ex_masks[ex_counter[0]] if ex_masks is not None else None
+        ex_counter[0] += 1
+        return encode_ts(ts.unsqueeze(-1) if ts.ndim == 2 else ts, m)[0]
+
+    # prompt first (its example parts go through encode_ts before the window does, models/medtsllm.py:330-341)
+    prompt = assemble_prompt(prompt_ids, word_emb, spec["pad_id"], encode_example)
+    enc, mean, stdev, pe, rp = encode_ts(x_enc, dropout_masks)
+    stages["patch_embedding"] = pe
+    stages["reprogramming_layer"] = rp                                 # (the module's own output, pre-merge)
+    N = enc.shape[1]
 
     # prompt + backbone (models/medtsllm.py:330-351)
-    prompt = assemble_prompt(prompt_ids, word_emb, spec["pad_id"])
     if mode in ("independent", "merge-end"):                           # models/medtsllm.py:343-344
         prompt = prompt.repeat_interleave(C, dim=0)
     Bp = enc.shape[0]

@@ -17,7 +17,41 @@ for p in (REPO, REPO / "med-ts-llm_b200"):
 
 CASES = ["llama_seg_concat", "gpt2_anomaly_concat", "llama_semseg_univariate", "llama_forecast_clip_stats",
          "llama_forecast_truncate", "gpt2_reconstruction_average", "llama_forecast_independent",
-         "gpt2_forecast_merge_end", "llama_anomaly_add", "gpt2_anomaly_weighted_average", "llama_forecast_interleave"]
+         "gpt2_forecast_merge_end", "llama_anomaly_add", "gpt2_anomaly_weighted_average", "llama_forecast_interleave",
+         "llama_seg_examples"]
+
+
+def same_items(a, b) -> bool:
+    """Equality of prompt parts / prompt items that may hold time-series tensors (prompting.examples)."""
+    if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+        return len(a) == len(b) and all(same_items(x, y) for x, y in zip(a, b))
+    if isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor):
+        return isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and torch.equal(a.cpu(), b.cpu())
+    return a == b
+
+
+def prompt_items(model, inputs):
+    """The kernel model's host prompt table as the oracle wants it: per sample a flat list of token ids (left padding
+    included) with every run of example-part positions (negative ids) replaced by the example tensor itself."""
+    table = model.prompt_token_ids(inputs)
+    segs = {(b, pos): ts for (b, pos, ts) in (getattr(table, "example_segments", None) or [])}
+    out = []
+    for b, row in enumerate(table.tolist()):
+        items, pos = [], 0
+        while pos < len(row):
+            ts = segs.get((b, pos))
+            if ts is not None:
+                items.append(ts.detach().cpu())
+                n = 0
+                while pos + n < len(row) and row[pos + n] < 0 and (n == 0 or (b, pos + n) not in segs):
+                    n += 1
+                pos += n
+            else:
+                assert row[pos] >= 0
+                items.append(row[pos])
+                pos += 1
+        out.append(items)
+    return out
 
 
 def load_case(name: str) -> dict:

@@ -156,6 +156,7 @@ def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
     ids = model.prompt_token_ids({"x_enc": x_dev}).tolist()
     spec = oracle_spec(w, model)
     bb = model._backbone
+    adapters0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
 
     def oracle_grads(device, autocast):
         sd_cpu = LazyBackboneState(bb, keep=(device == "cpu"))
@@ -167,7 +168,7 @@ def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
                     self[key] = sd_cpu[key].to(device)
                     return self[key]
             sd = _Dev()
-        ad = {k: v.detach().to(device).clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        ad = {k: v.to(device).clone().requires_grad_(True) for k, v in adapters0.items()}
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             o = O.medtsllm_forward(inputs["x_enc"].to(device), ids, ad, sd, spec, training=True)
         (o.float() * wgt.to(device)).sum().backward()

@@ -7,7 +7,7 @@ from pathlib import Path
 import pytest
 import torch
 
-from _fixtures import CASES, Cfg, Dataset, config_for, load_case, materialize_llm_dir
+from _fixtures import CASES, Cfg, Dataset, config_for, load_case, materialize_llm_dir, same_items
 
 REPO = Path(__file__).resolve().parent.parent
 
@@ -58,13 +58,25 @@ def test_dropin_surface_and_prompts(name, tmp_path):
     assert "forecasting" in model.supported_tasks and model.lora_enabled is False
     # prompt text + tokenisation identical to the reference's (models/medtsllm.py:386-439, :299-302)
     inputs = dict(fix["inputs"])
-    assert model.build_prompt(inputs) == fix["prompts"]
+    assert same_items(model.build_prompt(inputs), fix["prompts"])
     table = model.prompt_token_ids(inputs)
-    Lp = max(len(p) for p in fix["prompt_ids"])
-    assert table.shape == (len(fix["prompt_ids"]), Lp) and table.dtype == torch.int32
-    for b, ids in enumerate(fix["prompt_ids"]):
-        assert table[b, Lp - len(ids):].tolist() == ids
-        assert all(t == fix["pad_id"] for t in table[b, : Lp - len(ids)].tolist())
+    if "examples" in fix["inputs"]:
+        # prompting.examples: a time-series part occupies n_patches(T_ex) positions marked by negative ids
+        from _fixtures import prompt_items
+        items = prompt_items(model, inputs)
+        Lp = table.shape[1]
+        assert Lp == fix["stages"]["llm_input"].shape[1] - model.n_patches        # the reference's own prompt length
+        for b, want in enumerate(fix["prompt_ids"]):
+            got = items[b]
+            n_pad = len(got) - len(want)
+            assert all(t == fix["pad_id"] for t in got[:n_pad]) and same_items(got[n_pad:], want)
+            assert sorted(set(t for t in table[b].tolist() if t < 0)) == [-(b + 1)]
+    else:
+        Lp = max(len(p) for p in fix["prompt_ids"])
+        assert table.shape == (len(fix["prompt_ids"]), Lp) and table.dtype == torch.int32
+        for b, ids in enumerate(fix["prompt_ids"]):
+            assert table[b, Lp - len(ids):].tolist() == ids
+            assert all(t == fix["pad_id"] for t in table[b, : Lp - len(ids)].tolist())
     # load_pretrained drops the head (models/medtsllm.py:515-527)
     loaded = model.load_pretrained(dict(fix["adapters"]))
     assert "output_projection.linear.weight" not in loaded and "mapping_layer.weight" in loaded
@@ -81,10 +93,11 @@ def test_unsupported_options_fail_loudly(tmp_path):
     cfg["models"]["medtsllm"]["covariate_mode"] = "stacked"
     with pytest.raises(ValueError):
         MedTsLLM(Cfg(cfg), Dataset(fix["dataset"]))
-    cfg["models"]["medtsllm"]["covariate_mode"] = "concat"
+    cfg["models"]["medtsllm"]["covariate_mode"] = "independent"
     cfg["models"]["medtsllm"]["prompting"]["examples"] = True
-    with pytest.raises(NotImplementedError):
-        MedTsLLM(Cfg(cfg), Dataset(fix["dataset"])).build_prompt(fix["inputs"])
+    ex = {**fix["inputs"], "examples": [("Example segment:", torch.zeros(1, 40, 3))] * fix["inputs"]["x_enc"].shape[0]}
+    with pytest.raises(NotImplementedError):     # the reference's own torch.cat of prompt parts breaks for this mode
+        MedTsLLM(Cfg(cfg), Dataset(fix["dataset"])).prompt_token_ids(ex)
     cfg = config_for(fix, llm_dir)
     cfg["models"]["medtsllm"]["lora"] = {"enabled": True, "layers": "auto", "rank": 8, "alpha": 16, "dropout": 0.1}
     with pytest.raises(NotImplementedError):

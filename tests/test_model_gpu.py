@@ -16,7 +16,7 @@ The fixtures' backbone weights are bf16-representable, so weight rounding is not
 import pytest
 import torch
 
-from _fixtures import CASES, Cfg, Dataset, config_for, load_case, materialize_llm_dir, run_oracle
+from _fixtures import CASES, Cfg, Dataset, config_for, load_case, materialize_llm_dir, prompt_items, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -52,9 +52,9 @@ def test_forward_parity(name, precision, tmp_path, cuda, monkeypatch):
     # the input-statistics prompt ranks FFT autocorrelation lags whose values tie exactly in theory
     # (corr[k] == corr[T-k]), so CPU and GPU can order them differently: embed the GPU-side tokens in
     # the oracle, and compare with the CPU-generated goldens only when the prompts agree
-    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ids = prompt_items(model, inputs)        # token ids; time-series example parts (prompting.examples) as tensors
     Lp_max = max(len(p) for p in fix["prompt_ids"])
-    same_prompt = all(r[Lp_max - len(p):] == p for r, p in zip(ids, fix["prompt_ids"]))
+    same_prompt = "examples" in fix["inputs"] or all(r[Lp_max - len(p):] == p for r, p in zip(ids, fix["prompt_ids"]))
     ref_out, st = run_oracle(fix, prompt_ids=ids)
     g = fix["stages"] if same_prompt else {**st, "output": ref_out, "output_train": run_oracle(fix, True, ids)[0]}
 
@@ -145,7 +145,7 @@ def test_training_step_gradients(name, tmp_path, cuda):
     torch.cuda.synchronize()
 
     # oracle gradients (prompt ids from the GPU-side host logic so both sides embed the same tokens)
-    ids = [row.tolist() for row in model.prompt_token_ids(inputs)]
+    ids = prompt_items(model, inputs)
     ad = {k: v.clone().requires_grad_(True) for k, v in fix["adapters"].items()}
     sd = {k: v.float() for k, v in fix["backbone_state"].items()}
     ref = O.medtsllm_forward(fix["inputs"]["x_enc"], ids, ad, sd, oracle_spec(fix), training=True)
