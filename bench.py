@@ -250,7 +250,18 @@ def run_ours(args):
                  "steps": n_tr, "gpu_launches_per_step": int((_lib.launch_count() - n1) // n_tr),
                  "what": "fwd + bwd (dgrad through all frozen blocks, 15 adapter grads) + Adam step + loss.item(), "
                          "host windows/labels copied in every step; dropout 0"}
-        if Lc > 0:
+        if world > 1:
+            # exposed cost of the gradient exchange: the SAME step on the same ranks with the all-reduces skipped
+            from medtsllm_b200 import dp
+            with dp.suspended():
+                step_train()
+                ms_nc = timed(step_train, n_tr) / n_tr
+            train["dp_efficiency"] = round(ms_nc / ms_train, 4)
+            train["ms_per_step_without_allreduce"] = round(ms_nc, 3)
+            train["dp_what"] = ("ms_per_step_without_allreduce / ms_per_step: the same training step on the same ranks with the "
+                                "gradient all-reduces skipped vs issued (NCCL, mean of the adapter gradients; the mapping-layer "
+                                "gradient is exchanged as dSource, see dp.py)")
+        if Lc > 0 and world == 1:
             model.share_prompt_prefix = False
             for _ in range(2):
                 step_train()
@@ -297,6 +308,24 @@ def run_ours(args):
         gemm_flops = sum(fl) / 3
     barrier()
 
+    # ---- the other BASELINE workloads (configs[2..4]: the 8 x B200 data-parallel ones) and one strong-scaling point,
+    # through the same public API; every rank takes part (the training steps all-reduce)
+    extras, strong = None, None
+    if not args.no_extra_workloads:
+        del model, backbone
+        model = backbone = None
+        torch.cuda.empty_cache()
+        n_x = max(3, min(args.steps, 5))
+        extras = {}
+        for name in ("ludb_llama2_7b", "psm_gpt2_medium", "ventilator_llama2_7b"):
+            if name != args.workload:
+                extras[name] = measure_workload(name, dev, world, rank, timed, n_x)
+        if world > 1 and w.B % world == 0:
+            strong = measure_workload(args.workload, dev, world, rank, timed, n_x, batch=w.B // world)
+            strong["what"] = (f"strong scaling: the BASELINE batch of {w.B} split over {world} GPUs "
+                              f"({w.B // world} windows per GPU); values are whole-job samples/s")
+    barrier()
+
     if rank == 0:
         peaks = _peaks()
         fl = forward_flops(w)
@@ -308,7 +337,7 @@ def run_ours(args):
         cpu = cpu_baseline(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
         ref_gpu = None
         if world == 1 and not args.no_ref_gpu:
-            del model, backbone
+            model = backbone = None
             torch.cuda.empty_cache()
             ref_gpu = hf_gpu_backbone(w, dev)
         Lp = w.prompt_len
@@ -327,11 +356,15 @@ def run_ours(args):
                                           "outputs bit-identical to per-sample prompts, which 'per_sample_prompts' times")
                                          if Lc else "off",
                        "l2_policy": f"inputs larger than L2: {weight_gb:.1f} GB of weights streamed per step",
+                       "cached_in_eval": "the batch-independent prototype path (source = W_map E + b, K, V^T: 268 GFLOP for "
+                                         "Llama-2-7B; models/medtsllm.py:281 recomputes it every forward) is computed once "
+                                         "per weight version in evaluation and is NOT inside the timed forward; the train "
+                                         "step recomputes it every step",
                        "parallelism": f"dp{world} (batch sharded, frozen backbone replicated, no forward collective)",
                        "build_s": round(t_build, 1)},
             "clocks": clocks,
             "e2e": {"value": round(world * w.B / (ms_e2e * 1e-3), 2), "unit": "samples/s",
-                    "h2d_bytes_per_step": host["x_enc"].numel() * 4 + w.B * Lp * 4,
+                    "h2d_bytes_per_step": host["x_enc"].numel() * 4,    # the windows (the prompt-id table is static: copied once)
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e, 3)},
             "per_sample_prompts": plain,
             "train_step": train,
@@ -341,14 +374,83 @@ def run_ours(args):
                          "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": traffic,
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "gemm_ms_per_step": round(gemm_ms, 3), "gemm_share_of_step": round(gemm_ms / ms_step, 3),
+                         "step_level": {"achieved": round(gemm_flops / (ms_step * 1e-3) / 1e12, 1),
+                                        "frac": round(gemm_flops / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"], 4),
+                                        "what": "GEMM FLOPs launched per step / ms_per_step (attention, norms, gather and "
+                                                "launch gaps count as lost tensor time)"},
                          "gemm_flops_per_step": gemm_flops, "algorithmic_fwd_flops": fl["total"]},
             "hbm_roofline": hbm,
+            "other_workloads": extras,
+            "strong_scaling": strong,
             "cpu_baseline": cpu,
             "ref_gpu_backbone": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_workload(name, dev, world, rank, timed, steps, batch=None, train=True):
+    """Forward (eval, windows resident in HBM) and training step (host windows / labels in, loss.item() out, gradient
+    all-reduce when world > 1) of another BASELINE workload at its per-GPU batch: the same public API calls as the main
+    workload, fewer steps.  `batch`: per-GPU batch override (strong-scaling point)."""
+    import dataclasses
+    from medtsllm_b200 import dp
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.model import MedTsLLM
+    from medtsllm_b200.synthetic import (WORKLOADS, AttrDict, FixedLengthTokenizer, SyntheticDataset,
+                                         experiment_config, make_inputs)
+    w = WORKLOADS[name]
+    if batch is not None:
+        w = dataclasses.replace(w, B=batch)
+    bb = KernelBackbone.random_init(w.backbone, dev, seed=0)
+    torch.manual_seed(0)
+    model = MedTsLLM(AttrDict(experiment_config(w)), SyntheticDataset(w), backbone=bb,
+                     tokenizer=FixedLengthTokenizer(w.backbone.vocab, w.prompt_len)).to(dev, torch.float32).eval()
+    host = make_inputs(w, seed=1234 + rank, pin=True)
+    resident = {"x_enc": host["x_enc"].to(dev)}
+    res = {"per_gpu_batch": w.B, "T": w.T, "C": w.C, "backbone": f"{w.backbone.kind} D={w.backbone.hidden} x{w.backbone.layers}",
+           "lora_rank": w.lora_rank or None}
+
+    def step_fwd():
+        with torch.no_grad():
+            model(resident)
+
+    for _ in range(3):
+        step_fwd()
+    ms = timed(step_fwd, steps) / steps
+    res["forward"] = {"value": round(world * w.B / (ms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms, 3)}
+    if train:
+        model.train()
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+        with torch.no_grad():
+            y_host = torch.zeros(model.eval()(resident).shape).pin_memory()
+        model.train()
+        loss_fn = torch.nn.MSELoss()
+
+        def step_train():
+            x = host["x_enc"].to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True)
+            loss = loss_fn(model({"x_enc": x}), y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss.item()
+
+        for _ in range(3):
+            step_train()
+        ms_t = timed(step_train, steps) / steps
+        res["train_step"] = {"value": round(world * w.B / (ms_t * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms_t, 3)}
+        if world > 1:
+            with dp.suspended():
+                step_train()
+                ms_nc = timed(step_train, steps) / steps
+            res["train_step"]["dp_efficiency"] = round(ms_nc / ms_t, 4)
+            res["train_step"]["ms_per_step_without_allreduce"] = round(ms_nc, 3)
+        del opt
+    del model, bb
+    torch.cuda.empty_cache()
+    return res
 
 
 def gpt4ts_cpu_baseline(w, layers, x, n_cpu: int = 5):
@@ -696,6 +798,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the HuggingFace-on-GPU backbone baseline")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="skip the forward / training-step numbers of the other BASELINE workloads and the strong-scaling point")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the inference path kernel by kernel")
     ap.add_argument("--per-sample-prompts", action="store_true",
                     help="disable the shared prompt prefix for the whole run (every sample carries its own prompt rows)")

@@ -25,8 +25,32 @@ import torch
 import torch.distributed as dist
 
 
+_suspended = False
+
+
 def is_active() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def comm_enabled() -> bool:
+    """is_active() and not inside `suspended()`: whether the gradient exchanges are actually issued."""
+    return is_active() and not _suspended
+
+
+class suspended:
+    """Context manager: run training steps WITHOUT the gradient exchange (every rank keeps its local gradients; the
+    choice between the captured-graph and the kernel-by-kernel step is unaffected).  Measurement only — bench.py times the same step with and without the all-reduces to report the exposed
+    communication cost of data parallelism (`train_step.dp_efficiency`)."""
+
+    def __enter__(self):
+        global _suspended
+        self._prev, _suspended = _suspended, True
+        return self
+
+    def __exit__(self, *exc):
+        global _suspended
+        _suspended = self._prev
+        return False
 
 
 def _avg_supported(group=None) -> bool:
@@ -72,7 +96,7 @@ class GradArena:
     def launch(self, group=None):
         """Start the (async) in-place mean all-reduce of the whole arena.  The collective is enqueued after the
         work already on the current stream (torch's ProcessGroupNCCL waits on the current stream's tail)."""
-        if self.flat.numel() == 0 or not is_active():
+        if self.flat.numel() == 0 or not comm_enabled():
             return self
         self.group = group
         self.handle, self._needs_div = all_reduce_mean_(self.flat, group, async_op=True)
@@ -100,7 +124,7 @@ class GradBucket:
         self._needs_div = False
 
     def launch(self):
-        if not self.tensors or not is_active():
+        if not self.tensors or not comm_enabled():
             return self
         self.flat = torch.cat([t.reshape(-1) for t in self.tensors])
         self.handle, self._needs_div = all_reduce_mean_(self.flat, self.group, async_op=True)

@@ -35,14 +35,10 @@ w = torch.randn(B, fix["config"]["pred_len"], generator=torch.Generator().manual
 def grads(idx, sync):
     for p in model.parameters():
         p.grad = None
-    if not sync:                       # single-process reference: no all-reduce
-        real, dp.is_active = dp.is_active, (lambda: False)
-    try:
+    import contextlib
+    with (contextlib.nullcontext() if sync else dp.suspended()):      # single-process reference: no all-reduce
         out = model({"x_enc": x[idx]})
         (out * w[idx]).sum().backward()
-    finally:
-        if not sync:
-            dp.is_active = real
     return {k: p.grad.clone() for k, p in model.named_parameters()}
 
 
