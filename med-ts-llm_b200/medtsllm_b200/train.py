@@ -104,7 +104,7 @@ class TrainGraph:
             ctx["early"].launch()
             ctx["dsrc_arena"].launch()
             ctx["late"].launch()
-            lora_bucket = dp.GradBucket(ctx["lora_grads"]).launch()
+            ctx["lora_arena"].launch()
             ctx["dsrc_arena"].finish()
         if e.get("bwd2") is None:
             graph = torch.cuda.CUDAGraph()
@@ -119,7 +119,7 @@ class TrainGraph:
         if active:
             ctx["early"].finish()
             ctx["late"].finish()
-            lora_bucket.finish()
+            ctx["lora_arena"].finish()
         return [g.clone() if g is not None else None for g in e["grads"]]
 
 
@@ -187,17 +187,16 @@ def _arena_layout(m):
 
 def _backward_chain(m, st, dout, use_dp=True):
     """The manual backward of the hot path (see the module docstring): returns the gradients aligned with
-    `m.adapter_params()`.  Kernel-by-kernel path; with data parallelism the three exchanges (early arena, dSource,
-    late arena — always in this order, the graph path issues the same sequence) overlap the chain."""
+    `m.adapter_params()`.  Kernel-by-kernel path; with data parallelism the exchanges (early arena, dSource, late
+    arena, LoRA arena — always in this order, the graph path issues the same sequence) overlap the chain."""
     ctx = _backward_part1(m, st, dout, use_dp=use_dp)
     if use_dp:
         ctx["dsrc_arena"].finish()
     grads = _backward_part2(m, ctx)
     if use_dp:
-        lora_bucket = dp.GradBucket(ctx["lora_grads"]).launch()
         ctx["early"].finish()
         ctx["late"].finish()
-        lora_bucket.finish()
+        ctx["lora_arena"].finish()
     return grads
 
 
@@ -373,8 +372,15 @@ def _backward_part1(m, st, dout, use_dp):
              ldb=src_t.shape[1])
     if use_dp:
         late.launch()
-    lora_grads = [g.contiguous() for g in lora_grads] if lora_grads else []
-    return {"early": early, "late": late, "dsrc_arena": dsrc_arena, "lora_grads": lora_grads}
+    # LoRA pairs: one flat buffer as well (128 small tensors for Llama-2-7B: a `torch.cat` + per-tensor copy back around
+    # the all-reduce would cost more launches than the exchange itself; inside a captured step the copies are graph nodes)
+    lora_arena = dp.GradArena([(f"lora{i}", tuple(g.shape)) for i, g in enumerate(lora_grads or [])], dev)
+    for i, g in enumerate(lora_grads or []):
+        lora_arena.view(f"lora{i}").copy_(g)
+    lora_views = [lora_arena.view(f"lora{i}") for i in range(len(lora_grads or []))]
+    if use_dp:
+        lora_arena.launch()
+    return {"early": early, "late": late, "dsrc_arena": dsrc_arena, "lora_grads": lora_views, "lora_arena": lora_arena}
 
 
 def _backward_part2(m, ctx):
