@@ -669,6 +669,8 @@ def hbm_kernels(model, w, dev, Lc=0):
         row = {"kernel": name, "bytes_per_launch": nbytes, "us_per_launch": round(us, 2),
                "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
                "frac": round(nbytes / us / 1e3 / peak, 4)}
+        # only rows whose working set exceeds the 126 MB L2 and whose launch is long enough are evidence of HBM bandwidth
+        row["hbm_evidence"] = bool(nbytes >= 8e6 and row["frac"] <= 1.0)
         if nbytes < 8e6:     # a few hundred KB per launch: the launch itself (~5-10 us) dominates, not the bytes
             row["note"] = "launch-latency bound at this size: %.1f MB per launch" % (nbytes / 1e6)
         elif row["frac"] > 1.0:

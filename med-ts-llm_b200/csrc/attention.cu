@@ -388,18 +388,28 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+      // k-step outer, key group inner: the 8 MMAs of a k-step hit 8 different accumulators (no dependent chain) and the
+      // 4 K-fragment loads of a k-step are issued back to back ahead of them
+      const int n_grp = min(4, (last_row - j0) / 16 + 1);                   // warp-uniform causal skip
+      uint32_t krow_addr[4];
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        if (j0 + np * 16 > last_row) continue;   // warp-uniform causal skip
         const int id = lane >> 3;
         const int kp = j0 + np * 16 + (id >> 1) * 8 + (lane & 7);          // key position of this lane's row
-        const __nv_bfloat16* krow = Ks + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id & 1) * 8;
+        krow_addr[np] = smem_u32(Ks + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id & 1) * 8);
+      }
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-          uint32_t r0, r1, r2, r3;
-          ldmatrix_x4(smem_u32(krow + ks * 16), r0, r1, r2, r3);
-          mma_bf16_16816(s[2 * np], qf[ks], r0, r1);
-          mma_bf16_16816(s[2 * np + 1], qf[ks], r2, r3);
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint32_t kf[4][4];
+#pragma unroll
+        for (int np = 0; np < 4; ++np)
+          if (np < n_grp) ldmatrix_x4(krow_addr[np] + ks * 32, kf[np][0], kf[np][1], kf[np][2], kf[np][3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (np < n_grp) {
+            mma_bf16_16816(s[2 * np], qf[ks], kf[np][0], kf[np][1]);
+            mma_bf16_16816(s[2 * np + 1], qf[ks], kf[np][2], kf[np][3]);
+          }
         }
       }
       float mx[2] = {-INFINITY, -INFINITY};
@@ -463,13 +473,16 @@ attn_causal_fwd_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
         pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
         const int id = lane >> 3;
         const int kp = j0 + kk * 16 + (id & 1) * 8 + (lane & 7);
-        const __nv_bfloat16* vrow = Vs + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id >> 1) * 8;
+        const uint32_t vaddr = smem_u32(Vs + (kp + (kp < Lc ? 0 : soff)) * kPitch + (id >> 1) * 8);
+        uint32_t vf[2][4];                       // double-buffered V fragments: load np+1 ahead of the MMAs of np
+        ldmatrix_x4_trans(vaddr, vf[0][0], vf[0][1], vf[0][2], vf[0][3]);
 #pragma unroll
         for (int np = 0; np < HD / 16; ++np) {
-          uint32_t r0, r1, r2, r3;
-          ldmatrix_x4_trans(smem_u32(vrow + np * 16), r0, r1, r2, r3);
-          mma_bf16_16816(o[2 * np], pa, r0, r1);
-          mma_bf16_16816(o[2 * np + 1], pa, r2, r3);
+          if (np + 1 < HD / 16)
+            ldmatrix_x4_trans(vaddr + (np + 1) * 32, vf[(np + 1) & 1][0], vf[(np + 1) & 1][1], vf[(np + 1) & 1][2],
+                              vf[(np + 1) & 1][3]);
+          mma_bf16_16816(o[2 * np], pa, vf[np & 1][0], vf[np & 1][1]);
+          mma_bf16_16816(o[2 * np + 1], pa, vf[np & 1][2], vf[np & 1][3]);
         }
       }
     }
@@ -602,7 +615,9 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* 
 // C(16 x 64) = A(16 x HD, rows [arow0, +16) of As) * B^T, B = 64 rows of Bs (both [row][HD+8] bf16)
 // Rows of Bs at or beyond `thr` (relative to Bs) lie `shift` rows further down: the shared-prefix layout keeps the
 // own keys of sample i of a CTA i*Ls rows behind the prefix keys (thr = INT_MAX: plain contiguous rows).
-template <int HD>
+// kBatch: issue the 4 B-fragment loads of a k-step ahead of its 8 MMAs (16 more live registers: the dK/dV loops, which
+// carry two HD-wide accumulators, stay on the interleaved order).
+template <int HD, bool kBatch = true>
 __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* As, int arow0,
                                          const __nv_bfloat16* Bs, int lane, int g_lo = 0, int g_hi = 4,
                                          int thr = 0x7fffffff, int shift = 0) {
@@ -613,16 +628,34 @@ __device__ __forceinline__ void mma_a_bt(float (&c)[8][4], const __nv_bfloat16* 
   for (int ks = 0; ks < HD / 16; ++ks) {
     uint32_t a[4];
     ldmatrix_x4(smem_u32(As + (arow0 + (lane & 15)) * kPitch + ks * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+    if constexpr (kBatch) {
+      uint32_t bf[4][4];                         // the B fragments of this k-step first, then the 8 independent MMAs
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      if (np < g_lo || np >= g_hi) continue;   // warp-uniform: 16-column groups outside the causal range
-      const int id = lane >> 3;
-      int brow = np * 16 + (id >> 1) * 8 + (lane & 7);
-      brow += brow >= thr ? shift : 0;
-      uint32_t r0, r1, r2, r3;
-      ldmatrix_x4(smem_u32(Bs + brow * kPitch + ks * 16 + (id & 1) * 8), r0, r1, r2, r3);
-      mma_bf16_16816(c[2 * np], a, r0, r1);
-      mma_bf16_16816(c[2 * np + 1], a, r2, r3);
+      for (int np = 0; np < 4; ++np) {
+        if (np < g_lo || np >= g_hi) continue;   // warp-uniform: 16-column groups outside the causal range
+        const int id = lane >> 3;
+        int brow = np * 16 + (id >> 1) * 8 + (lane & 7);
+        brow += brow >= thr ? shift : 0;
+        ldmatrix_x4(smem_u32(Bs + brow * kPitch + ks * 16 + (id & 1) * 8), bf[np][0], bf[np][1], bf[np][2], bf[np][3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < g_lo || np >= g_hi) continue;
+        mma_bf16_16816(c[2 * np], a, bf[np][0], bf[np][1]);
+        mma_bf16_16816(c[2 * np + 1], a, bf[np][2], bf[np][3]);
+      }
+    } else {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < g_lo || np >= g_hi) continue;
+        const int id = lane >> 3;
+        int brow = np * 16 + (id >> 1) * 8 + (lane & 7);
+        brow += brow >= thr ? shift : 0;
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4(smem_u32(Bs + brow * kPitch + ks * 16 + (id & 1) * 8), r0, r1, r2, r3);
+        mma_bf16_16816(c[2 * np], a, r0, r1);
+        mma_bf16_16816(c[2 * np + 1], a, r2, r3);
+      }
     }
   }
 }
@@ -641,15 +674,19 @@ __device__ __forceinline__ void mma_p_b(float (&acc)[HD / 8][4], const float (&p
     pa[1] = pack_bf16(pm[2 * kk][2], pm[2 * kk][3]);
     pa[2] = pack_bf16(pm[2 * kk + 1][0], pm[2 * kk + 1][1]);
     pa[3] = pack_bf16(pm[2 * kk + 1][2], pm[2 * kk + 1][3]);
+    const int id = lane >> 3;
+    int brow = kk * 16 + (id & 1) * 8 + (lane & 7);
+    brow += brow >= thr ? shift : 0;
+    const uint32_t baddr = smem_u32(Bs + brow * kPitch + (id >> 1) * 8);
+    uint32_t bf[2][4];                           // double-buffered: fragment np+1 is in flight during the MMAs of np
+    ldmatrix_x4_trans(baddr, bf[0][0], bf[0][1], bf[0][2], bf[0][3]);
 #pragma unroll
     for (int np = 0; np < HD / 16; ++np) {
-      const int id = lane >> 3;
-      int brow = kk * 16 + (id & 1) * 8 + (lane & 7);
-      brow += brow >= thr ? shift : 0;
-      uint32_t r0, r1, r2, r3;
-      ldmatrix_x4_trans(smem_u32(Bs + brow * kPitch + np * 16 + (id >> 1) * 8), r0, r1, r2, r3);
-      mma_bf16_16816(acc[2 * np], pa, r0, r1);
-      mma_bf16_16816(acc[2 * np + 1], pa, r2, r3);
+      if (np + 1 < HD / 16)
+        ldmatrix_x4_trans(baddr + (np + 1) * 32, bf[(np + 1) & 1][0], bf[(np + 1) & 1][1], bf[(np + 1) & 1][2],
+                          bf[(np + 1) & 1][3]);
+      mma_bf16_16816(acc[2 * np], pa, bf[np & 1][0], bf[np & 1][1]);
+      mma_bf16_16816(acc[2 * np + 1], pa, bf[np & 1][2], bf[np & 1][3]);
     }
   }
 }
@@ -1045,8 +1082,8 @@ attn_bwd_dkv_seq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       const int g_lo = max(0, (k0 - i0) / 16);
       const int g_hi = min(4, (L - 1 - i0) / 16 + 1);
       float st[8][4], dpt[8][4];                 // rows = keys, cols = queries
-      mma_a_bt<HD>(st, Ks, 0, Qb + i0 * kPitch, lane, g_lo, g_hi);
-      mma_a_bt<HD>(dpt, Vs, 0, dOb + i0 * kPitch, lane, g_lo, g_hi);
+      mma_a_bt<HD, false>(st, Ks, 0, Qb + i0 * kPitch, lane, g_lo, g_hi);
+      mma_a_bt<HD, false>(dpt, Vs, 0, dOb + i0 * kPitch, lane, g_lo, g_hi);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -1238,8 +1275,8 @@ attn_bwd_own_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __
         const int g_lo = max(0, (k0 - i0) / 16);
         const int g_hi = min(4, (Ls - 1 - i0) / 16 + 1);
         float st[8][4], dpt[8][4];                          // rows = keys, cols = queries
-        mma_a_bt<HD>(st, Ks, krow, Qb + i0 * kPitch, lane, g_lo, g_hi);
-        mma_a_bt<HD>(dpt, Vs, krow, dOb + i0 * kPitch, lane, g_lo, g_hi);
+        mma_a_bt<HD, false>(st, Ks, krow, Qb + i0 * kPitch, lane, g_lo, g_hi);
+        mma_a_bt<HD, false>(dpt, Vs, krow, dOb + i0 * kPitch, lane, g_lo, g_hi);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -1368,8 +1405,8 @@ attn_bwd_dkv_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, const float* _
       const float* del_b = del_s + stage * 64;
       const int g_hi = min(4, (M - 1 - i0) / 16 + 1);
       float st[8][4], dpt[8][4];                 // rows = keys, cols = queries
-      mma_a_bt<HD>(st, Ks, 0, Qb, lane, 0, g_hi);
-      mma_a_bt<HD>(dpt, Vs, 0, dOb, lane, 0, g_hi);
+      mma_a_bt<HD, false>(st, Ks, 0, Qb, lane, 0, g_hi);
+      mma_a_bt<HD, false>(dpt, Vs, 0, dOb, lane, 0, g_hi);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll

@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmtsb200.so"
+import os
+
+# MTS_LIB_PATH: load another build of the library (A/B timing of kernel changes, tools/bench_attn.py)
+LIB_PATH = Path(os.environ.get("MTS_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libmtsb200.so")
 
 MTS_OK = 0
 MTS_BF16, MTS_F32 = 0, 1
