@@ -310,7 +310,7 @@ def run_ours(args):
 
     # ---- the other BASELINE workloads (configs[2..4]: the 8 x B200 data-parallel ones) and one strong-scaling point,
     # through the same public API; every rank takes part (the training steps all-reduce)
-    extras, strong = None, None
+    extras, strong, precision_modes = None, None, None
     if not args.no_extra_workloads:
         del model, backbone
         model = backbone = None
@@ -320,6 +320,8 @@ def run_ours(args):
         for name in ("ludb_llama2_7b", "psm_gpt2_medium", "ventilator_llama2_7b"):
             if name != args.workload:
                 extras[name] = measure_workload(name, dev, world, rank, timed, n_x)
+        if world == 1 and not args.no_precision_modes:
+            precision_modes = measure_precision_modes(args.workload, dev, timed)
         if world > 1 and w.B % world == 0:
             strong = measure_workload(args.workload, dev, world, rank, timed, n_x, batch=w.B // world)
             strong["what"] = (f"strong scaling: the BASELINE batch of {w.B} split over {world} GPUs "
@@ -382,6 +384,7 @@ def run_ours(args):
             "hbm_roofline": hbm,
             "other_workloads": extras,
             "strong_scaling": strong,
+            "precision_modes": precision_modes,
             "cpu_baseline": cpu,
             "ref_gpu_backbone": ref_gpu,
         }
@@ -448,6 +451,35 @@ def measure_workload(name, dev, world, rank, timed, steps, batch=None, train=Tru
             res["train_step"]["dp_efficiency"] = round(ms_nc / ms_t, 4)
             res["train_step"]["ms_per_step_without_allreduce"] = round(ms_nc, 3)
         del opt
+    del model, bb
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_precision_modes(name, dev, timed, steps=3):
+    """Evaluation forward of the main workload in the parity modes (precise.py): "tf32" = the reference's own evaluation
+    regime (fp32 weights, TF32 matmuls) on tcgen05 kind::tf32, "fp32" = 3xTF32; fp32 activations, fp32 attention."""
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.model import MedTsLLM
+    from medtsllm_b200.synthetic import (WORKLOADS, AttrDict, FixedLengthTokenizer, SyntheticDataset,
+                                         experiment_config, make_inputs)
+    w = WORKLOADS[name]
+    bb = KernelBackbone.random_init(w.backbone, dev, seed=0, precision="fp32")
+    torch.manual_seed(0)
+    model = MedTsLLM(AttrDict(experiment_config(w)), SyntheticDataset(w), backbone=bb,
+                     tokenizer=FixedLengthTokenizer(w.backbone.vocab, w.prompt_len)).to(dev, torch.float32).eval()
+    x = {"x_enc": make_inputs(w)["x_enc"].to(dev)}
+    res = {"what": "MedTsLLM.forward (eval) of the main workload with fp32 activations end to end; samples/s, windows resident"}
+    for mode in ("tf32", "fp32"):
+        model.set_precision(mode)
+
+        def step():
+            with torch.no_grad():
+                model(x)
+        for _ in range(3):
+            step()
+        ms = timed(step, steps) / steps
+        res[mode] = {"value": round(w.B / (ms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms, 3)}
     del model, bb
     torch.cuda.empty_cache()
     return res
@@ -800,6 +832,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the HuggingFace-on-GPU backbone baseline")
+    ap.add_argument("--no-precision-modes", action="store_true",
+                    help="skip the evaluation-parity-mode (tf32 / fp32) forward timings of the main workload")
     ap.add_argument("--no-extra-workloads", action="store_true",
                     help="skip the forward / training-step numbers of the other BASELINE workloads and the strong-scaling point")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the inference path kernel by kernel")

@@ -123,17 +123,31 @@ class KernelBackbone:
         return self.precision != "bf16"
 
     def gemm32(self, a_op, w_op, d, **kw):
-        """mts_gemm on fp32 operand pairs (kind::tf32; 3xTF32 when the pairs carry low pieces)."""
+        """mts_gemm on fp32 operand pairs (kind::tf32; 3xTF32 when both pairs carry low pieces)."""
+        if a_op[1] is None or w_op[1] is None:      # "tf32" on a stack built for "fp32": the hi pieces ARE the TF32 operands
+            return ops.gemm(a_op[0], w_op[0], d, **kw)
         return ops.gemm(a_op[0], w_op[0], d, a_lo=a_op[1], b_lo=w_op[1], **kw)
+
+    def set_precision(self, precision: str):
+        """Switch the evaluation regime of an already built stack: "bf16" always works; "tf32" needs fp32 operands
+        (built with "tf32" or "fp32": the hi piece of the 3xTF32 split is the nearest-TF32 weight); "fp32" needs the split."""
+        have = getattr(self, "_built_precision", self.precision)
+        ok = {"bf16": ("bf16",), "tf32": ("bf16", "tf32"), "fp32": ("bf16", "tf32", "fp32")}[have]
+        if precision not in ok:
+            raise MtsError(f"this backbone was built for {have!r}: cannot switch to {precision!r}")
+        self._built_precision = have
+        self.precision = precision
+        self.cache_gen += 1
 
     def embed_t_f32(self):
         """fp32 [D, ceil4(V)] operand pair of the mapping GEMM (built on first use: 0.5 GB for Llama-2-7B)."""
-        if getattr(self, "_embed_t_f32", None) is None:
+        cache = self.__dict__.setdefault("_embed_t_f32", {})
+        if self.precision not in cache:
             V, D = self.embed.shape
             t = torch.zeros(D, (V + 3) // 4 * 4, device=self.device, dtype=torch.float32)
             t[:, :V] = self.embed.t()
-            self._embed_t_f32 = self.operand(t, inplace=True)
-        return self._embed_t_f32
+            cache[self.precision] = self.operand(t, inplace=True)
+        return cache[self.precision]
 
     def _finish_embeddings(self, emb: torch.Tensor):
         self.embed = self._f32(emb)

@@ -616,6 +616,18 @@ class MedTsLLM(nn.Module):
         self._cache_gen += 1
         return w
 
+    def set_precision(self, precision: str):
+        """Switch the numerics of evaluation-mode forwards ("bf16" | "tf32" | "fp32", see precise.py).  The parity modes
+        need a backbone built with fp32 operands (MTS_PRECISION / setup.dtype at load time, or an injected stack)."""
+        if precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError(f"precision {precision!r}: expected bf16, tf32 or fp32")
+        if precision != "bf16":
+            if self._backbone is None:
+                raise MtsError("move the model to the GPU first")
+            self._backbone.set_precision(precision)
+        self.precision = precision
+        self._cache_gen += 1
+
     def invalidate_caches(self):
         """Drops every derived device-side copy (bf16 adapter weights, prototype K / V, LoRA operands) and the captured
         graphs.  Needed only after weight surgery that neither bumps `Parameter._version` nor goes through a torch
