@@ -128,9 +128,8 @@ class GPT4TS(nn.Module):
             hf.config.n_layer = len(hf.h)
             object.__setattr__(self, "_hf_model", hf)
         hf_cfg = getattr(getattr(self, "_hf_model", None), "config", None)
-        # (an injected random-init backbone stands for the "gpt2" checkpoint, whose config carries 0.1 everywhere)
-        self._hf_pdrop = max(float(getattr(hf_cfg, k, 0.1) or 0.0) for k in ("embd_pdrop", "attn_pdrop", "resid_pdrop")) \
-            if hf_cfg is not None else 0.1
+        self._hf_pdrop = {k: float(getattr(hf_cfg, k + "_pdrop", 0.0) or 0.0) if hf_cfg is not None else 0.0
+                          for k in ("embd", "attn", "resid")}
         self.device = None
         self._w_cache: dict[str, tuple] = {}
         self.use_cuda_graph = os.environ.get("MTS_CUDA_GRAPH", "1") != "0"      # see graph.GraphReplay
@@ -174,30 +173,31 @@ class GPT4TS(nn.Module):
         bb = self._backbone
         if self.d_model > bb.spec.hidden or self.d_ff > bb.spec.hidden or C > bb.spec.hidden:
             raise MtsError(f"d_model / d_ff / n_features must not exceed the GPT-2 width {bb.spec.hidden}")
-        if self.training:
-            self._warn_dropout_once()
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             names, params = zip(*self._trainable())
             return _GPT4TSFn.apply(self, x, names, *params)                 # autograd path (training-mode forwards)
-        if not self.use_cuda_graph:
-            return self._forward_impl(x)
+        if not self.use_cuda_graph or (self.training and self._dropout_state() is not None):
+            return self._forward_impl(x)            # (dropout draws fresh seeds every call)
         key = (tuple(x.shape), x.device.index, self.training, tuple((p._version, p.data_ptr()) for p in self.parameters()))
         return self._graph.run(key, x, self._forward_impl)
 
-    def _warn_dropout_once(self):
-        """Known divergence: the reference's GPT4TS regularises training with
-        `DataEmbedding.dropout(training.dropout)` (models/layers/embed.py:113, :120-131) and with GPT-2's own 0.1
-        embd / attn / resid dropouts, live because `model.train()` flips the HF module.  This class trains WITHOUT them
-        (MedTsLLM implements both kinds); say so once instead of silently dropping the regularisation."""
-        if getattr(self, "_warned_dropout", False):
-            return
-        p_cfg = float(_get(_get(self.config, "training"), "dropout", 0.0) or 0.0)
-        if p_cfg > 0 or self._hf_pdrop > 0:
-            import warnings
-            warnings.warn(f"medtsllm_b200.GPT4TS trains without dropout: training.dropout={p_cfg} (DataEmbedding) and the "
-                          f"GPT-2 backbone's own dropouts (p={self._hf_pdrop}) are not applied on the kernel path",
-                          stacklevel=3)
-        self._warned_dropout = True
+    def _dropout_state(self):
+        """Train-mode dropouts of the reference's GPT4TS: `DataEmbedding.dropout(training.dropout)` on the embedded window
+        (models/layers/embed.py:113, :120-131) and GPT-2's own embd / attn / resid dropouts, live because `model.train()`
+        flips the HF module (the "gpt2" checkpoint carries 0.1).  Returns None in evaluation / when everything is zero,
+        else {"p_embed", "seed_embed", "bb": backbone dropout dict or None} with fresh seeds from torch's generator.
+        `self.backbone_dropout = {"embd", "attn", "resid"}` overrides the HF config (injected backbones carry none)."""
+        if not self.training:
+            return None
+        p_embed = float(_get(_get(self.config, "training"), "dropout", 0.0) or 0.0)
+        probs = getattr(self, "backbone_dropout", None) or self._hf_pdrop
+        bb_on = max(probs.values()) > 0
+        if p_embed <= 0 and not bb_on:
+            return None
+        n = 2 + 3 * len(self._backbone.layers)
+        seeds = [int(v) for v in torch.randint(0, 2 ** 62, (n,))]
+        return {"p_embed": p_embed, "seed_embed": seeds[0],
+                "bb": {**probs, "seeds": seeds[1:]} if bb_on else None}
 
     # ------------------------------------------------------------------------------------------ parameters
     def _mirror_gpt2_parameters(self):
@@ -236,8 +236,11 @@ class GPT4TS(nn.Module):
         bb = self._backbone
         D, dev = bb.spec.hidden, x.device
         T2 = T + self.pred_len
+        drop = self._dropout_state()
+        self._last_dropout = drop
+        p_emb = drop["p_embed"] if drop is not None else 0.0
         if self.task == "anomaly_detection":
-            return self._anomaly_detection(x, stash)
+            return self._anomaly_detection(x, stash, drop)
         mean = torch.empty(B, C, device=dev, dtype=torch.float32)
         std = torch.empty(B, C, device=dev, dtype=torch.float32)
         w_conv = self.enc_embedding.value_embedding.tokenConv.weight.detach()
@@ -248,11 +251,17 @@ class GPT4TS(nn.Module):
         if self.task == "forecasting":
             ld_t = ops.ceil8(T)
             enc_t = torch.empty(B, self.d_model, ld_t, device=dev, dtype=torch.bfloat16)
-            if stash is not None:     # non-transposed copy: B operand of the time-axis Linear's weight gradient
+            if stash is not None or p_emb > 0:   # non-transposed copy: B operand of the time-axis Linear's weight gradient
                 enc_nt = torch.empty(B, T, self.d_model, device=dev, dtype=torch.bfloat16)
             _lib.call("mts_gpt4ts_embed", x.data_ptr(), w_conv.data_ptr(), pe.data_ptr(), 0, mean.data_ptr(),
                       std.data_ptr(), enc_t.data_ptr(), 0, 0 if enc_nt is None else enc_nt.data_ptr(), B, T, C,
                       self.d_model, D, ld_t, 0, 1e-5, stream)
+            if p_emb > 0:
+                # DataEmbedding.dropout on [B, T, d_model] (embed.py:131); the transposed operand is rebuilt from it
+                ops.dropout(enc_nt, p_emb, drop["seed_embed"], out=enc_nt)
+                for b in range(B):
+                    ops.transpose_strided(enc_nt, rows=T, cols=self.d_model, in_off=b * T * self.d_model,
+                                          out=enc_t[b], ld_out=ld_t)
             # rows of X = wpe[t] (+ 0): HF's GPT2Model adds the position table to inputs_embeds (modeling_gpt2.py:584-585)
             ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T2, B=B)
             # Linear along time (models/gpt4ts.py:137): X[b, t', :d_model] += W_pre[t', :] . enc[b, :, :] + b_pre[t']
@@ -260,12 +269,25 @@ class GPT4TS(nn.Module):
             ops.gemm(w_pre, enc_t, X, m=T2, n=self.d_model, k=T, batch=B, lda=w_pre.shape[1], a_bs=0, ldb=ld_t,
                      b_bs=self.d_model * ld_t, ldd=D, d_bs=T2 * D, bias=self.predict_linear_pre.bias.detach(),
                      bias_axis=BIAS_M, epilogue=EPI_RESID_ADD)
+        elif p_emb > 0:
+            if self.d_model != D:
+                raise NotImplementedError("training.dropout > 0 with d_model != GPT-2 width on the segmentation tasks")
+            # dropout(embedding) THEN + wpe: the embedding alone first (zero position table), its dropout, then the rows
+            # of the position table with the dropped embedding accumulated onto them
+            if getattr(self, "_zero_wpe", None) is None or self._zero_wpe.device != dev:
+                self._zero_wpe = torch.zeros_like(bb.wpe)
+            E = torch.empty(B * T, D, device=dev, dtype=torch.float32)
+            _lib.call("mts_gpt4ts_embed", x.data_ptr(), w_conv.data_ptr(), pe.data_ptr(), self._zero_wpe.data_ptr(),
+                      mean.data_ptr(), std.data_ptr(), 0, E.data_ptr(), 0, B, T, C, self.d_model, D, 0, 1, 1e-5, stream)
+            ops.dropout(E, p_emb, drop["seed_embed"], out=E)
+            ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T, B=B)
+            ops.group_reduce(E, B, 1, T * D, out=X, accumulate=True)
         else:
             _lib.call("mts_gpt4ts_embed", x.data_ptr(), w_conv.data_ptr(), pe.data_ptr(), bb.wpe.data_ptr(),
                       mean.data_ptr(), std.data_ptr(), 0, X.data_ptr(), 0, B, T, C, self.d_model, D, 0, 1, 1e-5, stream)
-        out = self._blocks_and_out_layer(X, B, T2, stash)
+        out = self._blocks_and_out_layer(X, B, T2, stash, drop)
         if stash is not None:
-            stash.update(x=x, mean=mean, std=std, enc_nt=enc_nt, B=B, T2=T2)
+            stash.update(x=x, mean=mean, std=std, enc_nt=enc_nt, B=B, T2=T2, drop=drop)
         if self.task == "forecasting":
             ops.revin_denorm(out, mean, std)                                           # :146-147
             return out[:, -self.pred_len:, :].contiguous()
@@ -281,12 +303,12 @@ class GPT4TS(nn.Module):
                 ops.sigmoid_(out)
         return out
 
-    def _blocks_and_out_layer(self, X, B, T2, stash=None):
+    def _blocks_and_out_layer(self, X, B, T2, stash=None, drop=None):
         """GPT-2 blocks + ln_f, then out_layer on the first d_ff features (models/gpt4ts.py:140-143): fp32 [B, T2, n_out]."""
         bb = self._backbone
         D = bb.spec.hidden
         layers = [] if stash is not None else None
-        hid, x_final = bb.forward(X, B, T2, stash=layers)                              # bf16 [B*T2, D], ln_f applied
+        hid, x_final = bb.forward(X, B, T2, stash=layers, dropout=drop["bb"] if drop is not None else None)   # bf16 [B*T2, D], ln_f applied
         n_out = self.out_layer.weight.shape[0]
         w_out = self._bf16_weight("out", self.out_layer.weight)                        # [n_out, ceil8(d_ff)]
         out = torch.empty(B * T2, n_out, device=X.device, dtype=torch.float32)
@@ -296,21 +318,23 @@ class GPT4TS(nn.Module):
             stash.update(layers=layers, hid=hid, x_final=x_final, rows=B * T2)
         return out.view(B, T2, n_out)
 
-    def _anomaly_detection(self, x, stash=None):
+    def _anomaly_detection(self, x, stash=None, drop=None):
         """models/gpt4ts.py:151-177.  The statistics are taken over "segments" of seg_num = 1 time step (:155-159):
         mean = x, the centred series is identically zero, stdev = sqrt(1e-5).  The GPT-2 therefore sees the same
         input for every sample — zeros plus its position table — and the prediction is dec * sqrt(1e-5) + x
-        (:172-175).  That one sequence goes through the blocks once; the de-normalisation broadcasts it."""
+        (:172-175).  That one sequence goes through the blocks once; the de-normalisation broadcasts it.  With the
+        GPT-2's own dropouts live (training) every sample draws its own masks, so all B sequences go through."""
         B, T, C = x.shape
         bb = self._backbone
-        X = torch.empty(T, bb.spec.hidden, device=x.device, dtype=torch.float32)
-        ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T, B=1)            # 0 + wpe[t]
-        dec = self._blocks_and_out_layer(X, 1, T, stash)                               # [1, T, C]
+        Bb = B if (drop is not None and drop["bb"] is not None) else 1
+        X = torch.empty(Bb * T, bb.spec.hidden, device=x.device, dtype=torch.float32)
+        ops.prompt_gather(None, bb.embed, bb.wpe, X, rep=1, Lp=0, L=T, B=Bb)           # 0 + wpe[t]
+        dec = self._blocks_and_out_layer(X, Bb, T, stash, drop)                        # [Bb, T, C]
         out = dec.expand(B, T, C).contiguous()
         std = torch.full((1, B * T * C), float(torch.tensor(1e-5, dtype=torch.float32).sqrt()), device=x.device)
         ops.revin_denorm(out.view(1, 1, -1), x.reshape(1, -1), std)                    # out * sqrt(1e-5) + x
         if stash is not None:
-            stash.update(x=x, B=B, T2=T)
+            stash.update(x=x, B=B, T2=T, drop=drop, Bb=Bb)
         return out
 
     # ------------------------------------------------------------------------------------------ backward
@@ -332,6 +356,10 @@ class GPT4TS(nn.Module):
             full = torch.zeros(B, T2, C, device=dev, dtype=torch.float32)
             full[:, -self.pred_len:, :] = dout                                       # only the last pred_len steps are returned
             dy = ops.revin_denorm_bwd(full, st["std"]).view(B * T2, n_out)            # d dec = dout * std
+        elif anomaly and st.get("Bb", 1) > 1:
+            # every sample went through the blocks (live GPT-2 dropouts): d dec[b] = sqrt(1e-5) * dout[b]
+            dy = ops.revin_denorm_bwd(dout.reshape(1, 1, -1).contiguous(),
+                                      torch.full((1, B * T * C), float(torch.tensor(1e-5).sqrt()), device=dev)).view(B * T, n_out)
         elif anomaly:
             # out[b] = dec * sqrt(1e-5) + x[b] with ONE dec for the whole batch: d dec = sqrt(1e-5) * sum_b dout[b]
             summed = ops.colsum(dout.reshape(B, T * C).contiguous()).view(1, T * C)
@@ -356,7 +384,10 @@ class GPT4TS(nn.Module):
         ops.gemm(dy_b, w_out_t, dhid, m=M, n=dff, k=n_out, lda=dy_b.shape[1], ldb=w_out_t.shape[1], ldd=D)
         # ---- GPT-2 blocks: dgrad + LayerNorm parameter gradients
         ng = {}
-        dX, _ = bb.backward(dhid, st["x_final"], st["layers"], Bb, T2, norm_grads=ng)  # fp32 [M, D]
+        drop = st.get("drop")
+        dX, _ = bb.backward(dhid, st["x_final"], st["layers"], Bb, T2, norm_grads=ng,
+                            dropout=drop["bb"] if drop is not None else None)            # fp32 [M, D]
+        p_emb = drop["p_embed"] if drop is not None else 0.0
         grads["gpt2.ln_f.weight"], grads["gpt2.ln_f.bias"] = ng[("ln_f",)]
         for li in range(len(bb.layers)):
             grads[f"gpt2.h.{li}.ln_1.weight"], grads[f"gpt2.h.{li}.ln_1.bias"] = ng[(li, "ln1")]
@@ -383,15 +414,27 @@ class GPT4TS(nn.Module):
             grads["predict_linear_pre.bias"] = ops.rowsum(g_pos[:, :dm].contiguous())
             w_pre = self._bf16_weight("pre", self.predict_linear_pre.weight)          # [T2, ceil8(T)]
             w_pre_t = ops.transpose_strided(w_pre, rows=T2, cols=T, ld_in=w_pre.shape[1])     # [T, ceil8(T2)]
-            denc_t = f32(B, dm, T)                                                    # d enc, transposed like enc_t
-            for b in range(B):
-                dx_t = ops.transpose_strided(dX, rows=T2, cols=dm, ld_in=D, in_off=b * T2 * D)   # [dm, ceil8(T2)]
-                ops.gemm(dx_t, w_pre_t, denc_t[b], m=dm, n=T, k=T2, lda=dx_t.shape[1], ldb=w_pre_t.shape[1])
-            _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), denc_t.data_ptr(),
-                      g_conv.data_ptr(), B, T, C, dm, dm * T, T, 1, stream)
+            if p_emb > 0:
+                # d enc in [B, T, d_model] order (transposed store), so that the DataEmbedding dropout mask applies
+                denc = f32(B, T, dm)
+                for b in range(B):
+                    dx_t = ops.transpose_strided(dX, rows=T2, cols=dm, ld_in=D, in_off=b * T2 * D)   # [dm, ceil8(T2)]
+                    ops.gemm(dx_t, w_pre_t, denc[b], m=dm, n=T, k=T2, lda=dx_t.shape[1], ldb=w_pre_t.shape[1],
+                             d_transposed=True, ldd=dm)
+                ops.dropout(denc, p_emb, drop["seed_embed"], out=denc)
+                _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), denc.data_ptr(),
+                          g_conv.data_ptr(), B, T, C, dm, T * dm, 1, dm, stream)
+            else:
+                denc_t = f32(B, dm, T)                                                # d enc, transposed like enc_t
+                for b in range(B):
+                    dx_t = ops.transpose_strided(dX, rows=T2, cols=dm, ld_in=D, in_off=b * T2 * D)   # [dm, ceil8(T2)]
+                    ops.gemm(dx_t, w_pre_t, denc_t[b], m=dm, n=T, k=T2, lda=dx_t.shape[1], ldb=w_pre_t.shape[1])
+                _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), denc_t.data_ptr(),
+                          g_conv.data_ptr(), B, T, C, dm, dm * T, T, 1, stream)
         else:
-            # the embedding went straight into the residual stream: d enc[b, t, d] = dX[b, t, d]
-            _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), dX.data_ptr(),
+            # the embedding went straight into the residual stream: d enc[b, t, d] = dX[b, t, d] (x its dropout mask)
+            dE = ops.dropout(dX, p_emb, drop["seed_embed"]) if p_emb > 0 else dX
+            _lib.call("mts_gpt4ts_conv_wgrad", x.data_ptr(), mean.data_ptr(), std.data_ptr(), dE.data_ptr(),
                       g_conv.data_ptr(), B, T, C, dm, T * D, 1, D, stream)
         grads["enc_embedding.value_embedding.tokenConv.weight"] = g_conv
         return grads

@@ -505,6 +505,18 @@ class MedTsLLM(nn.Module):
         self._ids_cache = (key if key is not None else object(), table, None)   # (+ shared-prefix length once measured)
         return table
 
+    def _ids_device(self, ids: torch.Tensor, dev) -> torch.Tensor:
+        """Device copy of the host id table, re-used while the prompts do not change (dataset / task prompts are static;
+        only clip descriptions, input statistics and examples vary per batch) — also what keeps host-to-device copies
+        out of a CUDA-graph capture."""
+        c = self._ids_cache
+        if c is not None and c[1] is ids and c[2] is not None and c[2].device == dev:
+            return c[2]
+        ids_dev = ids.to(dev, non_blocking=True)
+        if c is not None and c[1] is ids:
+            self._ids_cache = (c[0], c[1], ids_dev) + tuple(c[3:])
+        return ids_dev
+
     def _shared_prefix_len(self, ids: torch.Tensor, Bp: int, L: int, precise: bool = False) -> int:
         """Number of leading prompt positions (left padding included) that hold the same token in every
         sample of the batch.  The backbone is causal and the reference passes no padding mask
@@ -793,17 +805,7 @@ class MedTsLLM(nn.Module):
             ids = self.prompt_token_ids(inputs)
         Lp = ids.shape[1]
         L = Lp + N
-        ids_dev = None
-        if Lp > 0:
-            # device copy of the id table, re-used while the prompts do not change (dataset / task prompts are
-            # static; only clip descriptions and input statistics vary per batch)
-            c = self._ids_cache
-            if c is not None and c[1] is ids and c[2] is not None and c[2].device == dev:
-                ids_dev = c[2]
-            else:
-                ids_dev = ids.to(dev, non_blocking=True)
-                if c is not None and c[1] is ids:
-                    self._ids_cache = (c[0], c[1], ids_dev) + tuple(c[3:])
+        ids_dev = self._ids_device(ids, dev) if Lp > 0 else None
         # shared-prefix row layout: Lc leading prompt positions once, then Ls = L - Lc own rows per sequence
         # (not with live backbone dropouts: their masks differ per sample on the prompt rows too)
         bb_drop = self._backbone_dropout()

@@ -113,7 +113,7 @@ def forward_precise(m, inputs, ids=None):
         raise NotImplementedError("prompting.examples is implemented on the bf16 path only (set MTS_PRECISION=bf16)")
     Lp = ids.shape[1]
     L = Lp + N
-    ids_dev = ids.to(dev, non_blocking=True) if Lp > 0 else None
+    ids_dev = m._ids_device(ids, dev) if Lp > 0 else None
     Lc = m._shared_prefix_len(ids, Bp, L, precise=True)
     Ls = L - Lc
     X = f32(Lc + Bp * Ls, D)

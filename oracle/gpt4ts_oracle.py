@@ -45,12 +45,15 @@ def data_embedding(xn: torch.Tensor, w_conv: torch.Tensor) -> torch.Tensor:
     return val + positional_embedding(xn.shape[1], w_conv.shape[0])[None]
 
 
-def gpt4ts_forward(x_enc, params, gpt2_sd, spec, *, training: bool = False, return_stages: bool = False):
+def gpt4ts_forward(x_enc, params, gpt2_sd, spec, *, training: bool = False, return_stages: bool = False,
+                   dropout_masks=None):
     """GPT4TS.forward (models/gpt4ts.py:83-104) for the tasks the reference's Trainers run it on.
 
     params: the module's own tensors by reference name (enc_embedding.value_embedding.tokenConv.weight,
             predict_linear_pre.{weight,bias}, out_layer.{weight,bias}).
-    spec:   task, pred_len, d_ff, gpt_layers, n_heads, eps, n_classes, seg_mode."""
+    spec:   task, pred_len, d_ff, gpt_layers, n_heads, eps, n_classes, seg_mode.
+    dropout_masks (train mode): {"embed": multiplicative mask [B, T, d_model] of DataEmbedding.dropout
+            (models/layers/embed.py:131) or None, "backbone": the GPT-2 masks of medtsllm_oracle.gpt2_forward or None}."""
     B, T, C = x_enc.shape
     task = spec["task"]
     stages = {}
@@ -68,12 +71,15 @@ def gpt4ts_forward(x_enc, params, gpt2_sd, spec, *, training: bool = False, retu
     else:
         xn, mean, stdev = instance_norm(x_enc)
         enc = data_embedding(xn, params["enc_embedding.value_embedding.tokenConv.weight"])
+        if dropout_masks is not None and dropout_masks.get("embed") is not None:
+            enc = enc * dropout_masks["embed"]
         if task == "forecasting":                            # :137: Linear along time, T -> T + pred
             enc = F.linear(enc.permute(0, 2, 1), params["predict_linear_pre.weight"],
                            params["predict_linear_pre.bias"]).permute(0, 2, 1)
     stages["embedding"] = enc
     enc = F.pad(enc, (0, D - enc.shape[-1]))                 # :138, :164, :212, :242
-    dec = gpt2_forward(enc, gpt2_sd, n_layers=spec["gpt_layers"], n_heads=spec["n_heads"], eps=spec.get("eps", 1e-5))
+    dec = gpt2_forward(enc, gpt2_sd, n_layers=spec["gpt_layers"], n_heads=spec["n_heads"], eps=spec.get("eps", 1e-5),
+                       dropout=dropout_masks.get("backbone") if dropout_masks is not None else None)
     stages["gpt2"] = dec
     dec = F.linear(dec[:, :, : spec["d_ff"]], params["out_layer.weight"], params["out_layer.bias"])
     if task in ("forecasting", "anomaly_detection"):         # de-normalisation, :146-147, :172-175

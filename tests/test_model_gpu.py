@@ -675,6 +675,74 @@ def test_gpt4ts_training_gradients(name, cuda):
     assert not torch.equal(backbone.layers[0]["ln1"], before)
 
 
+@pytest.mark.parametrize("name", ["gpt4ts_forecast_etth1", "gpt4ts_semseg", "gpt4ts_anomaly"])
+def test_gpt4ts_training_with_dropout(name, cuda):
+    """the reference's GPT4TS trains with DataEmbedding.dropout(training.dropout) and with GPT-2's own 0.1
+    embd / attn / resid dropouts (model.train() flips the HF module).  Same scheme as MedTsLLM: counter-based masks read
+    back from the step's seeds and replayed in the oracle; forward and every trained tensor's gradient are compared."""
+    import copy
+    from medtsllm_b200 import ops
+    from medtsllm_b200.backbone import KernelBackbone
+    from medtsllm_b200.gpt4ts import GPT4TS
+    from oracle import gpt4ts_oracle as G
+    fix = load_case(name)
+    bbf = load_gpt4ts_backbone()
+    cfg = copy.deepcopy(fix["config"])
+    p_emb, p_bb = 0.1, 0.1
+    cfg["training"]["dropout"] = p_emb
+    n_layers = cfg["models"]["gpt4ts"]["gpt_layers"]
+    backbone = KernelBackbone.from_hf(gpt4ts_hf_model(bbf, n_layers), cuda)
+    model = GPT4TS(Cfg(cfg), Dataset(fix["dataset"]), backbone=backbone)
+    model.load_state_dict(fix["params"], strict=False)
+    model = model.to(cuda, torch.float32).train()
+    model.backbone_dropout = {"embd": p_bb, "attn": p_bb, "resid": p_bb}
+    x = fix["inputs"]["x_enc"]
+    torch.manual_seed(7)
+    out = model({"x_enc": x.to(cuda)})
+    drop = model._last_dropout
+    wgt = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * wgt.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    spec = gpt4ts_spec(fix, bbf)
+    B, T, C = x.shape
+    D, H = backbone.spec.hidden, backbone.spec.heads
+    T2 = T + (cfg["pred_len"] if cfg["task"] == "forecasting" else 0)
+    dm = cfg["models"]["gpt4ts"]["d_model"]
+
+    def mask(shape, prob, seed, dtype=torch.float32):
+        keep = ops.dropout(torch.ones(shape, device=cuda, dtype=dtype), prob, seed) != 0
+        return keep.float().cpu() / (1 - prob)
+
+    seeds = drop["bb"]["seeds"]
+    bbm = {"embd": mask((B, T2, D), p_bb, seeds[0]),
+           "attn": [mask((B, H, T2, T2), p_bb, seeds[1 + 3 * i]) for i in range(n_layers)],
+           "resid_attn": [mask((B, T2, D), p_bb, seeds[2 + 3 * i]) for i in range(n_layers)],
+           "resid_mlp": [mask((B, T2, D), p_bb, seeds[3 + 3 * i]) for i in range(n_layers)]}
+    emb_mask = None
+    if cfg["task"] != "anomaly_detection":
+        # forecasting: dropped on the bf16 [B, T, d_model] copy; segmentation tasks: on the fp32 [B, T, D] rows (d_model = D)
+        emb_mask = mask((B, T, dm), p_emb, drop["seed_embed"], torch.bfloat16 if cfg["task"] == "forecasting" else torch.float32)
+    params = {k: v.clone().requires_grad_(True) for k, v in fix["params"].items()}
+    sd = {k: v.float().requires_grad_(k.startswith("ln_f") or ".ln_" in k or k.startswith("wpe")) for k, v in bbf["state"].items()}
+    ref = G.gpt4ts_forward(x, params, sd, spec, training=True, dropout_masks={"embed": emb_mask, "backbone": bbm})
+    assert _rel_l2(out, ref) < 2e-2, _rel_l2(out, ref)
+    (ref * wgt).sum().backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        gref = sd[k[5:]].grad if k.startswith("gpt2.") else params[k].grad
+        if gref is None or gref.abs().max() == 0 or p.grad is None:
+            continue
+        if k == "predict_linear_pre.bias":            # structurally zero (see test_gpt4ts_training_gradients)
+            continue
+        e = _rel_l2(p.grad, gref)
+        assert e < 6e-2, (k, e)
+        checked += 1
+    assert checked >= 4 + 4 * n_layers
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model({"x_enc": x.to(cuda)}), model({"x_enc": x.to(cuda)})) and model._last_dropout is None
+
+
 @pytest.mark.parametrize("name,lora", [("llama_seg_concat", False), ("gpt2_anomaly_concat", False), ("llama_seg_concat", True)])
 def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda):
     """Training steps replay two captured CUDA graphs (forward + stash, backward chain) once the same step shape
