@@ -57,6 +57,7 @@ int mts_clear_caches(void);
  *               (tcgen05 cta_group::2, 256x256 tile per two SMs) when the cost model prefers it.
  *   "gemm_force" (0 auto | 1 single-CTA kernel | 2 CTA-pair kernel; default 0): override that cost model (experiments,
  *               tools/bench_gemm.py --force-sweep).
+ *   "streamk"   (0 off | 1 auto | 2 force; default 1, env MTS_STREAMK): see mts_gemm_args.sk_workspace.
  *   "pdl"       (0/1; default 1, env MTS_PDL=0): launch the per-layer kernels with programmatic stream serialization
  *               (their prologues overlap the previous kernel's tail; they block in griddepcontrol.wait before
  *               touching its results).
@@ -210,6 +211,18 @@ typedef struct mts_gemm_args {
    * HF:models/gpt2/modeling_gpt2.py:233, :243 resid_dropout).  0 = off. */
   float drop_p;
   uint64_t drop_seed;
+  /* Stream-K (optional, batch 1, bf16 or fp32 operands): when the output tiles do not fill the SMs evenly (small m:
+   * M = 800 .. 900 rows of the Ventilator / PSM configs leave 24 .. 60 % of the SMs idle or waiting on a last wave), the
+   * library deals the (tile, k-block) units out evenly over one CTA per SM instead; CTAs whose range starts inside a tile
+   * park their fp32 partial in `sk_workspace` first thing, the CTA holding the tile's first k-blocks adds them in
+   * ascending CTA order (deterministic) at the end of its own range and runs the epilogue.  The caller lends the scratch: sk_workspace >= #SMs * 128 * 256 * 4 bytes,
+   * sk_flags >= #SMs int32 (zero-initialised once; every flag raised by a launch is lowered again by its single reader,
+   * so launches and graph replays on one stream can share them), sk_epoch the non-zero "ready" value.  NULL workspace = never.  mts_set_option("streamk", 0 off | 1 auto (default) | 2 whenever legal). */
+  void* sk_workspace;
+  int64_t sk_workspace_bytes;
+  int32_t* sk_flags;
+  int32_t sk_flags_len;
+  int32_t sk_epoch;
 } mts_gemm_args;
 
 int mts_gemm(const mts_gemm_args* args, mts_stream_t stream);

@@ -36,6 +36,15 @@ struct GemmParams {
   uint32_t drop_thresh;
   float drop_scale;
   uint64_t drop_seed;
+  // stream-K (single-CTA kernel, batch 1): the (tile, k-block) units are dealt out evenly over the CTAs; a CTA whose
+  // range STARTS inside a tile parks its raw fp32 partial in sk_ws[slot = its CTA index] (always its first segment)
+  // and raises sk_flags[CTA] to sk_epoch; the CTA that holds the tile's FIRST k-blocks (its last segment) adds the
+  // partials in ascending CTA order (deterministic) and runs the epilogue.  Contributors never wait: no deadlock, and an
+  // owner finds the partials already there when it gets to the end of its own range.
+  int streamk;
+  float* sk_ws;
+  int* sk_flags;
+  int sk_epoch;
   int precise;     // fp32 operands (evaluation parity modes): accurate expf / tanhf in the activation epilogues
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)

@@ -33,6 +33,46 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kEpiStageBytes + 1024;
 };
 
+// Work of one CTA: plain = whole tiles blockIdx.x, +gridDim.x, ... ; stream-K = the contiguous range of (tile, k-block)
+// units [U*c/G, U*(c+1)/G) cut at tile boundaries.  All three warp roles walk the same sequence of segments.
+struct SegIter {
+  long long u, u_end;
+  int k_blocks, step;
+  bool streamk;
+};
+__device__ __forceinline__ SegIter seg_init(const GemmParams& p, int num_tiles, int k_blocks) {
+  SegIter s;
+  s.k_blocks = k_blocks;
+  s.streamk = p.streamk != 0;
+  if (s.streamk) {
+    const long long U = (long long)num_tiles * k_blocks;
+    s.u = U * blockIdx.x / gridDim.x;
+    s.u_end = U * (blockIdx.x + 1) / gridDim.x;
+    s.step = 0;
+  } else {
+    s.u = blockIdx.x;
+    s.u_end = num_tiles;
+    s.step = gridDim.x;
+  }
+  return s;
+}
+__device__ __forceinline__ bool seg_next(SegIter& s, int& tile, int& kb0, int& kb1) {
+  if (s.u >= s.u_end) return false;
+  if (s.streamk) {
+    tile = (int)(s.u / s.k_blocks);
+    kb0 = (int)(s.u - (long long)tile * s.k_blocks);
+    const long long rem = s.u_end - s.u;
+    kb1 = (long long)kb0 + rem < (long long)s.k_blocks ? (int)(kb0 + rem) : s.k_blocks;
+    s.u += kb1 - kb0;
+  } else {
+    tile = (int)s.u;
+    kb0 = 0;
+    kb1 = s.k_blocks;
+    s.u += s.step;
+  }
+  return true;
+}
+
 // TF32 = true: A and B are fp32 in global / shared memory and the tensor cores read them as TF32 (kind::tf32, K = 8 per
 // instruction).  A 128-byte swizzled smem row then holds 32 elements instead of 64, so a stage covers half the K extent
 // with the same bytes, the same descriptors and the same 4 MMAs; everything else is shared with the bf16 kernel.
@@ -108,7 +148,9 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      SegIter it_ = seg_init(p, num_tiles, k_blocks);
+      int tile, kb0, kb1;
+      while (seg_next(it_, tile, kb0, kb1)) {
         const int b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
         int m_blk, n_blk;
@@ -116,7 +158,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int seg = 0; seg < k_segments; ++seg) {
           const CUtensorMap* ma = (seg == 1) ? &tmap_a_lo : &tmap_a;
           const CUtensorMap* mb = (seg == 2) ? &tmap_b_lo : &tmap_b;
-          for (int kb = 0; kb < k_blocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
             mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_3d(smem_a + stage * Cfg::kABytes, ma, full_bar(stage), kb * kBK,
@@ -135,13 +177,16 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      SegIter it_ = seg_init(p, num_tiles, k_blocks);
+      int tile, kb0, kb1;
+      for (; seg_next(it_, tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < k_blocks * k_segments; ++kb) {
+        const int n_kb = (kb1 - kb0) * k_segments;
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_a + stage * Cfg::kABytes);
@@ -166,7 +211,9 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
     float* stage_buf = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) +
                        quarter * (32 * kEpiPitch);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    SegIter it_ = seg_init(p, num_tiles, k_blocks);
+    int tile, kb0, kb1;
+    for (; seg_next(it_, tile, kb0, kb1); ++it) {
       const int b = tile / tiles_per_batch;
       const int t = tile - b * tiles_per_batch;
       int m_blk, n_blk;
@@ -175,10 +222,77 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
-
-      epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk,
-                             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN),
-                             stage_buf, lane);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      bool run_epilogue = true;
+      if (p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
+        const int64_t slot_elems = (int64_t)kBlockM * BN;
+        const int64_t row_off = (int64_t)(quarter * 32 + lane) * BN;
+        if (kb0 > 0) {
+          // ---- contributor: this CTA's range STARTS inside the tile (always its first segment, so the partial is parked
+          // before anybody can be waiting for it).  Raw fp32 partial -> workspace slot, then the flag.
+          float* ws = p.sk_ws + (int64_t)blockIdx.x * slot_elems + row_off;
+#pragma unroll 1
+          for (int ci = 0; ci < BN / 32; ++ci) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + ci * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(ws + ci * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+          if (threadIdx.x == 64) st_release_gpu(p.sk_flags + blockIdx.x, p.sk_epoch);
+          run_epilogue = false;
+        } else {
+          // ---- owner: holds the tile's FIRST k-blocks (the last segment of its range).  The CTAs that hold the rest — a
+          // run of consecutive higher CTA indices, each of which parked its partial at the very start of its own range —
+          // are added into the TMEM accumulator in ascending order, then the ordinary epilogue runs.
+          const long long U = (long long)num_tiles * k_blocks, G = gridDim.x;
+          const long long last_unit = (long long)(tile + 1) * k_blocks - 1;
+          int c_last = (int)(last_unit * G / U);
+          while (U * (c_last + 1) / G <= last_unit) ++c_last;
+          while (U * c_last / G > last_unit) --c_last;
+          for (int cc = (int)blockIdx.x + 1; cc <= c_last; ++cc) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(p.sk_flags + cc) != p.sk_epoch) {
+              if (clock64() - t0 > MTS_WATCHDOG_CYCLES) {
+                printf("[mtsb200] watchdog: block %d stuck waiting for the stream-K partial of block %d\n", (int)blockIdx.x, cc);
+                __trap();
+              }
+            }
+          }
+#pragma unroll 1
+          for (int ci = 0; ci < BN / 32; ++ci) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + ci * 32, r);
+            tmem_ld_wait();
+            for (int cc = (int)blockIdx.x + 1; cc <= c_last; ++cc) {
+              const float* ws = p.sk_ws + (int64_t)cc * slot_elems + row_off + ci * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
+                r[j] = __float_as_uint(__uint_as_float(r[j]) + v.x);
+                r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + v.y);
+                r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + v.z);
+                r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + v.w);
+              }
+            }
+            tmem_st_32x32(taddr + ci * 32, r);
+            tmem_st_wait();
+          }
+          __syncwarp();
+          // every partial has exactly one reader: lower the flags again, so that the next launch — or the next replay of
+          // a captured graph, which carries the same sk_epoch — starts from "not ready"
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64)
+            for (int cc = (int)blockIdx.x + 1; cc <= c_last; ++cc) st_release_gpu(p.sk_flags + cc, 0);
+        }
+      }
+      if (run_epilogue)
+        epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr, stage_buf, lane);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -212,7 +326,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(gemm smem)", e);
     attr_done = true;
   }
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  // stream-K: one CTA per SM, each takes an equal share of the (tile, k-block) units
+  const int grid = p.streamk ? num_sms() : (num_tiles < num_sms() ? num_tiles : num_sms());
   cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p,
                               (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
   if (le != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_kernel)", le);
@@ -262,6 +377,15 @@ bool gemm_2cta_enabled() {
   }
   return g_gemm_2cta == 1;
 }
+static int g_streamk = -1;        // 0 off | 1 auto | 2 whenever legal
+static int streamk_mode() {
+  if (g_streamk < 0) {
+    const char* e = getenv("MTS_STREAMK");
+    g_streamk = e ? atoi(e) : 1;
+    if (g_streamk < 0 || g_streamk > 2) g_streamk = 1;
+  }
+  return g_streamk;
+}
 static int g_gemm_force = 0;      // mts_set_option("gemm_force", 0 auto | 1 single-CTA kernel | 2 CTA-pair kernel): experiments
 static int g_pdl = -1;
 bool pdl_enabled() {
@@ -275,12 +399,13 @@ bool pdl_enabled() {
 
 using namespace mts;
 
-static_assert(sizeof(mts_gemm_args) == 216, "mts_gemm_args layout is part of the C ABI (ctypes mirror: _lib.GemmArgs)");
+static_assert(sizeof(mts_gemm_args) == 248, "mts_gemm_args layout is part of the C ABI (ctypes mirror: _lib.GemmArgs)");
 
 extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
+  if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 1 : value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
@@ -352,6 +477,23 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   }
   if (a->c && a->epilogue != MTS_EPI_RESID_ADD)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: c is only used by MTS_EPI_RESID_ADD");
+  // ---- stream-K: worth it when whole tiles leave the SMs unevenly loaded (small m) and every CTA still gets a few k-blocks
+  int use_sk = 0;
+  {
+    const int skm = streamk_mode();
+    const int kb_elems = (a->ab_dtype == MTS_F32) ? kBlockK / 2 : kBlockK;
+    if (skm != 0 && a->sk_workspace && a->sk_flags && a->batch == 1 && g_gemm_force != 2 &&
+        (reinterpret_cast<uintptr_t>(a->sk_workspace) & 15) == 0 && a->sk_flags_len >= num_sms()) {
+      int bn_sk = bn != 0 ? bn : (a->n >= 2048 ? 256 : 128);
+      const long tiles = (long)((a->m + kBlockM - 1) / kBlockM) * ((a->n + bn_sk - 1) / bn_sk);
+      const long kbs = (a->k + kb_elems - 1) / kb_elems;
+      const long G = num_sms();
+      const double eff = (double)tiles / (double)(((tiles + G - 1) / G) * G);
+      const bool fits = a->sk_workspace_bytes >= (int64_t)G * kBlockM * bn_sk * 4;
+      const bool enough = tiles * kbs >= 4 * G && kbs >= 4;
+      if (fits && enough && (skm == 2 || eff < 0.85)) { use_sk = 1; bn = bn_sk; }
+    }
+  }
   if (bn == 0) bn = pick_block_n(a->m, a->n, a->batch);
   if (bn != 64 && bn != 128 && bn != 256)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: block_n must be 0, 64, 128 or 256");
@@ -393,6 +535,10 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   }
   p.round_tf32 = (a->round_tf32 && f32) ? 1 : 0;
   p.precise = tf32 ? 1 : 0;
+  p.streamk = use_sk;
+  p.sk_ws = static_cast<float*>(a->sk_workspace);
+  p.sk_flags = a->sk_flags;
+  p.sk_epoch = a->sk_epoch;
   p.aux = nullptr; p.ld_aux = 0;
   if (a->aux && tf32) return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: aux is a training (bf16) feature");
   if (a->aux) {
@@ -429,7 +575,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
       default: return dispatch_epi<64, true>(a->epilogue, ta, tb, p, (int)tl, stream);
     }
   }
-  if (bn == 256 && !a->d_transposed && gemm_2cta_enabled()) {
+  if (bn == 256 && !a->d_transposed && gemm_2cta_enabled() && !use_sk) {
     // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them
     // unless the 256-row granularity wastes more than it saves (odd / single 128-row block counts).
     const long nb256 = (a->n + 255) / 256;

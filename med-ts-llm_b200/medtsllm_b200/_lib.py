@@ -38,6 +38,8 @@ class GemmArgs(C.Structure):
         ("ab_dtype", C.c_int32), ("round_tf32", C.c_int32),
         ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint64),
+        ("sk_workspace", C.c_void_p), ("sk_workspace_bytes", C.c_int64), ("sk_flags", C.c_void_p),
+        ("sk_flags_len", C.c_int32), ("sk_epoch", C.c_int32),
     ]
 
 

@@ -33,6 +33,22 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
+_SK_SCRATCH: dict = {}
+
+
+def _streamk_scratch(device, stream):
+    """Scratch the library may use for stream-K (include/mts_b200.h, mts_gemm_args.sk_workspace): one partial-tile slot
+    and one flag per SM, per (device, stream) — launches on one stream are ordered, so they can share it."""
+    key = (device.index, stream)
+    hit = _SK_SCRATCH.get(key)
+    if hit is None:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        hit = (torch.empty(sms * 128 * 256, device=device, dtype=torch.float32),
+               torch.zeros(sms, device=device, dtype=torch.int32))
+        _SK_SCRATCH[key] = hit
+    return hit
+
+
 def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_bs=0, d_bs=0,
          bias=None, bias_axis=BIAS_NONE, epilogue=EPI_STORE, alpha=1.0, d_transposed=False,
          block_n=0, a_off=0, b_off=0, d_off=0, c=None, rope=None, rope_L=0, rope_hd=0, rope_cols=0,
@@ -70,6 +86,11 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.ab_dtype = MTS_F32 if ab == torch.float32 else MTS_BF16
     args.round_tf32 = 1 if round_tf32 else 0
     args.drop_p, args.drop_seed = float(drop_p), int(drop_seed) & (2 ** 64 - 1)
+    stream = _stream()
+    if batch == 1:
+        ws, flags = _streamk_scratch(d.device, stream)
+        args.sk_workspace, args.sk_workspace_bytes = ws.data_ptr(), ws.numel() * 4
+        args.sk_flags, args.sk_flags_len, args.sk_epoch = flags.data_ptr(), flags.numel(), 1
     if (a_lo is None) != (b_lo is None):
         raise MtsError("a_lo and b_lo go together (3xTF32 split)")
     if a_lo is not None:
@@ -86,7 +107,7 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     if aux is not None:
         _chk(aux, torch.bfloat16, "aux")
         args.aux, args.ld_aux = aux.data_ptr(), aux.shape[-1]
-    _lib.call("mts_gemm", C.byref(args), _stream())
+    _lib.call("mts_gemm", C.byref(args), stream)
     return d
 
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"{sym} declared in include/mts_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     assert _lib.version() == 2
-    assert ctypes.sizeof(_lib.GemmArgs) == 216      # layout of mts_gemm_args (8-byte aligned)
+    assert ctypes.sizeof(_lib.GemmArgs) == 248      # layout of mts_gemm_args (8-byte aligned)
 
 
 def test_no_cpu_fallback():

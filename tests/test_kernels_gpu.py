@@ -780,3 +780,73 @@ def test_input_stats_kernel(ops, cuda, B, T, C, f0, csel):
         for i, k in enumerate(seen):
             if 0 < k < T // 2 and (T - k) in seen:
                 assert seen.index(T - k) > i, seen
+
+
+# --------------------------------------------------------------------------------------------- stream-K
+@pytest.mark.parametrize("m,n,k,epi", [(800, 4096, 4096, 1), (800, 4096, 11008, 1), (896, 1024, 4096, 1), (896, 3072, 1024, 0),
+                                        (896, 4096, 1024, 2), (800, 12288, 4096, 0), (300, 520, 2048, 0), (128, 256, 8192, 0),
+                                        (130, 4096, 512, 1)])
+def test_gemm_streamk_matches_plain_schedule(ops, cuda, m, n, k, epi):
+    """Stream-K (mts_gemm_args.sk_workspace; forced here) against the plain whole-tile schedule of the same kernel and
+    against the fp32 reference: the (tile, k-block) units are dealt out evenly over one CTA per SM, partial tiles are
+    summed by the tile's owner in ascending CTA order — deterministic, and equal to the plain result up to the fp32
+    regrouping of the k-sum."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    b = (torch.randn(n, k, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(cuda) if epi == 2 else None
+    c0 = torch.randn(m, n, generator=g).to(cuda)
+
+    def run(mode):
+        _lib.set_option("streamk", mode)
+        d = c0.clone() if epi == 1 else torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
+        ops.gemm(a, b, d, m=m, n=n, k=k, epilogue=epi, bias=bias, bias_axis=1 if bias is not None else 0)
+        return d
+
+    try:
+        plain = run(0)
+        sk1, sk2 = run(2), run(2)
+    finally:
+        _lib.set_option("streamk", 1)
+    assert torch.equal(sk1, sk2)                                   # deterministic
+    z = a.float() @ b.float().t()
+    if epi == 1:
+        ref = c0 + z
+    elif epi == 2:
+        z = z + bias
+        ref = 0.5 * z * (1 + torch.tanh(math.sqrt(2 / math.pi) * (z + 0.044715 * z ** 3)))
+    else:
+        ref = z
+    tol = dict(rtol=1e-4, atol=1e-3) if epi == 1 else dict(rtol=8e-3, atol=2e-2)
+    torch.testing.assert_close(sk1.float(), ref, **tol)
+    torch.testing.assert_close(sk1.float(), plain.float(), **tol)
+
+
+def test_gemm_streamk_under_graph_replay(ops, cuda):
+    """The flags a launch raises are lowered again by their single reader, so a captured graph (same arguments on every
+    replay) can be replayed back to back."""
+    from medtsllm_b200 import _lib
+    m, n, k = 800, 4096, 4096
+    g = torch.Generator().manual_seed(1)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    b = (torch.randn(n, k, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    d = torch.empty(m, n, device=cuda, dtype=torch.bfloat16)
+    _lib.set_option("streamk", 2)
+    try:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ops.gemm(a, b, d, m=m, n=n, k=k)
+            s.synchronize()
+            ref = d.clone()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                for _ in range(3):
+                    ops.gemm(a, b, d, m=m, n=n, k=k)
+            for _ in range(4):
+                d.zero_()
+                graph.replay()
+                s.synchronize()
+                assert torch.equal(d, ref)
+    finally:
+        _lib.set_option("streamk", 1)

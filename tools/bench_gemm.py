@@ -22,14 +22,28 @@ shapes = [  # (name, m, n, k, epilogue, block_n)
     ("gpt2m_fc_gelu", 8960, 4096, 1024, 2, 0),
     ("gpt2m_proj_resid", 8960, 1024, 4096, 1, 0),
     ("mapping", 1024, 4096, 32000, 0, 0),
+    # small-M regime (shared-prefix row counts of Ventilator: 128 + 16*42 = 800, PSM: 128 + 64*12 = 896)
+    ("vent_qkv", 800, 12288, 4096, 0, 0),
+    ("vent_o_resid", 800, 4096, 4096, 1, 0),
+    ("vent_gateup_swiglu", 800, 22016, 4096, 3, 256),
+    ("vent_down_resid", 800, 4096, 11008, 1, 0),
+    ("psm_qkv", 896, 3072, 1024, 0, 0),
+    ("psm_o_resid", 896, 1024, 1024, 1, 0),
+    ("psm_fc_gelu", 896, 4096, 1024, 2, 0),
+    ("psm_proj_resid", 896, 1024, 4096, 1, 0),
 ]
 from medtsllm_b200 import _lib
 res = []
 force_modes = [0, 1, 2] if "--force-sweep" in sys.argv else [0]      # auto / single-CTA kernel / CTA-pair kernel
 if "--shared-prefix-only" in sys.argv:
     shapes = shapes[:4]
-for (name, m, n, k, epi, bn), force in ((sh, f) for sh in shapes for f in force_modes):
+if "--small-m" in sys.argv:
+    shapes = shapes[-8:]
+sk_modes = [0, 1, 2] if "--streamk-sweep" in sys.argv else [None]
+for (name, m, n, k, epi, bn), force, skm in ((sh, f, sk) for sh in shapes for f in force_modes for sk in sk_modes):
     _lib.set_option("gemm_force", force)
+    if skm is not None:
+        _lib.set_option("streamk", skm)
     nrot = 3
     A = [torch.randn(m, k, device=dev).to(torch.bfloat16) for _ in range(nrot)]
     B = [(torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16) for _ in range(nrot)]
@@ -55,7 +69,7 @@ for (name, m, n, k, epi, bn), force in ((sh, f) for sh in shapes for f in force_
     e1.record(); torch.cuda.synchronize()
     ms_cublas = e0.elapsed_time(e1) / iters
     fl = 2.0 * m * n * k
-    r = dict(name=name, force=force, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+    r = dict(name=name, force=force, streamk=skm, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
              cublas_ms=round(ms_cublas, 4), cublas_tflops=round(fl / ms_cublas / 1e9, 1))
     print(json.dumps(r), flush=True)
     res.append(r)
