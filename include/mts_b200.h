@@ -57,7 +57,7 @@ int mts_clear_caches(void);
  *               (tcgen05 cta_group::2, 256x256 tile per two SMs) when the cost model prefers it.
  *   "gemm_force" (0 auto | 1 single-CTA kernel | 2 CTA-pair kernel; default 0): override that cost model (experiments,
  *               tools/bench_gemm.py --force-sweep).
- *   "streamk"   (0 off | 1 auto | 2 force; default 1, env MTS_STREAMK): see mts_gemm_args.sk_workspace.
+ *   "streamk"   (0 off | 1 auto | 2 force; default 0, env MTS_STREAMK): see mts_gemm_args.sk_workspace.
  *   "pdl"       (0/1; default 1, env MTS_PDL=0): launch the per-layer kernels with programmatic stream serialization
  *               (their prologues overlap the previous kernel's tail; they block in griddepcontrol.wait before
  *               touching its results).
@@ -217,7 +217,8 @@ typedef struct mts_gemm_args {
    * park their fp32 partial in `sk_workspace` first thing, the CTA holding the tile's first k-blocks adds them in
    * ascending CTA order (deterministic) at the end of its own range and runs the epilogue.  The caller lends the scratch: sk_workspace >= #SMs * 128 * 256 * 4 bytes,
    * sk_flags >= #SMs int32 (zero-initialised once; every flag raised by a launch is lowered again by its single reader,
-   * so launches and graph replays on one stream can share them), sk_epoch the non-zero "ready" value.  NULL workspace = never.  mts_set_option("streamk", 0 off | 1 auto (default) | 2 whenever legal). */
+   * so launches and graph replays on one stream can share them), sk_epoch the non-zero "ready" value.  NULL workspace = never.  mts_set_option("streamk", 0 off (default) | 1 auto | 2 whenever legal): experimental — on B200 the
+   * plain whole-tile schedule is faster at every BASELINE shape (profiles/r02_streamk_gemm.md). */
   void* sk_workspace;
   int64_t sk_workspace_bytes;
   int32_t* sk_flags;

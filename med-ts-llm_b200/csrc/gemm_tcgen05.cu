@@ -377,12 +377,15 @@ bool gemm_2cta_enabled() {
   }
   return g_gemm_2cta == 1;
 }
-static int g_streamk = -1;        // 0 off | 1 auto | 2 whenever legal
+// 0 off (default) | 1 auto (uneven whole-tile schedules) | 2 whenever legal.  Off by default: measured on B200
+// (profiles/r02_streamk_gemm.md) the contiguous unit ranges spread the concurrently live weight strips over the whole B
+// matrix and the fix-up serialises at the end of every CTA; the plain schedule wins at every BASELINE shape today.
+static int g_streamk = -1;
 static int streamk_mode() {
   if (g_streamk < 0) {
     const char* e = getenv("MTS_STREAMK");
-    g_streamk = e ? atoi(e) : 1;
-    if (g_streamk < 0 || g_streamk > 2) g_streamk = 1;
+    g_streamk = e ? atoi(e) : 0;
+    if (g_streamk < 0 || g_streamk > 2) g_streamk = 0;
   }
   return g_streamk;
 }
@@ -405,7 +408,7 @@ extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
-  if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 1 : value; return MTS_OK; }
+  if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 0 : value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }
 

@@ -808,7 +808,7 @@ def test_gemm_streamk_matches_plain_schedule(ops, cuda, m, n, k, epi):
         plain = run(0)
         sk1, sk2 = run(2), run(2)
     finally:
-        _lib.set_option("streamk", 1)
+        _lib.set_option("streamk", 0)
     assert torch.equal(sk1, sk2)                                   # deterministic
     z = a.float() @ b.float().t()
     if epi == 1:
@@ -849,4 +849,4 @@ def test_gemm_streamk_under_graph_replay(ops, cuda):
                 s.synchronize()
                 assert torch.equal(d, ref)
     finally:
-        _lib.set_option("streamk", 1)
+        _lib.set_option("streamk", 0)
