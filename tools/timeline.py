@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="evaluation precision mode (fwd only): tf32 / fp32 = the parity modes of precise.py")
     args = ap.parse_args()
     from medtsllm_b200.backbone import KernelBackbone
     from medtsllm_b200.model import MedTsLLM
@@ -42,7 +44,7 @@ def main():
                                          experiment_config, make_inputs)
     dev = torch.device("cuda", 0)
     w = WORKLOADS[args.workload]
-    bb = KernelBackbone.random_init(w.backbone, dev, seed=0)
+    bb = KernelBackbone.random_init(w.backbone, dev, seed=0, precision=args.precision)
     torch.manual_seed(0)
     model = MedTsLLM(AttrDict(experiment_config(w)), SyntheticDataset(w), backbone=bb,
                      tokenizer=FixedLengthTokenizer(w.backbone.vocab, w.prompt_len)).to(dev, torch.float32)
@@ -100,7 +102,7 @@ def main():
         busy += max(0.0, s + d - max(cur_end, s))
         cur_end = max(cur_end, s + d)
     idle = span - busy
-    lines = [f"# Kernel timeline — {args.workload}, {args.mode} step ({'kernel by kernel' if args.no_graph else 'graph replay'})", "",
+    lines = [f"# Kernel timeline — {args.workload}, {args.mode} step, precision {args.precision} ({'kernel by kernel' if args.no_graph else 'graph replay'})", "",
              f"CUPTI (torch.profiler), one warm step on one B200; {len(ev)} device activities.", "",
              f"* step span (first kernel start -> last kernel end): **{span / 1e3:.3f} ms**",
              f"* device busy (union of kernel intervals): {busy / 1e3:.3f} ms = {100 * busy / span:.1f} % of the span",
