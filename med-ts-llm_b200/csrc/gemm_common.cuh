@@ -212,13 +212,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
                   pack_bf16(__uint_as_float(u[j + 6]) * p.alpha, __uint_as_float(u[j + 7]) * p.alpha));
             }
           }
+          if (p.precise) {        // evaluation parity modes: library-accurate expf (warp-uniform branch, hoisted)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // the activation is computed from the bf16-rounded pre-activations when they are kept, so that the
-            // saved tensors reproduce exactly what the forward used
-            float gv = __uint_as_float(g[j]) * p.alpha, uv = __uint_as_float(u[j]) * p.alpha;
-            if (p.aux != nullptr) { gv = __bfloat162float(__float2bfloat16_rn(gv)); uv = __bfloat162float(__float2bfloat16_rn(uv)); }
-            v[j] = (p.precise ? silu_precise_f(gv) : silu_f(gv)) * uv;
+            for (int j = 0; j < 32; ++j)
+              v[j] = silu_precise_f(__uint_as_float(g[j]) * p.alpha) * (__uint_as_float(u[j]) * p.alpha);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              // the activation is computed from the bf16-rounded pre-activations when they are kept, so that the
+              // saved tensors reproduce exactly what the forward used
+              float gv = __uint_as_float(g[j]) * p.alpha, uv = __uint_as_float(u[j]) * p.alpha;
+              if (p.aux != nullptr) { gv = __bfloat162float(__float2bfloat16_rn(gv)); uv = __bfloat162float(__float2bfloat16_rn(uv)); }
+              v[j] = silu_f(gv) * uv;
+            }
           }
         } else {
           uint32_t r[32];

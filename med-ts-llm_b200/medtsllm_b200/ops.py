@@ -34,6 +34,15 @@ def _ptr(t):
 # GEMM
 # ------------------------------------------------------------------------------------------------
 _SK_SCRATCH: dict = {}
+_STREAMK_MODE = 0
+
+
+def set_streamk(mode: int) -> None:
+    """0 off (default) | 1 auto | 2 whenever legal — mts_set_option("streamk") plus the scratch the library needs for it
+    (only lent while the mode is on: experimental, see profiles/r02_streamk_gemm.md)."""
+    global _STREAMK_MODE
+    _lib.set_option("streamk", int(mode))
+    _STREAMK_MODE = int(mode)
 
 
 def _streamk_scratch(device, stream):
@@ -87,7 +96,7 @@ def gemm(a, b, d, *, m, n, k, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     args.round_tf32 = 1 if round_tf32 else 0
     args.drop_p, args.drop_seed = float(drop_p), int(drop_seed) & (2 ** 64 - 1)
     stream = _stream()
-    if batch == 1:
+    if batch == 1 and _STREAMK_MODE:
         ws, flags = _streamk_scratch(d.device, stream)
         args.sk_workspace, args.sk_workspace_bytes = ws.data_ptr(), ws.numel() * 4
         args.sk_flags, args.sk_flags_len, args.sk_epoch = flags.data_ptr(), flags.numel(), 1

@@ -799,7 +799,7 @@ def test_gemm_streamk_matches_plain_schedule(ops, cuda, m, n, k, epi):
     c0 = torch.randn(m, n, generator=g).to(cuda)
 
     def run(mode):
-        _lib.set_option("streamk", mode)
+        ops.set_streamk(mode)
         d = c0.clone() if epi == 1 else torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
         ops.gemm(a, b, d, m=m, n=n, k=k, epilogue=epi, bias=bias, bias_axis=1 if bias is not None else 0)
         return d
@@ -808,7 +808,7 @@ def test_gemm_streamk_matches_plain_schedule(ops, cuda, m, n, k, epi):
         plain = run(0)
         sk1, sk2 = run(2), run(2)
     finally:
-        _lib.set_option("streamk", 0)
+        ops.set_streamk(0)
     assert torch.equal(sk1, sk2)                                   # deterministic
     z = a.float() @ b.float().t()
     if epi == 1:
@@ -832,7 +832,7 @@ def test_gemm_streamk_under_graph_replay(ops, cuda):
     a = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
     b = (torch.randn(n, k, generator=g) * 0.05).to(cuda, torch.bfloat16)
     d = torch.empty(m, n, device=cuda, dtype=torch.bfloat16)
-    _lib.set_option("streamk", 2)
+    ops.set_streamk(2)
     try:
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
@@ -849,4 +849,4 @@ def test_gemm_streamk_under_graph_replay(ops, cuda):
                 s.synchronize()
                 assert torch.equal(d, ref)
     finally:
-        _lib.set_option("streamk", 0)
+        ops.set_streamk(0)

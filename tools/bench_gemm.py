@@ -43,7 +43,7 @@ sk_modes = [0, 1, 2] if "--streamk-sweep" in sys.argv else [None]
 for (name, m, n, k, epi, bn), force, skm in ((sh, f, sk) for sh in shapes for f in force_modes for sk in sk_modes):
     _lib.set_option("gemm_force", force)
     if skm is not None:
-        _lib.set_option("streamk", skm)
+        ops.set_streamk(skm)
     nrot = 3
     A = [torch.randn(m, k, device=dev).to(torch.bfloat16) for _ in range(nrot)]
     B = [(torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16) for _ in range(nrot)]
