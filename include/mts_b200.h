@@ -381,6 +381,11 @@ int mts_softmax_rows_f32(const float* s, float* p, int64_t rows, int n, float sc
  *   round_out != 0: store the result rounded to TF32 (operand of the out-projection in "tf32" mode).  hd in {64, 128}. */
 int mts_attn_causal_f32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, int hd, float scale,
                         int round_out, mts_stream_t stream);
+/* The same attention with both contractions on the tensor cores in TF32 (mma.sync m16n8k8; q / k / v / P rounded to
+ * nearest TF32, softmax and accumulation fp32): the attention of the "tf32" mode — in the reference's evaluation regime
+ * Q K^T and P V are TF32 matmuls as well (tasks/base.py:19-22).  Same arguments and layouts as mts_attn_causal_f32. */
+int mts_attn_causal_tf32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                         int round_out, mts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Training path (adapter gradients; dgrad through the frozen backbone)                        */

@@ -1,0 +1,455 @@
+// attention_tc.cu — causal attention forward for the short sequences of this path (prompt + patches, L <= 256) on the
+// 5th-generation tensor cores.  Reference op: HF eager attention, HF:models/llama/modeling_llama.py:199-221 and
+// HF:models/gpt2/modeling_gpt2.py:54-72 (softmax(Q K^T / sqrt(hd) + causal mask) V), q / k already rotated.
+//
+// One job = up to 128 query rows that are contiguous in the row layout (several whole samples' own tokens, or one
+// 128-row tile of a longer sequence) against at most 256 keys, so the whole score tile lives in tensor memory and the
+// softmax is a single pass (no running maximum, no rescaling of the output):
+//
+//   TMA      Q [128 x hd], K and V [keys x hd] (16-row boxes, 128B swizzle) -> shared memory
+//   tcgen05  S[128 x keys] = Q K^T            (kind::f16, fp32 accumulators: 256 TMEM columns)
+//   4 warps  thread = query row: row maximum and exp2 straight out of TMEM (tcgen05.ld), P (bf16) written into
+//            128B-swizzled K-major shared memory, row sum kept in a register
+//   tcgen05  O[128 x hd] = P V                (V consumed MN-major, exactly as TMA delivers its rows; 128 TMEM columns)
+//   4 warps  O / rowsum -> bf16 rows in global memory (+ log-sum-exp for the backward)
+//
+// Key columns of a job: [keys every row sees: the shared prompt prefix] followed by one 16-aligned column segment per
+// sample for (the earlier tiles of the same sequence and) its own, causally masked keys; a segment starts with
+// Lc mod 16 dummy columns (its first 16-row box simply begins that many rows early).  Every key therefore sits at a column
+// that is congruent to its POSITION modulo 16 and in position order, masked columns contribute exact zeros and the row
+// sum runs strictly left to right: a row's result does not depend on which other samples share its tile, nor on whether
+// the prompt prefix is stored once (shared-prefix layout) or per sample — bit-identical outputs either way.
+//
+// A CTA (one per SM, persistent) walks a contiguous range of jobs, head-major, so that the prefix K / V of a head stay
+// resident in shared memory across its jobs.  Warp roles: 0-3 softmax + epilogue (TMEM lane quarters), 4 TMA producer,
+// 5 MMA issuer; the S MMA of job i+1 is issued right behind the O MMA of job i and overlaps epilogue i.
+//
+// Algorithmic work per launch: 4 * hd * (visible query-key pairs) FLOP (roofline: tensor pipe).
+#include <stdlib.h>
+
+#include "mts_internal.h"
+#include "ptx.cuh"
+
+namespace mts {
+
+constexpr int kTcThreads = 192;
+
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  float* lse;
+  int Bp, Lc, Ls, H, D;          // Lc = 0: plain layout (Ls = L positions per sample)
+  int n_pt;                      // 128-row tiles of the shared prefix (per head)
+  int n_qt;                      // 128-row tiles per sample; 1: several samples share a job
+  int spj;                       // samples per job (n_qt == 1)
+  int jobs_per_head, n_jobs;
+  float scale_log2e;
+  long long* dbg;                // MTS_ATTN_TC_DBG=1: clock64 stamps of block 0 (debug)
+};
+#define TC_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
+
+struct TcJob {
+  int head, q_row0, R;           // query rows: global rows [q_row0, q_row0 + R)
+  int Ls, nseg;                  // rows per sample, samples in the job
+  int na, na16;                  // prefix keys every row sees: global rows [0, na) in columns [0, na); na16 = na rounded up to 16
+  int nb;                        // earlier own rows of the (single) sample, also seen by every row: global rows [q_row0 - nb, q_row0)
+  int e, Lsp;                    // segment of sample s: columns [na16 + s*Lsp, +Lsp) <- global rows q_row0 - nb + s*Ls - e + [0, Lsp);
+                                 // its keys start e columns in (e = Lc mod 16 keeps column = position modulo 16)
+  int nk;                        // key columns in all (multiple of 16, <= 256)
+  int64_t lse_off;               // lse index of local row r: lse_off + (r / Ls) * lse_stride + r % Ls
+  int lse_stride;
+};
+
+__device__ __forceinline__ TcJob tc_decode(const AttnTcParams& p, int job) {
+  TcJob j;
+  j.head = job / p.jobs_per_head;
+  int i = job - j.head * p.jobs_per_head;
+  j.nb = 0; j.lse_stride = 0; j.e = 0;
+  if (i < p.n_pt) {                        // tile i of the prefix: an ordinary causal sequence of Lc positions
+    j.q_row0 = 128 * i;
+    j.R = min(128, p.Lc - 128 * i);
+    j.Ls = j.R; j.nseg = 1;
+    j.na = 0; j.nb = 128 * i;
+    j.lse_off = (int64_t)j.head * p.Lc + 128 * i;
+  } else {
+    i -= p.n_pt;
+    const int64_t lse_s = (int64_t)p.H * p.Lc;          // the samples' part follows the prefix part
+    j.na = p.Lc;
+    j.e = p.Lc & 15;
+    if (p.n_qt == 1) {                     // samples b0s .. b0s + nseg - 1, all their own rows
+      const int b0s = i * p.spj;
+      j.nseg = min(p.spj, p.Bp - b0s);
+      j.q_row0 = p.Lc + b0s * p.Ls;
+      j.R = j.nseg * p.Ls;
+      j.Ls = p.Ls;
+      j.lse_off = lse_s + ((int64_t)b0s * p.H + j.head) * p.Ls;
+      j.lse_stride = p.H * p.Ls;
+    } else {                               // tile t of sample b: its earlier own rows are keys every row of the tile sees
+      const int b = i / p.n_qt, t = i - b * p.n_qt;
+      j.nseg = 1;
+      j.q_row0 = p.Lc + b * p.Ls + 128 * t;
+      j.R = min(128, p.Ls - 128 * t);
+      j.Ls = j.R;
+      j.nb = 128 * t;
+      j.lse_off = lse_s + ((int64_t)b * p.H + j.head) * p.Ls + 128 * t;
+    }
+  }
+  j.na16 = (j.na + 15) & ~15;
+  j.Lsp = j.nb + ((j.e + j.Ls + 15) & ~15);
+  j.nk = j.na16 + j.nseg * j.Lsp;
+  return j;
+}
+
+// 2^x on the special-function unit, one instruction (results below 2^-126 flush to zero: far below bf16 resolution of P)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MN-major, 128B-swizzled shared-memory matrix descriptor: rows of the K dimension (keys) are 128 bytes (64 bf16 of the
+// MN dimension) apart, 8-row groups 1024 bytes (SBO), the next 64 elements of the MN dimension `lbo` bytes further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int HD>
+struct AttnTcCfg {
+  static constexpr int KB = HD / 64;                  // 64-column blocks of the head dim
+  static constexpr int kSlabQ = 128 * 128;            // bytes: 128 query rows x 128 B
+  static constexpr int kSlabKV = 256 * 128;           // 256 key rows x 128 B
+  static constexpr int kSlabP = 128 * 128;            // 128 query rows x 64 keys
+  static constexpr int kOffK = KB * kSlabQ;
+  static constexpr int kOffV = kOffK + KB * kSlabKV;
+  static constexpr int kOffP = kOffV + KB * kSlabKV;
+  static constexpr int kOffBar = kOffP + 4 * kSlabP;
+  static constexpr int kSmemBytes = kOffBar + 128 + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                   const AttnTcParams p) {
+  using Cfg = AttnTcCfg<HD>;
+  constexpr int KB = Cfg::KB;
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = tc_smem_raw + (base - smem_u32(tc_smem_raw));
+  const uint32_t sQ = base, sK = base + Cfg::kOffK, sV = base + Cfg::kOffV, sP = base + Cfg::kOffP;
+  const uint32_t bar = base + Cfg::kOffBar;
+  const uint32_t q_full = bar, v_full = bar + 8, q_empty = bar + 16, v_empty = bar + 24, s_full = bar + 32,
+                 p_full = bar + 40, o_full = bar + 48, tmem_slot = bar + 56;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1); mbar_init(v_full, 1); mbar_init(q_empty, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(base_ptr + Cfg::kOffBar + 56);
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) TC_STAMP(0);
+
+  const int j_begin = (int)((long long)p.n_jobs * blockIdx.x / gridDim.x);
+  const int j_end = (int)((long long)p.n_jobs * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ph = 0;
+      int res_head = -1, res_na = -1;            // prefix rows [0, res_na) of head res_head are resident in the slabs
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+        const TcJob jb = tc_decode(p, job);
+        const bool reuse = (jb.head == res_head && jb.na == res_na);
+        const int col_h = jb.head * HD;
+        const int n_boxes = (reuse ? 0 : (jb.na16 >> 4)) + jb.nseg * (jb.Lsp >> 4);
+        const int seg_row0 = jb.q_row0 - jb.nb - jb.e;            // >= 0: sample jobs start at or after row Lc >= e
+        auto load_keys = [&](uint32_t slab, int col0, uint32_t full) {
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t dst = slab + kb * Cfg::kSlabKV;
+            const int col = col0 + col_h + kb * 64;
+            if (!reuse)
+              for (int r = 0; r < jb.na16; r += 16) tma_load_3d(dst + r * 128, &tmap_kv, full, col, r, 0, kEvictLast);
+            for (int s = 0; s < jb.nseg; ++s)
+              for (int r = 0; r < jb.Lsp; r += 16)
+                tma_load_3d(dst + (jb.na16 + s * jb.Lsp + r) * 128, &tmap_kv, full, col, seg_row0 + s * jb.Ls + r, 0,
+                            kEvictNormal);
+          }
+        };
+        // Q and K: free once the S MMA of the previous job has retired
+        mbar_wait(q_empty, ph ^ 1u, 500);
+        mbar_arrive_expect_tx(q_full, KB * (Cfg::kSlabQ + n_boxes * 2048));
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_3d(sQ + kb * Cfg::kSlabQ, &tmap_q, q_full, col_h + kb * 64, jb.q_row0, 0, kEvictFirst);
+        load_keys(sK, p.D, q_full);
+        if (job == j_begin) TC_STAMP(1);
+        // V: free once the O MMA of the previous job has retired
+        mbar_wait(v_empty, ph ^ 1u, 501);
+        mbar_arrive_expect_tx(v_full, KB * n_boxes * 2048);
+        load_keys(sV, 2 * p.D, v_full);
+        if (job == j_begin) TC_STAMP(2);
+        res_head = jb.head;
+        res_na = jb.na;
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const uint32_t tS = tmem_base, tO = tmem_base + 256;
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD) | (1u << 16);      // B (= V) is MN-major
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+        const TcJob jb = tc_decode(p, job);
+        const int nk = jb.nk;                                                  // key columns, multiple of 16, <= 256
+        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk);
+        mbar_wait(q_full, ph, 510);
+        tc_fence_after();
+        if (job == j_begin) TC_STAMP(3);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t adesc = umma_desc_sw128(sQ + kb * Cfg::kSlabQ);
+          const uint64_t bdesc = umma_desc_sw128(sK + kb * Cfg::kSlabKV);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS, adesc + 2u * k, bdesc + 2u * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(q_empty);
+        umma_commit(s_full);
+        if (job == j_begin) TC_STAMP(4);
+        mbar_wait(p_full, ph, 511);          // P is in shared memory; the softmax warps are done with S (and with O of job - 1)
+        mbar_wait(v_full, ph, 512);
+        tc_fence_after();
+        if (job == j_begin) TC_STAMP(5);
+        for (int ks = 0; ks < (nk >> 4); ++ks) {
+          const uint64_t adesc = umma_desc_sw128(sP + (ks >> 2) * Cfg::kSlabP) + 2u * (ks & 3);
+          const uint64_t bdesc = umma_desc_mn_sw128(sV + ks * 2048, Cfg::kSlabKV);
+          umma_bf16(tO, adesc, bdesc, idesc_o, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(v_empty);
+        umma_commit(o_full);
+        if (job == j_begin) TC_STAMP(6);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax + epilogue
+    const int r = warp * 32 + lane;                               // query row of the tile = TMEM lane
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(warp * 32) << 16), tO = tS + 256;
+    uint8_t* p_row = base_ptr + Cfg::kOffP + r * 128;
+    const int rx = r & 7;
+    uint32_t ph = 0;
+    for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+      const TcJob jb = tc_decode(p, job);
+      const int nk = jb.nk;
+      const int nab = jb.na;                       // columns [0, na): the prefix, seen by every row
+      const bool row_valid = r < jb.R;
+      const int s = row_valid ? r / jb.Ls : 0, t = r - s * jb.Ls;
+      // this row's segment keys (earlier tiles of its sequence + own keys up to itself): columns [own_lo, own_hi];
+      // rows past the tile see nothing
+      const int own_lo = row_valid ? jb.na16 + s * jb.Lsp + jb.e : (1 << 30);
+      const int own_hi = row_valid ? own_lo + jb.nb + t : -1;
+      const int nab_row = row_valid ? nab : 0;
+      if (lane == 0) mbar_wait(s_full, ph, 520);      // one poller per warp: 128 spinning threads would flood the smem pipe
+      __syncwarp();
+      tc_fence_after();
+      if (job == j_begin && threadIdx.x == 0) TC_STAMP(7);
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nk; c0 += 32) {
+        if (c0 >= nab && !__any_sync(0xffffffffu, c0 <= own_hi && c0 + 31 >= own_lo)) continue;   // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= nab) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            const bool vis = (c < nab_row) | ((c >= own_lo) & (c <= own_hi));
+            mx = fmaxf(mx, vis ? __uint_as_float(v[j]) : -INFINITY);
+          }
+        }
+      }
+      const float m_sc = row_valid ? mx * p.scale_log2e : 0.0f;
+      if (job == j_begin && threadIdx.x == 0) TC_STAMP(8);
+      float l = 0.0f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nk; c0 += 32) {
+        uint8_t* dst = p_row + (c0 >> 6) * Cfg::kSlabP;
+        const int q0 = (c0 & 63) >> 3;
+        if (c0 >= nab && !__any_sync(0xffffffffu, c0 <= own_hi && c0 + 31 >= own_lo)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (((q0 + g) ^ rx) << 4)) = make_uint4(0, 0, 0, 0);
+          continue;
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c0, v);
+        tmem_ld_wait();
+        float pv[32];
+        if (c0 + 32 <= nab) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -m_sc));
+        } else {
+          // branch-free: the exponential is taken of every column (a masked one may overflow to +inf, never NaN) and
+          // the mask selects afterwards — a per-element branch here diverges 32 times per chunk
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            const bool vis = (c < nab_row) | ((c >= own_lo) & (c <= own_hi));
+            const float ev = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -m_sc));
+            pv[j] = vis ? ev : 0.0f;
+          }
+        }
+        // the row sum runs strictly left to right (masked columns add exact zeros): independent of the tile's make-up
+#pragma unroll
+        for (int j = 0; j < 32; ++j) l += pv[j];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dst + (((q0 + g) ^ rx) << 4)) =
+              make_uint4(pack_bf16(pv[8 * g], pv[8 * g + 1]), pack_bf16(pv[8 * g + 2], pv[8 * g + 3]),
+                         pack_bf16(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16(pv[8 * g + 6], pv[8 * g + 7]));
+      }
+      fence_proxy_async_smem();             // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+      if (job == j_begin && threadIdx.x == 0) TC_STAMP(9);
+      if (job == j_begin && lane == 0) TC_STAMP(16 + warp);
+
+      if (lane == 0) mbar_wait(o_full, ph, 521);
+      __syncwarp();
+      tc_fence_after();
+      if (job == j_begin && threadIdx.x == 0) TC_STAMP(10);
+      const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+      __nv_bfloat16* orow = p.out + (int64_t)(jb.q_row0 + r) * p.D + (int64_t)jb.head * HD;
+#pragma unroll 1
+      for (int ci = 0; ci < HD / 32; ++ci) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + ci * 32, v);
+        tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(orow + ci * 32 + 8 * g) = make_uint4(
+                pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+        }
+      }
+      if (p.lse != nullptr && row_valid)
+        p.lse[jb.lse_off + (int64_t)s * jb.lse_stride + t] = (m_sc + log2f(l)) * 0.6931471805599453f;
+      tc_fence_before();
+      if (threadIdx.x == 0) TC_STAMP(job == j_begin ? 11 : 12);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(13);
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int g_attn_tc = -1;
+bool attn_tc_enabled() {
+  if (g_attn_tc < 0) {
+    const char* e = getenv("MTS_ATTN_TC");
+    g_attn_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_attn_tc == 1;
+}
+void attn_tc_set(int v) { g_attn_tc = v ? 1 : 0; }
+
+// Whether the tensor-memory kernel covers this shape.  The answer depends on the sequence length only (and on the prefix
+// being a multiple of 16 rows), never on the batch: the shared-prefix and the per-sample layouts of one model take the
+// same route, which is what keeps their outputs bit-identical.
+bool attn_tc_eligible(int L, int Lc, int hd) {
+  // L <= 240 always fits 256 key columns; up to 256 when no dummy columns are needed (prefix a multiple of 16)
+  return attn_tc_enabled() && (hd == 64 || hd == 128) && Lc >= 0 && Lc < L && (L <= 240 || (L <= 256 && (Lc % 16) == 0));
+}
+
+template <int HD>
+static int launch_attn_tc_t(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H, float scale,
+                            cudaStream_t stream) {
+  using Cfg = AttnTcCfg<HD>;
+  auto kern = attn_fwd_tc_kernel<HD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_fwd_tc_kernel)", e);
+    attr_done = true;
+  }
+  AttnTcParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.Bp = Bp; p.Lc = Lc; p.Ls = L - Lc; p.H = H; p.D = H * HD;
+  p.n_pt = (Lc + 127) / 128;
+  p.n_qt = (p.Ls + 127) / 128;
+  const int lsp = ((Lc & 15) + p.Ls + 15) & ~15;
+  int sample_jobs;
+  if (p.n_qt == 1) {
+    int spj = 128 / p.Ls;
+    const int by_cols = (256 - ((Lc + 15) & ~15)) / lsp;
+    if (by_cols < spj) spj = by_cols;
+    if (spj > Bp) spj = Bp;
+    if (spj < 1) spj = 1;
+    p.spj = spj;
+    sample_jobs = (Bp + spj - 1) / spj;
+  } else {
+    p.spj = 1;
+    sample_jobs = Bp * p.n_qt;
+  }
+  p.jobs_per_head = p.n_pt + sample_jobs;
+  const int64_t n_jobs = (int64_t)p.jobs_per_head * H;
+  if (n_jobs > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "attention: too many tiles");
+  p.n_jobs = (int)n_jobs;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  const int64_t rows = (int64_t)Lc + (int64_t)Bp * p.Ls;
+  CUtensorMap tq, tkv;
+  int rc = get_tmap_3d(&tq, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 128, 2);
+  if (rc) return rc;
+  rc = get_tmap_3d(&tkv, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 16, 2);
+  if (rc) return rc;
+  const int grid = p.n_jobs < num_sms() ? p.n_jobs : num_sms();
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* e = getenv("MTS_ATTN_TC_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+  p.dbg = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 24 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 24 * sizeof(long long), stream);
+    p.dbg = dbg_buf;
+  }
+  LAUNCH_PDL(kern, grid, kTcThreads, Cfg::kSmemBytes, stream, tq, tkv, p);
+  count_launch();
+  if (dbg_on) {
+    long long h[24];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* names[14] = {"start", "K issued", "V issued", "q_full seen", "S issued", "p_full+v_full seen", "O issued",
+                                    "s_full seen", "pass1 done", "P written", "o_full seen", "job0 done", "last job done", "end"};
+    fprintf(stderr, "[attn_tc dbg] jobs=%d grid=%d spj=%d:", p.n_jobs, grid, p.spj);
+    for (int i = 1; i < 14; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
+    for (int i = 16; i < 20; ++i) fprintf(stderr, " P of warp %d=%lld", i & 3, h[i] ? h[i] - h[0] : -1);
+    fprintf(stderr, "\n");
+  }
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+int launch_attn_tc(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H, int hd, float scale,
+                   cudaStream_t stream) {
+  if (hd == 128) return launch_attn_tc_t<128>(qkv, out, lse, Bp, L, Lc, H, scale, stream);
+  return launch_attn_tc_t<64>(qkv, out, lse, Bp, L, Lc, H, scale, stream);
+}
+
+}  // namespace mts

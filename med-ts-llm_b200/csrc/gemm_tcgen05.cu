@@ -368,6 +368,7 @@ static int pick_block_n(int m, int n, int batch) {
 }  // namespace mts
 
 namespace mts {
+void attn_tc_set(int v);
 int launch_gemm_2cta(int epilogue, const mts_gemm_args* a, const GemmParams& p, cudaStream_t stream);
 static int g_gemm_2cta = -1;
 bool gemm_2cta_enabled() {
@@ -408,6 +409,7 @@ extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
+  if (name && !strcmp(name, "attn_tc")) { attn_tc_set(value); return MTS_OK; }
   if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 0 : value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }

@@ -188,6 +188,169 @@ attn_causal_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The same attention on the tensor cores in TF32 (mma.sync.m16n8k8) — the "tf32" mode's attention: the reference's
+// evaluation regime runs Q K^T and P V as TF32 matmuls too (tasks/base.py:19-22).  q / k / v are rounded to nearest TF32
+// while they are staged, P when it goes through shared memory (the m16n8k8 accumulator layout is not the A-operand
+// layout: one per-warp smem round trip); softmax, running max / sum and the output stay fp32.
+//   grid (ceil(max(Lc, Ls) / 64), H, Bp + (Lc > 0)), 128 threads = 4 warps x 16 query rows; 32-key tiles.
+//   Shared memory pitches (HD+4 for Q / K / P rows, HD+8 for V) make every fragment load conflict-free.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_causal_tf32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int Bp, int Lc, int Ls, int H,
+                        float scale, int round_out) {
+  constexpr int TQ = 64, TK = 32, PQ = HD + 4, PVp = HD + 8, PP = TK + 4;
+  extern __shared__ __align__(16) float attn_tf32_smem[];
+  float* Qs = attn_tf32_smem;                 // [TQ][PQ]
+  float* Ks = Qs + TQ * PQ;                   // [TK][PQ]
+  float* Vs = Ks + TK * PQ;                   // [TK][PVp]
+  float* Ps = Vs + TK * PVp;                  // [4 warps][16][PP]
+  const int z = blockIdx.z, head = blockIdx.y;
+  const bool prefix = (z == Bp);
+  const int q_begin = prefix ? 0 : Lc, q_end = prefix ? Lc : Lc + Ls;
+  const int q0 = q_begin + blockIdx.x * TQ;
+  if (q0 >= q_end) return;
+  const int64_t ld = 3 * (int64_t)H * HD;
+  auto row_of = [&](int pos) -> int64_t { return pos < Lc ? pos : (int64_t)Lc + (int64_t)z * Ls + (pos - Lc); };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < TQ * (HD / 4); i += 128) {
+    const int rr = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + rr < q_end) v = *reinterpret_cast<const float4*>(qkv + row_of(q0 + rr) * ld + (int64_t)head * HD + c4);
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    *reinterpret_cast<float4*>(Qs + rr * PQ + c4) = v;
+  }
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int strip0 = q0 + warp * 16;
+  const int row_a = strip0 + g, row_b = row_a + 8;
+  const int k_last = min(q0 + TQ - 1, q_end - 1);
+  const int strip_last = min(strip0 + 15, q_end - 1);
+  const float* qa = Qs + (warp * 16 + g) * PQ;
+  const float* qb = qa + 8 * PQ;
+  float* pw = Ps + warp * 16 * PP;
+
+  for (int k0 = 0; k0 <= k_last; k0 += TK) {
+    __syncthreads();
+    for (int i = tid; i < TK * (HD / 4); i += 128) {
+      const int kk = i / (HD / 4), c4 = (i % (HD / 4)) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + kk <= k_last) {
+        const float* base = qkv + row_of(k0 + kk) * ld + (int64_t)head * HD + c4;
+        kv = *reinterpret_cast<const float4*>(base + (int64_t)H * HD);
+        vv = *reinterpret_cast<const float4*>(base + 2 * (int64_t)H * HD);
+      }
+      kv.x = round_tf32(kv.x); kv.y = round_tf32(kv.y); kv.z = round_tf32(kv.z); kv.w = round_tf32(kv.w);
+      vv.x = round_tf32(vv.x); vv.y = round_tf32(vv.y); vv.z = round_tf32(vv.z); vv.w = round_tf32(vv.w);
+      *reinterpret_cast<float4*>(Ks + kk * PQ + c4) = kv;
+      *reinterpret_cast<float4*>(Vs + kk * PVp + c4) = vv;
+    }
+    __syncthreads();
+    if (k0 > strip_last || strip0 >= q_end) continue;          // warp-uniform: every key of this tile is masked for the strip
+
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks) {
+      uint32_t a[4];
+      a[0] = __float_as_uint(qa[ks * 8 + t]);
+      a[1] = __float_as_uint(qb[ks * 8 + t]);
+      a[2] = __float_as_uint(qa[ks * 8 + t + 4]);
+      a[3] = __float_as_uint(qb[ks * 8 + t + 4]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* kr = Ks + (nt * 8 + g) * PQ + ks * 8 + t;
+        mma_tf32_1688(s[nt], a, __float_as_uint(kr[0]), __float_as_uint(kr[4]));
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = k0 + nt * 8 + 2 * t + (e & 1);
+        const int row = (e < 2) ? row_a : row_b;
+        const float v = (col <= row && row < q_end) ? s[nt][e] * scale : -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2], m_new[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      m_new[r] = fmaxf(m_run[r], mx[r]);
+      corr[r] = (m_new[r] == -INFINITY) ? 1.0f : expf(m_run[r] - m_new[r]);
+      m_run[r] = m_new[r];
+    }
+    float psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        p[e] = (s[nt][e] == -INFINITY) ? 0.f : expf(s[nt][e] - m_new[e >> 1]);
+        psum[e >> 1] += p[e];
+      }
+      *reinterpret_cast<float2*>(pw + g * PP + nt * 8 + 2 * t) = make_float2(round_tf32(p[0]), round_tf32(p[1]));
+      *reinterpret_cast<float2*>(pw + (g + 8) * PP + nt * 8 + 2 * t) = make_float2(round_tf32(p[2]), round_tf32(p[3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 1);
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 2);
+      l_run[r] = l_run[r] * corr[r] + psum[r];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int kst = 0; kst < TK / 8; ++kst) {
+      uint32_t a[4];
+      a[0] = __float_as_uint(pw[g * PP + kst * 8 + t]);
+      a[1] = __float_as_uint(pw[(g + 8) * PP + kst * 8 + t]);
+      a[2] = __float_as_uint(pw[g * PP + kst * 8 + t + 4]);
+      a[3] = __float_as_uint(pw[(g + 8) * PP + kst * 8 + t + 4]);
+      const float* v0 = Vs + (kst * 8 + t) * PVp + g;
+      const float* v1 = v0 + 4 * PVp;
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt)
+        mma_tf32_1688(o[nt], a, __float_as_uint(v0[nt * 8]), __float_as_uint(v1[nt * 8]));
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = r ? row_b : row_a;
+    if (row < q_end) {
+      const float inv = 1.0f / l_run[r];
+      float* dst = out + row_of(row) * ((int64_t)H * HD) + (int64_t)head * HD + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt) {
+        float2 v = make_float2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+        if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); }
+        *reinterpret_cast<float2*>(dst + nt * 8) = v;
+      }
+    }
+  }
+}
+
 }  // namespace mts
 
 using namespace mts;
@@ -224,6 +387,35 @@ extern "C" int mts_softmax_rows_f32(const float* s, float* p, int64_t rows, int 
   softmax_rows_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(s, p, rows, n, scale);
   count_launch();
   return check_launch("softmax_rows_f32_kernel");
+}
+
+template <int HD>
+static int launch_attn_tf32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, float scale, int round_out,
+                            cudaStream_t stream) {
+  constexpr int kSmem = (64 * (HD + 4) + 32 * (HD + 4) + 32 * (HD + 8) + 4 * 16 * 36) * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_causal_tf32_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_causal_tf32_kernel)", e);
+    attr = true;
+  }
+  const int qmax = Lc > Ls ? Lc : Ls;
+  dim3 grid((qmax + 63) / 64, H, Bp + (Lc > 0 ? 1 : 0));
+  attn_causal_tf32_kernel<HD><<<grid, 128, kSmem, stream>>>(qkv, out, Bp, Lc, Ls, H, scale, round_out);
+  count_launch();
+  return check_launch("attn_causal_tf32_kernel");
+}
+
+extern "C" int mts_attn_causal_tf32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                                    int round_out, mts_stream_t stream_) {
+  if (!qkv || !out || Bp <= 0 || Lc < 0 || Ls <= 0 || H <= 0)
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_tf32: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(MTS_ERR_INVALID_ARG, "mts_attn_causal_tf32: pointers must be 16-byte aligned");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (hd == 128) return launch_attn_tf32<128>(qkv, out, Bp, Lc, Ls, H, scale, round_out, stream);
+  if (hd == 64) return launch_attn_tf32<64>(qkv, out, Bp, Lc, Ls, H, scale, round_out, stream);
+  return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_tf32: head dim must be 64 or 128");
 }
 
 extern "C" int mts_attn_causal_f32(const float* qkv, float* out, int Bp, int Lc, int Ls, int H, int hd, float scale,

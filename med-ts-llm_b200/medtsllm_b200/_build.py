@@ -21,7 +21,7 @@ LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libmtsb200.so"
 OBJ_DIR = REPO / "build" / "mtsb200"
 
-SOURCES = ["common.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "rowops.cu", "frontend.cu", "attention.cu", "backward.cu", "precise.cu", "stats.cu"]
+SOURCES = ["common.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "rowops.cu", "frontend.cu", "attention.cu", "attention_tc.cu", "backward.cu", "precise.cu", "stats.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

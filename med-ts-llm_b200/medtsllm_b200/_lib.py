@@ -95,6 +95,7 @@ SIGNATURES = {
     "mts_split_tf32": [_p, _p, _p, _i64, _p],
     "mts_softmax_rows_f32": [_p, _p, _i64, _i, _f, _p],
     "mts_attn_causal_f32": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
+    "mts_attn_causal_tf32": [_p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mts_input_stats": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mts_attn_causal_dropout": [_p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _p],
     "mts_attn_causal_dropout_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _p],

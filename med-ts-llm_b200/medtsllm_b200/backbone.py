@@ -450,8 +450,10 @@ class KernelBackbone:
                 ops.layernorm(x, lay["ln1"], lay["ln1b"], s.eps, out=h)
                 self.gemm32(self.operand(h, inplace=True), wqkv, qkv, m=M, n=3 * D, k=D, bias=lay["bqkv"],
                             bias_axis=BIAS_N)
-            ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, out=att)
-            self.gemm32(self.operand(att, inplace=True), lay["wo_f32"], x, m=M, n=D, k=D, epilogue=EPI_RESID_ADD,
+            # "tf32": Q K^T and P V on the tensor cores in TF32 like the reference's matmuls, output already rounded for the
+            # out-projection; "fp32": plain fp32 arithmetic
+            ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, out=att, tf32=tf32, round_out=tf32)
+            self.gemm32((att, None) if tf32 else self.operand(att), lay["wo_f32"], x, m=M, n=D, k=D, epilogue=EPI_RESID_ADD,
                         bias=None if llama else lay["bo"], bias_axis=BIAS_NONE if llama else BIAS_N)
             if llama:
                 ops.rmsnorm(x, lay["ln2"], s.eps, out=h)

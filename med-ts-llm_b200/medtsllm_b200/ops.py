@@ -707,8 +707,9 @@ def softmax_rows_f32(s, scale, out=None):
     return out
 
 
-def attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, *, scale=None, out=None, round_out=False):
-    """fp32 causal attention: qkv fp32 [Lc + Bp*Ls, 3*H*hd] (q / k rotated) -> out fp32 [Lc + Bp*Ls, H*hd]."""
+def attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, *, scale=None, out=None, round_out=False, tf32=False):
+    """fp32 causal attention: qkv fp32 [Lc + Bp*Ls, 3*H*hd] (q / k rotated) -> out fp32 [Lc + Bp*Ls, H*hd].
+    tf32=True: both contractions on the tensor cores in TF32 (the "tf32" mode); False: plain fp32 FMA arithmetic."""
     _chk(qkv, torch.float32, "qkv")
     M = Lc + Bp * Ls
     if not qkv.is_contiguous() or qkv.shape != (M, 3 * H * hd):
@@ -717,8 +718,8 @@ def attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, *, scale=None, out=None, round_out=F
         scale = 1.0 / math.sqrt(hd)
     if out is None:
         out = torch.empty(M, H * hd, device=qkv.device, dtype=torch.float32)
-    _lib.call("mts_attn_causal_f32", qkv.data_ptr(), out.data_ptr(), Bp, Lc, Ls, H, hd, scale, 1 if round_out else 0,
-              _stream())
+    _lib.call("mts_attn_causal_tf32" if tf32 else "mts_attn_causal_f32", qkv.data_ptr(), out.data_ptr(), Bp, Lc, Ls, H, hd,
+              scale, 1 if round_out else 0, _stream())
     return out
 
 

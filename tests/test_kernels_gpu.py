@@ -273,6 +273,62 @@ def test_attn_causal(ops, cuda, Bp, L, H, hd, rope):
     torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("Bp,Lc,Ls,H,hd", [
+    (5, 128, 64, 2, 128),      # BIDMC: two samples share a tile
+    (11, 128, 12, 3, 64),      # PSM: eight samples per tile, ragged last group
+    (7, 128, 42, 2, 128),      # Ventilator: own rows not a multiple of 16
+    (3, 128, 128, 1, 128),     # LUDB: 256 key columns
+    (4, 37, 12, 3, 64),        # prefix not a multiple of 16: dummy columns
+    (5, 130, 33, 1, 128),      # prefix in two tiles
+    (2, 32, 150, 2, 64),       # own rows in two tiles
+    (3, 0, 192, 2, 128),       # plain layout, two tiles per sample
+    (6, 0, 49, 2, 64),         # plain layout, two samples per tile
+    (2, 0, 256, 1, 128),
+])
+def test_attn_tensor_memory_kernel(ops, cuda, Bp, Lc, Ls, H, hd):
+    """The tcgen05 / TMEM forward (attention_tc.cu) against fp64 attention and against the mma.sync kernels it replaces,
+    on every tiling case: several samples per 128-row tile, tiled prefix, tiled own rows, dummy columns."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(Lc * 5 + Ls + hd)
+    D, L = H * hd, Lc + Ls
+    M = Lc + Bp * Ls
+    qkv = (torch.randn(M, 3 * D, generator=g) * 0.8).to(cuda, torch.bfloat16)
+
+    def run():
+        if Lc:
+            out, lse_full = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, want_lse=True)
+            return out, lse_full
+        return ops.attn_causal(qkv, Bp, L, H, hd, rope=None, want_lse=True)
+
+    out, lse = run()
+    _lib.set_option("attn_tc", 0)
+    try:
+        out_old, lse_old = run()
+    finally:
+        _lib.set_option("attn_tc", 1)
+    # fp64 reference on the per-sample view
+    full = _expand_shared(qkv, Bp, Lc, Ls) if Lc else qkv
+    q, k, v = (t.view(Bp, L, H, hd).transpose(1, 2) for t in full.double().split(D, dim=-1))
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    mask = torch.ones(L, L, device=cuda, dtype=torch.bool).tril()
+    sc = sc.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(Bp, L, D)
+    ref_lse = torch.logsumexp(sc, -1)                                   # [Bp, H, L]
+    got = (_expand_shared(out, Bp, Lc, Ls) if Lc else out).view(Bp, L, D)
+    assert torch.isfinite(out.float()).all()
+    assert _rel_l2(got, ref) < 6e-3                                     # bf16 P and output
+    assert _rel_l2(out, out_old) < 6e-3
+    if Lc:
+        own = ops.lse_own_view(lse, Bp, Lc, Ls, H)
+        torch.testing.assert_close(own.double(), ref_lse[:, :, Lc:], rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(lse[:H * Lc].view(H, Lc).double(), ref_lse[0, :, :Lc], rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(lse, lse_old, rtol=1e-4, atol=2e-4)
+    else:
+        torch.testing.assert_close(lse.double(), ref_lse, rtol=1e-4, atol=2e-4)
+    out2, lse2 = run()                                                  # deterministic
+    assert torch.equal(out, out2) and torch.equal(lse, lse2)
+
+
 # ------------------------------------------------------------------------------- training-path kernels
 def test_gemm_resid_out_of_place_and_scalar_epilogue(ops, cuda):
     g = torch.Generator().manual_seed(21)
@@ -740,6 +796,14 @@ def test_gemm_tf32_rope_epilogue_and_attn_f32(ops, cuda, hd, Lc):
     assert _rel_l2(expand(out.cpu()).double(), ref) < 5e-6
     if Lc:   # the shared rows are computed once and identical for every sample by construction
         assert torch.isfinite(out).all()
+    # the "tf32" mode's attention: both contractions on the tensor cores with q / k / v / P rounded to nearest TF32
+    # (2^-11 relative per operand, averaging out over the head dim and the keys), fp32 softmax and accumulation
+    out_t = ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, tf32=True)
+    assert torch.isfinite(out_t).all()
+    err_t = _rel_l2(expand(out_t.cpu()).double(), ref)
+    assert 1e-6 < err_t < 6e-4, err_t
+    out_r = ops.attn_causal_f32(qkv, Bp, Lc, Ls, H, hd, tf32=True, round_out=True)
+    assert torch.equal(out_r, ops.round_tf32(out_t))
 
 
 def test_softmax_rows_f32(ops, cuda):
