@@ -19,7 +19,7 @@
 namespace mts {
 
 // attention_tc.cu: the tensor-memory (tcgen05) forward for L <= 256
-bool attn_tc_eligible(int L, int Lc, int hd);
+bool attn_tc_eligible(int L, int Lc, int hd, int Bp, int H);
 int launch_attn_tc(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L, int Lc, int H, int hd, float scale,
                    cudaStream_t stream);
 
@@ -561,7 +561,7 @@ static int launch_attn_seq(const uint16_t* qkv, uint16_t* out, float* lse, int B
 template <int HD>
 static int launch_attn(const uint16_t* qkv, const float* rc, const float* rs, uint16_t* out,
                        float* lse, int Bp, int L, int H, float scale, cudaStream_t stream) {
-  if (rc == nullptr && attn_tc_eligible(L, 0, HD)) return launch_attn_tc(qkv, out, lse, Bp, L, 0, H, HD, scale, stream);
+  if (rc == nullptr && attn_tc_eligible(L, 0, HD, Bp, H)) return launch_attn_tc(qkv, out, lse, Bp, L, 0, H, HD, scale, stream);
   if (rc == nullptr && seq_smem_bytes<HD>(L) <= 220 * 1024)
     return launch_attn_seq<HD>(qkv, out, lse, Bp, L, 0, H, scale, stream);
   constexpr int kSmem = 3 * 64 * (HD + 8) * 2;
@@ -1554,7 +1554,7 @@ template <int HD>
 static int launch_attn_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
                               float scale, cudaStream_t stream) {
   const int L = Lc + Ls;
-  if (attn_tc_eligible(L, Lc, HD)) return launch_attn_tc(qkv, out, lse, Bp, L, Lc, H, HD, scale, stream);
+  if (attn_tc_eligible(L, Lc, HD, Bp, H)) return launch_attn_tc(qkv, out, lse, Bp, L, Lc, H, HD, scale, stream);
   if (seq_smem_bytes<HD>(L) > 220 * 1024)
     return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared: %d positions do not fit in shared memory", L);
   // one launch: H CTAs for the prefix as an ordinary sequence of Lc positions, the rest for the samples' own tokens

@@ -21,8 +21,9 @@
 // the prompt prefix is stored once (shared-prefix layout) or per sample — bit-identical outputs either way.
 //
 // A CTA (one per SM, persistent) walks a contiguous range of jobs, head-major, so that the prefix K / V of a head stay
-// resident in shared memory across its jobs.  Warp roles: 0-3 softmax + epilogue (TMEM lane quarters), 4 TMA producer,
-// 5 MMA issuer; the S MMA of job i+1 is issued right behind the O MMA of job i and overlaps epilogue i.
+// resident in shared memory across its jobs.  Warp roles: 0-3 softmax, 4-7 epilogue (both sets cover the four TMEM lane
+// quarters), 8 TMA producer, 9 MMA issuer.  The S MMA of job i+1 is issued right behind the O MMA of job i, so softmax
+// i+1 runs while the epilogue warps drain O of job i: the kernel's bound is the TMEM read bandwidth (S twice, O once).
 //
 // Algorithmic work per launch: 4 * hd * (visible query-key pairs) FLOP (roofline: tensor pipe).
 #include <stdlib.h>
@@ -32,7 +33,7 @@
 
 namespace mts {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warps 0-3 softmax, 4-7 epilogue, 8 TMA producer, 9 MMA issuer
 
 struct AttnTcParams {
   __nv_bfloat16* out;
@@ -59,10 +60,18 @@ struct TcJob {
   int lse_stride;
 };
 
-__device__ __forceinline__ TcJob tc_decode(const AttnTcParams& p, int job) {
+// Jobs are numbered head-major; a CTA walks a contiguous range, so (head, index within the head) advance incrementally
+// (one division per CTA, none per job).
+struct TcJobIter {
+  int head, i;
+  __device__ __forceinline__ void init(const AttnTcParams& p, int job) { head = job / p.jobs_per_head; i = job - head * p.jobs_per_head; }
+  __device__ __forceinline__ void next(const AttnTcParams& p) { if (++i == p.jobs_per_head) { i = 0; ++head; } }
+};
+
+__device__ __forceinline__ TcJob tc_decode(const AttnTcParams& p, const TcJobIter& it) {
   TcJob j;
-  j.head = job / p.jobs_per_head;
-  int i = job - j.head * p.jobs_per_head;
+  j.head = it.head;
+  int i = it.i;
   j.nb = 0; j.lse_stride = 0; j.e = 0;
   if (i < p.n_pt) {                        // tile i of the prefix: an ordinary causal sequence of Lc positions
     j.q_row0 = 128 * i;
@@ -106,6 +115,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Bit j set: column c0 + j is visible to a row that sees the prefix columns [0, n_prefix) and its segment keys
+// [lo, hi] (hi < lo: none).  One mask per 32-column chunk instead of three comparisons per element.
+__device__ __forceinline__ uint32_t chunk_mask(int c0, int n_prefix, int lo, int hi) {
+  const int np = min(max(n_prefix - c0, 0), 32);
+  uint32_t m = np >= 32 ? 0xffffffffu : ((1u << np) - 1u);
+  const int a = max(lo - c0, 0), b = min(hi - c0, 31);
+  if (b >= a) m |= (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
+  return m;
+}
+
 // MN-major, 128B-swizzled shared-memory matrix descriptor: rows of the K dimension (keys) are 128 bytes (64 bf16 of the
 // MN dimension) apart, 8-row groups 1024 bytes (SBO), the next 64 elements of the MN dimension `lbo` bytes further.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
@@ -122,7 +141,8 @@ struct AttnTcCfg {
   static constexpr int kOffK = KB * kSlabQ;
   static constexpr int kOffV = kOffK + KB * kSlabKV;
   static constexpr int kOffP = kOffV + KB * kSlabKV;
-  static constexpr int kOffBar = kOffP + 4 * kSlabP;
+  static constexpr int kOffLM = kOffP + 4 * kSlabP;   // row sums and scaled row maxima, softmax -> epilogue warps: 2 x 128 floats
+  static constexpr int kOffBar = kOffLM + 1024;
   static constexpr int kSmemBytes = kOffBar + 128 + 1024;
 };
 
@@ -138,16 +158,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t sQ = base, sK = base + Cfg::kOffK, sV = base + Cfg::kOffV, sP = base + Cfg::kOffP;
   const uint32_t bar = base + Cfg::kOffBar;
   const uint32_t q_full = bar, v_full = bar + 8, q_empty = bar + 16, v_empty = bar + 24, s_full = bar + 32,
-                 p_full = bar + 40, o_full = bar + 48, tmem_slot = bar + 56;
+                 p_full = bar + 40, o_full = bar + 48, tmem_slot = bar + 56, o_empty = bar + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1); mbar_init(v_full, 1); mbar_init(q_empty, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_empty, 128);
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,13 +179,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int j_begin = (int)((long long)p.n_jobs * blockIdx.x / gridDim.x);
   const int j_end = (int)((long long)p.n_jobs * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t ph = 0;
       int res_head = -1, res_na = -1;            // prefix rows [0, res_na) of head res_head are resident in the slabs
-      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
-        const TcJob jb = tc_decode(p, job);
+      TcJobIter it;
+      it.init(p, j_begin);
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u, it.next(p)) {
+        const TcJob jb = tc_decode(p, it);
         const bool reuse = (jb.head == res_head && jb.na == res_na);
         const int col_h = jb.head * HD;
         const int n_boxes = (reuse ? 0 : (jb.na16 >> 4)) + jb.nseg * (jb.Lsp >> 4);
@@ -200,19 +222,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         res_na = jb.na;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t ph = 0;
       const uint32_t tS = tmem_base, tO = tmem_base + 256;
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD) | (1u << 16);      // B (= V) is MN-major
-      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
-        const TcJob jb = tc_decode(p, job);
-        const int nk = jb.nk;                                                  // key columns, multiple of 16, <= 256
-        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk);
-        mbar_wait(q_full, ph, 510);
+      // S of job i+1 is issued BEFORE O of job i (both become possible when the softmax warps hand over P of job i and
+      // release S): the softmax warps get their next score tile one MMA earlier and O of job i runs underneath pass 1.
+      auto issue_s = [&](int nk, uint32_t ph_q) {
+        mbar_wait(q_full, ph_q, 510);
         tc_fence_after();
-        if (job == j_begin) TC_STAMP(3);
+        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t adesc = umma_desc_sw128(sQ + kb * Cfg::kSlabQ);
@@ -222,9 +243,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         umma_commit(q_empty);
         umma_commit(s_full);
-        if (job == j_begin) TC_STAMP(4);
-        mbar_wait(p_full, ph, 511);          // P is in shared memory; the softmax warps are done with S (and with O of job - 1)
+      };
+      TcJobIter it;
+      it.init(p, j_begin);
+      TcJob jb = tc_decode(p, it);
+      if (j_begin < j_end) issue_s(jb.nk, 0);
+      TC_STAMP(4);
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+        const int nk = jb.nk;                                                  // key columns, multiple of 16, <= 256
+        it.next(p);
+        TcJob jn = jb;
+        if (job + 1 < j_end) jn = tc_decode(p, it);      // (before the wait: off the critical path)
+        asm volatile("" ::"r"(jn.nk));
+        mbar_wait(p_full, ph, 511);          // P is in shared memory and the softmax warps are done with S
+        if (job + 1 < j_end) issue_s(jn.nk, ph ^ 1u);
         mbar_wait(v_full, ph, 512);
+        mbar_wait(o_empty, ph ^ 1u, 513);    // the epilogue warps have drained O of the previous job
         tc_fence_after();
         if (job == j_begin) TC_STAMP(5);
         for (int ks = 0; ks < (nk >> 4); ++ks) {
@@ -235,27 +269,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         umma_commit(v_empty);
         umma_commit(o_full);
         if (job == j_begin) TC_STAMP(6);
+        jb = jn;
       }
     }
-  } else {
-    // ------------------------------------------------------------------------------------------ softmax + epilogue
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------------------------------ softmax
     const int r = warp * 32 + lane;                               // query row of the tile = TMEM lane
-    const uint32_t tS = tmem_base + (static_cast<uint32_t>(warp * 32) << 16), tO = tS + 256;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     uint8_t* p_row = base_ptr + Cfg::kOffP + r * 128;
+    float* lm = reinterpret_cast<float*>(base_ptr + Cfg::kOffLM);
     const int rx = r & 7;
     uint32_t ph = 0;
-    for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
-      const TcJob jb = tc_decode(p, job);
+    const int r_div = r / p.Ls;                    // sample of this row inside a several-samples job (the only job kind with s > 0)
+    TcJobIter it;
+    it.init(p, j_begin);
+    for (int job = j_begin; job < j_end; ++job, ph ^= 1u, it.next(p)) {
+      const TcJob jb = tc_decode(p, it);
       const int nk = jb.nk;
       const int nab = jb.na;                       // columns [0, na): the prefix, seen by every row
       const bool row_valid = r < jb.R;
-      const int s = row_valid ? r / jb.Ls : 0, t = r - s * jb.Ls;
+      const int s = (row_valid && jb.nseg > 1) ? r_div : 0, t = r - s * jb.Ls;
       // this row's segment keys (earlier tiles of its sequence + own keys up to itself): columns [own_lo, own_hi];
       // rows past the tile see nothing
       const int own_lo = row_valid ? jb.na16 + s * jb.Lsp + jb.e : (1 << 30);
       const int own_hi = row_valid ? own_lo + jb.nb + t : -1;
       const int nab_row = row_valid ? nab : 0;
-      if (lane == 0) mbar_wait(s_full, ph, 520);      // one poller per warp: 128 spinning threads would flood the smem pipe
+      // (keep the job arithmetic above the wait: the compiler would otherwise sink it behind the barrier, onto the critical path)
+      asm volatile("" ::"r"(own_lo), "r"(own_hi), "r"(nab_row), "r"(nk), "r"(t));
+      // S of this job is complete
+      if (lane == 0) mbar_wait(s_full, ph, 520);
       __syncwarp();
       tc_fence_after();
       if (job == j_begin && threadIdx.x == 0) TC_STAMP(7);
@@ -266,20 +308,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         uint32_t v[32];
         tmem_ld_32x32(tS + c0, v);
         tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // four chains: the maximum is order-independent
         if (c0 + 32 <= nab) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
         } else {
+          const uint32_t bits = chunk_mask(c0, nab_row, own_lo, own_hi);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            const bool vis = (c < nab_row) | ((c >= own_lo) & (c <= own_hi));
-            mx = fmaxf(mx, vis ? __uint_as_float(v[j]) : -INFINITY);
-          }
+          for (int j = 0; j < 32; ++j)
+            m4[j & 3] = fmaxf(m4[j & 3], (bits & (1u << j)) ? __uint_as_float(v[j]) : -INFINITY);
         }
+        mx = fmaxf(fmaxf(mx, fmaxf(m4[0], m4[1])), fmaxf(m4[2], m4[3]));
       }
       const float m_sc = row_valid ? mx * p.scale_log2e : 0.0f;
       if (job == j_begin && threadIdx.x == 0) TC_STAMP(8);
+      // P is rewritten from here on: O of the previous job (issued after this job's S) must have finished reading it
+      if (lane == 0) mbar_wait(o_full, ph ^ 1u, 523);
+      __syncwarp();
       float l = 0.0f;
 #pragma unroll 1
       for (int c0 = 0; c0 < nk; c0 += 32) {
@@ -300,12 +345,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         } else {
           // branch-free: the exponential is taken of every column (a masked one may overflow to +inf, never NaN) and
           // the mask selects afterwards — a per-element branch here diverges 32 times per chunk
+          const uint32_t bits = chunk_mask(c0, nab_row, own_lo, own_hi);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            const bool vis = (c < nab_row) | ((c >= own_lo) & (c <= own_hi));
             const float ev = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -m_sc));
-            pv[j] = vis ? ev : 0.0f;
+            pv[j] = (bits & (1u << j)) ? ev : 0.0f;
           }
         }
         // the row sum runs strictly left to right (masked columns add exact zeros): independent of the tile's make-up
@@ -317,65 +361,95 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               make_uint4(pack_bf16(pv[8 * g], pv[8 * g + 1]), pack_bf16(pv[8 * g + 2], pv[8 * g + 3]),
                          pack_bf16(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16(pv[8 * g + 6], pv[8 * g + 7]));
       }
+      // row sum and maximum go to the epilogue warps through shared memory, once they have read the previous job's
+      if (lane == 0) mbar_wait(o_empty, ph ^ 1u, 522);
+      __syncwarp();
+      lm[r] = l;
+      lm[128 + r] = m_sc;
       fence_proxy_async_smem();             // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
       if (job == j_begin && threadIdx.x == 0) TC_STAMP(9);
       if (job == j_begin && lane == 0) TC_STAMP(16 + warp);
-
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue (warps 4..7)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256;
+    const float* lm = reinterpret_cast<const float*>(base_ptr + Cfg::kOffLM);
+    uint32_t ph = 0;
+    const int r_div = r / p.Ls;
+    TcJobIter it;
+    it.init(p, j_begin);
+    for (int job = j_begin; job < j_end; ++job, ph ^= 1u, it.next(p)) {
+      const TcJob jb = tc_decode(p, it);
+      const bool row_valid = r < jb.R;
+      const int s = (row_valid && jb.nseg > 1) ? r_div : 0, t = r - s * jb.Ls;
+      __nv_bfloat16* orow = p.out + (int64_t)(jb.q_row0 + r) * p.D + (int64_t)jb.head * HD;
+      float* lse_ptr = (p.lse != nullptr && row_valid) ? p.lse + jb.lse_off + (int64_t)s * jb.lse_stride + t : nullptr;
+      asm volatile("" ::"l"(orow), "l"(lse_ptr));
       if (lane == 0) mbar_wait(o_full, ph, 521);
       __syncwarp();
       tc_fence_after();
-      if (job == j_begin && threadIdx.x == 0) TC_STAMP(10);
+      if (job == j_begin && threadIdx.x == 128) TC_STAMP(10);
+      const float l = lm[r], m_sc = lm[128 + r];
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-      __nv_bfloat16* orow = p.out + (int64_t)(jb.q_row0 + r) * p.D + (int64_t)jb.head * HD;
-#pragma unroll 1
-      for (int ci = 0; ci < HD / 32; ++ci) {
-        uint32_t v[32];
-        tmem_ld_32x32(tO + ci * 32, v);
-        tmem_ld_wait();
-        if (row_valid) {
+      uint32_t v[HD / 32][32];
+#pragma unroll
+      for (int ci = 0; ci < HD / 32; ++ci) tmem_ld_32x32(tO + ci * 32, v[ci]);
+      tmem_ld_wait();
+      tc_fence_before();                    // O and (l, m) are in registers: hand both back before the global stores
+      mbar_arrive(o_empty);
+      if (row_valid) {
+#pragma unroll
+        for (int ci = 0; ci < HD / 32; ++ci) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(orow + ci * 32 + 8 * g) = make_uint4(
-                pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-                pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-                pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-                pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+                pack_bf16(__uint_as_float(v[ci][8 * g]) * inv, __uint_as_float(v[ci][8 * g + 1]) * inv),
+                pack_bf16(__uint_as_float(v[ci][8 * g + 2]) * inv, __uint_as_float(v[ci][8 * g + 3]) * inv),
+                pack_bf16(__uint_as_float(v[ci][8 * g + 4]) * inv, __uint_as_float(v[ci][8 * g + 5]) * inv),
+                pack_bf16(__uint_as_float(v[ci][8 * g + 6]) * inv, __uint_as_float(v[ci][8 * g + 7]) * inv));
         }
       }
-      if (p.lse != nullptr && row_valid)
-        p.lse[jb.lse_off + (int64_t)s * jb.lse_stride + t] = (m_sc + log2f(l)) * 0.6931471805599453f;
-      tc_fence_before();
-      if (threadIdx.x == 0) TC_STAMP(job == j_begin ? 11 : 12);
+      if (lse_ptr != nullptr) *lse_ptr = (m_sc + log2f(l)) * 0.6931471805599453f;
+      if (threadIdx.x == 128) TC_STAMP(job == j_begin ? 11 : 12);
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(13);
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
+// 0 off | 1 auto (default) | 2 whenever the shape fits (tests) — MTS_ATTN_TC / mts_set_option("attn_tc", v)
 static int g_attn_tc = -1;
-bool attn_tc_enabled() {
+static int attn_tc_mode() {
   if (g_attn_tc < 0) {
     const char* e = getenv("MTS_ATTN_TC");
-    g_attn_tc = (e && e[0] == '0') ? 0 : 1;
+    g_attn_tc = e ? atoi(e) : 1;
+    if (g_attn_tc < 0 || g_attn_tc > 2) g_attn_tc = 1;
   }
-  return g_attn_tc == 1;
+  return g_attn_tc;
 }
-void attn_tc_set(int v) { g_attn_tc = v ? 1 : 0; }
+void attn_tc_set(int v) { g_attn_tc = (v < 0 || v > 2) ? 1 : v; }
 
-// Whether the tensor-memory kernel covers this shape.  The answer depends on the sequence length only (and on the prefix
-// being a multiple of 16 rows), never on the batch: the shared-prefix and the per-sample layouts of one model take the
-// same route, which is what keeps their outputs bit-identical.
-bool attn_tc_eligible(int L, int Lc, int hd) {
+// Whether the tensor-memory kernel takes this shape.  The answer depends on (Bp, H, L, hd) only — never on how much of L
+// is a shared prefix — so the shared-prefix and the per-sample layouts of one model take the same route, which is what
+// keeps their outputs bit-identical.  Head dim 64 with little work (one job per SM or less: launch + pipeline-fill bound)
+// stays on the mma.sync kernels, which start faster (tools/bench_attn.py --hd64, profiles/r02_attn_tc.md).
+bool attn_tc_eligible(int L, int Lc, int hd, int Bp, int H) {
+  const int mode = attn_tc_mode();
+  if (mode == 0 || !(hd == 64 || hd == 128) || Lc < 0 || Lc >= L) return false;
   // L <= 240 always fits 256 key columns; up to 256 when no dummy columns are needed (prefix a multiple of 16)
-  return attn_tc_enabled() && (hd == 64 || hd == 128) && Lc >= 0 && Lc < L && (L <= 240 || (L <= 256 && (Lc % 16) == 0));
+  if (!(L <= 240 || (L <= 256 && (Lc % 16) == 0))) return false;
+  if (mode == 1 && hd == 64 && (long long)Bp * H * L < 65536) return false;
+  return true;
 }
 
 template <int HD>

@@ -536,6 +536,11 @@ class MedTsLLM(nn.Module):
             return 0
         if precise:           # the fp32 attention kernel tiles the keys: no length limit
             return Lc
+        if 240 < L <= 256:
+            # the tensor-memory attention kernel takes sequences of 241..256 positions only with a prefix that is a
+            # multiple of 16 rows (csrc/attention_tc.cu: attn_tc_eligible); the per-sample layout of the same model always
+            # takes it there, so give the shared layout the same route (identical outputs): a few prefix rows become own rows
+            Lc -= Lc % 16
         # the sequence-resident attention kernels keep all L positions of one head in shared memory
         hd = self.backbone_spec.head_dim
         L64 = (L + 63) // 64 * 64

@@ -31,8 +31,12 @@ def timed(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-for name, Bp, Lc, Ls, H, hd in (("bidmc", 32, 128, 64, 32, 128), ("ludb", 16, 128, 128, 32, 128), ("vent", 16, 128, 42, 32, 128),
-                                ("psm", 64, 128, 12, 16, 64), ("bidmc per-sample", 32, 0, 192, 32, 128)):
+SHAPES = [("bidmc", 32, 128, 64, 32, 128), ("ludb", 16, 128, 128, 32, 128), ("vent", 16, 128, 42, 32, 128),
+          ("psm", 64, 128, 12, 16, 64), ("bidmc per-sample", 32, 0, 192, 32, 128)]
+if "--hd64" in sys.argv:      # GPT-2 family shapes (head dim 64)
+    SHAPES = [("psm", 64, 128, 12, 16, 64), ("psm per-sample", 64, 0, 140, 16, 64), ("gpt4ts etth1", 8, 0, 192, 12, 64),
+              ("gpt2-medium bidmc", 32, 128, 64, 16, 64), ("gpt2-medium ludb", 16, 128, 128, 16, 64), ("gpt2 small", 16, 64, 24, 12, 64)]
+for name, Bp, Lc, Ls, H, hd in SHAPES:
     M = Lc + Bp * Ls
     D = H * hd
     gen = torch.Generator(device=dev).manual_seed(0)
