@@ -58,6 +58,10 @@ int mts_clear_caches(void);
  *   "gemm_force" (0 auto | 1 single-CTA kernel | 2 CTA-pair kernel; default 0): override that cost model (experiments,
  *               tools/bench_gemm.py --force-sweep).
  *   "streamk"   (0 off | 1 auto | 2 force; default 0, env MTS_STREAMK): see mts_gemm_args.sk_workspace.
+ *   "attn_tc"   (0 off | 1 auto | 2 whenever the shape fits; default 1, env MTS_ATTN_TC): the causal-attention forward on
+ *               tcgen05 / tensor memory (sequences of at most 256 positions, head dim 64 / 128) instead of the mma.sync
+ *               kernels.  "auto" decides from (samples, heads, positions, head dim) only, so that the shared-prefix and
+ *               the per-sample layout of one model always run the same arithmetic.
  *   "pdl"       (0/1; default 1, env MTS_PDL=0): launch the per-layer kernels with programmatic stream serialization
  *               (their prologues overlap the previous kernel's tail; they block in griddepcontrol.wait before
  *               touching its results).
@@ -260,7 +264,10 @@ int mts_layernorm(const float* x, int64_t ldx, const float* w, const float* b, u
  *   rope_cos, rope_sin fp32 [L, hd/2] or NULL (GPT-2); rotate-half convention
  *   out  bf16 [Bp*L, H*hd]
  *   lse  fp32 [Bp, H, L] or NULL: log-sum-exp of the scaled scores (saved for backward)
- *   hd in {64, 128}. */
+ *   hd in {64, 128}.
+ *   Pre-rotated q / k (rope NULL) and L <= 256: runs on tcgen05 with the score tile in tensor memory (TMA loads, Q K^T and
+ *   P V as tcgen05.mma, single-pass softmax straight out of TMEM; csrc/attention_tc.cu) unless mts_set_option("attn_tc")
+ *   says otherwise; longer sequences and the rotate-while-staging form use the mma.sync kernels. */
 int mts_attn_causal(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                     uint16_t* out, float* lse, int Bp, int L, int H, int hd, float scale,
                     mts_stream_t stream);

@@ -441,14 +441,15 @@ void attn_tc_set(int v) { g_attn_tc = (v < 0 || v > 2) ? 1 : v; }
 
 // Whether the tensor-memory kernel takes this shape.  The answer depends on (Bp, H, L, hd) only — never on how much of L
 // is a shared prefix — so the shared-prefix and the per-sample layouts of one model take the same route, which is what
-// keeps their outputs bit-identical.  Head dim 64 with little work (one job per SM or less: launch + pipeline-fill bound)
-// stays on the mma.sync kernels, which start faster (tools/bench_attn.py --hd64, profiles/r02_attn_tc.md).
+// keeps their outputs bit-identical.  Head dim 64 with short sequences or little work (one job per SM or less: launch +
+// pipeline-fill bound) stays on the mma.sync kernels, which start faster (tools/bench_attn.py --hd64,
+// profiles/r02_attn_tc.md).
 bool attn_tc_eligible(int L, int Lc, int hd, int Bp, int H) {
   const int mode = attn_tc_mode();
   if (mode == 0 || !(hd == 64 || hd == 128) || Lc < 0 || Lc >= L) return false;
   // L <= 240 always fits 256 key columns; up to 256 when no dummy columns are needed (prefix a multiple of 16)
   if (!(L <= 240 || (L <= 256 && (Lc % 16) == 0))) return false;
-  if (mode == 1 && hd == 64 && (long long)Bp * H * L < 65536) return false;
+  if (mode == 1 && hd == 64 && (L < 160 || (long long)Bp * H * L < 65536)) return false;
   return true;
 }
 
