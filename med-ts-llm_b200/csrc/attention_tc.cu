@@ -427,6 +427,379 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
+// =============================================================================================================
+// Backward on the shared-prefix layout with a frozen backbone (gradient enters at the samples' own rows and only their
+// own q / k / v rows receive one): the same job structure as the forward, five tcgen05 contractions per job and no
+// data movement between them — every operand is consumed in the layout TMA (or the previous stage) left it in:
+//
+//   S  = Q K^T,  dP = dO V^T            K-major A and B                          -> 2 x 256 TMEM columns
+//   8 warps (two per TMEM lane quarter, alternating 32-column chunks; thread = query row):
+//        P = exp2(S c - lse),  dS = P (dP - delta) scale,  delta = rowsum(dO o O)
+//        dS (bf16) -> 128B-swizzled shared memory over the dead V tile, P of the own columns -> its own tile
+//   dQ = dS K                           A = dS K-major, B = K MN-major            -> TMEM columns   0..127
+//   dV = P_own^T dO                     A = P  MN-major (M = own keys), B = dO MN-major ->        128..255
+//   dK = dS_own^T Q                     A = dS MN-major,                B = Q  MN-major ->        256..383
+//   8 warps: TMEM -> (RoPE rotated back on dQ / dK) -> bf16 rows of dqkv
+//
+// Own-key column segments start at a multiple of 64 (the M block of dK / dV must begin on a swizzle row), 16-aligned per
+// sample; no dummy columns (the backward makes no bit-identity promise between row layouts).
+// Algorithmic work per launch: 10 * hd * (visible query-key pairs) FLOP.
+// =============================================================================================================
+struct AttnTcBwdParams {
+  const __nv_bfloat16* out_own;      // [Bp*Ls, D]
+  const float* lse_own;              // [Bp, H, Ls]
+  const float* rope_cos;             // [>= Lc + Ls, hd/2] or null
+  const float* rope_sin;
+  __nv_bfloat16* dqkv_own;           // [Bp*Ls, 3D]
+  int Bp, Lc, Ls, H, D;
+  int spj, groups, n_jobs;
+  int na64, Lsp;                     // first own-key column (Lc rounded up to 64), column segment per sample
+  float scale, scale_log2e;
+};
+
+template <int HD>
+struct AttnTcBwdCfg {
+  static constexpr int KB = HD / 64;
+  static constexpr int kSlabQ = 128 * 128;
+  static constexpr int kSlabKV = 256 * 128;
+  static constexpr int kSlab = 128 * 128;                 // one 64-column slab of P / dS
+  static constexpr int kOffK = KB * kSlabQ;
+  static constexpr int kOffV = kOffK + KB * kSlabKV;
+  static constexpr int kOffdO = kOffV + KB * kSlabKV;
+  static constexpr int kOffdS = (HD == 128) ? kOffV : kOffdO + KB * kSlabQ;       // hd 128: over the V tile, dead after dP
+  static constexpr int kOffP = (HD == 128) ? kOffdO + KB * kSlabQ : kOffdS + 4 * kSlab;
+  static constexpr int kOffBar = kOffP + 2 * kSlab;
+  static constexpr int kSmemBytes = kOffBar + 128 + 1024;
+};
+
+constexpr int kTcBwdThreads = 320;     // warps 0-7 compute (quarter = warp % 4, half = warp / 4), 8 TMA producer, 9 MMA issuer
+
+template <int HD>
+__global__ void __launch_bounds__(kTcBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                   const __grid_constant__ CUtensorMap tmap_do, const AttnTcBwdParams p) {
+  using Cfg = AttnTcBwdCfg<HD>;
+  constexpr int KB = Cfg::KB;
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = tc_smem_raw + (base - smem_u32(tc_smem_raw));
+  const uint32_t sQ = base, sK = base + Cfg::kOffK, sV = base + Cfg::kOffV, sdO = base + Cfg::kOffdO,
+                 sdS = base + Cfg::kOffdS, sP = base + Cfg::kOffP;
+  const uint32_t bar = base + Cfg::kOffBar;
+  const uint32_t ld_full = bar, smem_free = bar + 8, s_full = bar + 16, ds_full = bar + 24, g_full = bar + 32,
+                 epi_done = bar + 40, tmem_slot = bar + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(ld_full, 1); mbar_init(smem_free, 1); mbar_init(s_full, 1); mbar_init(ds_full, 256);
+    mbar_init(g_full, 1); mbar_init(epi_done, 256);
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); tma_prefetch_desc(&tmap_do); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(base_ptr + Cfg::kOffBar + 48);
+  pdl_wait();
+  pdl_trigger();
+
+  const int j_begin = (int)((long long)p.n_jobs * blockIdx.x / gridDim.x);
+  const int j_end = (int)((long long)p.n_jobs * (blockIdx.x + 1) / gridDim.x);
+  // job -> (head, first sample, samples): head-major
+  auto job_head = [&](int job) { return job / p.groups; };
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ph = 0;
+      int res_head = -1;
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+        const int head = job_head(job), b0s = (job - head * p.groups) * p.spj;
+        const int nseg = min(p.spj, p.Bp - b0s);
+        const bool reuse = head == res_head;                         // prefix K rows stay; V is overwritten by dS at hd 128
+        const bool reuse_v = reuse && HD != 128;
+        const int col_h = head * HD;
+        const int own_row0 = b0s * p.Ls;                              // first own row of the job (among the own rows)
+        const int seg_boxes = nseg * (p.Lsp >> 4);
+        // the prefix boxes run up to column na64: the rows between the prefix and the first own segment are masked, but the
+        // tensor core multiplies them by the zeros of P / dS, so they must hold finite data, not stale shared memory
+        const int k_boxes = (reuse ? 0 : (p.na64 >> 4)) + seg_boxes, v_boxes = (reuse_v ? 0 : (p.na64 >> 4)) + seg_boxes;
+        mbar_wait(smem_free, ph ^ 1u, 600);                           // the previous job's dQ / dV / dK MMAs have retired
+        mbar_arrive_expect_tx(ld_full, KB * (2 * Cfg::kSlabQ + (k_boxes + v_boxes) * 2048));
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(sQ + kb * Cfg::kSlabQ, &tmap_q, ld_full, col_h + kb * 64, p.Lc + own_row0, 0, kEvictFirst);
+          tma_load_3d(sdO + kb * Cfg::kSlabQ, &tmap_do, ld_full, col_h + kb * 64, own_row0, 0, kEvictFirst);
+        }
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {                     // 0: K, 1: V
+          const uint32_t slab = which ? sV : sK;
+          const bool skip_prefix = which ? reuse_v : reuse;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t dst = slab + kb * Cfg::kSlabKV;
+            const int col = (which + 1) * p.D + col_h + kb * 64;
+            if (!skip_prefix)
+              for (int r = 0; r < p.na64; r += 16) tma_load_3d(dst + r * 128, &tmap_kv, ld_full, col, r, 0, kEvictLast);
+            for (int s = 0; s < nseg; ++s)
+              for (int r = 0; r < p.Lsp; r += 16)
+                tma_load_3d(dst + (p.na64 + s * p.Lsp + r) * 128, &tmap_kv, ld_full, col, p.Lc + own_row0 + s * p.Ls + r, 0,
+                            kEvictNormal);
+          }
+        }
+        res_head = head;
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const uint32_t tS = tmem_base, tdP = tmem_base + 256, tdQ = tmem_base, tdV = tmem_base + 128, tdK = tmem_base + 256;
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD) | (1u << 16);                 // B MN-major
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD) | (1u << 15) | (1u << 16);    // A and B MN-major
+      for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+        const int head = job_head(job), b0s = (job - head * p.groups) * p.spj;
+        const int nseg = min(p.spj, p.Bp - b0s);
+        const int nk = p.na64 + nseg * p.Lsp;                         // key columns (multiple of 16, <= 256)
+        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk);
+        mbar_wait(ld_full, ph, 610);
+        mbar_wait(epi_done, ph ^ 1u, 611);                            // the previous job's gradients have left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t aq = umma_desc_sw128(sQ + kb * Cfg::kSlabQ), bk = umma_desc_sw128(sK + kb * Cfg::kSlabKV);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS, aq + 2u * k, bk + 2u * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t ao = umma_desc_sw128(sdO + kb * Cfg::kSlabQ), bv = umma_desc_sw128(sV + kb * Cfg::kSlabKV);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tdP, ao + 2u * k, bv + 2u * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        mbar_wait(ds_full, ph, 612);                                  // P / dS are in shared memory, S / dP are consumed
+        tc_fence_after();
+        for (int ks = 0; ks < (nk >> 4); ++ks)                        // dQ = dS K
+          umma_bf16(tdQ, umma_desc_sw128(sdS + (ks >> 2) * Cfg::kSlab) + 2u * (ks & 3),
+                    umma_desc_mn_sw128(sK + ks * 2048, Cfg::kSlabKV), idesc_dq, ks != 0 ? 1u : 0u);
+        const uint32_t ds_own = sdS + (p.na64 >> 6) * Cfg::kSlab;
+#pragma unroll
+        for (int kq = 0; kq < 8; ++kq) {                              // dV = P_own^T dO,  dK = dS_own^T Q   (K = 128 query rows)
+          umma_bf16(tdV, umma_desc_mn_sw128(sP + kq * 2048, Cfg::kSlab), umma_desc_mn_sw128(sdO + kq * 2048, Cfg::kSlabQ),
+                    idesc_kv, kq != 0 ? 1u : 0u);
+          umma_bf16(tdK, umma_desc_mn_sw128(ds_own + kq * 2048, Cfg::kSlab), umma_desc_mn_sw128(sQ + kq * 2048, Cfg::kSlabQ),
+                    idesc_kv, kq != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_free);
+        umma_commit(g_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ compute warps 0..7
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;                                // TMEM lane: query row (phase 1), own key (phase 2)
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int rx = r & 7;
+    uint8_t* ds_row = base_ptr + Cfg::kOffdS + r * 128;
+    uint8_t* p_row = base_ptr + Cfg::kOffP + r * 128;
+    const uint8_t* do_row = base_ptr + Cfg::kOffdO + r * 128;
+    const int r_div = r / p.Ls, m_div = r / p.Lsp;
+    uint32_t ph = 0;
+    for (int job = j_begin; job < j_end; ++job, ph ^= 1u) {
+      const int head = job_head(job), b0s = (job - head * p.groups) * p.spj;
+      const int nseg = min(p.spj, p.Bp - b0s);
+      const int nk = p.na64 + nseg * p.Lsp;
+      const int R = nseg * p.Ls;
+      const int own_row0 = b0s * p.Ls;
+      // ---- phase 1 role: query row r
+      const bool row_valid = r < R;
+      const int s = row_valid ? r_div : 0, t = r - s * p.Ls;
+      const int own_lo = row_valid ? p.na64 + s * p.Lsp : (1 << 30);
+      const int own_hi = row_valid ? own_lo + t : -1;
+      const int n_prefix = row_valid ? p.Lc : 0;
+      const float lse2 = row_valid ? p.lse_own[((int64_t)(b0s + s) * p.H + head) * p.Ls + t] * 1.4426950408889634f : INFINITY;
+      // O row of this query (for delta), in flight before the operands land
+      uint4 orow[HD / 8];
+      {
+        const uint4* op = reinterpret_cast<const uint4*>(p.out_own + (int64_t)(own_row0 + (row_valid ? r : 0)) * p.D +
+                                                         (int64_t)head * HD);
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) orow[i] = __ldg(op + i);
+      }
+      uint32_t vmask = 0;                         // 32-column chunks in which some row of this quarter sees a key
+      for (int c0 = 0, k = 0; c0 < nk; c0 += 32, ++k)
+        if (c0 < p.Lc || __any_sync(0xffffffffu, c0 <= own_hi && c0 + 31 >= own_lo)) vmask |= 1u << k;
+      if (lane == 0) mbar_wait(s_full, ph, 620);  // implies ld_full: Q / K / V / dO are in shared memory
+      __syncwarp();
+      tc_fence_after();
+      // delta = rowsum(dO o O): dO from its swizzled tile (16-byte chunk q of row r sits at q ^ (r & 7))
+      float delta = 0.0f;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 d = *reinterpret_cast<const uint4*>(do_row + kb * Cfg::kSlabQ + ((q ^ rx) << 4));
+          const uint4 o = orow[kb * 8 + q];
+          const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) delta += bf16_lo(dw[i]) * bf16_lo(ow[i]) + bf16_hi(dw[i]) * bf16_hi(ow[i]);
+        }
+      }
+      if (!row_valid) delta = 0.0f;
+      // the two warps of a quarter alternate chunks; chunks nobody sees are zero-filled
+      for (int c0 = 32 * half, k = half; c0 < nk; c0 += 64, k += 2) {
+        uint8_t* dsd = ds_row + (c0 >> 6) * Cfg::kSlab;
+        const int q0 = (c0 & 63) >> 3;
+        const bool own_chunk = c0 >= p.na64;
+        uint8_t* pd = p_row + (own_chunk ? ((c0 - p.na64) >> 6) : 0) * Cfg::kSlab;
+        if (!(vmask & (1u << k))) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<uint4*>(dsd + (((q0 + g) ^ rx) << 4)) = make_uint4(0, 0, 0, 0);
+            if (own_chunk) *reinterpret_cast<uint4*>(pd + (((q0 + g) ^ rx) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tq + c0, sv);
+        tmem_ld_32x32(tq + 256 + c0, dv);
+        tmem_ld_wait();
+        const uint32_t bits = chunk_mask(c0, n_prefix, own_lo, own_hi);
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool vis = (bits & (1u << j)) != 0;               // selects, not products: a masked column may hold anything
+          const float e = ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2e, -lse2));
+          pv[j] = vis ? e : 0.0f;
+          dsv[j] = vis ? e * (__uint_as_float(dv[j]) - delta) * p.scale : 0.0f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(dsd + (((q0 + g) ^ rx) << 4)) =
+              make_uint4(pack_bf16(dsv[8 * g], dsv[8 * g + 1]), pack_bf16(dsv[8 * g + 2], dsv[8 * g + 3]),
+                         pack_bf16(dsv[8 * g + 4], dsv[8 * g + 5]), pack_bf16(dsv[8 * g + 6], dsv[8 * g + 7]));
+          if (own_chunk)
+            *reinterpret_cast<uint4*>(pd + (((q0 + g) ^ rx) << 4)) =
+                make_uint4(pack_bf16(pv[8 * g], pv[8 * g + 1]), pack_bf16(pv[8 * g + 2], pv[8 * g + 3]),
+                           pack_bf16(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16(pv[8 * g + 6], pv[8 * g + 7]));
+        }
+      }
+      // own columns past the job's segments (last, smaller group): P must still be zero there — those are M rows of dV
+      for (int c0 = ((nk + 31) & ~31) + 32 * half; c0 < p.na64 + 128; c0 += 64) {
+        uint8_t* pd = p_row + ((c0 - p.na64) >> 6) * Cfg::kSlab;
+        uint8_t* dsd = ds_row + (c0 >> 6) * Cfg::kSlab;
+        const int q0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(pd + (((q0 + g) ^ rx) << 4)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dsd + (((q0 + g) ^ rx) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+
+      // ---- phase 2 role: lane r = query row for dQ, own key index for dV / dK
+      const int ms = m_div, mj = r - ms * p.Lsp;                       // own key r: sample ms of the job, token mj
+      const bool key_valid = ms < nseg && mj < p.Ls;
+      __nv_bfloat16* dq_dst = p.dqkv_own + (int64_t)(own_row0 + r) * 3 * p.D + (int64_t)head * HD;
+      __nv_bfloat16* dk_dst = p.dqkv_own + (int64_t)(own_row0 + ms * p.Ls + mj) * 3 * p.D + p.D + (int64_t)head * HD;
+      __nv_bfloat16* dv_dst = dk_dst + p.D;
+      const float* cq = p.rope_cos ? p.rope_cos + (int64_t)(p.Lc + t) * (HD / 2) : nullptr;
+      const float* sq = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + t) * (HD / 2) : nullptr;
+      const float* ck = p.rope_cos ? p.rope_cos + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
+      const float* sk = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
+      if (lane == 0) mbar_wait(g_full, ph, 621);
+      __syncwarp();
+      tc_fence_after();
+      // a (lo, hi) chunk pair of a rotated gradient: rotate back and store;  lo chunk c holds columns [32c, 32c + 32)
+      auto store_pair = [&](uint32_t tcol, int c_lo, __nv_bfloat16* dst, const float* cosr, const float* sinr, bool valid) {
+        constexpr int kHalfChunks = HD / 64;
+        uint32_t lo[32], hi[32];
+        tmem_ld_32x32(tq + tcol + 32 * c_lo, lo);
+        tmem_ld_32x32(tq + tcol + 32 * (c_lo + kHalfChunks), hi);
+        tmem_ld_wait();
+        if (!valid) return;
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(lo[j]), y = __uint_as_float(hi[j]);
+          if (cosr != nullptr) {
+            const float c = cosr[32 * c_lo + j], sn = sinr[32 * c_lo + j];
+            a[j] = x * c + y * sn;
+            b[j] = y * c - x * sn;
+          } else {
+            a[j] = x; b[j] = y;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(dst + 32 * c_lo + 8 * g) =
+              make_uint4(pack_bf16(a[8 * g], a[8 * g + 1]), pack_bf16(a[8 * g + 2], a[8 * g + 3]),
+                         pack_bf16(a[8 * g + 4], a[8 * g + 5]), pack_bf16(a[8 * g + 6], a[8 * g + 7]));
+          *reinterpret_cast<uint4*>(dst + 32 * (c_lo + kHalfChunks) + 8 * g) =
+              make_uint4(pack_bf16(b[8 * g], b[8 * g + 1]), pack_bf16(b[8 * g + 2], b[8 * g + 3]),
+                         pack_bf16(b[8 * g + 4], b[8 * g + 5]), pack_bf16(b[8 * g + 6], b[8 * g + 7]));
+        }
+      };
+      if constexpr (HD == 128) {
+        // half 0: dQ pair (0, 2), dK pair (0, 2), dV chunks 0, 1;   half 1: dQ pair (1, 3), dK pair (1, 3), dV chunks 2, 3
+        store_pair(0, half, dq_dst, cq, sq, row_valid);
+        store_pair(256, half, dk_dst, ck, sk, key_valid);
+        // dV: two adjacent chunks, no rotation (store_pair with a pair distance of one chunk would need another shape)
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(tq + 128 + 64 * half, v0);
+          tmem_ld_32x32(tq + 128 + 64 * half + 32, v1);
+          tmem_ld_wait();
+          if (key_valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              *reinterpret_cast<uint4*>(dv_dst + 64 * half + 8 * g) = make_uint4(
+                  pack_bf16(__uint_as_float(v0[8 * g]), __uint_as_float(v0[8 * g + 1])),
+                  pack_bf16(__uint_as_float(v0[8 * g + 2]), __uint_as_float(v0[8 * g + 3])),
+                  pack_bf16(__uint_as_float(v0[8 * g + 4]), __uint_as_float(v0[8 * g + 5])),
+                  pack_bf16(__uint_as_float(v0[8 * g + 6]), __uint_as_float(v0[8 * g + 7])));
+              *reinterpret_cast<uint4*>(dv_dst + 64 * half + 32 + 8 * g) = make_uint4(
+                  pack_bf16(__uint_as_float(v1[8 * g]), __uint_as_float(v1[8 * g + 1])),
+                  pack_bf16(__uint_as_float(v1[8 * g + 2]), __uint_as_float(v1[8 * g + 3])),
+                  pack_bf16(__uint_as_float(v1[8 * g + 4]), __uint_as_float(v1[8 * g + 5])),
+                  pack_bf16(__uint_as_float(v1[8 * g + 6]), __uint_as_float(v1[8 * g + 7])));
+            }
+          }
+        }
+      } else {
+        // hd 64: half 0: dQ pair (0, 1) + dV chunk 0;   half 1: dK pair (0, 1) + dV chunk 1
+        if (half == 0) store_pair(0, 0, dq_dst, cq, sq, row_valid);
+        else store_pair(256, 0, dk_dst, ck, sk, key_valid);
+        uint32_t v0[32];
+        tmem_ld_32x32(tq + 128 + 32 * half, v0);
+        tmem_ld_wait();
+        if (key_valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(dv_dst + 32 * half + 8 * g) = make_uint4(
+                pack_bf16(__uint_as_float(v0[8 * g]), __uint_as_float(v0[8 * g + 1])),
+                pack_bf16(__uint_as_float(v0[8 * g + 2]), __uint_as_float(v0[8 * g + 3])),
+                pack_bf16(__uint_as_float(v0[8 * g + 4]), __uint_as_float(v0[8 * g + 5])),
+                pack_bf16(__uint_as_float(v0[8 * g + 6]), __uint_as_float(v0[8 * g + 7])));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(epi_done);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // 0 off | 1 auto (default) | 2 whenever the shape fits (tests) — MTS_ATTN_TC / mts_set_option("attn_tc", v)
 static int g_attn_tc = -1;
 static int attn_tc_mode() {
@@ -525,6 +898,71 @@ int launch_attn_tc(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L
                    cudaStream_t stream) {
   if (hd == 128) return launch_attn_tc_t<128>(qkv, out, lse, Bp, L, Lc, H, scale, stream);
   return launch_attn_tc_t<64>(qkv, out, lse, Bp, L, Lc, H, scale, stream);
+}
+
+// The tensor-memory backward covers the frozen-backbone case (own rows only) when a sample's own rows fit one tile and
+// prefix + own columns fit the 256-column score tile with the own columns starting on a multiple of 64.
+bool attn_tc_bwd_eligible(int Lc, int Ls, int hd, int Bp, int H) {
+  const int mode = attn_tc_mode();
+  if (mode == 0 || !(hd == 64 || hd == 128) || Lc < 16 || Ls < 1 || Ls > 128) return false;
+  const int na64 = (Lc + 63) & ~63, lsp = (Ls + 15) & ~15;
+  if (na64 > 128 || na64 + lsp > 256) return false;
+  if (mode == 1 && hd == 64 && (long long)Bp * H * (Lc + Ls) < 65536) return false;
+  return true;
+}
+
+template <int HD>
+static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own,
+                                const uint16_t* dout_own, const float* lse_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls,
+                                int H, float scale, cudaStream_t stream) {
+  using Cfg = AttnTcBwdCfg<HD>;
+  auto kern = attn_bwd_tc_kernel<HD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_bwd_tc_kernel)", e);
+    attr_done = true;
+  }
+  AttnTcBwdParams p;
+  p.out_own = reinterpret_cast<const __nv_bfloat16*>(out_own);
+  p.lse_own = lse_own;
+  p.rope_cos = rc; p.rope_sin = rs;
+  p.dqkv_own = reinterpret_cast<__nv_bfloat16*>(dqkv_own);
+  p.Bp = Bp; p.Lc = Lc; p.Ls = Ls; p.H = H; p.D = H * HD;
+  p.na64 = (Lc + 63) & ~63;
+  p.Lsp = (Ls + 15) & ~15;
+  int spj = 128 / Ls;
+  const int by_cols = (256 - p.na64) / p.Lsp, by_m = 128 / p.Lsp;    // score columns; the 128-row M block of dK / dV
+  if (by_cols < spj) spj = by_cols;
+  if (by_m < spj) spj = by_m;
+  if (spj > Bp) spj = Bp;
+  if (spj < 1) spj = 1;
+  p.spj = spj;
+  p.groups = (Bp + spj - 1) / spj;
+  const int64_t n_jobs = (int64_t)p.groups * H;
+  if (n_jobs > 0x7fffffffLL) return set_error(MTS_ERR_INVALID_ARG, "attention backward: too many tiles");
+  p.n_jobs = (int)n_jobs;
+  p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  const int64_t rows = (int64_t)Lc + (int64_t)Bp * Ls, own_rows = (int64_t)Bp * Ls;
+  CUtensorMap tq, tkv, tdo;
+  int rc_ = get_tmap_3d(&tq, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 128, 2);
+  if (rc_) return rc_;
+  rc_ = get_tmap_3d(&tkv, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 16, 2);
+  if (rc_) return rc_;
+  rc_ = get_tmap_3d(&tdo, dout_own, (int64_t)p.D, own_rows, 1, (int64_t)p.D, own_rows * p.D, 64, 128, 2);
+  if (rc_) return rc_;
+  const int grid = p.n_jobs < num_sms() ? p.n_jobs : num_sms();
+  LAUNCH_PDL(kern, grid, kTcBwdThreads, Cfg::kSmemBytes, stream, tq, tkv, tdo, p);
+  count_launch();
+  return check_launch("attn_bwd_tc_kernel");
+}
+
+int launch_attn_bwd_tc(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own, const uint16_t* dout_own,
+                       const float* lse_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd, float scale,
+                       cudaStream_t stream) {
+  if (hd == 128) return launch_attn_bwd_tc_t<128>(qkv, rc, rs, out_own, dout_own, lse_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
+  return launch_attn_bwd_tc_t<64>(qkv, rc, rs, out_own, dout_own, lse_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
 }
 
 }  // namespace mts

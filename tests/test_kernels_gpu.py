@@ -334,6 +334,63 @@ def test_attn_tensor_memory_kernel(ops, cuda, Bp, Lc, Ls, H, hd):
         torch.testing.assert_close(lse.double(), ref_lse, rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("rope", [False, True])
+@pytest.mark.parametrize("Bp,Lc,Ls,H,hd", [
+    (5, 128, 64, 2, 128),      # BIDMC: two samples per tile, ragged last group
+    (11, 128, 12, 3, 64),      # PSM: eight samples per tile
+    (7, 128, 42, 2, 128),      # Ventilator: own rows not a multiple of 16
+    (3, 128, 128, 1, 128),     # LUDB: 256 key columns
+    (4, 37, 12, 3, 64),        # prefix not a multiple of 64: masked gap columns
+    (5, 100, 33, 1, 128),
+])
+def test_attn_tensor_memory_backward(ops, cuda, Bp, Lc, Ls, H, hd, rope):
+    """The tcgen05 / TMEM backward of the shared-prefix layout (own rows only: frozen backbone) against fp64 autograd and
+    against the mma.sync kernels it replaces."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(Lc * 3 + Ls + hd)
+    D, L = H * hd, Lc + Ls
+    M = Lc + Bp * Ls
+    qkv = (torch.randn(M, 3 * D, generator=g) * 0.7).to(cuda, torch.bfloat16)       # q / k are taken as already rotated
+    dout = torch.randn(Bp * Ls, D, generator=g).to(cuda, torch.bfloat16)
+    tabs = _rope_tables(L, hd, cuda) if rope else None
+    out, lse_full = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, want_lse=True)
+    lse = ops.lse_own_view(lse_full, Bp, Lc, Ls, H)
+
+    def run():
+        return ops.attn_causal_shared_bwd(qkv, out[Lc:], dout, lse, Bp, Lc, Ls, H, hd, rope=tabs)
+
+    _lib.set_option("attn_tc", 2)
+    try:
+        got = run()
+        assert torch.equal(run(), got)                                              # deterministic
+        _lib.set_option("attn_tc", 0)
+        old = run()
+    finally:
+        _lib.set_option("attn_tc", 1)
+    # fp64 reference on the per-sample view; the gradient w.r.t. the ROTATED q / k is rotated back like the kernels do
+    x = _expand_shared(qkv, Bp, Lc, Ls).double().requires_grad_(True)
+    q, k, v = (t.view(Bp, L, H, hd).transpose(1, 2) for t in x.split(D, dim=-1))
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    mask = torch.ones(L, L, device=cuda, dtype=torch.bool).tril()
+    o = (torch.softmax(sc.masked_fill(~mask, float("-inf")), -1) @ v).transpose(1, 2).reshape(Bp, L, D)
+    dfull = torch.zeros(Bp, L, D, device=cuda, dtype=torch.float64)
+    dfull[:, Lc:] = dout.double().view(Bp, Ls, D)
+    (gx,) = torch.autograd.grad(o, x, dfull)
+    ref = gx.view(Bp, L, 3 * D)[:, Lc:].reshape(Bp * Ls, 3 * D)
+    if rope:
+        cos = torch.cat([tabs[0], tabs[0]], -1).double()[Lc:]                       # positions of the own tokens
+        sin = torch.cat([tabs[1], tabs[1]], -1).double()[Lc:]
+        rot_t = lambda t: torch.cat([t[..., hd // 2:], -t[..., :hd // 2]], -1)      # transpose of rotate-half
+        for sl in (slice(0, D), slice(D, 2 * D)):
+            gsec = ref[:, sl].view(Bp, Ls, H, hd)
+            ref[:, sl] = (gsec * cos[None, :, None] + rot_t(gsec * sin[None, :, None])).reshape(Bp * Ls, D)
+    assert torch.isfinite(got.float()).all()
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e_ref, e_old = _rel_l2(got[:, sl], ref[:, sl]), _rel_l2(got[:, sl], old[:, sl])
+        assert e_ref < 1.5e-2, (name, e_ref)        # bf16 P / dS / outputs
+        assert e_old < 1.5e-2, (name, e_old)
+
+
 # ------------------------------------------------------------------------------- training-path kernels
 def test_gemm_resid_out_of_place_and_scalar_epilogue(ops, cuda):
     g = torch.Generator().manual_seed(21)
@@ -592,7 +649,7 @@ def _expand_shared(t, Bp, Lc, Ls):
 
 
 @pytest.mark.parametrize("Bp,Lc,Ls,H,hd", [(3, 128, 64, 2, 128), (4, 37, 12, 3, 64), (2, 16, 100, 2, 64), (5, 130, 33, 1, 128)])
-def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
+def test_attn_causal_shared_prefix_matches_plain(ops, cuda, request, Bp, Lc, Ls, H, hd):
     """The prefix rows are stored once; results must equal the plain kernels run on the layout with the
     prefix repeated in front of every sample (same kernel, same key order: bit-identical forward)."""
     g = torch.Generator().manual_seed(Lc * 7 + Ls)
@@ -607,7 +664,11 @@ def test_attn_causal_shared_prefix_matches_plain(ops, cuda, Bp, Lc, Ls, H, hd):
     lse = ops.lse_own_view(lse_full, Bp, Lc, Ls, H)
     assert torch.equal(lse, lse_p[:, :, Lc:])
     assert torch.equal(lse_full[:H * Lc].view(H, Lc), lse_p[0, :, :Lc])
-    # backward: gradient only enters through the samples' own rows
+    # backward: gradient only enters through the samples' own rows.  The mma.sync kernels of both layouts share their
+    # arithmetic (1e-6); the tensor-memory backward of the shared layout is checked in test_attn_tensor_memory_backward.
+    from medtsllm_b200 import _lib
+    _lib.set_option("attn_tc", 0)
+    request.addfinalizer(lambda: _lib.set_option("attn_tc", 1))
     tabs = _rope_tables(L, hd, cuda)
     dout = torch.randn(Bp * Ls, D, generator=g).to(cuda, torch.bfloat16)
     dqkv = ops.attn_causal_shared_bwd(qkv, out[Lc:], dout, lse, Bp, Lc, Ls, H, hd, rope=tabs)
