@@ -711,43 +711,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const float* sq = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + t) * (HD / 2) : nullptr;
       const float* ck = p.rope_cos ? p.rope_cos + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
       const float* sk = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
+      // RoPE table rows of this lane's chunk pair, in flight before the gradients are ready.  With Ls a multiple of 16 lane r
+      // is query (s, t) AND own key (s, t): one pair of table rows serves dQ and dK.
+      constexpr int kHalfChunks = HD / 64;
+      const int c_pair = (HD == 128) ? half : 0;
+      const bool same_rows = p.Lsp == p.Ls;
+      float cs[32], sn[32];
+      auto load_tables = [&](const float* cosr, const float* sinr) {
+        const float4* c4 = reinterpret_cast<const float4*>(cosr + 32 * c_pair);
+        const float4* s4 = reinterpret_cast<const float4*>(sinr + 32 * c_pair);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cv = __ldg(c4 + j), sv4 = __ldg(s4 + j);
+          cs[4 * j] = cv.x; cs[4 * j + 1] = cv.y; cs[4 * j + 2] = cv.z; cs[4 * j + 3] = cv.w;
+          sn[4 * j] = sv4.x; sn[4 * j + 1] = sv4.y; sn[4 * j + 2] = sv4.z; sn[4 * j + 3] = sv4.w;
+        }
+      };
+      const bool roped = p.rope_cos != nullptr;
+      const bool first_is_q = (HD == 128) || half == 0;               // hd 64: half 1 only handles dK
+      if (roped) {
+        if (first_is_q) load_tables(cq, sq); else load_tables(ck, sk);
+      }
       if (lane == 0) mbar_wait(g_full, ph, 621);
       __syncwarp();
       tc_fence_after();
-      // a (lo, hi) chunk pair of a rotated gradient: rotate back and store;  lo chunk c holds columns [32c, 32c + 32)
-      auto store_pair = [&](uint32_t tcol, int c_lo, __nv_bfloat16* dst, const float* cosr, const float* sinr, bool valid) {
-        constexpr int kHalfChunks = HD / 64;
+      // a (lo, hi) chunk pair of a rotated gradient: rotate back with the loaded table rows and store;
+      // lo chunk c holds columns [32c, 32c + 32)
+      auto store_pair = [&](uint32_t tcol, __nv_bfloat16* dst, bool valid) {
         uint32_t lo[32], hi[32];
-        tmem_ld_32x32(tq + tcol + 32 * c_lo, lo);
-        tmem_ld_32x32(tq + tcol + 32 * (c_lo + kHalfChunks), hi);
+        tmem_ld_32x32(tq + tcol + 32 * c_pair, lo);
+        tmem_ld_32x32(tq + tcol + 32 * (c_pair + kHalfChunks), hi);
         tmem_ld_wait();
         if (!valid) return;
         float a[32], b[32];
+        if (roped) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(lo[j]), y = __uint_as_float(hi[j]);
-          if (cosr != nullptr) {
-            const float c = cosr[32 * c_lo + j], sn = sinr[32 * c_lo + j];
-            a[j] = x * c + y * sn;
-            b[j] = y * c - x * sn;
-          } else {
-            a[j] = x; b[j] = y;
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(lo[j]), y = __uint_as_float(hi[j]);
+            a[j] = x * cs[j] + y * sn[j];
+            b[j] = y * cs[j] - x * sn[j];
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(lo[j]); b[j] = __uint_as_float(hi[j]); }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          *reinterpret_cast<uint4*>(dst + 32 * c_lo + 8 * g) =
+          *reinterpret_cast<uint4*>(dst + 32 * c_pair + 8 * g) =
               make_uint4(pack_bf16(a[8 * g], a[8 * g + 1]), pack_bf16(a[8 * g + 2], a[8 * g + 3]),
                          pack_bf16(a[8 * g + 4], a[8 * g + 5]), pack_bf16(a[8 * g + 6], a[8 * g + 7]));
-          *reinterpret_cast<uint4*>(dst + 32 * (c_lo + kHalfChunks) + 8 * g) =
+          *reinterpret_cast<uint4*>(dst + 32 * (c_pair + kHalfChunks) + 8 * g) =
               make_uint4(pack_bf16(b[8 * g], b[8 * g + 1]), pack_bf16(b[8 * g + 2], b[8 * g + 3]),
                          pack_bf16(b[8 * g + 4], b[8 * g + 5]), pack_bf16(b[8 * g + 6], b[8 * g + 7]));
         }
       };
       if constexpr (HD == 128) {
         // half 0: dQ pair (0, 2), dK pair (0, 2), dV chunks 0, 1;   half 1: dQ pair (1, 3), dK pair (1, 3), dV chunks 2, 3
-        store_pair(0, half, dq_dst, cq, sq, row_valid);
-        store_pair(256, half, dk_dst, ck, sk, key_valid);
+        store_pair(0, dq_dst, row_valid);
+        if (roped && !same_rows) load_tables(ck, sk);
+        store_pair(256, dk_dst, key_valid);
         // dV: two adjacent chunks, no rotation (store_pair with a pair distance of one chunk would need another shape)
         {
           uint32_t v0[32], v1[32];
@@ -772,8 +794,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       } else {
         // hd 64: half 0: dQ pair (0, 1) + dV chunk 0;   half 1: dK pair (0, 1) + dV chunk 1
-        if (half == 0) store_pair(0, 0, dq_dst, cq, sq, row_valid);
-        else store_pair(256, 0, dk_dst, ck, sk, key_valid);
+        if (half == 0) store_pair(0, dq_dst, row_valid);
+        else store_pair(256, dk_dst, key_valid);
         uint32_t v0[32];
         tmem_ld_32x32(tq + 128 + 32 * half, v0);
         tmem_ld_wait();
@@ -902,8 +924,9 @@ int launch_attn_tc(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L
 
 // The tensor-memory backward covers the frozen-backbone case (own rows only) when a sample's own rows fit one tile and
 // prefix + own columns fit the 256-column score tile with the own columns starting on a multiple of 64.
-bool attn_tc_bwd_eligible(int Lc, int Ls, int hd, int Bp, int H) {
+bool attn_tc_bwd_eligible(int Lc, int Ls, int hd, int Bp, int H, const float* rc, const float* rs) {
   const int mode = attn_tc_mode();
+  if ((reinterpret_cast<uintptr_t>(rc) & 15) || (reinterpret_cast<uintptr_t>(rs) & 15)) return false;   // float4 table loads
   if (mode == 0 || !(hd == 64 || hd == 128) || Lc < 16 || Ls < 1 || Ls > 128) return false;
   const int na64 = (Lc + 63) & ~63, lsp = (Ls + 15) & ~15;
   if (na64 > 128 || na64 + lsp > 256) return false;

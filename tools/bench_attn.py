@@ -43,15 +43,20 @@ for name, Bp, Lc, Ls, H, hd in SHAPES:
     qkv = (torch.randn(M, 3 * D, device=dev, generator=gen) * 0.5).to(torch.bfloat16)
     dout = (torch.randn(M, D, device=dev, generator=gen) * 0.5).to(torch.bfloat16)
     flops = 4.0 * H * hd * (Lc * Lc / 2 + Bp * Ls * (Lc + Ls / 2))
+    # Llama shapes (head dim 128): the backward rotates dQ / dK back (RoPE), as in the training step
+    Ltab = Lc + Ls
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device=dev, dtype=torch.float32) / hd))
+    ang = torch.arange(Ltab, device=dev, dtype=torch.float32)[:, None] * inv[None, :]
+    rope = (ang.cos().contiguous(), ang.sin().contiguous()) if hd == 128 else None
     if Lc:
         out, lse = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, want_lse=True)
         t_f = timed(lambda: ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, out=out, want_lse=True))
         own = slice(Lc, None)
         lse_own = ops.lse_own_view(lse, Bp, Lc, Ls, H)
-        t_b = timed(lambda: ops.attn_causal_shared_bwd(qkv, out[own], dout[own], lse_own, Bp, Lc, Ls, H, hd))
+        t_b = timed(lambda: ops.attn_causal_shared_bwd(qkv, out[own], dout[own], lse_own, Bp, Lc, Ls, H, hd, rope=rope))
     else:
         out, lse = ops.attn_causal(qkv, Bp, Ls, H, hd, want_lse=True)
         t_f = timed(lambda: ops.attn_causal(qkv, Bp, Ls, H, hd, out=out, want_lse=True))
-        t_b = timed(lambda: ops.attn_causal_bwd(qkv, out, dout, lse, Bp, Ls, H, hd, pre_roped=True))
+        t_b = timed(lambda: ops.attn_causal_bwd(qkv, out, dout, lse, Bp, Ls, H, hd, rope=rope, pre_roped=True))
     print(f"[attn] {name:18s} Bp={Bp} Lc={Lc} Ls={Ls} H={H} hd={hd}: fwd {t_f:7.1f} us ({flops / t_f / 1e6:6.1f} TFLOP/s)   "
           f"bwd {t_b:7.1f} us ({2.5 * flops / t_b / 1e6:6.1f} TFLOP/s)")
