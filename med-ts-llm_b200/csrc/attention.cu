@@ -24,8 +24,8 @@ int launch_attn_tc(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int L
                    cudaStream_t stream);
 bool attn_tc_bwd_eligible(int Lc, int Ls, int hd, int Bp, int H, const float* rc, const float* rs);
 int launch_attn_bwd_tc(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own, const uint16_t* dout_own,
-                       const float* lse_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd, float scale,
-                       cudaStream_t stream);
+                       const float* lse_own, float* delta_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
+                       float scale, cudaStream_t stream);
 
 
 constexpr int kAttnBlockQ = 64;
@@ -1574,8 +1574,10 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   // so the fused kernel — which keeps delta in shared memory only — cannot be used
   const int L = Lc + Ls;
   const int D = H * HD;
-  if (!delta_needed_later && attn_tc_bwd_eligible(Lc, Ls, HD, Bp, H, rc, rs))
-    return launch_attn_bwd_tc(qkv, rc, rs, out_own, dout_own, lse_own, dqkv_own, Bp, Lc, Ls, H, HD, scale, stream);
+  // tensor-memory kernel (attention_tc.cu); it leaves delta of the own rows behind when the full backward needs it
+  if (attn_tc_bwd_eligible(Lc, Ls, HD, Bp, H, rc, rs))
+    return launch_attn_bwd_tc(qkv, rc, rs, out_own, dout_own, lse_own, delta_needed_later ? delta : nullptr, dqkv_own, Bp, Lc,
+                              Ls, H, HD, scale, stream);
   if (seq_bwd_smem_bytes<HD>(L) > 220 * 1024)
     return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd: %d positions do not fit in shared memory", L);
   auto sq = attn_bwd_dq_seq_kernel<HD>;

@@ -451,6 +451,7 @@ struct AttnTcBwdParams {
   const float* rope_cos;             // [>= Lc + Ls, hd/2] or null
   const float* rope_sin;
   __nv_bfloat16* dqkv_own;           // [Bp*Ls, 3D]
+  float* delta_own;                  // [Bp, H, Ls] or null: rowsum(dO o O), kept for the prefix-key kernels of the full backward
   int Bp, Lc, Ls, H, D;
   int spj, groups, n_jobs;
   int na64, Lsp;                     // first own-key column (Lc rounded up to 64), column segment per sample
@@ -648,6 +649,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
       if (!row_valid) delta = 0.0f;
+      if (p.delta_own != nullptr && half == 0 && row_valid)
+        p.delta_own[((int64_t)(b0s + s) * p.H + head) * p.Ls + t] = delta;
       // the two warps of a quarter alternate chunks; chunks nobody sees are zero-filled
       for (int c0 = 32 * half, k = half; c0 < nk; c0 += 64, k += 2) {
         uint8_t* dsd = ds_row + (c0 >> 6) * Cfg::kSlab;
@@ -936,8 +939,8 @@ bool attn_tc_bwd_eligible(int Lc, int Ls, int hd, int Bp, int H, const float* rc
 
 template <int HD>
 static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own,
-                                const uint16_t* dout_own, const float* lse_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls,
-                                int H, float scale, cudaStream_t stream) {
+                                const uint16_t* dout_own, const float* lse_own, float* delta_own, uint16_t* dqkv_own, int Bp,
+                                int Lc, int Ls, int H, float scale, cudaStream_t stream) {
   using Cfg = AttnTcBwdCfg<HD>;
   auto kern = attn_bwd_tc_kernel<HD>;
   static bool attr_done = false;
@@ -951,6 +954,7 @@ static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const floa
   p.lse_own = lse_own;
   p.rope_cos = rc; p.rope_sin = rs;
   p.dqkv_own = reinterpret_cast<__nv_bfloat16*>(dqkv_own);
+  p.delta_own = delta_own;
   p.Bp = Bp; p.Lc = Lc; p.Ls = Ls; p.H = H; p.D = H * HD;
   p.na64 = (Lc + 63) & ~63;
   p.Lsp = (Ls + 15) & ~15;
@@ -982,10 +986,11 @@ static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const floa
 }
 
 int launch_attn_bwd_tc(const uint16_t* qkv, const float* rc, const float* rs, const uint16_t* out_own, const uint16_t* dout_own,
-                       const float* lse_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd, float scale,
-                       cudaStream_t stream) {
-  if (hd == 128) return launch_attn_bwd_tc_t<128>(qkv, rc, rs, out_own, dout_own, lse_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
-  return launch_attn_bwd_tc_t<64>(qkv, rc, rs, out_own, dout_own, lse_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
+                       const float* lse_own, float* delta_own, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
+                       float scale, cudaStream_t stream) {
+  if (hd == 128)
+    return launch_attn_bwd_tc_t<128>(qkv, rc, rs, out_own, dout_own, lse_own, delta_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
+  return launch_attn_bwd_tc_t<64>(qkv, rc, rs, out_own, dout_own, lse_own, delta_own, dqkv_own, Bp, Lc, Ls, H, scale, stream);
 }
 
 }  // namespace mts

@@ -389,6 +389,18 @@ def test_attn_tensor_memory_backward(ops, cuda, Bp, Lc, Ls, H, hd, rope):
         e_ref, e_old = _rel_l2(got[:, sl], ref[:, sl]), _rel_l2(got[:, sl], old[:, sl])
         assert e_ref < 1.5e-2, (name, e_ref)        # bf16 P / dS / outputs
         assert e_old < 1.5e-2, (name, e_old)
+    # full backward (LoRA: the prefix rows' gradients too): own rows from the tensor-memory kernel, which leaves delta
+    # behind for the prefix-key kernels; against the all-mma.sync path
+    dout_all = torch.cat([torch.randn(Lc, D, generator=g).to(cuda, torch.bfloat16), dout])
+    _lib.set_option("attn_tc", 2)
+    try:
+        full_tc = ops.attn_causal_shared_bwd_full(qkv, out, dout_all, lse_full, Bp, Lc, Ls, H, hd, rope=tabs)
+        _lib.set_option("attn_tc", 0)
+        full_old = ops.attn_causal_shared_bwd_full(qkv, out, dout_all, lse_full, Bp, Lc, Ls, H, hd, rope=tabs)
+    finally:
+        _lib.set_option("attn_tc", 1)
+    assert torch.equal(full_tc[Lc:], got)                       # same own-row kernel, same inputs
+    assert _rel_l2(full_tc[:Lc], full_old[:Lc]) < 1e-5          # prefix rows: same kernels fed the new delta
 
 
 # ------------------------------------------------------------------------------- training-path kernels
