@@ -48,7 +48,9 @@ struct GemmParams {
   int precise;     // fp32 operands (evaluation parity modes): accurate expf / tanhf in the activation epilogues
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
+  long long* dbg;  // MTS_GEMM_DBG=1 (single-CTA kernel): clock64 stamps of block 0, printed by the launcher (debug)
 };
+#define GEMM_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ float gelu_new_f(float x) {
   // HF:activations.py:65-66  0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))

@@ -83,6 +83,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_a_lo,
                     const __grid_constant__ CUtensorMap tmap_b_lo) {
   using Cfg = GemmCfg<BN>;
+  if (threadIdx.x == 0) GEMM_STAMP(0);
   constexpr int kStages = Cfg::kStages;
   constexpr int kBK = TF32 ? kBlockK / 2 : kBlockK;   // elements per 128-byte smem row
   // p.split3 (TF32 only): fp32-grade contraction from TF32 pieces, A = A_hi + A_lo, B = B_hi + B_lo (each piece
@@ -138,10 +139,12 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) GEMM_STAMP(1);
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are
   // needed from here on.  The successor may be scheduled as soon as every CTA of this grid got this far.
   pdl_wait();
   pdl_trigger();
+  if (threadIdx.x == 0) GEMM_STAMP(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -165,6 +168,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         m_blk * kBlockM, p.a_batched ? b : 0, kEvictNormal);
             tma_load_3d(smem_b + stage * Cfg::kBBytes, mb, full_bar(stage), kb * kBK,
                         n_blk * BN, p.b_batched ? b : 0, kEvictNormal);
+            if (kb == kb0 && seg == 0) GEMM_STAMP(3);
+            if (kb == kb1 - 1) GEMM_STAMP(9);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -189,6 +194,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
+          if (kb == 0) GEMM_STAMP(4);
           const uint64_t adesc = umma_desc_sw128(smem_a + stage * Cfg::kABytes);
           const uint64_t bdesc = umma_desc_sw128(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
@@ -201,6 +207,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        GEMM_STAMP(5);
       }
     }
   } else {
@@ -222,6 +229,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
+      if (threadIdx.x == 64) GEMM_STAMP(6);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
       bool run_epilogue = true;
       if (p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
@@ -296,6 +304,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+      if (threadIdx.x == 64) GEMM_STAMP(7);
     }
   }
 
@@ -305,6 +314,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 0) GEMM_STAMP(8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -328,10 +338,29 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   // stream-K: one CTA per SM, each takes an equal share of the (tile, k-block) units
   const int grid = p.streamk ? num_sms() : (num_tiles < num_sms() ? num_tiles : num_sms());
-  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p,
+  static int dbg_on = -1;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on < 0) { const char* e = getenv("MTS_GEMM_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+  GemmParams pp = p;
+  pp.dbg = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
+    pp.dbg = dbg_buf;
+  }
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, pp,
                               (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
   if (le != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_kernel)", le);
   count_launch();
+  if (dbg_on) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gemm dbg] m=%d n=%d k=%d BN=%d epi=%d tiles=%d grid=%d: setup done=%lld pdl passed=%lld first TMA issued=%lld "
+            "last TMA issued=%lld first stage landed=%lld MMAs issued=%lld accumulator seen=%lld epilogue done=%lld end=%lld\n",
+            p.m, p.n, p.k, BN, EPI, num_tiles, grid, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[9] - h[0], h[4] - h[0], h[5] - h[0],
+            h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+  }
   return check_launch("gemm_bf16_nt_kernel");
 }
 
@@ -515,6 +544,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   if (rc) return rc;
 
   GemmParams p;
+  p.dbg = nullptr;
   p.d = a->d;
   p.bias = a->bias;
   p.ldd = a->ldd;
