@@ -35,6 +35,9 @@ class BackboneSpec:
     eps: float
     rope_theta: float = 10000.0
     max_pos: int = 4096
+    kv_heads: int = 0    # grouped-query checkpoints: K / V heads of the checkpoint (0 = heads).  The kernels see `heads` K / V
+                         # heads: from_hf repeats each K / V head's projection rows heads / kv_heads times, which is exactly
+                         # HuggingFace's repeat_kv (HF:models/llama/modeling_llama.py:186-196) folded into the weights
 
     @property
     def head_dim(self):
@@ -44,15 +47,16 @@ class BackboneSpec:
 def spec_from_hf_config(cfg) -> BackboneSpec:
     mt = cfg.model_type
     if mt == "llama":
-        if getattr(cfg, "num_key_value_heads", cfg.num_attention_heads) != cfg.num_attention_heads:
-            raise MtsError("grouped-query attention is not supported (Llama-2-7B has 32 KV heads)")
+        kv = getattr(cfg, "num_key_value_heads", None) or cfg.num_attention_heads
+        if cfg.num_attention_heads % kv or getattr(cfg, "head_dim", None) not in (None, cfg.hidden_size // cfg.num_attention_heads):
+            raise MtsError("unsupported attention geometry (K / V heads must divide the heads, head_dim = hidden / heads)")
         rp = getattr(cfg, "rope_parameters", None) or {}
         theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
         if rp.get("rope_type", "default") != "default":
             raise MtsError(f"rope_type {rp.get('rope_type')} is not supported")
         return BackboneSpec("llama", cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
                             cfg.intermediate_size, cfg.vocab_size, cfg.rms_norm_eps, theta,
-                            cfg.max_position_embeddings)
+                            cfg.max_position_embeddings, kv_heads=0 if kv == cfg.num_attention_heads else kv)
     if mt == "gpt2":
         inner = cfg.n_inner if cfg.n_inner is not None else 4 * cfg.n_embd
         if cfg.activation_function != "gelu_new":
@@ -208,11 +212,15 @@ class KernelBackbone:
         self = cls(spec, device, precision=precision)
         sd = hf_model.state_dict()
         if spec.kind == "llama":
+            hd, rep = spec.head_dim, (spec.heads // spec.kv_heads if spec.kv_heads else 1)
+
+            def kv_rows(w):       # [kv_heads*hd, D] -> [heads*hd, D]: query head h reads K / V head h // rep
+                return w if rep == 1 else w.view(-1, hd, w.shape[1]).repeat_interleave(rep, dim=0).reshape(-1, w.shape[1])
             for i in range(spec.layers):
                 p = f"layers.{i}."
                 self._add_llama_layer(
-                    sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
-                    sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.o_proj.weight"],
+                    sd[p + "self_attn.q_proj.weight"], kv_rows(sd[p + "self_attn.k_proj.weight"]),
+                    kv_rows(sd[p + "self_attn.v_proj.weight"]), sd[p + "self_attn.o_proj.weight"],
                     sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"],
                     sd[p + "mlp.down_proj.weight"], sd[p + "input_layernorm.weight"],
                     sd[p + "post_attention_layernorm.weight"])

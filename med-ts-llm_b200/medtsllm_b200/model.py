@@ -310,6 +310,9 @@ class MedTsLLM(nn.Module):
                                       "models/medtsllm.py:219-222) are outside the BASELINE configs")
         if self.lora_enabled:
             from .lora import LoraAdapters
+            if spec.kv_heads:
+                raise NotImplementedError("LoRA on a grouped-query backbone (v_proj is narrower than the kernel's expanded "
+                                          "K / V projection) is outside the BASELINE configs")
             init = _get(lora, "init", True)
             if init not in (True, False):
                 raise NotImplementedError(f"lora.init = {init!r}")

@@ -803,3 +803,24 @@ def test_training_step_graphs_match_kernel_by_kernel(name, lora, tmp_path, cuda)
     m1(base)
     with pytest.raises(MtsError):
         ya.sum().backward()
+
+
+def test_grouped_query_backbone_matches_live_hf(cuda):
+    """Grouped-query checkpoints (fewer K / V heads than query heads): from_hf folds HuggingFace's repeat_kv
+    (HF:models/llama/modeling_llama.py:186-196) into the K / V projection weights; the kernels run unchanged.  Against the
+    live HuggingFace model in fp32 on the same GPU."""
+    from transformers import LlamaConfig, LlamaModel
+    from medtsllm_b200.backbone import KernelBackbone
+    torch.manual_seed(11)
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                      vocab_size=128, rms_norm_eps=1e-5, max_position_embeddings=256, attn_implementation="eager")
+    hf = LlamaModel(cfg).eval()
+    bb = KernelBackbone.from_hf(hf, cuda)
+    assert bb.spec.kv_heads == 2 and bb.spec.heads == 4
+    Bp, L = 3, 40
+    x = torch.randn(Bp, L, 256) * 0.5
+    with torch.no_grad():
+        ref = hf.to(cuda)(inputs_embeds=x.to(cuda)).last_hidden_state
+    out, _ = bb.forward(x.view(Bp * L, 256).to(cuda).clone(), Bp, L)
+    err = ((out.float().view(Bp, L, 256) - ref).norm() / ref.norm()).item()
+    assert err < 2e-2, err                                  # bf16 operands, two layers
