@@ -296,12 +296,18 @@ int mts_rope_qk(uint16_t* qkv, const float* rope_cos, const float* rope_sin, int
  * mts_gemm_args.rope_prefix); only attention needs to know about it:
  *   qkv bf16 [Lc + Bp*Ls, 3*H*hd] with q / k ALREADY rotated (MTS_EPI_ROPE_QK or mts_rope_qk_shared);
  *   out bf16 [Lc + Bp*Ls, H*hd];  lse fp32 [H*Lc + Bp*H*Ls] (prefix [H, Lc] first, then [Bp, H, Ls]) or NULL.
- * All Lc + Ls positions of one head must fit in shared memory (<= ~350 positions at hd 128, ~700 at hd 64). */
+ * Up to 256 positions the forward runs on tcgen05 with the score tile in tensor memory (csrc/attention_tc.cu, see
+ * mts_attn_causal); beyond that all Lc + Ls positions of one head must fit in shared memory (<= ~350 positions at hd 128,
+ * ~700 at hd 64) for the mma.sync kernels. */
 int mts_attn_causal_shared(const uint16_t* qkv, uint16_t* out, float* lse, int Bp, int Lc, int Ls, int H,
                            int hd, float scale, mts_stream_t stream);
 /* Backward for the samples' own tokens only (the prefix has no trainable ancestor when the backbone is frozen):
  * qkv as above (all rows); out_own / dout_own bf16 [Bp*Ls, H*hd], lse_own / delta fp32 [Bp, H, Ls],
- * dqkv_own bf16 [Bp*Ls, 3*H*hd] = the rows from Lc on.  rope tables fp32 [>= Lc+Ls, hd/2] (rotate dq/dk back) or NULL. */
+ * dqkv_own bf16 [Bp*Ls, 3*H*hd] = the rows from Lc on.  rope tables fp32 [>= Lc+Ls, hd/2] (rotate dq/dk back) or NULL.
+ * Lc <= 128, Ls <= 128 (prefix rounded up to 64 + own rows rounded up to 16 <= 256 key columns): one tcgen05 kernel —
+ * S = Q K^T and dP = dO V^T in tensor memory, dS / P to swizzled shared memory, dQ = dS K, dV = P^T dO, dK = dS^T Q with the
+ * operands consumed in place (MN-major descriptors) — unless mts_set_option("attn_tc", 0); `delta` is then only written
+ * when the full backward below asks for it. */
 int mts_attn_causal_shared_bwd(const uint16_t* qkv, const float* rope_cos, const float* rope_sin,
                                const uint16_t* out_own, const uint16_t* dout_own, const float* lse_own,
                                float* delta, uint16_t* dqkv_own, int Bp, int Lc, int Ls, int H, int hd,
