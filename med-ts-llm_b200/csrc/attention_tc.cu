@@ -125,6 +125,41 @@ __device__ __forceinline__ uint32_t chunk_mask(int c0, int n_prefix, int lo, int
   return m;
 }
 
+// K / V rows [grow, grow + n) (n a multiple of 16) of one 64-column block -> shared-memory rows [srow, srow + n) of a slab, in
+// as few TMA operations as the three box heights allow (a TMA instruction costs the issuing thread ~120 cycles whatever
+// its size: 16-row boxes alone made the producer the slowest role of the backward).
+__device__ __forceinline__ void tma_load_rows(uint32_t slab, const CUtensorMap* m128, const CUtensorMap* m64,
+                                              const CUtensorMap* m16, uint32_t bar, int col, int srow, int grow, int n,
+                                              uint64_t policy) {
+  int r = 0;
+  for (; r + 128 <= n; r += 128) tma_load_3d(slab + (srow + r) * 128, m128, bar, col, grow + r, 0, policy);
+  for (; r + 64 <= n; r += 64) tma_load_3d(slab + (srow + r) * 128, m64, bar, col, grow + r, 0, policy);
+  for (; r < n; r += 16) tma_load_3d(slab + (srow + r) * 128, m16, bar, col, grow + r, 0, policy);
+}
+
+// The same boxes as an L2 prefetch (no shared-memory destination, no barrier): issued for the NEXT job while the current one
+// computes, so that its loads — which can only start when the current job's MMAs release the tiles — hit L2 instead of HBM.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_rows(const CUtensorMap* m128, const CUtensorMap* m64, const CUtensorMap* m16,
+                                                  int col, int grow, int n) {
+  int r = 0;
+  for (; r + 128 <= n; r += 128) tma_prefetch_3d(m128, col, grow + r, 0);
+  for (; r + 64 <= n; r += 64) tma_prefetch_3d(m64, col, grow + r, 0);
+  for (; r < n; r += 16) tma_prefetch_3d(m16, col, grow + r, 0);
+}
+
+// 32-byte global store (STG.256): one full sector per lane
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4),
+               "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 // MN-major, 128B-swizzled shared-memory matrix descriptor: rows of the K dimension (keys) are 128 bytes (64 bf16 of the
 // MN dimension) apart, 8-row groups 1024 bytes (SBO), the next 64 elements of the MN dimension `lbo` bytes further.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
@@ -149,7 +184,7 @@ struct AttnTcCfg {
 template <int HD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                   const AttnTcParams p) {
+                   const __grid_constant__ CUtensorMap tmap_kv64, const AttnTcParams p) {
   using Cfg = AttnTcCfg<HD>;
   constexpr int KB = Cfg::KB;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -166,7 +201,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_empty, 128);
     fence_mbar_init();
   }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); }
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); tma_prefetch_desc(&tmap_kv64); }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -197,11 +232,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t dst = slab + kb * Cfg::kSlabKV;
             const int col = col0 + col_h + kb * 64;
-            if (!reuse)
-              for (int r = 0; r < jb.na16; r += 16) tma_load_3d(dst + r * 128, &tmap_kv, full, col, r, 0, kEvictLast);
+            if (!reuse) tma_load_rows(dst, &tmap_q, &tmap_kv64, &tmap_kv, full, col, 0, 0, jb.na16, kEvictLast);
             for (int s = 0; s < jb.nseg; ++s)
-              for (int r = 0; r < jb.Lsp; r += 16)
-                tma_load_3d(dst + (jb.na16 + s * jb.Lsp + r) * 128, &tmap_kv, full, col, seg_row0 + s * jb.Ls + r, 0,
+              tma_load_rows(dst, &tmap_q, &tmap_kv64, &tmap_kv, full, col, jb.na16 + s * jb.Lsp, seg_row0 + s * jb.Ls, jb.Lsp,
                             kEvictNormal);
           }
         };
@@ -405,12 +438,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int ci = 0; ci < HD / 32; ++ci) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(orow + ci * 32 + 8 * g) = make_uint4(
-                pack_bf16(__uint_as_float(v[ci][8 * g]) * inv, __uint_as_float(v[ci][8 * g + 1]) * inv),
-                pack_bf16(__uint_as_float(v[ci][8 * g + 2]) * inv, __uint_as_float(v[ci][8 * g + 3]) * inv),
-                pack_bf16(__uint_as_float(v[ci][8 * g + 4]) * inv, __uint_as_float(v[ci][8 * g + 5]) * inv),
-                pack_bf16(__uint_as_float(v[ci][8 * g + 6]) * inv, __uint_as_float(v[ci][8 * g + 7]) * inv));
+          for (int g = 0; g < 2; ++g) {         // 16 bf16 = one full 32-byte sector per store
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              w[q] = pack_bf16(__uint_as_float(v[ci][16 * g + 2 * q]) * inv, __uint_as_float(v[ci][16 * g + 2 * q + 1]) * inv);
+            st_global_v8(orow + ci * 32 + 16 * g, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+          }
         }
       }
       if (lse_ptr != nullptr) *lse_ptr = (m_sc + log2f(l)) * 0.6931471805599453f;
@@ -456,6 +490,7 @@ struct AttnTcBwdParams {
   int spj, groups, n_jobs;
   int na64, Lsp;                     // first own-key column (Lc rounded up to 64), column segment per sample
   float scale, scale_log2e;
+  long long* dbg;                    // MTS_ATTN_TC_DBG=1: clock64 stamps of block 0, second job (debug)
 };
 
 template <int HD>
@@ -478,7 +513,8 @@ constexpr int kTcBwdThreads = 320;     // warps 0-7 compute (quarter = warp % 4,
 template <int HD>
 __global__ void __launch_bounds__(kTcBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                   const __grid_constant__ CUtensorMap tmap_do, const AttnTcBwdParams p) {
+                   const __grid_constant__ CUtensorMap tmap_kv64, const __grid_constant__ CUtensorMap tmap_do,
+                   const AttnTcBwdParams p) {
   using Cfg = AttnTcBwdCfg<HD>;
   constexpr int KB = Cfg::KB;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -496,7 +532,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(g_full, 1); mbar_init(epi_done, 256);
     fence_mbar_init();
   }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); tma_prefetch_desc(&tmap_do); }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_do);
+  }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -527,6 +565,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // tensor core multiplies them by the zeros of P / dS, so they must hold finite data, not stale shared memory
         const int k_boxes = (reuse ? 0 : (p.na64 >> 4)) + seg_boxes, v_boxes = (reuse_v ? 0 : (p.na64 >> 4)) + seg_boxes;
         mbar_wait(smem_free, ph ^ 1u, 600);                           // the previous job's dQ / dV / dK MMAs have retired
+        if (job == j_begin + 1) TC_STAMP(1);
         mbar_arrive_expect_tx(ld_full, KB * (2 * Cfg::kSlabQ + (k_boxes + v_boxes) * 2048));
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -541,15 +580,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t dst = slab + kb * Cfg::kSlabKV;
             const int col = (which + 1) * p.D + col_h + kb * 64;
-            if (!skip_prefix)
-              for (int r = 0; r < p.na64; r += 16) tma_load_3d(dst + r * 128, &tmap_kv, ld_full, col, r, 0, kEvictLast);
+            if (!skip_prefix) tma_load_rows(dst, &tmap_q, &tmap_kv64, &tmap_kv, ld_full, col, 0, 0, p.na64, kEvictLast);
             for (int s = 0; s < nseg; ++s)
-              for (int r = 0; r < p.Lsp; r += 16)
-                tma_load_3d(dst + (p.na64 + s * p.Lsp + r) * 128, &tmap_kv, ld_full, col, p.Lc + own_row0 + s * p.Ls + r, 0,
-                            kEvictNormal);
+              tma_load_rows(dst, &tmap_q, &tmap_kv64, &tmap_kv, ld_full, col, p.na64 + s * p.Lsp, p.Lc + own_row0 + s * p.Ls,
+                            p.Lsp, kEvictNormal);
           }
         }
+        if (job == j_begin + 1) TC_STAMP(2);
         res_head = head;
+        if (job + 1 < j_end) {              // next job's Q / dO / own K / own V (and its prefix when the head changes) -> L2
+          const int nh = job_head(job + 1), nb0 = (job + 1 - nh * p.groups) * p.spj;
+          const int nns = min(p.spj, p.Bp - nb0), nrow0 = nb0 * p.Ls, ncol = nh * HD;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_prefetch_3d(&tmap_q, ncol + kb * 64, p.Lc + nrow0, 0);
+            tma_prefetch_3d(&tmap_do, ncol + kb * 64, nrow0, 0);
+#pragma unroll
+            for (int which = 1; which <= 2; ++which) {
+              const int col = which * p.D + ncol + kb * 64;
+              if (nh != head) tma_prefetch_rows(&tmap_q, &tmap_kv64, &tmap_kv, col, 0, p.na64);
+              for (int s = 0; s < nns; ++s)
+                tma_prefetch_rows(&tmap_q, &tmap_kv64, &tmap_kv, col, p.Lc + nrow0 + s * p.Ls, p.Lsp);
+            }
+          }
+        }
       }
     }
   } else if (warp == 9) {
@@ -565,8 +619,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int nk = p.na64 + nseg * p.Lsp;                         // key columns (multiple of 16, <= 256)
         const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk);
         mbar_wait(ld_full, ph, 610);
+        if (job == j_begin + 1) TC_STAMP(3);
         mbar_wait(epi_done, ph ^ 1u, 611);                            // the previous job's gradients have left TMEM
         tc_fence_after();
+        if (job == j_begin + 1) TC_STAMP(4);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t aq = umma_desc_sw128(sQ + kb * Cfg::kSlabQ), bk = umma_desc_sw128(sK + kb * Cfg::kSlabKV);
@@ -580,8 +636,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int k = 0; k < 4; ++k) umma_bf16(tdP, ao + 2u * k, bv + 2u * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(s_full);
+        if (job == j_begin + 1) TC_STAMP(5);
         mbar_wait(ds_full, ph, 612);                                  // P / dS are in shared memory, S / dP are consumed
         tc_fence_after();
+        if (job == j_begin + 1) TC_STAMP(6);
         for (int ks = 0; ks < (nk >> 4); ++ks)                        // dQ = dS K
           umma_bf16(tdQ, umma_desc_sw128(sdS + (ks >> 2) * Cfg::kSlab) + 2u * (ks & 3),
                     umma_desc_mn_sw128(sK + ks * 2048, Cfg::kSlabKV), idesc_dq, ks != 0 ? 1u : 0u);
@@ -595,6 +653,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         umma_commit(smem_free);
         umma_commit(g_full);
+        if (job == j_begin + 1) TC_STAMP(7);
       }
     }
   } else {
@@ -632,9 +691,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       uint32_t vmask = 0;                         // 32-column chunks in which some row of this quarter sees a key
       for (int c0 = 0, k = 0; c0 < nk; c0 += 32, ++k)
         if (c0 < p.Lc || __any_sync(0xffffffffu, c0 <= own_hi && c0 + 31 >= own_lo)) vmask |= 1u << k;
+      if (job == j_begin && threadIdx.x == 0) TC_STAMP(0);
+      if (job == j_begin + 1 && threadIdx.x == 0) TC_STAMP(8);
       if (lane == 0) mbar_wait(s_full, ph, 620);  // implies ld_full: Q / K / V / dO are in shared memory
       __syncwarp();
       tc_fence_after();
+      if (job == j_begin + 1 && threadIdx.x == 0) TC_STAMP(9);
       // delta = rowsum(dO o O): dO from its swizzled tile (16-byte chunk q of row r sits at q ^ (r & 7))
       float delta = 0.0f;
 #pragma unroll
@@ -703,6 +765,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_full);
+      if (job == j_begin + 1 && lane == 0) TC_STAMP(16 + warp);
 
       // ---- phase 2 role: lane r = query row for dQ, own key index for dV / dK
       const int ms = m_div, mj = r - ms * p.Lsp;                       // own key r: sample ms of the job, token mj
@@ -738,6 +801,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (lane == 0) mbar_wait(g_full, ph, 621);
       __syncwarp();
       tc_fence_after();
+      if (job == j_begin + 1 && threadIdx.x == 0) TC_STAMP(10);
       // a (lo, hi) chunk pair of a rotated gradient: rotate back with the loaded table rows and store;
       // lo chunk c holds columns [32c, 32c + 32)
       auto store_pair = [&](uint32_t tcol, __nv_bfloat16* dst, bool valid) {
@@ -759,13 +823,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(lo[j]); b[j] = __uint_as_float(hi[j]); }
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          *reinterpret_cast<uint4*>(dst + 32 * c_pair + 8 * g) =
-              make_uint4(pack_bf16(a[8 * g], a[8 * g + 1]), pack_bf16(a[8 * g + 2], a[8 * g + 3]),
-                         pack_bf16(a[8 * g + 4], a[8 * g + 5]), pack_bf16(a[8 * g + 6], a[8 * g + 7]));
-          *reinterpret_cast<uint4*>(dst + 32 * (c_pair + kHalfChunks) + 8 * g) =
-              make_uint4(pack_bf16(b[8 * g], b[8 * g + 1]), pack_bf16(b[8 * g + 2], b[8 * g + 3]),
-                         pack_bf16(b[8 * g + 4], b[8 * g + 5]), pack_bf16(b[8 * g + 6], b[8 * g + 7]));
+        for (int g = 0; g < 2; ++g) {           // 32-byte stores: one full sector per lane
+          st_global_v8(dst + 32 * c_pair + 16 * g, pack_bf16(a[16 * g], a[16 * g + 1]), pack_bf16(a[16 * g + 2], a[16 * g + 3]),
+                       pack_bf16(a[16 * g + 4], a[16 * g + 5]), pack_bf16(a[16 * g + 6], a[16 * g + 7]),
+                       pack_bf16(a[16 * g + 8], a[16 * g + 9]), pack_bf16(a[16 * g + 10], a[16 * g + 11]),
+                       pack_bf16(a[16 * g + 12], a[16 * g + 13]), pack_bf16(a[16 * g + 14], a[16 * g + 15]));
+          st_global_v8(dst + 32 * (c_pair + kHalfChunks) + 16 * g, pack_bf16(b[16 * g], b[16 * g + 1]),
+                       pack_bf16(b[16 * g + 2], b[16 * g + 3]), pack_bf16(b[16 * g + 4], b[16 * g + 5]),
+                       pack_bf16(b[16 * g + 6], b[16 * g + 7]), pack_bf16(b[16 * g + 8], b[16 * g + 9]),
+                       pack_bf16(b[16 * g + 10], b[16 * g + 11]), pack_bf16(b[16 * g + 12], b[16 * g + 13]),
+                       pack_bf16(b[16 * g + 14], b[16 * g + 15]));
         }
       };
       if constexpr (HD == 128) {
@@ -780,19 +847,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           tmem_ld_32x32(tq + 128 + 64 * half + 32, v1);
           tmem_ld_wait();
           if (key_valid) {
+            auto store32 = [&](__nv_bfloat16* dst, const uint32_t (&v)[32]) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              *reinterpret_cast<uint4*>(dv_dst + 64 * half + 8 * g) = make_uint4(
-                  pack_bf16(__uint_as_float(v0[8 * g]), __uint_as_float(v0[8 * g + 1])),
-                  pack_bf16(__uint_as_float(v0[8 * g + 2]), __uint_as_float(v0[8 * g + 3])),
-                  pack_bf16(__uint_as_float(v0[8 * g + 4]), __uint_as_float(v0[8 * g + 5])),
-                  pack_bf16(__uint_as_float(v0[8 * g + 6]), __uint_as_float(v0[8 * g + 7])));
-              *reinterpret_cast<uint4*>(dv_dst + 64 * half + 32 + 8 * g) = make_uint4(
-                  pack_bf16(__uint_as_float(v1[8 * g]), __uint_as_float(v1[8 * g + 1])),
-                  pack_bf16(__uint_as_float(v1[8 * g + 2]), __uint_as_float(v1[8 * g + 3])),
-                  pack_bf16(__uint_as_float(v1[8 * g + 4]), __uint_as_float(v1[8 * g + 5])),
-                  pack_bf16(__uint_as_float(v1[8 * g + 6]), __uint_as_float(v1[8 * g + 7])));
-            }
+              for (int g = 0; g < 2; ++g) {
+                uint32_t w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  w[q] = pack_bf16(__uint_as_float(v[16 * g + 2 * q]), __uint_as_float(v[16 * g + 2 * q + 1]));
+                st_global_v8(dst + 16 * g, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+              }
+            };
+            store32(dv_dst + 64 * half, v0);
+            store32(dv_dst + 64 * half + 32, v1);
           }
         }
       } else {
@@ -804,16 +870,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tmem_ld_wait();
         if (key_valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(dv_dst + 32 * half + 8 * g) = make_uint4(
-                pack_bf16(__uint_as_float(v0[8 * g]), __uint_as_float(v0[8 * g + 1])),
-                pack_bf16(__uint_as_float(v0[8 * g + 2]), __uint_as_float(v0[8 * g + 3])),
-                pack_bf16(__uint_as_float(v0[8 * g + 4]), __uint_as_float(v0[8 * g + 5])),
-                pack_bf16(__uint_as_float(v0[8 * g + 6]), __uint_as_float(v0[8 * g + 7])));
+          for (int g = 0; g < 2; ++g) {
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              w[q] = pack_bf16(__uint_as_float(v0[16 * g + 2 * q]), __uint_as_float(v0[16 * g + 2 * q + 1]));
+            st_global_v8(dv_dst + 32 * half + 16 * g, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(epi_done);
+      if (job == j_begin + 1 && lane == 0) TC_STAMP(24 + warp);
     }
   }
 
@@ -888,10 +956,12 @@ static int launch_attn_tc_t(const uint16_t* qkv, uint16_t* out, float* lse, int 
   p.n_jobs = (int)n_jobs;
   p.scale_log2e = scale * 1.4426950408889634f;
   const int64_t rows = (int64_t)Lc + (int64_t)Bp * p.Ls;
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tkv64;
   int rc = get_tmap_3d(&tq, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 128, 2);
   if (rc) return rc;
   rc = get_tmap_3d(&tkv, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 16, 2);
+  if (rc) return rc;
+  rc = get_tmap_3d(&tkv64, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 64, 2);
   if (rc) return rc;
   const int grid = p.n_jobs < num_sms() ? p.n_jobs : num_sms();
   static long long* dbg_buf = nullptr;
@@ -903,7 +973,7 @@ static int launch_attn_tc_t(const uint16_t* qkv, uint16_t* out, float* lse, int 
     cudaMemsetAsync(dbg_buf, 0, 24 * sizeof(long long), stream);
     p.dbg = dbg_buf;
   }
-  LAUNCH_PDL(kern, grid, kTcThreads, Cfg::kSmemBytes, stream, tq, tkv, p);
+  LAUNCH_PDL(kern, grid, kTcThreads, Cfg::kSmemBytes, stream, tq, tkv, tkv64, p);
   count_launch();
   if (dbg_on) {
     long long h[24];
@@ -972,16 +1042,39 @@ static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const floa
   p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
   const int64_t rows = (int64_t)Lc + (int64_t)Bp * Ls, own_rows = (int64_t)Bp * Ls;
-  CUtensorMap tq, tkv, tdo;
+  CUtensorMap tq, tkv, tkv64, tdo;
   int rc_ = get_tmap_3d(&tq, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 128, 2);
   if (rc_) return rc_;
   rc_ = get_tmap_3d(&tkv, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 16, 2);
   if (rc_) return rc_;
+  rc_ = get_tmap_3d(&tkv64, qkv, 3 * (int64_t)p.D, rows, 1, 3 * (int64_t)p.D, rows * 3 * p.D, 64, 64, 2);
+  if (rc_) return rc_;
   rc_ = get_tmap_3d(&tdo, dout_own, (int64_t)p.D, own_rows, 1, (int64_t)p.D, own_rows * p.D, 64, 128, 2);
   if (rc_) return rc_;
   const int grid = p.n_jobs < num_sms() ? p.n_jobs : num_sms();
-  LAUNCH_PDL(kern, grid, kTcBwdThreads, Cfg::kSmemBytes, stream, tq, tkv, tdo, p);
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* e = getenv("MTS_ATTN_TC_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+  p.dbg = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 32 * sizeof(long long), stream);
+    p.dbg = dbg_buf;
+  }
+  LAUNCH_PDL(kern, grid, kTcBwdThreads, Cfg::kSmemBytes, stream, tq, tkv, tkv64, tdo, p);
   count_launch();
+  if (dbg_on) {
+    long long h[32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* names[11] = {"", "producer: smem free", "loads issued", "MMA: operands landed", "TMEM free", "S + dP issued",
+                                    "dS seen", "dQ dV dK issued", "compute: waits for S", "S seen", "gradients seen"};
+    fprintf(stderr, "[attn_bwd_tc dbg] jobs=%d grid=%d spj=%d, second job of block 0 (cycles since its first job's S wait):", p.n_jobs, grid, p.spj);
+    for (int i = 1; i < 11; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
+    for (int i = 16; i < 24; ++i) fprintf(stderr, " dS of warp %d=%lld", i - 16, h[i] ? h[i] - h[0] : -1);
+    for (int i = 24; i < 32; ++i) fprintf(stderr, " done warp %d=%lld", i - 24, h[i] ? h[i] - h[0] : -1);
+    fprintf(stderr, "\n");
+  }
   return check_launch("attn_bwd_tc_kernel");
 }
 

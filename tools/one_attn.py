@@ -16,5 +16,10 @@ dev = torch.device("cuda", 0)
 qkv = (torch.randn(Lc + Bp * Ls, 3 * H * hd, device=dev) * 0.5).to(torch.bfloat16)
 for _ in range(4):
     out, lse = ops.attn_causal_shared(qkv, Bp, Lc, Ls, H, hd, want_lse=True)
+if "--bwd" in sys.argv:
+    dout = (torch.randn(Bp * Ls, H * hd, device=dev) * 0.5).to(torch.bfloat16)
+    lse_own = ops.lse_own_view(lse, Bp, Lc, Ls, H)
+    for _ in range(3):
+        ops.attn_causal_shared_bwd(qkv, out[Lc:], dout, lse_own, Bp, Lc, Ls, H, hd)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))
