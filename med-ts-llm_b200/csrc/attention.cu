@@ -1574,21 +1574,21 @@ static int launch_attn_shared_bwd(const uint16_t* qkv, const float* rc, const fl
   // so the fused kernel — which keeps delta in shared memory only — cannot be used
   const int L = Lc + Ls;
   const int D = H * HD;
-  // tensor-memory kernel (attention_tc.cu); it leaves delta of the own rows behind when the full backward needs it
-  if (attn_tc_bwd_eligible(Lc, Ls, HD, Bp, H, rc, rs))
-    return launch_attn_bwd_tc(qkv, rc, rs, out_own, dout_own, lse_own, delta_needed_later ? delta : nullptr, dqkv_own, Bp, Lc,
-                              Ls, H, HD, scale, stream);
-  if (seq_bwd_smem_bytes<HD>(L) > 220 * 1024)
-    return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd: %d positions do not fit in shared memory", L);
   auto sq = attn_bwd_dq_seq_kernel<HD>;
   auto skv = attn_bwd_dkv_seq_kernel<HD>;
-  static bool seq_attr = false;
+  static bool seq_attr = false;      // (first: the full backward launches these kernels for the prefix rows whatever route the own rows take)
   if (!seq_attr) {
     cudaError_t e = cudaFuncSetAttribute(sq, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(skv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn bwd seq)", e);
     seq_attr = true;
   }
+  // tensor-memory kernel (attention_tc.cu); it leaves delta of the own rows behind when the full backward needs it
+  if (attn_tc_bwd_eligible(Lc, Ls, HD, Bp, H, rc, rs))
+    return launch_attn_bwd_tc(qkv, rc, rs, out_own, dout_own, lse_own, delta_needed_later ? delta : nullptr, dqkv_own, Bp, Lc,
+                              Ls, H, HD, scale, stream);
+  if (seq_bwd_smem_bytes<HD>(L) > 220 * 1024)
+    return set_error(MTS_ERR_UNSUPPORTED, "mts_attn_causal_shared_bwd: %d positions do not fit in shared memory", L);
   // everything of one CTA's samples resident at once?  then one fused kernel does delta, dQ and dK/dV
   if (!delta_needed_later && fused_bwd_enabled() && fused_bwd_smem_bytes<HD>(L, Lc, 1) <= 220 * 1024) {
     int spc = 1;

@@ -4,6 +4,7 @@ PyTorch fp32 reference of the same op on identical inputs.  Tolerances are state
 Integer/index work (patch gather) is compared bit-exactly.
 """
 import math
+from pathlib import Path
 
 import pytest
 import torch
@@ -401,6 +402,27 @@ def test_attn_tensor_memory_backward(ops, cuda, Bp, Lc, Ls, H, hd, rope):
         _lib.set_option("attn_tc", 1)
     assert torch.equal(full_tc[Lc:], got)                       # same own-row kernel, same inputs
     assert _rel_l2(full_tc[:Lc], full_old[:Lc]) < 1e-5          # prefix rows: same kernels fed the new delta
+
+
+def test_full_attention_backward_first_call_in_a_fresh_process(cuda):
+    """The full (LoRA) backward as the very first attention call of a process: every kernel it launches must have its
+    shared-memory attribute set by that call itself, not by an earlier call of another route (regression: the own rows
+    going to the tensor-memory kernel skipped the set-up the prefix-row kernels rely on)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); from medtsllm_b200 import ops\n"
+        "Bp, Lc, Ls, H, hd = 4, 128, 42, 2, 128; D = H * hd; M = Lc + Bp * Ls\n"
+        "dev = torch.device('cuda', 0); g = torch.Generator().manual_seed(0)\n"
+        "qkv = (torch.randn(M, 3 * D, generator=g) * 0.5).to(dev, torch.bfloat16)\n"
+        "out = (torch.randn(M, D, generator=g) * 0.5).to(dev, torch.bfloat16)\n"
+        "dout = torch.randn(M, D, generator=g).to(dev, torch.bfloat16)\n"
+        "lse = torch.randn(H * Lc + Bp * H * Ls, generator=g).abs().to(dev) + 5\n"
+        "d = ops.attn_causal_shared_bwd_full(qkv, out, dout, lse, Bp, Lc, Ls, H, hd)\n"
+        "torch.cuda.synchronize(); assert torch.isfinite(d.float()).all(); print('ok')\n"
+    ) % str(Path(__file__).resolve().parent.parent / "med-ts-llm_b200")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 # ------------------------------------------------------------------------------- training-path kernels
