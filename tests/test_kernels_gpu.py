@@ -285,6 +285,10 @@ def test_attn_causal(ops, cuda, Bp, L, H, hd, rope):
     (3, 0, 192, 2, 128),       # plain layout, two tiles per sample
     (6, 0, 49, 2, 64),         # plain layout, two samples per tile
     (2, 0, 256, 1, 128),
+    (2, 0, 5, 1, 64),          # tiny: sixteen-column segments mostly padding
+    (3, 16, 1, 2, 128),        # one own token per sample
+    (1, 0, 129, 1, 64),        # one row in the second tile
+    (40, 48, 3, 1, 64),        # samples-per-tile limited by the 256 key columns
 ])
 def test_attn_tensor_memory_kernel(ops, cuda, Bp, Lc, Ls, H, hd):
     """The tcgen05 / TMEM forward (attention_tc.cu) against fp64 attention and against the mma.sync kernels it replaces,
@@ -343,6 +347,8 @@ def test_attn_tensor_memory_kernel(ops, cuda, Bp, Lc, Ls, H, hd):
     (3, 128, 128, 1, 128),     # LUDB: 256 key columns
     (4, 37, 12, 3, 64),        # prefix not a multiple of 64: masked gap columns
     (5, 100, 33, 1, 128),
+    (3, 16, 1, 2, 128),        # one own token per sample
+    (9, 64, 128, 1, 64),       # a full tile of own rows behind a short prefix
 ])
 def test_attn_tensor_memory_backward(ops, cuda, Bp, Lc, Ls, H, hd, rope):
     """The tcgen05 / TMEM backward of the shared-prefix layout (own rows only: frozen backbone) against fp64 autograd and
