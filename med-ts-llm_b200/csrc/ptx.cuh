@@ -64,21 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
-// The same wait for warps that share their scheduler with working warps: between polls the thread sleeps, so the spin
-// does not take issue slots away from the warps doing the arithmetic (attention_tc.cu: ten warps on four schedulers).
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int tag, unsigned ns = 32) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(ns);
-    if (clock64() - t0 > MTS_WATCHDOG_CYCLES) {
-      printf("[mtsb200] watchdog: block %d thread %d stuck on barrier tag %d parity %u\n",
-             (int)blockIdx.x, (int)threadIdx.x, tag, parity);
-      __trap();
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
