@@ -62,6 +62,8 @@ int mts_clear_caches(void);
  *               tcgen05 / tensor memory (sequences of at most 256 positions, head dim 64 / 128) instead of the mma.sync
  *               kernels.  "auto" decides from (samples, heads, positions, head dim) only, so that the shared-prefix and
  *               the per-sample layout of one model always run the same arithmetic.
+ *   "epi_direct" (0/1; default 1, env MTS_EPI_DIRECT=0): GEMM epilogues store full 32-column chunks straight from the
+ *               registers with 32-byte accesses when the rows of D are 32-byte aligned (0 = always stage through smem).
  *   "pdl"       (0/1; default 1, env MTS_PDL=0): launch the per-layer kernels with programmatic stream serialization
  *               (their prologues overlap the previous kernel's tail; they block in griddepcontrol.wait before
  *               touching its results).

@@ -49,6 +49,8 @@ struct GemmParams {
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
   long long* dbg;  // MTS_GEMM_DBG=1 (single-CTA kernel): clock64 stamps of block 0, printed by the launcher (debug)
+  int direct;      // rows of D (and C) are 32-byte aligned: full 32-column chunks are stored straight from the registers with
+                   // 32-byte accesses (a lane's 32 columns are 64 / 128 contiguous bytes) instead of being staged through smem
 };
 #define GEMM_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
@@ -288,6 +290,57 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n) dptr[(int64_t)(col0 + j) * p.ldd] = __float2bfloat16_rn(v[j]);
+            }
+          }
+          continue;
+        }
+
+        if (p.direct && col0 + 32 <= n_store) {
+          // direct path: this lane's 32 columns of row `row` are contiguous in memory — whole 32-byte sectors per access,
+          // no shared-memory round trip, no warp synchronisation (the exposed epilogue of a one-tile-per-CTA launch is a
+          // serial chain on four warps: every dependent step removed is time off the launch)
+          if (row < p.m) {
+            const int64_t off = (int64_t)b * p.d_batch_stride + (int64_t)row * p.ldd + col0;
+            if (p.d_is_f32) {
+              float* dptr = reinterpret_cast<float*>(p.d) + off;
+              if constexpr (EPI == MTS_EPI_RESID_ADD) {
+                const float* cptr = p.c + off;
+                uint32_t cw[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ld_global_v8(cptr + 8 * q, cw[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) cw[q][e] = __float_as_uint(__uint_as_float(cw[q][e]) + v[8 * q + e]);
+                  st_global_v8(dptr + 8 * q, cw[q]);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(v[8 * q + e]);
+                  st_global_v8(dptr + 8 * q, w);
+                }
+              }
+            } else {
+              __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
+              if constexpr (EPI == MTS_EPI_RESID_ADD) {   // bf16 accumulate (LoRA side GEMMs): D = bf16(D + v)
+                uint32_t ow[2][8];
+                ld_global_v8(dptr, ow[0]);
+                ld_global_v8(dptr + 16, ow[1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { v[16 * q + 2 * e] += bf16_lo(ow[q][e]); v[16 * q + 2 * e + 1] += bf16_hi(ow[q][e]); }
+              }
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[16 * q + 2 * e], v[16 * q + 2 * e + 1]);
+                st_global_v8(dptr + 16 * q, w);
+              }
             }
           }
           continue;

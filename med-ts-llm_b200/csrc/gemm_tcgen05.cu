@@ -419,6 +419,14 @@ static int streamk_mode() {
   }
   return g_streamk;
 }
+static int g_epi_direct = -1;      // MTS_EPI_DIRECT=0 / mts_set_option("epi_direct", 0): always stage the epilogue through smem
+static bool epi_direct_enabled() {
+  if (g_epi_direct < 0) {
+    const char* e = getenv("MTS_EPI_DIRECT");
+    g_epi_direct = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_epi_direct == 1;
+}
 static int g_gemm_force = 0;      // mts_set_option("gemm_force", 0 auto | 1 single-CTA kernel | 2 CTA-pair kernel): experiments
 static int g_pdl = -1;
 bool pdl_enabled() {
@@ -438,6 +446,7 @@ extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
+  if (name && !strcmp(name, "epi_direct")) { g_epi_direct = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "attn_tc")) { attn_tc_set(value); return MTS_OK; }
   if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 0 : value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
@@ -569,6 +578,13 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
     p.drop_seed = a->drop_seed;
   }
   p.round_tf32 = (a->round_tf32 && f32) ? 1 : 0;
+  {
+    const int eb = f32 ? 4 : 2;
+    p.direct = (epi_direct_enabled() && vec_ok && !a->d_transposed && (reinterpret_cast<uintptr_t>(a->d) & 31) == 0 &&
+                ((a->ldd * eb) % 32) == 0 && ((a->d_batch_stride * eb) % 32) == 0 &&
+                (!a->c || (reinterpret_cast<uintptr_t>(a->c) & 31) == 0))
+                   ? 1 : 0;
+  }
   p.precise = tf32 ? 1 : 0;
   p.streamk = use_sk;
   p.sk_ws = static_cast<float*>(a->sk_workspace);

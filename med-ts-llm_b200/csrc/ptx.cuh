@@ -301,6 +301,19 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32
   return mix32(seed * 0xD1342543DE82EF95ull + idx) >= thresh;
 }
 
+// 32-byte global accesses (LDG.256 / STG.256 on sm_100): one full sector per lane
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&w)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(ptr)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
