@@ -773,10 +773,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       __nv_bfloat16* dq_dst = p.dqkv_own + (int64_t)(own_row0 + r) * 3 * p.D + (int64_t)head * HD;
       __nv_bfloat16* dk_dst = p.dqkv_own + (int64_t)(own_row0 + ms * p.Ls + mj) * 3 * p.D + p.D + (int64_t)head * HD;
       __nv_bfloat16* dv_dst = dk_dst + p.D;
-      const float* cq = p.rope_cos ? p.rope_cos + (int64_t)(p.Lc + t) * (HD / 2) : nullptr;
-      const float* sq = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + t) * (HD / 2) : nullptr;
-      const float* ck = p.rope_cos ? p.rope_cos + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
-      const float* sk = p.rope_sin ? p.rope_sin + (int64_t)(p.Lc + mj) * (HD / 2) : nullptr;
+      // table rows of lanes without a query / key are never used: point them at row Lc so that the (unconditional,
+      // early) loads below stay inside the [Lc + Ls, hd/2] tables
+      const int tq_pos = p.Lc + (row_valid ? t : 0), tk_pos = p.Lc + (key_valid ? mj : 0);
+      const float* cq = p.rope_cos ? p.rope_cos + (int64_t)tq_pos * (HD / 2) : nullptr;
+      const float* sq = p.rope_sin ? p.rope_sin + (int64_t)tq_pos * (HD / 2) : nullptr;
+      const float* ck = p.rope_cos ? p.rope_cos + (int64_t)tk_pos * (HD / 2) : nullptr;
+      const float* sk = p.rope_sin ? p.rope_sin + (int64_t)tk_pos * (HD / 2) : nullptr;
       // RoPE table rows of this lane's chunk pair, in flight before the gradients are ready.  With Ls a multiple of 16 lane r
       // is query (s, t) AND own key (s, t): one pair of table rows serves dQ and dK.
       constexpr int kHalfChunks = HD / 64;
@@ -930,6 +933,8 @@ static int launch_attn_tc_t(const uint16_t* qkv, uint16_t* out, float* lse, int 
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_fwd_tc_kernel)", e);
     attr_done = true;
   }
+  if (reinterpret_cast<uintptr_t>(out) & 31)
+    return set_error(MTS_ERR_INVALID_ARG, "attention: the output must be 32-byte aligned (32-byte stores)");
   AttnTcParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
@@ -1019,6 +1024,8 @@ static int launch_attn_bwd_tc_t(const uint16_t* qkv, const float* rc, const floa
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_bwd_tc_kernel)", e);
     attr_done = true;
   }
+  if ((reinterpret_cast<uintptr_t>(dqkv_own) & 31) || (reinterpret_cast<uintptr_t>(out_own) & 15))
+    return set_error(MTS_ERR_INVALID_ARG, "attention backward: dqkv must be 32-byte and out 16-byte aligned (vector accesses)");
   AttnTcBwdParams p;
   p.out_own = reinterpret_cast<const __nv_bfloat16*>(out_own);
   p.lse_own = lse_own;
