@@ -9,8 +9,13 @@ namespace mts {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
-constexpr int kNumEpiThreads = 128;
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue set 0, warps 6..9 epilogue set 1.  A warp may only read the
+// TMEM lanes of its quarter (warp % 4), so the two sets cover the same rows; when the tile's stores take the direct path
+// (GemmParams::direct, whole 32-column chunks) they split the COLUMN chunks between them — the epilogue of a launch with
+// one tile per CTA is fully exposed, and it is a latency chain (tcgen05.ld -> residual load -> store) that two warps per
+// scheduler overlap.  Otherwise set 1 only hands the accumulator back.
+constexpr int kGemmThreads = 320;
+constexpr int kNumEpiThreads = 256;
 constexpr int kEpiPitch = 36;  // floats per staged row (144 B: 16-byte aligned, bank-conflict free)
 
 struct GemmParams {
@@ -83,6 +88,15 @@ __device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, i
   m_blk = first_m + (r - n_blk * gsize);
 }
 
+// 2 when both epilogue warp sets share a tile's column chunks: every chunk takes the direct store path (no staging buffer,
+// which only set 0 owns), i.e. p.direct and a column count that is a multiple of 32.  Warp-uniform, launch-uniform.
+template <int EPI>
+__device__ __forceinline__ int epilogue_parts(const GemmParams& p) {
+  if constexpr (EPI == MTS_EPI_ROPE_QK) return 1;
+  const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
+  return (p.direct && !p.streamk && !p.d_transposed && (n_store % 32) == 0) ? 2 : 1;
+}
+
 // Epilogue of one warp's 32-row slab of a 128 x BN accumulator tile:
 //   TMEM -> registers (thread = accumulator row, 32 columns per tcgen05.ld) -> bias / activation ->
 //   per-warp padded smem tile -> coalesced 16-byte global accesses.
@@ -91,7 +105,10 @@ __device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, i
 //   (tail splitting in the CTA-pair kernel); full tiles pass (0, BN).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int row0, int n_blk, uint32_t taddr,
-                                              float* stage_buf, int lane, int col_off = 0, int n_cols = BN) {
+                                              float* stage_buf, int lane, int col_off = 0, int n_cols = BN,
+                                              int part = 0, int parts = 1) {
+      // part / parts: this warp takes the 32-column chunks part, part + parts, ... (epilogue_parts() below says when the
+      // second warp set may join: never on the paths that stage through stage_buf)
       const int row = row0 + lane;                       // the accumulator row this thread reads
       if constexpr (EPI == MTS_EPI_ROPE_QK) {
         // q/k columns are rotated in fp32 straight from the accumulators: x1' = x1 cos - x2 sin,
@@ -188,7 +205,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
       const int kChunks = (EPI == MTS_EPI_SWIGLU) ? BN / 64 : n_cols / 32;
       const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
 #pragma unroll 1
-      for (int ci = 0; ci < kChunks; ++ci) {
+      for (int ci = part; ci < kChunks; ci += parts) {
         float v[32];
         int col0;  // first output column of this chunk
         __syncwarp();  // tcgen05.ld is .sync.aligned; also orders the previous chunk's smem reads

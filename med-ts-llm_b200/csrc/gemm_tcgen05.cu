@@ -9,8 +9,9 @@
 //   warp 1 / lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per
 //                     stage; fp32 accumulators in TMEM, two accumulator stages (2*BN columns) so
 //                     the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5      : epilogue      — tcgen05.ld 32x32b.x32 (thread = row, 32 columns), fused
-//                     bias / residual-add / gelu_new / silu*up, vectorised global stores
+//   warps 2..9      : epilogue      — tcgen05.ld 32x32b.x32 (thread = row, 32 columns), fused
+//                     bias / residual-add / gelu_new / silu*up, vectorised global stores; two warps per
+//                     TMEM lane quarter share the column chunks on the direct-store path (gemm_common.cuh)
 //
 // Algorithmic work per launch: 2*m*n*k*batch FLOP (roofline: tensor pipe).
 #include <stdlib.h>
@@ -211,10 +212,12 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------------ epilogue warps 2..9
     // TMEM -> registers (thread = accumulator row, 32 columns) -> per-warp padded smem tile ->
     // coalesced 16-byte global accesses (a quarter-warp covers one contiguous 128-byte row piece).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int eset = (warp - 2) >> 2;                       // 0: warps 2..5 (own the staging buffers), 1: warps 6..9
+    const int parts = epilogue_parts<EPI>(p);
     float* stage_buf = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) +
                        quarter * (32 * kEpiPitch);
     int it = 0;
@@ -231,8 +234,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       if (threadIdx.x == 64) GEMM_STAMP(6);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      bool run_epilogue = true;
-      if (p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
+      bool run_epilogue = eset < parts;
+      if (eset == 0 && p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
         const int64_t slot_elems = (int64_t)kBlockM * BN;
         const int64_t row_off = (int64_t)(quarter * 32 + lane) * BN;
         if (kb0 > 0) {
@@ -300,7 +303,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
       if (run_epilogue)
-        epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr, stage_buf, lane);
+        epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr, stage_buf, lane, 0, BN, eset, parts);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));

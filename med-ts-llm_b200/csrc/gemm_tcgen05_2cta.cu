@@ -12,7 +12,7 @@
 //             all four TMA loads of a stage credit their bytes to the leader's barrier
 //   empty[s]  per CTA; released by the leader's multicast tcgen05.commit
 //   tfull[a]  per CTA; multicast commit after the tile's last k-block
-//   tempty[a] leader only; 256 arrivals (both CTAs' epilogue threads, the peer's remotely)
+//   tempty[a] leader only; 512 arrivals (both CTAs' epilogue threads, the peer's remotely)
 #include "gemm_common.cuh"
 
 namespace mts {
@@ -170,8 +170,10 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5 (both CTAs)
+    // ------------------------------------------------------------------ epilogue warps 2..9 (both CTAs)
     const int quarter = warp & 3;
+    const int eset = (warp - 2) >> 2;                       // 0: warps 2..5 (own the staging buffers), 1: warps 6..9
+    const int parts = epilogue_parts<EPI>(p);
     float* stage_buf = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) +
                        quarter * (32 * kEpiPitch);
     int it = 0;
@@ -185,9 +187,10 @@ gemm_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(p, b, m_blk * 2 * kBlockM + (int)rank * kBlockM + quarter * 32, n_blk,
-                             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN),
-                             stage_buf, lane, pu.col_off, pu.n_cols);
+      if (eset < parts)
+        epilogue_tile<BN, EPI>(p, b, m_blk * 2 * kBlockM + (int)rank * kBlockM + quarter * 32, n_blk,
+                               tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN),
+                               stage_buf, lane, pu.col_off, pu.n_cols, eset, parts);
       tc_fence_before();
       if (rank == 0) mbar_arrive(tempty_bar(acc));
       else           mbar_arrive_cluster(tempty_bar(acc), 0);
