@@ -47,6 +47,8 @@ struct GemmParams {
   // partials in ascending CTA order (deterministic) and runs the epilogue.  Contributors never wait: no deadlock, and an
   // owner finds the partials already there when it gets to the end of its own range.
   int streamk;
+  int sk_grid;     // stream-K grid size: the SM count, or tiles x s for the even split-K form (every tile cut into s equal
+                   // k ranges held by s consecutive CTAs: small tile counts with a deep k, mts_set_option("streamk", 3))
   float* sk_ws;
   int* sk_flags;
   int sk_epoch;
@@ -54,6 +56,10 @@ struct GemmParams {
   int split3;      // TF32 kernels: three k sweeps (hi*hi, lo*hi, hi*lo) over the split operands
   int round_tf32;  // fp32 D only: round the stored values to TF32 (they feed a kind::tf32 GEMM next)
   long long* dbg;  // MTS_GEMM_DBG=1 (single-CTA kernel): clock64 stamps of block 0, printed by the launcher (debug)
+  int ksplit;      // cluster split-K (single-CTA kernel): clusters of ksplit CTAs share one tile, CTA r of a cluster runs the
+                   // r-th k range over the whole tile, sends the column parts it does not own into their owners' shared
+                   // memory (the operand ring, idle by then) and runs the epilogue of column part r — no workspace, no
+                   // global-memory round trip; 0 / 1 = off
   int direct;      // rows of D (and C) are 32-byte aligned: full 32-column chunks are stored straight from the registers with
                    // 32-byte accesses (a lane's 32 columns are 64 / 128 contiguous bytes) instead of being staged through smem
 };
@@ -94,7 +100,7 @@ template <int EPI>
 __device__ __forceinline__ int epilogue_parts(const GemmParams& p) {
   if constexpr (EPI == MTS_EPI_ROPE_QK) return 1;
   const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
-  return (p.direct && !p.streamk && !p.d_transposed && (n_store % 32) == 0) ? 2 : 1;
+  return (p.direct && !p.d_transposed && (n_store % 32) == 0) ? 2 : 1;
 }
 
 // Epilogue of one warp's 32-row slab of a 128 x BN accumulator tile:
@@ -106,7 +112,25 @@ __device__ __forceinline__ int epilogue_parts(const GemmParams& p) {
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int row0, int n_blk, uint32_t taddr,
                                               float* stage_buf, int lane, int col_off = 0, int n_cols = BN,
-                                              int part = 0, int parts = 1) {
+                                              int part = 0, int parts = 1, const float* sk_src = nullptr,
+                                              int sk_n = 0, int64_t sk_stride = 0, bool sk_smem = false) {
+      // sk_src / sk_n / sk_stride: split-K partials of sk_n other CTAs for this thread's row (workspace layout of
+      // gemm_tcgen05.cu: chunk c, column group g at (c * 8 + g) * 512 floats), added to every chunk read from TMEM
+      auto sk_add = [&](uint32_t (&r)[32], int chunk) {
+        for (int c = 0; c < sk_n; ++c) {
+          const float* w = sk_src + (int64_t)c * sk_stride + chunk * 4096;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            // partials in the workspace were written by other SMs: L2 only; cluster split-K parks them in this CTA's smem
+            const float4 v = sk_smem ? *reinterpret_cast<const float4*>(w + g * 512)
+                                     : __ldcg(reinterpret_cast<const float4*>(w + g * 512));
+            r[4 * g] = __float_as_uint(__uint_as_float(r[4 * g]) + v.x);
+            r[4 * g + 1] = __float_as_uint(__uint_as_float(r[4 * g + 1]) + v.y);
+            r[4 * g + 2] = __float_as_uint(__uint_as_float(r[4 * g + 2]) + v.z);
+            r[4 * g + 3] = __float_as_uint(__uint_as_float(r[4 * g + 3]) + v.w);
+          }
+        }
+      };
       // part / parts: this warp takes the 32-column chunks part, part + parts, ... (epilogue_parts() below says when the
       // second warp set may join: never on the paths that stage through stage_buf)
       const int row = row0 + lane;                       // the accumulator row this thread reads
@@ -131,6 +155,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
             tmem_ld_32x32(taddr + ca * 32, xa);
             tmem_ld_32x32(taddr + cb * 32, xb);
             tmem_ld_wait();
+            if (sk_n > 0) { sk_add(xa, ca); sk_add(xb, cb); }
             const int col_a = n_blk * BN + ca * 32, col_b = n_blk * BN + cb * 32;
             if (col_a >= p.n) continue;                                 // warp-uniform
             float va[32], vb[32];
@@ -215,6 +240,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           tmem_ld_32x32(taddr + ci * 32, g);
           tmem_ld_32x32(taddr + BN / 2 + ci * 32, u);
           tmem_ld_wait();
+          if (sk_n > 0) { sk_add(g, ci); sk_add(u, BN / 64 + ci); }
           col0 = n_blk * (BN / 2) + ci * 32;
           if (p.aux != nullptr && row < p.m && n_blk * BN + ci * 32 < p.n) {
             // pre-activations for the backward: 64 contiguous bytes per thread and half (16-byte stores)
@@ -251,6 +277,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
           uint32_t r[32];
           tmem_ld_32x32(taddr + ci * 32, r);
           tmem_ld_wait();
+          if (sk_n > 0) sk_add(r, ci);
           col0 = n_blk * BN + col_off + ci * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha + bias_m;

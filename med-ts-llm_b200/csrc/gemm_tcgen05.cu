@@ -44,7 +44,7 @@ struct SegIter {
 __device__ __forceinline__ SegIter seg_init(const GemmParams& p, int num_tiles, int k_blocks) {
   SegIter s;
   s.k_blocks = k_blocks;
-  s.streamk = p.streamk != 0;
+  s.streamk = p.streamk != 0 || p.ksplit > 1;   // cluster split-K: grid = tiles x ksplit, the same even unit ranges
   if (s.streamk) {
     const long long U = (long long)num_tiles * k_blocks;
     s.u = U * blockIdx.x / gridDim.x;
@@ -103,6 +103,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  // cluster split-K: peers_free = every peer's operand ring is idle (its MMAs are done), parts_in = every peer's partial of
+  // this CTA's column part has landed in this CTA's ring
+  const uint32_t peers_free_bar = bar_base + 8u * (2 * kStages + 5);
+  const uint32_t parts_in_bar = bar_base + 8u * (2 * kStages + 6);
   const uint32_t stage_base = bar_base + Cfg::kBarrierBytes;  // 16-byte aligned
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -125,6 +129,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kNumEpiThreads);
     }
+    if (p.ksplit > 1) {
+      mbar_init(peers_free_bar, p.ksplit - 1);                          // one arrive per peer
+      mbar_init(parts_in_bar, (p.ksplit - 1) * (kNumEpiThreads / 32));   // one arrive per peer epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -137,6 +145,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
+  if (p.ksplit > 1) cluster_sync_all();   // the peers' barriers exist before anybody arrives on them remotely
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
@@ -234,32 +243,80 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       if (threadIdx.x == 64) GEMM_STAMP(6);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      bool run_epilogue = eset < parts;
-      if (eset == 0 && p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
-        const int64_t slot_elems = (int64_t)kBlockM * BN;
-        const int64_t row_off = (int64_t)(quarter * 32 + lane) * BN;
-        if (kb0 > 0) {
-          // ---- contributor: this CTA's range STARTS inside the tile (always its first segment, so the partial is parked
-          // before anybody can be waiting for it).  Raw fp32 partial -> workspace slot, then the flag.
-          float* ws = p.sk_ws + (int64_t)blockIdx.x * slot_elems + row_off;
+      if (p.ksplit > 1) {
+        // ---- cluster split-K (one segment per CTA; EPI is STORE / RESID_ADD / GELU_NEW, batch 1)
+        const int ks = p.ksplit, r = (int)cluster_ctarank();
+        const int cols_per = BN / ks, cpp = cols_per / 32;            // columns / 32-column chunks of one part
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t part_bytes = (uint32_t)(kBlockM * cols_per * 4);
+        // this CTA's MMAs are done (tfull): its operand ring is idle -> tell every peer; wait until all peers said so
+        if (threadIdx.x == 64)
+          for (int q = 0; q < ks; ++q)
+            if (q != r) mbar_arrive_release_cluster(peers_free_bar, (uint32_t)q);
+        mbar_wait_acquire_cluster(peers_free_bar, 0, 500);
+        // send: chunk ci belongs to part ci / cpp; partial slot of sender r in owner q = r's index among q's peers.
+        // Slot layout as the stream-K workspace: [chunk][group of 4 columns][row][4] fp32 (conflict-free 16-byte stores)
 #pragma unroll 1
-          for (int ci = 0; ci < BN / 32; ++ci) {
+        for (int ci = eset; ci < BN / 32; ci += 2) {
+          const int q = ci / cpp;
+          if (q == r) continue;
+          uint32_t rr[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr + ci * 32, rr);
+          tmem_ld_wait();
+          const uint32_t local = smem_base + (uint32_t)(r < q ? r : r - 1) * part_bytes +
+                                 (uint32_t)((((ci - q * cpp) * 8) * 128 + row_in_tile) * 16);
+          const uint32_t remote = mapa_cluster(local, (uint32_t)q);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) st_cluster_v4(remote + g * 2048, rr[4 * g], rr[4 * g + 1], rr[4 * g + 2], rr[4 * g + 3]);
+        }
+        fence_acq_rel_cluster();
+        __syncwarp();
+        if (lane == 0)
+          for (int q = 0; q < ks; ++q)
+            if (q != r) mbar_arrive_release_cluster(parts_in_bar, (uint32_t)q);
+        mbar_wait_acquire_cluster(parts_in_bar, 0, 501);
+        const int kparts = (parts == 2 && cpp >= 2) ? 2 : 1;
+        if (eset < kparts) {
+          const float* src = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + row_in_tile * 4;
+          epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr + r * cols_per, stage_buf, lane,
+                                 r * cols_per, cols_per, eset, kparts, src, ks - 1, (int64_t)kBlockM * cols_per, true);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        continue;
+      }
+      bool run_epilogue = eset < parts;
+      const float* sk_src = nullptr;     // owner of a split tile: the contributors' partials, added inside the epilogue
+      int sk_n = 0;
+      const int64_t slot_elems = (int64_t)kBlockM * BN;
+      if (p.streamk && !(kb0 == 0 && kb1 == k_blocks)) {
+        // Workspace slot of a CTA: [32-column chunk][group of 4 columns][row][4] fp32 — for a fixed chunk and group the 128
+        // rows (= lanes of the four warp quarters) are 16 bytes apart, so every warp access is one contiguous 512 bytes.
+        const int row_in_tile = quarter * 32 + lane;
+        if (kb0 > 0) {
+          // ---- contributor: this CTA's range STARTS inside the tile (always its first segment under stream-K, its only one
+          // under the even split, so the partial is parked without waiting for anybody).  Raw fp32 partial -> workspace
+          // slot (both warp sets, alternate chunks), then the flag.
+          float* ws = p.sk_ws + (int64_t)blockIdx.x * slot_elems + row_in_tile * 4;
+#pragma unroll 1
+          for (int ci = eset; ci < BN / 32; ci += 2) {
             uint32_t r[32];
             __syncwarp();
             tmem_ld_32x32(taddr + ci * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(ws + ci * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<uint4*>(ws + (ci * 8 + j4) * 512) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
           }
           __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+          asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
           if (threadIdx.x == 64) st_release_gpu(p.sk_flags + blockIdx.x, p.sk_epoch);
           run_epilogue = false;
-        } else {
+        } else if (eset < parts) {
           // ---- owner: holds the tile's FIRST k-blocks (the last segment of its range).  The CTAs that hold the rest — a
-          // run of consecutive higher CTA indices, each of which parked its partial at the very start of its own range —
-          // are added into the TMEM accumulator in ascending order, then the ordinary epilogue runs.
+          // run of consecutive higher CTA indices — parked their partials; the epilogue adds them to the accumulator chunk
+          // it has just read, in ascending CTA order (deterministic), before alpha / bias / activation.
           const long long U = (long long)num_tiles * k_blocks, G = gridDim.x;
           const long long last_unit = (long long)(tile + 1) * k_blocks - 1;
           int c_last = (int)(last_unit * G / U);
@@ -274,36 +331,21 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
           }
-#pragma unroll 1
-          for (int ci = 0; ci < BN / 32; ++ci) {
-            uint32_t r[32];
-            __syncwarp();
-            tmem_ld_32x32(taddr + ci * 32, r);
-            tmem_ld_wait();
-            for (int cc = (int)blockIdx.x + 1; cc <= c_last; ++cc) {
-              const float* ws = p.sk_ws + (int64_t)cc * slot_elems + row_off + ci * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
-                r[j] = __float_as_uint(__uint_as_float(r[j]) + v.x);
-                r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + v.y);
-                r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + v.z);
-                r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + v.w);
-              }
-            }
-            tmem_st_32x32(taddr + ci * 32, r);
-            tmem_st_wait();
-          }
-          __syncwarp();
-          // every partial has exactly one reader: lower the flags again, so that the next launch — or the next replay of
-          // a captured graph, which carries the same sk_epoch — starts from "not ready"
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64)
-            for (int cc = (int)blockIdx.x + 1; cc <= c_last; ++cc) st_release_gpu(p.sk_flags + cc, 0);
+          sk_src = p.sk_ws + ((int64_t)blockIdx.x + 1) * slot_elems + row_in_tile * 4;
+          sk_n = c_last - (int)blockIdx.x;
         }
       }
       if (run_epilogue)
-        epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr, stage_buf, lane, 0, BN, eset, parts);
+        epilogue_tile<BN, EPI>(p, b, m_blk * kBlockM + quarter * 32, n_blk, taddr, stage_buf, lane, 0, BN, eset, parts,
+                               sk_src, sk_n, slot_elems);
+      if (sk_n > 0) {
+        // every partial has exactly one reader: lower the flags again, so that the next launch — or the next replay of
+        // a captured graph, which carries the same sk_epoch — starts from "not ready"
+        if (parts == 2) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else            asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (threadIdx.x == 64)
+          for (int cc = (int)blockIdx.x + 1; cc <= (int)blockIdx.x + sk_n; ++cc) st_release_gpu(p.sk_flags + cc, 0);
+      }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -340,7 +382,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_done = true;
   }
   // stream-K: one CTA per SM, each takes an equal share of the (tile, k-block) units
-  const int grid = p.streamk ? num_sms() : (num_tiles < num_sms() ? num_tiles : num_sms());
+  const int grid = p.streamk ? p.sk_grid : (num_tiles < num_sms() ? num_tiles : num_sms());
   static int dbg_on = -1;
   static long long* dbg_buf = nullptr;
   if (dbg_on < 0) { const char* e = getenv("MTS_GEMM_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
@@ -351,8 +393,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
     pp.dbg = dbg_buf;
   }
-  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, pp,
-                              (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
+  cudaError_t le;
+  if (p.ksplit > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_tiles * p.ksplit);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.ksplit;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    le = cudaLaunchKernelEx(&cfg, kern, ta, tb, pp, (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
+  } else {
+    le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, pp,
+                    (TF32 && g_ta_lo) ? *g_ta_lo : ta, (TF32 && g_tb_lo) ? *g_tb_lo : tb);
+  }
   if (le != cudaSuccess) return set_cuda_error("cudaLaunchKernelEx(gemm_bf16_nt_kernel)", le);
   count_launch();
   if (dbg_on) {
@@ -418,7 +479,7 @@ static int streamk_mode() {
   if (g_streamk < 0) {
     const char* e = getenv("MTS_STREAMK");
     g_streamk = e ? atoi(e) : 0;
-    if (g_streamk < 0 || g_streamk > 2) g_streamk = 0;
+    if (g_streamk < 0 || g_streamk > 3) g_streamk = 0;
   }
   return g_streamk;
 }
@@ -429,6 +490,16 @@ static bool epi_direct_enabled() {
     g_epi_direct = (e && e[0] == '0') ? 0 : 1;
   }
   return g_epi_direct == 1;
+}
+// cluster split-K of the single-CTA kernel: -1 auto (default) | 0 off | 2 / 4 forced whenever legal (experiments, tests)
+static int g_gemm_ksplit = -2;
+static int gemm_ksplit_mode() {
+  if (g_gemm_ksplit == -2) {
+    const char* e = getenv("MTS_GEMM_KSPLIT");
+    g_gemm_ksplit = e ? atoi(e) : -1;
+    if (!(g_gemm_ksplit == -1 || g_gemm_ksplit == 0 || g_gemm_ksplit == 2 || g_gemm_ksplit == 4)) g_gemm_ksplit = -1;
+  }
+  return g_gemm_ksplit;
 }
 static int g_gemm_force = 0;      // mts_set_option("gemm_force", 0 auto | 1 single-CTA kernel | 2 CTA-pair kernel): experiments
 static int g_pdl = -1;
@@ -449,9 +520,15 @@ extern "C" int mts_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_2cta")) { g_gemm_2cta = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "gemm_force")) { g_gemm_force = value; return MTS_OK; }
+  if (name && !strcmp(name, "gemm_ksplit")) {
+    if (!(value == -1 || value == 0 || value == 2 || value == 4))
+      return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: gemm_ksplit is -1 (auto), 0, 2 or 4");
+    g_gemm_ksplit = value;
+    return MTS_OK;
+  }
   if (name && !strcmp(name, "epi_direct")) { g_epi_direct = value ? 1 : 0; return MTS_OK; }
   if (name && !strcmp(name, "attn_tc")) { attn_tc_set(value); return MTS_OK; }
-  if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 2) ? 0 : value; return MTS_OK; }
+  if (name && !strcmp(name, "streamk")) { g_streamk = (value < 0 || value > 3) ? 0 : value; return MTS_OK; }
   return set_error(MTS_ERR_INVALID_ARG, "mts_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
@@ -524,7 +601,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   if (a->c && a->epilogue != MTS_EPI_RESID_ADD)
     return set_error(MTS_ERR_INVALID_ARG, "mts_gemm: c is only used by MTS_EPI_RESID_ADD");
   // ---- stream-K: worth it when whole tiles leave the SMs unevenly loaded (small m) and every CTA still gets a few k-blocks
-  int use_sk = 0;
+  int use_sk = 0, sk_grid = num_sms();
   {
     const int skm = streamk_mode();
     const int kb_elems = (a->ab_dtype == MTS_F32) ? kBlockK / 2 : kBlockK;
@@ -537,7 +614,36 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
       const double eff = (double)tiles / (double)(((tiles + G - 1) / G) * G);
       const bool fits = a->sk_workspace_bytes >= (int64_t)G * kBlockM * bn_sk * 4;
       const bool enough = tiles * kbs >= 4 * G && kbs >= 4;
-      if (fits && enough && (skm == 2 || eff < 0.85)) { use_sk = 1; bn = bn_sk; }
+      if (skm == 3) {
+        // even split-K: tiles x s CTAs in one wave, CTA c holds k range c % s of tile c / s (the general unit arithmetic with
+        // G = tiles x s; the owner is the CTA with the first range, its s - 1 contributors are the next CTA indices)
+        long sp = G / tiles;
+        if (sp > 4) sp = 4;
+        while (sp >= 2 && (kbs % sp) != 0) --sp;
+        if (tiles >= 1 && sp >= 2 && kbs / sp >= 8 && fits) { use_sk = 1; bn = bn_sk; sk_grid = (int)(tiles * sp); }
+      } else if (fits && enough && (skm == 2 || eff < 0.85)) { use_sk = 1; bn = bn_sk; }
+    }
+  }
+  // ---- cluster split-K: few tiles with a deep k (GPT-2-sized projections on ~900 rows): clusters of s CTAs share a tile
+  int ksplit = 0;
+  {
+    const int km = gemm_ksplit_mode();
+    const bool epi_ok = a->epilogue == MTS_EPI_STORE || a->epilogue == MTS_EPI_RESID_ADD || a->epilogue == MTS_EPI_GELU_NEW;
+    if (km != 0 && !use_sk && !tf32 && epi_ok && a->batch == 1 && !a->d_transposed && g_gemm_force != 2) {
+      const long kbs = (a->k + kBlockK - 1) / kBlockK, mb = (a->m + kBlockM - 1) / kBlockM;
+      auto legal = [&](int bn_k, int s) {
+        const long tiles = mb * ((a->n + bn_k - 1) / bn_k);
+        return tiles * s <= num_sms() && (kbs % s) == 0 && kbs / s >= 4 && bn_k / s >= 32;
+      };
+      if (km > 0) {                               // forced (tests / sweeps): the caller's tile width or the widest legal one
+        const int bn_k = bn != 0 ? bn : (km == 4 ? 256 : 128);
+        if ((bn_k == 64 || bn_k == 128 || bn_k == 256) && legal(bn_k, km)) { ksplit = km; bn = bn_k; }
+      } else if (bn == 0) {
+        // auto: measured on B200 (profiles/r02_ksplit_gemm.md): pairs on 128-wide tiles win whenever they fit one wave and
+        // the k loop is deep enough to pay for the exchange (K >= 2048); the distributed-shared-memory stores run at
+        // ~20 B/clk per SM, so clusters of four (three quarters of a 128 x 256 tile sent) stay behind pairs
+        if (kbs >= 32 && legal(128, 2)) { ksplit = 2; bn = 128; }
+      }
     }
   }
   if (bn == 0) bn = pick_block_n(a->m, a->n, a->batch);
@@ -590,6 +696,8 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
   }
   p.precise = tf32 ? 1 : 0;
   p.streamk = use_sk;
+  p.sk_grid = sk_grid;
+  p.ksplit = ksplit;
   p.sk_ws = static_cast<float*>(a->sk_workspace);
   p.sk_flags = a->sk_flags;
   p.sk_epoch = a->sk_epoch;
@@ -629,7 +737,7 @@ extern "C" int mts_gemm(const mts_gemm_args* a, mts_stream_t stream_) {
       default: return dispatch_epi<64, true>(a->epilogue, ta, tb, p, (int)tl, stream);
     }
   }
-  if (bn == 256 && !a->d_transposed && gemm_2cta_enabled() && !use_sk) {
+  if (bn == 256 && !a->d_transposed && gemm_2cta_enabled() && !use_sk && ksplit == 0) {
     // CTA pairs own 256x256 tiles (74 pairs); a tile costs ~0.92 of two 128x256 tiles' time.  Prefer them
     // unless the 256-row granularity wastes more than it saves (odd / single 128-row block counts).
     const long nb256 = (a->n + 255) / 256;

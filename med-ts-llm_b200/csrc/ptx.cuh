@@ -209,6 +209,46 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "}" ::"r"(bar), "r"(cta)
       : "memory");
 }
+// ---- distributed shared memory (cluster split-K of the single-CTA GEMM): data stores into a peer CTA's shared memory,
+// published with a cluster-scope release arrive on the peer's mbarrier and consumed behind a cluster-scope acquire wait
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t remote, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > MTS_WATCHDOG_CYCLES) {
+      printf("[mtsb200] watchdog: block %d thread %d stuck on cluster barrier tag %d\n", (int)blockIdx.x, (int)threadIdx.x, tag);
+      __trap();
+    }
+  }
+}
 // TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared).
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar,
                                                 int c0, int c1, int c2, uint64_t policy) {

@@ -45,7 +45,20 @@ def test_full_size_forward_properties(workload, cuda):
     assert ref.shape[0] == w.B and torch.isfinite(ref).all()
     ids = model.prompt_token_ids({"x_enc": x})
     assert model._shared_prefix_len(ids, w.B, w.seq) == w.prompt_len          # the whole prompt is shared
-    assert torch.equal(fwd(x, share=False), ref)                              # prompt sharing
+    # prompt sharing: bit-identical whenever both layouts run the same GEMM schedules.  Cluster split-K (on by default)
+    # halves the k loop of few-tile / deep-k GEMMs — the 896-row MLP projection of GPT-2-medium in the shared layout, not
+    # its 8960-row per-sample counterpart — so with it the layouts differ by the fp32 regrouping of that one k-sum.
+    from medtsllm_b200 import _lib
+    _lib.set_option("gemm_ksplit", 0)
+    try:
+        ref0 = fwd(x)
+        assert torch.equal(fwd(x, share=False), ref0)
+    finally:
+        _lib.set_option("gemm_ksplit", -1)
+    assert _rel(ref, ref0) < 5e-3, _rel(ref, ref0)                            # bf16 re-rounding of regrouped fp32 sums
+    if workload == "bidmc_llama2_7b":
+        # only GEMMs whose row count is the same in both layouts (head, reprogramming) are split here: still identical
+        assert torch.equal(fwd(x, share=False), ref)
     for _ in range(3):                                                        # eager, capture, replay
         assert torch.equal(fwd(x, graph=True), ref)
     perm = torch.randperm(w.B, generator=torch.Generator().manual_seed(1)).to(cuda)

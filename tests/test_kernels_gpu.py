@@ -993,6 +993,92 @@ def test_gemm_streamk_matches_plain_schedule(ops, cuda, m, n, k, epi):
     torch.testing.assert_close(sk1.float(), plain.float(), **tol)
 
 
+@pytest.mark.parametrize("m,n,k,epi,bn", [(896, 1024, 4096, 1, 0), (896, 1024, 4096, 1, 256), (896, 1024, 1024, 1, 0),
+                                           (300, 520, 2048, 0, 0), (128, 256, 8192, 2, 128), (130, 1024, 1536, 1, 64)])
+def test_gemm_even_split_k(ops, cuda, m, n, k, epi, bn):
+    """Even split-K (stream-K mode 3): tiles x s CTAs, each tile cut into s equal k ranges on consecutive CTAs, the first of
+    which adds the others' partials in ascending order and runs the epilogue.  Deterministic, back-to-back launches reuse
+    the flags, and the result equals the plain schedule up to the fp32 regrouping of the k-sum."""
+    g = torch.Generator().manual_seed(m + n + k + bn)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    b = (torch.randn(n, k, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(cuda) if epi == 2 else None
+    c0 = torch.randn(m, n, generator=g).to(cuda)
+
+    def run(mode):
+        ops.set_streamk(mode)
+        d = c0.clone() if epi == 1 else torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
+        ops.gemm(a, b, d, m=m, n=n, k=k, epilogue=epi, bias=bias, bias_axis=1 if bias is not None else 0, block_n=bn)
+        return d
+
+    try:
+        plain = run(0)
+        outs = [run(3) for _ in range(4)]
+    finally:
+        ops.set_streamk(0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    z = a.float() @ b.float().t()
+    if epi == 1:
+        ref = c0 + z
+    elif epi == 2:
+        z = z + bias
+        ref = 0.5 * z * (1 + torch.tanh(math.sqrt(2 / math.pi) * (z + 0.044715 * z ** 3)))
+    else:
+        ref = z
+    tol = dict(rtol=1e-4, atol=1e-3) if epi == 1 else dict(rtol=8e-3, atol=2e-2)
+    torch.testing.assert_close(outs[0].float(), ref, **tol)
+    torch.testing.assert_close(outs[0].float(), plain.float(), **tol)
+
+
+@pytest.mark.parametrize("m,n,k,epi,bn,ks", [
+    (896, 1024, 4096, 1, 256, 4),     # GPT-2-medium MLP projection on the PSM rows: 28 tiles x 4
+    (896, 1024, 4096, 1, 128, 2),
+    (896, 1024, 1024, 1, 128, 2),
+    (896, 1024, 4096, 1, 0, -1),      # auto
+    (300, 520, 2048, 0, 128, 4),      # ragged rows / columns, one chunk per part (bf16 store)
+    (300, 520, 2048, 0, 256, 2),
+    (128, 256, 8192, 2, 256, 4),      # bias + gelu_new
+    (130, 1000, 1536, 1, 64, 2),      # column count not a multiple of 32: staged stores on warp set 0 only
+    (77, 96, 512, 0, 64, 2),
+])
+def test_gemm_cluster_split_k(ops, cuda, m, n, k, epi, bn, ks):
+    """Cluster split-K of the single-CTA kernel (mts_set_option("gemm_ksplit")): the CTAs of a cluster run equal k ranges of
+    one tile, exchange column parts through distributed shared memory and each finish one part.  Deterministic, and equal
+    to the plain schedule up to the fp32 regrouping of the k-sum."""
+    from medtsllm_b200 import _lib
+    g = torch.Generator().manual_seed(m + n + k + bn)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(cuda, torch.bfloat16)
+    b = (torch.randn(n, k, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(cuda) if epi == 2 else None
+    c0 = torch.randn(m, n, generator=g).to(cuda)
+
+    def run(mode):
+        _lib.set_option("gemm_ksplit", mode)
+        d = c0.clone() if epi == 1 else torch.full((m, n), float("nan"), device=cuda, dtype=torch.bfloat16)
+        ops.gemm(a, b, d, m=m, n=n, k=k, epilogue=epi, bias=bias, bias_axis=1 if bias is not None else 0, block_n=bn)
+        return d
+
+    try:
+        plain = run(0)
+        outs = [run(ks) for _ in range(3)]
+    finally:
+        _lib.set_option("gemm_ksplit", -1)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    z = a.float() @ b.float().t()
+    if epi == 1:
+        ref = c0 + z
+    elif epi == 2:
+        z = z + bias
+        ref = 0.5 * z * (1 + torch.tanh(math.sqrt(2 / math.pi) * (z + 0.044715 * z ** 3)))
+    else:
+        ref = z
+    tol = dict(rtol=1e-4, atol=1e-3) if epi == 1 else dict(rtol=8e-3, atol=2e-2)
+    torch.testing.assert_close(outs[0].float(), ref, **tol)
+    torch.testing.assert_close(outs[0].float(), plain.float(), **tol)
+
+
 def test_gemm_streamk_under_graph_replay(ops, cuda):
     """The flags a launch raises are lowered again by their single reader, so a captured graph (same arguments on every
     replay) can be replayed back to back."""

@@ -40,7 +40,21 @@ if "--shared-prefix-only" in sys.argv:
 if "--small-m" in sys.argv:
     shapes = shapes[-8:]
 sk_modes = [0, 1, 2] if "--streamk-sweep" in sys.argv else [None]
-for (name, m, n, k, epi, bn), force, skm in ((sh, f, sk) for sh in shapes for f in force_modes for sk in sk_modes):
+if "--splitk-sweep" in sys.argv:     # even split-K (mode 3) at forced tile widths, against the auto schedule
+    shapes = [s for s in shapes if s[0] in ("psm_o_resid", "psm_proj_resid", "vent_o_resid")]
+    shapes = [(nm, m, n, k, e, bn) for (nm, m, n, k, e, _) in shapes for bn in (0, 64, 128, 256)]
+    sk_modes = [0, 3]
+ks_modes = [None]
+if "--ksplit-sweep" in sys.argv:     # cluster split-K at forced (tile width, cluster size) against the plain schedules
+    shapes = [s for s in shapes if s[0].startswith("psm_") and s[4] != 3] + [s for s in shapes if s[0] == "vent_o_resid"]
+    shapes = [(nm, m, n, k, e, bn) for (nm, m, n, k, e, _) in shapes for bn in (0, 64, 128, 256)]
+    ks_modes = [0, 2, 4, -1]
+for (name, m, n, k, epi, bn), force, skm, ksm in ((sh, f, sk, ks) for sh in shapes for f in force_modes for sk in sk_modes
+                                                 for ks in ks_modes):
+    if ksm is not None:
+        if (bn == 0) != (ksm in (0, -1)) and not (bn != 0 and ksm == 0):
+            continue          # auto width only with off / auto; forced widths with off / 2 / 4
+        _lib.set_option("gemm_ksplit", ksm)
     _lib.set_option("gemm_force", force)
     if skm is not None:
         ops.set_streamk(skm)
@@ -57,19 +71,27 @@ for (name, m, n, k, epi, bn), force, skm in ((sh, f, sk) for sh in shapes for f 
     torch.cuda.synchronize()
     iters = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters): run(i)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    use_graph = "--graph" in sys.argv      # launches replayed from a CUDA graph: no host launch-rate floor (~15 us from Python)
+    def timed(fn):
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(iters): fn(i)
+            g.replay(); torch.cuda.synchronize()
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        else:
+            e0.record()
+            for i in range(iters): fn(i)
+            e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    ms = timed(run)
     # cuBLAS yardstick (library GEMM, plain store)
     C = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
     for i in range(3): torch.matmul(A[i % nrot], B[i % nrot].t(), out=C)
-    torch.cuda.synchronize(); e0.record()
-    for i in range(iters): torch.matmul(A[i % nrot], B[i % nrot].t(), out=C)
-    e1.record(); torch.cuda.synchronize()
-    ms_cublas = e0.elapsed_time(e1) / iters
+    torch.cuda.synchronize()
+    ms_cublas = timed(lambda i: torch.matmul(A[i % nrot], B[i % nrot].t(), out=C))
     fl = 2.0 * m * n * k
-    r = dict(name=name, force=force, streamk=skm, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+    r = dict(name=name, force=force, streamk=skm, ksplit=ksm, m=m, n=n, k=k, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
              cublas_ms=round(ms_cublas, 4), cublas_tflops=round(fl / ms_cublas / 1e9, 1))
     print(json.dumps(r), flush=True)
     res.append(r)
