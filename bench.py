@@ -355,7 +355,8 @@ def run_ours(args):
                        "cuda_graph": "off" if args.no_cuda_graph else "inference steps replay one captured graph of the whole path",
                        "prompt_sharing": (f"the {Lc} prompt positions that are identical in all {w.B} samples of a batch are "
                                           f"computed once per batch ({rows_per_step} backbone rows instead of {w.B * w.seq}); "
-                                          "outputs bit-identical to per-sample prompts, which 'per_sample_prompts' times")
+                                          "outputs bit-identical to per-sample prompts, which 'per_sample_prompts' times (GPT-2-medium / PSM: up "
+                                          "to the regrouped fp32 k-sum of the one GEMM that cluster split-K takes)")
                                          if Lc else "off",
                        "l2_policy": f"inputs larger than L2: {weight_gb:.1f} GB of weights streamed per step",
                        "cached_in_eval": "the batch-independent prototype path (source = W_map E + b, K, V^T: 268 GFLOP for "

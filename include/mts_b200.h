@@ -57,7 +57,14 @@ int mts_clear_caches(void);
  *               (tcgen05 cta_group::2, 256x256 tile per two SMs) when the cost model prefers it.
  *   "gemm_force" (0 auto | 1 single-CTA kernel | 2 CTA-pair kernel; default 0): override that cost model (experiments,
  *               tools/bench_gemm.py --force-sweep).
- *   "streamk"   (0 off | 1 auto | 2 force; default 0, env MTS_STREAMK): see mts_gemm_args.sk_workspace.
+ *   "streamk"   (0 off | 1 auto | 2 force | 3 even split-K: tiles x s CTAs, s <= 4; default 0, env MTS_STREAMK): see
+ *               mts_gemm_args.sk_workspace.
+ *   "gemm_ksplit" (-1 auto | 0 off | 2 / 4 forced whenever legal; default -1, env MTS_GEMM_KSPLIT): cluster split-K of the
+ *               single-CTA kernel — clusters of s CTAs share one tile, each runs 1/s of the k loop, the partial column
+ *               parts are exchanged through distributed shared memory and every CTA finishes one part (STORE /
+ *               RESID_ADD / GELU_NEW epilogues, batch 1, bf16 operands).  Auto: pairs on 128-wide tiles when
+ *               tiles x 2 <= SMs and k >= 2048.  Regroups the fp32 k-sum (deterministic, but not the order of the
+ *               unsplit schedule).
  *   "attn_tc"   (0 off | 1 auto | 2 whenever the shape fits; default 1, env MTS_ATTN_TC): the causal-attention forward on
  *               tcgen05 / tensor memory (sequences of at most 256 positions, head dim 64 / 128) instead of the mma.sync
  *               kernels.  "auto" decides from (samples, heads, positions, head dim) only, so that the shared-prefix and
