@@ -25,6 +25,19 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.GemmArgs) == 248      # layout of mts_gemm_args (8-byte aligned)
 
 
+def test_process_wide_options_are_validated():
+    """mts_set_option (include/mts_b200.h): known names with legal values are accepted without a device, anything else is
+    an error with a message — a mistyped switch must not silently run the default schedule."""
+    from medtsllm_b200 import MtsError, _lib
+    for name, value in (("gemm_ksplit", 0), ("gemm_ksplit", 2), ("gemm_ksplit", 4), ("gemm_ksplit", -1), ("streamk", 3),
+                        ("streamk", 0), ("epi_direct", 1), ("gemm_2cta", 1), ("pdl", 1), ("attn_tc", 1)):
+        _lib.set_option(name, value)
+    with pytest.raises(MtsError, match="gemm_ksplit"):
+        _lib.set_option("gemm_ksplit", 3)
+    with pytest.raises(MtsError, match="unknown option"):
+        _lib.set_option("gemm_split_k", 2)
+
+
 def test_no_cpu_fallback():
     from medtsllm_b200 import MtsError, ops
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
