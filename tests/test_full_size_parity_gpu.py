@@ -135,7 +135,7 @@ def test_full_depth_forward_vs_oracle(workload, precision, cuda):
             assert k["llm"] <= 1.5 * rows["hf_bf16_autocast"]["llm"] + 1e-3, rows
 
 
-@pytest.mark.parametrize("workload", ["bidmc_llama2_7b", "psm_gpt2_medium"])
+@pytest.mark.parametrize("workload", ["bidmc_llama2_7b", "psm_gpt2_medium", "ludb_llama2_7b", "ventilator_llama2_7b"])
 def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
     """loss.backward() through the full-depth kernel stack (bf16 path: the reference trains under bf16 autocast,
     tasks/forecasting.py:22) against autograd through the fp32 CPU oracle on the same weights / windows / loss, batch 2.
@@ -144,6 +144,11 @@ def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
     i.e. the kernel path's gradients are as close to exact arithmetic as the reference's own mixed-precision training."""
     from oracle import medtsllm_oracle as O
     w, model, inputs = build(workload, cuda, 2)
+    if w.lora_rank:        # Ventilator + LoRA: non-trivial B (zero at initialisation: dA would vanish on both sides)
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            for p in model.llm.B:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(cuda))
     model.train()
     model.use_train_graph = "0"
     x_dev = inputs["x_enc"].to(cuda)
@@ -157,6 +162,13 @@ def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
     spec = oracle_spec(w, model)
     bb = model._backbone
     adapters0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    lora0 = None
+    if w.lora_rank:        # the LoRA pairs are trained too (peft marks them trainable): their gradients are compared as well
+        lora0 = {"scale": model.llm.scale, "n_targets": len(model.llm.targets),
+                 "A": [p.detach().cpu().clone() for p in model.llm.A], "B": [p.detach().cpu().clone() for p in model.llm.B]}
+        lora_names = {id(p): k for k, p in model.named_parameters()}
+        names_a = [lora_names[id(p)] for p in model.llm.A]
+        names_b = [lora_names[id(p)] for p in model.llm.B]
 
     def oracle_grads(device, autocast):
         sd_cpu = LazyBackboneState(bb, keep=(device == "cpu"))
@@ -169,10 +181,19 @@ def test_full_depth_adapter_gradients_vs_oracle(workload, cuda):
                     return self[key]
             sd = _Dev()
         ad = {k: v.to(device).clone().requires_grad_(True) for k, v in adapters0.items()}
+        lora = None
+        if lora0 is not None:
+            lora = {"scale": lora0["scale"], "n_targets": lora0["n_targets"],
+                    "A": [t.to(device).clone().requires_grad_(True) for t in lora0["A"]],
+                    "B": [t.to(device).clone().requires_grad_(True) for t in lora0["B"]]}
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            o = O.medtsllm_forward(inputs["x_enc"].to(device), ids, ad, sd, spec, training=True)
+            o = O.medtsllm_forward(inputs["x_enc"].to(device), ids, ad, sd, spec, training=True, lora=lora)
         (o.float() * wgt.to(device)).sum().backward()
-        return {k: v.grad.detach().float().cpu() for k, v in ad.items()}
+        grads = {k: v.grad.detach().float().cpu() for k, v in ad.items() if v.grad is not None}
+        if lora is not None:
+            grads.update({n: t.grad.detach().float().cpu() for n, t in zip(names_a, lora["A"])})
+            grads.update({n: t.grad.detach().float().cpu() for n, t in zip(names_b, lora["B"])})
+        return grads
 
     ref = oracle_grads("cpu", False)
     del model
