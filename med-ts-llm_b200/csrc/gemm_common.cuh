@@ -98,7 +98,7 @@ __device__ __forceinline__ void tile_coords(int t, int m_blocks, int n_blocks, i
 // which only set 0 owns), i.e. p.direct and a column count that is a multiple of 32.  Warp-uniform, launch-uniform.
 template <int EPI>
 __device__ __forceinline__ int epilogue_parts(const GemmParams& p) {
-  if constexpr (EPI == MTS_EPI_ROPE_QK) return 1;
+  if constexpr (EPI == MTS_EPI_ROPE_QK) return (p.direct && !p.d_is_f32 && (p.n % 32) == 0) ? 2 : 1;
   const int n_store = (EPI == MTS_EPI_SWIGLU) ? p.n / 2 : p.n;
   return (p.direct && !p.d_transposed && (n_store % 32) == 0) ? 2 : 1;
 }
@@ -145,10 +145,66 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
         const float* sr = p.rope_sin + (int64_t)pos * (p.rope_hd / 2);
         __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)b * p.d_batch_stride;
         const int rr = lane >> 2, cc = (lane & 3) * 8;
+        // one 32-column chunk of rotated values -> D
+        auto store_chunk = [&](const float (&v)[32], int col0) {
+          if (!p.d_is_f32 && p.direct && col0 + 32 <= p.n) {
+            // direct path (as in the generic epilogue below): the lane's 32 bf16 columns are 64 contiguous bytes
+            if (row < p.m) {
+              __nv_bfloat16* dptr = dbase + (int64_t)row * p.ldd + col0;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[16 * q + 2 * e], v[16 * q + 2 * e + 1]);
+                st_global_v8(dptr + 16 * q, w);
+              }
+            }
+            return;
+          }
+          __syncwarp();
+          if (p.d_is_f32) {
+            // fp32 output (evaluation parity modes; q / k / v feed the fp32 attention unrounded unless asked):
+            // 8 lanes x float4 per row, 4 rows per pass
+            const bool rnd = p.round_tf32 != 0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
+                  rnd ? make_float4(round_tf32(v[j]), round_tf32(v[j + 1]), round_tf32(v[j + 2]), round_tf32(v[j + 3]))
+                      : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            float* fbase = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride;
+            const int rr4 = lane >> 3, cc4 = (lane & 7) * 4;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int r_g = row0 + ps * 4 + rr4;
+              if (col0 + cc4 < p.n && r_g < p.m)
+                *reinterpret_cast<float4*>(fbase + (int64_t)r_g * p.ldd + col0 + cc4) =
+                    *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr4) * kEpiPitch + cc4);
+            }
+            return;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int r_g = row0 + ps * 8 + rr;
+            if (col0 + cc < p.n && r_g < p.m) {
+              const float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
+              const float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
+              *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd + col0 + cc) =
+                  make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
+                             pack_bf16(a1.z, a1.w));
+            }
+          }
+        };
+        int pair_idx = 0;                                              // (x1, x2) chunk pairs are dealt out to the warp sets
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 32; c0 += 2 * half_chunks) {        // one head (hd columns) per iteration
 #pragma unroll 1
-          for (int h = 0; h < half_chunks; ++h) {
+          for (int h = 0; h < half_chunks; ++h, ++pair_idx) {
+            if ((pair_idx % parts) != part) continue;                   // warp-uniform
             const int ca = c0 + h, cb = ca + half_chunks;
             uint32_t xa[32], xb[32];
             __syncwarp();
@@ -179,48 +235,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int b, int ro
                 vb[j] = __uint_as_float(xb[j]) * p.alpha;
               }
             }
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              const float* v = half ? vb : va;
-              const int col0 = half ? col_b : col_a;
-              __syncwarp();
-              if (p.d_is_f32) {
-                // fp32 output (evaluation parity modes; q / k / v feed the fp32 attention unrounded unless asked):
-                // 8 lanes x float4 per row, 4 rows per pass
-                const bool rnd = p.round_tf32 != 0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) =
-                      rnd ? make_float4(round_tf32(v[j]), round_tf32(v[j + 1]), round_tf32(v[j + 2]), round_tf32(v[j + 3]))
-                          : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                __syncwarp();
-                float* fbase = reinterpret_cast<float*>(p.d) + (int64_t)b * p.d_batch_stride;
-                const int rr4 = lane >> 3, cc4 = (lane & 7) * 4;
-#pragma unroll
-                for (int ps = 0; ps < 8; ++ps) {
-                  const int r_g = row0 + ps * 4 + rr4;
-                  if (col0 + cc4 < p.n && r_g < p.m)
-                    *reinterpret_cast<float4*>(fbase + (int64_t)r_g * p.ldd + col0 + cc4) =
-                        *reinterpret_cast<const float4*>(stage_buf + (ps * 4 + rr4) * kEpiPitch + cc4);
-                }
-                continue;
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(stage_buf + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              __syncwarp();
-#pragma unroll
-              for (int ps = 0; ps < 4; ++ps) {
-                const int r_g = row0 + ps * 8 + rr;
-                if (col0 + cc < p.n && r_g < p.m) {
-                  const float4 a0 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc);
-                  const float4 a1 = *reinterpret_cast<const float4*>(stage_buf + (ps * 8 + rr) * kEpiPitch + cc + 4);
-                  *reinterpret_cast<uint4*>(dbase + (int64_t)r_g * p.ldd + col0 + cc) =
-                      make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y),
-                                 pack_bf16(a1.z, a1.w));
-                }
-              }
-            }
+            store_chunk(va, col_a);
+            store_chunk(vb, col_b);
           }
         }
         return;
